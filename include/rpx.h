@@ -1,0 +1,362 @@
+/*
+ * rpx.h -- C ABI of librpx, the B200-native (sm_100a) replacement for the
+ * non-sequential ray-tracing core of raypier (raypier/core).
+ *
+ * Drop-in boundary: librpx replaces what
+ *     raypier.core.tracer.trace_rays            (raypier/core/tracer.py:9-47)
+ * does between "scene and source rays are known" and "every generation of
+ * rays is known":  ctracer.trace_segment_c (raypier/core/ctracer.pyx:2062-2118),
+ * ctracer.trace_gausslet_c + trace_parabasal_rays (ctracer.pyx:2214-2281,
+ * 2350-2385), FaceList.intersect_c / compute_orientation_c (ctracer.pyx:1882-1953),
+ * every cfaces.*.intersect_c / compute_normal_c (raypier/core/cfaces.pyx) and
+ * every cmaterials.*.eval_child_ray_c / eval_parabasal_ray_c
+ * (raypier/core/cmaterials.pyx).
+ *
+ * The reference has no FFI for this path (it is Cython calling Cython); the
+ * entry points below are what a `ctypes`/`cffi` binding inside
+ * raypier/core/tracer.py would bind (see INTEGRATION.md for that stub).
+ *
+ * Conventions
+ *   - plain C: pointers + sizes, no C++/torch types, no exceptions cross the ABI
+ *   - every function returns RPX_OK (0) or a negative rpx_status; the message
+ *     is available from rpx_last_error()
+ *   - the caller owns every buffer it passes in; the library owns device
+ *     buffers and rpx_result/rpx_rays handles until the matching *_free
+ *   - ray records cross the ABI in the reference's own packed AoS layouts
+ *     (ray_t 188 B, gausslet_t 668 B, raypier/core/ctracer.pxd:40-64)
+ *   - there is NO CPU fallback: without a CUDA device rpx_init fails
+ */
+#ifndef RPX_H_
+#define RPX_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define RPX_ABI_VERSION 1
+
+/* ------------------------------------------------------------------ status */
+typedef enum rpx_status {
+    RPX_OK = 0,
+    RPX_ERR_INVALID = -1,     /* bad argument / malformed scene               */
+    RPX_ERR_UNSUPPORTED = -2, /* face / material type not implemented         */
+    RPX_ERR_CUDA = -3,        /* CUDA runtime error                           */
+    RPX_ERR_NOMEM = -4,       /* device or host allocation failed             */
+    RPX_ERR_NODEVICE = -5,    /* no CUDA device: there is no CPU fallback     */
+    RPX_ERR_STATE = -6        /* call order (e.g. trace before scene_set)     */
+} rpx_status;
+
+/* --------------------------------------------------------- ray record AoS */
+/* Bit-compatible with ray_t / para_t / gausslet_t (ctracer.pxd:40-64) and the
+ * numpy ray_dtype / gausslet_dtype (ctracer.pyx:45-76).                      */
+#pragma pack(push, 1)
+typedef struct rpx_ray {
+    double origin[3], direction[3], normal[3], E_vector[3];
+    double refractive_index[2], E1_amp[2], E2_amp[2]; /* complex128 (re, im)  */
+    double length, phase, accumulated_path;
+    uint32_t wavelength_idx, parent_idx, end_face_idx, ray_ident, ray_type_id;
+} rpx_ray; /* 188 bytes */
+
+typedef struct rpx_para {
+    double origin[3], direction[3], normal[3];
+    double length;
+} rpx_para; /* 80 bytes */
+
+typedef struct rpx_gausslet {
+    rpx_ray base_ray;
+    rpx_para para[6];
+} rpx_gausslet; /* 668 bytes */
+#pragma pack(pop)
+
+#define RPX_RAY_BYTES 188u
+#define RPX_GAUSSLET_BYTES 668u
+#define RPX_NPARA 6
+
+/* ray_type_id bit flags (ctracer.pxd:35-37) */
+#define RPX_REFL_RAY 1u
+#define RPX_GAUSSLET 2u
+#define RPX_PARABASAL 4u
+/* end_face_idx of an unterminated ray: (unsigned)-1 (ctracer.pyx:2087) */
+#define RPX_NO_FACE 0xFFFFFFFFu
+
+/* ------------------------------------------------------------- face types */
+/* One enum value per concrete cfaces.pyx class; p[] holds its parameters.   */
+typedef enum rpx_face_type {
+    RPX_FACE_CIRCULAR = 1,         /* cfaces.pyx:140  p: diameter, offset, z_plane, invert_normals */
+    RPX_FACE_SHAPED_PLANAR = 2,    /* :194  p: z_height ; shape                                     */
+    RPX_FACE_IMPLICIT_PLANAR = 3,  /* :251  p: origin[3], normal[3] ; aux = implicit program        */
+    RPX_FACE_ELLIPTICAL_PLANE = 4, /* :313  p: g_x, g_y, diameter                                   */
+    RPX_FACE_RECTANGULAR = 5,      /* :354  p: length, width, offset, z_plane                       */
+    RPX_FACE_SPHERICAL = 6,        /* :410  p: diameter, curvature, z_height                        */
+    RPX_FACE_SHAPED_SPHERICAL = 7, /* :501  p: curvature, z_height ; shape                          */
+    RPX_FACE_EXTRUDED_PLANAR = 8,  /* :611  p: x1, y1, x2, y2, z1, z2, normal[3]                    */
+    RPX_FACE_POLYGON = 9,          /* :1077 p: z_plane ; aux = xy points (pool)                     */
+    RPX_FACE_ORIENTED_POLYGON = 10,/* :1121 p: origin[3], normal[3], x_axis[3], y_axis[3]; aux pts  */
+    RPX_FACE_OFFAXIS_PARABOLIC = 11,/* :1224 p: EFL, diameter, height                               */
+    RPX_FACE_ELLIPSOIDAL = 12,     /* :1320 p: major, minor, x1,x2,y1,y2,z1,z2; aux = 2 transforms  */
+    RPX_FACE_SADDLE = 13,          /* :1429 p: z_height, curvature ; shape                          */
+    RPX_FACE_CYLINDRICAL = 14,     /* :1516 p: z_height, radius ; shape                             */
+    RPX_FACE_AXICON = 15,          /* :1607 p: z_height, gradient ; shape                           */
+    RPX_FACE_CONIC = 16,           /* :1751 p: curvature, z_height, conic_const, invert_normals; shape */
+    RPX_FACE_ASPHERIC = 17,        /* :1885 p: curvature, z_height, conic_const, invert_normals,
+                                              A4,A6,A8,A10,A12,A14,A16, atol ; shape                */
+    RPX_FACE_EXT_POLY = 18,        /* :2130 p: R(=-curvature), beta(=1+k), norm_radius, z_height,
+                                              atol, invert_normals ; aux = coefs[Nx][Ny] (pool)     */
+    RPX_FACE_DISTORTION = 19       /* :2323 p: accuracy ; base_face, aux = distortion idx ; shape   */
+} rpx_face_type;
+
+#define RPX_FACE_NPARAM 16
+
+typedef struct rpx_face {
+    int32_t type;          /* rpx_face_type                                              */
+    int32_t face_set;      /* index into scene.face_sets (the owning FaceList)           */
+    int32_t material;      /* index into scene.materials                                 */
+    int32_t invert_normal; /* Face.invert_normal (ctracer.pyx:1948)                      */
+    int32_t shape_off;     /* first op of this face's shape program, -1 = none           */
+    int32_t shape_len;     /* number of ops                                              */
+    int32_t aux_off;       /* type-specific: offset into pool / implicit ops / distortions */
+    int32_t aux_n;         /* type-specific count (points, Nx, ops ...)                  */
+    int32_t aux_m;         /* type-specific second count (Ny)                            */
+    int32_t base_face;     /* DISTORTION: index into scene.faces of the wrapped face     */
+    double tolerance;      /* Face.tolerance (default 1e-4, ctracer.pyx:1736)            */
+    double p[RPX_FACE_NPARAM];
+} rpx_face;
+
+/* --------------------------------------------------- 2-D aperture shapes */
+/* cshapes.pyx trees flattened to a postfix (RPN) program evaluated on a bit
+ * stack.  Leaves push, NOT pops 1 / pushes 1, AND/OR/XOR pop 2 / push 1.    */
+typedef enum rpx_shape_op_type {
+    RPX_SHAPE_TRUE = 0,    /* base Shape: always inside (ctracer.pyx:1659)  */
+    RPX_SHAPE_CIRCLE = 1,  /* cshapes.pyx:102  p: cx, cy, radius             */
+    RPX_SHAPE_RECT = 2,    /* :119  p: cx, cy, width, height                 */
+    RPX_SHAPE_POLYGON = 3, /* :139  aux_off/aux_n -> xy points in pool       */
+    RPX_SHAPE_NOT = 4,     /* :34 */
+    RPX_SHAPE_AND = 5,     /* :56 */
+    RPX_SHAPE_OR = 6,      /* :60 */
+    RPX_SHAPE_XOR = 7      /* :64 */
+} rpx_shape_op_type;
+
+typedef struct rpx_shape_op {
+    int32_t type;
+    int32_t aux_off, aux_n;
+    int32_t pad_;
+    double p[4];
+} rpx_shape_op;
+
+/* ---------------------------------------------------- implicit surfaces */
+/* cimplicit_surfs.pyx trees as an RPN program on a double stack.           */
+typedef enum rpx_implicit_op_type {
+    RPX_IMPL_NULL = 0,     /* :23  pushes -1.0                               */
+    RPX_IMPL_PLANE = 1,    /* :27  p: origin[3], normal[3] (normalised)      */
+    RPX_IMPL_SPHERE = 2,   /* :60  p: centre[3], radius                      */
+    RPX_IMPL_CYLINDER = 3, /* :83  p: origin[3], axis[3] (normalised), radius */
+    RPX_IMPL_NEG = 4,      /* Invert :122                                    */
+    RPX_IMPL_MIN = 5,      /* Union.apply_op :173                            */
+    RPX_IMPL_MAX = 6,      /* Intersection.apply_op :181                     */
+    RPX_IMPL_SUB = 7       /* Difference.apply_op :189                       */
+} rpx_implicit_op_type;
+
+typedef struct rpx_implicit_op {
+    int32_t type;
+    int32_t pad_;
+    double p[7];
+} rpx_implicit_op;
+
+/* ------------------------------------------------------------ distortions */
+typedef enum rpx_distortion_type {
+    RPX_DIST_ZERNIKE_J7 = 1, /* SimpleTestZernikeJ7 cdistortions.pyx:39  p: unit_radius, amplitude */
+    RPX_DIST_ZERNIKE = 2     /* ZernikeDistortion   cdistortions.pyx:323 p: unit_radius            */
+} rpx_distortion_type;
+
+/* The reference evaluates Zernike radial polynomials by memoised recursion
+ * (cdistortions.pyx:149-316).  Which memo slot is filled when depends only on
+ * the coefficient set, never on the ray, so the host unrolls the recursion
+ * ONCE into a straight-line "tape" (exactly the reference's evaluation order,
+ * including its slot-aliasing quirks) and the device just runs the tape.
+ * Operand encoding: 0 -> constant 0.0, 1 -> constant 1.0,
+ *                   2 + 3*slot + w -> workspace[w][slot], w in {0:R, 1:R', 2:R/r} */
+typedef struct rpx_ztape_op {
+    int32_t kind;  /* 0: R      ws0[dst] = r*(a + b) - c
+                      1: R'     ws1[dst] = (a + b) + r*(d + e) - c
+                      2: R/r    ws2[dst] = (a + b) - c                      */
+    int32_t dst;   /* slot k                                                 */
+    int32_t a, b, c, d, e; /* operands (see encoding above)                  */
+    int32_t pad_;
+} rpx_ztape_op;
+
+typedef struct rpx_zcoef {
+    int32_t j, n, m, k;   /* ANSI index and (n, m, k) (cdistortions.pyx:104-136) */
+    double value;
+    int32_t opR, opRp, opRr; /* operands holding R, R', R/r after the tape ran
+                                (gradient tape); opR_z: R after the z-only tape */
+    int32_t opR_z;
+} rpx_zcoef;
+
+typedef struct rpx_distortion {
+    int32_t type;
+    int32_t n_coefs, coef_off;       /* into scene.zcoefs                    */
+    int32_t tape_z_off, tape_z_len;  /* tape for z_offset_c (R only)         */
+    int32_t tape_g_off, tape_g_len;  /* tape for z_offset_and_gradient_c     */
+    int32_t k_max;                   /* workspace slots                      */
+    double p[4];
+} rpx_distortion;
+
+#define RPX_ZERNIKE_MAX_K 64 /* device workspace bound: n_max <= 12 */
+
+/* --------------------------------------------------------------- materials */
+typedef enum rpx_material_type {
+    RPX_MAT_OPAQUE = 1,               /* cmaterials.pyx:242                                   */
+    RPX_MAT_TRANSPARENT = 2,          /* :254                                                 */
+    RPX_MAT_PEC = 3,                  /* :281                                                 */
+    RPX_MAT_PARTIALLY_REFLECTIVE = 4, /* :322  p: reflectivity                                */
+    RPX_MAT_LINEAR_POLARISING = 5,    /* :400                                                 */
+    RPX_MAT_WAVEPLATE = 6,            /* :458  p: retardance_re, retardance_im, fast_axis[3]  */
+    RPX_MAT_DIELECTRIC = 7,           /* :554  n tables                                       */
+    RPX_MAT_FULL_DIELECTRIC = 8,      /* :727 and :875 (dispersive)  p: refl_thr, trans_thr   */
+    RPX_MAT_COATED = 9,               /* :1017 and :1187 (dispersive) p: refl_thr, trans_thr, thickness */
+    RPX_MAT_GRATING = 10,             /* :1437 p: lines_per_mm, order, efficiency, origin[3]  */
+    RPX_MAT_CIRC_APERTURE = 11,       /* :1602 p: outer_radius, radius, edge_width, invert, origin[3] */
+    RPX_MAT_RECT_APERTURE = 12        /* :1677 p: outer_width, outer_height, width, height, edge_width, invert, origin[3] */
+} rpx_material_type;
+
+/* rpx_material.para_model: which eval_parabasal_ray_c the reference class has */
+#define RPX_PARA_DEFAULT 0   /* InterfaceMaterial default, ctracer.pyx:1588-1610   */
+#define RPX_PARA_SNELL 1     /* DielectricMaterial :683 / CoatedDispersive :1393   */
+#define RPX_PARA_GRATING 2   /* DiffractionGratingMaterial :1544                   */
+
+#define RPX_MAT_NPARAM 12
+
+typedef struct rpx_material {
+    int32_t type;
+    int32_t para_model;
+    int32_t ntab_off; /* offset (in complex elements) into scene.ntab of this material's
+                         [3][n_wavelengths] table: row 0 n_inside, 1 n_outside, 2 n_coating;
+                         non-dispersive materials carry their constant n replicated, so the
+                         device has one code path (on_set_wavelengths, cmaterials.pyx:883,1220) */
+    int32_t pad_;
+    double p[RPX_MAT_NPARAM];
+} rpx_material;
+
+/* ------------------------------------------------------------- transforms */
+typedef struct rpx_transform {
+    double m[9]; /* row-major m00..m22 (transform_t, ctracer.pxd:67-69) */
+    double t[3];
+} rpx_transform;
+
+typedef struct rpx_face_set {
+    rpx_transform trans;     /* FaceList.trans      */
+    rpx_transform inv_trans; /* FaceList.inv_trans  */
+    int32_t face_begin, face_end; /* [begin, end) into the traced face list */
+} rpx_face_set;
+
+/* ------------------------------------------------------------------ scene */
+typedef struct rpx_scene {
+    int32_t abi_version;       /* RPX_ABI_VERSION */
+    int32_t n_traced_faces;    /* len(all_faces): faces[0..n) are traced, idx == position;
+                                  faces[n..n_faces) are only referenced as DistortionFace bases */
+    int32_t n_faces;
+    int32_t n_face_sets;
+    int32_t n_materials;
+    int32_t n_shape_ops;
+    int32_t n_implicit_ops;
+    int32_t n_distortions;
+    int32_t n_zcoefs;
+    int32_t n_ztape;
+    int32_t n_wavelengths;
+    int32_t n_ntab;            /* complex elements in ntab */
+    int32_t n_pool;            /* doubles in pool          */
+    int32_t pad_;
+    const rpx_face* faces;
+    const rpx_face_set* face_sets;
+    const rpx_material* materials;
+    const rpx_shape_op* shape_ops;
+    const rpx_implicit_op* implicit_ops;
+    const rpx_distortion* distortions;
+    const rpx_zcoef* zcoefs;
+    const rpx_ztape_op* ztape;
+    const double* wavelengths; /* microns, RayCollection.wavelengths */
+    const double* ntab;        /* interleaved (re, im) */
+    const double* pool;        /* polygon points, ext-poly coefs, ellipsoid transforms */
+} rpx_scene;
+
+/* ------------------------------------------------------------ the library */
+typedef struct rpx_ctx rpx_ctx;       /* one per process per GPU              */
+typedef struct rpx_rays rpx_rays;     /* a device-resident SoA ray generation */
+typedef struct rpx_result rpx_result; /* all generations of one trace         */
+
+/* rpx_trace flags */
+#define RPX_TRACE_DEFAULT 0u
+#define RPX_TRACE_KEEP_LAST_ONLY 1u /* streaming mode: keep counts + face counts, free
+                                       generation g-1 once g is built (N too big to keep) */
+
+/* Replaces: module import of raypier.core.ctracer (no device state exists there). */
+int rpx_init(int device, rpx_ctx** out_ctx);
+void rpx_shutdown(rpx_ctx* ctx);
+/* Last error text for this context (or for a failed rpx_init when ctx==NULL). */
+const char* rpx_last_error(const rpx_ctx* ctx);
+int rpx_abi_version(void);
+
+/* Replaces the per-trace set-up loop of trace_rays (core/tracer.py:28-37):
+ * f.idx = i, f.update(), f.material.wavelengths = wavelengths,
+ * fs.sync_transforms() (ctracer.pyx:1820-1837) -- the host flattens the objects
+ * into rpx_scene after doing those calls; this uploads the tables.            */
+int rpx_scene_set(rpx_ctx* ctx, const rpx_scene* scene);
+
+/* Pinned host memory for ray records (replaces malloc in RayCollection.__cinit__,
+ * ctracer.pyx:983-987, when the caller wants full-speed DMA).                 */
+void* rpx_host_alloc(size_t bytes);
+void rpx_host_free(void* p);
+
+/* Replaces RayCollection.from_array / GaussletCollection.from_array
+ * (ctracer.pyx:1142-1154, 1304-1319): copies n packed AoS records to the device
+ * and transposes them into the SoA generation buffer.                         */
+int rpx_rays_upload(rpx_ctx* ctx, const void* aos, uint64_t n, int is_gausslet,
+                    rpx_rays** out_rays);
+/* Replaces copy_as_array (ctracer.pyx:1048-1054, 1286-1292).                  */
+int rpx_rays_download(rpx_ctx* ctx, const rpx_rays* rays, void* out_aos, uint64_t capacity);
+uint64_t rpx_rays_count(const rpx_rays* rays);
+void rpx_rays_free(rpx_ctx* ctx, rpx_rays* rays);
+
+/* Replaces the generation loop of trace_rays (core/tracer.py:22,39-45) over
+ * trace_segment_c / trace_gausslet_c, inputs already resident on the device.
+ * `rays` becomes generation 0 of the result (it is mutated like the reference
+ * mutates its parent collection: length, end_face_idx) and is owned by the
+ * result afterwards.  max_length is rounded to float for plain rays exactly as
+ * trace_segment_c's `float max_length` argument does (ctracer.pyx:2066).      */
+int rpx_trace_device(rpx_ctx* ctx, rpx_rays* rays, double max_length, int recursion_limit,
+                     uint32_t flags, rpx_result** out_result);
+
+/* Convenience = rpx_rays_upload + rpx_trace_device (host buffers in).         */
+int rpx_trace(rpx_ctx* ctx, const void* rays_aos, uint64_t n, int is_gausslet,
+              double max_length, int recursion_limit, uint32_t flags,
+              rpx_result** out_result);
+
+/* len(traced_rays) */
+int rpx_result_n_generations(const rpx_result* res);
+/* [len(traced_rays[g]) for g]; counts has room for n_generations entries */
+int rpx_result_counts(const rpx_result* res, uint64_t* counts);
+/* traced_rays[g].copy_as_array() into out_aos (capacity in records) */
+int rpx_result_generation(rpx_ctx* ctx, const rpx_result* res, int g, void* out_aos,
+                          uint64_t capacity);
+/* Face.count for every traced face (ctracer.pyx:2108), n_traced_faces entries */
+int rpx_result_face_counts(const rpx_result* res, uint32_t* counts);
+/* Device time of the generation loop (CUDA events on the tracing stream), ms */
+double rpx_result_device_ms(const rpx_result* res);
+/* Kernels launched by this trace (for bench.py's gpu_launches claim) */
+uint64_t rpx_result_launches(const rpx_result* res);
+/* Average device time (ms) and launch count per kernel family over this trace:
+ * which = 0 intersect, 1 shade (orientation + material + ordered emit)       */
+int rpx_result_kernel_ms(const rpx_result* res, int which, double* total_ms, uint64_t* launches);
+void rpx_result_free(rpx_ctx* ctx, rpx_result* res);
+
+/* Raw CUDA stream the context launches on (so a caller can bracket the trace
+ * with its own events); returned as void* to keep CUDA types out of the ABI. */
+void* rpx_stream(rpx_ctx* ctx);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RPX_H_ */

@@ -1,0 +1,264 @@
+"""TEST INFRASTRUCTURE ONLY -- ctypes wrapper around oracle/librpx_oracle.so
+(the plain-C CPU restatement of the reference trace, oracle/rpx_oracle.c).
+
+Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference
+legs may import this module.  The product package never does.
+"""
+import ctypes as C
+import os
+import subprocess
+import sys
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_ROOT = os.path.dirname(_HERE)
+if _ROOT not in sys.path:
+    sys.path.insert(0, _ROOT)
+
+from raypier_optics_b200 import _abi as A  # layout only (dtypes / rpx_scene struct)
+
+_LIB = None
+
+
+def build():
+    subprocess.check_call(["make", "-C", _HERE, "librpx_oracle.so"], stdout=subprocess.DEVNULL)
+
+
+def lib():
+    global _LIB
+    if _LIB is None:
+        path = os.path.join(_HERE, "librpx_oracle.so")
+        if not os.path.exists(path):
+            build()
+        L = C.CDLL(path)
+        vp, d, i, u32, u64 = C.c_void_p, C.c_double, C.c_int, C.c_uint32, C.c_uint64
+        L.rpxo_trace_segment.restype = u64
+        L.rpxo_trace_segment.argtypes = [vp, vp, u64, d, vp, vp]
+        L.rpxo_trace_gausslet.restype = u64
+        L.rpxo_trace_gausslet.argtypes = [vp, vp, u64, d, vp, vp]
+        L.rpxo_face_intersect.restype = d
+        L.rpxo_face_intersect.argtypes = [vp, i, vp, vp, i]
+        L.rpxo_face_normal.argtypes = [vp, i, vp, vp]
+        L.rpxo_orientation.argtypes = [vp, i, vp, vp, vp]
+        L.rpxo_convert_to_sp.argtypes = [vp, vp, vp]
+        L.rpxo_material_eval.restype = i
+        L.rpxo_material_eval.argtypes = [vp, i, vp, u32, vp, vp, vp, vp]
+        L.rpxo_material_eval_para.argtypes = [vp, i, vp, vp, vp, vp, vp, u32, vp]
+        L.rpxo_distortion_z.restype = d
+        L.rpxo_distortion_z.argtypes = [vp, i, d, d]
+        L.rpxo_distortion_zgrad.argtypes = [vp, i, d, d, vp]
+        L.rpxo_shape_inside.restype = i
+        L.rpxo_shape_inside.argtypes = [vp, i, d, d]
+        L.rpxo_implicit_eval.restype = d
+        L.rpxo_implicit_eval.argtypes = [vp, i, i, vp]
+        for name in ("rpxo_zernike_R", "rpxo_zernike_Rprime", "rpxo_zernike_R_over_r"):
+            f = getattr(L, name)
+            f.restype = d
+            f.argtypes = [d, i, i, i, vp, i]
+        assert L.rpxo_sizeof_ray() == 188 and L.rpxo_sizeof_gausslet() == 668
+        _LIB = L
+    return _LIB
+
+
+def _v3(v):
+    return np.ascontiguousarray(v, dtype=np.double).reshape(3)
+
+
+def trace_generation(scene, rays, max_length, face_counts=None):
+    """One generation (trace_segment_c / trace_gausslet_c).  ``rays`` (ray_dtype or
+    gausslet_dtype array) is mutated in place like the reference mutates the parent
+    collection; returns the child array."""
+    L = lib()
+    rays_c = rays
+    assert rays_c.flags.c_contiguous
+    n = rays_c.shape[0]
+    out = np.zeros(max(2 * n, 1), dtype=rays_c.dtype)
+    fc = face_counts.ctypes.data if face_counts is not None else None
+    if rays_c.dtype == A.ray_dtype:
+        n_out = L.rpxo_trace_segment(scene.byref_ptr(), rays_c.ctypes.data, n, float(max_length),
+                                     out.ctypes.data, fc)
+    elif rays_c.dtype == A.gausslet_dtype:
+        n_out = L.rpxo_trace_gausslet(scene.byref_ptr(), rays_c.ctypes.data, n, float(max_length),
+                                      out.ctypes.data, fc)
+    else:
+        raise TypeError("rays must be ray_dtype or gausslet_dtype")
+    return out[:n_out].copy()
+
+
+class OracleScene:
+    """Adapter giving the oracle a stable pointer to a flattened Scene."""
+
+    def __init__(self, scene):
+        self.scene = scene
+
+    def byref_ptr(self):
+        return C.cast(C.pointer(self.scene.c_scene), C.c_void_p)
+
+
+def trace_rays(scene, input_rays, recursion_limit=100, max_length=100.0):
+    """The generation loop of raypier.core.tracer.trace_rays (core/tracer.py:9-47) on
+    numpy arrays.  Returns (list of generation arrays, face_counts)."""
+    osc = scene if isinstance(scene, OracleScene) else OracleScene(scene)
+    rays = np.ascontiguousarray(input_rays).copy()
+    is_g = rays.dtype == A.gausslet_dtype
+    # input_rays.reset_length(max_length), core/tracer.py:22
+    if is_g:
+        rays['base_ray']['length'] = max_length
+        rays['para_rays']['length'] = max_length
+    else:
+        rays['length'] = max_length
+    counts = np.zeros(max(scene.c_scene.n_traced_faces, 1), dtype=np.uint32)
+    traced = []
+    count = 0
+    while rays.shape[0] > 0 and count < recursion_limit:
+        traced.append(rays)
+        rays = trace_generation(osc, rays, max_length, counts)
+        count += 1
+    return traced, counts[:scene.c_scene.n_traced_faces]
+
+
+# ---- unit entry points (for pinning against the reference's own KATs) -------
+def face_intersect(scene, face_idx, p1, p2, is_base_ray=1):
+    osc = OracleScene(scene)
+    return lib().rpxo_face_intersect(osc.byref_ptr(), face_idx, _v3(p1).ctypes.data,
+                                     _v3(p2).ctypes.data, int(is_base_ray))
+
+
+def face_normal(scene, face_idx, p):
+    osc = OracleScene(scene)
+    out = np.zeros(3)
+    lib().rpxo_face_normal(osc.byref_ptr(), face_idx, _v3(p).ctypes.data, out.ctypes.data)
+    return out
+
+
+def orientation(scene, face_idx, point):
+    osc = OracleScene(scene)
+    n, t = np.zeros(3), np.zeros(3)
+    lib().rpxo_orientation(osc.byref_ptr(), face_idx, _v3(point).ctypes.data, n.ctypes.data,
+                           t.ctypes.data)
+    return n, t
+
+
+def convert_to_sp(ray, normal):
+    r = np.ascontiguousarray(ray, dtype=A.ray_dtype).reshape(1).copy()
+    out = np.zeros(1, dtype=A.ray_dtype)
+    lib().rpxo_convert_to_sp(r.ctypes.data, _v3(normal).ctypes.data, out.ctypes.data)
+    return out[0]
+
+
+def material_eval(scene, mat_idx, ray, idx, point, normal, tangent=(1.0, 0.0, 0.0)):
+    osc = OracleScene(scene)
+    r = np.ascontiguousarray(ray, dtype=A.ray_dtype).reshape(1).copy()
+    out = np.zeros(2, dtype=A.ray_dtype)
+    n = lib().rpxo_material_eval(osc.byref_ptr(), mat_idx, r.ctypes.data, int(idx),
+                                 _v3(point).ctypes.data, _v3(normal).ctypes.data,
+                                 _v3(tangent).ctypes.data, out.ctypes.data)
+    return out[:n].copy()
+
+
+def material_eval_para(scene, mat_idx, base_ray, direction, point, normal, tangent=(1.0, 0.0, 0.0),
+                       ray_type_id=0):
+    osc = OracleScene(scene)
+    r = np.ascontiguousarray(base_ray, dtype=A.ray_dtype).reshape(1).copy()
+    out = np.zeros(1, dtype=A.para_dtype)
+    lib().rpxo_material_eval_para(osc.byref_ptr(), mat_idx, r.ctypes.data, _v3(direction).ctypes.data,
+                                  _v3(point).ctypes.data, _v3(normal).ctypes.data,
+                                  _v3(tangent).ctypes.data, int(ray_type_id), out.ctypes.data)
+    return out[0]
+
+
+def distortion_z(scene, dist_idx, x, y):
+    return lib().rpxo_distortion_z(OracleScene(scene).byref_ptr(), dist_idx, float(x), float(y))
+
+
+def distortion_zgrad(scene, dist_idx, x, y):
+    out = np.zeros(3)
+    lib().rpxo_distortion_zgrad(OracleScene(scene).byref_ptr(), dist_idx, float(x), float(y),
+                                out.ctypes.data)
+    return out
+
+
+def shape_inside(scene, face_idx, x, y):
+    return lib().rpxo_shape_inside(OracleScene(scene).byref_ptr(), face_idx, float(x), float(y))
+
+
+def implicit_eval(scene, off, length, p):
+    return lib().rpxo_implicit_eval(OracleScene(scene).byref_ptr(), off, length, _v3(p).ctypes.data)
+
+
+def zernike(which, r, k, n, m, kmax):
+    ws = np.full(3 * kmax, np.nan)
+    f = {"R": lib().rpxo_zernike_R, "Rprime": lib().rpxo_zernike_Rprime,
+         "R_over_r": lib().rpxo_zernike_R_over_r}[which]
+    return f(float(r), int(k), int(n), int(m), ws.ctypes.data, int(kmax))
+
+
+# ---- the real reference, when it was built here (oracle/_ref) ----------------
+def reference_path(flavour="parity"):
+    return os.path.join(_HERE, "_ref", flavour)
+
+
+def import_reference(flavour="parity"):
+    """Import the unmodified reference core from oracle/_ref/<flavour> (built by
+    oracle/build_ref.sh).  Returns the ``raypier.core`` package or None."""
+    path = reference_path(flavour)
+    if not os.path.isdir(os.path.join(path, "raypier", "core")):
+        return None
+    for m in [k for k in sys.modules if k == "raypier" or k.startswith("raypier.")]:
+        # a different flavour may already be loaded; extension modules cannot be reloaded
+        mod = sys.modules[m]
+        f = getattr(mod, "__file__", "") or ""
+        if f and not f.startswith(path):
+            return None
+    if path not in sys.path:
+        sys.path.insert(0, path)
+    try:
+        import importlib
+        core = importlib.import_module("raypier.core")
+        for name in ("ctracer", "cfaces", "cmaterials", "cshapes", "cdistortions", "cimplicit_surfs"):
+            importlib.import_module("raypier.core." + name)
+        return core
+    except Exception:
+        return None
+
+
+def reference_trace_rays(core, input_rays, face_lists, recursion_limit=100, max_length=100.0):
+    """raypier.core.tracer.trace_rays (core/tracer.py:9-47) driven over the REAL reference
+    kernels (ctracer.trace_segment / trace_gausslet from oracle/_ref).  The 40-line Python
+    driver is restated here rather than copied into oracle/_ref."""
+    ct = core.ctracer
+    input_rays.reset_length(max_length)
+    traced_rays = []
+    trace_func = ct.trace_segment if isinstance(input_rays, ct.RayCollection) else ct.trace_gausslet
+    count = 0
+    wavelengths = np.asarray(input_rays.wavelengths)
+    all_faces = [f for fs in face_lists for f in fs.faces]
+    for i, f in enumerate(all_faces):
+        f.idx = i
+        f.count = 0
+        f.update()
+        f.material.wavelengths = wavelengths
+        f.max_length = max_length
+    face_sets = list(face_lists)
+    decomp_faces = [f for f in all_faces if f.material.is_decomp_material()]
+    rays = input_rays
+    while rays.n_rays > 0 and count < recursion_limit:
+        traced_rays.append(rays)
+        rays = trace_func(rays, face_sets, all_faces, max_length=max_length,
+                          decomp_faces=decomp_faces)
+        count += 1
+    return traced_rays, all_faces
+
+
+def reference_collection(core, rays, wavelengths):
+    """numpy ray_dtype / gausslet_dtype array -> reference RayCollection / GaussletCollection."""
+    ct = core.ctracer
+    if rays.dtype == A.gausslet_dtype:
+        rc = ct.GaussletCollection.from_array(np.ascontiguousarray(rays).view(ct.gausslet_dtype))
+    else:
+        a = np.empty(rays.shape[0], dtype=ct.ray_dtype)  # from_array asserts dtype identity
+        a.view(np.uint8)[:] = np.ascontiguousarray(rays).view(np.uint8)
+        rc = ct.RayCollection.from_array(a)
+    rc.wavelengths = np.ascontiguousarray(wavelengths, dtype=np.double)
+    return rc

@@ -1,0 +1,355 @@
+"""Synthetic restatements of the BASELINE.json configs.
+
+Every builder takes ``core`` -- a namespace exposing ``cfaces, cmaterials, ctracer,
+cshapes, cdistortions, cimplicit_surfs`` -- so the *same* model can be assembled
+from this package's host mirrors (``raypier_optics_b200.core``) or from the genuine
+reference (``raypier.core`` built into oracle/_ref), which is how the parity pins
+and the reference arm of bench.py get identical scenes.
+
+Glass coefficients are the Schott Sellmeier (formula 2) rows of the reference's
+sqlite glass database (raypier/material_data/glass_dispersion_database.db), copied
+here as data because that file does not exist on the GPU box.
+"""
+import math
+
+import numpy as np
+
+from ._abi import GAUSSLET, gausslet_dtype, ray_dtype
+
+# name -> (formula_id, wavelength_min, wavelength_max, coefs)
+GLASS = {
+    "N-LAK22": (2, 0.31, 2.5, [0.0, 1.14229781, 0.00585778594, 0.535138441, 0.0198546147,
+                               1.04088385, 100.834017]),
+    "N-SF6": (2, 0.37, 2.5, [0.0, 1.77931763, 0.0133714182, 0.338149866, 0.0617533621,
+                             2.08734474, 174.01759]),
+    "N-BK7": (2, 0.3, 2.5, [0.0, 1.03961212, 0.00600069867, 0.231792344, 0.0200179144,
+                            1.01046945, 103.560653]),
+    "N-SF11": (2, 0.37, 2.5, [0.0, 1.73759695, 0.013188707, 0.313747346, 0.0623068142,
+                              1.89878101, 155.23629]),
+}
+
+
+def glass_curve(core, name, absorption=0.0):
+    """NamedDispersionCurve(name) of raypier/dispersion.py:66-99."""
+    fid, wmin, wmax, coefs = GLASS[name]
+    return core.cmaterials.BaseDispersionCurve(fid, np.array(coefs, dtype=np.double), absorption,
+                                               wmin, wmax)
+
+
+def nondispersive(core, n=1.0, absorption=0.0):
+    """NondispersiveCurve of raypier/dispersion.py:21-40."""
+    return core.cmaterials.BaseDispersionCurve(0, np.array([n], dtype=np.double), absorption, 0.0,
+                                               1000000.0)
+
+
+# ---------------------------------------------------------------------------------
+# Optic pose: what raypier.bases.Traceable builds in a tvtk.Transform
+# (bases.py:195-203: translate(centre) . rotate_z(o) . rotate_x(e) . rotate_z(rotation),
+#  with (o, e) from the direction vector, bases.py:246-252)
+# ---------------------------------------------------------------------------------
+class _Matrix(object):
+    def __init__(self, m):
+        self._m = np.asarray(m, dtype=np.double)
+
+    def get_element(self, i, j):
+        return float(self._m[i, j])
+
+
+class _VtkLikeTransform(object):
+    def __init__(self, m):
+        self.matrix = _Matrix(m)
+        self._m = np.asarray(m, dtype=np.double)
+
+    @property
+    def linear_inverse(self):
+        R = self._m[:3, :3]
+        t = self._m[:3, 3]
+        inv = np.eye(4)
+        inv[:3, :3] = R.T
+        inv[:3, 3] = -(R.T @ t)
+        return _VtkLikeTransform(inv)
+
+
+class Pose(object):
+    """Duck-typed FaceList owner: exposes ``.transform.matrix.get_element(i, j)`` and
+    ``.transform.linear_inverse.matrix`` -- all FaceList.sync_transforms touches
+    (ctracer.pyx:1820-1837).  Extra keyword arguments become attributes (what
+    Face.update() copies from its owner, e.g. diameter / offset)."""
+
+    def __init__(self, centre=(0., 0., 0.), direction=(0., 0., 1.), rotation=0.0, **attrs):
+        x, y, z = np.asarray(direction, dtype=np.double) / np.linalg.norm(direction)
+        theta = 180 * math.acos(z) / math.pi
+        phi = 180 * math.atan2(x, y) / math.pi
+        o, e = -phi, -theta
+
+        def rz(deg):
+            a = math.radians(deg)
+            c, s = math.cos(a), math.sin(a)
+            return np.array([[c, -s, 0, 0], [s, c, 0, 0], [0, 0, 1, 0], [0, 0, 0, 1.0]])
+
+        def rx(deg):
+            a = math.radians(deg)
+            c, s = math.cos(a), math.sin(a)
+            return np.array([[1, 0, 0, 0], [0, c, -s, 0], [0, s, c, 0], [0, 0, 0, 1.0]])
+
+        T = np.eye(4)
+        T[:3, 3] = centre
+        self.transform = _VtkLikeTransform(T @ rz(o) @ rx(e) @ rz(rotation))
+        self.centre = tuple(centre)
+        self.direction = (x, y, z)
+        for k, v in attrs.items():
+            setattr(self, k, v)
+
+
+# ---------------------------------------------------------------------------------
+# Synthetic sources
+# ---------------------------------------------------------------------------------
+def _frame(axis):
+    w = np.asarray(axis, dtype=np.double)
+    w = w / np.linalg.norm(w)
+    a = np.array([1.0, 0.0, 0.0]) if abs(w[0]) < 0.9 else np.array([0.0, 1.0, 0.0])
+    u = np.cross(w, a)
+    u /= np.linalg.norm(u)
+    v = np.cross(w, u)
+    return u, v, w
+
+
+def disc_source(n, centre, axis, radius, seed, n_wavelengths=1, E_vector=None, E1=1.0, E2=0.0,
+                jitter=0.0, ray_type_id=0, gaussian_sigma=None):
+    """Collimated disc of ``n`` rays, uniformly random in area (numpy default_rng(seed)),
+    travelling along ``axis``; the synthetic stand-in for ParallelRaySource
+    (raypier/sources.py:572-608).  Returns a ``ray_dtype`` array."""
+    rng = np.random.default_rng(seed)
+    u, v, w = _frame(axis)
+    r = radius * np.sqrt(rng.random(n))
+    phi = 2 * np.pi * rng.random(n)
+    rays = np.zeros(n, dtype=ray_dtype)
+    rays['origin'] = (np.asarray(centre, dtype=np.double)[None, :] + (r * np.cos(phi))[:, None] * u[None, :]
+                      + (r * np.sin(phi))[:, None] * v[None, :])
+    d = np.repeat(w[None, :], n, axis=0)
+    if jitter:
+        d = d + rng.normal(0.0, jitter, size=(n, 3))
+        d /= np.linalg.norm(d, axis=1)[:, None]
+    rays['direction'] = d
+    rays['E_vector'] = u if E_vector is None else np.asarray(E_vector, dtype=np.double)
+    amp = 1.0
+    if gaussian_sigma is not None:
+        amp = np.exp(-(r * r) / (gaussian_sigma * gaussian_sigma))
+    rays['E1_amp'] = E1 * amp
+    rays['E2_amp'] = E2 * amp
+    rays['refractive_index'] = 1.0
+    rays['normal'] = (0.0, 1.0, 0.0)
+    rays['length'] = np.inf
+    if n_wavelengths > 1:
+        rays['wavelength_idx'] = rng.integers(0, n_wavelengths, size=n, dtype=np.uint32)
+    rays['ray_ident'] = np.arange(n, dtype=np.uint32)
+    rays['ray_type_id'] = ray_type_id
+    return rays
+
+
+# ---------------------------------------------------------------------------------
+# Config builders.  Each returns a dict:
+#   face_lists, rays (ray_dtype | gausslet_dtype array), wavelengths, max_length,
+#   recursion_limit, name
+# ---------------------------------------------------------------------------------
+def _facelist(core, owner, faces):
+    fl = core.ctracer.FaceList(owner=owner)
+    fl.faces = faces
+    fl.sync_transforms()
+    return fl
+
+
+def config1_singlet(core, n=10000, seed=0):
+    """Config 1: PlanoConvexLens (raypier/lenses.py:50-103) = CircularFace +
+    SphericalFace with one SingleLayerCoatedMaterial (coating thickness stays at the
+    0.1 um default, quirk Q9), collimated disc source, one wavelength."""
+    F, M = core.cfaces, core.cmaterials
+    owner = Pose(centre=(0., -20., 0.), direction=(0., 1., 0.), diameter=25.4, offset=0.0)
+    mat = M.SingleLayerCoatedMaterial(n_inside=1.5, n_outside=1.0, n_coating=1.3)
+    f1 = F.CircularFace(owner=owner, diameter=25.4, material=mat)
+    f2 = F.SphericalFace(owner=owner, diameter=25.4, material=mat, z_height=6.0, curvature=20.0)
+    fl = _facelist(core, owner, [f1, f2])
+    rays = disc_source(n, centre=(0., -50., 0.), axis=(0., 1., 0.), radius=10.0, seed=seed,
+                       E_vector=(1., 0., 0.))
+    return dict(name="config1_singlet", face_lists=[fl], rays=rays, wavelengths=np.array([0.78]),
+                max_length=200.0, recursion_limit=200)
+
+
+def config2_achromat(core, n=1000000, seed=0, reflection_threshold=0.1, transmission_threshold=0.1):
+    """Config 2: EdmundOptic45805 achromatic doublet (raypier/achromats.py:244-298,
+    423-435): 3 SphericalFace, 3 CoatedDispersiveMaterial (N-LAK22 / N-SF6 / air,
+    MgF2-like n=1.37 coating 0.283 um on the outer faces), 5 wavelengths, elliptical
+    polarisation."""
+    F, M = core.cfaces, core.cmaterials
+    owner = Pose(centre=(1.0, -2.0, 3.0), direction=(0.2, 1.0, 0.1), diameter=25.4)
+    air = nondispersive(core, 1.0)
+    d1, d2 = glass_curve(core, "N-LAK22"), glass_curve(core, "N-SF6")
+    coat = nondispersive(core, 1.37)
+    kw = dict(reflection_threshold=reflection_threshold,
+              transmission_threshold=transmission_threshold)
+    m1 = M.CoatedDispersiveMaterial(dispersion_inside=d1, dispersion_outside=air,
+                                    dispersion_coating=coat, coating_thickness=0.283, **kw)
+    m2 = M.CoatedDispersiveMaterial(dispersion_inside=d2, dispersion_outside=d1,
+                                    dispersion_coating=coat, coating_thickness=0.0, **kw)
+    m3 = M.CoatedDispersiveMaterial(dispersion_inside=air, dispersion_outside=d2,
+                                    dispersion_coating=coat, coating_thickness=0.283, **kw)
+    faces = [F.SphericalFace(owner=owner, diameter=25.4, material=m1, z_height=6.0, curvature=43.96),
+             F.SphericalFace(owner=owner, diameter=25.4, material=m2, z_height=0.0, curvature=-42.90),
+             F.SphericalFace(owner=owner, diameter=25.4, material=m3, z_height=-4.0,
+                             curvature=-392.21)]
+    fl = _facelist(core, owner, faces)
+    axis = np.array(owner.direction)
+    start = np.array(owner.centre) + 40.0 * axis
+    wl = np.array([0.45, 0.55, 0.65, 0.8, 1.0])
+    rays = disc_source(n, centre=start, axis=-axis, radius=10.0, seed=seed, n_wavelengths=len(wl),
+                       E1=1.0, E2=0.5j)
+    return dict(name="config2_achromat", face_lists=[fl], rays=rays, wavelengths=wl,
+                max_length=200.0, recursion_limit=200)
+
+
+def config3_aspheric_zernike(core, n=10000000, seed=3):
+    """Config 3: AsphericFace (Newton) + DistortionFace(ShapedPlanarFace, Zernike)
+    with an N-BK7 CoatedDispersiveMaterial (cf. examples/zernike_distortion_example.py,
+    examples/aspheric_lens_example.py), jittered directions."""
+    F, M, S, D = core.cfaces, core.cmaterials, core.cshapes, core.cdistortions
+    owner = Pose(centre=(0., 0., 0.), direction=(0., 0., 1.))
+    air, bk7, coat = nondispersive(core, 1.0), glass_curve(core, "N-BK7"), nondispersive(core, 1.37)
+    shape = S.CircleShape(radius=10.0)
+    m1 = M.CoatedDispersiveMaterial(dispersion_inside=bk7, dispersion_outside=air,
+                                    dispersion_coating=coat, coating_thickness=0.1)
+    m2 = M.CoatedDispersiveMaterial(dispersion_inside=air, dispersion_outside=bk7,
+                                    dispersion_coating=coat, coating_thickness=0.1)
+    f1 = F.AsphericFace(owner=owner, shape=shape, material=m1, z_height=8.0, curvature=30.0,
+                        conic_const=-0.8, A4=1e-5, A6=-2e-8)
+    base = F.ShapedPlanarFace(owner=owner, shape=shape, z_height=0.0)
+    dist = D.ZernikeDistortion(unit_radius=10.0, j4=2e-3, j7=1e-3, j8=-1.5e-3, j12=5e-4)
+    f2 = F.DistortionFace(owner=owner, base_face=base, distortion=dist, shape=shape, material=m2)
+    fl = _facelist(core, owner, [f1, f2])
+    rays = disc_source(n, centre=(0., 0., 40.), axis=(0., 0., -1.), radius=8.0, seed=seed,
+                       jitter=0.01, E1=1.0, E2=0.0)
+    return dict(name="config3_aspheric_zernike", face_lists=[fl], rays=rays,
+                wavelengths=np.array([0.633]), max_length=200.0, recursion_limit=200)
+
+
+def _extrusion_faces(core, owner, profile, z1, z2, material, trace_ends=True):
+    """Extrusion.make_faces (raypier/prisms.py:81-100): circular pairwise over the
+    profile, then the two PolygonFace end caps."""
+    F = core.cfaces
+    profile = np.asarray(profile, dtype=np.double)
+    sides = []
+    k = profile.shape[0]
+    for i in range(k):
+        (x2, y2), (x1, y1) = profile[i], profile[(i + 1) % k]
+        sides.append(F.ExtrudedPlanarFace(owner=owner, z1=z1, z2=z2, x1=x1, y1=y1, x2=x2, y2=y2,
+                                          material=material))
+    if trace_ends:
+        sides.append(F.PolygonFace(owner=owner, z_plane=z1, xy_points=profile, material=material))
+        sides.append(F.PolygonFace(owner=owner, z_plane=z2, material=material, xy_points=profile,
+                                   invert_normal=True))
+    return sides
+
+
+def michelson_face_lists(core):
+    """UnpolarisingBeamsplitterCube(size=10) + two PEC mirrors (flat, R=2000 mm),
+    examples/michelson_interferometer_example.py:10-40, raypier/beamsplitters.py:86-97."""
+    F, M, S = core.cfaces, core.cmaterials, core.cshapes
+    h = 5.0
+    cube = Pose(centre=(0., 0., 0.), direction=(0., 0., 1.))
+    glass = M.FullDielectricMaterial(n_inside=1.5, n_outside=1.0)
+    faces = _extrusion_faces(core, cube, [(-h, -h), (-h, h), (h, h), (h, -h)], -h, h, glass)
+    faces.append(F.ExtrudedPlanarFace(owner=cube, z1=-h, z2=h, x1=-h, y1=-h, x2=h, y2=h,
+                                      material=M.PartiallyReflectiveMaterial(reflectivity=0.5)))
+    fl_cube = _facelist(core, cube, faces)
+    shape = S.CircleShape(radius=10.0)
+    m1 = Pose(centre=(0., 20., 0.), direction=(0., -1., 0.))
+    m2 = Pose(centre=(20., 0., 0.), direction=(-1., 0., 0.))
+    fl_m1 = _facelist(core, m1, [F.ShapedPlanarFace(owner=m1, shape=shape, z_height=0.0,
+                                                    material=M.PECMaterial())])
+    fl_m2 = _facelist(core, m2, [F.ShapedSphericalFace(owner=m2, shape=shape, z_height=0.0,
+                                                       curvature=2000.0, material=M.PECMaterial())])
+    return [fl_cube, fl_m1, fl_m2]
+
+
+def config5_michelson(core, n=20000, seed=5, gausslets=True, radius=3.0):
+    """Config 5: Michelson interferometer with an unpolarising beamsplitter cube
+    (branching ray tree), Gaussian-weighted collimated source of gausslets."""
+    face_lists = michelson_face_lists(core)
+    wl = np.array([1.0])
+    rays = disc_source(n, centre=(-30., 0., 0.), axis=(1., 0., 0.), radius=radius, seed=seed,
+                       E_vector=(0., 1., 0.), gaussian_sigma=5.0,
+                       ray_type_id=GAUSSLET if gausslets else 0)
+    out = dict(name="config5_michelson" + ("" if gausslets else "_rays"), face_lists=face_lists,
+               wavelengths=wl, max_length=50.0, recursion_limit=200)
+    if gausslets:
+        rays['length'] = 50.0
+        gc = core.ctracer.GaussletCollection.from_rays(rays)
+        gc.config_parabasal_rays(wl, 0.5, 0.0)
+        out['rays'] = gc.copy_as_array()
+    else:
+        out['rays'] = rays
+    return out
+
+
+def config4_prisms(core, n=100000, seed=4):
+    """Config 4 (TIR part): a rhomboid + a right-angle (Dove-like) prism built as
+    extrusions with FullDielectricMaterial (examples/ctracer_demo_prisms.py), low
+    thresholds so weak Fresnel branches are followed over many generations, plus an
+    OpaqueMaterial beam stop (raypier/beamstop.py)."""
+    F, M = core.cfaces, core.cmaterials
+    p1 = Pose(centre=(0., 0., 0.), direction=(0., 0., 1.))
+    glass = M.FullDielectricMaterial(n_inside=1.5, n_outside=1.0, reflection_threshold=0.02,
+                                     transmission_threshold=0.02)
+    rhomboid = [(-10., -5.), (-4., 5.), (10., 5.), (4., -5.)]
+    fl1 = _facelist(core, p1, _extrusion_faces(core, p1, rhomboid, -6., 6., glass))
+    p2 = Pose(centre=(30., 2., 0.), direction=(0., 0., 1.), rotation=10.0)
+    glass2 = M.FullDielectricMaterial(n_inside=1.764, n_outside=1.0, reflection_threshold=0.02,
+                                      transmission_threshold=0.02)
+    tri = [(-8., -8.), (-8., 8.), (8., -8.)]
+    fl2 = _facelist(core, p2, _extrusion_faces(core, p2, tri, -6., 6., glass2))
+    stop = Pose(centre=(60., 0., 0.), direction=(-1., 0., 0.), diameter=40.0, offset=0.0)
+    fl3 = _facelist(core, stop, [F.CircularFace(owner=stop, diameter=40.0,
+                                                material=M.OpaqueMaterial())])
+    rays = disc_source(n, centre=(-30., 0.3, 0.2), axis=(1., 0.02, 0.01), radius=3.0, seed=seed,
+                       E1=1.0, E2=0.3j)
+    return dict(name="config4_prisms", face_lists=[fl1, fl2, fl3], rays=rays,
+                wavelengths=np.array([0.633]), max_length=300.0, recursion_limit=200)
+
+
+def config4_grating(core, n=100000, seed=44, n_wavelengths=260):
+    """Config 4 (grating part): the diffraction-grating dispersion compensator
+    (examples/grating_dispersion_compensator_example.py:19-50): RectangularGrating
+    1400 l/mm order -1, an achromat, a PEC mirror and a beam stop; broadband source
+    with 260 wavelengths 0.76-0.80 um."""
+    F, M = core.cfaces, core.cmaterials
+    wl = np.linspace(0.76, 0.80, n_wavelengths)
+    ang = math.radians(41.0)
+    g = Pose(centre=(0., 0., 0.), direction=(-math.cos(ang), math.sin(ang), 0.0), rotation=180.0,
+             length=25.0, width=25.0, offset=0.0)
+    gmat = M.DiffractionGratingMaterial(lines_per_mm=1400.0, order=-1, efficiency=0.9,
+                                        origin=(0., 0., 0.))
+    fl_g = _facelist(core, g, [F.RectangularFace(owner=g, length=25.0, width=25.0, offset=0.0,
+                                                 material=gmat)])
+    mir = Pose(centre=(-57.9, 15.7, 0.), direction=(0.965, -0.261, 0.0), diameter=25.0, offset=0.0)
+    fl_m = _facelist(core, mir, [F.CircularFace(owner=mir, diameter=25.0,
+                                                material=M.PECMaterial())])
+    stop = Pose(centre=(-120., 0., 0.), direction=(1., 0., 0.), diameter=200.0, offset=0.0)
+    fl_s = _facelist(core, stop, [F.CircularFace(owner=stop, diameter=200.0,
+                                                 material=M.OpaqueMaterial())])
+    rays = disc_source(n, centre=(-80., 0., 0.), axis=(1., 0., 0.), radius=2.0, seed=seed,
+                       n_wavelengths=n_wavelengths, E_vector=(0., 0., 1.))
+    return dict(name="config4_grating", face_lists=[fl_g, fl_m, fl_s], rays=rays, wavelengths=wl,
+                max_length=300.0, recursion_limit=200)
+
+
+CONFIGS = {
+    "config1": config1_singlet,
+    "config2": config2_achromat,
+    "config3": config3_aspheric_zernike,
+    "config4_prisms": config4_prisms,
+    "config4_grating": config4_grating,
+    "config5": config5_michelson,
+}
+
+
+def build(core, name, **kw):
+    return CONFIGS[name](core, **kw)
