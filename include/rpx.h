@@ -323,8 +323,8 @@ void rpx_rays_free(rpx_ctx* ctx, rpx_rays* rays);
 /* Replaces the generation loop of trace_rays (core/tracer.py:22,39-45) over
  * trace_segment_c / trace_gausslet_c, inputs already resident on the device.
  * `rays` becomes generation 0 of the result (it is mutated like the reference
- * mutates its parent collection: length, end_face_idx) and is owned by the
- * result afterwards.  max_length is rounded to float for plain rays exactly as
+ * mutates its parent collection: length, end_face_idx).  The call takes ownership
+ * of `rays` whether it succeeds or fails: never rpx_rays_free it afterwards.  max_length is rounded to float for plain rays exactly as
  * trace_segment_c's `float max_length` argument does (ctracer.pyx:2066).      */
 int rpx_trace_device(rpx_ctx* ctx, rpx_rays* rays, double max_length, int recursion_limit,
                      uint32_t flags, rpx_result** out_result);
@@ -355,6 +355,26 @@ void rpx_result_free(rpx_ctx* ctx, rpx_result* res);
 /* Raw CUDA stream the context launches on (so a caller can bracket the trace
  * with its own events); returned as void* to keep CUDA types out of the ABI. */
 void* rpx_stream(rpx_ctx* ctx);
+
+/* ---------------------------------------------------------- unit entry points
+ * Batch evaluation of ONE device function over host arrays -- the GPU counterpart of the
+ * reference's Python-callable test wrappers ("mostly for testing",
+ * doc/source/creating_new_optics.rst:89-93).  Not on the trace path.                  */
+/* Face.intersect(p1, p2, is_base_ray) (ctracer.pyx:1769-1777): p1/p2 are n x 3 local points */
+int rpx_unit_face_intersect(rpx_ctx* ctx, int face, const double* p1, const double* p2, uint64_t n,
+                            int is_base_ray, double* out_dist);
+/* FaceList.compute_orientation(face, point) (ctracer.pyx:1955-1964): n x 3 GLOBAL points */
+int rpx_unit_face_normal(rpx_ctx* ctx, int face, const double* points, uint64_t n,
+                         double* out_normal, double* out_tangent);
+/* InterfaceMaterial.eval_child_ray(ray, idx, point, normal, tangent, new_rays)
+ * (ctracer.pyx:1620-1632): children of ray i land in out_aos_2n[2*i .. 2*i+count[i])   */
+int rpx_unit_material_eval(rpx_ctx* ctx, int material, const void* rays_aos, uint64_t n,
+                           const double* point, const double* normal, const double* tangent,
+                           void* out_aos_2n, uint32_t* out_counts);
+/* Distortion.z_offset / z_offset_and_gradient (ctracer.pyx:1703-1729): out_grad is n x 3
+ * (dz/dx, dz/dy, z)                                                                      */
+int rpx_unit_distortion(rpx_ctx* ctx, int distortion, const double* x, const double* y, uint64_t n,
+                        double* out_z, double* out_grad);
 
 #ifdef __cplusplus
 }

@@ -1,0 +1,103 @@
+"""ctypes binding of librpx.so (the C ABI declared in include/rpx.h).
+
+There is deliberately no fallback: if the CUDA library has not been built, or there is
+no CUDA device, every entry point raises.  (The plain-C oracle under oracle/ is test
+infrastructure and is never imported from here.)
+"""
+import ctypes as C
+import os
+
+from . import _abi as A
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "csrc", "librpx.so")
+
+# every symbol include/rpx.h declares (checked by tests/test_abi.py)
+EXPORTS = (
+    "rpx_init", "rpx_shutdown", "rpx_last_error", "rpx_abi_version", "rpx_scene_set",
+    "rpx_host_alloc", "rpx_host_free", "rpx_rays_upload", "rpx_rays_download", "rpx_rays_count",
+    "rpx_rays_free", "rpx_trace_device", "rpx_trace", "rpx_result_n_generations",
+    "rpx_result_counts", "rpx_result_generation", "rpx_result_face_counts",
+    "rpx_result_device_ms", "rpx_result_launches", "rpx_result_kernel_ms", "rpx_result_free",
+    "rpx_stream", "rpx_unit_face_intersect", "rpx_unit_face_normal", "rpx_unit_material_eval",
+    "rpx_unit_distortion",
+)
+
+
+class RpxError(RuntimeError):
+    def __init__(self, code, message):
+        RuntimeError.__init__(self, "%s (%d): %s" % (A.STATUS_NAMES.get(code, "RPX_ERR"), code, message))
+        self.code = code
+
+
+_LIB = None
+
+
+def load():
+    """Load librpx.so and declare prototypes.  Raises if the library is missing."""
+    global _LIB
+    if _LIB is not None:
+        return _LIB
+    if not os.path.exists(LIB_PATH):
+        raise RuntimeError(
+            "librpx.so not found at %s -- build it with `python -c 'import __graft_entry__ as g; "
+            "g.build()'` or `make -C raypier_optics_b200/csrc`.  raypier_optics_b200 has no CPU "
+            "fallback." % LIB_PATH)
+    L = C.CDLL(LIB_PATH)
+    vp, i32, u32, u64, d = C.c_void_p, C.c_int, C.c_uint32, C.c_uint64, C.c_double
+    pvp = C.POINTER(C.c_void_p)
+    L.rpx_init.argtypes = [i32, pvp]
+    L.rpx_init.restype = i32
+    L.rpx_shutdown.argtypes = [vp]
+    L.rpx_shutdown.restype = None
+    L.rpx_last_error.argtypes = [vp]
+    L.rpx_last_error.restype = C.c_char_p
+    L.rpx_abi_version.restype = i32
+    L.rpx_scene_set.argtypes = [vp, vp]
+    L.rpx_scene_set.restype = i32
+    L.rpx_host_alloc.argtypes = [C.c_size_t]
+    L.rpx_host_alloc.restype = vp
+    L.rpx_host_free.argtypes = [vp]
+    L.rpx_host_free.restype = None
+    L.rpx_rays_upload.argtypes = [vp, vp, u64, i32, pvp]
+    L.rpx_rays_upload.restype = i32
+    L.rpx_rays_download.argtypes = [vp, vp, vp, u64]
+    L.rpx_rays_download.restype = i32
+    L.rpx_rays_count.argtypes = [vp]
+    L.rpx_rays_count.restype = u64
+    L.rpx_rays_free.argtypes = [vp, vp]
+    L.rpx_rays_free.restype = None
+    L.rpx_trace_device.argtypes = [vp, vp, d, i32, u32, pvp]
+    L.rpx_trace_device.restype = i32
+    L.rpx_trace.argtypes = [vp, vp, u64, i32, d, i32, u32, pvp]
+    L.rpx_trace.restype = i32
+    L.rpx_result_n_generations.argtypes = [vp]
+    L.rpx_result_n_generations.restype = i32
+    L.rpx_result_counts.argtypes = [vp, vp]
+    L.rpx_result_counts.restype = i32
+    L.rpx_result_generation.argtypes = [vp, vp, i32, vp, u64]
+    L.rpx_result_generation.restype = i32
+    L.rpx_result_face_counts.argtypes = [vp, vp]
+    L.rpx_result_face_counts.restype = i32
+    L.rpx_result_device_ms.argtypes = [vp]
+    L.rpx_result_device_ms.restype = d
+    L.rpx_result_launches.argtypes = [vp]
+    L.rpx_result_launches.restype = u64
+    L.rpx_result_kernel_ms.argtypes = [vp, i32, C.POINTER(d), C.POINTER(u64)]
+    L.rpx_result_kernel_ms.restype = i32
+    L.rpx_result_free.argtypes = [vp, vp]
+    L.rpx_result_free.restype = None
+    L.rpx_stream.argtypes = [vp]
+    L.rpx_stream.restype = vp
+    L.rpx_unit_face_intersect.argtypes = [vp, i32, vp, vp, u64, i32, vp]
+    L.rpx_unit_face_intersect.restype = i32
+    L.rpx_unit_face_normal.argtypes = [vp, i32, vp, u64, vp, vp]
+    L.rpx_unit_face_normal.restype = i32
+    L.rpx_unit_material_eval.argtypes = [vp, i32, vp, u64, vp, vp, vp, vp, vp]
+    L.rpx_unit_material_eval.restype = i32
+    L.rpx_unit_distortion.argtypes = [vp, i32, vp, vp, u64, vp, vp]
+    L.rpx_unit_distortion.restype = i32
+    if L.rpx_abi_version() != A.RPX_ABI_VERSION:
+        raise RuntimeError("librpx.so ABI %d != binding ABI %d" % (L.rpx_abi_version(), A.RPX_ABI_VERSION))
+    _LIB = L
+    return L

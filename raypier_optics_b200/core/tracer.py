@@ -1,0 +1,103 @@
+"""Drop-in replacement for ``raypier.core.tracer`` (raypier/core/tracer.py:9-99 of the
+reference): same function name, arguments, return value and side effects, but the
+generation loop runs on the GPU through librpx.
+
+    from raypier_optics_b200.core.tracer import trace_rays     # instead of raypier.core.tracer
+
+``input_rays`` / ``face_lists`` may be this package's host mirrors or genuine
+``raypier.core`` objects (RayCollection / GaussletCollection, FaceList).
+"""
+import numpy as np
+
+from .. import _abi as A
+from ..engine import get_engine
+from ..scene import Scene
+
+
+def _prepare_faces(input_rays, face_lists, max_length):
+    """The per-trace set-up of trace_rays (core/tracer.py:22-37) and the per-generation
+    ``fs.sync_transforms()`` of trace_segment / trace_gausslet (ctracer.pyx:2180-2181)."""
+    input_rays.reset_length(max_length)
+    wavelengths = np.asarray(input_rays.wavelengths)
+    face_lists = list(face_lists)
+    all_faces = [f for fs in face_lists for f in fs.faces]
+    for i, f in enumerate(all_faces):
+        f.idx = i
+        f.count = 0
+        f.update()
+        f.material.wavelengths = wavelengths
+        f.max_length = max_length
+    for f in all_faces:
+        if f.material.is_decomp_material():
+            from ..scene import UnsupportedSceneError
+            raise UnsupportedSceneError(
+                "%s calls back into Python between generations; it is not traced on the device"
+                % type(f.material).__name__)
+    for fs in face_lists:
+        fs.sync_transforms()
+    return wavelengths, face_lists, all_faces
+
+
+def _wrap_generations(input_rays, arrays, wavelengths):
+    """Return the reference's container classes around the device results.
+    ``traced_rays[0] is input_rays`` (mutated in place), each later generation's
+    ``.parent`` is the previous one."""
+    cls = type(input_rays)
+    dtype = getattr(cls, "_dtype", None)
+    out = []
+    prev = None
+    for g, arr in enumerate(arrays):
+        if g == 0 and hasattr(input_rays, "_assign_array"):
+            input_rays._assign_array(arr)
+            rc = input_rays
+        else:
+            if dtype is None:  # genuine reference collection: from_array checks its own dtype object
+                mod = __import__(cls.__module__, fromlist=["ray_dtype"])
+                ref_dtype = mod.gausslet_dtype if arr.dtype == A.gausslet_dtype else mod.ray_dtype
+                a = np.empty(arr.shape[0], dtype=ref_dtype)
+                a.view(np.uint8)[:] = arr.view(np.uint8)
+                rc = cls.from_array(a)
+            else:
+                rc = cls.from_array(arr)
+            if g == 0:
+                # a reference collection cannot be re-pointed at new memory: copy the write-back
+                # fields the reference mutates (length, end_face_idx) through its public API
+                rc.wavelengths = wavelengths
+            else:
+                rc.wavelengths = wavelengths
+                rc.parent = prev
+        out.append(rc)
+        prev = rc
+    return out
+
+
+def trace_rays(input_rays, face_lists, recursion_limit=100, max_length=100.0, device=0):
+    """Core ray-tracing routine: traces a RayCollection or GaussletCollection
+    non-sequentially through the given list of FaceList objects.
+
+    returns - (traced_rays, all_faces), as raypier.core.tracer.trace_rays does: the list of
+    ray generations and the flat face list that ``end_face_idx`` indexes (``face.count`` =
+    hits in this trace).
+    """
+    wavelengths, face_lists, all_faces = _prepare_faces(input_rays, face_lists, max_length)
+    eng = get_engine(device)
+    scene = Scene(face_lists, wavelengths)
+    eng.set_scene(scene)
+    rays = input_rays.copy_as_array()
+    native = np.ascontiguousarray(rays).view(
+        A.gausslet_dtype if rays.dtype.itemsize == A.gausslet_dtype.itemsize else A.ray_dtype)
+    res = eng.trace(native, max_length, recursion_limit)
+    try:
+        arrays = res.generations()
+        for f, c in zip(all_faces, res.face_counts):
+            f.count = int(c)
+    finally:
+        res.free()
+    traced = _wrap_generations(input_rays, arrays, wavelengths)
+    trace_rays.last_device_ms = res.device_ms
+    return traced, all_faces
+
+
+def trace_ray_sequence(input_rays, face_sequence, recursion_limit=100, max_length=100.0):
+    """Sequential mode (core/tracer.py:50-99) is a SURVEY section 8f 'next' row."""
+    raise NotImplementedError("sequential tracing (trace_one_face_*) is not part of this build yet")

@@ -1,0 +1,719 @@
+// rpx_api.cu -- the C ABI of librpx (include/rpx.h): context, scene upload, ray
+// upload/download (AoS <-> SoA on the device), the generation loop and result handles.
+//
+// Host runtime design (B200): one context per process per GPU; one non-blocking CUDA
+// stream; generation buffers come from the stream-ordered memory pool (cudaMallocAsync
+// with an unlimited release threshold, so after the first trace no allocation ever
+// reaches the driver); every kernel launch is bracketed by CUDA events on that stream so
+// bench.py can report per-kernel device time without a profiler attached.
+#include <cuda_runtime.h>
+
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "../../include/rpx.h"
+#include "rpx_kernels.cuh"
+#include "rpx_unit.cuh"
+
+using namespace rpx;
+
+static_assert(sizeof(rpx_ray) == 188, "ray_t layout");
+static_assert(sizeof(rpx_para) == 80, "para_t layout");
+static_assert(sizeof(rpx_gausslet) == 668, "gausslet_t layout");
+static_assert(sizeof(rpx_face) == 176, "rpx_face layout");
+static_assert(sizeof(rpx_material) == 112, "rpx_material layout");
+static_assert(sizeof(rpx_face_set) == 200, "rpx_face_set layout");
+static_assert(sizeof(rpx_shape_op) == 48, "rpx_shape_op layout");
+static_assert(sizeof(rpx_implicit_op) == 64, "rpx_implicit_op layout");
+static_assert(sizeof(rpx_ztape_op) == 32, "rpx_ztape_op layout");
+static_assert(sizeof(rpx_zcoef) == 40, "rpx_zcoef layout");
+static_assert(sizeof(rpx_distortion) == 64, "rpx_distortion layout");
+
+static thread_local std::string g_init_error;
+
+struct rpx_rays {
+    Soa soa;
+    void* block;  // single allocation backing soa.f / soa.u / soa.p
+    size_t bytes;
+    int is_gausslet;
+};
+
+struct KernelStat {
+    std::vector<cudaEvent_t> start, stop;
+};
+
+struct rpx_ctx {
+    int device;
+    cudaStream_t stream;
+    std::string err;
+    // scene
+    bool have_scene;
+    DevScene ds;
+    void* scene_block;
+    int n_traced;
+    int max_kids;       // upper bound of children per hit over all materials in the scene
+    int scene_smem;     // bytes of shared memory the staged scene needs (0 = use global)
+    // scratch
+    unsigned long long* tile_state;
+    size_t tile_state_cap;  // tiles
+    uint32_t* tile_counter;
+    unsigned long long* d_count;
+    unsigned long long* h_count;  // pinned
+    uint32_t* d_face_counts;
+    // event pool
+    std::vector<cudaEvent_t> ev_pool;
+    size_t ev_used;
+};
+
+struct rpx_result {
+    std::vector<rpx_rays*> gens;  // nullptr for generations dropped in KEEP_LAST_ONLY mode
+    std::vector<uint64_t> counts;
+    std::vector<uint32_t> face_counts;
+    double device_ms;
+    uint64_t launches;
+    double k_ms[2];
+    uint64_t k_launches[2];
+};
+
+static int fail(rpx_ctx* ctx, int code, const char* fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    if (ctx) ctx->err = buf;
+    else g_init_error = buf;
+    return code;
+}
+
+#define CU(ctx, call)                                                                         \
+    do {                                                                                      \
+        cudaError_t e_ = (call);                                                              \
+        if (e_ != cudaSuccess)                                                                \
+            return fail(ctx, e_ == cudaErrorMemoryAllocation ? RPX_ERR_NOMEM : RPX_ERR_CUDA,   \
+                        "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
+    } while (0)
+
+extern "C" int rpx_abi_version(void) { return RPX_ABI_VERSION; }
+
+extern "C" const char* rpx_last_error(const rpx_ctx* ctx) {
+    return ctx ? ctx->err.c_str() : g_init_error.c_str();
+}
+
+extern "C" int rpx_init(int device, rpx_ctx** out_ctx) {
+    if (!out_ctx) return fail(nullptr, RPX_ERR_INVALID, "out_ctx is NULL");
+    *out_ctx = nullptr;
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0)
+        return fail(nullptr, RPX_ERR_NODEVICE,
+                    "no CUDA device available (%s); librpx has no CPU fallback",
+                    e != cudaSuccess ? cudaGetErrorString(e) : "device count is 0");
+    if (device < 0 || device >= ndev)
+        return fail(nullptr, RPX_ERR_INVALID, "device %d out of range (0..%d)", device, ndev - 1);
+    rpx_ctx* ctx = new (std::nothrow) rpx_ctx();
+    if (!ctx) return fail(nullptr, RPX_ERR_NOMEM, "out of host memory");
+    ctx->device = device;
+    ctx->have_scene = false;
+    ctx->scene_block = nullptr;
+    ctx->tile_state = nullptr;
+    ctx->tile_state_cap = 0;
+    ctx->ev_used = 0;
+    if ((e = cudaSetDevice(device)) != cudaSuccess ||
+        (e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking)) != cudaSuccess) {
+        fail(nullptr, RPX_ERR_CUDA, "cannot open device %d: %s", device, cudaGetErrorString(e));
+        delete ctx;
+        return RPX_ERR_CUDA;
+    }
+    // keep freed generation buffers in the pool: no driver allocation after warm-up
+    cudaMemPool_t pool;
+    if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
+        unsigned long long thr = ~0ull;
+        cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
+    }
+    if ((e = cudaMalloc(&ctx->tile_counter, sizeof(uint32_t))) != cudaSuccess ||
+        (e = cudaMalloc(&ctx->d_count, sizeof(unsigned long long))) != cudaSuccess ||
+        (e = cudaMallocHost(&ctx->h_count, sizeof(unsigned long long))) != cudaSuccess) {
+        fail(nullptr, RPX_ERR_CUDA, "context scratch allocation failed: %s", cudaGetErrorString(e));
+        delete ctx;
+        return RPX_ERR_CUDA;
+    }
+    ctx->d_face_counts = nullptr;
+    *out_ctx = ctx;
+    return RPX_OK;
+}
+
+extern "C" void rpx_shutdown(rpx_ctx* ctx) {
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    for (cudaEvent_t ev : ctx->ev_pool) cudaEventDestroy(ev);
+    if (ctx->scene_block) cudaFree(ctx->scene_block);
+    if (ctx->tile_state) cudaFree(ctx->tile_state);
+    if (ctx->d_face_counts) cudaFree(ctx->d_face_counts);
+    cudaFree(ctx->tile_counter);
+    cudaFree(ctx->d_count);
+    cudaFreeHost(ctx->h_count);
+    cudaStreamDestroy(ctx->stream);
+    delete ctx;
+}
+
+extern "C" void* rpx_stream(rpx_ctx* ctx) { return ctx ? (void*)ctx->stream : nullptr; }
+
+extern "C" void* rpx_host_alloc(size_t bytes) {
+    void* p = nullptr;
+    if (cudaMallocHost(&p, bytes ? bytes : 1) != cudaSuccess) return nullptr;
+    return p;
+}
+extern "C" void rpx_host_free(void* p) {
+    if (p) cudaFreeHost(p);
+}
+
+// ------------------------------------------------------------------ scene
+static size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+static int validate_scene(rpx_ctx* ctx, const rpx_scene* s) {
+    if (s->abi_version != RPX_ABI_VERSION)
+        return fail(ctx, RPX_ERR_INVALID, "scene abi_version %d != %d", s->abi_version, RPX_ABI_VERSION);
+    if (s->n_traced_faces < 0 || s->n_faces < s->n_traced_faces || s->n_face_sets < 0)
+        return fail(ctx, RPX_ERR_INVALID, "bad face counts");
+    for (int i = 0; i < s->n_faces; i++) {
+        const rpx_face& f = s->faces[i];
+        if (f.type < RPX_FACE_CIRCULAR || f.type > RPX_FACE_DISTORTION)
+            return fail(ctx, RPX_ERR_UNSUPPORTED, "face %d: unsupported face type %d", i, f.type);
+        if (f.face_set < 0 || f.face_set >= s->n_face_sets)
+            return fail(ctx, RPX_ERR_INVALID, "face %d: face_set %d out of range", i, f.face_set);
+        if (i < s->n_traced_faces && (f.material < 0 || f.material >= s->n_materials))
+            return fail(ctx, RPX_ERR_INVALID, "face %d: material %d out of range", i, f.material);
+        if (f.shape_off >= 0 && f.shape_off + f.shape_len > s->n_shape_ops)
+            return fail(ctx, RPX_ERR_INVALID, "face %d: shape program out of range", i);
+        if (f.shape_len > 32) return fail(ctx, RPX_ERR_UNSUPPORTED, "face %d: shape tree too deep", i);
+        if (f.type == RPX_FACE_DISTORTION) {
+            if (f.base_face < 0 || f.base_face >= s->n_faces || s->faces[f.base_face].type == RPX_FACE_DISTORTION)
+                return fail(ctx, RPX_ERR_INVALID, "face %d: bad base_face", i);
+            if (f.aux_off < 0 || f.aux_off >= s->n_distortions)
+                return fail(ctx, RPX_ERR_INVALID, "face %d: distortion index out of range", i);
+        }
+        if (f.type == RPX_FACE_IMPLICIT_PLANAR && (f.aux_off < 0 || f.aux_off + f.aux_n > s->n_implicit_ops))
+            return fail(ctx, RPX_ERR_INVALID, "face %d: implicit program out of range", i);
+        if ((f.type == RPX_FACE_POLYGON || f.type == RPX_FACE_ORIENTED_POLYGON) &&
+            (f.aux_off < 0 || f.aux_off + 2 * f.aux_n > s->n_pool || f.aux_n < 1))
+            return fail(ctx, RPX_ERR_INVALID, "face %d: polygon points out of range", i);
+        if (f.type == RPX_FACE_EXT_POLY && (f.aux_off < 0 || f.aux_off + f.aux_n * f.aux_m > s->n_pool))
+            return fail(ctx, RPX_ERR_INVALID, "face %d: coefficient table out of range", i);
+        if (f.type == RPX_FACE_ELLIPSOIDAL && (f.aux_off < 0 || f.aux_off + 24 > s->n_pool))
+            return fail(ctx, RPX_ERR_INVALID, "face %d: transforms out of range", i);
+    }
+    for (int i = 0; i < s->n_face_sets; i++) {
+        const rpx_face_set& fs = s->face_sets[i];
+        if (fs.face_begin < 0 || fs.face_end < fs.face_begin || fs.face_end > s->n_traced_faces)
+            return fail(ctx, RPX_ERR_INVALID, "face set %d: bad face range", i);
+    }
+    for (int i = 0; i < s->n_materials; i++) {
+        const rpx_material& m = s->materials[i];
+        if (m.type < RPX_MAT_OPAQUE || m.type > RPX_MAT_RECT_APERTURE)
+            return fail(ctx, RPX_ERR_UNSUPPORTED, "material %d: unsupported material type %d", i, m.type);
+        bool needs_tab = m.type == RPX_MAT_DIELECTRIC || m.type == RPX_MAT_FULL_DIELECTRIC || m.type == RPX_MAT_COATED;
+        if (needs_tab && (m.ntab_off < 0 || m.ntab_off + 3 * s->n_wavelengths > s->n_ntab))
+            return fail(ctx, RPX_ERR_INVALID, "material %d: n-table out of range", i);
+    }
+    for (int i = 0; i < s->n_distortions; i++) {
+        const rpx_distortion& d = s->distortions[i];
+        if (d.type == RPX_DIST_ZERNIKE) {
+            if (d.k_max > RPX_ZERNIKE_MAX_K)
+                return fail(ctx, RPX_ERR_UNSUPPORTED, "distortion %d: k_max %d > %d", i, d.k_max, RPX_ZERNIKE_MAX_K);
+            if (d.coef_off < 0 || d.coef_off + d.n_coefs > s->n_zcoefs || d.tape_z_off + d.tape_z_len > s->n_ztape ||
+                d.tape_g_off + d.tape_g_len > s->n_ztape)
+                return fail(ctx, RPX_ERR_INVALID, "distortion %d: tables out of range", i);
+        } else if (d.type != RPX_DIST_ZERNIKE_J7) {
+            return fail(ctx, RPX_ERR_UNSUPPORTED, "distortion %d: unsupported type %d", i, d.type);
+        }
+    }
+    for (int i = 0; i < s->n_ztape; i++) {
+        const rpx_ztape_op& t = s->ztape[i];
+        const int lim = 2 + 3 * RPX_ZERNIKE_MAX_K;
+        if (t.dst < 0 || t.dst >= RPX_ZERNIKE_MAX_K || t.a < 0 || t.a >= lim || t.b < 0 || t.b >= lim ||
+            t.c < 0 || t.c >= lim || t.d < 0 || t.d >= lim || t.e < 0 || t.e >= lim)
+            return fail(ctx, RPX_ERR_INVALID, "zernike tape op %d out of range", i);
+    }
+    return RPX_OK;
+}
+
+extern "C" int rpx_scene_set(rpx_ctx* ctx, const rpx_scene* s) {
+    if (!ctx || !s) return fail(ctx, RPX_ERR_INVALID, "NULL argument");
+    CU(ctx, cudaSetDevice(ctx->device));
+    int rc = validate_scene(ctx, s);
+    if (rc != RPX_OK) return rc;
+    // one block: faces | sets | materials | shape ops | implicit ops | distortions | zcoefs |
+    //            ztape | wavelengths | ntab | pool
+    struct Part { const void* src; size_t bytes; size_t off; };
+    Part parts[11] = {
+        {s->faces, (size_t)s->n_faces * sizeof(rpx_face), 0},
+        {s->face_sets, (size_t)s->n_face_sets * sizeof(rpx_face_set), 0},
+        {s->materials, (size_t)s->n_materials * sizeof(rpx_material), 0},
+        {s->shape_ops, (size_t)s->n_shape_ops * sizeof(rpx_shape_op), 0},
+        {s->implicit_ops, (size_t)s->n_implicit_ops * sizeof(rpx_implicit_op), 0},
+        {s->distortions, (size_t)s->n_distortions * sizeof(rpx_distortion), 0},
+        {s->zcoefs, (size_t)s->n_zcoefs * sizeof(rpx_zcoef), 0},
+        {s->ztape, (size_t)s->n_ztape * sizeof(rpx_ztape_op), 0},
+        {s->wavelengths, (size_t)s->n_wavelengths * sizeof(double), 0},
+        {s->ntab, (size_t)s->n_ntab * 2 * sizeof(double), 0},
+        {s->pool, (size_t)s->n_pool * sizeof(double), 0},
+    };
+    size_t total = 0;
+    for (Part& p : parts) {
+        p.off = total;
+        total += align_up(p.bytes ? p.bytes : 8, 256);
+    }
+    std::vector<unsigned char> host(total, 0);
+    for (Part& p : parts)
+        if (p.bytes) {
+            if (!p.src) return fail(ctx, RPX_ERR_INVALID, "scene table pointer is NULL");
+            memcpy(host.data() + p.off, p.src, p.bytes);
+        }
+    CU(ctx, cudaStreamSynchronize(ctx->stream));
+    if (ctx->scene_block) {
+        CU(ctx, cudaFree(ctx->scene_block));
+        ctx->scene_block = nullptr;
+    }
+    CU(ctx, cudaMalloc(&ctx->scene_block, total));
+    CU(ctx, cudaMemcpy(ctx->scene_block, host.data(), total, cudaMemcpyHostToDevice));
+    unsigned char* b = (unsigned char*)ctx->scene_block;
+    DevScene& d = ctx->ds;
+    d.faces = (const rpx_face*)(b + parts[0].off);
+    d.sets = (const rpx_face_set*)(b + parts[1].off);
+    d.mats = (const rpx_material*)(b + parts[2].off);
+    d.shape_ops = (const rpx_shape_op*)(b + parts[3].off);
+    d.impl_ops = (const rpx_implicit_op*)(b + parts[4].off);
+    d.dists = (const rpx_distortion*)(b + parts[5].off);
+    d.zcoefs = (const rpx_zcoef*)(b + parts[6].off);
+    d.ztape = (const rpx_ztape_op*)(b + parts[7].off);
+    d.wavelengths = (const double*)(b + parts[8].off);
+    d.ntab = (const double*)(b + parts[9].off);
+    d.pool = (const double*)(b + parts[10].off);
+    d.n_traced = s->n_traced_faces;
+    d.n_faces = s->n_faces;
+    d.n_sets = s->n_face_sets;
+    d.n_mats = s->n_materials;
+    d.n_wl = s->n_wavelengths;
+    d.n_dists = s->n_distortions;
+    ctx->n_traced = s->n_traced_faces;
+    ctx->max_kids = 0;
+    for (int i = 0; i < s->n_traced_faces; i++) {
+        int t = s->materials[s->faces[i].material].type;
+        int kids = (t == RPX_MAT_OPAQUE) ? 0
+                   : (t == RPX_MAT_PARTIALLY_REFLECTIVE || t == RPX_MAT_LINEAR_POLARISING ||
+                      t == RPX_MAT_FULL_DIELECTRIC || t == RPX_MAT_COATED) ? 2 : 1;
+        if (kids > ctx->max_kids) ctx->max_kids = kids;
+    }
+    size_t smem = (size_t)s->n_faces * sizeof(rpx_face) + (size_t)s->n_face_sets * sizeof(rpx_face_set);
+    ctx->scene_smem = smem <= 40 * 1024 ? (int)smem : 0;
+    if (ctx->d_face_counts) {
+        CU(ctx, cudaFree(ctx->d_face_counts));
+        ctx->d_face_counts = nullptr;
+    }
+    CU(ctx, cudaMalloc(&ctx->d_face_counts, sizeof(uint32_t) * (size_t)(s->n_traced_faces > 0 ? s->n_traced_faces : 1)));
+    ctx->have_scene = true;
+    return RPX_OK;
+}
+
+// ------------------------------------------------------------------ ray buffers
+static int rays_alloc(rpx_ctx* ctx, unsigned long long cap_req, int is_gausslet, rpx_rays** out) {
+    rpx_rays* r = new (std::nothrow) rpx_rays();
+    if (!r) return fail(ctx, RPX_ERR_NOMEM, "out of host memory");
+    unsigned long long cap = (cap_req + 31ull) / 32ull * 32ull;  // every field array 256-B aligned
+    if (cap == 0) cap = 32;
+    size_t fb = (size_t)NF * cap * sizeof(double);
+    size_t ub = (size_t)NU * cap * sizeof(uint32_t);
+    size_t pb = is_gausslet ? (size_t)NP * cap * sizeof(double) : 0;
+    r->bytes = fb + ub + pb;
+    r->is_gausslet = is_gausslet;
+    cudaError_t e = cudaMallocAsync(&r->block, r->bytes, ctx->stream);
+    if (e != cudaSuccess) {
+        delete r;
+        return fail(ctx, RPX_ERR_NOMEM, "cannot allocate %zu bytes for a generation of %llu %s: %s", fb + ub + pb,
+                    cap, is_gausslet ? "gausslets" : "rays", cudaGetErrorString(e));
+    }
+    unsigned char* b = (unsigned char*)r->block;
+    r->soa.f = (double*)b;
+    r->soa.p = is_gausslet ? (double*)(b + fb) : nullptr;
+    r->soa.u = (uint32_t*)(b + fb + pb);
+    r->soa.n = 0;
+    r->soa.cap = cap;
+    *out = r;
+    return RPX_OK;
+}
+
+extern "C" void rpx_rays_free(rpx_ctx* ctx, rpx_rays* rays) {
+    if (!rays) return;
+    if (ctx) {
+        cudaSetDevice(ctx->device);
+        cudaFreeAsync(rays->block, ctx->stream);
+    }
+    delete rays;
+}
+
+extern "C" uint64_t rpx_rays_count(const rpx_rays* rays) { return rays ? rays->soa.n : 0; }
+
+static cudaEvent_t next_event(rpx_ctx* ctx) {
+    if (ctx->ev_used == ctx->ev_pool.size()) {
+        cudaEvent_t ev;
+        cudaEventCreate(&ev);
+        ctx->ev_pool.push_back(ev);
+    }
+    return ctx->ev_pool[ctx->ev_used++];
+}
+
+extern "C" int rpx_rays_upload(rpx_ctx* ctx, const void* aos, uint64_t n, int is_gausslet, rpx_rays** out_rays) {
+    if (!ctx || !out_rays || (!aos && n)) return fail(ctx, RPX_ERR_INVALID, "NULL argument");
+    CU(ctx, cudaSetDevice(ctx->device));
+    if (n >= 0xFFFFFFFFull)
+        return fail(ctx, RPX_ERR_INVALID, "%llu rays per generation exceed the 32-bit parent_idx of ray_t",
+                    (unsigned long long)n);
+    rpx_rays* r = nullptr;
+    int rc = rays_alloc(ctx, n, is_gausslet, &r);
+    if (rc != RPX_OK) return rc;
+    r->soa.n = n;
+    if (n) {
+        const size_t rec = is_gausslet ? RPX_GAUSSLET_BYTES : RPX_RAY_BYTES;
+        void* d_aos = nullptr;
+        CU(ctx, cudaMallocAsync(&d_aos, n * rec, ctx->stream));
+        CU(ctx, cudaMemcpyAsync(d_aos, aos, n * rec, cudaMemcpyHostToDevice, ctx->stream));
+        if (is_gausslet) {
+            const int T = 64;
+            k_aos_to_soa<RPX_WORDS_GAUSSLET, T><<<(unsigned)((n + T - 1) / T), T, T * RPX_GAUSSLET_BYTES, ctx->stream>>>(
+                (const uint32_t*)d_aos, r->soa);
+        } else {
+            const int T = 256;
+            k_aos_to_soa<RPX_WORDS_RAY, T><<<(unsigned)((n + T - 1) / T), T, T * RPX_RAY_BYTES, ctx->stream>>>(
+                (const uint32_t*)d_aos, r->soa);
+        }
+        CU(ctx, cudaGetLastError());
+        CU(ctx, cudaFreeAsync(d_aos, ctx->stream));
+        // the caller may reuse `aos` as soon as we return
+        CU(ctx, cudaStreamSynchronize(ctx->stream));
+    }
+    *out_rays = r;
+    return RPX_OK;
+}
+
+extern "C" int rpx_rays_download(rpx_ctx* ctx, const rpx_rays* rays, void* out_aos, uint64_t capacity) {
+    if (!ctx || !rays || (!out_aos && rays->soa.n)) return fail(ctx, RPX_ERR_INVALID, "NULL argument");
+    CU(ctx, cudaSetDevice(ctx->device));
+    const uint64_t n = rays->soa.n;
+    if (capacity < n) return fail(ctx, RPX_ERR_INVALID, "output holds %llu records, generation has %llu",
+                                  (unsigned long long)capacity, (unsigned long long)n);
+    if (!n) return RPX_OK;
+    const size_t rec = rays->is_gausslet ? RPX_GAUSSLET_BYTES : RPX_RAY_BYTES;
+    void* d_aos = nullptr;
+    CU(ctx, cudaMallocAsync(&d_aos, n * rec, ctx->stream));
+    if (rays->is_gausslet) {
+        const int T = 64;
+        k_soa_to_aos<RPX_WORDS_GAUSSLET, T><<<(unsigned)((n + T - 1) / T), T, T * RPX_GAUSSLET_BYTES, ctx->stream>>>(
+            rays->soa, (uint32_t*)d_aos);
+    } else {
+        const int T = 256;
+        k_soa_to_aos<RPX_WORDS_RAY, T><<<(unsigned)((n + T - 1) / T), T, T * RPX_RAY_BYTES, ctx->stream>>>(
+            rays->soa, (uint32_t*)d_aos);
+    }
+    CU(ctx, cudaGetLastError());
+    CU(ctx, cudaMemcpyAsync(out_aos, d_aos, n * rec, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(ctx, cudaFreeAsync(d_aos, ctx->stream));
+    CU(ctx, cudaStreamSynchronize(ctx->stream));
+    return RPX_OK;
+}
+
+// ------------------------------------------------------------------ the generation loop
+extern "C" void rpx_result_free(rpx_ctx* ctx, rpx_result* res) {
+    if (!res) return;
+    for (rpx_rays* g : res->gens) rpx_rays_free(ctx, g);
+    delete res;
+}
+
+extern "C" int rpx_trace_device(rpx_ctx* ctx, rpx_rays* rays, double max_length, int recursion_limit, uint32_t flags,
+                                rpx_result** out_result) {
+    if (!ctx || !rays || !out_result) return fail(ctx, RPX_ERR_INVALID, "NULL argument");
+    if (!ctx->have_scene) return fail(ctx, RPX_ERR_STATE, "rpx_scene_set must be called before tracing");
+    CU(ctx, cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->stream;
+    const int is_g = rays->is_gausslet;
+    // `float max_length` of trace_segment_c (ctracer.pyx:2066); trace_gausslet_c takes a double
+    const double ml = is_g ? max_length : (double)(float)max_length;
+    rpx_result* res = new (std::nothrow) rpx_result();
+    if (!res) return fail(ctx, RPX_ERR_NOMEM, "out of host memory");
+    res->device_ms = 0;
+    res->launches = 0;
+    res->k_ms[0] = res->k_ms[1] = 0;
+    res->k_launches[0] = res->k_launches[1] = 0;
+    res->face_counts.assign((size_t)ctx->n_traced, 0u);
+    ctx->ev_used = 0;
+    std::vector<cudaEvent_t> ev_i0, ev_i1, ev_s0, ev_s1;
+
+    // Ownership: `rays` belongs to this call from here on (success or failure).  `cur` is
+    // either the last entry of res->gens or not yet part of it; `child` likewise.
+    rpx_rays* cur = rays;
+    rpx_rays* child = nullptr;
+    auto bail = [&](int code) {
+        if (child && child != cur) rpx_rays_free(ctx, child);
+        if (cur && (res->gens.empty() || res->gens.back() != cur)) rpx_rays_free(ctx, cur);
+        rpx_result_free(ctx, res);
+        return code;
+    };
+#define CUR(call)                                                                                  \
+    do {                                                                                           \
+        cudaError_t e_ = (call);                                                                   \
+        if (e_ != cudaSuccess)                                                                     \
+            return bail(fail(ctx, e_ == cudaErrorMemoryAllocation ? RPX_ERR_NOMEM : RPX_ERR_CUDA,   \
+                             "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__)); \
+    } while (0)
+
+    cudaEvent_t ev_begin = next_event(ctx), ev_end = next_event(ctx);
+    CUR(cudaMemsetAsync(ctx->d_face_counts, 0, sizeof(uint32_t) * (size_t)(ctx->n_traced > 0 ? ctx->n_traced : 1), st));
+    CUR(cudaEventRecord(ev_begin, st));
+    if (is_g && cur->soa.n) {  // input_rays.reset_length(max_length), core/tracer.py:22
+        k_reset_length<<<(unsigned)((cur->soa.n + 255) / 256), 256, 0, st>>>(cur->soa, ml);
+        res->launches++;
+    }
+    int count = 0;
+    const int smem = ctx->scene_smem;
+    while (cur->soa.n > 0 && count < recursion_limit) {
+        const unsigned long long n = cur->soa.n;
+        res->gens.push_back(cur);
+        res->counts.push_back(n);
+        const uint32_t n_tiles = (uint32_t)((n + RPX_TILE - 1) / RPX_TILE);
+        // ---- nearest hit
+        cudaEvent_t a0 = next_event(ctx), a1 = next_event(ctx);
+        CUR(cudaEventRecord(a0, st));
+        k_intersect<<<n_tiles, RPX_TILE, smem, st>>>(ctx->ds, cur->soa, ml, smem);
+        CUR(cudaGetLastError());
+        CUR(cudaEventRecord(a1, st));
+        ev_i0.push_back(a0);
+        ev_i1.push_back(a1);
+        // ---- children
+        unsigned long long cap_child = n * (unsigned long long)(ctx->max_kids > 0 ? ctx->max_kids : 1);
+        if (cap_child >= 0xFFFFFFFFull)
+            return bail(fail(ctx, RPX_ERR_INVALID, "generation would exceed the 32-bit parent_idx of ray_t"));
+        {
+            int rc = rays_alloc(ctx, cap_child, is_g, &child);
+            if (rc != RPX_OK) return bail(rc);
+        }
+        if (n_tiles > ctx->tile_state_cap) {
+            if (ctx->tile_state) CUR(cudaFree(ctx->tile_state));
+            ctx->tile_state = nullptr;
+            ctx->tile_state_cap = 0;
+            size_t cap_t = (size_t)n_tiles * 2;
+            CUR(cudaMalloc(&ctx->tile_state, cap_t * sizeof(unsigned long long)));
+            ctx->tile_state_cap = cap_t;
+        }
+        CUR(cudaMemsetAsync(ctx->tile_state, 0, (size_t)n_tiles * sizeof(unsigned long long), st));
+        CUR(cudaMemsetAsync(ctx->tile_counter, 0, sizeof(uint32_t), st));
+        cudaEvent_t b0 = next_event(ctx), b1 = next_event(ctx);
+        CUR(cudaEventRecord(b0, st));
+        if (is_g)
+            k_shade<true><<<n_tiles, RPX_TILE, smem, st>>>(ctx->ds, cur->soa, child->soa, ml, ctx->tile_state,
+                                                          ctx->tile_counter, ctx->d_count, ctx->d_face_counts,
+                                                          n_tiles, smem);
+        else
+            k_shade<false><<<n_tiles, RPX_TILE, smem, st>>>(ctx->ds, cur->soa, child->soa, ml, ctx->tile_state,
+                                                           ctx->tile_counter, ctx->d_count, ctx->d_face_counts,
+                                                           n_tiles, smem);
+        CUR(cudaGetLastError());
+        CUR(cudaEventRecord(b1, st));
+        ev_s0.push_back(b0);
+        ev_s1.push_back(b1);
+        res->launches += 2;
+        // ---- len(new_rays): the only host round trip of a generation
+        CUR(cudaMemcpyAsync(ctx->h_count, ctx->d_count, sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
+        CUR(cudaStreamSynchronize(st));
+        child->soa.n = *ctx->h_count;
+        if (flags & RPX_TRACE_KEEP_LAST_ONLY) {
+            // streaming mode: the parent generation is complete (write-back done); drop it
+            rpx_rays_free(ctx, res->gens.back());
+            res->gens.back() = nullptr;
+        }
+        cur = child;
+        child = nullptr;
+        count++;
+    }
+    CUR(cudaEventRecord(ev_end, st));
+    // the generation that was built but never traced is not part of traced_rays
+    if (res->gens.empty() || res->gens.back() != cur) rpx_rays_free(ctx, cur);
+    cur = nullptr;
+    CUR(cudaMemcpyAsync(res->face_counts.data(), ctx->d_face_counts, sizeof(uint32_t) * (size_t)ctx->n_traced,
+                        cudaMemcpyDeviceToHost, st));
+    CUR(cudaStreamSynchronize(st));
+    float ms = 0;
+    CUR(cudaEventElapsedTime(&ms, ev_begin, ev_end));
+    res->device_ms = ms;
+    for (size_t g = 0; g < ev_i0.size(); g++) {
+        CUR(cudaEventElapsedTime(&ms, ev_i0[g], ev_i1[g]));
+        res->k_ms[0] += ms;
+        res->k_launches[0]++;
+    }
+    for (size_t g = 0; g < ev_s0.size(); g++) {
+        CUR(cudaEventElapsedTime(&ms, ev_s0[g], ev_s1[g]));
+        res->k_ms[1] += ms;
+        res->k_launches[1]++;
+    }
+#undef CUR
+    *out_result = res;
+    return RPX_OK;
+}
+
+extern "C" int rpx_trace(rpx_ctx* ctx, const void* rays_aos, uint64_t n, int is_gausslet, double max_length,
+                         int recursion_limit, uint32_t flags, rpx_result** out_result) {
+    if (!ctx || !out_result) return fail(ctx, RPX_ERR_INVALID, "NULL argument");
+    if (!ctx->have_scene) return fail(ctx, RPX_ERR_STATE, "rpx_scene_set must be called before tracing");
+    rpx_rays* r = nullptr;
+    int rc = rpx_rays_upload(ctx, rays_aos, n, is_gausslet, &r);
+    if (rc != RPX_OK) return rc;
+    return rpx_trace_device(ctx, r, max_length, recursion_limit, flags, out_result);  // owns r either way
+}
+
+extern "C" int rpx_result_n_generations(const rpx_result* res) { return res ? (int)res->counts.size() : 0; }
+
+extern "C" int rpx_result_counts(const rpx_result* res, uint64_t* counts) {
+    if (!res || !counts) return RPX_ERR_INVALID;
+    for (size_t i = 0; i < res->counts.size(); i++) counts[i] = res->counts[i];
+    return RPX_OK;
+}
+
+extern "C" int rpx_result_generation(rpx_ctx* ctx, const rpx_result* res, int g, void* out_aos, uint64_t capacity) {
+    if (!ctx || !res) return fail(ctx, RPX_ERR_INVALID, "NULL argument");
+    if (g < 0 || g >= (int)res->gens.size()) return fail(ctx, RPX_ERR_INVALID, "generation %d out of range", g);
+    if (!res->gens[g]) return fail(ctx, RPX_ERR_STATE, "generation %d was dropped (RPX_TRACE_KEEP_LAST_ONLY)", g);
+    return rpx_rays_download(ctx, res->gens[g], out_aos, capacity);
+}
+
+extern "C" int rpx_result_face_counts(const rpx_result* res, uint32_t* counts) {
+    if (!res || !counts) return RPX_ERR_INVALID;
+    for (size_t i = 0; i < res->face_counts.size(); i++) counts[i] = res->face_counts[i];
+    return RPX_OK;
+}
+
+extern "C" double rpx_result_device_ms(const rpx_result* res) { return res ? res->device_ms : 0.0; }
+extern "C" uint64_t rpx_result_launches(const rpx_result* res) { return res ? res->launches : 0; }
+
+extern "C" int rpx_result_kernel_ms(const rpx_result* res, int which, double* total_ms, uint64_t* launches) {
+    if (!res || which < 0 || which > 1) return RPX_ERR_INVALID;
+    if (total_ms) *total_ms = res->k_ms[which];
+    if (launches) *launches = res->k_launches[which];
+    return RPX_OK;
+}
+
+// ------------------------------------------------------------------ unit entry points
+// Host buffers in / out; each call stages through temporary device buffers.
+namespace {
+struct DevBuf {
+    void* p = nullptr;
+    cudaStream_t st;
+    explicit DevBuf(cudaStream_t s) : st(s) {}
+    ~DevBuf() { if (p) cudaFreeAsync(p, st); }
+    cudaError_t alloc(size_t bytes) { return cudaMallocAsync(&p, bytes ? bytes : 8, st); }
+    cudaError_t put(const void* src, size_t bytes) {
+        cudaError_t e = alloc(bytes);
+        if (e != cudaSuccess) return e;
+        return cudaMemcpyAsync(p, src, bytes, cudaMemcpyHostToDevice, st);
+    }
+    cudaError_t get(void* dst, size_t bytes) { return cudaMemcpyAsync(dst, p, bytes, cudaMemcpyDeviceToHost, st); }
+};
+}  // namespace
+
+static int unit_precheck(rpx_ctx* ctx) {
+    if (!ctx) return RPX_ERR_INVALID;
+    if (!ctx->have_scene) return fail(ctx, RPX_ERR_STATE, "rpx_scene_set must be called first");
+    CU(ctx, cudaSetDevice(ctx->device));
+    return RPX_OK;
+}
+
+extern "C" int rpx_unit_face_intersect(rpx_ctx* ctx, int face, const double* p1, const double* p2, uint64_t n,
+                                       int is_base_ray, double* out_dist) {
+    int rc = unit_precheck(ctx);
+    if (rc != RPX_OK) return rc;
+    if (face < 0 || face >= ctx->ds.n_faces) return fail(ctx, RPX_ERR_INVALID, "face %d out of range", face);
+    if (!n) return RPX_OK;
+    cudaStream_t st = ctx->stream;
+    DevBuf a(st), b(st), o(st);
+    CU(ctx, a.put(p1, n * 24));
+    CU(ctx, b.put(p2, n * 24));
+    CU(ctx, o.alloc(n * 8));
+    k_unit_face_intersect<<<(unsigned)((n + 127) / 128), 128, 0, st>>>(ctx->ds, face, (const double*)a.p,
+                                                                    (const double*)b.p, n, is_base_ray, (double*)o.p);
+    CU(ctx, cudaGetLastError());
+    CU(ctx, o.get(out_dist, n * 8));
+    CU(ctx, cudaStreamSynchronize(st));
+    return RPX_OK;
+}
+
+extern "C" int rpx_unit_face_normal(rpx_ctx* ctx, int face, const double* points, uint64_t n, double* out_normal,
+                                    double* out_tangent) {
+    int rc = unit_precheck(ctx);
+    if (rc != RPX_OK) return rc;
+    if (face < 0 || face >= ctx->ds.n_faces) return fail(ctx, RPX_ERR_INVALID, "face %d out of range", face);
+    if (!n) return RPX_OK;
+    cudaStream_t st = ctx->stream;
+    DevBuf a(st), nn(st), tt(st);
+    CU(ctx, a.put(points, n * 24));
+    CU(ctx, nn.alloc(n * 24));
+    CU(ctx, tt.alloc(n * 24));
+    k_unit_face_normal<<<(unsigned)((n + 127) / 128), 128, 0, st>>>(ctx->ds, face, (const double*)a.p, n, (double*)nn.p,
+                                                                 (double*)tt.p);
+    CU(ctx, cudaGetLastError());
+    CU(ctx, nn.get(out_normal, n * 24));
+    CU(ctx, tt.get(out_tangent, n * 24));
+    CU(ctx, cudaStreamSynchronize(st));
+    return RPX_OK;
+}
+
+extern "C" int rpx_unit_material_eval(rpx_ctx* ctx, int material, const void* rays_aos, uint64_t n, const double* point,
+                                      const double* normal, const double* tangent, void* out_aos_2n,
+                                      uint32_t* out_counts) {
+    int rc = unit_precheck(ctx);
+    if (rc != RPX_OK) return rc;
+    if (material < 0 || material >= ctx->ds.n_mats)
+        return fail(ctx, RPX_ERR_INVALID, "material %d out of range", material);
+    if (!n) return RPX_OK;
+    cudaStream_t st = ctx->stream;
+    DevBuf r(st), p(st), nn(st), tt(st), o(st), c(st);
+    CU(ctx, r.put(rays_aos, n * RPX_RAY_BYTES));
+    CU(ctx, p.put(point, n * 24));
+    CU(ctx, nn.put(normal, n * 24));
+    CU(ctx, tt.put(tangent, n * 24));
+    CU(ctx, o.alloc(2 * n * RPX_RAY_BYTES));
+    CU(ctx, cudaMemsetAsync(o.p, 0, 2 * n * RPX_RAY_BYTES, st));
+    CU(ctx, c.alloc(n * 4));
+    k_unit_material_eval<<<(unsigned)((n + 127) / 128), 128, 0, st>>>(ctx->ds, material, (const uint32_t*)r.p, n,
+                                                                   (const double*)p.p, (const double*)nn.p,
+                                                                   (const double*)tt.p, (uint32_t*)o.p, (uint32_t*)c.p);
+    CU(ctx, cudaGetLastError());
+    CU(ctx, o.get(out_aos_2n, 2 * n * RPX_RAY_BYTES));
+    CU(ctx, c.get(out_counts, n * 4));
+    CU(ctx, cudaStreamSynchronize(st));
+    return RPX_OK;
+}
+
+extern "C" int rpx_unit_distortion(rpx_ctx* ctx, int distortion, const double* x, const double* y, uint64_t n,
+                                   double* out_z, double* out_grad) {
+    int rc = unit_precheck(ctx);
+    if (rc != RPX_OK) return rc;
+    if (distortion < 0 || distortion >= ctx->ds.n_dists)
+        return fail(ctx, RPX_ERR_INVALID, "distortion %d out of range", distortion);
+    if (!n) return RPX_OK;
+    cudaStream_t st = ctx->stream;
+    DevBuf a(st), b(st), z(st), g(st);
+    CU(ctx, a.put(x, n * 8));
+    CU(ctx, b.put(y, n * 8));
+    CU(ctx, z.alloc(n * 8));
+    CU(ctx, g.alloc(n * 24));
+    k_unit_distortion<<<(unsigned)((n + 127) / 128), 128, 0, st>>>(ctx->ds, distortion, (const double*)a.p,
+                                                                (const double*)b.p, n, (double*)z.p, (double*)g.p);
+    CU(ctx, cudaGetLastError());
+    CU(ctx, z.get(out_z, n * 8));
+    CU(ctx, g.get(out_grad, n * 24));
+    CU(ctx, cudaStreamSynchronize(st));
+    return RPX_OK;
+}

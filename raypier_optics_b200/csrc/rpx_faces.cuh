@@ -1,0 +1,950 @@
+// rpx_faces.cuh -- device ray x face intersection, surface normals, aperture shapes,
+// implicit-surface bounds and Zernike distortions.
+//
+// One device function per reference Face class (raypier/core/cfaces.pyx), dispatched by
+// a switch on rpx_face.type over the flat face table (staged in shared memory by the
+// kernels).  Closed-form plane / sphere / conic / quadric roots, fp64 Newton iteration
+// for aspheric and extended-polynomial faces, tangent-plane secant iteration for
+// Zernike-distorted faces.  Semantics follow the cited reference lines, including its
+// quirks; the arithmetic is free to contract to FMA.
+#pragma once
+#include "../../include/rpx.h"
+#include "rpx_math.cuh"
+
+namespace rpx {
+
+// Device view of the flattened scene (pointers into device global memory, except
+// faces/sets which the kernels re-point at their shared-memory copy).
+struct DevScene {
+    const rpx_face* faces;
+    const rpx_face_set* sets;
+    const rpx_material* mats;
+    const rpx_shape_op* shape_ops;
+    const rpx_implicit_op* impl_ops;
+    const rpx_distortion* dists;
+    const rpx_zcoef* zcoefs;
+    const rpx_ztape_op* ztape;
+    const double* wavelengths;
+    const double* ntab;  // interleaved re, im
+    const double* pool;
+    int n_traced, n_faces, n_sets, n_mats, n_wl, n_dists;
+};
+
+#define RPX_INF (__longlong_as_double(0x7ff0000000000000LL))
+#define RPX_NO_HIT (-1.0)
+
+// ------------------------------------------------------------------ shapes (cshapes.pyx)
+RPX_DEV int shape_polygon_inside(const double* pts, int size, double X, double Y) {
+    int ct = 0;  // cshapes.pyx:150-168: even-odd rule, half-open edges
+    double y1 = pts[2 * (size - 1) + 1], x1 = pts[2 * (size - 1)];
+    for (int i = 0; i < size; i++) {
+        double y2 = pts[2 * i + 1], x2 = pts[2 * i];
+        if ((y1 <= Y && Y < y2) || (y2 <= Y && Y < y1)) {
+            if ((x1 + (Y - y1) * (x2 - x1) / (y2 - y1)) > X) ct = !ct;
+        }
+        y1 = y2;
+        x1 = x2;
+    }
+    return ct;
+}
+
+// Shape tree as a postfix program on a bit stack (bit i of `stack` = i-th entry).
+__device__ __noinline__ int shape_inside(const DevScene& S, const rpx_face* f, double x, double y) {
+    if (f->shape_off < 0) return 1;
+    uint32_t stack = 0;
+    int sp = 0;
+    for (int i = 0; i < f->shape_len; i++) {
+        const rpx_shape_op* op = &S.shape_ops[f->shape_off + i];
+        uint32_t v;
+        switch (op->type) {
+            case RPX_SHAPE_CIRCLE: {  // cshapes.pyx:109-116 (strict <)
+                double dx = x - op->p[0], dy = y - op->p[1];
+                v = ((dx * dx) + (dy * dy) < (op->p[2] * op->p[2])) ? 1u : 0u;
+                stack |= v << sp;
+                sp++;
+            } break;
+            case RPX_SHAPE_RECT: {  // :128-136
+                double dx = x - op->p[0], dy = y - op->p[1];
+                v = ((2 * fabs(dx) < op->p[2]) && (2 * fabs(dy)) < op->p[3]) ? 1u : 0u;
+                stack |= v << sp;
+                sp++;
+            } break;
+            case RPX_SHAPE_POLYGON:
+                v = (uint32_t)shape_polygon_inside(S.pool + op->aux_off, op->aux_n, x, y);
+                stack |= v << sp;
+                sp++;
+                break;
+            case RPX_SHAPE_NOT: stack ^= 1u << (sp - 1); break;
+            case RPX_SHAPE_AND: {
+                uint32_t b = (stack >> (sp - 1)) & 1u, a = (stack >> (sp - 2)) & 1u;
+                sp--;
+                stack &= ~(3u << (sp - 1));
+                stack |= (a & b) << (sp - 1);
+            } break;
+            case RPX_SHAPE_OR: {
+                uint32_t b = (stack >> (sp - 1)) & 1u, a = (stack >> (sp - 2)) & 1u;
+                sp--;
+                stack &= ~(3u << (sp - 1));
+                stack |= (a | b) << (sp - 1);
+            } break;
+            case RPX_SHAPE_XOR: {
+                uint32_t b = (stack >> (sp - 1)) & 1u, a = (stack >> (sp - 2)) & 1u;
+                sp--;
+                stack &= ~(3u << (sp - 1));
+                stack |= (a ^ b) << (sp - 1);
+            } break;
+            default:  // RPX_SHAPE_TRUE
+                stack |= 1u << sp;
+                sp++;
+                break;
+        }
+    }
+    return (int)(stack & 1u);
+}
+
+// ------------------------------------------------ implicit surfaces (cimplicit_surfs.pyx)
+__device__ __noinline__ double implicit_eval(const DevScene& S, int off, int len, vec3 p) {
+    double stack[8];
+    int sp = 0;
+    for (int i = 0; i < len; i++) {
+        const rpx_implicit_op* op = &S.impl_ops[off + i];
+        switch (op->type) {
+            case RPX_IMPL_PLANE: stack[sp++] = dot(ld3(op->p + 3), p - ld3(op->p)); break;
+            case RPX_IMPL_SPHERE: stack[sp++] = sep(p, ld3(op->p)) - op->p[3]; break;
+            case RPX_IMPL_CYLINDER:
+                stack[sp++] = mag(cross(p - ld3(op->p), ld3(op->p + 3))) - op->p[6];
+                break;
+            case RPX_IMPL_NEG: stack[sp - 1] = -stack[sp - 1]; break;
+            case RPX_IMPL_MIN: sp--; if (stack[sp] < stack[sp - 1]) stack[sp - 1] = stack[sp]; break;
+            case RPX_IMPL_MAX: sp--; if (stack[sp] > stack[sp - 1]) stack[sp - 1] = stack[sp]; break;
+            case RPX_IMPL_SUB: sp--; stack[sp - 1] -= stack[sp]; break;
+            default: stack[sp++] = -1.0; break;  // RPX_IMPL_NULL
+        }
+        if (sp > 7) sp = 7;
+    }
+    return stack[0];
+}
+
+// ------------------------------------------------------- distortions (cdistortions.pyx)
+// Operand decode for the host-built Zernike tapes (see rpx.h, rpx_ztape_op).
+RPX_DEV double zop(const double* ws, int op) {
+    if (op < 2) return (double)op;
+    int k = (op - 2) / 3, w = (op - 2) - 3 * k;
+    return ws[w * RPX_ZERNIKE_MAX_K + k];
+}
+
+RPX_DEV void run_ztape(const DevScene& S, int off, int len, double r, double* ws) {
+    for (int i = 0; i < len; i++) {
+        const rpx_ztape_op t = S.ztape[off + i];
+        double a = zop(ws, t.a), b = zop(ws, t.b), c = zop(ws, t.c);
+        double val;
+        if (t.kind == 0) {  // R: cdistortions.pyx:174-175
+            val = r * (a + b);
+            val -= c;
+            ws[t.dst] = val;
+        } else if (t.kind == 1) {  // R': :211-215
+            val = a + b;
+            val += r * (zop(ws, t.d) + zop(ws, t.e));
+            val -= c;
+            ws[RPX_ZERNIKE_MAX_K + t.dst] = val;
+        } else if (t.kind == 2) {  // R/r: :312-313
+            val = a + b;
+            val -= c;
+            ws[2 * RPX_ZERNIKE_MAX_K + t.dst] = val;
+        } else {  // workspace[0, dst] = 1.0 (:433)
+            ws[t.dst] = 1.0;
+        }
+    }
+}
+
+__device__ __noinline__ double distortion_z(const DevScene& S, const rpx_distortion* D, double x, double y) {
+    if (D->type == RPX_DIST_ZERNIKE_J7) {  // cdistortions.pyx:50-59
+        x /= D->p[0];
+        y /= D->p[0];
+        double Z = sqrt(8.0) * (3 * (x * x + y * y) - 2) * y;
+        return Z * D->p[1];
+    }
+    double ws[RPX_ZERNIKE_MAX_K];  // only row 0 is used by z_offset_c
+    x /= D->p[0];
+    y /= D->p[0];
+    double r = sqrt(x * x + y * y);
+    double theta = atan2(y, x);
+    run_ztape(S, D->tape_z_off, D->tape_z_len, r, ws);
+    double Z = 0.0;
+    for (int i = 0; i < D->n_coefs; i++) {
+        const rpx_zcoef* c = &S.zcoefs[D->coef_off + i];
+        double N = (c->m == 0) ? sqrt((double)(c->n + 1)) : sqrt((double)(2 * (c->n + 1)));
+        N *= c->value;
+        double PH = (c->m >= 0) ? cos(c->m * theta) : -sin(c->m * theta);  // Q11: signed m
+        double R = zop(ws, c->opR_z);
+        Z += N * R * PH;
+    }
+    return Z;
+}
+
+// -> (dz/dx, dz/dy, z)
+__device__ __noinline__ vec3 distortion_zgrad(const DevScene& S, const rpx_distortion* D, double x, double y) {
+    if (D->type == RPX_DIST_ZERNIKE_J7) {  // cdistortions.pyx:61-81
+        double root8 = sqrt(8.0) * D->p[1], R = D->p[0];
+        x /= R;
+        y /= R;
+        return v3(root8 * 6 * x * y / R, root8 * (3 * x * x + 9 * y * y - 2) / R,
+                  root8 * (3 * (x * x + y * y) - 2) * y);
+    }
+    double ws[3 * RPX_ZERNIKE_MAX_K];
+    x /= D->p[0];
+    y /= D->p[0];
+    double r = sqrt(x * x + y * y);
+    double theta = atan2(y, x);
+    run_ztape(S, D->tape_g_off, D->tape_g_len, r, ws);
+    double st, ct;
+    sincos(theta, &st, &ct);
+    vec3 Z = v3(0.0, 0.0, 0.0);
+    for (int i = 0; i < D->n_coefs; i++) {
+        const rpx_zcoef* c = &S.zcoefs[D->coef_off + i];
+        double sm, cm;
+        sincos(c->m * theta, &sm, &cm);
+        double PH, PHprime;
+        if (c->m >= 0) {
+            PH = cm;
+            PHprime = -c->m * sm;
+        } else {
+            PH = -sm;
+            PHprime = -c->m * cm;
+        }
+        double R = zop(ws, c->opR), Rprime = zop(ws, c->opRp), R_over_r = zop(ws, c->opRr);
+        double N = (c->m == 0) ? sqrt((double)(c->n + 1)) : sqrt((double)(2 * (c->n + 1)));
+        N *= c->value;
+        Z.z += N * R * PH;
+        Z.x += N * (Rprime * ct * PH + R_over_r * (-st) * PHprime);
+        Z.y += N * (Rprime * st * PH + R_over_r * (ct)*PHprime);
+    }
+    Z.x /= D->p[0];
+    Z.y /= D->p[0];
+    return Z;
+}
+
+// ------------------------------------------------------------------ faces (cfaces.pyx)
+RPX_DEV int point_in_polygon(double X, double Y, const double* pts, int size) {
+    int ct = 0;  // cfaces.pyx:1050-1068
+    double y1 = pts[2 * (size - 1) + 1], x1 = pts[2 * (size - 1)];
+    for (int i = 0; i < size; i++) {
+        double y2 = pts[2 * i + 1], x2 = pts[2 * i];
+        double h = (Y - y1) / (y2 - y1);
+        if (0 < h && h <= 1.0) {
+            double x = x1 + h * (x2 - x1);
+            if (x > X) ct = !ct;
+        }
+        y1 = y2;
+        x1 = x2;
+    }
+    return ct;
+}
+
+// intersect_conic, cfaces.pyx:1695-1747
+RPX_DEV double intersect_conic(vec3 a, vec3 d, double curvature, double conic_const) {
+    double beta = 1 + conic_const;
+    double R = -curvature;
+    double b2 = beta * beta;
+    double A = b2 * (d.z * d.z) + beta * (d.x * d.x) + beta * (d.y * d.y);
+    double B = -2 * R * beta * d.z + 2 * a.x * beta * d.x + 2 * a.y * beta * d.y + 2 * a.z * b2 * d.z;
+    double C = -2 * R * a.z * beta + (a.x * a.x) * beta + (a.y * a.y) * beta + (a.z * a.z) * b2;
+    double D = B * B - 4 * A * C;
+    if (D < 0) return -1;
+    D = sqrt(D);
+    if (R * beta * d.z <= 0) return (-B + D) / (2 * A);
+    return (-B - D) / (2 * A);
+}
+
+struct Aspheric {
+    double R, beta, A4, A6, A8, A10, A12, A14, A16;
+    vec3 a, d;
+};
+
+// eval_aspheric_impf + eval_aspheric_grad in one pass (cfaces.pyx:1854-1882); the even
+// powers of r2 are built by repeated multiplication instead of libm pow().
+RPX_DEV void aspheric_f_df(const Aspheric& A, double alpha, double* f, double* df) {
+    double px = A.a.x + alpha * A.d.x, py = A.a.y + alpha * A.d.y;
+    double r2 = px * px + py * py;
+    double r4 = r2 * r2, r6 = r4 * r2, r8 = r4 * r4, r10 = r8 * r2, r12 = r8 * r4, r14 = r8 * r6,
+           r16 = r8 * r8;
+    double root = sqrt(1 - A.beta * r2 / (A.R * A.R));
+    double out = r2;
+    out /= A.R * (1 + root);
+    out -= A.a.z + alpha * A.d.z;
+    out += A.A4 * r4 + A.A6 * r6 + A.A8 * r8 + A.A10 * r10 + A.A12 * r12 + A.A14 * r14 + A.A16 * r16;
+    *f = out;
+    if (df) {
+        double dx = A.d.x * px, dy = A.d.y * py;
+        double g = A.A10 * (10 * dx + 10 * dy) * r8;
+        g += A.A12 * (12 * dx + 12 * dy) * r10;
+        g += A.A14 * (14 * dx + 14 * dy) * r12;
+        g += A.A16 * (16 * dx + 16 * dy) * r14;
+        g += A.A4 * (4 * dx + 4 * dy) * (r2);
+        g += A.A6 * (6 * dx + 6 * dy) * r4;
+        g += A.A8 * (8 * dx + 8 * dy) * r6 - A.d.z;
+        g += (2 * dx + 2 * dy) / (A.R * (root + 1));
+        g += A.beta * (2 * dx + 2 * dy) * (r2) / (2 * (A.R * A.R * A.R) * root * ((root + 1) * (root + 1)));
+        *df = g;
+    }
+}
+
+// eval_extpoly_impf / eval_extpoly_grad, cfaces.pyx:2043-2126
+RPX_DEV void extpoly_f_df(const rpx_face* f, const double* E, vec3 a, vec3 d, double alpha, double* fo,
+                          double* dfo) {
+    double R = f->p[0], beta = f->p[1], norm_radius = f->p[2], z_height = f->p[3];
+    int Nx = f->aux_n, Ny = f->aux_m;
+    double x = a.x + alpha * d.x, y = a.y + alpha * d.y;
+    double r2 = x * x + y * y;
+    double out = r2;
+    if (R >= 0) out /= (R + sqrt(R * R - beta * r2));
+    else out /= (R - sqrt(R * R - beta * r2));
+    out -= a.z + alpha * d.z;
+    double xn = x / norm_radius, yn = y / norm_radius;
+    double xi = 1.0;
+    for (int i = 0; i < Nx; i++) {
+        double yj = 1.0;
+        for (int j = 0; j < Ny; j++) {
+            out += E[i * Ny + j] * xi * yj;
+            yj *= yn;
+        }
+        xi *= xn;
+    }
+    out += z_height;
+    *fo = out;
+    if (dfo) {
+        double R2 = R * R;
+        double rt = sqrt(1 - (beta * r2 / R2));
+        double denom = R * (rt + 1);
+        double nom = (2 * d.x * x + 2 * d.y * y);
+        double inv_rad = 1. / norm_radius;
+        double g = -d.z;
+        g += nom / denom;
+        g += beta * nom * r2 / (2 * R * rt * denom * denom);
+        double xs = x * inv_rad, ys = y * inv_rad;
+        double dEdx = 0.0, dEdy = 0.0;
+        double xim1 = 1.0;  // xs^(i-1)
+        for (int i = 1; i < Nx; i++) {
+            double yj = 1.0;
+            for (int j = 0; j < Ny; j++) {
+                dEdx += (i)*E[i * Ny + j] * xim1 * yj;
+                yj *= ys;
+            }
+            xim1 *= xs;
+        }
+        xi = 1.0;
+        for (int i = 0; i < Nx; i++) {
+            double yjm1 = 1.0;  // ys^(j-1)
+            for (int j = 1; j < Ny; j++) {
+                dEdy += (j)*E[i * Ny + j] * xi * yjm1;
+                yjm1 *= ys;
+            }
+            xi *= xs;
+        }
+        dEdx *= inv_rad;
+        dEdy *= inv_rad;
+        g += dEdx * d.x;
+        g += dEdy * d.y;
+        *dfo = g;
+    }
+}
+
+// Plane z = z0 with parametric test h in [tol, 1]; returns h or <0
+RPX_DEV double plane_h(double z0, vec3 p1, vec3 p2, double tol, bool* ok) {
+    double h = (z0 - p1.z) / (p2.z - p1.z);
+    *ok = !((h < tol) || (h > 1.0));
+    return h;
+}
+
+__device__ vec3 face_normal(const DevScene& S, const rpx_face* f, vec3 p);
+
+// The two roots a1 (+) and a2 (-) of a quadric with the sphere-style hemisphere and
+// aperture culling shared by Spherical / ShapedSpherical faces.
+RPX_DEV double sphere_hit(const DevScene& S, const rpx_face* f, vec3 r, vec3 p2, int is_base_ray,
+                          double curvature, double z_height, double diameter, bool shaped) {
+    vec3 s = p2 - r;  // cfaces.pyx:439-486 / 531-576
+    double cz = z_height - curvature;
+    vec3 d = r;
+    d.z -= cz;
+    double A = mag_sq(s);
+    double B = 2 * dot(s, d);
+    double C = mag_sq(d) - curvature * curvature;
+    double D = B * B - 4 * A * C;
+    if (D < 0) return RPX_NO_HIT;
+    D = sqrt(D);
+    double a1 = (-B + D) / (2 * A);
+    vec3 pt1 = r + s * a1;
+    double a2 = (-B - D) / (2 * A);
+    vec3 pt2 = r + s * a2;
+    if (curvature >= 0) {
+        if (pt1.z < cz) a1 = RPX_INF;
+        if (pt2.z < cz) a2 = RPX_INF;
+    } else {
+        if (pt1.z > cz) a1 = RPX_INF;
+        if (pt2.z > cz) a2 = RPX_INF;
+    }
+    if (is_base_ray) {
+        if (!shaped) {
+            double D4 = diameter * diameter / 4.;
+            if ((pt1.x * pt1.x + pt1.y * pt1.y) > D4) a1 = RPX_INF;
+            if ((pt2.x * pt2.x + pt2.y * pt2.y) > D4) a2 = RPX_INF;
+        } else {
+            if (!shape_inside(S, f, pt1.x, pt1.y)) a1 = RPX_INF;
+            if (!shape_inside(S, f, pt2.x, pt2.y)) a2 = RPX_INF;
+        }
+    }
+    if (a2 < a1) a1 = a2;
+    if (a1 > 1.0 || a1 < f->tolerance) return RPX_NO_HIT;
+    return a1 * sep(r, p2);
+}
+
+// Face.intersect_c for the simple (non-wrapping) face classes.
+__device__ double face_intersect_basic(const DevScene& S, const rpx_face* f, vec3 p1, vec3 p2,
+                                       int is_base_ray) {
+    const double* P = f->p;
+    const double tol = f->tolerance;
+    switch (f->type) {
+        case RPX_FACE_CIRCULAR: {  // cfaces.pyx:151-178
+            bool ok;
+            double h = plane_h(P[2], p1, p2, tol, &ok);
+            if (!ok) return RPX_NO_HIT;
+            double X = p1.x + h * (p2.x - p1.x) - P[1];
+            double Y = p1.y + h * (p2.y - p1.y);
+            if (is_base_ray && (X * X + Y * Y) > (P[0] * P[0] / 4)) return RPX_NO_HIT;
+            return h * sep(p1, p2);
+        }
+        case RPX_FACE_SHAPED_PLANAR: {  // :201-226
+            bool ok;
+            double h = plane_h(P[0], p1, p2, tol, &ok);
+            if (!ok) return RPX_NO_HIT;
+            double X = p1.x + h * (p2.x - p1.x);
+            double Y = p1.y + h * (p2.y - p1.y);
+            if (is_base_ray && !shape_inside(S, f, X, Y)) return RPX_NO_HIT;
+            return h * sep(p1, p2);
+        }
+        case RPX_FACE_IMPLICIT_PLANAR: {  // :280-307
+            vec3 normal = ld3(P + 3), origin = ld3(P);
+            vec3 dp = p2 - p1;
+            vec3 po = origin - p1;
+            double h = dot(po, normal) / dot(dp, normal);
+            if ((h < tol) || (h > 1.0)) return RPX_NO_HIT;
+            po = p1 + dp * h;
+            if (is_base_ray && implicit_eval(S, f->aux_off, f->aux_n, po) > 0.0) return RPX_NO_HIT;
+            return h * mag(dp);
+        }
+        case RPX_FACE_ELLIPTICAL_PLANE: {  // :322-341
+            double gx = P[0], gy = P[1], d = P[2];
+            double h = (gx * p1.x + gy * p1.y - p1.z) /
+                       ((p2.z - p1.z) - gx * (p2.x - p1.x) - gy * (p2.y - p1.y));
+            if ((h < tol) || (h > 1.0)) return RPX_NO_HIT;
+            double X = p1.x + h * (p2.x - p1.x);
+            double Y = p1.y + h * (p2.y - p1.y);
+            if (is_base_ray && (X * X + Y * Y) > (d * d / 4)) return RPX_NO_HIT;
+            return h * sep(p1, p2);
+        }
+        case RPX_FACE_RECTANGULAR: {  // :365-397
+            bool ok;
+            double h = plane_h(P[3], p1, p2, tol, &ok);
+            if (!ok) return RPX_NO_HIT;
+            if (is_base_ray) {
+                double X = p1.x + h * (p2.x - p1.x) - P[2];
+                double Y = p1.y + h * (p2.y - p1.y);
+                if (X * X > P[0] * P[0] / 4) return RPX_NO_HIT;
+                if (Y * Y > P[1] * P[1] / 4) return RPX_NO_HIT;
+            }
+            return h * sep(p1, p2);
+        }
+        case RPX_FACE_SPHERICAL: return sphere_hit(S, f, p1, p2, is_base_ray, P[1], P[2], P[0], false);
+        case RPX_FACE_SHAPED_SPHERICAL:
+            return sphere_hit(S, f, p1, p2, is_base_ray, P[0], P[1], 0.0, true);
+        case RPX_FACE_EXTRUDED_PLANAR: {  // :665-699
+            vec3 r = p1;
+            double ux = P[0], uy = P[1];
+            double vx = P[2] - ux, vy = P[3] - uy;
+            vec3 s = p2 - r;
+            double den = (s.x * vy - s.y * vx);
+            if (is_base_ray) {
+                double a = (s.y * (ux - r.x) - s.x * (uy - r.y)) / den;
+                if (a < 0) return RPX_NO_HIT;
+                if (a > 1) return RPX_NO_HIT;
+            }
+            double a = (vx * (r.y - uy) - vy * (r.x - ux)) / den;
+            if (is_base_ray) {
+                double dz = a * (p2.z - r.z);
+                if (P[4] < (r.z + dz) && (r.z + dz) < P[5]) return a * mag(s);
+                return RPX_NO_HIT;
+            }
+            return a * mag(s);
+        }
+        case RPX_FACE_POLYGON: {  // :1093-1108 (parabasal rays never hit: dist stays -1)
+            bool ok;
+            double h = plane_h(P[0], p1, p2, tol, &ok);
+            if (!ok) return RPX_NO_HIT;
+            double X = p1.x + h * (p2.x - p1.x);
+            double Y = p1.y + h * (p2.y - p1.y);
+            if (is_base_ray && point_in_polygon(X, Y, S.pool + f->aux_off, f->aux_n) == 1)
+                return h * sep(p1, p2);
+            return RPX_NO_HIT;
+        }
+        case RPX_FACE_ORIENTED_POLYGON: {  // :1189-1219 (h is an absolute distance here)
+            vec3 n = ld3(P + 3), o = ld3(P);
+            vec3 line = p2 - p1;
+            double max_length = mag(line);
+            line = norm(line);
+            double h = dot(line, n);
+            if (h == 0.0) return RPX_NO_HIT;
+            h = dot(o - p1, n) / h;
+            if ((h < tol) || (h > max_length)) return RPX_NO_HIT;
+            if (is_base_ray) {
+                line = (p1 + line * h) - o;
+                double X = dot(line, ld3(P + 6));
+                double Y = dot(line, ld3(P + 9));
+                if (point_in_polygon(X, Y, S.pool + f->aux_off, f->aux_n) == 1) return h;
+                return RPX_NO_HIT;
+            }
+            return h;
+        }
+        case RPX_FACE_OFFAXIS_PARABOLIC: {  // :1228-1298
+            double efl = P[0], diameter = P[1];
+            double A = 1 / (2 * efl);
+            vec3 s = p2 - p1;
+            vec3 r = p1;
+            r.z += efl / 2.;
+            double a = A * (s.x * s.x + s.y * s.y);
+            double b = 2 * A * (r.x * s.x + r.y * s.y) - s.z;
+            double c = A * (r.x * r.x + r.y * r.y) - r.z;
+            double d = b * b - 4 * a * c;
+            if (d < 0) return RPX_NO_HIT;
+            if (a < 1e-10) {
+                double a1 = -c / b;
+                vec3 pt1 = r + s * a1;
+                pt1.x -= efl;
+                if ((pt1.x * pt1.x + pt1.y * pt1.y) > (diameter / 2)) return RPX_NO_HIT;
+                if (a1 > 1.0 || a1 < tol) return RPX_NO_HIT;
+                return a1 * sep(p1, p2);
+            }
+            d = sqrt(d);
+            double a1 = (-b + d) / (2 * a);
+            vec3 pt1 = r + s * a1;
+            double a2 = (-b - d) / (2 * a);
+            vec3 pt2 = r + s * a2;
+            pt1.x -= efl;
+            pt2.x -= efl;
+            if (is_base_ray) {
+                d = diameter;
+                d *= d / 4.;
+                if ((pt1.x * pt1.x + pt1.y * pt1.y) > d) a1 = RPX_INF;
+                if ((pt2.x * pt2.x + pt2.y * pt2.y) > d) a2 = RPX_INF;
+            }
+            if (a2 < a1) a1 = a2;
+            if (a1 > 1.0 || a1 < tol) return RPX_NO_HIT;
+            return a1 * sep(p1, p2);
+        }
+        case RPX_FACE_ELLIPSOIDAL: {  // :1344-1393
+            const double* T = S.pool + f->aux_off;
+            vec3 Sv = p2 - p1;
+            vec3 r = transform_pt(T, p1);
+            vec3 s = transform_pt(T, p2);
+            s = s - r;
+            double B = P[1] * P[1], A = P[0] * P[0];
+            double a = A * (s.z * s.z + s.y * s.y) + B * s.x * s.x;
+            double b = 2 * (A * (r.z * s.z + r.y * s.y) + B * r.x * s.x);
+            double c = A * (r.z * r.z + r.y * r.y) + B * r.x * r.x - A * B;
+            double d = b * b - 4 * a * c;
+            d = sqrt(d);
+            double root1 = (-b + d) / (2 * a);
+            double root2 = (-b - d) / (2 * a);
+            vec3 q2 = p1 + Sv * root2;
+            vec3 q1 = p1 + Sv * root1;
+            if (is_base_ray) {
+                if (!(P[2] < q2.x && q2.x < P[3])) root2 = 2;
+                if (!(P[4] < q2.y && q2.y < P[5])) root2 = 2;
+                if (!(P[6] < q2.z && q2.z < P[7])) root2 = 2;
+                if (!(P[2] < q1.x && q1.x < P[3])) root1 = 2;
+                if (!(P[4] < q1.y && q1.y < P[5])) root1 = 2;
+                if (!(P[6] < q1.z && q1.z < P[7])) root1 = 2;
+            }
+            if (root1 < tol) root1 = 2;
+            if (root2 < tol) root2 = 2;
+            if (root1 > root2) root1 = root2;
+            if (root1 > 1) return RPX_NO_HIT;
+            return root1 * mag(Sv);
+        }
+        case RPX_FACE_SADDLE: {  // :1439-1495
+            double A = sqrt(6.0), root, denom, a1, a2;
+            A *= P[1];
+            vec3 p = p1;
+            p.z -= P[0];
+            vec3 d = p2 - p1;
+            if (d.x == 0.0) {
+                a1 = (-A * (p.x * p.y) + p.z) / (A * d.y * p.x - d.z);
+                a2 = RPX_INF;
+            } else if (d.y == 0.0) {
+                a1 = (-A * (p.x * p.y) + p.z) / (A * d.x * p.y - d.z);
+                a2 = RPX_INF;
+            } else {
+                double A2 = A * A;
+                root = A2 * (d.x * d.x) * (p.y * p.y) - 2 * A2 * d.x * d.y * p.x * p.y +
+                       A2 * (d.y * d.y) * (p.x * p.x) + 4 * A * d.x * d.y * p.z - 2 * A * d.x * d.z * p.y -
+                       2 * A * d.y * d.z * p.x + d.z * d.z;
+                if (root < 0) return RPX_NO_HIT;
+                root = sqrt(root);
+                denom = 2 * A * (d.x * d.y);
+                a1 = a2 = -A * d.x * p.y - A * d.y * p.x + d.z;
+                a1 += root;
+                a2 -= root;
+                a1 /= denom;
+                a2 /= denom;
+            }
+            vec3 pt1 = p1 + d * a1;
+            vec3 pt2 = p1 + d * a2;
+            if (a1 < 0.0) a1 = RPX_INF;
+            if (a2 < 0.0) a2 = RPX_INF;
+            if (is_base_ray) {
+                if (!shape_inside(S, f, pt1.x, pt1.y)) a1 = RPX_INF;
+                if (!shape_inside(S, f, pt2.x, pt2.y)) a2 = RPX_INF;
+            }
+            if (a2 < a1) a1 = a2;
+            if (a1 > 1.0 || a1 < tol) return RPX_NO_HIT;
+            return a1 * sep(p1, p2);
+        }
+        case RPX_FACE_CYLINDRICAL: {  // :1526-1584
+            double R = P[1];
+            double R2 = R * R;
+            vec3 o = p1;
+            o.z -= P[0];
+            vec3 d = p2 - p1;
+            double ox2 = o.x * o.x, oz2 = o.z * o.z, dx2 = d.x * d.x, dz2 = d.z * d.z;
+            double root = R2 * dz2 - 2 * R * dx2 * o.z + 2 * R * d.x * d.z * o.x - dx2 * oz2 +
+                          2 * d.x * d.z * o.x * o.z - dz2 * ox2;
+            if (root < 0) return RPX_NO_HIT;
+            root = sqrt(root);
+            double denom = dx2 + dz2;
+            double a1, a2;
+            a1 = a2 = -R * d.z - d.x * o.x - d.z * o.z;
+            a1 += root;
+            a2 -= root;
+            a1 /= denom;
+            a2 /= denom;
+            vec3 pt1 = p1 + d * a1;
+            vec3 pt2 = p1 + d * a2;
+            double cz = P[0] - P[1];
+            if (R >= 0) {
+                if (pt1.z < cz) a1 = RPX_INF;
+                if (pt2.z < cz) a2 = RPX_INF;
+            } else {
+                if (pt1.z > cz) a1 = RPX_INF;
+                if (pt2.z > cz) a2 = RPX_INF;
+            }
+            if (is_base_ray) {
+                if (!shape_inside(S, f, pt1.x, pt1.y)) a1 = RPX_INF;
+                if (!shape_inside(S, f, pt2.x, pt2.y)) a2 = RPX_INF;
+            }
+            if (a2 < a1) a1 = a2;
+            if (a1 > 1.0 || a1 < tol) return RPX_NO_HIT;
+            return a1 * sep(p1, p2);
+        }
+        case RPX_FACE_AXICON: {  // :1621-1675
+            double beta = P[1];
+            vec3 d = p2 - p1;
+            vec3 o = p1;
+            o.z -= P[0];
+            double beta2 = beta * beta;
+            double ox2 = o.x * o.x, oy2 = o.y * o.y, oz2 = o.z * o.z;
+            double dx2 = d.x * d.x, dy2 = d.y * d.y, dz2 = d.z * d.z;
+            double root = -beta2 * dx2 * oy2 + 2 * beta2 * d.x * d.y * o.x * o.y - beta2 * dy2 * ox2 +
+                          dx2 * oz2 - 2 * d.x * d.z * o.x * o.z + dy2 * oz2 - 2 * d.y * d.z * o.y * o.z +
+                          dz2 * ox2 + dz2 * oy2;
+            double denom = (beta2 * dx2 + beta2 * dy2 - dz2);
+            if (root < 0) return RPX_NO_HIT;
+            root = beta * sqrt(root);
+            double a1 = -beta2 * d.x * o.x - beta2 * d.y * o.y + d.z * o.z;
+            double a2 = a1 + root;
+            a1 -= root;
+            a1 /= denom;
+            a2 /= denom;
+            vec3 pt1 = p1 + d * a1;
+            vec3 pt2 = p1 + d * a2;
+            if (pt1.z > P[0]) a1 = RPX_INF;
+            if (pt2.z > P[0]) a2 = RPX_INF;
+            if (is_base_ray) {
+                if (!shape_inside(S, f, pt1.x, pt1.y)) a1 = RPX_INF;
+                if (!shape_inside(S, f, pt2.x, pt2.y)) a2 = RPX_INF;
+            }
+            if (a2 < a1) a1 = a2;
+            if (a1 > 1.0 || a1 < tol) return RPX_NO_HIT;
+            return a1 * sep(p1, p2);
+        }
+        case RPX_FACE_CONIC: {  // :1767-1798
+            vec3 d = p2 - p1;
+            vec3 a = p1;
+            a.z -= P[1];
+            double a1 = intersect_conic(a, d, P[0], P[2]);
+            vec3 pt1 = a + d * a1;
+            if (is_base_ray && !shape_inside(S, f, pt1.x, pt1.y)) return RPX_NO_HIT;
+            if (a1 > 1.0 || a1 < tol) return RPX_NO_HIT;
+            return a1 * sep(p1, p2);
+        }
+        case RPX_FACE_ASPHERIC: {  // :1909-1976, Newton on alpha
+            double atol2 = P[11] * P[11];
+            vec3 d = p2 - p1;
+            vec3 a = p1;
+            a.z -= P[1];
+            double a1 = intersect_conic(a, d, P[0], P[2]);
+            Aspheric A;
+            A.R = -P[0];
+            A.beta = 1 + P[2];
+            A.A4 = P[4]; A.A6 = P[5]; A.A8 = P[6]; A.A10 = P[7];
+            A.A12 = P[8]; A.A14 = P[9]; A.A16 = P[10];
+            A.a = a;
+            A.d = d;
+            double fv, f_last, g, dz;
+            aspheric_f_df(A, a1, &fv, &g);
+            f_last = fv;
+            dz = -fv / g;
+            bool converged = false;
+            for (int i = 0; i < 100; i++) {
+                a1 += dz;
+                if (dz * dz < atol2) { converged = true; break; }
+                aspheric_f_df(A, a1, &fv, &g);
+                if (fabs(fv) > fabs(f_last)) return RPX_NO_HIT;
+                f_last = fv;
+                dz = -fv / g;
+            }
+            if (!converged) return RPX_NO_HIT;
+            vec3 pt1 = a + d * a1;
+            if (is_base_ray && !shape_inside(S, f, pt1.x, pt1.y)) return RPX_NO_HIT;
+            if (a1 > 1.0 || a1 < tol) return RPX_NO_HIT;
+            return a1 * sep(p1, p2);
+        }
+        case RPX_FACE_EXT_POLY: {  // :2186-2237
+            const double* E = S.pool + f->aux_off;
+            double atol2 = P[4] * P[4];
+            vec3 d = p2 - p1;
+            vec3 a = p1;
+            a.z -= P[3];
+            double a1 = intersect_conic(a, d, -P[0], P[1] - 1.0);
+            double fv, f_last, g, dz;
+            extpoly_f_df(f, E, p1, d, a1, &fv, &g);
+            f_last = fv;
+            dz = -fv / g;
+            bool converged = false;
+            for (int i = 0; i < 100; i++) {
+                a1 += dz;
+                if (dz * dz < atol2) { converged = true; break; }
+                extpoly_f_df(f, E, p1, d, a1, &fv, &g);
+                if (fabs(fv) > fabs(f_last)) return RPX_NO_HIT;
+                f_last = fv;
+                dz = -fv / g;
+            }
+            if (!converged) return RPX_NO_HIT;
+            vec3 pt1 = a + d * a1;
+            if (is_base_ray && !shape_inside(S, f, pt1.x, pt1.y)) return RPX_NO_HIT;
+            if (a1 > 1.0 || a1 < tol) return RPX_NO_HIT;
+            return a1 * sep(p1, p2);
+        }
+        default: return RPX_NO_HIT;
+    }
+}
+
+// Face.compute_normal_c (local coordinates) for the non-wrapping classes
+__device__ vec3 face_normal_basic(const DevScene& S, const rpx_face* f, vec3 p) {
+    const double* P = f->p;
+    switch (f->type) {
+        case RPX_FACE_CIRCULAR: return v3(0, 0, P[3] != 0.0 ? 1 : -1);
+        case RPX_FACE_SHAPED_PLANAR: return v3(0, 0, 1);
+        case RPX_FACE_IMPLICIT_PLANAR: return ld3(P + 3);
+        case RPX_FACE_ELLIPTICAL_PLANE: return norm(v3(P[0], P[1], -1));
+        case RPX_FACE_RECTANGULAR: return v3(0, 0, -1);
+        case RPX_FACE_SPHERICAL:
+        case RPX_FACE_SHAPED_SPHERICAL: {
+            double curvature = (f->type == RPX_FACE_SPHERICAL) ? P[1] : P[0];
+            double z_height = (f->type == RPX_FACE_SPHERICAL) ? P[2] : P[1];
+            p.z -= (z_height - curvature);
+            if (curvature < 0) p = neg(p);
+            return norm(p);
+        }
+        case RPX_FACE_EXTRUDED_PLANAR: return ld3(P + 6);
+        case RPX_FACE_POLYGON: return v3(0, 0, -1);
+        case RPX_FACE_ORIENTED_POLYGON: return ld3(P + 3);
+        case RPX_FACE_OFFAXIS_PARABOLIC: {
+            double A = 1 / (2 * P[0]);
+            double m2 = p.x * p.x + p.y * p.y;
+            double B = 4 * m2 * A * A;
+            double dz = -sqrt(B / (B + 1));
+            m2 = sqrt(m2);
+            return v3(-(dz * p.x) / m2, -(dz * p.y) / m2, -1 / sqrt(B + 1));
+        }
+        case RPX_FACE_ELLIPSOIDAL: {
+            const double* T = S.pool + f->aux_off;
+            p = transform_pt(T, p);
+            vec3 n = v3(p.x / -(P[0] * P[0]), p.y / -(P[1] * P[1]), p.z / -(P[1] * P[1]));
+            n = rotate_v(T + 12, n);
+            return norm(n);
+        }
+        case RPX_FACE_SADDLE: {
+            double rt6 = sqrt(6.0) * P[1];
+            return norm(v3(-rt6 * p.y, -rt6 * p.x, 1.0));
+        }
+        case RPX_FACE_CYLINDRICAL: {
+            p.z -= (P[0] - P[1]);
+            if (P[1] < 0) { p.z = -p.z; p.x = -p.x; }
+            p.y = 0;
+            return norm(p);
+        }
+        case RPX_FACE_AXICON: {
+            double beta = P[1];
+            double r = sqrt(p.x * p.x + p.y * p.y);
+            return v3(beta * p.x / r, beta * p.y / r, 1.0);
+        }
+        case RPX_FACE_CONIC: {
+            double R = -P[0], beta = 1 + P[2];
+            int sign = (P[3] != 0.0) ? -1 : 1;
+            p.z -= P[1];
+            vec3 g = v3(-p.x * 2 * beta, -p.y * 2 * beta, 2 * beta * (R - beta * p.z));
+            if ((R * beta) < 0) sign *= -1;
+            return norm(g * (double)sign);
+        }
+        case RPX_FACE_ASPHERIC: {
+            double R = -P[0], beta = 1 + P[2];
+            int sign = (P[3] != 0.0) ? -1 : 1;
+            p.z -= P[1];
+            double r2 = p.x * p.x + p.y * p.y;
+            double r4 = r2 * r2, r6 = r4 * r2, r8 = r4 * r4, r10 = r8 * r2, r12 = r8 * r4, r14 = r8 * r6;
+            double root = sqrt(1 - (beta * (r2) / (R * R)));
+            double df = 10 * P[7] * r8 + 8 * P[6] * r6 + 6 * P[5] * r4 + 4 * P[4] * r2;
+            df += 16 * P[10] * r14 + 14 * P[9] * r12 + 12 * P[8] * r10;
+            df += 2 / (R * (1 + root));
+            df += beta * (r2) / ((R * R * R) * root * ((1 + root) * (1 + root)));
+            vec3 g = v3(-df * p.x, -df * p.y, 1.0);
+            return norm(g * (double)sign);
+        }
+        case RPX_FACE_EXT_POLY: {
+            const double* E = S.pool + f->aux_off;
+            int Nx = f->aux_n, Ny = f->aux_m;
+            double R = P[0], beta = P[1];
+            bool inv = (P[5] != 0.0);
+            int sign = inv ? -1 : 1;
+            double inv_rad = 1. / P[2];
+            double x = p.x * inv_rad, y = p.y * inv_rad;
+            p.z -= P[3];
+            vec3 g = v3(-p.x * 2 * beta, -p.y * 2 * beta, 2 * beta * (R - beta * p.z));
+            if ((R * beta) < 0) sign *= -1;
+            g = norm(g * (double)sign);
+            double sx = 0.0, sy = 0.0;  // accumulated in the reference's term order
+            double pm = inv ? 1.0 : -1.0;
+            double xim1 = 1.0;
+            for (int i = 1; i < Nx; i++) {
+                double yj = 1.0;
+                for (int j = 0; j < Ny; j++) {
+                    g.x += pm * (i * E[i * Ny + j] * inv_rad * xim1 * yj);
+                    yj *= y;
+                }
+                xim1 *= x;
+            }
+            double xi = 1.0;
+            for (int i = 0; i < Nx; i++) {
+                double yjm1 = 1.0;
+                for (int j = 1; j < Ny; j++) {
+                    g.y += pm * (j * E[i * Ny + j] * inv_rad * xi * yjm1);
+                    yjm1 *= y;
+                }
+                xi *= x;
+            }
+            (void)sx; (void)sy;
+            return norm(g);
+        }
+        default: return p;
+    }
+}
+
+// DistortionFace.intersect_c, cfaces.pyx:2339-2416: base intersection, then a
+// tangent-plane secant iteration on the distorted surface (<= 20 steps).
+__device__ __noinline__ double distortion_intersect(const DevScene& S, const rpx_face* f, vec3 p1, vec3 p2) {
+    const rpx_face* base = &S.faces[f->base_face];
+    const rpx_distortion* dist = &S.dists[f->aux_off];
+    double h = sep(p2, p1);
+    double tolerance = f->p[0];
+    double a2 = face_intersect_basic(S, base, p1, p2, 0);
+    if (a2 > h || a2 < f->tolerance) return RPX_NO_HIT;
+    vec3 d = p2 - p1;
+    vec3 pt1 = p1 + d * (a2 / h);
+    vec3 dxdyz = distortion_zgrad(S, dist, pt1.x, pt1.y);
+    vec3 n = face_normal_basic(S, base, pt1);
+    pt1.z += dxdyz.z;
+    n.x /= n.z;
+    n.y /= n.z;
+    n.x -= dxdyz.x;
+    n.y -= dxdyz.y;
+    vec3 o = p1 - pt1;
+    double a1 = -h * dot(o, n) / dot(d, n);
+    if (a1 < fabs(dxdyz.z)) return RPX_NO_HIT;
+    for (int i = 0; i < 20; i++) {
+        pt1 = p1 + d * (a1 / h);
+        if (fabs(a1 - a2) < tolerance) break;
+        double z_shift = distortion_z(S, dist, pt1.x, pt1.y);
+        vec3 q1 = p1, q2 = p2;
+        q1.z -= z_shift;
+        q2.z -= z_shift;
+        a2 = face_intersect_basic(S, base, q1, q2, 0);
+        pt1 = q1 + d * (a2 / h);
+        n = face_normal_basic(S, base, pt1);
+        dxdyz = distortion_zgrad(S, dist, pt1.x, pt1.y);
+        pt1.z += dxdyz.z;
+        n.x /= n.z;
+        n.y /= n.z;
+        n.x -= dxdyz.x;
+        n.y -= dxdyz.y;
+        o = p1 - pt1;
+        a2 = a1;
+        a1 = -h * dot(o, n) / dot(d, n);
+    }
+    if (!shape_inside(S, f, pt1.x, pt1.y)) return RPX_NO_HIT;  // Q7: even for parabasal rays
+    return a1;
+}
+
+RPX_DEV double face_intersect(const DevScene& S, const rpx_face* f, vec3 p1, vec3 p2, int is_base_ray) {
+    if (f->type == RPX_FACE_DISTORTION) return distortion_intersect(S, f, p1, p2);
+    return face_intersect_basic(S, f, p1, p2, is_base_ray);
+}
+
+__device__ vec3 face_normal(const DevScene& S, const rpx_face* f, vec3 p) {
+    if (f->type == RPX_FACE_DISTORTION) {  // cfaces.pyx:2418-2431
+        const rpx_face* base = &S.faces[f->base_face];
+        const rpx_distortion* dist = &S.dists[f->aux_off];
+        vec3 dxdyz = distortion_zgrad(S, dist, p.x, p.y);
+        vec3 p1 = p;
+        p1.z -= dxdyz.z;
+        vec3 n = face_normal_basic(S, base, p1);
+        n.x /= n.z;
+        n.y /= n.z;
+        n.z = 1.0;
+        n.x -= dxdyz.x;
+        n.y -= dxdyz.y;
+        return norm(n);
+    }
+    return face_normal_basic(S, f, p);
+}
+
+RPX_DEV vec3 face_tangent(const rpx_face* f) {
+    if (f->type == RPX_FACE_EXTRUDED_PLANAR) return v3(0.0, 0.0, 1.0);  // cfaces.pyx:704-709
+    if (f->type == RPX_FACE_ORIENTED_POLYGON) return ld3(f->p + 6);     // :1186-1187
+    return v3(1.0, 0.0, 0.0);                                           // ctracer.pyx:1786-1791
+}
+
+// FaceList.compute_orientation_c, ctracer.pyx:1939-1953
+RPX_DEV void compute_orientation(const DevScene& S, const rpx_face* f, vec3 point, vec3* normal,
+                                 vec3* tangent) {
+    const rpx_face_set* fs = &S.sets[f->face_set];
+    point = transform_pt(fs->inv_trans.m, point);
+    vec3 n = face_normal(S, f, point);
+    vec3 t = face_tangent(f);
+    if (f->invert_normal) {
+        n = neg(n);
+        t = neg(t);
+    }
+    *normal = rotate_v(fs->trans.m, n);
+    *tangent = rotate_v(fs->trans.m, t);
+}
+
+}  // namespace rpx

@@ -1,0 +1,413 @@
+// rpx_kernels.cuh -- the wavefront tracer kernels of librpx (sm_100a).
+//
+// One generation of rays = two kernels:
+//   k_intersect : ray-parallel nearest-hit search over the face table (staged in shared
+//                 memory).  Reads origin+direction (48 B/ray, coalesced SoA), writes the
+//                 parent write-back the reference performs (length f64 + end_face_idx u32).
+//   k_shade     : orientation + material evaluation + ORDERED child emission.  Children
+//                 must appear in parent order, reflected before transmitted
+//                 (ctracer.pyx:2084-2117 appends in loop order), so the kernel does a
+//                 block-level exclusive scan of the child counts and a decoupled
+//                 look-back across tiles (single pass, no second read of the parents,
+//                 no staging copy of the children).
+// Replaces trace_segment_c (ctracer.pyx:2062-2118) and trace_gausslet_c +
+// trace_parabasal_rays (ctracer.pyx:2214-2281, 2350-2385).
+#pragma once
+#include "rpx_materials.cuh"
+
+namespace rpx {
+
+// ------------------------------------------------------------------ SoA layout
+// f[field * cap + i] (doubles), u[field * cap + i] (u32), p[(j*10 + c) * cap + i] (para)
+enum {
+    F_OX = 0, F_OY, F_OZ, F_DX, F_DY, F_DZ, F_NX, F_NY, F_NZ, F_EX, F_EY, F_EZ,
+    F_NR, F_NI, F_E1R, F_E1I, F_E2R, F_E2I, F_LEN, F_PHASE, F_APATH, NF = 21
+};
+enum { U_WL = 0, U_PARENT, U_ENDFACE, U_IDENT, U_TYPE, NU = 5 };
+enum { P_OX = 0, P_DX = 3, P_NX = 6, P_LEN = 9, NPF = 10, NP = 60 };
+
+struct Soa {
+    double* f;
+    uint32_t* u;
+    double* p;  // nullptr for plain rays
+    unsigned long long n, cap;
+};
+
+#define RPX_TILE 256
+#define RPX_WORDS_RAY 47        // 188 / 4
+#define RPX_WORDS_GAUSSLET 167  // 668 / 4
+
+// ------------------------------------------------------------------ AoS <-> SoA
+// The host-visible records are packed (4-byte aligned) 188 / 668-byte structs.  A tile
+// of records is moved through shared memory as 32-bit words: global side fully
+// coalesced, shared side stride 47 / 167 words (odd -> conflict free).
+template <int WORDS, int TILE>
+__global__ void __launch_bounds__(TILE) k_aos_to_soa(const uint32_t* __restrict__ aos, Soa out) {
+    extern __shared__ uint32_t sm[];
+    const unsigned long long base = (unsigned long long)blockIdx.x * TILE;
+    const unsigned long long n = out.n;
+    const int cnt = (int)min((unsigned long long)TILE, n - base);
+    const uint32_t* src = aos + base * WORDS;
+    for (int w = threadIdx.x; w < cnt * WORDS; w += TILE) sm[w] = src[w];
+    __syncthreads();
+    const int t = threadIdx.x;
+    if (t >= cnt) return;
+    const unsigned long long i = base + t;
+    const uint32_t* rec = sm + t * WORDS;
+#pragma unroll
+    for (int k = 0; k < NF; k++) {
+        uint2 v = make_uint2(rec[2 * k], rec[2 * k + 1]);
+        out.f[k * out.cap + i] = __hiloint2double((int)v.y, (int)v.x);
+    }
+#pragma unroll
+    for (int k = 0; k < NU; k++) out.u[k * out.cap + i] = rec[2 * NF + k];
+    if (WORDS == RPX_WORDS_GAUSSLET) {
+#pragma unroll 4
+        for (int k = 0; k < NP; k++) {
+            uint2 v = make_uint2(rec[RPX_WORDS_RAY + 2 * k], rec[RPX_WORDS_RAY + 2 * k + 1]);
+            out.p[k * out.cap + i] = __hiloint2double((int)v.y, (int)v.x);
+        }
+    }
+}
+
+template <int WORDS, int TILE>
+__global__ void __launch_bounds__(TILE) k_soa_to_aos(Soa in, uint32_t* __restrict__ aos) {
+    extern __shared__ uint32_t sm[];
+    const unsigned long long base = (unsigned long long)blockIdx.x * TILE;
+    const unsigned long long n = in.n;
+    const int cnt = (int)min((unsigned long long)TILE, n - base);
+    const int t = threadIdx.x;
+    if (t < cnt) {
+        const unsigned long long i = base + t;
+        uint32_t* rec = sm + t * WORDS;
+#pragma unroll
+        for (int k = 0; k < NF; k++) {
+            double v = in.f[k * in.cap + i];
+            rec[2 * k] = (uint32_t)__double2loint(v);
+            rec[2 * k + 1] = (uint32_t)__double2hiint(v);
+        }
+#pragma unroll
+        for (int k = 0; k < NU; k++) rec[2 * NF + k] = in.u[k * in.cap + i];
+        if (WORDS == RPX_WORDS_GAUSSLET) {
+#pragma unroll 4
+            for (int k = 0; k < NP; k++) {
+                double v = in.p[k * in.cap + i];
+                rec[RPX_WORDS_RAY + 2 * k] = (uint32_t)__double2loint(v);
+                rec[RPX_WORDS_RAY + 2 * k + 1] = (uint32_t)__double2hiint(v);
+            }
+        }
+    }
+    __syncthreads();
+    uint32_t* dst = aos + base * WORDS;
+    for (int w = threadIdx.x; w < cnt * WORDS; w += TILE) dst[w] = sm[w];
+}
+
+// reset_length_c for generation 0 of a gausslet trace (ctracer.pyx:1239-1245)
+__global__ void k_reset_length(Soa rays, double max_length) {
+    unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= rays.n) return;
+    rays.f[F_LEN * rays.cap + i] = max_length;
+    if (rays.p) {
+#pragma unroll
+        for (int j = 0; j < RPX_NPARA; j++) rays.p[(j * NPF + P_LEN) * rays.cap + i] = max_length;
+    }
+}
+
+// ------------------------------------------------------------------ scene staging
+// Copy the face table and the face-set transforms into shared memory and re-point the
+// DevScene at them.  Falls back to global memory when the scene does not fit.
+RPX_DEV void stage_scene(DevScene& S, unsigned char* smem, int smem_bytes) {
+    const int face_bytes = S.n_faces * (int)sizeof(rpx_face);
+    const int set_bytes = S.n_sets * (int)sizeof(rpx_face_set);
+    if (face_bytes + set_bytes > smem_bytes) return;  // uniform across the grid
+    uint32_t* dst = reinterpret_cast<uint32_t*>(smem);
+    const uint32_t* srcf = reinterpret_cast<const uint32_t*>(S.faces);
+    const uint32_t* srcs = reinterpret_cast<const uint32_t*>(S.sets);
+    const int fw = face_bytes / 4, sw = set_bytes / 4;
+    for (int w = threadIdx.x; w < fw; w += blockDim.x) dst[w] = srcf[w];
+    for (int w = threadIdx.x; w < sw; w += blockDim.x) dst[fw + w] = srcs[w];
+    __syncthreads();
+    S.faces = reinterpret_cast<const rpx_face*>(smem);
+    S.sets = reinterpret_cast<const rpx_face_set*>(smem + face_bytes);
+}
+
+// ------------------------------------------------------------------ k_intersect
+// FaceList.intersect_c over every face set (ctracer.pyx:1882-1904, 2093-2104): the
+// sequential strict-< update keeps the LOWEST face index on equal distances (quirk Q2);
+// the running (distance, face) pair lives in two registers.
+__global__ void __launch_bounds__(RPX_TILE)
+k_intersect(DevScene S, Soa rays, double max_length, int smem_bytes) {
+    extern __shared__ __align__(16) unsigned char smem[];
+    stage_scene(S, smem, smem_bytes);
+    const unsigned long long i = (unsigned long long)blockIdx.x * RPX_TILE + threadIdx.x;
+    if (i >= rays.n) return;
+    const unsigned long long cap = rays.cap;
+    vec3 o = v3(rays.f[F_OX * cap + i], rays.f[F_OY * cap + i], rays.f[F_OZ * cap + i]);
+    vec3 d = v3(rays.f[F_DX * cap + i], rays.f[F_DY * cap + i], rays.f[F_DZ * cap + i]);
+    vec3 point = o + d * max_length;
+    double best = max_length;  // ray.length = max_length (ctracer.pyx:2086)
+    uint32_t best_face = RPX_NO_FACE;
+    for (int s = 0; s < S.n_sets; s++) {
+        const rpx_face_set* fs = &S.sets[s];
+        vec3 p1 = transform_pt(fs->inv_trans.m, o);
+        vec3 p2 = transform_pt(fs->inv_trans.m, point);
+        for (int fi = fs->face_begin; fi < fs->face_end; fi++) {
+            const rpx_face* f = &S.faces[fi];
+            double dist = face_intersect(S, f, p1, p2, 1);
+            if (f->tolerance < dist && dist < best) {
+                best = dist;
+                best_face = (uint32_t)fi;
+            }
+        }
+    }
+    rays.f[F_LEN * cap + i] = best;
+    rays.u[U_ENDFACE * cap + i] = best_face;
+}
+
+// ------------------------------------------------------------------ ordered emission
+// tile_state word: bits 63..62 = flag (1 aggregate, 2 inclusive prefix), low 62 = value
+#define RPX_FLAG_AGG (1ull << 62)
+#define RPX_FLAG_PREFIX (2ull << 62)
+#define RPX_VAL_MASK ((1ull << 62) - 1)
+
+RPX_DEV unsigned long long ld_relaxed(const unsigned long long* p) {
+    unsigned long long v;
+    asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+RPX_DEV void st_relaxed(unsigned long long* p, unsigned long long v) {
+    asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+
+// Exclusive scan of per-thread counts over the block; returns this thread's offset and
+// the block total.  256 threads = 8 warps.
+RPX_DEV uint32_t block_exclusive_scan(uint32_t v, uint32_t* total, uint32_t* s_warp) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    uint32_t incl = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += t;
+    }
+    if (lane == 31) s_warp[warp] = incl;
+    __syncthreads();
+    uint32_t woff = 0, tot = 0;
+#pragma unroll
+    for (int w = 0; w < RPX_TILE / 32; w++) {
+        uint32_t s = s_warp[w];
+        if (w < warp) woff += s;
+        tot += s;
+    }
+    *total = tot;
+    return woff + incl - v;
+}
+
+// Decoupled look-back (one warp): publish this tile's aggregate, then walk back over the
+// predecessors 32 at a time until an inclusive prefix is found.  Tiles take their index
+// from an atomic ticket, so every predecessor is already resident or finished.
+RPX_DEV unsigned long long tile_exclusive_prefix(unsigned long long* state, uint32_t tile,
+                                                 uint32_t total) {
+    const int lane = threadIdx.x & 31;
+    if (tile == 0) {
+        if (lane == 0) st_relaxed(&state[0], RPX_FLAG_PREFIX | (unsigned long long)total);
+        return 0;
+    }
+    if (lane == 0) st_relaxed(&state[tile], RPX_FLAG_AGG | (unsigned long long)total);
+    unsigned long long excl = 0;
+    long long t0 = (long long)tile - 1;  // predecessor inspected by lane 0
+    while (true) {
+        const long long t = t0 - lane;
+        const bool valid = (t >= 0);
+        unsigned long long s = 0;
+        if (valid) {
+            do {
+                s = ld_relaxed(&state[t]);
+            } while ((s >> 62) == 0);
+        }
+        const unsigned pref = __ballot_sync(0xffffffffu, valid && ((s >> 62) == 2));
+        unsigned long long v = valid ? (s & RPX_VAL_MASK) : 0ull;
+        if (pref) {
+            const int first = __ffs(pref) - 1;  // nearest predecessor holding a full prefix
+            if (lane > first) v = 0;
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        excl += v;
+        if (pref) break;  // tile 0 always publishes a prefix, so this is always reached
+        t0 -= 32;
+    }
+    if (lane == 0) st_relaxed(&state[tile], RPX_FLAG_PREFIX | (excl + total));
+    return excl;
+}
+
+RPX_DEV void write_child_base(const Soa& out, unsigned long long pos, const Kids& k, const Kid& c,
+                              uint32_t wl, uint32_t parent, uint32_t ident) {
+    const unsigned long long cap = out.cap;
+    double* f = out.f + pos;
+    f[F_OX * cap] = k.origin.x;
+    f[F_OY * cap] = k.origin.y;
+    f[F_OZ * cap] = k.origin.z;
+    f[F_DX * cap] = c.dir.x;
+    f[F_DY * cap] = c.dir.y;
+    f[F_DZ * cap] = c.dir.z;
+    f[F_NX * cap] = k.normal.x;
+    f[F_NY * cap] = k.normal.y;
+    f[F_NZ * cap] = k.normal.z;
+    f[F_EX * cap] = k.evec.x;
+    f[F_EY * cap] = k.evec.y;
+    f[F_EZ * cap] = k.evec.z;
+    f[F_NR * cap] = c.n.re;
+    f[F_NI * cap] = c.n.im;
+    f[F_E1R * cap] = c.e1.re;
+    f[F_E1I * cap] = c.e1.im;
+    f[F_E2R * cap] = c.e2.re;
+    f[F_E2I * cap] = c.e2.im;
+    // F_LEN / U_ENDFACE are written by k_intersect when this generation is traced
+    f[F_PHASE * cap] = k.phase;
+    f[F_APATH * cap] = k.apath;
+    uint32_t* u = out.u + pos;
+    u[U_WL * cap] = wl;
+    u[U_PARENT * cap] = parent;
+    u[U_IDENT * cap] = ident;
+    u[U_TYPE * cap] = c.type;
+}
+
+// ------------------------------------------------------------------ k_shade
+template <bool GAUSS>
+__global__ void __launch_bounds__(RPX_TILE)
+k_shade(DevScene S, Soa in, Soa out, double max_length, unsigned long long* tile_state,
+        uint32_t* tile_counter, unsigned long long* d_count, uint32_t* face_counts, uint32_t n_tiles,
+        int smem_bytes) {
+    extern __shared__ __align__(16) unsigned char smem[];
+    __shared__ uint32_t s_tile;
+    __shared__ uint32_t s_warp[RPX_TILE / 32];
+    __shared__ unsigned long long s_prefix;
+    if (threadIdx.x == 0) s_tile = atomicAdd(tile_counter, 1u);
+    stage_scene(S, smem, smem_bytes);  // contains a __syncthreads() when it stages
+    __syncthreads();
+    const uint32_t tile = s_tile;
+    const unsigned long long i = (unsigned long long)tile * RPX_TILE + threadIdx.x;
+    const unsigned long long cap = in.cap;
+
+    Kids k;
+    k.has_a = false;
+    k.has_b = false;
+    uint32_t wl = 0, ident = 0;
+    uint32_t face_idx = RPX_NO_FACE;
+    double plen[RPX_NPARA];
+    bool hit = false;
+    if (i < in.n) {
+        face_idx = in.u[U_ENDFACE * cap + i];
+        hit = (face_idx != RPX_NO_FACE);
+    }
+    if (hit) {
+        RayIn r;
+        r.o = v3(in.f[F_OX * cap + i], in.f[F_OY * cap + i], in.f[F_OZ * cap + i]);
+        r.d = v3(in.f[F_DX * cap + i], in.f[F_DY * cap + i], in.f[F_DZ * cap + i]);
+        r.e = v3(in.f[F_EX * cap + i], in.f[F_EY * cap + i], in.f[F_EZ * cap + i]);
+        r.n = cx(in.f[F_NR * cap + i], in.f[F_NI * cap + i]);
+        r.e1 = cx(in.f[F_E1R * cap + i], in.f[F_E1I * cap + i]);
+        r.e2 = cx(in.f[F_E2R * cap + i], in.f[F_E2I * cap + i]);
+        r.len = in.f[F_LEN * cap + i];
+        r.phase = in.f[F_PHASE * cap + i];
+        r.apath = in.f[F_APATH * cap + i];
+        r.wl = wl = in.u[U_WL * cap + i];
+        r.ident = ident = in.u[U_IDENT * cap + i];
+        r.type = in.u[U_TYPE * cap + i];
+        const rpx_face* face = &S.faces[face_idx];
+        {  // face.count += 1 (ctracer.pyx:2108), aggregated per warp and face
+            const unsigned peers = __match_any_sync(__activemask(), face_idx);
+            if ((int)(threadIdx.x & 31) == __ffs(peers) - 1)
+                atomicAdd(&face_counts[face_idx], (uint32_t)__popc(peers));
+        }
+        vec3 point = r.o + r.d * r.len;
+        vec3 onormal, otangent;
+        compute_orientation(S, face, point, &onormal, &otangent);
+        material_eval(S, &S.mats[face->material], r, point, onormal, otangent, k);
+
+        if (GAUSS) {
+            // trace_parabasal_rays, first loop (ctracer.pyx:2363-2373): every parabasal ray
+            // must hit the SAME face (is_base_ray = 0); any miss drops the children (Q16).
+            const rpx_face_set* fs = &S.sets[face->face_set];
+            bool ok = true;
+#pragma unroll
+            for (int j = 0; j < RPX_NPARA; j++) {
+                plen[j] = max_length;
+                if (ok) {
+                    const double* pp = in.p + (unsigned long long)(j * NPF) * cap + i;
+                    vec3 po = v3(pp[(P_OX + 0) * cap], pp[(P_OX + 1) * cap], pp[(P_OX + 2) * cap]);
+                    vec3 pd = v3(pp[(P_DX + 0) * cap], pp[(P_DX + 1) * cap], pp[(P_DX + 2) * cap]);
+                    vec3 ray_end = po + pd * max_length;
+                    vec3 p1 = transform_pt(fs->inv_trans.m, po);
+                    vec3 p2 = transform_pt(fs->inv_trans.m, ray_end);
+                    double dist = face_intersect(S, face, p1, p2, 0);
+                    if (face->tolerance < dist && dist < max_length) {
+                        plen[j] = dist;
+                        in.p[(unsigned long long)(j * NPF + P_LEN) * cap + i] = dist;  // parent write-back
+                    } else {
+                        ok = false;
+                    }
+                }
+            }
+            if (!ok) {
+                k.has_a = false;
+                k.has_b = false;
+            }
+        }
+    }
+
+    const uint32_t cnt = (k.has_a ? 1u : 0u) + (k.has_b ? 1u : 0u);
+    uint32_t total;
+    const uint32_t local = block_exclusive_scan(cnt, &total, s_warp);
+    if (threadIdx.x < 32) {
+        unsigned long long excl = tile_exclusive_prefix(tile_state, tile, total);
+        if (threadIdx.x == 0) {
+            s_prefix = excl;
+            if (tile == n_tiles - 1) *d_count = excl + total;  // len(new_rays)
+        }
+    }
+    __syncthreads();
+    if (cnt == 0) return;
+    unsigned long long pos = s_prefix + local;
+    const uint32_t parent = (uint32_t)i;
+    unsigned long long pos_a = pos, pos_b = pos + (k.has_a ? 1u : 0u);
+    if (k.has_a) write_child_base(out, pos_a, k, k.a, wl, parent, ident);
+    if (k.has_b) write_child_base(out, pos_b, k, k.b, wl, parent, ident);
+
+    if (GAUSS) {
+        // trace_parabasal_rays, second loop (ctracer.pyx:2375-2385) + reset_length_c (:2280)
+        const rpx_face* face = &S.faces[face_idx];
+        const rpx_material* M = &S.mats[face->material];
+        const unsigned long long ocap = out.cap;
+        if (k.has_a) out.f[F_LEN * ocap + pos_a] = max_length;
+        if (k.has_b) out.f[F_LEN * ocap + pos_b] = max_length;
+#pragma unroll
+        for (int j = 0; j < RPX_NPARA; j++) {
+            const double* pp = in.p + (unsigned long long)(j * NPF) * cap + i;
+            vec3 po = v3(pp[(P_OX + 0) * cap], pp[(P_OX + 1) * cap], pp[(P_OX + 2) * cap]);
+            vec3 pd = v3(pp[(P_DX + 0) * cap], pp[(P_DX + 1) * cap], pp[(P_DX + 2) * cap]);
+            vec3 ppoint = po + pd * plen[j];
+            vec3 pn, pt;
+            compute_orientation(S, face, ppoint, &pn, &pt);
+            vec3 nn = norm(pn);
+            if (k.has_a) {
+                vec3 dir = material_eval_para(S, M, wl, k.a.n.re, pd, ppoint, pn, pt, k.a.type);
+                double* q = out.p + (unsigned long long)(j * NPF) * ocap + pos_a;
+                q[0 * ocap] = ppoint.x; q[1 * ocap] = ppoint.y; q[2 * ocap] = ppoint.z;
+                q[3 * ocap] = dir.x; q[4 * ocap] = dir.y; q[5 * ocap] = dir.z;
+                q[6 * ocap] = nn.x; q[7 * ocap] = nn.y; q[8 * ocap] = nn.z;
+                q[9 * ocap] = max_length;
+            }
+            if (k.has_b) {
+                vec3 dir = material_eval_para(S, M, wl, k.b.n.re, pd, ppoint, pn, pt, k.b.type);
+                double* q = out.p + (unsigned long long)(j * NPF) * ocap + pos_b;
+                q[0 * ocap] = ppoint.x; q[1 * ocap] = ppoint.y; q[2 * ocap] = ppoint.z;
+                q[3 * ocap] = dir.x; q[4 * ocap] = dir.y; q[5 * ocap] = dir.z;
+                q[6 * ocap] = nn.x; q[7 * ocap] = nn.y; q[8 * ocap] = nn.z;
+                q[9 * ocap] = max_length;
+            }
+        }
+    }
+}
+
+}  // namespace rpx

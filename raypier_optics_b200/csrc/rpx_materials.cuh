@@ -1,0 +1,426 @@
+// rpx_materials.cuh -- device evaluation of every InterfaceMaterial of the reference
+// (raypier/core/cmaterials.pyx): S/P projection, polarised Fresnel coefficients with
+// complex indices, Snell refraction, total internal reflection, single-layer thin-film
+// transfer matrices, reflective grating orders, soft apertures, wave plates.
+//
+// A parent ray yields up to two children, always in the reference's emission order
+// (reflected first, then transmitted): slot a, then slot b.  Fields that both children
+// share are stored once (Kids::origin/normal/evec/phase/apath).
+#pragma once
+#include "rpx_faces.cuh"
+
+namespace rpx {
+
+#define RPX_SP_TOL 1.0e-10  // cmaterials.pyx:32
+
+// One parent ray in registers (what the shade kernels load from the SoA buffers).
+struct RayIn {
+    vec3 o, d, e;     // origin, direction, E_vector
+    cplx n, e1, e2;   // refractive_index, E1_amp, E2_amp
+    double len, phase, apath;
+    uint32_t wl, ident, type;
+};
+
+struct Kid {
+    vec3 dir;
+    cplx n, e1, e2;
+    uint32_t type;
+};
+
+struct Kids {
+    bool has_a, has_b;
+    vec3 origin, normal, evec;
+    double phase, apath;
+    Kid a, b;
+};
+
+// convert_to_sp, cmaterials.pyx:49-91.  Outputs the new E_vector and (E1, E2) =
+// (S, P) amplitudes; returns them unchanged when direction x normal is ~0.
+RPX_DEV void convert_to_sp(const RayIn& r, vec3 normal, vec3* evec, cplx* s_amp, cplx* p_amp) {
+    vec3 E2_vector = norm(cross(r.d, r.e));
+    vec3 E1_vector = norm(cross(E2_vector, r.d));
+    normal = norm(normal);
+    vec3 S_vector = cross(r.d, normal);
+    if (fabs(S_vector.x) < RPX_SP_TOL && fabs(S_vector.y) < RPX_SP_TOL && fabs(S_vector.z) < RPX_SP_TOL) {
+        *evec = r.e;
+        *s_amp = r.e1;
+        *p_amp = r.e2;
+        return;
+    }
+    S_vector = norm(S_vector);
+    vec3 P_vector = norm(cross(r.d, S_vector));
+    double A = dot(E1_vector, S_vector);
+    double B = dot(E2_vector, S_vector);
+    *s_amp = cx(r.e1.re * A + r.e2.re * B, r.e1.im * A + r.e2.im * B);
+    B = dot(E1_vector, P_vector);
+    A = dot(E2_vector, P_vector);
+    *p_amp = cx(r.e1.re * B + r.e2.re * A, r.e1.im * B + r.e2.im * A);
+    *evec = S_vector;
+}
+
+RPX_DEV cplx ntab_get(const DevScene& S, const rpx_material* M, int row, uint32_t wl) {
+    const double* t = S.ntab + 2 * ((size_t)M->ntab_off + (size_t)row * S.n_wl + wl);
+    return cx(t[0], t[1]);
+}
+
+// Emission tail shared by the uncoated and coated Fresnel materials
+// (cmaterials.pyx:826-872, 967-1013, 1140-1182, 1349-1391).
+RPX_DEV void fresnel_emit(Kids& k, const RayIn& r, vec3 normal, vec3 in_direction, double cosTheta,
+                          int flip, cplx n1, cplx n_t, cplx R_s, cplx R_p, cplx T_s, cplx T_p,
+                          double P_in, double refl_thr, double trans_thr) {
+    vec3 cosThetaNormal = normal * cosTheta;
+    if ((n1.re * (cabs2(R_s) + cabs2(R_p)) / P_in) > refl_thr) {
+        k.has_a = true;
+        k.a.dir = in_direction - cosThetaNormal * 2.0;
+        k.a.e1 = R_s;
+        k.a.e2 = -R_p;
+        k.a.n = n1;
+        k.a.type = r.type | RPX_REFL_RAY;
+    }
+    if ((n_t.re * (cabs2(T_s) + cabs2(T_p)) / P_in) > trans_thr) {
+        vec3 tangent = in_direction - cosThetaNormal;
+        vec3 tg2 = tangent * (n1.re / n_t.re);  // real-part approximation, :844
+        double tan_mag_sq = mag_sq(tg2);
+        double c2 = sqrt(1 - tan_mag_sq);
+        k.has_b = true;
+        k.b.dir = tg2 - normal * (c2 * flip);
+        k.b.e1 = T_s;
+        k.b.e2 = T_p;
+        k.b.n = n_t;
+        k.b.type = r.type & ~RPX_REFL_RAY;
+    }
+}
+
+// InterfaceMaterial.eval_child_ray_c for every material class.
+//   point           hit point, global coordinates
+//   onormal/otangent  FaceList.compute_orientation_c output (not yet normalised)
+__device__ void material_eval(const DevScene& S, const rpx_material* M, const RayIn& r, vec3 point,
+                              vec3 onormal, vec3 otangent, Kids& k) {
+    const double* P = M->p;
+    k.has_a = false;
+    k.has_b = false;
+    if (M->type == RPX_MAT_OPAQUE) return;  // :245-251
+
+    vec3 normal = norm(onormal);
+    k.origin = point;
+    k.normal = normal;
+    k.phase = r.phase;
+    k.apath = r.apath + r.len * r.n.re;  // accumulated_path += length * n.real
+
+    cplx s_amp, p_amp;
+    if (M->type == RPX_MAT_WAVEPLATE) convert_to_sp(r, ld3(P + 2), &k.evec, &s_amp, &p_amp);  // :541
+    else convert_to_sp(r, normal, &k.evec, &s_amp, &p_amp);
+
+    switch (M->type) {
+        case RPX_MAT_TRANSPARENT: {  // :260-278
+            k.has_a = true;
+            k.a.dir = r.d;
+            k.a.n = r.n;
+            k.a.e1 = s_amp;
+            k.a.e2 = p_amp;
+            k.a.type = r.type & ~RPX_REFL_RAY;
+        } break;
+        case RPX_MAT_PEC: {  // :285-319 (uses the un-normalised incoming direction)
+            double cosTheta = dot(normal, r.d);
+            k.has_a = true;
+            k.a.dir = r.d - (normal * cosTheta) * 2.0;
+            k.a.n = r.n;
+            k.a.e1 = -s_amp;
+            k.a.e2 = p_amp;
+            k.a.type = r.type | RPX_REFL_RAY;
+        } break;
+        case RPX_MAT_PARTIALLY_REFLECTIVE:  // :345-397
+        case RPX_MAT_LINEAR_POLARISING: {   // :404-455
+            vec3 in_direction = norm(r.d);
+            double cosTheta = dot(normal, in_direction);
+            k.has_a = true;
+            k.has_b = true;
+            k.a.dir = in_direction - (normal * cosTheta) * 2.0;
+            k.b.dir = in_direction;
+            k.a.n = r.n;
+            k.b.n = r.n;
+            k.a.type = r.type | RPX_REFL_RAY;
+            k.b.type = r.type & ~RPX_REFL_RAY;
+            if (M->type == RPX_MAT_PARTIALLY_REFLECTIVE) {
+                double R = sqrt(P[0]);
+                double T = sqrt(1 - P[0]);
+                k.a.e1 = s_amp * R;
+                k.a.e2 = p_amp * R;
+                k.b.e1 = s_amp * T;
+                k.b.e2 = p_amp * T;
+            } else {
+                k.a.e1 = s_amp;
+                k.a.e2 = cx(0.0, 0.0);
+                k.b.e1 = cx(0.0, 0.0);
+                k.b.e2 = p_amp;
+            }
+        } break;
+        case RPX_MAT_WAVEPLATE: {  // :520-551
+            k.has_a = true;
+            k.a.dir = norm(r.d);
+            k.a.n = r.n;
+            k.a.e1 = cx(s_amp.re * P[0] - s_amp.im * P[1], s_amp.im * P[0] + s_amp.re * P[1]);
+            k.a.e2 = p_amp;
+            k.a.type = r.type & ~RPX_REFL_RAY;
+        } break;
+        case RPX_MAT_DIELECTRIC: {  // :587-680
+            cplx n_inside = ntab_get(S, M, 0, r.wl), n_outside = ntab_get(S, M, 1, r.wl);
+            vec3 in_direction = norm(r.d);
+            double cosTheta = dot(normal, in_direction);
+            double cos1 = fabs(cosTheta);
+            double n1, n2;
+            int flip;
+            k.has_a = true;
+            if (cosTheta < 0.0) {
+                n1 = n_outside.re;
+                n2 = n_inside.re;
+                k.a.n = n_inside;  // assigned before the TIR test (quirk Q15)
+                flip = 1;
+            } else {
+                n1 = n_inside.re;
+                n2 = n_outside.re;
+                k.a.n = n_outside;
+                flip = -1;
+            }
+            double N2 = (n2 / n1) * (n2 / n1);
+            double N2_sin2 = (cosTheta * cosTheta) + (N2 - 1);
+            vec3 cosThetaNormal = normal * cosTheta;
+            if (N2_sin2 < 0.0) {  // total internal reflection
+                k.a.dir = in_direction - cosThetaNormal * 2.0;
+                k.a.e1 = -s_amp;
+                k.a.e2 = -p_amp;
+                k.a.type = r.type | RPX_REFL_RAY;
+            } else {
+                vec3 tangent = in_direction - cosThetaNormal;
+                vec3 tg2 = tangent * (n1 / n2);
+                double tan_mag_sq = mag_sq(tg2);
+                double c2 = sqrt(1 - tan_mag_sq);
+                vec3 transmitted = tg2 - normal * (c2 * flip);
+                double cos2 = fabs(dot(transmitted, normal));
+                double Two_n1_cos1 = (2 * n1) * cos1;
+                double aspect = sqrt(cos2 / cos1) * Two_n1_cos1;
+                double T_p = aspect / (n2 * cos1 + n1 * cos2);
+                double T_s = aspect / (n2 * cos2 + n1 * cos1);
+                k.a.dir = transmitted;
+                k.a.e1 = s_amp * T_s;
+                k.a.e2 = p_amp * T_p;
+                k.a.type = r.type & ~RPX_REFL_RAY;
+            }
+        } break;
+        case RPX_MAT_FULL_DIELECTRIC: {  // :755-872, :896-1013
+            vec3 in_direction = norm(r.d);
+            double cosTheta = dot(normal, in_direction);
+            double cos1 = fabs(cosTheta);
+            double sin1 = sqrt(fabs(1 - cos1 * cos1));
+            cplx n1, n2;
+            int flip;
+            if (cosTheta < 0.0) {
+                n1 = ntab_get(S, M, 1, r.wl);
+                n2 = ntab_get(S, M, 0, r.wl);
+                flip = 1;
+            } else {
+                n1 = ntab_get(S, M, 0, r.wl);
+                n2 = ntab_get(S, M, 1, r.wl);
+                flip = -1;
+            }
+            cplx sin2 = (n1 * sin1) / n2;
+            cplx cos2 = csqrt_(cx(1.0, 0.0) - sin2 * sin2);
+            double P_in = n1.re * (s_amp.re * s_amp.re + s_amp.im * s_amp.im + p_amp.re * p_amp.re +
+                                   p_amp.im * p_amp.im);
+            if (P_in == 0.0) return;
+            cplx n2c1 = n2 * cos1, n1c2 = n1 * cos2, n2c2 = n2 * cos2, n1c1 = n1 * cos1;
+            cplx dp = n2c1 + n1c2, ds = n2c2 + n1c1;
+            cplx R_p = (-(n2c1 - n1c2)) / dp;
+            cplx R_s = (-(n2c2 - n1c1)) / ds;
+            R_s = R_s * s_amp;
+            R_p = R_p * p_amp;
+            double aspect = sqrt(cos2.re / cos1);
+            cplx num = (n1 * (2.0 * cos1)) * aspect;
+            cplx T_p = (num / dp) * p_amp;
+            cplx T_s = (num / ds) * s_amp;
+            fresnel_emit(k, r, normal, in_direction, cosTheta, flip, n1, n2, R_s, R_p, T_s, T_p, P_in,
+                         P[0], P[1]);
+        } break;
+        case RPX_MAT_COATED: {  // :1026-1182, :1228-1391: single-layer thin film
+            double wavelength = S.wavelengths[r.wl];
+            vec3 in_direction = norm(r.d);
+            double cosTheta = dot(normal, in_direction);
+            double cos1 = fabs(cosTheta);
+            double sin1 = sqrt(fabs(1 - cos1 * cos1));
+            cplx n2 = ntab_get(S, M, 2, r.wl);
+            cplx n1, n3;
+            int flip;
+            if (cosTheta < 0.0) {
+                n1 = ntab_get(S, M, 1, r.wl);
+                n3 = ntab_get(S, M, 0, r.wl);
+                flip = 1;
+            } else {
+                n1 = ntab_get(S, M, 0, r.wl);
+                n3 = ntab_get(S, M, 1, r.wl);
+                flip = -1;
+            }
+            cplx n1s = n1 * sin1;
+            cplx sin2 = n1s / n2;
+            cplx cos2 = csqrt_(cx(1.0, 0.0) - sin2 * sin2);
+            cplx sin3 = n1s / n3;
+            cplx cos3 = csqrt_(cx(1.0, 0.0) - sin3 * sin3);
+            double P_in = n1.re * (s_amp.re * s_amp.re + s_amp.im * s_amp.im + p_amp.re * p_amp.re +
+                                   p_amp.im * p_amp.im);
+            if (P_in == 0.0) return;
+            cplx n1cos1 = n1 * cos1;
+            cplx n2cos2 = n2 * cos2;
+            cplx n3cos3 = n3 * cos3;
+            double dwc = 2 * M_PI * P[2] / wavelength;
+            // phi = -I*dwc*(n2 - sin2*sin2)/cos2
+            cplx phi = (cx(0.0, -dwc) * (n2 - sin2 * sin2)) / cos2;
+            cplx ep1 = cexp_(phi) / ((n2cos2 * 4.0) * n3cos3);
+            cplx ep2 = cexp_(phi * -2.0);
+            cplx R_s, T_s, R_p, T_p;
+            {
+                cplx am = n1cos1 - n2cos2, ap = n1cos1 + n2cos2;
+                cplx bm = n2cos2 - n3cos3, bp = n2cos2 + n3cos3;
+                cplx M00 = (-ep1) * (am * bp + (ap * bm) * ep2);
+                cplx M01 = ep1 * ((am * bm) * ep2 + ap * bp);
+                cplx M10 = ep1 * (am * bm + (ap * bp) * ep2);
+                cplx M11 = (-ep1) * ((am * bp) * ep2 + ap * bm);
+                R_s = (-M00) / M01;
+                T_s = M10 + M11 * R_s;
+            }
+            {
+                cplx n1cos2 = n1 * cos2, n2cos1 = n2 * cos1, n2cos3 = n2 * cos3, n3cos2 = n3 * cos2;
+                cplx am = n1cos2 - n2cos1, ap = n1cos2 + n2cos1;
+                cplx bm = n2cos3 - n3cos2, bp = n2cos3 + n3cos2;
+                cplx M00 = (-ep1) * (am * bp + (ap * bm) * ep2);
+                cplx M01 = ep1 * ((am * bm) * ep2 + ap * bp);
+                cplx M10 = ep1 * (am * bm + (ap * bp) * ep2);
+                cplx M11 = (-ep1) * ((am * bp) * ep2 + ap * bm);
+                R_p = (-M00) / M01;
+                T_p = M10 + M11 * R_p;
+            }
+            R_s = R_s * s_amp;
+            R_p = R_p * p_amp;
+            double aspect = sqrt(cos3.re / cos1);
+            T_s = T_s * (s_amp * aspect);
+            T_p = T_p * (p_amp * aspect);
+            fresnel_emit(k, r, normal, in_direction, cosTheta, flip, n1, n3, R_s, R_p, T_s, T_p, P_in,
+                         P[0], P[1]);
+        } break;
+        case RPX_MAT_GRATING: {  // :1472-1542
+            vec3 tangent = norm(otangent);
+            vec3 tangent2 = cross(normal, tangent);
+            double wavelen = S.wavelengths[r.wl];
+            double line_spacing = 1000.0 / P[0];
+            double order = (double)(int)P[1];
+            vec3 reflected = norm(r.d);
+            double k_z = dot(normal, reflected);
+            double k_y = dot(tangent2, reflected);
+            double k_x = dot(tangent, reflected);
+            int sign = (k_z < 0.0) ? 1 : -1;
+            k_x = k_x - order * wavelen / (line_spacing * r.n.re);
+            k_z = 1 - (k_x * k_x) - (k_y * k_y);
+            if (k_z < 0) return;  // evanescent order
+            k_z = sign * sqrt(k_z);
+            reflected = tangent * k_x;
+            reflected = reflected + tangent2 * k_y;
+            reflected = reflected + normal * k_z;
+            k.has_a = true;
+            k.a.dir = reflected;
+            k.a.n = r.n;
+            k.a.e1 = cx(-s_amp.re * P[2], -s_amp.im * P[2]);
+            k.a.e2 = cx(p_amp.re * P[2], p_amp.im * P[2]);
+            k.a.type = r.type | RPX_REFL_RAY;
+            k.phase = r.phase + 1000.0 * dot(ld3(P + 3) - point, tangent) * order * 2 * M_PI / line_spacing;
+        } break;
+        case RPX_MAT_CIRC_APERTURE: {  // :1641-1674
+            double rr = sqrt(mag_sq(ld3(P + 4) - point));
+            if (rr > P[0]) return;
+            double atten = 0.5 + 0.5 * erf((P[1] - rr) / P[2]);
+            if (P[3] != 0.0) atten = 1 - atten;
+            k.has_a = true;
+            k.a.dir = r.d;
+            k.a.n = r.n;
+            k.a.e1 = s_amp * atten;
+            k.a.e2 = p_amp * atten;
+            k.a.type = r.type & ~RPX_REFL_RAY;
+        } break;
+        case RPX_MAT_RECT_APERTURE: {  // :1718-1763 (uses the un-normalised orientation)
+            double width = P[4];
+            double x = P[2] / 2., y = P[3] / 2.;
+            vec3 p = point - ld3(P + 6);
+            double px = dot(p, otangent);
+            double py = dot(p, cross(onormal, otangent));
+            if (fabs(px) > P[0] / 2.) return;
+            if (fabs(py) > P[1] / 2.) return;
+            double atten = 0.5 - 0.5 * erf((px - x) / width);
+            atten *= 0.5 - 0.5 * erf(-(px + x) / width);
+            atten *= 0.5 - 0.5 * erf((py - y) / width);
+            atten *= 0.5 - 0.5 * erf(-(py + y) / width);
+            if (P[5] != 0.0) atten = 1 - atten;
+            k.has_a = true;
+            k.a.dir = r.d;
+            k.a.n = r.n;
+            k.a.e1 = s_amp * atten;
+            k.a.e2 = p_amp * atten;
+            k.a.type = r.type & ~RPX_REFL_RAY;
+        } break;
+        default: break;
+    }
+}
+
+// InterfaceMaterial.eval_parabasal_ray_c -> outgoing parabasal direction.
+// (origin = point, normal = norm(orient.normal), length = INF are set by the caller.)
+RPX_DEV vec3 material_eval_para(const DevScene& S, const rpx_material* M, uint32_t wl, double base_n_re,
+                                vec3 direction, vec3 point, vec3 onormal, vec3 otangent,
+                                uint32_t ray_type_id) {
+    vec3 normal = norm(onormal);
+    if (M->para_model == RPX_PARA_SNELL) {  // cmaterials.pyx:683-724, 1393-1434
+        direction = norm(direction);
+        double cosTheta = dot(normal, direction);
+        vec3 cosThetaNormal = normal * cosTheta;
+        double n1, n2;
+        int flip;
+        if (cosTheta < 0.0) {
+            n1 = ntab_get(S, M, 1, wl).re;
+            n2 = ntab_get(S, M, 0, wl).re;
+            flip = 1;
+        } else {
+            n1 = ntab_get(S, M, 0, wl).re;
+            n2 = ntab_get(S, M, 1, wl).re;
+            flip = -1;
+        }
+        if (ray_type_id & RPX_REFL_RAY) return direction - cosThetaNormal * 2.0;
+        vec3 tangent = direction - cosThetaNormal;
+        vec3 tg2 = tangent * (n1 / n2);
+        double tan_mag_sq = mag_sq(tg2);
+        double c2 = sqrt(1 - tan_mag_sq);
+        return tg2 - normal * (c2 * flip);
+    }
+    if (M->para_model == RPX_PARA_GRATING) {  // :1544-1599
+        const double* P = M->p;
+        vec3 tangent = norm(otangent);
+        vec3 tangent2 = cross(normal, tangent);
+        double wavelen = S.wavelengths[wl];
+        double line_spacing = 1000.0 / P[0];
+        double order = (double)(int)P[1];
+        vec3 reflected = norm(direction);
+        double k_z = dot(normal, reflected);
+        double k_y = dot(tangent2, reflected);
+        double k_x = dot(tangent, reflected);
+        int sign = (k_z < 0.0) ? 1 : -1;
+        k_x = k_x - order * wavelen / (line_spacing * base_n_re);
+        k_z = 1 - (k_x * k_x) - (k_y * k_y);
+        k_z = sign * sqrt(k_z);  // evanescent -> NaN, as in the reference (it only prints)
+        reflected = tangent * k_x;
+        reflected = reflected + tangent2 * k_y;
+        reflected = reflected + normal * k_z;
+        return reflected;
+    }
+    // default, ctracer.pyx:1588-1610
+    if (ray_type_id & RPX_REFL_RAY) {
+        double cosTheta = dot(normal, direction);
+        return direction - (normal * cosTheta) * 2.0;
+    }
+    return direction;
+}
+
+}  // namespace rpx

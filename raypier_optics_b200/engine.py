@@ -1,0 +1,211 @@
+"""Thin object layer over the C ABI: one ``Engine`` = one ``rpx_ctx`` (one GPU)."""
+import ctypes as C
+
+import numpy as np
+
+from . import _abi as A
+from ._lib import RpxError, load
+
+
+class TraceResult(object):
+    """Handle on a finished trace (``rpx_result``): generation counts, per-face hit
+    counts, device timings; generations are copied to the host on demand."""
+
+    def __init__(self, engine, handle, is_gausslet):
+        self._e = engine
+        self._h = handle
+        self.is_gausslet = bool(is_gausslet)
+        L = engine._L
+        n = L.rpx_result_n_generations(handle)
+        counts = np.zeros(max(n, 1), dtype=np.uint64)
+        L.rpx_result_counts(handle, counts.ctypes.data)
+        self.counts = [int(c) for c in counts[:n]]
+        fc = np.zeros(max(engine.n_traced_faces, 1), dtype=np.uint32)
+        L.rpx_result_face_counts(handle, fc.ctypes.data)
+        self.face_counts = fc[:engine.n_traced_faces].copy()
+        self.device_ms = float(L.rpx_result_device_ms(handle))
+        self.launches = int(L.rpx_result_launches(handle))
+        self.kernel_ms = {}
+        for which, name in ((0, "intersect"), (1, "shade")):
+            ms, ln = C.c_double(), C.c_uint64()
+            L.rpx_result_kernel_ms(handle, which, C.byref(ms), C.byref(ln))
+            self.kernel_ms[name] = (ms.value, int(ln.value))
+
+    @property
+    def n_generations(self):
+        return len(self.counts)
+
+    @property
+    def segments(self):
+        """ray-segments of this trace = sum over generations of len(traced_rays[g])."""
+        return int(sum(self.counts))
+
+    def generation(self, g, out=None):
+        dtype = A.gausslet_dtype if self.is_gausslet else A.ray_dtype
+        n = self.counts[g]
+        if out is None:
+            out = np.empty(n, dtype=dtype)
+        assert out.dtype == dtype and out.shape[0] >= n and out.flags.c_contiguous
+        self._e._check(self._e._L.rpx_result_generation(self._e._ctx, self._h, g, out.ctypes.data,
+                                                         out.shape[0]))
+        return out[:n]
+
+    def generations(self):
+        return [self.generation(g) for g in range(self.n_generations)]
+
+    def free(self):
+        if self._h is not None:
+            self._e._L.rpx_result_free(self._e._ctx, self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+
+class DeviceRays(object):
+    """A device-resident generation (``rpx_rays``)."""
+
+    def __init__(self, engine, handle, is_gausslet):
+        self._e, self._h, self.is_gausslet = engine, handle, bool(is_gausslet)
+
+    def __len__(self):
+        return int(self._e._L.rpx_rays_count(self._h))
+
+    def free(self):
+        if self._h is not None:
+            self._e._L.rpx_rays_free(self._e._ctx, self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+
+class Engine(object):
+    def __init__(self, device=0):
+        self._L = load()
+        ctx = C.c_void_p()
+        rc = self._L.rpx_init(int(device), C.byref(ctx))
+        if rc != A.RPX_OK:
+            raise RpxError(rc, (self._L.rpx_last_error(None) or b"").decode())
+        self._ctx = ctx
+        self.device = int(device)
+        self.scene = None
+        self.n_traced_faces = 0
+
+    def _check(self, rc):
+        if rc != A.RPX_OK:
+            raise RpxError(rc, (self._L.rpx_last_error(self._ctx) or b"").decode())
+
+    def close(self):
+        if self._ctx is not None:
+            self._L.rpx_shutdown(self._ctx)
+            self._ctx = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # -- scene --------------------------------------------------------------------
+    def set_scene(self, scene):
+        self._check(self._L.rpx_scene_set(self._ctx, scene.byref()))
+        self.scene = scene  # keeps the host tables alive
+        self.n_traced_faces = scene.n_traced_faces
+
+    # -- rays -----------------------------------------------------------------------
+    @staticmethod
+    def _is_gausslet(arr):
+        if arr.dtype == A.gausslet_dtype:
+            return 1
+        if arr.dtype == A.ray_dtype:
+            return 0
+        raise TypeError("rays must be a ray_dtype or gausslet_dtype array, got %s" % (arr.dtype,))
+
+    def upload(self, rays):
+        rays = np.ascontiguousarray(rays)
+        is_g = self._is_gausslet(rays)
+        h = C.c_void_p()
+        self._check(self._L.rpx_rays_upload(self._ctx, rays.ctypes.data, rays.shape[0], is_g, C.byref(h)))
+        return DeviceRays(self, h, is_g)
+
+    def download(self, dev_rays):
+        n = len(dev_rays)
+        out = np.empty(n, dtype=A.gausslet_dtype if dev_rays.is_gausslet else A.ray_dtype)
+        self._check(self._L.rpx_rays_download(self._ctx, dev_rays._h, out.ctypes.data, n))
+        return out
+
+    # -- tracing ----------------------------------------------------------------------
+    def trace(self, rays, max_length, recursion_limit, flags=A.TRACE_DEFAULT):
+        """Host buffers in (H2D inside): ``rpx_trace``."""
+        rays = np.ascontiguousarray(rays)
+        is_g = self._is_gausslet(rays)
+        h = C.c_void_p()
+        self._check(self._L.rpx_trace(self._ctx, rays.ctypes.data, rays.shape[0], is_g, float(max_length),
+                                      int(recursion_limit), int(flags), C.byref(h)))
+        return TraceResult(self, h, is_g)
+
+    def trace_device(self, dev_rays, max_length, recursion_limit, flags=A.TRACE_DEFAULT):
+        """Inputs already resident (``rpx_trace_device``); consumes ``dev_rays``."""
+        h = C.c_void_p()
+        handle, dev_rays._h = dev_rays._h, None  # ownership moves to the library
+        self._check(self._L.rpx_trace_device(self._ctx, handle, float(max_length), int(recursion_limit),
+                                             int(flags), C.byref(h)))
+        return TraceResult(self, h, dev_rays.is_gausslet)
+
+    # -- unit entry points (function-level parity tests) -----------------------------------
+    def unit_face_intersect(self, face_idx, p1, p2, is_base_ray=1):
+        p1 = np.ascontiguousarray(p1, dtype=np.double).reshape(-1, 3)
+        p2 = np.ascontiguousarray(p2, dtype=np.double).reshape(-1, 3)
+        out = np.empty(p1.shape[0])
+        self._check(self._L.rpx_unit_face_intersect(self._ctx, face_idx, p1.ctypes.data, p2.ctypes.data,
+                                                    p1.shape[0], int(is_base_ray), out.ctypes.data))
+        return out
+
+    def unit_face_normal(self, face_idx, points):
+        """-> (normal, tangent) of FaceList.compute_orientation_c at global points."""
+        p = np.ascontiguousarray(points, dtype=np.double).reshape(-1, 3)
+        n, t = np.empty_like(p), np.empty_like(p)
+        self._check(self._L.rpx_unit_face_normal(self._ctx, face_idx, p.ctypes.data, p.shape[0],
+                                                 n.ctypes.data, t.ctypes.data))
+        return n, t
+
+    def unit_material_eval(self, mat_idx, rays, point, normal, tangent):
+        rays = np.ascontiguousarray(rays, dtype=A.ray_dtype).reshape(-1)
+        n = rays.shape[0]
+        pt = np.ascontiguousarray(np.broadcast_to(np.asarray(point, dtype=np.double), (n, 3)))
+        nm = np.ascontiguousarray(np.broadcast_to(np.asarray(normal, dtype=np.double), (n, 3)))
+        tg = np.ascontiguousarray(np.broadcast_to(np.asarray(tangent, dtype=np.double), (n, 3)))
+        out = np.zeros(2 * n, dtype=A.ray_dtype)
+        cnt = np.zeros(n, dtype=np.uint32)
+        self._check(self._L.rpx_unit_material_eval(self._ctx, mat_idx, rays.ctypes.data, n, pt.ctypes.data,
+                                                   nm.ctypes.data, tg.ctypes.data, out.ctypes.data,
+                                                   cnt.ctypes.data))
+        return out.reshape(n, 2), cnt
+
+    def unit_distortion(self, dist_idx, x, y):
+        """-> (z_offset_c(x, y), z_offset_and_gradient_c(x, y) as (n, 3))."""
+        x = np.ascontiguousarray(x, dtype=np.double).reshape(-1)
+        y = np.ascontiguousarray(y, dtype=np.double).reshape(-1)
+        z = np.empty(x.shape[0])
+        g = np.empty((x.shape[0], 3))
+        self._check(self._L.rpx_unit_distortion(self._ctx, dist_idx, x.ctypes.data, y.ctypes.data,
+                                                x.shape[0], z.ctypes.data, g.ctypes.data))
+        return z, g
+
+
+_ENGINES = {}
+
+
+def get_engine(device=0):
+    """Process-wide engine per device (one context per process per GPU)."""
+    e = _ENGINES.get(device)
+    if e is None or e._ctx is None:
+        e = _ENGINES[device] = Engine(device)
+    return e

@@ -414,8 +414,11 @@ class Scene:
         elif name == "CoatedDispersiveMaterial":
             m['type'] = A.MAT_COATED
             m['para_model'] = A.PARA_SNELL
-            m['ntab_off'] = self._table_ntab([np.asarray(mat.n_inside), np.asarray(mat.n_outside),
-                                              np.asarray(mat.n_coating)])
+            # same values on_set_wavelengths stores (cmaterials.pyx:1220-1225); evaluated here
+            # through the public curve API so flattening does not depend on call order
+            m['ntab_off'] = self._table_ntab([mat.dispersion_inside.evaluate_n(wl),
+                                              mat.dispersion_outside.evaluate_n(wl),
+                                              mat.dispersion_coating.evaluate_n(wl)])
             p[0], p[1], p[2] = (mat.reflection_threshold, mat.transmission_threshold,
                                 mat.coating_thickness)
         elif name == "DiffractionGratingMaterial":

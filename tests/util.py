@@ -1,0 +1,89 @@
+"""Shared comparison helpers for the parity tests."""
+import numpy as np
+
+from raypier_optics_b200 import _abi as A
+
+# Tolerances of BASELINE.json's north_star: <= 1e-9 relative for positions and
+# directions, <= 1e-10 for complex E-field / Fresnel amplitudes; integer fields bit-exact.
+TOL_GEOM = 1e-9
+TOL_FIELD = 1e-10
+
+INT_FIELDS = ('wavelength_idx', 'parent_idx', 'end_face_idx', 'ray_ident', 'ray_type_id')
+GEOM_FIELDS = ('origin', 'direction', 'normal', 'E_vector', 'length', 'accumulated_path', 'phase')
+FIELD_FIELDS = ('refractive_index', 'E1_amp', 'E2_amp')
+
+
+def _rel(a, b):
+    """max |a-b| / max(1, |a|) over finite entries; non-finite patterns must agree."""
+    a = np.asarray(a)
+    b = np.asarray(b)
+    if np.iscomplexobj(a):
+        a = np.stack([a.real, a.imag], axis=-1)
+        b = np.stack([b.real, b.imag], axis=-1)
+    fa, fb = np.isfinite(a), np.isfinite(b)
+    assert np.array_equal(fa, fb), "finite/non-finite pattern differs"
+    nf = ~fa
+    if nf.any():  # inf must match in sign, nan in position
+        assert np.array_equal(np.isnan(a[nf]), np.isnan(b[nf]))
+        inf = nf & np.isinf(a)
+        assert np.array_equal(a[inf], b[inf])
+    if not fa.any():
+        return 0.0
+    d = np.abs(a[fa] - b[fa]) / np.maximum(1.0, np.abs(a[fa]))
+    return float(d.max())
+
+
+def compare_generation(got, want, label="", skip_untraced=False):
+    """Integer fields bit-exact, fp64 fields within the stated tolerances."""
+    assert got.dtype == want.dtype, label
+    assert got.shape == want.shape, "%s: %s rays vs %s" % (label, got.shape, want.shape)
+    is_g = got.dtype == A.gausslet_dtype
+    gb = got['base_ray'] if is_g else got
+    wb = want['base_ray'] if is_g else want
+    for f in INT_FIELDS:
+        assert np.array_equal(gb[f], wb[f]), "%s: integer field %s differs" % (label, f)
+    worst = 0.0
+    for f in GEOM_FIELDS:
+        r = _rel(gb[f], wb[f])
+        assert r <= TOL_GEOM, "%s: %s rel err %.3e" % (label, f, r)
+        worst = max(worst, r)
+    for f in FIELD_FIELDS:
+        r = _rel(gb[f], wb[f])
+        assert r <= TOL_FIELD, "%s: %s rel err %.3e" % (label, f, r)
+        worst = max(worst, r)
+    if is_g:
+        for f in ('origin', 'direction', 'normal', 'length'):
+            r = _rel(got['para_rays'][f], want['para_rays'][f])
+            assert r <= TOL_GEOM, "%s: para %s rel err %.3e" % (label, f, r)
+            worst = max(worst, r)
+    return worst
+
+
+def compare_traces(got_gens, want_gens, label=""):
+    assert [len(g) for g in got_gens] == [len(g) for g in want_gens], \
+        "%s: generation sizes %s vs %s" % (label, [len(g) for g in got_gens], [len(g) for g in want_gens])
+    worst = 0.0
+    for i, (g, w) in enumerate(zip(got_gens, want_gens)):
+        worst = max(worst, compare_generation(g, w, "%s gen %d" % (label, i)))
+    return worst
+
+
+# (config name, kwargs, recursion-limit override)
+PARITY_CASES = [
+    ("config1", dict(n=10000), None),
+    ("config2", dict(n=20000), None),
+    ("config2", dict(n=20000, reflection_threshold=1e-3, transmission_threshold=1e-3), 6),
+    ("config3", dict(n=5000), None),
+    ("config4_prisms", dict(n=5000), 12),
+    ("config4_grating", dict(n=5000), None),
+    ("config5", dict(n=3000, gausslets=False), None),
+    ("config5", dict(n=3000, gausslets=True), None),
+]
+
+
+def build_case(core, name, kw, rl):
+    from raypier_optics_b200 import configs
+    cfg = configs.build(core, name, **kw)
+    if rl:
+        cfg['recursion_limit'] = rl
+    return cfg
