@@ -1,0 +1,421 @@
+#!/usr/bin/env python
+"""bench.py -- ray-segments/s of the non-sequential trace (BASELINE.json's metric).
+
+A "step" is one complete trace (all generations) of one batch of synthetic source rays
+through one of the BASELINE configs.  Default workload: configs[1], the EdmundOptic45805
+achromatic doublet with AR coating, 1e6 polarised rays over 5 wavelengths with glass
+dispersion (188 MB of ray records per generation: larger than the 126 MB L2, so no L2
+flush is needed between steps).
+
+    python bench.py --gpus N --steps K --warmup W            # our CUDA path
+    python bench.py --impl reference --steps K --warmup W    # the reference's CPU path
+
+  value     whole-job ray-segments/s, inputs resident in HBM, device-timed (CUDA events on
+            the engine's stream around every generation loop), max over ranks
+  e2e       same metric through the reference-facing call with HOST buffers: pinned H2D of
+            the source rays + trace + D2H of every generation (what trace_rays returns)
+  roofline  dominant kernel (k_shade) achieved algorithmic GB/s vs MEASURED_PEAKS.json
+  cpu_baseline  the reference's own Cython trace (oracle/_ref) on the box's host cores
+
+Under torchrun every rank traces its own shard of the source (weak scaling: per-GPU work
+fixed); no collective inside the generation loop, one NCCL all-gather of the per-generation
+counts + all-reduce of Face.count at the end of each step (raypier_optics_b200.distributed).
+"""
+import argparse
+import json
+import multiprocessing as mp
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import numpy as np
+
+METRIC = "ray-segments/sec"
+WORKLOADS = {
+    "config1": dict(n=10000, kw={}),
+    "config2": dict(n=1000000, kw={}),
+    "config3": dict(n=10000000, kw={}),
+    "config4_prisms": dict(n=1000000, kw={}, recursion_limit=12),
+    "config4_grating": dict(n=1000000, kw={}),
+    "config5": dict(n=1000000, kw=dict(gausslets=True)),
+    "config5_rays": dict(n=1000000, kw=dict(gausslets=False)),
+}
+# algorithmic bytes per ray-segment: read the parent record, write
+# back length + end_face_idx, write c children
+BYTES_RAY = (188, 12, 188)
+BYTES_GAUSSLET = (668, 60, 668)
+
+
+def workload_cfg(core, name, n, seed):
+    from raypier_optics_b200 import configs
+    w = WORKLOADS[name]
+    key = "config5" if name.startswith("config5") else name
+    kw = dict(w["kw"])
+    kw["n"] = n
+    kw["seed"] = seed
+    cfg = configs.build(core, key, **kw)
+    if "recursion_limit" in w:
+        cfg["recursion_limit"] = w["recursion_limit"]
+    return cfg
+
+
+# --------------------------------------------------------------------------- clocks
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        threading.Thread.__init__(self, daemon=True)
+        self.gpu = gpu_index
+        self.samples = []
+        self.stop_flag = threading.Event()
+
+    def run(self):
+        while not self.stop_flag.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.Q,
+                                      "--format=csv,noheader,nounits"], capture_output=True, text=True,
+                                     timeout=5).stdout.strip()
+                if out:
+                    self.samples.append([x.strip() for x in out.split(",")])
+            except Exception:
+                pass
+            self.stop_flag.wait(0.2)
+
+    def summary(self):
+        sm, smax, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for s in self.samples:
+            try:
+                sm.append(float(s[0]))
+                smax.append(float(s[1]))
+            except Exception:
+                continue
+            for name, v in zip(names, s[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None,
+                "sm_max_mhz": float(max(smax)) if smax else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# --------------------------------------------------------------------------- CPU arms
+def _import_ref(flavour):
+    from oracle import oracle as O
+    return O, O.import_reference(flavour)
+
+
+def _cpu_worker(args):
+    """Trace a shard on one host core with the reference (or the C oracle port)."""
+    name, n, seed, kind = args
+    from oracle import oracle as O
+    if kind == "reference":
+        core = O.import_reference("timing") or O.import_reference("parity")
+        cfg = workload_cfg(core, name, n, seed)
+        rc = O.reference_collection(core, cfg["rays"], cfg["wavelengths"])
+        t0 = time.perf_counter()
+        traced, _ = O.reference_trace_rays(core, rc, cfg["face_lists"], cfg["recursion_limit"],
+                                           cfg["max_length"])
+        dt = time.perf_counter() - t0
+        return sum(len(t) for t in traced), dt
+    import raypier_optics_b200.core as core
+    from raypier_optics_b200 import scene
+    cfg = workload_cfg(core, name, n, seed)
+    sc = scene.Scene(cfg["face_lists"], cfg["wavelengths"])
+    t0 = time.perf_counter()
+    gens, _ = O.trace_rays(sc, cfg["rays"], cfg["recursion_limit"], cfg["max_length"])
+    dt = time.perf_counter() - t0
+    return sum(len(g) for g in gens), dt
+
+
+def cpu_trace(name, n_total, cores, kind, seed=1234):
+    """Shard n_total source rays over ``cores`` independent worker processes (each with its
+    own scene copy; the reference loop is single-threaded under the GIL).  Returns
+    (segments, wall seconds including only the trace_rays calls = max over workers)."""
+    per = max(n_total // cores, 1)
+    jobs = [(name, per, seed + i, kind) for i in range(cores)]
+    if cores == 1:
+        res = [_cpu_worker(jobs[0])]
+    else:
+        ctx = mp.get_context("spawn")
+        with ctx.Pool(cores) as pool:
+            res = pool.map(_cpu_worker, jobs)
+    segs = sum(r[0] for r in res)
+    wall = max(r[1] for r in res)
+    return segs, wall
+
+
+def cpu_kind():
+    from oracle import oracle as O
+    return "reference" if (O.import_reference("timing") or O.import_reference("parity")) else "port"
+
+
+def run_reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    kind = cpu_kind()
+    cores = os.cpu_count() or 1
+    name = args.workload
+    # bounded sample: ~2e5 source rays per core per step keeps a step at a few seconds
+    n_sample = min(WORKLOADS[name]["n"], args.ref_rays_per_core * cores)
+    for _ in range(args.warmup):
+        cpu_trace(name, max(n_sample // 8, cores), cores, kind)
+    segs_total, t_total = 0, 0.0
+    for k in range(args.steps):
+        segs, wall = cpu_trace(name, n_sample, cores, kind, seed=1000 + k)
+        segs_total += segs
+        t_total += wall
+    value = segs_total / t_total
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": "ray-segments/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": 1e3 * t_total / max(args.steps, 1), "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": name, "rays_per_step": n_sample,
+                   "note": "reference Cython trace_rays on host cores, source sharded over "
+                           "independent worker processes (the reference loop is single-threaded)"},
+        "cpu_baseline": {"value": value, "unit": "ray-segments/s", "cores": cores, "kind": kind,
+                         "sample": "%d source rays of %s per step, %d steps" % (n_sample, name, args.steps)},
+        "e2e": {"value": value, "unit": "ray-segments/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+    return 0
+
+
+# --------------------------------------------------------------------------- our arm
+def load_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            d = json.load(open(p))
+            return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def load_traffic(workload, kernel):
+    """dram bytes per launch of the dominant kernel from the committed ncu capture."""
+    p = os.path.join(ROOT, "profiles", "roofline_latest.json")
+    try:
+        d = json.load(open(p))
+        e = d.get(workload, {}).get(kernel)
+        return e
+    except Exception:
+        return None
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    distributed = world > 1
+    if not torch.cuda.is_available():
+        raise RuntimeError("bench.py needs a CUDA device: raypier_optics_b200 has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    if distributed:
+        dist.init_process_group(backend="nccl", device_id=torch.device("cuda", local_rank))
+    dev = torch.device("cuda", local_rank)
+
+    import raypier_optics_b200.core as core
+    from raypier_optics_b200 import scene
+    from raypier_optics_b200 import distributed as rdist
+    from raypier_optics_b200.engine import Engine
+
+    name = args.workload
+    n = args.rays if args.rays else WORKLOADS[name]["n"]
+    cfg = workload_cfg(core, name, n, seed=100 + rank)  # every rank traces its own shard
+    sc = scene.Scene(cfg["face_lists"], cfg["wavelengths"])
+    eng = Engine(local_rank)
+    eng.set_scene(sc)
+    rays = cfg["rays"]
+    is_g = rays.dtype.itemsize == 668
+    ml, rl = cfg["max_length"], cfg["recursion_limit"]
+
+    def barrier():
+        torch.cuda.synchronize()
+        if distributed:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---------------- device-resident arm (`value`)
+    pristine = eng.upload(rays)
+
+    def step_resident():
+        d = eng.clone(pristine)
+        res = eng.trace_device(d, ml, rl)
+        if distributed:  # the only collectives of a trace: counts all-gather + Face.count all-reduce
+            rdist.exchange_counts(res.counts, res.face_counts, device=dev)
+        return res
+
+    for _ in range(args.warmup):
+        step_resident().free()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    barrier()
+    t0 = time.perf_counter()
+    dev_ms, segs, launches = 0.0, 0, 0
+    k_ms = {"intersect": [0.0, 0], "shade": [0.0, 0]}
+    gen_counts = None
+    for _ in range(args.steps):
+        res = step_resident()
+        dev_ms += res.device_ms
+        segs += res.segments
+        launches += res.launches
+        for k in k_ms:
+            k_ms[k][0] += res.kernel_ms[k][0]
+            k_ms[k][1] += res.kernel_ms[k][1]
+        gen_counts = res.counts
+        res.free()
+    barrier()
+    wall_ms = 1e3 * (time.perf_counter() - t0)
+    if rank == 0:
+        sampler.stop_flag.set()
+        sampler.join()
+
+    # max over ranks of the device time, sum over ranks of the work
+    t = torch.tensor([dev_ms, wall_ms], dtype=torch.float64, device=dev)
+    s = torch.tensor([segs, launches], dtype=torch.float64, device=dev)
+    if distributed:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dist.all_reduce(s, op=dist.ReduceOp.SUM)
+    dev_ms_max, wall_ms_max = float(t[0]), float(t[1])
+    segs_all, launches_all = float(s[0]), float(s[1])
+    value = segs_all / (dev_ms_max * 1e-3)
+
+    # ---------------- end-to-end arm (`e2e`): host buffers, copies inside the timed region
+    rec = rays.dtype.itemsize
+    pinned_in = eng.pinned_empty(rays.shape[0], rays.dtype)
+    pinned_in[:] = rays
+    # output staging sized from the known generation profile (+ slack)
+    out_cap = int(sum(gen_counts) * 1.05) + 1024
+    pinned_out = eng.pinned_empty(out_cap, rays.dtype)
+
+    def step_e2e():
+        res = eng.trace(pinned_in, ml, rl)
+        off = 0
+        for g in range(res.n_generations):
+            c = res.counts[g]
+            res.generation(g, out=pinned_out[off:off + c])
+            off += c
+        if distributed:
+            rdist.exchange_counts(res.counts, res.face_counts, device=dev)
+        nseg = res.segments
+        res.free()
+        return nseg, off
+
+    e2e_steps = max(1, min(args.steps, args.e2e_steps))
+    for _ in range(min(args.warmup, 2)):
+        step_e2e()
+    barrier()
+    t0 = time.perf_counter()
+    e2e_segs, d2h_records = 0, 0
+    for _ in range(e2e_steps):
+        a, b = step_e2e()
+        e2e_segs += a
+        d2h_records = b
+    barrier()
+    e2e_s = time.perf_counter() - t0
+    te = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
+    se = torch.tensor([e2e_segs], dtype=torch.float64, device=dev)
+    if distributed:
+        dist.all_reduce(te, op=dist.ReduceOp.MAX)
+        dist.all_reduce(se, op=dist.ReduceOp.SUM)
+    e2e_value = float(se[0]) / float(te[0])
+
+    if rank != 0:
+        if distributed:
+            dist.destroy_process_group()
+        return 0
+
+    # ---------------- roofline of the dominant kernel
+    peak, peak_src = load_peaks()
+    b_in, b_wb, b_child = BYTES_GAUSSLET if is_g else BYTES_RAY
+    per_step_parents = sum(gen_counts)
+    per_step_children = sum(gen_counts[1:])  # children actually emitted and traced
+    # children emitted by the last traced generation are built too (then found empty / dropped)
+    shade_ms_avg = k_ms["shade"][0] / max(k_ms["shade"][1], 1)
+    isect_ms_avg = k_ms["intersect"][0] / max(k_ms["intersect"][1], 1)
+    n_launch = max(len(gen_counts), 1)
+    shade_bytes_per_launch = (b_in * per_step_parents + b_child * per_step_children) / n_launch
+    isect_bytes_per_launch = ((48 if not is_g else 48) + b_wb) * per_step_parents / n_launch
+    dominant = "k_shade" if k_ms["shade"][0] >= k_ms["intersect"][0] else "k_intersect"
+    if dominant == "k_shade":
+        ach = shade_bytes_per_launch / (shade_ms_avg * 1e-3) / 1e9
+    else:
+        ach = isect_bytes_per_launch / (isect_ms_avg * 1e-3) / 1e9
+    gen_bytes = (b_in + b_wb) * per_step_parents + b_child * per_step_children
+    gen_ach = gen_bytes / ((k_ms["shade"][0] + k_ms["intersect"][0]) / args.steps * 1e-3) / 1e9
+    traffic = load_traffic(name, dominant)
+    roofline = {"bound": "hbm", "kernel": dominant, "achieved": ach, "peak": peak, "unit": "GB/s",
+                "frac": ach / peak, "traffic": traffic, "peak_source": peak_src,
+                "per_launch_ms": {"k_shade": shade_ms_avg, "k_intersect": isect_ms_avg},
+                "generation": {"achieved": gen_ach, "frac": gen_ach / peak,
+                               "note": "388 B/segment model over k_intersect + k_shade together"}}
+
+    # ---------------- CPU baseline (rank 0, N=1 only, bounded sample)
+    cpu = None
+    if world == 1 and not args.no_cpu_baseline:
+        kind = cpu_kind()
+        cores = os.cpu_count() or 1
+        n_sample = min(WORKLOADS[name]["n"], args.ref_rays_per_core * cores)
+        csegs, cwall = cpu_trace(name, n_sample, cores, kind)
+        cpu = {"value": csegs / cwall, "unit": "ray-segments/s", "cores": cores, "kind": kind,
+               "sample": "%d source rays of %s sharded over %d worker processes" % (n_sample, name, cores)}
+
+    line = {
+        "metric": METRIC, "value": value, "unit": "ray-segments/s", "n_gpus": world,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": dev_ms_max / args.steps,
+        "wall_ms_per_step": wall_ms_max / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": name, "rays_per_gpu": int(rays.shape[0]), "generations": gen_counts,
+                   "segments_per_step_per_gpu": int(per_step_parents), "record_bytes": rec,
+                   "l2": "inputs larger than L2 (%.0f MB per generation)" % (rays.shape[0] * rec / 1e6)
+                   if rays.shape[0] * rec > 126e6 else "inputs smaller than L2: not flushed",
+                   "parallelism": "source rays sharded by rank, scene replicated"},
+        "e2e": {"value": e2e_value, "unit": "ray-segments/s",
+                "h2d_bytes_per_step": int(rays.shape[0] * rec), "d2h_bytes_per_step": int(d2h_records * rec),
+                "steps": e2e_steps},
+        "gpu_launches": int(launches_all),
+        "clocks": sampler.summary(),
+        "roofline": roofline,
+        "cpu_baseline": cpu,
+    }
+    print(json.dumps(line))
+    if distributed:
+        dist.destroy_process_group()
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="config2", choices=sorted(WORKLOADS))
+    ap.add_argument("--rays", type=int, default=0, help="source rays per GPU (default: the config's)")
+    ap.add_argument("--e2e-steps", type=int, default=5)
+    ap.add_argument("--ref-rays-per-core", type=int, default=200000)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference_arm(args)
+    return run_ours(args)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -318,6 +318,9 @@ int rpx_rays_upload(rpx_ctx* ctx, const void* aos, uint64_t n, int is_gausslet,
 /* Replaces copy_as_array (ctracer.pyx:1048-1054, 1286-1292).                  */
 int rpx_rays_download(rpx_ctx* ctx, const rpx_rays* rays, void* out_aos, uint64_t capacity);
 uint64_t rpx_rays_count(const rpx_rays* rays);
+/* Device-to-device copy of a generation (a trace consumes and mutates its input, so a
+ * caller that re-traces the same source keeps a pristine copy).                       */
+int rpx_rays_clone(rpx_ctx* ctx, const rpx_rays* rays, rpx_rays** out_rays);
 void rpx_rays_free(rpx_ctx* ctx, rpx_rays* rays);
 
 /* Replaces the generation loop of trace_rays (core/tracer.py:22,39-45) over

@@ -119,41 +119,43 @@ def trace_rays(scene, input_rays, recursion_limit=100, max_length=100.0):
 
 
 # ---- unit entry points (for pinning against the reference's own KATs) -------
+# NOTE: every array passed by pointer is bound to a local first, so it outlives the call.
 def face_intersect(scene, face_idx, p1, p2, is_base_ray=1):
     osc = OracleScene(scene)
-    return lib().rpxo_face_intersect(osc.byref_ptr(), face_idx, _v3(p1).ctypes.data,
-                                     _v3(p2).ctypes.data, int(is_base_ray))
+    a, b = _v3(p1), _v3(p2)
+    return lib().rpxo_face_intersect(osc.byref_ptr(), face_idx, a.ctypes.data, b.ctypes.data,
+                                     int(is_base_ray))
 
 
 def face_normal(scene, face_idx, p):
     osc = OracleScene(scene)
-    out = np.zeros(3)
-    lib().rpxo_face_normal(osc.byref_ptr(), face_idx, _v3(p).ctypes.data, out.ctypes.data)
+    a, out = _v3(p), np.zeros(3)
+    lib().rpxo_face_normal(osc.byref_ptr(), face_idx, a.ctypes.data, out.ctypes.data)
     return out
 
 
 def orientation(scene, face_idx, point):
     osc = OracleScene(scene)
-    n, t = np.zeros(3), np.zeros(3)
-    lib().rpxo_orientation(osc.byref_ptr(), face_idx, _v3(point).ctypes.data, n.ctypes.data,
-                           t.ctypes.data)
+    a, n, t = _v3(point), np.zeros(3), np.zeros(3)
+    lib().rpxo_orientation(osc.byref_ptr(), face_idx, a.ctypes.data, n.ctypes.data, t.ctypes.data)
     return n, t
 
 
 def convert_to_sp(ray, normal):
     r = np.ascontiguousarray(ray, dtype=A.ray_dtype).reshape(1).copy()
+    nn = _v3(normal)
     out = np.zeros(1, dtype=A.ray_dtype)
-    lib().rpxo_convert_to_sp(r.ctypes.data, _v3(normal).ctypes.data, out.ctypes.data)
+    lib().rpxo_convert_to_sp(r.ctypes.data, nn.ctypes.data, out.ctypes.data)
     return out[0]
 
 
 def material_eval(scene, mat_idx, ray, idx, point, normal, tangent=(1.0, 0.0, 0.0)):
     osc = OracleScene(scene)
     r = np.ascontiguousarray(ray, dtype=A.ray_dtype).reshape(1).copy()
+    p, nn, tt = _v3(point), _v3(normal), _v3(tangent)
     out = np.zeros(2, dtype=A.ray_dtype)
-    n = lib().rpxo_material_eval(osc.byref_ptr(), mat_idx, r.ctypes.data, int(idx),
-                                 _v3(point).ctypes.data, _v3(normal).ctypes.data,
-                                 _v3(tangent).ctypes.data, out.ctypes.data)
+    n = lib().rpxo_material_eval(osc.byref_ptr(), mat_idx, r.ctypes.data, int(idx), p.ctypes.data,
+                                 nn.ctypes.data, tt.ctypes.data, out.ctypes.data)
     return out[:n].copy()
 
 
@@ -161,10 +163,10 @@ def material_eval_para(scene, mat_idx, base_ray, direction, point, normal, tange
                        ray_type_id=0):
     osc = OracleScene(scene)
     r = np.ascontiguousarray(base_ray, dtype=A.ray_dtype).reshape(1).copy()
+    d, p, nn, tt = _v3(direction), _v3(point), _v3(normal), _v3(tangent)
     out = np.zeros(1, dtype=A.para_dtype)
-    lib().rpxo_material_eval_para(osc.byref_ptr(), mat_idx, r.ctypes.data, _v3(direction).ctypes.data,
-                                  _v3(point).ctypes.data, _v3(normal).ctypes.data,
-                                  _v3(tangent).ctypes.data, int(ray_type_id), out.ctypes.data)
+    lib().rpxo_material_eval_para(osc.byref_ptr(), mat_idx, r.ctypes.data, d.ctypes.data, p.ctypes.data,
+                                  nn.ctypes.data, tt.ctypes.data, int(ray_type_id), out.ctypes.data)
     return out[0]
 
 
@@ -184,7 +186,8 @@ def shape_inside(scene, face_idx, x, y):
 
 
 def implicit_eval(scene, off, length, p):
-    return lib().rpxo_implicit_eval(OracleScene(scene).byref_ptr(), off, length, _v3(p).ctypes.data)
+    a = _v3(p)
+    return lib().rpxo_implicit_eval(OracleScene(scene).byref_ptr(), off, length, a.ctypes.data)
 
 
 def zernike(which, r, k, n, m, kmax):

@@ -16,7 +16,7 @@ LIB_PATH = os.path.join(_HERE, "csrc", "librpx.so")
 EXPORTS = (
     "rpx_init", "rpx_shutdown", "rpx_last_error", "rpx_abi_version", "rpx_scene_set",
     "rpx_host_alloc", "rpx_host_free", "rpx_rays_upload", "rpx_rays_download", "rpx_rays_count",
-    "rpx_rays_free", "rpx_trace_device", "rpx_trace", "rpx_result_n_generations",
+    "rpx_rays_free", "rpx_rays_clone", "rpx_trace_device", "rpx_trace", "rpx_result_n_generations",
     "rpx_result_counts", "rpx_result_generation", "rpx_result_face_counts",
     "rpx_result_device_ms", "rpx_result_launches", "rpx_result_kernel_ms", "rpx_result_free",
     "rpx_stream", "rpx_unit_face_intersect", "rpx_unit_face_normal", "rpx_unit_material_eval",
@@ -65,6 +65,8 @@ def load():
     L.rpx_rays_download.restype = i32
     L.rpx_rays_count.argtypes = [vp]
     L.rpx_rays_count.restype = u64
+    L.rpx_rays_clone.argtypes = [vp, vp, pvp]
+    L.rpx_rays_clone.restype = i32
     L.rpx_rays_free.argtypes = [vp, vp]
     L.rpx_rays_free.restype = None
     L.rpx_trace_device.argtypes = [vp, vp, d, i32, u32, pvp]

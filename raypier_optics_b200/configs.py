@@ -156,6 +156,8 @@ def _facelist(core, owner, faces):
     fl = core.ctracer.FaceList(owner=owner)
     fl.faces = faces
     fl.sync_transforms()
+    for f in faces:
+        f.update()  # owner -> face parameter copy that trace_rays performs (core/tracer.py:32)
     return fl
 
 

@@ -359,6 +359,26 @@ extern "C" void rpx_rays_free(rpx_ctx* ctx, rpx_rays* rays) {
 
 extern "C" uint64_t rpx_rays_count(const rpx_rays* rays) { return rays ? rays->soa.n : 0; }
 
+extern "C" int rpx_rays_clone(rpx_ctx* ctx, const rpx_rays* rays, rpx_rays** out_rays) {
+    if (!ctx || !rays || !out_rays) return fail(ctx, RPX_ERR_INVALID, "NULL argument");
+    CU(ctx, cudaSetDevice(ctx->device));
+    rpx_rays* r = nullptr;
+    int rc = rays_alloc(ctx, rays->soa.cap, rays->is_gausslet, &r);
+    if (rc != RPX_OK) return rc;
+    r->soa.n = rays->soa.n;
+    if (r->bytes != rays->bytes) {
+        rpx_rays_free(ctx, r);
+        return fail(ctx, RPX_ERR_INVALID, "clone size mismatch");
+    }
+    cudaError_t e = cudaMemcpyAsync(r->block, rays->block, rays->bytes, cudaMemcpyDeviceToDevice, ctx->stream);
+    if (e != cudaSuccess) {
+        rpx_rays_free(ctx, r);
+        return fail(ctx, RPX_ERR_CUDA, "device copy failed: %s", cudaGetErrorString(e));
+    }
+    *out_rays = r;
+    return RPX_OK;
+}
+
 static cudaEvent_t next_event(rpx_ctx* ctx) {
     if (ctx->ev_used == ctx->ev_pool.size()) {
         cudaEvent_t ev;

@@ -1,0 +1,114 @@
+"""Multi-GPU sharding of a trace.
+
+A ray never interacts with another ray, so the source rays are split into contiguous
+blocks in index order, one block per rank (one process per GPU), scene tables replicated,
+and every rank runs the whole generation loop on its block with NO collective inside the
+loop.  Because children are emitted in parent order, the concatenation of the ranks'
+generation g in rank order *is* the single-GPU generation g, up to the parent index:
+
+    global_parent_idx = local_parent_idx + sum_{r' < rank} count_{g-1}(r')
+
+The only collectives (torch.distributed: NCCL over NVLink on GPUs, gloo in the CPU tests)
+run after the trace: an all-gather of the per-generation counts, an all-reduce of the
+per-face hit counts, and an optional gather of generations to rank 0.
+"""
+import numpy as np
+
+
+def shard_bounds(n, world_size, rank):
+    """Contiguous block [lo, hi) of rank ``rank`` when ``n`` rays are split over ranks."""
+    return (rank * n) // world_size, ((rank + 1) * n) // world_size
+
+
+def shard_rays(rays, world_size, rank):
+    lo, hi = shard_bounds(rays.shape[0], world_size, rank)
+    return np.ascontiguousarray(rays[lo:hi])
+
+
+def _dist():
+    import torch.distributed as dist
+    return dist
+
+
+def exchange_counts(counts, face_counts, device=None, group=None):
+    """All-gather the per-generation ray counts and all-reduce the per-face hit counts.
+
+    Returns (counts_all, face_counts_total): counts_all[r][g] (int64, zero padded to the
+    longest trace) and the summed Face.count array.
+    """
+    import torch
+    dist = _dist()
+    world = dist.get_world_size(group)
+    n_gen = torch.tensor([len(counts)], dtype=torch.int64, device=device)
+    dist.all_reduce(n_gen, op=dist.ReduceOp.MAX, group=group)
+    g_max = int(n_gen.item())
+    local = torch.zeros(max(g_max, 1), dtype=torch.int64, device=device)
+    if counts:
+        local[:len(counts)] = torch.tensor(list(counts), dtype=torch.int64, device=device)
+    gathered = [torch.zeros_like(local) for _ in range(world)]
+    dist.all_gather(gathered, local, group=group)
+    fc = torch.as_tensor(np.asarray(face_counts, dtype=np.int64), device=device).clone()
+    dist.all_reduce(fc, op=dist.ReduceOp.SUM, group=group)
+    counts_all = np.stack([g.cpu().numpy() for g in gathered])[:, :g_max]
+    return counts_all, fc.cpu().numpy()
+
+
+def parent_offsets(counts_all, rank):
+    """offset[g] = number of rays of generation g held by lower ranks."""
+    return counts_all[:rank].sum(axis=0) if rank > 0 else np.zeros(counts_all.shape[1], dtype=np.int64)
+
+
+def globalize_generation(arr, g, offsets):
+    """Rewrite ``parent_idx`` of local generation ``g`` (g >= 1) into the global numbering."""
+    if g == 0 or arr.shape[0] == 0:
+        return arr
+    base = arr['base_ray'] if 'base_ray' in (arr.dtype.names or ()) else arr
+    base['parent_idx'] = (base['parent_idx'].astype(np.int64) + int(offsets[g - 1])).astype(np.uint32)
+    return arr
+
+
+def gather_generation(arr, counts_g, dst=0, device=None, group=None):
+    """Gather one (globalized) generation to ``dst`` in rank order.  ``counts_g[r]`` is the
+    size of rank r's part.  Returns the concatenated array on ``dst`` and None elsewhere."""
+    import torch
+    dist = _dist()
+    world, rank = dist.get_world_size(group), dist.get_rank(group)
+    itemsize = arr.dtype.itemsize
+    nmax = int(max(counts_g)) if len(counts_g) else 0
+    buf = torch.zeros(max(nmax * itemsize, 1), dtype=torch.uint8, device=device)
+    raw = torch.from_numpy(np.ascontiguousarray(arr).view(np.uint8).reshape(-1).copy())
+    buf[:raw.numel()] = raw.to(buf.device)
+    if rank == dst:
+        parts = [torch.zeros_like(buf) for _ in range(world)]
+        dist.gather(buf, parts, dst=dst, group=group)
+        out = [p.cpu().numpy()[:int(c) * itemsize].view(arr.dtype) for p, c in zip(parts, counts_g)]
+        return np.concatenate(out) if out else arr[:0]
+    dist.gather(buf, None, dst=dst, group=group)
+    return None
+
+
+def trace_sharded(trace_fn, rays, world_size, rank, device=None, group=None, gather_to=None):
+    """Trace this rank's contiguous block of ``rays`` with ``trace_fn(block) ->
+    (list_of_generation_arrays, face_counts)`` and stitch the global numbering.
+
+    Returns dict(local=list of globalized generations, counts_all, face_counts, gathered)
+    where ``gathered`` is the full trace on rank ``gather_to`` (if requested)."""
+    block = shard_rays(rays, world_size, rank)
+    gens, face_counts = trace_fn(block)
+    counts_all, fc = exchange_counts([len(g) for g in gens], face_counts, device=device, group=group)
+    offs = parent_offsets(counts_all, rank)
+    n_gen = counts_all.shape[1]
+    dtype = rays.dtype
+    local = []
+    for g in range(n_gen):
+        arr = gens[g] if g < len(gens) else np.zeros(0, dtype=dtype)
+        local.append(globalize_generation(arr, g, offs))
+    gathered = None
+    if gather_to is not None:
+        gathered = []
+        for g in range(n_gen):
+            full = gather_generation(local[g], counts_all[:, g], dst=gather_to, device=device, group=group)
+            gathered.append(full)
+        if rank != gather_to:
+            gathered = None
+    return dict(local=local, counts_all=counts_all, face_counts=fc, gathered=gathered)

@@ -135,6 +135,24 @@ class Engine(object):
         self._check(self._L.rpx_rays_upload(self._ctx, rays.ctypes.data, rays.shape[0], is_g, C.byref(h)))
         return DeviceRays(self, h, is_g)
 
+    def clone(self, dev_rays):
+        h = C.c_void_p()
+        self._check(self._L.rpx_rays_clone(self._ctx, dev_rays._h, C.byref(h)))
+        return DeviceRays(self, h, dev_rays.is_gausslet)
+
+    def pinned_empty(self, n, dtype):
+        """numpy array over page-locked host memory (rpx_host_alloc)."""
+        dtype = np.dtype(dtype)
+        nbytes = max(int(n) * dtype.itemsize, 1)
+        ptr = self._L.rpx_host_alloc(nbytes)
+        if not ptr:
+            raise MemoryError("rpx_host_alloc(%d) failed" % nbytes)
+        buf = (C.c_char * nbytes).from_address(ptr)
+        arr = np.frombuffer(buf, dtype=dtype, count=int(n))
+        self._pinned = getattr(self, "_pinned", [])
+        self._pinned.append(ptr)
+        return arr
+
     def download(self, dev_rays):
         n = len(dev_rays)
         out = np.empty(n, dtype=A.gausslet_dtype if dev_rays.is_gausslet else A.ray_dtype)

@@ -1,0 +1,132 @@
+"""Host-side logic that needs no GPU: Zernike tape construction, scene validation errors,
+collection containers, sharding arithmetic."""
+import numpy as np
+import pytest
+
+from raypier_optics_b200 import _abi as A
+from raypier_optics_b200 import configs, distributed, scene as SC
+
+
+def test_zernike_tape_matches_recursive_oracle(core):
+    """The host-built straight-line tape must evaluate to exactly what the reference's
+    memoised recursion gives (the oracle runs the recursion itself)."""
+    from oracle import oracle as O
+    D, F, S = core.cdistortions, core.cfaces, core.cshapes
+    coefs = {"j%d" % j: 0.001 * ((-1) ** j) * (j + 1) for j in (1, 2, 3, 4, 5, 7, 8, 11, 12, 13, 17, 22, 24, 28)}
+    dist = D.ZernikeDistortion(unit_radius=7.5, **coefs)
+    shape = S.CircleShape(radius=10.0)
+    face = F.DistortionFace(base_face=F.ShapedPlanarFace(shape=shape), distortion=dist, shape=shape)
+    fl = core.ctracer.FaceList()
+    fl.faces = [face]
+    sc = SC.Scene([fl], np.array([1.0]))
+    d = sc.distortions[0]
+    K = A.ZERNIKE_MAX_K
+
+    def run_tape(off, length, r):
+        ws = np.full((3, K), np.nan)
+
+        def op(o):
+            if o < 2:
+                return float(o)
+            k, w = divmod(o - 2, 3)
+            return ws[w, k]
+        for t in sc.ztape[off:off + length]:
+            a, b, c = op(t['a']), op(t['b']), op(t['c'])
+            if t['kind'] == 0:
+                ws[0, t['dst']] = r * (a + b) - c
+            elif t['kind'] == 1:
+                v = a + b
+                v += r * (op(t['d']) + op(t['e']))
+                ws[1, t['dst']] = v - c
+            elif t['kind'] == 2:
+                ws[2, t['dst']] = (a + b) - c
+            else:
+                ws[0, t['dst']] = 1.0
+        return op
+
+    rng = np.random.default_rng(0)
+    for _ in range(20):
+        x, y = rng.uniform(-7, 7, 2)
+        xn, yn = x / 7.5, y / 7.5
+        r, theta = np.sqrt(xn * xn + yn * yn), np.arctan2(yn, xn)
+        opz = run_tape(d['tape_z_off'], d['tape_z_len'], r)
+        opg = run_tape(d['tape_g_off'], d['tape_g_len'], r)
+        Z, Zg = 0.0, np.zeros(3)
+        for c in sc.zcoefs[d['coef_off']:d['coef_off'] + d['n_coefs']]:
+            n, m = int(c['n']), int(c['m'])
+            N = (np.sqrt(n + 1) if m == 0 else np.sqrt(2 * (n + 1))) * c['value']
+            PH = np.cos(m * theta) if m >= 0 else -np.sin(m * theta)
+            PHp = -m * np.sin(m * theta) if m >= 0 else -m * np.cos(m * theta)
+            Z += N * opz(c['opR_z']) * PH
+            R, Rp, Rr = opg(c['opR']), opg(c['opRp']), opg(c['opRr'])
+            Zg[2] += N * R * PH
+            Zg[0] += N * (Rp * np.cos(theta) * PH + Rr * (-np.sin(theta)) * PHp)
+            Zg[1] += N * (Rp * np.sin(theta) * PH + Rr * (np.cos(theta)) * PHp)
+        Zg[:2] /= 7.5
+        assert Z == pytest.approx(O.distortion_z(sc, 0, x, y), rel=1e-13, abs=1e-15)
+        assert np.allclose(Zg, O.distortion_zgrad(sc, 0, x, y), rtol=1e-12, atol=1e-15)
+
+
+def test_unsupported_types_are_reported(core):
+    class UVPatchFace(core.ctracer.Face):
+        pass
+    fl = core.ctracer.FaceList()
+    fl.faces = [UVPatchFace()]
+    with pytest.raises(SC.UnsupportedSceneError):
+        SC.Scene([fl], np.array([1.0]))
+    fl.faces = [core.cfaces.CircularFace(material=core.cmaterials.ResampleGaussletMaterial())]
+    with pytest.raises(SC.UnsupportedSceneError):
+        SC.Scene([fl], np.array([1.0]))
+
+
+def test_subclasses_resolve_through_mro(core):
+    class MyLensFace(core.cfaces.SphericalFace):
+        pass
+    fl = core.ctracer.FaceList()
+    fl.faces = [MyLensFace(diameter=10.0, curvature=30.0)]
+    sc = SC.Scene([fl], np.array([1.0]))
+    assert sc.faces[0]['type'] == A.FACE_SPHERICAL
+
+
+def test_scene_roundtrip_through_dict(core):
+    cfg = configs.build(core, "config3", n=10)
+    sc = SC.Scene(cfg['face_lists'], cfg['wavelengths'])
+    back = SC.Scene.from_dict(sc.to_dict())
+    for t in SC.Scene.TABLES:
+        assert np.asarray(getattr(sc, t)).tobytes() == np.asarray(getattr(back, t)).tobytes()
+    assert back.c_scene.n_traced_faces == 2 and back.c_scene.n_faces == 3
+
+
+def test_collections_behave_like_the_reference(core):
+    ct = core.ctracer
+    rays = configs.disc_source(10, (0, 0, 0), (0, 0, 1), 1.0, seed=1)
+    rc = ct.RayCollection.from_array(rays)
+    rc.wavelengths = [0.5]
+    assert len(rc) == rc.n_rays == 10
+    a = rc.copy_as_array()
+    a['length'] = 3.0
+    assert np.all(np.isinf(rc.length))          # copy_as_array always copies
+    rc.reset_length(7.0)
+    assert np.all(rc.length == 7.0)
+    child = ct.RayCollection.from_array(rays[:4])
+    child.parent = rc
+    assert child.parent is rc and np.array_equal(child.wavelengths, rc.wavelengths)
+    with pytest.raises(ValueError):
+        ct.RayCollection.from_array(np.zeros(3))
+    gc = ct.GaussletCollection.from_rays(rays)
+    assert gc.copy_as_array().dtype == A.gausslet_dtype
+    assert np.array_equal(gc.para_origin[:, 3], rays['origin'])
+
+
+def test_shard_bounds_cover_everything():
+    for n in (0, 1, 7, 1000003):
+        for w in (1, 2, 8):
+            spans = [distributed.shard_bounds(n, w, r) for r in range(w)]
+            assert spans[0][0] == 0 and spans[-1][1] == n
+            assert all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
+
+
+def test_parent_offsets():
+    counts_all = np.array([[4, 4, 7], [3, 5, 5]])
+    assert distributed.parent_offsets(counts_all, 0).tolist() == [0, 0, 0]
+    assert distributed.parent_offsets(counts_all, 1).tolist() == [4, 4, 7]

@@ -1,0 +1,50 @@
+"""Pins the plain-C oracle against the REAL reference (raypier/core built unmodified into
+oracle/_ref): every parity case must agree BIT FOR BIT (same gcc, same flags, no FMA
+contraction).  Skipped where the reference is not built (the GPU box)."""
+import numpy as np
+import pytest
+
+from raypier_optics_b200 import scene as SC
+
+from util import PARITY_CASES, build_case
+
+
+@pytest.mark.parametrize("name,kw,rl", PARITY_CASES, ids=[c[0] + "-" + str(i) for i, c in enumerate(PARITY_CASES)])
+def test_oracle_bit_exact_with_reference(refcore, name, kw, rl):
+    from oracle import oracle as O
+    kw = dict(kw, n=min(kw.get("n", 2000), 4000))
+    cfg = build_case(refcore, name, kw, rl)
+    rc = O.reference_collection(refcore, cfg['rays'], cfg['wavelengths'])
+    traced, all_faces = O.reference_trace_rays(refcore, rc, cfg['face_lists'], cfg['recursion_limit'],
+                                               cfg['max_length'])
+    ref = [t.copy_as_array() for t in traced]
+    sc = SC.Scene(cfg['face_lists'], cfg['wavelengths'])
+    gens, counts = O.trace_rays(sc, cfg['rays'], cfg['recursion_limit'], cfg['max_length'])
+    assert [len(g) for g in gens] == [len(r) for r in ref]
+    for gi, (g, r) in enumerate(zip(gens, ref)):
+        assert g.tobytes() == r.tobytes(), "%s generation %d is not bit-identical" % (name, gi)
+    assert counts.tolist() == [f.count for f in all_faces]
+
+
+def test_mirror_sources_match_reference_gausslet_setup(refcore, core):
+    """GaussletCollection.from_rays + config_parabasal_rays of the host mirror reproduce the
+    reference's (ctracer.pyx:1321-1345, 1430-1481) bit for bit."""
+    from raypier_optics_b200 import configs
+    a = configs.build(core, "config5", n=500, gausslets=True)['rays']
+    b = configs.build(refcore, "config5", n=500, gausslets=True)['rays']
+    assert a.tobytes() == b.tobytes()
+
+
+def test_dispersion_curves_match_reference(refcore, core):
+    from raypier_optics_b200 import configs
+    wl = np.array([0.45, 0.55, 0.65, 0.8, 1.0])
+    for glass in configs.GLASS:
+        a = configs.glass_curve(core, glass, absorption=0.3).evaluate_n(wl)
+        b = configs.glass_curve(refcore, glass, absorption=0.3).evaluate_n(wl)
+        assert np.array_equal(a, b)
+    M, R = core.cmaterials, refcore.cmaterials
+    coefs3 = np.array([2.1, 0.01, 2.0, -0.003, -2.0, 0.0002, 4.0])
+    for fid, coefs in ((1, np.array([0.0, 0.6961663, 0.0684043, 0.4079426, 0.1162414, 0.8974794, 9.896161])),
+                       (3, coefs3), (0, np.array([1.37]))):
+        assert np.array_equal(M.BaseDispersionCurve(fid, coefs).evaluate_n(wl),
+                              R.BaseDispersionCurve(fid, coefs).evaluate_n(wl))
