@@ -16,7 +16,7 @@
 #include <vector>
 
 #include "../../include/rpx.h"
-#include "rpx_kernels.cuh"
+#include "rpx_launch.h"
 #include "rpx_unit.cuh"
 
 using namespace rpx;
@@ -57,6 +57,8 @@ struct rpx_ctx {
     int n_traced;
     int max_kids;       // upper bound of children per hit over all materials in the scene
     int scene_smem;     // bytes of shared memory the staged scene needs (0 = use global)
+    int face_class;     // RPX_FC_SIMPLE / RPX_FC_FULL kernel variant for this scene
+    int mm_idx;         // material-mask kernel variant: 0 LIGHT, 1 COATED, 2 FULLDIEL, 3 ALL
     // scratch
     unsigned long long* tile_state;
     size_t tile_state_cap;  // tiles
@@ -310,6 +312,24 @@ extern "C" int rpx_scene_set(rpx_ctx* ctx, const rpx_scene* s) {
                       t == RPX_MAT_FULL_DIELECTRIC || t == RPX_MAT_COATED) ? 2 : 1;
         if (kids > ctx->max_kids) ctx->max_kids = kids;
     }
+    // kernel variant: the smallest compiled face class / material mask covering the scene
+    ctx->face_class = RPX_FC_SIMPLE;
+    for (int i = 0; i < s->n_faces; i++) {
+        int t = s->faces[i].type;
+        bool simple = t == RPX_FACE_CIRCULAR || t == RPX_FACE_SHAPED_PLANAR || t == RPX_FACE_ELLIPTICAL_PLANE ||
+                      t == RPX_FACE_RECTANGULAR || t == RPX_FACE_SPHERICAL || t == RPX_FACE_SHAPED_SPHERICAL ||
+                      t == RPX_FACE_EXTRUDED_PLANAR || t == RPX_FACE_POLYGON || t == RPX_FACE_ORIENTED_POLYGON;
+        if (!simple) ctx->face_class = RPX_FC_FULL;
+    }
+    uint32_t used = 0;
+    for (int i = 0; i < s->n_traced_faces; i++) used |= RPX_MBIT(s->materials[s->faces[i].material].type);
+    const uint32_t masks[RPX_N_MM] = {RPX_MM_LIGHT, RPX_MM_COATED, RPX_MM_FULLDIEL, RPX_MM_ALL};
+    ctx->mm_idx = RPX_N_MM - 1;
+    for (int m = 0; m < RPX_N_MM; m++)
+        if ((used & ~masks[m]) == 0) {
+            ctx->mm_idx = m;
+            break;
+        }
     size_t smem = (size_t)s->n_faces * sizeof(rpx_face) + (size_t)s->n_face_sets * sizeof(rpx_face_set);
     ctx->scene_smem = smem <= 40 * 1024 ? (int)smem : 0;
     if (ctx->d_face_counts) {
@@ -505,14 +525,16 @@ extern "C" int rpx_trace_device(rpx_ctx* ctx, rpx_rays* rays, double max_length,
         res->gens.push_back(cur);
         res->counts.push_back(n);
         const uint32_t n_tiles = (uint32_t)((n + RPX_TILE - 1) / RPX_TILE);
-        // ---- nearest hit
-        cudaEvent_t a0 = next_event(ctx), a1 = next_event(ctx);
-        CUR(cudaEventRecord(a0, st));
-        k_intersect<<<n_tiles, RPX_TILE, smem, st>>>(ctx->ds, cur->soa, ml, smem);
-        CUR(cudaGetLastError());
-        CUR(cudaEventRecord(a1, st));
-        ev_i0.push_back(a0);
-        ev_i1.push_back(a1);
+        // ---- nearest hit: generation 0 only (k_shade traces its children ahead)
+        if (count == 0) {
+            cudaEvent_t a0 = next_event(ctx), a1 = next_event(ctx);
+            CUR(cudaEventRecord(a0, st));
+            CUR(launch_intersect(ctx->face_class, st, n_tiles, smem, ctx->ds, cur->soa, ml));
+            CUR(cudaEventRecord(a1, st));
+            ev_i0.push_back(a0);
+            ev_i1.push_back(a1);
+            res->launches++;
+        }
         // ---- children
         unsigned long long cap_child = n * (unsigned long long)(ctx->max_kids > 0 ? ctx->max_kids : 1);
         if (cap_child >= 0xFFFFFFFFull)
@@ -533,19 +555,31 @@ extern "C" int rpx_trace_device(rpx_ctx* ctx, rpx_rays* rays, double max_length,
         CUR(cudaMemsetAsync(ctx->tile_counter, 0, sizeof(uint32_t), st));
         cudaEvent_t b0 = next_event(ctx), b1 = next_event(ctx);
         CUR(cudaEventRecord(b0, st));
-        if (is_g)
-            k_shade<true><<<n_tiles, RPX_TILE, smem, st>>>(ctx->ds, cur->soa, child->soa, ml, ctx->tile_state,
-                                                          ctx->tile_counter, ctx->d_count, ctx->d_face_counts,
-                                                          n_tiles, smem);
-        else
-            k_shade<false><<<n_tiles, RPX_TILE, smem, st>>>(ctx->ds, cur->soa, child->soa, ml, ctx->tile_state,
-                                                           ctx->tile_counter, ctx->d_count, ctx->d_face_counts,
-                                                           n_tiles, smem);
-        CUR(cudaGetLastError());
+        {
+            ShadeArgs sa;
+            sa.S = ctx->ds;
+            sa.in = cur->soa;
+            sa.out = child->soa;
+            sa.max_length = ml;
+            sa.tile_state = ctx->tile_state;
+            sa.tile_counter = ctx->tile_counter;
+            sa.d_count = ctx->d_count;
+            sa.face_counts = ctx->d_face_counts;
+            sa.n_tiles = n_tiles;
+            sa.smem_bytes = smem;
+            cudaError_t le;
+            if (is_g)
+                le = ctx->face_class == RPX_FC_SIMPLE ? launch_shade_g1_f0(ctx->mm_idx, st, sa)
+                                                      : launch_shade_g1_f1(ctx->mm_idx, st, sa);
+            else
+                le = ctx->face_class == RPX_FC_SIMPLE ? launch_shade_g0_f0(ctx->mm_idx, st, sa)
+                                                      : launch_shade_g0_f1(ctx->mm_idx, st, sa);
+            CUR(le);
+        }
         CUR(cudaEventRecord(b1, st));
         ev_s0.push_back(b0);
         ev_s1.push_back(b1);
-        res->launches += 2;
+        res->launches += 1;
         // ---- len(new_rays): the only host round trip of a generation
         CUR(cudaMemcpyAsync(ctx->h_count, ctx->d_count, sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
         CUR(cudaStreamSynchronize(st));

@@ -30,6 +30,18 @@ struct DevScene {
     int n_traced, n_faces, n_sets, n_mats, n_wl, n_dists;
 };
 
+// Face-class specialisation of the kernels.  A scene made only of planes, spheres,
+// extrusions and polygons runs kernels compiled WITHOUT the Newton / quadric / distortion
+// code (RPX_FC_SIMPLE): fewer registers, no spills, a code footprint the instruction cache
+// holds.  The host picks the variant from the face types present (rpx_scene_set).
+#define RPX_FC_SIMPLE 0
+#define RPX_FC_FULL 1
+RPX_DEV bool face_type_is_simple(int t) {
+    return t == RPX_FACE_CIRCULAR || t == RPX_FACE_SHAPED_PLANAR || t == RPX_FACE_ELLIPTICAL_PLANE ||
+           t == RPX_FACE_RECTANGULAR || t == RPX_FACE_SPHERICAL || t == RPX_FACE_SHAPED_SPHERICAL ||
+           t == RPX_FACE_EXTRUDED_PLANAR || t == RPX_FACE_POLYGON || t == RPX_FACE_ORIENTED_POLYGON;
+}
+
 #define RPX_INF (__longlong_as_double(0x7ff0000000000000LL))
 #define RPX_NO_HIT (-1.0)
 
@@ -40,7 +52,7 @@ RPX_DEV int shape_polygon_inside(const double* pts, int size, double X, double Y
     for (int i = 0; i < size; i++) {
         double y2 = pts[2 * i + 1], x2 = pts[2 * i];
         if ((y1 <= Y && Y < y2) || (y2 <= Y && Y < y1)) {
-            if ((x1 + (Y - y1) * (x2 - x1) / (y2 - y1)) > X) ct = !ct;
+            if ((x1 + fdiv((Y - y1) * (x2 - x1), y2 - y1)) > X) ct = !ct;
         }
         y1 = y2;
         x1 = x2;
@@ -49,7 +61,7 @@ RPX_DEV int shape_polygon_inside(const double* pts, int size, double X, double Y
 }
 
 // Shape tree as a postfix program on a bit stack (bit i of `stack` = i-th entry).
-__device__ __noinline__ int shape_inside(const DevScene& S, const rpx_face* f, double x, double y) {
+static __device__ __noinline__ int shape_inside(const DevScene& S, const rpx_face* f, double x, double y) {
     if (f->shape_off < 0) return 1;
     uint32_t stack = 0;
     int sp = 0;
@@ -103,7 +115,7 @@ __device__ __noinline__ int shape_inside(const DevScene& S, const rpx_face* f, d
 }
 
 // ------------------------------------------------ implicit surfaces (cimplicit_surfs.pyx)
-__device__ __noinline__ double implicit_eval(const DevScene& S, int off, int len, vec3 p) {
+static __device__ __noinline__ double implicit_eval(const DevScene& S, int off, int len, vec3 p) {
     double stack[8];
     int sp = 0;
     for (int i = 0; i < len; i++) {
@@ -157,7 +169,7 @@ RPX_DEV void run_ztape(const DevScene& S, int off, int len, double r, double* ws
     }
 }
 
-__device__ __noinline__ double distortion_z(const DevScene& S, const rpx_distortion* D, double x, double y) {
+static __device__ __noinline__ double distortion_z(const DevScene& S, const rpx_distortion* D, double x, double y) {
     if (D->type == RPX_DIST_ZERNIKE_J7) {  // cdistortions.pyx:50-59
         x /= D->p[0];
         y /= D->p[0];
@@ -167,13 +179,13 @@ __device__ __noinline__ double distortion_z(const DevScene& S, const rpx_distort
     double ws[RPX_ZERNIKE_MAX_K];  // only row 0 is used by z_offset_c
     x /= D->p[0];
     y /= D->p[0];
-    double r = sqrt(x * x + y * y);
+    double r = sqrt_(x * x + y * y);
     double theta = atan2(y, x);
     run_ztape(S, D->tape_z_off, D->tape_z_len, r, ws);
     double Z = 0.0;
     for (int i = 0; i < D->n_coefs; i++) {
         const rpx_zcoef* c = &S.zcoefs[D->coef_off + i];
-        double N = (c->m == 0) ? sqrt((double)(c->n + 1)) : sqrt((double)(2 * (c->n + 1)));
+        double N = (c->m == 0) ? sqrt_((double)(c->n + 1)) : sqrt_((double)(2 * (c->n + 1)));
         N *= c->value;
         double PH = (c->m >= 0) ? cos(c->m * theta) : -sin(c->m * theta);  // Q11: signed m
         double R = zop(ws, c->opR_z);
@@ -183,7 +195,7 @@ __device__ __noinline__ double distortion_z(const DevScene& S, const rpx_distort
 }
 
 // -> (dz/dx, dz/dy, z)
-__device__ __noinline__ vec3 distortion_zgrad(const DevScene& S, const rpx_distortion* D, double x, double y) {
+static __device__ __noinline__ vec3 distortion_zgrad(const DevScene& S, const rpx_distortion* D, double x, double y) {
     if (D->type == RPX_DIST_ZERNIKE_J7) {  // cdistortions.pyx:61-81
         double root8 = sqrt(8.0) * D->p[1], R = D->p[0];
         x /= R;
@@ -194,7 +206,7 @@ __device__ __noinline__ vec3 distortion_zgrad(const DevScene& S, const rpx_disto
     double ws[3 * RPX_ZERNIKE_MAX_K];
     x /= D->p[0];
     y /= D->p[0];
-    double r = sqrt(x * x + y * y);
+    double r = sqrt_(x * x + y * y);
     double theta = atan2(y, x);
     run_ztape(S, D->tape_g_off, D->tape_g_len, r, ws);
     double st, ct;
@@ -213,7 +225,7 @@ __device__ __noinline__ vec3 distortion_zgrad(const DevScene& S, const rpx_disto
             PHprime = -c->m * cm;
         }
         double R = zop(ws, c->opR), Rprime = zop(ws, c->opRp), R_over_r = zop(ws, c->opRr);
-        double N = (c->m == 0) ? sqrt((double)(c->n + 1)) : sqrt((double)(2 * (c->n + 1)));
+        double N = (c->m == 0) ? sqrt_((double)(c->n + 1)) : sqrt_((double)(2 * (c->n + 1)));
         N *= c->value;
         Z.z += N * R * PH;
         Z.x += N * (Rprime * ct * PH + R_over_r * (-st) * PHprime);
@@ -230,7 +242,7 @@ RPX_DEV int point_in_polygon(double X, double Y, const double* pts, int size) {
     double y1 = pts[2 * (size - 1) + 1], x1 = pts[2 * (size - 1)];
     for (int i = 0; i < size; i++) {
         double y2 = pts[2 * i + 1], x2 = pts[2 * i];
-        double h = (Y - y1) / (y2 - y1);
+        double h = fdiv(Y - y1, y2 - y1);
         if (0 < h && h <= 1.0) {
             double x = x1 + h * (x2 - x1);
             if (x > X) ct = !ct;
@@ -251,9 +263,9 @@ RPX_DEV double intersect_conic(vec3 a, vec3 d, double curvature, double conic_co
     double C = -2 * R * a.z * beta + (a.x * a.x) * beta + (a.y * a.y) * beta + (a.z * a.z) * b2;
     double D = B * B - 4 * A * C;
     if (D < 0) return -1;
-    D = sqrt(D);
-    if (R * beta * d.z <= 0) return (-B + D) / (2 * A);
-    return (-B - D) / (2 * A);
+    D = sqrt_(D);
+    if (R * beta * d.z <= 0) return fdiv(-B + D, 2 * A);
+    return fdiv(-B - D, 2 * A);
 }
 
 struct Aspheric {
@@ -268,7 +280,7 @@ RPX_DEV void aspheric_f_df(const Aspheric& A, double alpha, double* f, double* d
     double r2 = px * px + py * py;
     double r4 = r2 * r2, r6 = r4 * r2, r8 = r4 * r4, r10 = r8 * r2, r12 = r8 * r4, r14 = r8 * r6,
            r16 = r8 * r8;
-    double root = sqrt(1 - A.beta * r2 / (A.R * A.R));
+    double root = sqrt_(1 - A.beta * r2 / (A.R * A.R));
     double out = r2;
     out /= A.R * (1 + root);
     out -= A.a.z + alpha * A.d.z;
@@ -297,8 +309,8 @@ RPX_DEV void extpoly_f_df(const rpx_face* f, const double* E, vec3 a, vec3 d, do
     double x = a.x + alpha * d.x, y = a.y + alpha * d.y;
     double r2 = x * x + y * y;
     double out = r2;
-    if (R >= 0) out /= (R + sqrt(R * R - beta * r2));
-    else out /= (R - sqrt(R * R - beta * r2));
+    if (R >= 0) out /= (R + sqrt_(R * R - beta * r2));
+    else out /= (R - sqrt_(R * R - beta * r2));
     out -= a.z + alpha * d.z;
     double xn = x / norm_radius, yn = y / norm_radius;
     double xi = 1.0;
@@ -314,7 +326,7 @@ RPX_DEV void extpoly_f_df(const rpx_face* f, const double* E, vec3 a, vec3 d, do
     *fo = out;
     if (dfo) {
         double R2 = R * R;
-        double rt = sqrt(1 - (beta * r2 / R2));
+        double rt = sqrt_(1 - (beta * r2 / R2));
         double denom = R * (rt + 1);
         double nom = (2 * d.x * x + 2 * d.y * y);
         double inv_rad = 1. / norm_radius;
@@ -351,12 +363,11 @@ RPX_DEV void extpoly_f_df(const rpx_face* f, const double* E, vec3 a, vec3 d, do
 
 // Plane z = z0 with parametric test h in [tol, 1]; returns h or <0
 RPX_DEV double plane_h(double z0, vec3 p1, vec3 p2, double tol, bool* ok) {
-    double h = (z0 - p1.z) / (p2.z - p1.z);
+    double h = fdiv(z0 - p1.z, p2.z - p1.z);
     *ok = !((h < tol) || (h > 1.0));
     return h;
 }
 
-__device__ vec3 face_normal(const DevScene& S, const rpx_face* f, vec3 p);
 
 // The two roots a1 (+) and a2 (-) of a quadric with the sphere-style hemisphere and
 // aperture culling shared by Spherical / ShapedSpherical faces.
@@ -371,10 +382,11 @@ RPX_DEV double sphere_hit(const DevScene& S, const rpx_face* f, vec3 r, vec3 p2,
     double C = mag_sq(d) - curvature * curvature;
     double D = B * B - 4 * A * C;
     if (D < 0) return RPX_NO_HIT;
-    D = sqrt(D);
-    double a1 = (-B + D) / (2 * A);
+    D = sqrt_(D);
+    const double inv2A = rcp(2 * A);
+    double a1 = (-B + D) * inv2A;
     vec3 pt1 = r + s * a1;
-    double a2 = (-B - D) / (2 * A);
+    double a2 = (-B - D) * inv2A;
     vec3 pt2 = r + s * a2;
     if (curvature >= 0) {
         if (pt1.z < cz) a1 = RPX_INF;
@@ -395,10 +407,11 @@ RPX_DEV double sphere_hit(const DevScene& S, const rpx_face* f, vec3 r, vec3 p2,
     }
     if (a2 < a1) a1 = a2;
     if (a1 > 1.0 || a1 < f->tolerance) return RPX_NO_HIT;
-    return a1 * sep(r, p2);
+    return a1 * sqrt_(A);  // sep(r, p2) == sqrt_(mag_sq(s))
 }
 
 // Face.intersect_c for the simple (non-wrapping) face classes.
+template <int FC>
 __device__ double face_intersect_basic(const DevScene& S, const rpx_face* f, vec3 p1, vec3 p2,
                                        int is_base_ray) {
     const double* P = f->p;
@@ -423,10 +436,11 @@ __device__ double face_intersect_basic(const DevScene& S, const rpx_face* f, vec
             return h * sep(p1, p2);
         }
         case RPX_FACE_IMPLICIT_PLANAR: {  // :280-307
+            if (FC == RPX_FC_SIMPLE) return RPX_NO_HIT;
             vec3 normal = ld3(P + 3), origin = ld3(P);
             vec3 dp = p2 - p1;
             vec3 po = origin - p1;
-            double h = dot(po, normal) / dot(dp, normal);
+            double h = fdiv(dot(po, normal), dot(dp, normal));
             if ((h < tol) || (h > 1.0)) return RPX_NO_HIT;
             po = p1 + dp * h;
             if (is_base_ray && implicit_eval(S, f->aux_off, f->aux_n, po) > 0.0) return RPX_NO_HIT;
@@ -434,8 +448,8 @@ __device__ double face_intersect_basic(const DevScene& S, const rpx_face* f, vec
         }
         case RPX_FACE_ELLIPTICAL_PLANE: {  // :322-341
             double gx = P[0], gy = P[1], d = P[2];
-            double h = (gx * p1.x + gy * p1.y - p1.z) /
-                       ((p2.z - p1.z) - gx * (p2.x - p1.x) - gy * (p2.y - p1.y));
+            double h = fdiv(gx * p1.x + gy * p1.y - p1.z,
+                            (p2.z - p1.z) - gx * (p2.x - p1.x) - gy * (p2.y - p1.y));
             if ((h < tol) || (h > 1.0)) return RPX_NO_HIT;
             double X = p1.x + h * (p2.x - p1.x);
             double Y = p1.y + h * (p2.y - p1.y);
@@ -464,11 +478,11 @@ __device__ double face_intersect_basic(const DevScene& S, const rpx_face* f, vec
             vec3 s = p2 - r;
             double den = (s.x * vy - s.y * vx);
             if (is_base_ray) {
-                double a = (s.y * (ux - r.x) - s.x * (uy - r.y)) / den;
+                double a = fdiv(s.y * (ux - r.x) - s.x * (uy - r.y), den);
                 if (a < 0) return RPX_NO_HIT;
                 if (a > 1) return RPX_NO_HIT;
             }
-            double a = (vx * (r.y - uy) - vy * (r.x - ux)) / den;
+            double a = fdiv(vx * (r.y - uy) - vy * (r.x - ux), den);
             if (is_base_ray) {
                 double dz = a * (p2.z - r.z);
                 if (P[4] < (r.z + dz) && (r.z + dz) < P[5]) return a * mag(s);
@@ -493,7 +507,7 @@ __device__ double face_intersect_basic(const DevScene& S, const rpx_face* f, vec
             line = norm(line);
             double h = dot(line, n);
             if (h == 0.0) return RPX_NO_HIT;
-            h = dot(o - p1, n) / h;
+            h = fdiv(dot(o - p1, n), h);
             if ((h < tol) || (h > max_length)) return RPX_NO_HIT;
             if (is_base_ray) {
                 line = (p1 + line * h) - o;
@@ -505,6 +519,7 @@ __device__ double face_intersect_basic(const DevScene& S, const rpx_face* f, vec
             return h;
         }
         case RPX_FACE_OFFAXIS_PARABOLIC: {  // :1228-1298
+            if (FC == RPX_FC_SIMPLE) return RPX_NO_HIT;
             double efl = P[0], diameter = P[1];
             double A = 1 / (2 * efl);
             vec3 s = p2 - p1;
@@ -523,7 +538,7 @@ __device__ double face_intersect_basic(const DevScene& S, const rpx_face* f, vec
                 if (a1 > 1.0 || a1 < tol) return RPX_NO_HIT;
                 return a1 * sep(p1, p2);
             }
-            d = sqrt(d);
+            d = sqrt_(d);
             double a1 = (-b + d) / (2 * a);
             vec3 pt1 = r + s * a1;
             double a2 = (-b - d) / (2 * a);
@@ -541,6 +556,7 @@ __device__ double face_intersect_basic(const DevScene& S, const rpx_face* f, vec
             return a1 * sep(p1, p2);
         }
         case RPX_FACE_ELLIPSOIDAL: {  // :1344-1393
+            if (FC == RPX_FC_SIMPLE) return RPX_NO_HIT;
             const double* T = S.pool + f->aux_off;
             vec3 Sv = p2 - p1;
             vec3 r = transform_pt(T, p1);
@@ -551,7 +567,7 @@ __device__ double face_intersect_basic(const DevScene& S, const rpx_face* f, vec
             double b = 2 * (A * (r.z * s.z + r.y * s.y) + B * r.x * s.x);
             double c = A * (r.z * r.z + r.y * r.y) + B * r.x * r.x - A * B;
             double d = b * b - 4 * a * c;
-            d = sqrt(d);
+            d = sqrt_(d);
             double root1 = (-b + d) / (2 * a);
             double root2 = (-b - d) / (2 * a);
             vec3 q2 = p1 + Sv * root2;
@@ -571,6 +587,7 @@ __device__ double face_intersect_basic(const DevScene& S, const rpx_face* f, vec
             return root1 * mag(Sv);
         }
         case RPX_FACE_SADDLE: {  // :1439-1495
+            if (FC == RPX_FC_SIMPLE) return RPX_NO_HIT;
             double A = sqrt(6.0), root, denom, a1, a2;
             A *= P[1];
             vec3 p = p1;
@@ -588,7 +605,7 @@ __device__ double face_intersect_basic(const DevScene& S, const rpx_face* f, vec
                        A2 * (d.y * d.y) * (p.x * p.x) + 4 * A * d.x * d.y * p.z - 2 * A * d.x * d.z * p.y -
                        2 * A * d.y * d.z * p.x + d.z * d.z;
                 if (root < 0) return RPX_NO_HIT;
-                root = sqrt(root);
+                root = sqrt_(root);
                 denom = 2 * A * (d.x * d.y);
                 a1 = a2 = -A * d.x * p.y - A * d.y * p.x + d.z;
                 a1 += root;
@@ -609,6 +626,7 @@ __device__ double face_intersect_basic(const DevScene& S, const rpx_face* f, vec
             return a1 * sep(p1, p2);
         }
         case RPX_FACE_CYLINDRICAL: {  // :1526-1584
+            if (FC == RPX_FC_SIMPLE) return RPX_NO_HIT;
             double R = P[1];
             double R2 = R * R;
             vec3 o = p1;
@@ -618,7 +636,7 @@ __device__ double face_intersect_basic(const DevScene& S, const rpx_face* f, vec
             double root = R2 * dz2 - 2 * R * dx2 * o.z + 2 * R * d.x * d.z * o.x - dx2 * oz2 +
                           2 * d.x * d.z * o.x * o.z - dz2 * ox2;
             if (root < 0) return RPX_NO_HIT;
-            root = sqrt(root);
+            root = sqrt_(root);
             double denom = dx2 + dz2;
             double a1, a2;
             a1 = a2 = -R * d.z - d.x * o.x - d.z * o.z;
@@ -645,6 +663,7 @@ __device__ double face_intersect_basic(const DevScene& S, const rpx_face* f, vec
             return a1 * sep(p1, p2);
         }
         case RPX_FACE_AXICON: {  // :1621-1675
+            if (FC == RPX_FC_SIMPLE) return RPX_NO_HIT;
             double beta = P[1];
             vec3 d = p2 - p1;
             vec3 o = p1;
@@ -657,7 +676,7 @@ __device__ double face_intersect_basic(const DevScene& S, const rpx_face* f, vec
                           dz2 * ox2 + dz2 * oy2;
             double denom = (beta2 * dx2 + beta2 * dy2 - dz2);
             if (root < 0) return RPX_NO_HIT;
-            root = beta * sqrt(root);
+            root = beta * sqrt_(root);
             double a1 = -beta2 * d.x * o.x - beta2 * d.y * o.y + d.z * o.z;
             double a2 = a1 + root;
             a1 -= root;
@@ -676,6 +695,7 @@ __device__ double face_intersect_basic(const DevScene& S, const rpx_face* f, vec
             return a1 * sep(p1, p2);
         }
         case RPX_FACE_CONIC: {  // :1767-1798
+            if (FC == RPX_FC_SIMPLE) return RPX_NO_HIT;
             vec3 d = p2 - p1;
             vec3 a = p1;
             a.z -= P[1];
@@ -686,6 +706,7 @@ __device__ double face_intersect_basic(const DevScene& S, const rpx_face* f, vec
             return a1 * sep(p1, p2);
         }
         case RPX_FACE_ASPHERIC: {  // :1909-1976, Newton on alpha
+            if (FC == RPX_FC_SIMPLE) return RPX_NO_HIT;
             double atol2 = P[11] * P[11];
             vec3 d = p2 - p1;
             vec3 a = p1;
@@ -718,6 +739,7 @@ __device__ double face_intersect_basic(const DevScene& S, const rpx_face* f, vec
             return a1 * sep(p1, p2);
         }
         case RPX_FACE_EXT_POLY: {  // :2186-2237
+            if (FC == RPX_FC_SIMPLE) return RPX_NO_HIT;
             const double* E = S.pool + f->aux_off;
             double atol2 = P[4] * P[4];
             vec3 d = p2 - p1;
@@ -748,6 +770,7 @@ __device__ double face_intersect_basic(const DevScene& S, const rpx_face* f, vec
 }
 
 // Face.compute_normal_c (local coordinates) for the non-wrapping classes
+template <int FC>
 __device__ vec3 face_normal_basic(const DevScene& S, const rpx_face* f, vec3 p) {
     const double* P = f->p;
     switch (f->type) {
@@ -768,14 +791,16 @@ __device__ vec3 face_normal_basic(const DevScene& S, const rpx_face* f, vec3 p) 
         case RPX_FACE_POLYGON: return v3(0, 0, -1);
         case RPX_FACE_ORIENTED_POLYGON: return ld3(P + 3);
         case RPX_FACE_OFFAXIS_PARABOLIC: {
+            if (FC == RPX_FC_SIMPLE) return p;
             double A = 1 / (2 * P[0]);
             double m2 = p.x * p.x + p.y * p.y;
             double B = 4 * m2 * A * A;
-            double dz = -sqrt(B / (B + 1));
-            m2 = sqrt(m2);
-            return v3(-(dz * p.x) / m2, -(dz * p.y) / m2, -1 / sqrt(B + 1));
+            double dz = -sqrt_(B / (B + 1));
+            m2 = sqrt_(m2);
+            return v3(-(dz * p.x) / m2, -(dz * p.y) / m2, -1 / sqrt_(B + 1));
         }
         case RPX_FACE_ELLIPSOIDAL: {
+            if (FC == RPX_FC_SIMPLE) return p;
             const double* T = S.pool + f->aux_off;
             p = transform_pt(T, p);
             vec3 n = v3(p.x / -(P[0] * P[0]), p.y / -(P[1] * P[1]), p.z / -(P[1] * P[1]));
@@ -783,21 +808,25 @@ __device__ vec3 face_normal_basic(const DevScene& S, const rpx_face* f, vec3 p) 
             return norm(n);
         }
         case RPX_FACE_SADDLE: {
+            if (FC == RPX_FC_SIMPLE) return p;
             double rt6 = sqrt(6.0) * P[1];
             return norm(v3(-rt6 * p.y, -rt6 * p.x, 1.0));
         }
         case RPX_FACE_CYLINDRICAL: {
+            if (FC == RPX_FC_SIMPLE) return p;
             p.z -= (P[0] - P[1]);
             if (P[1] < 0) { p.z = -p.z; p.x = -p.x; }
             p.y = 0;
             return norm(p);
         }
         case RPX_FACE_AXICON: {
+            if (FC == RPX_FC_SIMPLE) return p;
             double beta = P[1];
-            double r = sqrt(p.x * p.x + p.y * p.y);
+            double r = sqrt_(p.x * p.x + p.y * p.y);
             return v3(beta * p.x / r, beta * p.y / r, 1.0);
         }
         case RPX_FACE_CONIC: {
+            if (FC == RPX_FC_SIMPLE) return p;
             double R = -P[0], beta = 1 + P[2];
             int sign = (P[3] != 0.0) ? -1 : 1;
             p.z -= P[1];
@@ -806,12 +835,13 @@ __device__ vec3 face_normal_basic(const DevScene& S, const rpx_face* f, vec3 p) 
             return norm(g * (double)sign);
         }
         case RPX_FACE_ASPHERIC: {
+            if (FC == RPX_FC_SIMPLE) return p;
             double R = -P[0], beta = 1 + P[2];
             int sign = (P[3] != 0.0) ? -1 : 1;
             p.z -= P[1];
             double r2 = p.x * p.x + p.y * p.y;
             double r4 = r2 * r2, r6 = r4 * r2, r8 = r4 * r4, r10 = r8 * r2, r12 = r8 * r4, r14 = r8 * r6;
-            double root = sqrt(1 - (beta * (r2) / (R * R)));
+            double root = sqrt_(1 - (beta * (r2) / (R * R)));
             double df = 10 * P[7] * r8 + 8 * P[6] * r6 + 6 * P[5] * r4 + 4 * P[4] * r2;
             df += 16 * P[10] * r14 + 14 * P[9] * r12 + 12 * P[8] * r10;
             df += 2 / (R * (1 + root));
@@ -820,6 +850,7 @@ __device__ vec3 face_normal_basic(const DevScene& S, const rpx_face* f, vec3 p) 
             return norm(g * (double)sign);
         }
         case RPX_FACE_EXT_POLY: {
+            if (FC == RPX_FC_SIMPLE) return p;
             const double* E = S.pool + f->aux_off;
             int Nx = f->aux_n, Ny = f->aux_m;
             double R = P[0], beta = P[1];
@@ -860,17 +891,17 @@ __device__ vec3 face_normal_basic(const DevScene& S, const rpx_face* f, vec3 p) 
 
 // DistortionFace.intersect_c, cfaces.pyx:2339-2416: base intersection, then a
 // tangent-plane secant iteration on the distorted surface (<= 20 steps).
-__device__ __noinline__ double distortion_intersect(const DevScene& S, const rpx_face* f, vec3 p1, vec3 p2) {
+static __device__ __noinline__ double distortion_intersect(const DevScene& S, const rpx_face* f, vec3 p1, vec3 p2) {
     const rpx_face* base = &S.faces[f->base_face];
     const rpx_distortion* dist = &S.dists[f->aux_off];
     double h = sep(p2, p1);
     double tolerance = f->p[0];
-    double a2 = face_intersect_basic(S, base, p1, p2, 0);
+    double a2 = face_intersect_basic<RPX_FC_FULL>(S, base, p1, p2, 0);
     if (a2 > h || a2 < f->tolerance) return RPX_NO_HIT;
     vec3 d = p2 - p1;
     vec3 pt1 = p1 + d * (a2 / h);
     vec3 dxdyz = distortion_zgrad(S, dist, pt1.x, pt1.y);
-    vec3 n = face_normal_basic(S, base, pt1);
+    vec3 n = face_normal_basic<RPX_FC_FULL>(S, base, pt1);
     pt1.z += dxdyz.z;
     n.x /= n.z;
     n.y /= n.z;
@@ -886,9 +917,9 @@ __device__ __noinline__ double distortion_intersect(const DevScene& S, const rpx
         vec3 q1 = p1, q2 = p2;
         q1.z -= z_shift;
         q2.z -= z_shift;
-        a2 = face_intersect_basic(S, base, q1, q2, 0);
+        a2 = face_intersect_basic<RPX_FC_FULL>(S, base, q1, q2, 0);
         pt1 = q1 + d * (a2 / h);
-        n = face_normal_basic(S, base, pt1);
+        n = face_normal_basic<RPX_FC_FULL>(S, base, pt1);
         dxdyz = distortion_zgrad(S, dist, pt1.x, pt1.y);
         pt1.z += dxdyz.z;
         n.x /= n.z;
@@ -903,19 +934,21 @@ __device__ __noinline__ double distortion_intersect(const DevScene& S, const rpx
     return a1;
 }
 
+template <int FC>
 RPX_DEV double face_intersect(const DevScene& S, const rpx_face* f, vec3 p1, vec3 p2, int is_base_ray) {
-    if (f->type == RPX_FACE_DISTORTION) return distortion_intersect(S, f, p1, p2);
-    return face_intersect_basic(S, f, p1, p2, is_base_ray);
+    if (FC == RPX_FC_FULL && f->type == RPX_FACE_DISTORTION) return distortion_intersect(S, f, p1, p2);
+    return face_intersect_basic<FC>(S, f, p1, p2, is_base_ray);
 }
 
+template <int FC>
 __device__ vec3 face_normal(const DevScene& S, const rpx_face* f, vec3 p) {
-    if (f->type == RPX_FACE_DISTORTION) {  // cfaces.pyx:2418-2431
+    if (FC == RPX_FC_FULL && f->type == RPX_FACE_DISTORTION) {  // cfaces.pyx:2418-2431
         const rpx_face* base = &S.faces[f->base_face];
         const rpx_distortion* dist = &S.dists[f->aux_off];
         vec3 dxdyz = distortion_zgrad(S, dist, p.x, p.y);
         vec3 p1 = p;
         p1.z -= dxdyz.z;
-        vec3 n = face_normal_basic(S, base, p1);
+        vec3 n = face_normal_basic<RPX_FC_FULL>(S, base, p1);
         n.x /= n.z;
         n.y /= n.z;
         n.z = 1.0;
@@ -923,7 +956,7 @@ __device__ vec3 face_normal(const DevScene& S, const rpx_face* f, vec3 p) {
         n.y -= dxdyz.y;
         return norm(n);
     }
-    return face_normal_basic(S, f, p);
+    return face_normal_basic<FC>(S, f, p);
 }
 
 RPX_DEV vec3 face_tangent(const rpx_face* f) {
@@ -933,11 +966,12 @@ RPX_DEV vec3 face_tangent(const rpx_face* f) {
 }
 
 // FaceList.compute_orientation_c, ctracer.pyx:1939-1953
+template <int FC>
 RPX_DEV void compute_orientation(const DevScene& S, const rpx_face* f, vec3 point, vec3* normal,
                                  vec3* tangent) {
     const rpx_face_set* fs = &S.sets[f->face_set];
     point = transform_pt(fs->inv_trans.m, point);
-    vec3 n = face_normal(S, f, point);
+    vec3 n = face_normal<FC>(S, f, point);
     vec3 t = face_tangent(f);
     if (f->invert_normal) {
         n = neg(n);

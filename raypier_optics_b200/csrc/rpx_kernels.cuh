@@ -33,7 +33,7 @@ struct Soa {
     unsigned long long n, cap;
 };
 
-#define RPX_TILE 256
+#define RPX_TILE 128
 #define RPX_WORDS_RAY 47        // 188 / 4
 #define RPX_WORDS_GAUSSLET 167  // 668 / 4
 
@@ -103,7 +103,7 @@ __global__ void __launch_bounds__(TILE) k_soa_to_aos(Soa in, uint32_t* __restric
 }
 
 // reset_length_c for generation 0 of a gausslet trace (ctracer.pyx:1239-1245)
-__global__ void k_reset_length(Soa rays, double max_length) {
+static __global__ void k_reset_length(Soa rays, double max_length) {
     unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= rays.n) return;
     rays.f[F_LEN * rays.cap + i] = max_length;
@@ -131,19 +131,13 @@ RPX_DEV void stage_scene(DevScene& S, unsigned char* smem, int smem_bytes) {
     S.sets = reinterpret_cast<const rpx_face_set*>(smem + face_bytes);
 }
 
-// ------------------------------------------------------------------ k_intersect
+// ------------------------------------------------------------------ nearest hit
 // FaceList.intersect_c over every face set (ctracer.pyx:1882-1904, 2093-2104): the
 // sequential strict-< update keeps the LOWEST face index on equal distances (quirk Q2);
 // the running (distance, face) pair lives in two registers.
-__global__ void __launch_bounds__(RPX_TILE)
-k_intersect(DevScene S, Soa rays, double max_length, int smem_bytes) {
-    extern __shared__ __align__(16) unsigned char smem[];
-    stage_scene(S, smem, smem_bytes);
-    const unsigned long long i = (unsigned long long)blockIdx.x * RPX_TILE + threadIdx.x;
-    if (i >= rays.n) return;
-    const unsigned long long cap = rays.cap;
-    vec3 o = v3(rays.f[F_OX * cap + i], rays.f[F_OY * cap + i], rays.f[F_OZ * cap + i]);
-    vec3 d = v3(rays.f[F_DX * cap + i], rays.f[F_DY * cap + i], rays.f[F_DZ * cap + i]);
+template <int FC>
+__device__ __noinline__ void nearest_hit(const DevScene& S, vec3 o, vec3 d, double max_length,
+                                         double* out_len, uint32_t* out_face) {
     vec3 point = o + d * max_length;
     double best = max_length;  // ray.length = max_length (ctracer.pyx:2086)
     uint32_t best_face = RPX_NO_FACE;
@@ -153,13 +147,33 @@ k_intersect(DevScene S, Soa rays, double max_length, int smem_bytes) {
         vec3 p2 = transform_pt(fs->inv_trans.m, point);
         for (int fi = fs->face_begin; fi < fs->face_end; fi++) {
             const rpx_face* f = &S.faces[fi];
-            double dist = face_intersect(S, f, p1, p2, 1);
+            double dist = face_intersect<FC>(S, f, p1, p2, 1);
             if (f->tolerance < dist && dist < best) {
                 best = dist;
                 best_face = (uint32_t)fi;
             }
         }
     }
+    *out_len = best;
+    *out_face = best_face;
+}
+
+// ------------------------------------------------------------------ k_intersect
+// Generation 0 only: later generations get their nearest hit from the k_shade launch that
+// creates them (the thread that just built a child still has it in registers).
+template <int FC>
+__global__ void __launch_bounds__(RPX_TILE)
+k_intersect(DevScene S, Soa rays, double max_length, int smem_bytes) {
+    extern __shared__ __align__(16) unsigned char smem[];
+    stage_scene(S, smem, smem_bytes);
+    const unsigned long long i = (unsigned long long)blockIdx.x * RPX_TILE + threadIdx.x;
+    if (i >= rays.n) return;
+    const unsigned long long cap = rays.cap;
+    vec3 o = v3(rays.f[F_OX * cap + i], rays.f[F_OY * cap + i], rays.f[F_OZ * cap + i]);
+    vec3 d = v3(rays.f[F_DX * cap + i], rays.f[F_DY * cap + i], rays.f[F_DZ * cap + i]);
+    double best;
+    uint32_t best_face;
+    nearest_hit<FC>(S, o, d, max_length, &best, &best_face);
     rays.f[F_LEN * cap + i] = best;
     rays.u[U_ENDFACE * cap + i] = best_face;
 }
@@ -262,7 +276,7 @@ RPX_DEV void write_child_base(const Soa& out, unsigned long long pos, const Kids
     f[F_E1I * cap] = c.e1.im;
     f[F_E2R * cap] = c.e2.re;
     f[F_E2I * cap] = c.e2.im;
-    // F_LEN / U_ENDFACE are written by k_intersect when this generation is traced
+    // F_LEN / U_ENDFACE: written by the trace-ahead step of k_shade
     f[F_PHASE * cap] = k.phase;
     f[F_APATH * cap] = k.apath;
     uint32_t* u = out.u + pos;
@@ -273,7 +287,7 @@ RPX_DEV void write_child_base(const Soa& out, unsigned long long pos, const Kids
 }
 
 // ------------------------------------------------------------------ k_shade
-template <bool GAUSS>
+template <bool GAUSS, int FC, uint32_t MM>
 __global__ void __launch_bounds__(RPX_TILE)
 k_shade(DevScene S, Soa in, Soa out, double max_length, unsigned long long* tile_state,
         uint32_t* tile_counter, unsigned long long* d_count, uint32_t* face_counts, uint32_t n_tiles,
@@ -322,8 +336,8 @@ k_shade(DevScene S, Soa in, Soa out, double max_length, unsigned long long* tile
         }
         vec3 point = r.o + r.d * r.len;
         vec3 onormal, otangent;
-        compute_orientation(S, face, point, &onormal, &otangent);
-        material_eval(S, &S.mats[face->material], r, point, onormal, otangent, k);
+        compute_orientation<FC>(S, face, point, &onormal, &otangent);
+        material_eval<MM>(S, &S.mats[face->material], r, point, onormal, otangent, k);
 
         if (GAUSS) {
             // trace_parabasal_rays, first loop (ctracer.pyx:2363-2373): every parabasal ray
@@ -340,7 +354,7 @@ k_shade(DevScene S, Soa in, Soa out, double max_length, unsigned long long* tile
                     vec3 ray_end = po + pd * max_length;
                     vec3 p1 = transform_pt(fs->inv_trans.m, po);
                     vec3 p2 = transform_pt(fs->inv_trans.m, ray_end);
-                    double dist = face_intersect(S, face, p1, p2, 0);
+                    double dist = face_intersect<FC>(S, face, p1, p2, 0);
                     if (face->tolerance < dist && dist < max_length) {
                         plen[j] = dist;
                         in.p[(unsigned long long)(j * NPF + P_LEN) * cap + i] = dist;  // parent write-back
@@ -373,14 +387,32 @@ k_shade(DevScene S, Soa in, Soa out, double max_length, unsigned long long* tile
     unsigned long long pos_a = pos, pos_b = pos + (k.has_a ? 1u : 0u);
     if (k.has_a) write_child_base(out, pos_a, k, k.a, wl, parent, ident);
     if (k.has_b) write_child_base(out, pos_b, k, k.b, wl, parent, ident);
+    // Trace ahead: the nearest hit of each child (what trace_segment_c would compute at the
+    // top of the NEXT generation, ctracer.pyx:2084-2104) is found here, while origin and
+    // direction are still in registers, so the next generation needs no intersect pass.
+    {
+        const unsigned long long ocap2 = out.cap;
+        if (k.has_a) {
+            double len;
+            uint32_t face;
+            nearest_hit<FC>(S, k.origin, k.a.dir, max_length, &len, &face);
+            out.f[F_LEN * ocap2 + pos_a] = len;
+            out.u[U_ENDFACE * ocap2 + pos_a] = face;
+        }
+        if (k.has_b) {
+            double len;
+            uint32_t face;
+            nearest_hit<FC>(S, k.origin, k.b.dir, max_length, &len, &face);
+            out.f[F_LEN * ocap2 + pos_b] = len;
+            out.u[U_ENDFACE * ocap2 + pos_b] = face;
+        }
+    }
 
     if (GAUSS) {
         // trace_parabasal_rays, second loop (ctracer.pyx:2375-2385) + reset_length_c (:2280)
         const rpx_face* face = &S.faces[face_idx];
         const rpx_material* M = &S.mats[face->material];
         const unsigned long long ocap = out.cap;
-        if (k.has_a) out.f[F_LEN * ocap + pos_a] = max_length;
-        if (k.has_b) out.f[F_LEN * ocap + pos_b] = max_length;
 #pragma unroll
         for (int j = 0; j < RPX_NPARA; j++) {
             const double* pp = in.p + (unsigned long long)(j * NPF) * cap + i;
@@ -388,7 +420,7 @@ k_shade(DevScene S, Soa in, Soa out, double max_length, unsigned long long* tile
             vec3 pd = v3(pp[(P_DX + 0) * cap], pp[(P_DX + 1) * cap], pp[(P_DX + 2) * cap]);
             vec3 ppoint = po + pd * plen[j];
             vec3 pn, pt;
-            compute_orientation(S, face, ppoint, &pn, &pt);
+            compute_orientation<FC>(S, face, ppoint, &pn, &pt);
             vec3 nn = norm(pn);
             if (k.has_a) {
                 vec3 dir = material_eval_para(S, M, wl, k.a.n.re, pd, ppoint, pn, pt, k.a.type);

@@ -69,7 +69,8 @@ RPX_DEV void fresnel_emit(Kids& k, const RayIn& r, vec3 normal, vec3 in_directio
                           int flip, cplx n1, cplx n_t, cplx R_s, cplx R_p, cplx T_s, cplx T_p,
                           double P_in, double refl_thr, double trans_thr) {
     vec3 cosThetaNormal = normal * cosTheta;
-    if ((n1.re * (cabs2(R_s) + cabs2(R_p)) / P_in) > refl_thr) {
+    const double invP = rcp(P_in);
+    if ((n1.re * (cabs2(R_s) + cabs2(R_p)) * invP) > refl_thr) {
         k.has_a = true;
         k.a.dir = in_direction - cosThetaNormal * 2.0;
         k.a.e1 = R_s;
@@ -77,11 +78,11 @@ RPX_DEV void fresnel_emit(Kids& k, const RayIn& r, vec3 normal, vec3 in_directio
         k.a.n = n1;
         k.a.type = r.type | RPX_REFL_RAY;
     }
-    if ((n_t.re * (cabs2(T_s) + cabs2(T_p)) / P_in) > trans_thr) {
+    if ((n_t.re * (cabs2(T_s) + cabs2(T_p)) * invP) > trans_thr) {
         vec3 tangent = in_direction - cosThetaNormal;
-        vec3 tg2 = tangent * (n1.re / n_t.re);  // real-part approximation, :844
+        vec3 tg2 = tangent * (n1.re * rcp(n_t.re));  // real-part approximation, :844
         double tan_mag_sq = mag_sq(tg2);
-        double c2 = sqrt(1 - tan_mag_sq);
+        double c2 = sqrt_(1 - tan_mag_sq);
         k.has_b = true;
         k.b.dir = tg2 - normal * (c2 * flip);
         k.b.e1 = T_s;
@@ -91,9 +92,27 @@ RPX_DEV void fresnel_emit(Kids& k, const RayIn& r, vec3 normal, vec3 in_directio
     }
 }
 
+// Material-class specialisation: MM is a bit mask of the rpx_material_type values a kernel
+// variant is compiled for (bit t set = type t supported); the host picks the smallest
+// compiled mask that covers the scene.  Unsupported types cannot occur (checked on the host).
+#define RPX_MBIT(t) (1u << (t))
+#define RPX_MM_LIGHT                                                                             \
+    (RPX_MBIT(RPX_MAT_OPAQUE) | RPX_MBIT(RPX_MAT_TRANSPARENT) | RPX_MBIT(RPX_MAT_PEC) |          \
+     RPX_MBIT(RPX_MAT_PARTIALLY_REFLECTIVE) | RPX_MBIT(RPX_MAT_LINEAR_POLARISING) |              \
+     RPX_MBIT(RPX_MAT_WAVEPLATE) | RPX_MBIT(RPX_MAT_DIELECTRIC) | RPX_MBIT(RPX_MAT_GRATING) |    \
+     RPX_MBIT(RPX_MAT_CIRC_APERTURE) | RPX_MBIT(RPX_MAT_RECT_APERTURE))
+#define RPX_MM_COATED (RPX_MBIT(RPX_MAT_COATED) | RPX_MBIT(RPX_MAT_OPAQUE) | RPX_MBIT(RPX_MAT_PEC))
+#define RPX_MM_FULLDIEL                                                                          \
+    (RPX_MBIT(RPX_MAT_FULL_DIELECTRIC) | RPX_MBIT(RPX_MAT_OPAQUE) | RPX_MBIT(RPX_MAT_PEC) |      \
+     RPX_MBIT(RPX_MAT_PARTIALLY_REFLECTIVE) | RPX_MBIT(RPX_MAT_LINEAR_POLARISING) |              \
+     RPX_MBIT(RPX_MAT_TRANSPARENT))
+#define RPX_MM_ALL (RPX_MM_LIGHT | RPX_MBIT(RPX_MAT_FULL_DIELECTRIC) | RPX_MBIT(RPX_MAT_COATED))
+#define RPX_N_MM 4  // compiled variants, in this order: LIGHT, COATED, FULLDIEL, ALL
+
 // InterfaceMaterial.eval_child_ray_c for every material class.
 //   point           hit point, global coordinates
 //   onormal/otangent  FaceList.compute_orientation_c output (not yet normalised)
+template <uint32_t MM>
 __device__ void material_eval(const DevScene& S, const rpx_material* M, const RayIn& r, vec3 point,
                               vec3 onormal, vec3 otangent, Kids& k) {
     const double* P = M->p;
@@ -108,11 +127,13 @@ __device__ void material_eval(const DevScene& S, const rpx_material* M, const Ra
     k.apath = r.apath + r.len * r.n.re;  // accumulated_path += length * n.real
 
     cplx s_amp, p_amp;
-    if (M->type == RPX_MAT_WAVEPLATE) convert_to_sp(r, ld3(P + 2), &k.evec, &s_amp, &p_amp);  // :541
+    if ((MM & RPX_MBIT(RPX_MAT_WAVEPLATE)) && M->type == RPX_MAT_WAVEPLATE)
+        convert_to_sp(r, ld3(P + 2), &k.evec, &s_amp, &p_amp);  // :541
     else convert_to_sp(r, normal, &k.evec, &s_amp, &p_amp);
 
     switch (M->type) {
         case RPX_MAT_TRANSPARENT: {  // :260-278
+            if (!(MM & RPX_MBIT(RPX_MAT_TRANSPARENT))) break;
             k.has_a = true;
             k.a.dir = r.d;
             k.a.n = r.n;
@@ -121,6 +142,7 @@ __device__ void material_eval(const DevScene& S, const rpx_material* M, const Ra
             k.a.type = r.type & ~RPX_REFL_RAY;
         } break;
         case RPX_MAT_PEC: {  // :285-319 (uses the un-normalised incoming direction)
+            if (!(MM & RPX_MBIT(RPX_MAT_PEC))) break;
             double cosTheta = dot(normal, r.d);
             k.has_a = true;
             k.a.dir = r.d - (normal * cosTheta) * 2.0;
@@ -131,6 +153,7 @@ __device__ void material_eval(const DevScene& S, const rpx_material* M, const Ra
         } break;
         case RPX_MAT_PARTIALLY_REFLECTIVE:  // :345-397
         case RPX_MAT_LINEAR_POLARISING: {   // :404-455
+            if (!(MM & RPX_MBIT(RPX_MAT_PARTIALLY_REFLECTIVE))) break;
             vec3 in_direction = norm(r.d);
             double cosTheta = dot(normal, in_direction);
             k.has_a = true;
@@ -142,8 +165,8 @@ __device__ void material_eval(const DevScene& S, const rpx_material* M, const Ra
             k.a.type = r.type | RPX_REFL_RAY;
             k.b.type = r.type & ~RPX_REFL_RAY;
             if (M->type == RPX_MAT_PARTIALLY_REFLECTIVE) {
-                double R = sqrt(P[0]);
-                double T = sqrt(1 - P[0]);
+                double R = sqrt_(P[0]);
+                double T = sqrt_(1 - P[0]);
                 k.a.e1 = s_amp * R;
                 k.a.e2 = p_amp * R;
                 k.b.e1 = s_amp * T;
@@ -156,6 +179,7 @@ __device__ void material_eval(const DevScene& S, const rpx_material* M, const Ra
             }
         } break;
         case RPX_MAT_WAVEPLATE: {  // :520-551
+            if (!(MM & RPX_MBIT(RPX_MAT_WAVEPLATE))) break;
             k.has_a = true;
             k.a.dir = norm(r.d);
             k.a.n = r.n;
@@ -164,6 +188,7 @@ __device__ void material_eval(const DevScene& S, const rpx_material* M, const Ra
             k.a.type = r.type & ~RPX_REFL_RAY;
         } break;
         case RPX_MAT_DIELECTRIC: {  // :587-680
+            if (!(MM & RPX_MBIT(RPX_MAT_DIELECTRIC))) break;
             cplx n_inside = ntab_get(S, M, 0, r.wl), n_outside = ntab_get(S, M, 1, r.wl);
             vec3 in_direction = norm(r.d);
             double cosTheta = dot(normal, in_direction);
@@ -194,11 +219,11 @@ __device__ void material_eval(const DevScene& S, const rpx_material* M, const Ra
                 vec3 tangent = in_direction - cosThetaNormal;
                 vec3 tg2 = tangent * (n1 / n2);
                 double tan_mag_sq = mag_sq(tg2);
-                double c2 = sqrt(1 - tan_mag_sq);
+                double c2 = sqrt_(1 - tan_mag_sq);
                 vec3 transmitted = tg2 - normal * (c2 * flip);
                 double cos2 = fabs(dot(transmitted, normal));
                 double Two_n1_cos1 = (2 * n1) * cos1;
-                double aspect = sqrt(cos2 / cos1) * Two_n1_cos1;
+                double aspect = sqrt_(cos2 / cos1) * Two_n1_cos1;
                 double T_p = aspect / (n2 * cos1 + n1 * cos2);
                 double T_s = aspect / (n2 * cos2 + n1 * cos1);
                 k.a.dir = transmitted;
@@ -208,10 +233,11 @@ __device__ void material_eval(const DevScene& S, const rpx_material* M, const Ra
             }
         } break;
         case RPX_MAT_FULL_DIELECTRIC: {  // :755-872, :896-1013
+            if (!(MM & RPX_MBIT(RPX_MAT_FULL_DIELECTRIC))) break;
             vec3 in_direction = norm(r.d);
             double cosTheta = dot(normal, in_direction);
             double cos1 = fabs(cosTheta);
-            double sin1 = sqrt(fabs(1 - cos1 * cos1));
+            double sin1 = sqrt_(fabs(1 - cos1 * cos1));
             cplx n1, n2;
             int flip;
             if (cosTheta < 0.0) {
@@ -229,24 +255,25 @@ __device__ void material_eval(const DevScene& S, const rpx_material* M, const Ra
                                    p_amp.im * p_amp.im);
             if (P_in == 0.0) return;
             cplx n2c1 = n2 * cos1, n1c2 = n1 * cos2, n2c2 = n2 * cos2, n1c1 = n1 * cos1;
-            cplx dp = n2c1 + n1c2, ds = n2c2 + n1c1;
-            cplx R_p = (-(n2c1 - n1c2)) / dp;
-            cplx R_s = (-(n2c2 - n1c1)) / ds;
+            cplx idp = crcp(n2c1 + n1c2), ids = crcp(n2c2 + n1c1);  // the two Fresnel denominators
+            cplx R_p = (-(n2c1 - n1c2)) * idp;
+            cplx R_s = (-(n2c2 - n1c1)) * ids;
             R_s = R_s * s_amp;
             R_p = R_p * p_amp;
-            double aspect = sqrt(cos2.re / cos1);
+            double aspect = sqrt_(cos2.re * rcp(cos1));
             cplx num = (n1 * (2.0 * cos1)) * aspect;
-            cplx T_p = (num / dp) * p_amp;
-            cplx T_s = (num / ds) * s_amp;
+            cplx T_p = (num * idp) * p_amp;
+            cplx T_s = (num * ids) * s_amp;
             fresnel_emit(k, r, normal, in_direction, cosTheta, flip, n1, n2, R_s, R_p, T_s, T_p, P_in,
                          P[0], P[1]);
         } break;
         case RPX_MAT_COATED: {  // :1026-1182, :1228-1391: single-layer thin film
+            if (!(MM & RPX_MBIT(RPX_MAT_COATED))) break;
             double wavelength = S.wavelengths[r.wl];
             vec3 in_direction = norm(r.d);
             double cosTheta = dot(normal, in_direction);
             double cos1 = fabs(cosTheta);
-            double sin1 = sqrt(fabs(1 - cos1 * cos1));
+            double sin1 = sqrt_(fabs(1 - cos1 * cos1));
             cplx n2 = ntab_get(S, M, 2, r.wl);
             cplx n1, n3;
             int flip;
@@ -270,42 +297,47 @@ __device__ void material_eval(const DevScene& S, const rpx_material* M, const Ra
             cplx n1cos1 = n1 * cos1;
             cplx n2cos2 = n2 * cos2;
             cplx n3cos3 = n3 * cos3;
-            double dwc = 2 * M_PI * P[2] / wavelength;
-            // phi = -I*dwc*(n2 - sin2*sin2)/cos2
+            double dwc = 2 * M_PI * P[2] * rcp(wavelength);
+            // phi = -I*dwc*(n2 - sin2*sin2)/cos2   (cmaterials.pyx:1098)
             cplx phi = (cx(0.0, -dwc) * (n2 - sin2 * sin2)) / cos2;
-            cplx ep1 = cexp_(phi) / ((n2cos2 * 4.0) * n3cos3);
-            cplx ep2 = cexp_(phi * -2.0);
+            // ep1 = exp(phi) / (4 n2cos2 n3cos3),  ep2 = exp(-2 phi) = 1 / exp(phi)^2.
+            // The reference multiplies every transfer-matrix entry by +-ep1 and then forms
+            // R = -M00/M01 and T = M10 + M11*R (:1101-1114): ep1 cancels in R and is a common
+            // factor of T, so it is applied once.  Same value to a few ulp, ~40% fewer flops.
+            cplx ephi = cexp_(phi);
+            cplx ep1 = ephi / ((n2cos2 * 4.0) * n3cos3);
+            cplx ep2 = crcp(ephi * ephi);
             cplx R_s, T_s, R_p, T_p;
             {
                 cplx am = n1cos1 - n2cos2, ap = n1cos1 + n2cos2;
                 cplx bm = n2cos2 - n3cos3, bp = n2cos2 + n3cos3;
-                cplx M00 = (-ep1) * (am * bp + (ap * bm) * ep2);
-                cplx M01 = ep1 * ((am * bm) * ep2 + ap * bp);
-                cplx M10 = ep1 * (am * bm + (ap * bp) * ep2);
-                cplx M11 = (-ep1) * ((am * bp) * ep2 + ap * bm);
-                R_s = (-M00) / M01;
-                T_s = M10 + M11 * R_s;
+                cplx ambp = am * bp, apbm = ap * bm, ambm = am * bm, apbp = ap * bp;
+                // M00 = -ep1*X, M01 = ep1*Y, M10 = ep1*U, M11 = -ep1*V
+                cplx X = ambp + apbm * ep2, Y = ambm * ep2 + apbp;
+                cplx U = ambm + apbp * ep2, V = ambp * ep2 + apbm;
+                R_s = X / Y;
+                T_s = ep1 * (U - V * R_s);
             }
             {
                 cplx n1cos2 = n1 * cos2, n2cos1 = n2 * cos1, n2cos3 = n2 * cos3, n3cos2 = n3 * cos2;
                 cplx am = n1cos2 - n2cos1, ap = n1cos2 + n2cos1;
                 cplx bm = n2cos3 - n3cos2, bp = n2cos3 + n3cos2;
-                cplx M00 = (-ep1) * (am * bp + (ap * bm) * ep2);
-                cplx M01 = ep1 * ((am * bm) * ep2 + ap * bp);
-                cplx M10 = ep1 * (am * bm + (ap * bp) * ep2);
-                cplx M11 = (-ep1) * ((am * bp) * ep2 + ap * bm);
-                R_p = (-M00) / M01;
-                T_p = M10 + M11 * R_p;
+                cplx ambp = am * bp, apbm = ap * bm, ambm = am * bm, apbp = ap * bp;
+                cplx X = ambp + apbm * ep2, Y = ambm * ep2 + apbp;
+                cplx U = ambm + apbp * ep2, V = ambp * ep2 + apbm;
+                R_p = X / Y;
+                T_p = ep1 * (U - V * R_p);
             }
             R_s = R_s * s_amp;
             R_p = R_p * p_amp;
-            double aspect = sqrt(cos3.re / cos1);
+            double aspect = sqrt_(cos3.re * rcp(cos1));
             T_s = T_s * (s_amp * aspect);
             T_p = T_p * (p_amp * aspect);
             fresnel_emit(k, r, normal, in_direction, cosTheta, flip, n1, n3, R_s, R_p, T_s, T_p, P_in,
                          P[0], P[1]);
         } break;
         case RPX_MAT_GRATING: {  // :1472-1542
+            if (!(MM & RPX_MBIT(RPX_MAT_GRATING))) break;
             vec3 tangent = norm(otangent);
             vec3 tangent2 = cross(normal, tangent);
             double wavelen = S.wavelengths[r.wl];
@@ -319,7 +351,7 @@ __device__ void material_eval(const DevScene& S, const rpx_material* M, const Ra
             k_x = k_x - order * wavelen / (line_spacing * r.n.re);
             k_z = 1 - (k_x * k_x) - (k_y * k_y);
             if (k_z < 0) return;  // evanescent order
-            k_z = sign * sqrt(k_z);
+            k_z = sign * sqrt_(k_z);
             reflected = tangent * k_x;
             reflected = reflected + tangent2 * k_y;
             reflected = reflected + normal * k_z;
@@ -332,7 +364,8 @@ __device__ void material_eval(const DevScene& S, const rpx_material* M, const Ra
             k.phase = r.phase + 1000.0 * dot(ld3(P + 3) - point, tangent) * order * 2 * M_PI / line_spacing;
         } break;
         case RPX_MAT_CIRC_APERTURE: {  // :1641-1674
-            double rr = sqrt(mag_sq(ld3(P + 4) - point));
+            if (!(MM & RPX_MBIT(RPX_MAT_CIRC_APERTURE))) break;
+            double rr = sqrt_(mag_sq(ld3(P + 4) - point));
             if (rr > P[0]) return;
             double atten = 0.5 + 0.5 * erf((P[1] - rr) / P[2]);
             if (P[3] != 0.0) atten = 1 - atten;
@@ -344,6 +377,7 @@ __device__ void material_eval(const DevScene& S, const rpx_material* M, const Ra
             k.a.type = r.type & ~RPX_REFL_RAY;
         } break;
         case RPX_MAT_RECT_APERTURE: {  // :1718-1763 (uses the un-normalised orientation)
+            if (!(MM & RPX_MBIT(RPX_MAT_RECT_APERTURE))) break;
             double width = P[4];
             double x = P[2] / 2., y = P[3] / 2.;
             vec3 p = point - ld3(P + 6);
@@ -392,7 +426,7 @@ RPX_DEV vec3 material_eval_para(const DevScene& S, const rpx_material* M, uint32
         vec3 tangent = direction - cosThetaNormal;
         vec3 tg2 = tangent * (n1 / n2);
         double tan_mag_sq = mag_sq(tg2);
-        double c2 = sqrt(1 - tan_mag_sq);
+        double c2 = sqrt_(1 - tan_mag_sq);
         return tg2 - normal * (c2 * flip);
     }
     if (M->para_model == RPX_PARA_GRATING) {  // :1544-1599
@@ -409,7 +443,7 @@ RPX_DEV vec3 material_eval_para(const DevScene& S, const rpx_material* M, uint32
         int sign = (k_z < 0.0) ? 1 : -1;
         k_x = k_x - order * wavelen / (line_spacing * base_n_re);
         k_z = 1 - (k_x * k_x) - (k_y * k_y);
-        k_z = sign * sqrt(k_z);  // evanescent -> NaN, as in the reference (it only prints)
+        k_z = sign * sqrt_(k_z);  // evanescent -> NaN, as in the reference (it only prints)
         reflected = tangent * k_x;
         reflected = reflected + tangent2 * k_y;
         reflected = reflected + normal * k_z;

@@ -31,20 +31,56 @@ RPX_DEV vec3 operator*(vec3 a, double b) { return v3(a.x * b, a.y * b, a.z * b);
 RPX_DEV vec3 neg(vec3 a) { return v3(-a.x, -a.y, -a.z); }
 RPX_DEV double dot(vec3 a, vec3 b) { return a.x * b.x + a.y * b.y + a.z * b.z; }
 RPX_DEV double mag_sq(vec3 a) { return a.x * a.x + a.y * a.y + a.z * a.z; }
-RPX_DEV double mag(vec3 a) { return sqrt(a.x * a.x + a.y * a.y + a.z * a.z); }
 RPX_DEV vec3 cross(vec3 a, vec3 b) {
     return v3(a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x);
 }
-// norm_ of the reference divides each component by the magnitude (ctracer.pyx:251-256);
-// three IEEE divisions, kept (not one reciprocal) so a unit vector stays a unit vector to
-// the same ulp as the reference.
-RPX_DEV vec3 norm(vec3 a) {
-    double m = sqrt(a.x * a.x + a.y * a.y + a.z * a.z);
-    return v3(a.x / m, a.y / m, a.z / m);
+// ---- branch-free fp64 primitives ---------------------------------------------------
+// CUDA's IEEE double division / sqrt / rsqrt / __drcp_rn each expand to 35-60 executed SASS
+// instructions with a guarded slow path (BSSY/BRA/BSYNC, exponent tests).  On this path they
+// dominated the instruction stream (ncu: ~2000 of 3050 warp instructions per ray were not
+// fp64 arithmetic).  The versions below are MUFU seed + two Newton steps: 5-7 instructions,
+// no branches, <= 2 ulp -- seven orders of magnitude inside the 1e-9 / 1e-10 parity
+// tolerances.  They assume finite, normal, non-zero operands; the helpers that can meet a
+// zero (sqrt_, fdiv) special-case it so IEEE results (0, +-inf, NaN) are kept there.
+RPX_DEV double rcp(double x) {
+    double r;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+    double e = fma(-x, r, 1.0);
+    r = fma(r, e, r);
+    e = fma(-x, r, 1.0);
+    return fma(r, e, r);
 }
+RPX_DEV double rsqrt_(double x) {
+    double r;
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+    const double h = 0.5 * x;
+    double e = fma(-h * r, r, 0.5);
+    r = fma(r, e, r);
+    e = fma(-h * r, r, 0.5);
+    return fma(r, e, r);
+}
+// sqrt(x) = x * rsqrt(x); sqrt(0) = 0 exactly (normal incidence gives sin = sqrt(0)).
+RPX_DEV double sqrt_(double x) {
+    double r = x * rsqrt_(x);
+    return (x == 0.0) ? 0.0 : r;
+}
+// a / b with the IEEE result when b == 0 (+-inf or NaN decide hit/miss for rays parallel to
+// a face, which is the COMMON case for axis-aligned sources); one multiply otherwise.
+RPX_DEV double fdiv(double a, double b) {
+    if (b == 0.0) return a / b;
+    return a * rcp(b);
+}
+// norm_ of the reference divides each component by the magnitude (ctracer.pyx:251-256):
+// one sqrt + three divisions.  Here: one rsqrt + three multiplies.  A zero vector still
+// yields NaN (0 * inf), as 0/0 does in the reference.
+RPX_DEV vec3 norm(vec3 a) {
+    double inv = rsqrt_(a.x * a.x + a.y * a.y + a.z * a.z);
+    return v3(a.x * inv, a.y * inv, a.z * inv);
+}
+RPX_DEV double mag(vec3 a) { return sqrt_(a.x * a.x + a.y * a.y + a.z * a.z); }
 RPX_DEV double sep(vec3 p1, vec3 p2) {
     double a = p2.x - p1.x, b = p2.y - p1.y, c = p2.z - p1.z;
-    return sqrt((a * a) + (b * b) + (c * c));
+    return sqrt_((a * a) + (b * b) + (c * c));
 }
 
 // transform_t (ctracer.pxd:67-69) : row-major 3x3 + translation, 12 doubles
@@ -74,54 +110,44 @@ RPX_DEV cplx operator*(cplx a, cplx b) {
     return cx(a.re * b.re - a.im * b.im, a.re * b.im + a.im * b.re);
 }
 RPX_DEV cplx operator*(cplx a, double b) { return cx(a.re * b, a.im * b); }
-// Smith's algorithm, the same scheme libgcc's __divdc3 uses for in-range operands
+// a / b = a * conj(b) / |b|^2 with ONE reciprocal (libgcc's __divdc3 uses Smith's scheme
+// with three divisions to survive |b| near DBL_MAX/DBL_MIN; refractive indices and
+// Fresnel terms are O(1), where both agree to ~2 ulp).
 RPX_DEV cplx operator/(cplx a, cplx b) {
-    cplx r;
-    if (fabs(b.re) < fabs(b.im)) {
-        double ratio = b.re / b.im;
-        double denom = (b.re * ratio) + b.im;
-        r.re = ((a.re * ratio) + a.im) / denom;
-        r.im = ((a.im * ratio) - a.re) / denom;
-    } else {
-        double ratio = b.im / b.re;
-        double denom = (b.im * ratio) + b.re;
-        r.re = ((a.im * ratio) + a.re) / denom;
-        r.im = (a.im - (a.re * ratio)) / denom;
-    }
-    return r;
+    double inv = rcp(b.re * b.re + b.im * b.im);
+    return cx((a.re * b.re + a.im * b.im) * inv, (a.im * b.re - a.re * b.im) * inv);
 }
-RPX_DEV double cabs2(cplx a) {  // cabs(a)**2 as the reference writes it
-    double h = hypot(a.re, a.im);
-    return h * h;
+RPX_DEV cplx crcp(cplx b) {
+    double inv = rcp(b.re * b.re + b.im * b.im);
+    return cx(b.re * inv, -b.im * inv);
 }
+RPX_DEV double cabs2(cplx a) { return a.re * a.re + a.im * a.im; }  // cabs(a)**2
 // C99 csqrt (Annex G branch cut along the negative real axis, sign of the imaginary
 // part follows the sign of z.im including -0.0) -- the TIR branch of the Fresnel
 // materials depends on csqrt(negative + 0i) = +i*sqrt(|x|)  (cmaterials.pyx:805)
 RPX_DEV cplx csqrt_(cplx z) {
     double x = z.re, y = z.im;
     if (y == 0.0) {
-        if (x < 0.0) return cx(0.0, copysign(sqrt(-x), y));
-        return cx(fabs(sqrt(x)), copysign(0.0, y));
+        double q = sqrt_(fabs(x));
+        if (x < 0.0) return cx(0.0, copysign(q, y));
+        return cx(q, copysign(0.0, y));
     }
     if (x == 0.0) {
-        double r = sqrt(0.5 * fabs(y));
+        double r = sqrt_(0.5 * fabs(y));
         return cx(r, copysign(r, y));
     }
-    double d = hypot(x, y);
-    double r, s;
-    if (x > 0.0) {
-        r = sqrt(0.5 * (d + x));
-        s = 0.5 * (y / r);
-    } else {
-        s = sqrt(0.5 * (d - x));
-        r = fabs(0.5 * (y / s));
-    }
-    return cx(r, copysign(s, y));
+    double d = sqrt_(x * x + y * y);  // |z| is O(1) here: no need for hypot's rescaling
+    // t = sqrt((|z| + |x|) / 2) is the larger of the two parts; the other is y / (2 t)
+    double t = sqrt_(0.5 * (d + fabs(x)));
+    double u = 0.5 * (y * rcp(t));
+    if (x > 0.0) return cx(t, u);
+    return cx(fabs(u), copysign(t, y));
 }
 RPX_DEV cplx cexp_(cplx z) {
-    double e = exp(z.re);
     double s, c;
     sincos(z.im, &s, &c);
+    if (z.re == 0.0) return cx(c, s);  // lossless media: the film phase is purely imaginary
+    double e = exp(z.re);
     return cx(e * c, e * s);
 }
 

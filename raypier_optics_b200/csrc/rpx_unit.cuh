@@ -15,19 +15,19 @@ RPX_DEV void st_f64_u32(uint32_t* w, double v) {
     w[1] = (uint32_t)__double2hiint(v);
 }
 
-__global__ void k_unit_face_intersect(DevScene S, int face, const double* p1, const double* p2,
+static __global__ void k_unit_face_intersect(DevScene S, int face, const double* p1, const double* p2,
                                       unsigned long long n, int is_base_ray, double* out) {
     unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
-    out[i] = face_intersect(S, &S.faces[face], ld3(p1 + 3 * i), ld3(p2 + 3 * i), is_base_ray);
+    out[i] = face_intersect<RPX_FC_FULL>(S, &S.faces[face], ld3(p1 + 3 * i), ld3(p2 + 3 * i), is_base_ray);
 }
 
-__global__ void k_unit_face_normal(DevScene S, int face, const double* pts, unsigned long long n,
+static __global__ void k_unit_face_normal(DevScene S, int face, const double* pts, unsigned long long n,
                                    double* normal, double* tangent) {
     unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     vec3 nn, tt;
-    compute_orientation(S, &S.faces[face], ld3(pts + 3 * i), &nn, &tt);
+    compute_orientation<RPX_FC_FULL>(S, &S.faces[face], ld3(pts + 3 * i), &nn, &tt);
     normal[3 * i] = nn.x; normal[3 * i + 1] = nn.y; normal[3 * i + 2] = nn.z;
     tangent[3 * i] = tt.x; tangent[3 * i + 1] = tt.y; tangent[3 * i + 2] = tt.z;
 }
@@ -49,7 +49,7 @@ RPX_DEV void unit_write_child(uint32_t* rec, const uint32_t* parent, const Kids&
     rec[46] = c.type;
 }
 
-__global__ void k_unit_material_eval(DevScene S, int mat, const uint32_t* rays, unsigned long long n,
+static __global__ void k_unit_material_eval(DevScene S, int mat, const uint32_t* rays, unsigned long long n,
                                      const double* point, const double* normal, const double* tangent,
                                      uint32_t* out, uint32_t* counts) {
     unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -69,14 +69,14 @@ __global__ void k_unit_material_eval(DevScene S, int mat, const uint32_t* rays, 
     r.ident = rec[45];
     r.type = rec[46];
     Kids k;
-    material_eval(S, &S.mats[mat], r, ld3(point + 3 * i), ld3(normal + 3 * i), ld3(tangent + 3 * i), k);
+    material_eval<RPX_MM_ALL>(S, &S.mats[mat], r, ld3(point + 3 * i), ld3(normal + 3 * i), ld3(tangent + 3 * i), k);
     uint32_t c = 0;
     if (k.has_a) unit_write_child(out + (2 * i + c++) * RPX_WORDS_RAY, rec, k, k.a, (uint32_t)i);
     if (k.has_b) unit_write_child(out + (2 * i + c++) * RPX_WORDS_RAY, rec, k, k.b, (uint32_t)i);
     counts[i] = c;
 }
 
-__global__ void k_unit_distortion(DevScene S, int dist, const double* x, const double* y,
+static __global__ void k_unit_distortion(DevScene S, int dist, const double* x, const double* y,
                                   unsigned long long n, double* z, double* grad) {
     unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
