@@ -10,7 +10,8 @@ import os
 from . import _abi as A
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "csrc", "librpx.so")
+# RPX_LIB: developer override for A/B-testing a differently built librpx (never a fallback)
+LIB_PATH = os.environ.get("RPX_LIB") or os.path.join(_HERE, "csrc", "librpx.so")
 
 # every symbol include/rpx.h declares (checked by tests/test_abi.py)
 EXPORTS = (

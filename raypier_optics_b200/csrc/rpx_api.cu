@@ -17,7 +17,6 @@
 
 #include "../../include/rpx.h"
 #include "rpx_launch.h"
-#include "rpx_unit.cuh"
 
 using namespace rpx;
 
@@ -345,8 +344,9 @@ extern "C" int rpx_scene_set(rpx_ctx* ctx, const rpx_scene* s) {
 static int rays_alloc(rpx_ctx* ctx, unsigned long long cap_req, int is_gausslet, rpx_rays** out) {
     rpx_rays* r = new (std::nothrow) rpx_rays();
     if (!r) return fail(ctx, RPX_ERR_NOMEM, "out of host memory");
-    unsigned long long cap = (cap_req + 31ull) / 32ull * 32ull;  // every field array 256-B aligned
-    if (cap == 0) cap = 32;
+    // every field array 1-KB aligned and a whole number of tiles (TMA bulk copies fetch full tiles)
+    unsigned long long cap = (cap_req + (RPX_TILE - 1ull)) / RPX_TILE * RPX_TILE;
+    if (cap == 0) cap = RPX_TILE;
     size_t fb = (size_t)NF * cap * sizeof(double);
     size_t ub = (size_t)NU * cap * sizeof(uint32_t);
     size_t pb = is_gausslet ? (size_t)NP * cap * sizeof(double) : 0;
@@ -524,7 +524,8 @@ extern "C" int rpx_trace_device(rpx_ctx* ctx, rpx_rays* rays, double max_length,
         const unsigned long long n = cur->soa.n;
         res->gens.push_back(cur);
         res->counts.push_back(n);
-        const uint32_t n_tiles = (uint32_t)((n + RPX_TILE - 1) / RPX_TILE);
+        const uint32_t n_tiles = (uint32_t)((n + RPX_TILE - 1) / RPX_TILE);   // CTA tiles of k_intersect
+        const uint32_t n_wtiles = n_tiles;
         // ---- nearest hit: generation 0 only (k_shade traces its children ahead)
         if (count == 0) {
             cudaEvent_t a0 = next_event(ctx), a1 = next_event(ctx);
@@ -543,15 +544,15 @@ extern "C" int rpx_trace_device(rpx_ctx* ctx, rpx_rays* rays, double max_length,
             int rc = rays_alloc(ctx, cap_child, is_g, &child);
             if (rc != RPX_OK) return bail(rc);
         }
-        if (n_tiles > ctx->tile_state_cap) {
+        if (n_wtiles > ctx->tile_state_cap) {
             if (ctx->tile_state) CUR(cudaFree(ctx->tile_state));
             ctx->tile_state = nullptr;
             ctx->tile_state_cap = 0;
-            size_t cap_t = (size_t)n_tiles * 2;
+            size_t cap_t = (size_t)n_wtiles * 2;
             CUR(cudaMalloc(&ctx->tile_state, cap_t * sizeof(unsigned long long)));
             ctx->tile_state_cap = cap_t;
         }
-        CUR(cudaMemsetAsync(ctx->tile_state, 0, (size_t)n_tiles * sizeof(unsigned long long), st));
+        CUR(cudaMemsetAsync(ctx->tile_state, 0, (size_t)n_wtiles * sizeof(unsigned long long), st));
         CUR(cudaMemsetAsync(ctx->tile_counter, 0, sizeof(uint32_t), st));
         cudaEvent_t b0 = next_event(ctx), b1 = next_event(ctx);
         CUR(cudaEventRecord(b0, st));
@@ -565,15 +566,9 @@ extern "C" int rpx_trace_device(rpx_ctx* ctx, rpx_rays* rays, double max_length,
             sa.tile_counter = ctx->tile_counter;
             sa.d_count = ctx->d_count;
             sa.face_counts = ctx->d_face_counts;
-            sa.n_tiles = n_tiles;
+            sa.n_tiles = n_wtiles;
             sa.smem_bytes = smem;
-            cudaError_t le;
-            if (is_g)
-                le = ctx->face_class == RPX_FC_SIMPLE ? launch_shade_g1_f0(ctx->mm_idx, st, sa)
-                                                      : launch_shade_g1_f1(ctx->mm_idx, st, sa);
-            else
-                le = ctx->face_class == RPX_FC_SIMPLE ? launch_shade_g0_f0(ctx->mm_idx, st, sa)
-                                                      : launch_shade_g0_f1(ctx->mm_idx, st, sa);
+            cudaError_t le = shade_launcher(is_g, ctx->face_class, ctx->mm_idx)(st, sa);
             CUR(le);
         }
         CUR(cudaEventRecord(b1, st));
@@ -695,9 +690,8 @@ extern "C" int rpx_unit_face_intersect(rpx_ctx* ctx, int face, const double* p1,
     CU(ctx, a.put(p1, n * 24));
     CU(ctx, b.put(p2, n * 24));
     CU(ctx, o.alloc(n * 8));
-    k_unit_face_intersect<<<(unsigned)((n + 127) / 128), 128, 0, st>>>(ctx->ds, face, (const double*)a.p,
-                                                                    (const double*)b.p, n, is_base_ray, (double*)o.p);
-    CU(ctx, cudaGetLastError());
+    CU(ctx, launch_unit_face_intersect(st, ctx->ds, face, (const double*)a.p, (const double*)b.p, n, is_base_ray,
+                                       (double*)o.p));
     CU(ctx, o.get(out_dist, n * 8));
     CU(ctx, cudaStreamSynchronize(st));
     return RPX_OK;
@@ -714,9 +708,7 @@ extern "C" int rpx_unit_face_normal(rpx_ctx* ctx, int face, const double* points
     CU(ctx, a.put(points, n * 24));
     CU(ctx, nn.alloc(n * 24));
     CU(ctx, tt.alloc(n * 24));
-    k_unit_face_normal<<<(unsigned)((n + 127) / 128), 128, 0, st>>>(ctx->ds, face, (const double*)a.p, n, (double*)nn.p,
-                                                                 (double*)tt.p);
-    CU(ctx, cudaGetLastError());
+    CU(ctx, launch_unit_face_normal(st, ctx->ds, face, (const double*)a.p, n, (double*)nn.p, (double*)tt.p));
     CU(ctx, nn.get(out_normal, n * 24));
     CU(ctx, tt.get(out_tangent, n * 24));
     CU(ctx, cudaStreamSynchronize(st));
@@ -740,10 +732,8 @@ extern "C" int rpx_unit_material_eval(rpx_ctx* ctx, int material, const void* ra
     CU(ctx, o.alloc(2 * n * RPX_RAY_BYTES));
     CU(ctx, cudaMemsetAsync(o.p, 0, 2 * n * RPX_RAY_BYTES, st));
     CU(ctx, c.alloc(n * 4));
-    k_unit_material_eval<<<(unsigned)((n + 127) / 128), 128, 0, st>>>(ctx->ds, material, (const uint32_t*)r.p, n,
-                                                                   (const double*)p.p, (const double*)nn.p,
-                                                                   (const double*)tt.p, (uint32_t*)o.p, (uint32_t*)c.p);
-    CU(ctx, cudaGetLastError());
+    CU(ctx, launch_unit_material_eval(st, ctx->ds, material, (const uint32_t*)r.p, n, (const double*)p.p,
+                                      (const double*)nn.p, (const double*)tt.p, (uint32_t*)o.p, (uint32_t*)c.p));
     CU(ctx, o.get(out_aos_2n, 2 * n * RPX_RAY_BYTES));
     CU(ctx, c.get(out_counts, n * 4));
     CU(ctx, cudaStreamSynchronize(st));
@@ -763,9 +753,8 @@ extern "C" int rpx_unit_distortion(rpx_ctx* ctx, int distortion, const double* x
     CU(ctx, b.put(y, n * 8));
     CU(ctx, z.alloc(n * 8));
     CU(ctx, g.alloc(n * 24));
-    k_unit_distortion<<<(unsigned)((n + 127) / 128), 128, 0, st>>>(ctx->ds, distortion, (const double*)a.p,
-                                                                (const double*)b.p, n, (double*)z.p, (double*)g.p);
-    CU(ctx, cudaGetLastError());
+    CU(ctx, launch_unit_distortion(st, ctx->ds, distortion, (const double*)a.p, (const double*)b.p, n, (double*)z.p,
+                                   (double*)g.p));
     CU(ctx, z.get(out_z, n * 8));
     CU(ctx, g.get(out_grad, n * 24));
     CU(ctx, cudaStreamSynchronize(st));

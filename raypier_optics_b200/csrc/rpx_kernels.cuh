@@ -162,7 +162,7 @@ __device__ __noinline__ void nearest_hit(const DevScene& S, vec3 o, vec3 d, doub
 // Generation 0 only: later generations get their nearest hit from the k_shade launch that
 // creates them (the thread that just built a child still has it in registers).
 template <int FC>
-__global__ void __launch_bounds__(RPX_TILE)
+__global__ void __launch_bounds__(RPX_TILE, 4)
 k_intersect(DevScene S, Soa rays, double max_length, int smem_bytes) {
     extern __shared__ __align__(16) unsigned char smem[];
     stage_scene(S, smem, smem_bytes);
@@ -216,17 +216,19 @@ RPX_DEV uint32_t block_exclusive_scan(uint32_t v, uint32_t* total, uint32_t* s_w
     return woff + incl - v;
 }
 
-// Decoupled look-back (one warp): publish this tile's aggregate, then walk back over the
-// predecessors 32 at a time until an inclusive prefix is found.  Tiles take their index
-// from an atomic ticket, so every predecessor is already resident or finished.
-RPX_DEV unsigned long long tile_exclusive_prefix(unsigned long long* state, uint32_t tile,
-                                                 uint32_t total) {
+// Decoupled look-back, split in two so the wait can be hidden behind useful work:
+//   tile_publish   -- as soon as the tile's child count is known, publish it (AGG; tile 0
+//                     publishes its inclusive PREFIX at once);
+//   tile_lookback  -- later (after the trace-ahead intersections), one warp walks back over
+//                     the predecessors 32 at a time until it meets an inclusive prefix.
+// Tiles take their index from an atomic ticket, so every predecessor is resident or done.
+RPX_DEV void tile_publish(unsigned long long* state, uint32_t tile, uint32_t total) {
+    st_relaxed(&state[tile], (tile == 0 ? RPX_FLAG_PREFIX : RPX_FLAG_AGG) | (unsigned long long)total);
+}
+
+RPX_DEV unsigned long long tile_lookback(unsigned long long* state, uint32_t tile, uint32_t total) {
     const int lane = threadIdx.x & 31;
-    if (tile == 0) {
-        if (lane == 0) st_relaxed(&state[0], RPX_FLAG_PREFIX | (unsigned long long)total);
-        return 0;
-    }
-    if (lane == 0) st_relaxed(&state[tile], RPX_FLAG_AGG | (unsigned long long)total);
+    if (tile == 0) return 0;
     unsigned long long excl = 0;
     long long t0 = (long long)tile - 1;  // predecessor inspected by lane 0
     while (true) {
@@ -254,41 +256,66 @@ RPX_DEV unsigned long long tile_exclusive_prefix(unsigned long long* state, uint
     return excl;
 }
 
-RPX_DEV void write_child_base(const Soa& out, unsigned long long pos, const Kids& k, const Kid& c,
-                              uint32_t wl, uint32_t parent, uint32_t ident) {
-    const unsigned long long cap = out.cap;
-    double* f = out.f + pos;
-    f[F_OX * cap] = k.origin.x;
-    f[F_OY * cap] = k.origin.y;
-    f[F_OZ * cap] = k.origin.z;
-    f[F_DX * cap] = c.dir.x;
-    f[F_DY * cap] = c.dir.y;
-    f[F_DZ * cap] = c.dir.z;
-    f[F_NX * cap] = k.normal.x;
-    f[F_NY * cap] = k.normal.y;
-    f[F_NZ * cap] = k.normal.z;
-    f[F_EX * cap] = k.evec.x;
-    f[F_EY * cap] = k.evec.y;
-    f[F_EZ * cap] = k.evec.z;
-    f[F_NR * cap] = c.n.re;
-    f[F_NI * cap] = c.n.im;
-    f[F_E1R * cap] = c.e1.re;
-    f[F_E1I * cap] = c.e1.im;
-    f[F_E2R * cap] = c.e2.re;
-    f[F_E2I * cap] = c.e2.im;
-    // F_LEN / U_ENDFACE: written by the trace-ahead step of k_shade
-    f[F_PHASE * cap] = k.phase;
-    f[F_APATH * cap] = k.apath;
-    uint32_t* u = out.u + pos;
-    u[U_WL * cap] = wl;
-    u[U_PARENT * cap] = parent;
-    u[U_IDENT * cap] = ident;
-    u[U_TYPE * cap] = c.type;
+// ------------------------------------------------------------------ child staging
+// The children of one tile (<= 2 * RPX_TILE) are assembled in shared memory, field-major
+// like the SoA generation buffer: cs[field * RPX_SLOTS + slot], cu[field * RPX_SLOTS + slot].
+// This (a) frees the registers holding the children while their nearest hits are searched,
+// (b) lets ANY thread of the block intersect ANY child (parents with 0 children help those
+// with 2), and (c) makes the final global stores fully coalesced (slot == consecutive
+// addresses) instead of stride-2.
+#define RPX_SLOTS (2 * RPX_TILE)
+#define RPX_STAGE_BYTES (RPX_SLOTS * (NF * 8 + NU * 4))
+
+RPX_DEV void stage_child(double* cs, uint32_t* cu, uint32_t slot, const Kids& k, const Kid& c, uint32_t wl,
+                         uint32_t parent, uint32_t ident) {
+    double* f = cs + slot;
+    f[F_OX * RPX_SLOTS] = k.origin.x;
+    f[F_OY * RPX_SLOTS] = k.origin.y;
+    f[F_OZ * RPX_SLOTS] = k.origin.z;
+    f[F_DX * RPX_SLOTS] = c.dir.x;
+    f[F_DY * RPX_SLOTS] = c.dir.y;
+    f[F_DZ * RPX_SLOTS] = c.dir.z;
+    f[F_NX * RPX_SLOTS] = k.normal.x;
+    f[F_NY * RPX_SLOTS] = k.normal.y;
+    f[F_NZ * RPX_SLOTS] = k.normal.z;
+    f[F_EX * RPX_SLOTS] = k.evec.x;
+    f[F_EY * RPX_SLOTS] = k.evec.y;
+    f[F_EZ * RPX_SLOTS] = k.evec.z;
+    f[F_NR * RPX_SLOTS] = c.n.re;
+    f[F_NI * RPX_SLOTS] = c.n.im;
+    f[F_E1R * RPX_SLOTS] = c.e1.re;
+    f[F_E1I * RPX_SLOTS] = c.e1.im;
+    f[F_E2R * RPX_SLOTS] = c.e2.re;
+    f[F_E2I * RPX_SLOTS] = c.e2.im;
+    f[F_PHASE * RPX_SLOTS] = k.phase;
+    f[F_APATH * RPX_SLOTS] = k.apath;
+    uint32_t* u = cu + slot;
+    u[U_WL * RPX_SLOTS] = wl;
+    u[U_PARENT * RPX_SLOTS] = parent;
+    u[U_IDENT * RPX_SLOTS] = ident;
+    u[U_TYPE * RPX_SLOTS] = c.type;
 }
 
 // ------------------------------------------------------------------ k_shade
+// One launch per generation.  Per tile of RPX_TILE parents (tile index from an atomic ticket):
+//   1. load the parent records (coalesced SoA), orientation + material -> <= 2 children each
+//   2. block scan of the child counts; publish the tile aggregate (no waiting)
+//   3. stage the children in shared memory in emission order
+//   4. trace ahead: nearest hit of every staged child (balanced over the whole block) -- what
+//      trace_segment_c computes at the top of the NEXT generation (ctracer.pyx:2084-2104),
+//      so the next generation needs no intersect pass
+//   5. decoupled look-back for the tile's global offset (the predecessors published while
+//      step 4 ran, so it rarely spins)
+//   6. coalesced copy of the staged children to the next generation's SoA buffer
+//   7. gausslets only: parabasal children (ctracer.pyx:2375-2385), written directly
+// Design notes (measured on B200, profiles/r01_notes.md): persistent CTAs fed by per-field TMA
+// bulk copies and warp-granular tiles were both tried and were slower -- 22 sub-KB bulk copies
+// per tile serialise in the TMA unit, and 4x more tiles mean 4x more look-backs.
+#ifndef RPX_MIN_BLOCKS
+#define RPX_MIN_BLOCKS 4
+#endif
 template <bool GAUSS, int FC, uint32_t MM>
-__global__ void __launch_bounds__(RPX_TILE)
+__global__ void __launch_bounds__(RPX_TILE, RPX_MIN_BLOCKS)
 k_shade(DevScene S, Soa in, Soa out, double max_length, unsigned long long* tile_state,
         uint32_t* tile_counter, unsigned long long* d_count, uint32_t* face_counts, uint32_t n_tiles,
         int smem_bytes) {
@@ -297,7 +324,10 @@ k_shade(DevScene S, Soa in, Soa out, double max_length, unsigned long long* tile
     __shared__ uint32_t s_warp[RPX_TILE / 32];
     __shared__ unsigned long long s_prefix;
     if (threadIdx.x == 0) s_tile = atomicAdd(tile_counter, 1u);
-    stage_scene(S, smem, smem_bytes);  // contains a __syncthreads() when it stages
+    // dynamic shared memory: [child staging][scene copy]
+    double* cs = reinterpret_cast<double*>(smem);
+    uint32_t* cu = reinterpret_cast<uint32_t*>(smem + RPX_SLOTS * NF * 8);
+    stage_scene(S, smem + RPX_STAGE_BYTES, smem_bytes);  // contains a __syncthreads() when it stages
     __syncthreads();
     const uint32_t tile = s_tile;
     const unsigned long long i = (unsigned long long)tile * RPX_TILE + threadIdx.x;
@@ -310,12 +340,10 @@ k_shade(DevScene S, Soa in, Soa out, double max_length, unsigned long long* tile
     uint32_t face_idx = RPX_NO_FACE;
     double plen[RPX_NPARA];
     bool hit = false;
+    RayIn r;
     if (i < in.n) {
+        // every load is issued before the first use: one DRAM round trip per tile, not two
         face_idx = in.u[U_ENDFACE * cap + i];
-        hit = (face_idx != RPX_NO_FACE);
-    }
-    if (hit) {
-        RayIn r;
         r.o = v3(in.f[F_OX * cap + i], in.f[F_OY * cap + i], in.f[F_OZ * cap + i]);
         r.d = v3(in.f[F_DX * cap + i], in.f[F_DY * cap + i], in.f[F_DZ * cap + i]);
         r.e = v3(in.f[F_EX * cap + i], in.f[F_EY * cap + i], in.f[F_EZ * cap + i]);
@@ -328,6 +356,9 @@ k_shade(DevScene S, Soa in, Soa out, double max_length, unsigned long long* tile
         r.wl = wl = in.u[U_WL * cap + i];
         r.ident = ident = in.u[U_IDENT * cap + i];
         r.type = in.u[U_TYPE * cap + i];
+        hit = (face_idx != RPX_NO_FACE);
+    }
+    if (hit) {
         const rpx_face* face = &S.faces[face_idx];
         {  // face.count += 1 (ctracer.pyx:2108), aggregated per warp and face
             const unsigned peers = __match_any_sync(__activemask(), face_idx);
@@ -370,49 +401,64 @@ k_shade(DevScene S, Soa in, Soa out, double max_length, unsigned long long* tile
         }
     }
 
+    // ---- 2. counts -> offsets inside the tile; publish the tile aggregate
     const uint32_t cnt = (k.has_a ? 1u : 0u) + (k.has_b ? 1u : 0u);
     uint32_t total;
     const uint32_t local = block_exclusive_scan(cnt, &total, s_warp);
+    if (threadIdx.x == 0) tile_publish(tile_state, tile, total);
+    // ---- 3. stage children in emission order (reflected, then transmitted)
+    const uint32_t parent = (uint32_t)i;
+    const uint32_t slot_a = local, slot_b = local + (k.has_a ? 1u : 0u);
+    if (k.has_a) stage_child(cs, cu, slot_a, k, k.a, wl, parent, ident);
+    if (k.has_b) stage_child(cs, cu, slot_b, k, k.b, wl, parent, ident);
+    __syncthreads();
+    // ---- 4. trace ahead
+    for (uint32_t slot = threadIdx.x; slot < total; slot += RPX_TILE) {
+        const double* f = cs + slot;
+        vec3 o = v3(f[F_OX * RPX_SLOTS], f[F_OY * RPX_SLOTS], f[F_OZ * RPX_SLOTS]);
+        vec3 d = v3(f[F_DX * RPX_SLOTS], f[F_DY * RPX_SLOTS], f[F_DZ * RPX_SLOTS]);
+        double len;
+        uint32_t face;
+        nearest_hit<FC>(S, o, d, max_length, &len, &face);
+        cs[F_LEN * RPX_SLOTS + slot] = len;
+        cu[U_ENDFACE * RPX_SLOTS + slot] = face;
+    }
+    // ---- 5. global offset of the tile
     if (threadIdx.x < 32) {
-        unsigned long long excl = tile_exclusive_prefix(tile_state, tile, total);
+        unsigned long long excl = tile_lookback(tile_state, tile, total);
         if (threadIdx.x == 0) {
             s_prefix = excl;
             if (tile == n_tiles - 1) *d_count = excl + total;  // len(new_rays)
         }
     }
     __syncthreads();
-    if (cnt == 0) return;
-    unsigned long long pos = s_prefix + local;
-    const uint32_t parent = (uint32_t)i;
-    unsigned long long pos_a = pos, pos_b = pos + (k.has_a ? 1u : 0u);
-    if (k.has_a) write_child_base(out, pos_a, k, k.a, wl, parent, ident);
-    if (k.has_b) write_child_base(out, pos_b, k, k.b, wl, parent, ident);
-    // Trace ahead: the nearest hit of each child (what trace_segment_c would compute at the
-    // top of the NEXT generation, ctracer.pyx:2084-2104) is found here, while origin and
-    // direction are still in registers, so the next generation needs no intersect pass.
+    const unsigned long long base = s_prefix;
+    // ---- 6. coalesced copy-out
     {
-        const unsigned long long ocap2 = out.cap;
-        if (k.has_a) {
-            double len;
-            uint32_t face;
-            nearest_hit<FC>(S, k.origin, k.a.dir, max_length, &len, &face);
-            out.f[F_LEN * ocap2 + pos_a] = len;
-            out.u[U_ENDFACE * ocap2 + pos_a] = face;
+        const unsigned long long ocap = out.cap;
+#pragma unroll
+        for (int fld = 0; fld < NF; fld++) {
+            double* dst = out.f + (unsigned long long)fld * ocap + base;
+            const double* src = cs + fld * RPX_SLOTS;
+            for (uint32_t slot = threadIdx.x; slot < total; slot += RPX_TILE) dst[slot] = src[slot];
         }
-        if (k.has_b) {
-            double len;
-            uint32_t face;
-            nearest_hit<FC>(S, k.origin, k.b.dir, max_length, &len, &face);
-            out.f[F_LEN * ocap2 + pos_b] = len;
-            out.u[U_ENDFACE * ocap2 + pos_b] = face;
+#pragma unroll
+        for (int fld = 0; fld < NU; fld++) {
+            uint32_t* dst = out.u + (unsigned long long)fld * ocap + base;
+            const uint32_t* src = cu + fld * RPX_SLOTS;
+            for (uint32_t slot = threadIdx.x; slot < total; slot += RPX_TILE) dst[slot] = src[slot];
         }
     }
 
-    if (GAUSS) {
-        // trace_parabasal_rays, second loop (ctracer.pyx:2375-2385) + reset_length_c (:2280)
+    if (GAUSS && cnt) {
+        // trace_parabasal_rays, second loop (ctracer.pyx:2375-2385) + reset_length_c (:2280):
+        // parabasal lengths of a new gausslet are max_length; the base ray's length slot already
+        // holds its nearest-hit distance from the trace-ahead step, which is what the next
+        // generation's intersect would have written over max_length anyway.
         const rpx_face* face = &S.faces[face_idx];
         const rpx_material* M = &S.mats[face->material];
         const unsigned long long ocap = out.cap;
+        const unsigned long long pos_a = base + slot_a, pos_b = base + slot_b;
 #pragma unroll
         for (int j = 0; j < RPX_NPARA; j++) {
             const double* pp = in.p + (unsigned long long)(j * NPF) * cap + i;

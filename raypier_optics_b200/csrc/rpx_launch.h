@@ -20,12 +20,43 @@ struct ShadeArgs {
     int smem_bytes;
 };
 
-// mm_idx: 0 LIGHT, 1 COATED, 2 FULLDIEL, 3 ALL (RPX_MM_* in rpx_materials.cuh)
-cudaError_t launch_shade_g0_f0(int mm_idx, cudaStream_t st, const ShadeArgs& a);
-cudaError_t launch_shade_g0_f1(int mm_idx, cudaStream_t st, const ShadeArgs& a);
-cudaError_t launch_shade_g1_f0(int mm_idx, cudaStream_t st, const ShadeArgs& a);
-cudaError_t launch_shade_g1_f1(int mm_idx, cudaStream_t st, const ShadeArgs& a);
+// one launcher per compiled variant: g = gausslets, f = face class, m = material mask index
+cudaError_t launch_shade_g0_f0_m0(cudaStream_t st, const ShadeArgs& a);
+cudaError_t launch_shade_g0_f0_m1(cudaStream_t st, const ShadeArgs& a);
+cudaError_t launch_shade_g0_f0_m2(cudaStream_t st, const ShadeArgs& a);
+cudaError_t launch_shade_g0_f0_m3(cudaStream_t st, const ShadeArgs& a);
+cudaError_t launch_shade_g0_f1_m0(cudaStream_t st, const ShadeArgs& a);
+cudaError_t launch_shade_g0_f1_m1(cudaStream_t st, const ShadeArgs& a);
+cudaError_t launch_shade_g0_f1_m2(cudaStream_t st, const ShadeArgs& a);
+cudaError_t launch_shade_g0_f1_m3(cudaStream_t st, const ShadeArgs& a);
+cudaError_t launch_shade_g1_f0_m0(cudaStream_t st, const ShadeArgs& a);
+cudaError_t launch_shade_g1_f0_m1(cudaStream_t st, const ShadeArgs& a);
+cudaError_t launch_shade_g1_f0_m2(cudaStream_t st, const ShadeArgs& a);
+cudaError_t launch_shade_g1_f0_m3(cudaStream_t st, const ShadeArgs& a);
+cudaError_t launch_shade_g1_f1_m0(cudaStream_t st, const ShadeArgs& a);
+cudaError_t launch_shade_g1_f1_m1(cudaStream_t st, const ShadeArgs& a);
+cudaError_t launch_shade_g1_f1_m2(cudaStream_t st, const ShadeArgs& a);
+cudaError_t launch_shade_g1_f1_m3(cudaStream_t st, const ShadeArgs& a);
+typedef cudaError_t (*ShadeLauncher)(cudaStream_t, const ShadeArgs&);
+inline ShadeLauncher shade_launcher(int gauss, int fc, int mm_idx) {
+    static const ShadeLauncher table[2][2][4] = {
+        {{launch_shade_g0_f0_m0, launch_shade_g0_f0_m1, launch_shade_g0_f0_m2, launch_shade_g0_f0_m3},
+         {launch_shade_g0_f1_m0, launch_shade_g0_f1_m1, launch_shade_g0_f1_m2, launch_shade_g0_f1_m3}},
+        {{launch_shade_g1_f0_m0, launch_shade_g1_f0_m1, launch_shade_g1_f0_m2, launch_shade_g1_f0_m3},
+         {launch_shade_g1_f1_m0, launch_shade_g1_f1_m1, launch_shade_g1_f1_m2, launch_shade_g1_f1_m3}}};
+    return table[gauss ? 1 : 0][fc ? 1 : 0][mm_idx & 3];
+}
 cudaError_t launch_intersect(int fc, cudaStream_t st, unsigned n_tiles, int smem, const DevScene& S, const Soa& rays,
                              double max_length);
+
+cudaError_t launch_unit_face_intersect(cudaStream_t st, const DevScene& S, int face, const double* p1,
+                                       const double* p2, unsigned long long n, int is_base_ray, double* out);
+cudaError_t launch_unit_face_normal(cudaStream_t st, const DevScene& S, int face, const double* pts,
+                                    unsigned long long n, double* normal, double* tangent);
+cudaError_t launch_unit_material_eval(cudaStream_t st, const DevScene& S, int mat, const uint32_t* rays,
+                                      unsigned long long n, const double* point, const double* normal,
+                                      const double* tangent, uint32_t* out, uint32_t* counts);
+cudaError_t launch_unit_distortion(cudaStream_t st, const DevScene& S, int dist, const double* x, const double* y,
+                                   unsigned long long n, double* z, double* grad);
 
 }  // namespace rpx

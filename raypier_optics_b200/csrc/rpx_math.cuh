@@ -67,8 +67,10 @@ RPX_DEV double sqrt_(double x) {
 // a / b with the IEEE result when b == 0 (+-inf or NaN decide hit/miss for rays parallel to
 // a face, which is the COMMON case for axis-aligned sources); one multiply otherwise.
 RPX_DEV double fdiv(double a, double b) {
-    if (b == 0.0) return a / b;
-    return a * rcp(b);
+    // a * (+-inf) reproduces IEEE a / (+-0): +-inf with the right sign, NaN for 0 / 0 -- no branch
+    const double q = a * rcp(b);
+    const double z = a * copysign(__longlong_as_double(0x7ff0000000000000LL), b);
+    return (b == 0.0) ? z : q;
 }
 // norm_ of the reference divides each component by the magnitude (ctracer.pyx:251-256):
 // one sqrt + three divisions.  Here: one rsqrt + three multiplies.  A zero vector still

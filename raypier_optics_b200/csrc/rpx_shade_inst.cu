@@ -1,31 +1,41 @@
-// rpx_shade_inst.cu -- instantiates k_shade<RPX_I_GAUSS, RPX_I_FC, MM> for the four material
-// masks.  Compiled once per (RPX_I_GAUSS, RPX_I_FC) pair (see Makefile).
+// rpx_shade_inst.cu -- instantiates ONE k_shade<RPX_I_GAUSS, RPX_I_FC, MM[RPX_I_MM]> variant.
+// Compiled once per (gausslet, face class, material mask) triple (see Makefile) so all 16
+// variants build in parallel.
 #include "rpx_launch.h"
 
-#ifndef RPX_I_GAUSS
-#error "compile with -DRPX_I_GAUSS=0|1 -DRPX_I_FC=0|1"
+#if !defined(RPX_I_GAUSS) || !defined(RPX_I_FC) || !defined(RPX_I_MM)
+#error "compile with -DRPX_I_GAUSS=0|1 -DRPX_I_FC=0|1 -DRPX_I_MM=0..3"
 #endif
 
-#define RPX_CAT_(a, b, c) launch_shade_g##a##_f##b
-#define RPX_CAT(a, b) RPX_CAT_(a, b, 0)
+#define RPX_CAT_(a, b, c) launch_shade_g##a##_f##b##_m##c
+#define RPX_CAT(a, b, c) RPX_CAT_(a, b, c)
 
 namespace rpx {
 
-template <uint32_t MM>
-static cudaError_t go(cudaStream_t st, const ShadeArgs& a) {
-    k_shade<(RPX_I_GAUSS != 0), RPX_I_FC, MM><<<a.n_tiles, RPX_TILE, a.smem_bytes, st>>>(
-        a.S, a.in, a.out, a.max_length, a.tile_state, a.tile_counter, a.d_count, a.face_counts, a.n_tiles,
-        a.smem_bytes);
-    return cudaGetLastError();
-}
+#if RPX_I_MM == 0
+static constexpr uint32_t kMask = RPX_MM_LIGHT;
+#elif RPX_I_MM == 1
+static constexpr uint32_t kMask = RPX_MM_COATED;
+#elif RPX_I_MM == 2
+static constexpr uint32_t kMask = RPX_MM_FULLDIEL;
+#else
+static constexpr uint32_t kMask = RPX_MM_ALL;
+#endif
 
-cudaError_t RPX_CAT(RPX_I_GAUSS, RPX_I_FC)(int mm_idx, cudaStream_t st, const ShadeArgs& a) {
-    switch (mm_idx) {
-        case 0: return go<RPX_MM_LIGHT>(st, a);
-        case 1: return go<RPX_MM_COATED>(st, a);
-        case 2: return go<RPX_MM_FULLDIEL>(st, a);
-        default: return go<RPX_MM_ALL>(st, a);
+cudaError_t RPX_CAT(RPX_I_GAUSS, RPX_I_FC, RPX_I_MM)(cudaStream_t st, const ShadeArgs& a) {
+    // dynamic shared memory = child staging (47 KB) + the scene copy: needs the > 48 KB opt-in
+    static bool configured = false;
+    const int dyn = RPX_STAGE_BYTES + a.smem_bytes;
+    auto kern = k_shade<(RPX_I_GAUSS != 0), RPX_I_FC, kMask>;
+    if (!configured) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                             RPX_STAGE_BYTES + 40 * 1024);
+        if (e != cudaSuccess) return e;
+        configured = true;
     }
+    kern<<<a.n_tiles, RPX_TILE, dyn, st>>>(a.S, a.in, a.out, a.max_length, a.tile_state, a.tile_counter, a.d_count,
+                                           a.face_counts, a.n_tiles, a.smem_bytes);
+    return cudaGetLastError();
 }
 
 }  // namespace rpx
