@@ -105,7 +105,9 @@ typedef enum rpx_face_type {
                                               A4,A6,A8,A10,A12,A14,A16, atol ; shape                */
     RPX_FACE_EXT_POLY = 18,        /* :2130 p: R(=-curvature), beta(=1+k), norm_radius, z_height,
                                               atol, invert_normals ; aux = coefs[Nx][Ny] (pool)     */
-    RPX_FACE_DISTORTION = 19       /* :2323 p: accuracy ; base_face, aux = distortion idx ; shape   */
+    RPX_FACE_DISTORTION = 19,      /* :2323 p: accuracy ; base_face, aux = distortion idx ; shape   */
+    RPX_FACE_EXTRUDED_BEZIER = 20  /* :795  p: z_height_1, z_height_2, mincorner[2], maxcorner[2];
+                                              aux = cubic Bezier segments [n][4][2] (pool)          */
 } rpx_face_type;
 
 #define RPX_FACE_NPARAM 16

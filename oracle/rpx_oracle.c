@@ -423,6 +423,103 @@ static double extpoly_grad(const rpx_face* f, const double* E, vec3 a, vec3 d, d
 
 static vec3 face_normal(const rpx_scene* S, const rpx_face* f, vec3 p);
 
+/* ---- ExtrudedBezierFace helpers, cfaces.pyx:717-845 ---- */
+typedef struct { double x, y; } flat2;
+typedef struct { double roots[3]; int n; } poly_roots;
+
+/* eval_bezier, cfaces.pyx:717-719 */
+static double eval_bezier(double t, double cp0, double cp1, double cp2, double cp3) {
+    return cp0 * pow(1 - t, 3.0) + 3 * cp1 * t * pow(1 - t, 2.0) + 3 * cp2 * (1 - t) * pow(t, 2.0) +
+           cp3 * pow(t, 3.0);
+}
+/* dif_bezier, cfaces.pyx:721-727 (long double coefficients) */
+static double dif_bezier(double t, double cp0, double cp1, double cp2, double cp3) {
+    long double A, B, C;
+    A = cp3 - 3 * cp2 + 3 * cp1 - cp0;
+    B = 3 * cp2 - 6 * cp1 + 3 * cp0;
+    C = 3 * cp1 - 3 * cp0;
+    return 3 * A * pow(t, 2.0) + 2 * B * t + C;
+}
+/* roots_of_cubic, cfaces.pyx:735-787: x87 long double intermediates; the single-real-root
+ * branch divides by roots[0] == 0.0 and never yields a usable root (quirk Q8). */
+static poly_roots roots_of_cubic(double a, double b, double c, double d) {
+    long double a1 = b / a, a2 = c / a, a3 = d / a;
+    long double Q = (a1 * a1 - 3.0 * a2) / 9.0;
+    long double R = (2.0 * a1 * a1 * a1 - 9.0 * a1 * a2 + 27.0 * a3) / 54.0;
+    long double R2_Q3 = R * R - Q * Q * Q;
+    long double theta;
+    poly_roots x = {{0.0, 0.0, 0.0}, 0};
+    if (fabs(a) <= 0.0000000001) {
+        if (fabs(b) <= 0.0000000001) {
+            if (c == 0) {
+                x.n = 1;
+                x.roots[0] = 0;
+            } else {
+                x.n = 1;
+                x.roots[0] = -d / c;
+            }
+        } else {
+            a1 = pow(c, 2.0) - 4 * b * d;
+            a1 = sqrt((double)a1);
+            x.n = 2;
+            x.roots[0] = (-c + a1) / (2 * b);
+            x.roots[1] = (-c - a1) / (2 * b);
+        }
+    } else {
+        if (R2_Q3 < 0) {
+            x.n = 3;
+            theta = acos((double)(R / sqrt((double)(Q * Q * Q))));
+            x.roots[0] = -2.0 * sqrt((double)Q) * cos((double)(theta / 3.0)) - a1 / 3.0;
+            x.roots[1] = -2.0 * sqrt((double)Q) * cos((double)((theta + 2.0 * M_PI) / 3.0)) - a1 / 3.0;
+            x.roots[2] = -2.0 * sqrt((double)Q) * cos((double)((theta + 4.0 * M_PI) / 3.0)) - a1 / 3.0;
+        } else {
+            x.n = 1;
+            a2 = pow(sqrt((double)R2_Q3) + fabs((double)R), 1 / 3.0);
+            a2 += Q / x.roots[0];
+            a2 *= ((R < 0.0) ? 1 : -1);
+            a2 -= a1 / 3.0;
+            x.roots[0] = a2;
+        }
+    }
+    return x;
+}
+static flat2 rotate2D(double phi, flat2 p) { /* cfaces.pyx:789-793 */
+    flat2 r;
+    r.x = p.x * cos(phi) - p.y * sin(phi);
+    r.y = p.x * sin(phi) + p.y * cos(phi);
+    return r;
+}
+static int bz_ccw(flat2 A, flat2 B, flat2 C) { return (C.y - A.y) * (B.x - A.x) > (B.y - A.y) * (C.x - A.x); }
+static int bz_seg_overlap(flat2 A, flat2 B, flat2 C, flat2 D) {
+    return bz_ccw(A, C, D) != bz_ccw(B, C, D) && bz_ccw(A, B, C) != bz_ccw(A, B, D);
+}
+static int bz_pnt_in_hull(flat2 p, flat2 A, flat2 B, flat2 C, flat2 D) { /* cfaces.pyx:815-845 (float w) */
+    int i, j, k;
+    float w;
+    i = p.x > A.x || p.x > B.x || p.x > C.x || p.x > D.x;
+    j = p.x > A.x && p.x > B.x && p.x > C.x && p.x > D.x;
+    k = i && !j;
+    i = p.y > A.y || p.y > B.y || p.y > C.y || p.y > D.y;
+    j = p.y > A.y && p.y > B.y && p.y > C.y && p.y > D.y;
+    i = i && !j;
+    w = A.x - D.x;
+    w = w * w;
+    if (w <= .0005) {
+        w = B.x - A.x;
+        w = w * w;
+        if (w <= .0005) i = k = 1;
+    } else {
+        w = A.y - D.y;
+        w = w * w;
+        if (w <= .0005) {
+            w = B.y - A.y;
+            w = w * w;
+            if (w <= .0005) i = k = 1;
+        }
+    }
+    return i && k;
+}
+
 /* Face.intersect_c for every concrete class: distance along p1->p2, or <= 0 / -1 */
 static double face_intersect(const rpx_scene* S, const rpx_face* f, vec3 p1, vec3 p2,
                              int is_base_ray) {
@@ -852,6 +949,66 @@ static double face_intersect(const rpx_scene* S, const rpx_face* f, vec3 p1, vec
             if (!shape_inside(S, f, pt1.x, pt1.y)) return NO_HIT; /* even for parabasal rays */
             return a1;
         }
+        case RPX_FACE_EXTRUDED_BEZIER: { /* cfaces.pyx:867-971 (is_base_ray is ignored) */
+            const double* curves = S->pool + f->aux_off;
+            double z1 = P[0], z2 = P[1];
+            flat2 mincorner = {P[2], P[3]}, maxcorner = {P[4], P[5]};
+            flat2 origin = {0, 0}, r, q2, s, tempvector;
+            double result = ORACLE_INF;
+            if ((p1.z < z1 && p2.z < z1) || (p1.z > z2 && p2.z > z2)) return NO_HIT;
+            r.x = p1.x; r.y = p1.y;
+            q2.x = p2.x; q2.y = p2.y;
+            tempvector.x = mincorner.x;
+            tempvector.y = maxcorner.y;
+            if (!bz_seg_overlap(r, q2, mincorner, tempvector)) {
+                if (!bz_seg_overlap(r, q2, tempvector, maxcorner)) {
+                    tempvector.x = maxcorner.x;
+                    tempvector.y = mincorner.y;
+                    if (!bz_seg_overlap(r, q2, maxcorner, tempvector)) {
+                        if (!bz_seg_overlap(r, q2, tempvector, mincorner)) return NO_HIT;
+                    }
+                }
+            }
+            vec3 tempv = subvv(p2, p1);
+            double dZ = tempv.z;
+            s.x = tempv.x;
+            s.y = tempv.y;
+            double theta = atan2(s.y, s.x);
+            s = rotate2D(-theta, s);
+            for (int ci = 0; ci < f->aux_n; ci++) {
+                flat2 cp[4];
+                for (int q = 0; q < 4; q++) {
+                    cp[q].x = curves[(ci * 4 + q) * 2] - p1.x;
+                    cp[q].y = curves[(ci * 4 + q) * 2 + 1] - p1.y;
+                    cp[q] = rotate2D(-theta, cp[q]);
+                }
+                if (bz_seg_overlap(origin, s, cp[0], cp[1]) || bz_seg_overlap(origin, s, cp[1], cp[2]) ||
+                    bz_seg_overlap(origin, s, cp[2], cp[3]) || bz_seg_overlap(origin, s, cp[3], cp[0])) {
+                    double A = cp[3].y - 3 * cp[2].y + 3 * cp[1].y - cp[0].y;
+                    double B = 3 * cp[2].y - 6 * cp[1].y + 3 * cp[0].y;
+                    double C = 3 * cp[1].y - 3 * cp[0].y;
+                    double D = cp[0].y;
+                    poly_roots ts = roots_of_cubic(A, B, C, D);
+                    while (ts.n > 0) {
+                        ts.n -= 1;
+                        double t = ts.roots[ts.n];
+                        if (0. < t && t < 1.) {
+                            double b = eval_bezier(t, cp[0].x, cp[1].x, cp[2].x, cp[3].x);
+                            if (0 < b && b < s.x) {
+                                double c = dZ * b / s.x;
+                                double a = c + p1.z;
+                                if (z1 < a && a < z2) {
+                                    b = sqrt(pow(c, 2.0) + pow(b, 2.0));
+                                    if (b < result && b > tol) result = b;
+                                }
+                            }
+                        }
+                    }
+                }
+            }
+            if (result == ORACLE_INF) return NO_HIT;
+            return result;
+        }
         default: return NO_HIT;
     }
 }
@@ -988,6 +1145,51 @@ static vec3 face_normal(const rpx_scene* S, const rpx_face* f, vec3 p) {
             n.x -= dxdyz.x;
             n.y -= dxdyz.y;
             return norm(n);
+        }
+        case RPX_FACE_EXTRUDED_BEZIER: { /* cfaces.pyx:975-1046 */
+            const double* curves = S->pool + f->aux_off;
+            flat2 ray = {p.x, p.y};
+            double theta = atan2(p.y, p.x);
+            for (int ci = 0; ci < f->aux_n; ci++) {
+                flat2 cp[4];
+                for (int q = 0; q < 4; q++) {
+                    cp[q].x = curves[(ci * 4 + q) * 2];
+                    cp[q].y = curves[(ci * 4 + q) * 2 + 1];
+                }
+                if (bz_pnt_in_hull(ray, cp[0], cp[1], cp[2], cp[3])) {
+                    for (int q = 0; q < 4; q++) cp[q] = rotate2D(-theta, cp[q]);
+                    double A = cp[3].y - 3 * cp[2].y + 3 * cp[1].y - cp[0].y;
+                    double B = 3 * cp[2].y - 6 * cp[1].y + 3 * cp[0].y;
+                    double C = 3 * cp[1].y - 3 * cp[0].y;
+                    double D = cp[0].y;
+                    poly_roots ts = roots_of_cubic(A, B, C, D);
+                    while (ts.n > 0) {
+                        ts.n -= 1;
+                        double t = ts.roots[ts.n];
+                        if (0 <= t && t <= 1) {
+                            double tmp = eval_bezier(t, cp[0].x, cp[1].x, cp[2].x, cp[3].x);
+                            if (pow(tmp, 2.0) - (pow(ray.x, 2.0) + pow(ray.y, 2.0)) < .0001) {
+                                ray.x = dif_bezier(t, cp[0].x, cp[1].x, cp[2].x, cp[3].x);
+                                ray.y = dif_bezier(t, cp[0].y, cp[1].y, cp[2].y, cp[3].y);
+                                ray = rotate2D(theta, ray);
+                                p.z = 0;
+                                if (ray.y == 0) {
+                                    p.x = 0;
+                                    p.y = (ray.x > 0 ? 1 : -1);
+                                } else if (ray.y > 0) {
+                                    p.x = -1;
+                                    p.y = ray.x / ray.y;
+                                } else if (ray.y < 0) {
+                                    p.x = 1;
+                                    p.y = -ray.x / ray.y;
+                                }
+                                return norm(p);
+                            }
+                        }
+                    }
+                }
+            }
+            return v3(0, 0, 0); /* "Bezier normal not found": the reference prints and returns 0 */
         }
         default: return p; /* Face.compute_normal_c base, ctracer.pyx:1783-1784 */
     }

@@ -343,12 +343,69 @@ def config4_grating(core, n=100000, seed=44, n_wavelengths=260):
                 max_length=300.0, recursion_limit=200)
 
 
+def _cpc_profile(n_seg=6, a_in=6.0, a_out=14.0, length=30.0):
+    """A smooth trough wall from (a_in, 0) to (a_out, length) as a chain of cubic Bezier
+    segments (the shape family of examples/CPC3.py / dielectrictroughs.py)."""
+    ts = np.linspace(0.0, 1.0, n_seg + 1)
+
+    def pt(t):
+        return np.array([a_in + (a_out - a_in) * t ** 1.6, length * t])
+
+    def dpt(t):
+        return np.array([(a_out - a_in) * 1.6 * max(t, 1e-9) ** 0.6, length])
+
+    segs = []
+    for t0, t1 in zip(ts[:-1], ts[1:]):
+        h = (t1 - t0) / 3.0
+        segs.append([pt(t0), pt(t0) + h * dpt(t0), pt(t1) - h * dpt(t1), pt(t1)])
+    return np.array(segs)
+
+
+def config4_cpc(core, n=100000, seed=45):
+    """Config 4 (CPC / trough part): two mirrored extruded-Bezier walls (PEC) forming a
+    compound-parabolic-like trough (raypier.splines.Extruded_bezier, examples/CPC3.py), rays
+    entering the wide aperture at a spread of angles, a detector (OpaqueMaterial) at the throat."""
+    F, M = core.cfaces, core.cmaterials
+    right = _cpc_profile()
+    left = right.copy()
+    left[:, :, 0] *= -1.0
+    walls = Pose(centre=(0., 0., 0.), direction=(0., 0., 1.))
+    walls.control_points, walls.z_height_1, walls.z_height_2 = right, -20.0, 20.0
+    walls2 = Pose(centre=(0., 0., 0.), direction=(0., 0., 1.))
+    walls2.control_points, walls2.z_height_1, walls2.z_height_2 = left, -20.0, 20.0
+    pec = M.PECMaterial()
+    f_r = F.ExtrudedBezierFace(owner=walls, beziercurves=right, z_height_1=-20.0, z_height_2=20.0, material=pec)
+    f_l = F.ExtrudedBezierFace(owner=walls2, beziercurves=left, z_height_1=-20.0, z_height_2=20.0, material=pec)
+    fl_r = _facelist(core, walls, [f_r])
+    fl_l = _facelist(core, walls2, [f_l])
+    det = Pose(centre=(0., -0.5, 0.), direction=(0., 1., 0.), length=14.0, width=40.0, offset=0.0)
+    fl_d = _facelist(core, det, [F.RectangularFace(owner=det, length=14.0, width=40.0, offset=0.0,
+                                                   material=M.OpaqueMaterial())])
+    rng = np.random.default_rng(seed)
+    rays = np.zeros(n, dtype=ray_dtype)
+    rays['origin'] = np.stack([rng.uniform(-13.0, 13.0, n), np.full(n, 35.0), rng.uniform(-15.0, 15.0, n)], axis=1)
+    ang = rng.uniform(-0.35, 0.35, n)
+    tilt = rng.normal(0.0, 0.05, n)
+    d = np.stack([np.sin(ang), -np.cos(ang), tilt], axis=1)
+    rays['direction'] = d / np.linalg.norm(d, axis=1)[:, None]
+    rays['E_vector'] = (0.0, 0.0, 1.0)
+    rays['E1_amp'] = 1.0
+    rays['E2_amp'] = 0.4j
+    rays['refractive_index'] = 1.0
+    rays['normal'] = (0.0, 1.0, 0.0)
+    rays['length'] = np.inf
+    rays['ray_ident'] = np.arange(n, dtype=np.uint32)
+    return dict(name="config4_cpc", face_lists=[fl_r, fl_l, fl_d], rays=rays,
+                wavelengths=np.array([0.633]), max_length=120.0, recursion_limit=30)
+
+
 CONFIGS = {
     "config1": config1_singlet,
     "config2": config2_achromat,
     "config3": config3_aspheric_zernike,
     "config4_prisms": config4_prisms,
     "config4_grating": config4_grating,
+    "config4_cpc": config4_cpc,
     "config5": config5_michelson,
 }
 

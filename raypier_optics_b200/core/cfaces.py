@@ -113,6 +113,20 @@ class ExtrudedPlanarFace(Face):
         self.z2 = float(kwds.get('z2', 0))
 
 
+class ExtrudedBezierFace(Face):
+    """cfaces.pyx:795-1046: an extrusion along z of a chain of cubic Bezier segments
+    (``beziercurves`` has shape (n, 4, 2)), as built by raypier.splines.Extruded_bezier
+    (splines.py:145-160) for CPCs and dielectric troughs."""
+
+    def __init__(self, beziercurves=None, z_height_1=0, z_height_2=0, **kwds):
+        Face.__init__(self, **kwds)
+        self.curves_array = np.ascontiguousarray(beziercurves, dtype=np.float64)
+        if self.curves_array.ndim != 3 or self.curves_array.shape[1:] != (4, 2):
+            raise ValueError("beziercurves must have shape (n, 4, 2)")
+        self.z_height_1 = float(z_height_1)
+        self.z_height_2 = float(z_height_2)
+
+
 class PolygonFace(Face):
     """cfaces.pyx:1077-1118"""
 

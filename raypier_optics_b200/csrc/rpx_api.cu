@@ -184,7 +184,7 @@ static int validate_scene(rpx_ctx* ctx, const rpx_scene* s) {
         return fail(ctx, RPX_ERR_INVALID, "bad face counts");
     for (int i = 0; i < s->n_faces; i++) {
         const rpx_face& f = s->faces[i];
-        if (f.type < RPX_FACE_CIRCULAR || f.type > RPX_FACE_DISTORTION)
+        if (f.type < RPX_FACE_CIRCULAR || f.type > RPX_FACE_EXTRUDED_BEZIER)
             return fail(ctx, RPX_ERR_UNSUPPORTED, "face %d: unsupported face type %d", i, f.type);
         if (f.face_set < 0 || f.face_set >= s->n_face_sets)
             return fail(ctx, RPX_ERR_INVALID, "face %d: face_set %d out of range", i, f.face_set);
@@ -206,6 +206,8 @@ static int validate_scene(rpx_ctx* ctx, const rpx_scene* s) {
             return fail(ctx, RPX_ERR_INVALID, "face %d: polygon points out of range", i);
         if (f.type == RPX_FACE_EXT_POLY && (f.aux_off < 0 || f.aux_off + f.aux_n * f.aux_m > s->n_pool))
             return fail(ctx, RPX_ERR_INVALID, "face %d: coefficient table out of range", i);
+        if (f.type == RPX_FACE_EXTRUDED_BEZIER && (f.aux_off < 0 || f.aux_n < 1 || f.aux_off + 8 * f.aux_n > s->n_pool))
+            return fail(ctx, RPX_ERR_INVALID, "face %d: Bezier control points out of range", i);
         if (f.type == RPX_FACE_ELLIPSOIDAL && (f.aux_off < 0 || f.aux_off + 24 > s->n_pool))
             return fail(ctx, RPX_ERR_INVALID, "face %d: transforms out of range", i);
     }

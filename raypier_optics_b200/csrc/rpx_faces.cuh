@@ -253,6 +253,194 @@ RPX_DEV int point_in_polygon(double X, double Y, const double* pts, int size) {
     return ct;
 }
 
+// ---- ExtrudedBezierFace helpers (cfaces.pyx:717-845).  The reference evaluates the cubic's
+// roots with x87 long double intermediates; fp64 agrees to ~1e-15 away from tangency.
+struct flat2 {
+    double x, y;
+};
+RPX_DEV flat2 f2(double x, double y) {
+    flat2 r;
+    r.x = x;
+    r.y = y;
+    return r;
+}
+RPX_DEV double eval_bezier(double t, double cp0, double cp1, double cp2, double cp3) {
+    double u = 1 - t;
+    return cp0 * (u * u * u) + 3 * cp1 * t * (u * u) + 3 * cp2 * u * (t * t) + cp3 * (t * t * t);
+}
+RPX_DEV double dif_bezier(double t, double cp0, double cp1, double cp2, double cp3) {
+    double A = cp3 - 3 * cp2 + 3 * cp1 - cp0;
+    double B = 3 * cp2 - 6 * cp1 + 3 * cp0;
+    double C = 3 * cp1 - 3 * cp0;
+    return 3 * A * (t * t) + 2 * B * t + C;
+}
+// roots_of_cubic, cfaces.pyx:735-787.  Returns the root count; the single-real-root branch of
+// the reference divides by roots[0] == 0.0 (quirk Q8) and so never produces a usable root:
+// it is reported as one non-finite root.
+RPX_DEV int roots_of_cubic(double a, double b, double c, double d, double* roots) {
+    if (fabs(a) <= 0.0000000001) {
+        if (fabs(b) <= 0.0000000001) {
+            roots[0] = (c == 0) ? 0.0 : -d / c;
+            return 1;
+        }
+        double disc = sqrt(c * c - 4 * b * d);
+        roots[0] = (-c + disc) / (2 * b);
+        roots[1] = (-c - disc) / (2 * b);
+        return 2;
+    }
+    double a1 = b / a, a2 = c / a, a3 = d / a;
+    double Q = (a1 * a1 - 3.0 * a2) / 9.0;
+    double R = (2.0 * a1 * a1 * a1 - 9.0 * a1 * a2 + 27.0 * a3) / 54.0;
+    double R2_Q3 = R * R - Q * Q * Q;
+    if (R2_Q3 < 0) {
+        double theta = acos(R / sqrt(Q * Q * Q));
+        double sq = -2.0 * sqrt(Q);
+        roots[0] = sq * cos(theta / 3.0) - a1 / 3.0;
+        roots[1] = sq * cos((theta + 2.0 * M_PI) / 3.0) - a1 / 3.0;
+        roots[2] = sq * cos((theta + 4.0 * M_PI) / 3.0) - a1 / 3.0;
+        return 3;
+    }
+    roots[0] = RPX_INF;
+    return 1;
+}
+RPX_DEV flat2 rotate2D(double sn, double cs, flat2 p) { return f2(p.x * cs - p.y * sn, p.x * sn + p.y * cs); }
+RPX_DEV bool bz_ccw(flat2 A, flat2 B, flat2 C) { return (C.y - A.y) * (B.x - A.x) > (B.y - A.y) * (C.x - A.x); }
+RPX_DEV bool bz_seg_overlap(flat2 A, flat2 B, flat2 C, flat2 D) {
+    return bz_ccw(A, C, D) != bz_ccw(B, C, D) && bz_ccw(A, B, C) != bz_ccw(A, B, D);
+}
+RPX_DEV bool bz_pnt_in_hull(flat2 p, flat2 A, flat2 B, flat2 C, flat2 D) {  // cfaces.pyx:815-845, float w
+    bool i = p.x > A.x || p.x > B.x || p.x > C.x || p.x > D.x;
+    bool j = p.x > A.x && p.x > B.x && p.x > C.x && p.x > D.x;
+    bool k = i && !j;
+    i = p.y > A.y || p.y > B.y || p.y > C.y || p.y > D.y;
+    j = p.y > A.y && p.y > B.y && p.y > C.y && p.y > D.y;
+    i = i && !j;
+    float w = (float)(A.x - D.x);
+    w = w * w;
+    if (w <= .0005f) {
+        w = (float)(B.x - A.x);
+        w = w * w;
+        if (w <= .0005f) i = k = true;
+    } else {
+        w = (float)(A.y - D.y);
+        w = w * w;
+        if (w <= .0005f) {
+            w = (float)(B.y - A.y);
+            w = w * w;
+            if (w <= .0005f) i = k = true;
+        }
+    }
+    return i && k;
+}
+
+// ExtrudedBezierFace.intersect_c, cfaces.pyx:867-971 (is_base_ray is ignored by the reference)
+static __device__ __noinline__ double bezier_intersect(const DevScene& S, const rpx_face* f, vec3 p1, vec3 p2) {
+    const double* P = f->p;
+    const double* curves = S.pool + f->aux_off;
+    const double z1 = P[0], z2 = P[1];
+    const flat2 mincorner = f2(P[2], P[3]), maxcorner = f2(P[4], P[5]);
+    if ((p1.z < z1 && p2.z < z1) || (p1.z > z2 && p2.z > z2)) return RPX_NO_HIT;
+    const flat2 r = f2(p1.x, p1.y), q2 = f2(p2.x, p2.y);
+    flat2 tv = f2(mincorner.x, maxcorner.y);
+    if (!bz_seg_overlap(r, q2, mincorner, tv)) {
+        if (!bz_seg_overlap(r, q2, tv, maxcorner)) {
+            tv = f2(maxcorner.x, mincorner.y);
+            if (!bz_seg_overlap(r, q2, maxcorner, tv)) {
+                if (!bz_seg_overlap(r, q2, tv, mincorner)) return RPX_NO_HIT;
+            }
+        }
+    }
+    const double dZ = p2.z - p1.z;
+    flat2 s = f2(p2.x - p1.x, p2.y - p1.y);
+    const double theta = atan2(s.y, s.x);
+    double sn, cs;
+    sincos(-theta, &sn, &cs);
+    s = rotate2D(sn, cs, s);
+    const flat2 origin = f2(0, 0);
+    double result = RPX_INF;
+    for (int ci = 0; ci < f->aux_n; ci++) {
+        flat2 cp[4];
+#pragma unroll
+        for (int q = 0; q < 4; q++)
+            cp[q] = rotate2D(sn, cs, f2(curves[(ci * 4 + q) * 2] - p1.x, curves[(ci * 4 + q) * 2 + 1] - p1.y));
+        if (bz_seg_overlap(origin, s, cp[0], cp[1]) || bz_seg_overlap(origin, s, cp[1], cp[2]) ||
+            bz_seg_overlap(origin, s, cp[2], cp[3]) || bz_seg_overlap(origin, s, cp[3], cp[0])) {
+            double A = cp[3].y - 3 * cp[2].y + 3 * cp[1].y - cp[0].y;
+            double B = 3 * cp[2].y - 6 * cp[1].y + 3 * cp[0].y;
+            double C = 3 * cp[1].y - 3 * cp[0].y;
+            double D = cp[0].y;
+            double roots[3];
+            int n = roots_of_cubic(A, B, C, D, roots);
+            while (n > 0) {
+                n -= 1;
+                double t = roots[n];
+                if (0. < t && t < 1.) {
+                    double b = eval_bezier(t, cp[0].x, cp[1].x, cp[2].x, cp[3].x);
+                    if (0 < b && b < s.x) {
+                        double c = dZ * b / s.x;
+                        double a = c + p1.z;
+                        if (z1 < a && a < z2) {
+                            b = sqrt(c * c + b * b);
+                            if (b < result && b > f->tolerance) result = b;
+                        }
+                    }
+                }
+            }
+        }
+    }
+    if (result == RPX_INF) return RPX_NO_HIT;
+    return result;
+}
+
+// ExtrudedBezierFace.compute_normal_c, cfaces.pyx:975-1046
+static __device__ __noinline__ vec3 bezier_normal(const DevScene& S, const rpx_face* f, vec3 p) {
+    const double* curves = S.pool + f->aux_off;
+    flat2 ray = f2(p.x, p.y);
+    const double theta = atan2(p.y, p.x);
+    double sn, cs;
+    sincos(-theta, &sn, &cs);
+    for (int ci = 0; ci < f->aux_n; ci++) {
+        flat2 cp[4];
+#pragma unroll
+        for (int q = 0; q < 4; q++) cp[q] = f2(curves[(ci * 4 + q) * 2], curves[(ci * 4 + q) * 2 + 1]);
+        if (bz_pnt_in_hull(ray, cp[0], cp[1], cp[2], cp[3])) {
+#pragma unroll
+            for (int q = 0; q < 4; q++) cp[q] = rotate2D(sn, cs, cp[q]);
+            double A = cp[3].y - 3 * cp[2].y + 3 * cp[1].y - cp[0].y;
+            double B = 3 * cp[2].y - 6 * cp[1].y + 3 * cp[0].y;
+            double C = 3 * cp[1].y - 3 * cp[0].y;
+            double D = cp[0].y;
+            double roots[3];
+            int n = roots_of_cubic(A, B, C, D, roots);
+            while (n > 0) {
+                n -= 1;
+                double t = roots[n];
+                if (0 <= t && t <= 1) {
+                    double tmp = eval_bezier(t, cp[0].x, cp[1].x, cp[2].x, cp[3].x);
+                    if (tmp * tmp - (ray.x * ray.x + ray.y * ray.y) < .0001) {
+                        flat2 dr = f2(dif_bezier(t, cp[0].x, cp[1].x, cp[2].x, cp[3].x),
+                                      dif_bezier(t, cp[0].y, cp[1].y, cp[2].y, cp[3].y));
+                        dr = rotate2D(-sn, cs, dr);  // rotate back by +theta
+                        vec3 o = v3(0, 0, 0);
+                        if (dr.y == 0) {
+                            o.x = 0;
+                            o.y = (dr.x > 0 ? 1 : -1);
+                        } else if (dr.y > 0) {
+                            o.x = -1;
+                            o.y = dr.x / dr.y;
+                        } else {
+                            o.x = 1;
+                            o.y = -dr.x / dr.y;
+                        }
+                        return norm(o);
+                    }
+                }
+            }
+        }
+    }
+    return v3(0, 0, 0);  // "Bezier normal not found": the reference prints and returns 0
+}
+
 // intersect_conic, cfaces.pyx:1695-1747
 RPX_DEV double intersect_conic(vec3 a, vec3 d, double curvature, double conic_const) {
     double beta = 1 + conic_const;
@@ -937,6 +1125,7 @@ static __device__ __noinline__ double distortion_intersect(const DevScene& S, co
 template <int FC>
 RPX_DEV double face_intersect(const DevScene& S, const rpx_face* f, vec3 p1, vec3 p2, int is_base_ray) {
     if (FC == RPX_FC_FULL && f->type == RPX_FACE_DISTORTION) return distortion_intersect(S, f, p1, p2);
+    if (FC == RPX_FC_FULL && f->type == RPX_FACE_EXTRUDED_BEZIER) return bezier_intersect(S, f, p1, p2);
     return face_intersect_basic<FC>(S, f, p1, p2, is_base_ray);
 }
 
@@ -956,6 +1145,7 @@ __device__ vec3 face_normal(const DevScene& S, const rpx_face* f, vec3 p) {
         n.y -= dxdyz.y;
         return norm(n);
     }
+    if (FC == RPX_FC_FULL && f->type == RPX_FACE_EXTRUDED_BEZIER) return bezier_normal(S, f, p);
     return face_normal_basic<FC>(S, f, p);
 }
 

@@ -555,6 +555,22 @@ class Scene:
             f['aux_off'] = self._pool_add(coefs)
             f['aux_n'], f['aux_m'] = coefs.shape
             shaped()
+        elif name == "ExtrudedBezierFace":
+            f['type'] = A.FACE_EXTRUDED_BEZIER
+            if hasattr(face, "curves_array"):
+                curves, z1, z2 = face.curves_array, face.z_height_1, face.z_height_2
+            else:  # reference object: the members are private cdef attributes; the owner
+                # (raypier.splines.Extruded_bezier, splines.py:145-160) passed them in
+                o = face.owner
+                curves, z1, z2 = o.control_points, o.z_height_1, o.z_height_2
+            curves = np.ascontiguousarray(curves, dtype=np.double)
+            if curves.ndim != 3 or curves.shape[1:] != (4, 2) or curves.shape[0] < 1:
+                raise ValueError("ExtrudedBezierFace needs control points of shape (n, 4, 2)")
+            pts = curves.reshape(-1, 2)
+            # bounding box exactly as __cinit__ builds it (cfaces.pyx:852-865)
+            p[0:6] = (z1, z2, pts[:, 0].min(), pts[:, 1].min(), pts[:, 0].max(), pts[:, 1].max())
+            f['aux_off'] = self._pool_add(curves)
+            f['aux_n'] = curves.shape[0]
         elif name == "DistortionFace":
             f['type'] = A.FACE_DISTORTION
             p[0] = face.accuracy

@@ -48,3 +48,16 @@ def test_dispersion_curves_match_reference(refcore, core):
                        (3, coefs3), (0, np.array([1.37]))):
         assert np.array_equal(M.BaseDispersionCurve(fid, coefs).evaluate_n(wl),
                               R.BaseDispersionCurve(fid, coefs).evaluate_n(wl))
+
+
+def test_reference_bezier_face_is_broken_here(refcore):
+    """Documents why ExtrudedBezierFace is 'parity unpinned': with the only Cython available
+    (3.x; the reference pins cython<3) the reference's own roots_of_cubic raises at run time, so
+    no golden output can be produced for it.  The oracle restates the published algorithm
+    (cfaces.pyx:717-1046) and the CUDA path is checked against the oracle only."""
+    from raypier_optics_b200 import configs
+    from oracle import oracle as O
+    cfg = configs.build(refcore, "config4_cpc", n=50)
+    rc = O.reference_collection(refcore, cfg['rays'], cfg['wavelengths'])
+    with pytest.raises(TypeError):
+        O.reference_trace_rays(refcore, rc, cfg['face_lists'], cfg['recursion_limit'], cfg['max_length'])

@@ -5,12 +5,15 @@ import pytest
 
 from raypier_optics_b200 import scene as SC
 
-from util import PARITY_CASES, build_case, compare_traces
+from util import PARITY_CASES, UNPINNED_CASES, build_case, compare_traces
 
 pytestmark = pytest.mark.gpu
 
 
-@pytest.mark.parametrize("name,kw,rl", PARITY_CASES, ids=[c[0] + "-" + str(i) for i, c in enumerate(PARITY_CASES)])
+ALL_CASES = PARITY_CASES + UNPINNED_CASES
+
+
+@pytest.mark.parametrize("name,kw,rl", ALL_CASES, ids=[c[0] + "-" + str(i) for i, c in enumerate(ALL_CASES)])
 def test_cuda_matches_oracle(engine, core, name, kw, rl):
     from oracle import oracle as O
     cfg = build_case(core, name, kw, rl)

@@ -81,6 +81,15 @@ PARITY_CASES = [
 ]
 
 
+# Cases whose oracle could NOT be pinned against the reference: ExtrudedBezierFace raises a
+# TypeError inside the reference itself under the Cython 3 toolchain available here
+# (roots_of_cubic initialises a struct from a tuple, cfaces.pyx:746) -- see
+# tests/test_oracle_vs_reference.py::test_reference_bezier_face_is_broken_here.  "parity unpinned".
+UNPINNED_CASES = [
+    ("config4_cpc", dict(n=5000), None),
+]
+
+
 def build_case(core, name, kw, rl):
     from raypier_optics_b200 import configs
     cfg = configs.build(core, name, **kw)
