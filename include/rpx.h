@@ -339,6 +339,15 @@ int rpx_trace(rpx_ctx* ctx, const void* rays_aos, uint64_t n, int is_gausslet,
               double max_length, int recursion_limit, uint32_t flags,
               rpx_result** out_result);
 
+/* Replaces trace_ray_sequence (core/tracer.py:50-99) over trace_one_face_segment_c /
+ * trace_one_face_gausslet_c (ctracer.pyx:2121-2170, 2284-2347): step s intersects ONLY the
+ * face with global index face_seq[s] (FaceList.intersect_one_face_c, ctracer.pyx:1861-1879).
+ * traced_rays[0] is the input; the generation produced by the last step is returned
+ * untraced (length INF / max_length for gausslets, end_face_idx = the parent's).         */
+int rpx_trace_sequence(rpx_ctx* ctx, const void* rays_aos, uint64_t n, int is_gausslet,
+                       double max_length, int recursion_limit, const int32_t* face_seq,
+                       int n_seq, rpx_result** out_result);
+
 /* len(traced_rays) */
 int rpx_result_n_generations(const rpx_result* res);
 /* [len(traced_rays[g]) for g]; counts has room for n_generations entries */

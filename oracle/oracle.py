@@ -37,6 +37,10 @@ def lib():
         L.rpxo_trace_segment.argtypes = [vp, vp, u64, d, vp, vp]
         L.rpxo_trace_gausslet.restype = u64
         L.rpxo_trace_gausslet.argtypes = [vp, vp, u64, d, vp, vp]
+        L.rpxo_trace_segment_ex.restype = u64
+        L.rpxo_trace_segment_ex.argtypes = [vp, vp, u64, d, vp, vp, i]
+        L.rpxo_trace_gausslet_ex.restype = u64
+        L.rpxo_trace_gausslet_ex.argtypes = [vp, vp, u64, d, vp, vp, i]
         L.rpxo_face_intersect.restype = d
         L.rpxo_face_intersect.argtypes = [vp, i, vp, vp, i]
         L.rpxo_face_normal.argtypes = [vp, i, vp, vp]
@@ -65,7 +69,7 @@ def _v3(v):
     return np.ascontiguousarray(v, dtype=np.double).reshape(3)
 
 
-def trace_generation(scene, rays, max_length, face_counts=None):
+def trace_generation(scene, rays, max_length, face_counts=None, only_face=-1):
     """One generation (trace_segment_c / trace_gausslet_c).  ``rays`` (ray_dtype or
     gausslet_dtype array) is mutated in place like the reference mutates the parent
     collection; returns the child array."""
@@ -76,11 +80,11 @@ def trace_generation(scene, rays, max_length, face_counts=None):
     out = np.zeros(max(2 * n, 1), dtype=rays_c.dtype)
     fc = face_counts.ctypes.data if face_counts is not None else None
     if rays_c.dtype == A.ray_dtype:
-        n_out = L.rpxo_trace_segment(scene.byref_ptr(), rays_c.ctypes.data, n, float(max_length),
-                                     out.ctypes.data, fc)
+        n_out = L.rpxo_trace_segment_ex(scene.byref_ptr(), rays_c.ctypes.data, n, float(max_length),
+                                        out.ctypes.data, fc, int(only_face))
     elif rays_c.dtype == A.gausslet_dtype:
-        n_out = L.rpxo_trace_gausslet(scene.byref_ptr(), rays_c.ctypes.data, n, float(max_length),
-                                      out.ctypes.data, fc)
+        n_out = L.rpxo_trace_gausslet_ex(scene.byref_ptr(), rays_c.ctypes.data, n, float(max_length),
+                                         out.ctypes.data, fc, int(only_face))
     else:
         raise TypeError("rays must be ray_dtype or gausslet_dtype")
     return out[:n_out].copy()
@@ -116,6 +120,58 @@ def trace_rays(scene, input_rays, recursion_limit=100, max_length=100.0):
         rays = trace_generation(osc, rays, max_length, counts)
         count += 1
     return traced, counts[:scene.c_scene.n_traced_faces]
+
+
+def trace_ray_sequence(scene, input_rays, face_seq, recursion_limit=100, max_length=100.0):
+    """raypier.core.tracer.trace_ray_sequence (core/tracer.py:50-99) on numpy arrays;
+    ``face_seq`` holds the global face index of every step."""
+    osc = scene if isinstance(scene, OracleScene) else OracleScene(scene)
+    rays = np.ascontiguousarray(input_rays).copy()
+    if rays.dtype == A.gausslet_dtype:
+        rays['base_ray']['length'] = max_length
+        rays['para_rays']['length'] = max_length
+    else:
+        rays['length'] = max_length
+    counts = np.zeros(max(scene.c_scene.n_traced_faces, 1), dtype=np.uint32)
+    traced = [rays]
+    count = 0
+    for fidx in face_seq:
+        rays = trace_generation(osc, rays, max_length, counts, only_face=int(fidx))
+        if (count > recursion_limit) or rays.shape[0] == 0:
+            break
+        traced.append(rays)
+        count += 1
+    return traced, counts[:scene.c_scene.n_traced_faces]
+
+
+def reference_trace_ray_sequence(core, input_rays, face_sequence, recursion_limit=100, max_length=100.0):
+    """trace_ray_sequence (core/tracer.py:50-99) over the REAL reference kernels."""
+    ct = core.ctracer
+    input_rays.reset_length(max_length)
+    traced_rays = [input_rays]
+    face_lists = [fl for fl, fidx in face_sequence]
+    face_idx_list = [fidx for fl, fidx in face_sequence]
+    trace_func = (ct.trace_one_face_segment if isinstance(input_rays, ct.RayCollection)
+                  else ct.trace_one_face_gausslet)
+    count = 0
+    wavelengths = np.asarray(input_rays.wavelengths)
+    all_faces = [f for fs in face_lists for f in fs.faces]
+    for i, f in enumerate(all_faces):
+        f.idx = i
+        f.count = 0
+        f.update()
+        f.material.wavelengths = wavelengths
+        f.max_length = max_length
+    decomp_faces = [f for f in all_faces if f.material.is_decomp_material()]
+    rays = input_rays
+    for next_face_list, next_face_idx in zip(face_lists, face_idx_list):
+        rays = trace_func(rays, next_face_list, next_face_idx, all_faces, max_length=max_length,
+                          decomp_faces=decomp_faces)
+        if (count > recursion_limit) or (rays.n_rays == 0):
+            break
+        traced_rays.append(rays)
+        count += 1
+    return traced_rays, all_faces
 
 
 # ---- unit entry points (for pinning against the reference's own KATs) -------

@@ -1738,9 +1738,33 @@ static int nearest_hit(const rpx_scene* S, rpx_ray* ray, vec3 point) {
     return nearest_idx;
 }
 
-/* trace_segment_c, ctracer.pyx:2062-2118.  rays_out must hold 2*n records. */
+/* FaceList.intersect_one_face_c, ctracer.pyx:1861-1879 */
+static int one_face_hit(const rpx_scene* S, rpx_ray* ray, vec3 point, int face_idx) {
+    const rpx_face* f = &S->faces[face_idx];
+    const rpx_face_set* fs = &S->face_sets[f->face_set];
+    vec3 p1 = transform_pt(&fs->inv_trans, ld3(ray->origin));
+    vec3 p2 = transform_pt(&fs->inv_trans, point);
+    double dist = face_intersect(S, f, p1, p2, 1);
+    if (f->tolerance < dist && dist < ray->length) {
+        ray->length = dist;
+        ray->end_face_idx = (uint32_t)face_idx;
+        return face_idx;
+    }
+    return -1;
+}
+
+/* trace_segment_c (ctracer.pyx:2062-2118) when only_face < 0, trace_one_face_segment_c
+ * (ctracer.pyx:2121-2170) otherwise.  rays_out must hold 2*n records. */
+uint64_t rpxo_trace_segment_ex(const rpx_scene* S, rpx_ray* rays, uint64_t n, double max_length_d,
+                               rpx_ray* rays_out, uint32_t* face_counts, int only_face);
+
 uint64_t rpxo_trace_segment(const rpx_scene* S, rpx_ray* rays, uint64_t n, double max_length_d,
                             rpx_ray* rays_out, uint32_t* face_counts) {
+    return rpxo_trace_segment_ex(S, rays, n, max_length_d, rays_out, face_counts, -1);
+}
+
+uint64_t rpxo_trace_segment_ex(const rpx_scene* S, rpx_ray* rays, uint64_t n, double max_length_d,
+                               rpx_ray* rays_out, uint32_t* face_counts, int only_face) {
     float max_length = (float)max_length_d; /* `float max_length`, ctracer.pyx:2066 */
     childbuf_t out = {rays_out, 0};
     uint64_t n_out = 0;
@@ -1749,7 +1773,7 @@ uint64_t rpxo_trace_segment(const rpx_scene* S, rpx_ray* rays, uint64_t n, doubl
         ray->length = max_length;
         ray->end_face_idx = (uint32_t)-1;
         vec3 point = addvv(ld3(ray->origin), multvs(ld3(ray->direction), max_length));
-        int nearest_idx = nearest_hit(S, ray, point);
+        int nearest_idx = only_face < 0 ? nearest_hit(S, ray, point) : one_face_hit(S, ray, point, only_face);
         if (nearest_idx >= 0) {
             const rpx_face* face = &S->faces[nearest_idx];
             if (face_counts) face_counts[nearest_idx] += 1;
@@ -1764,9 +1788,18 @@ uint64_t rpxo_trace_segment(const rpx_scene* S, rpx_ray* rays, uint64_t n, doubl
     return n_out;
 }
 
-/* trace_gausslet_c + trace_parabasal_rays, ctracer.pyx:2214-2281, 2350-2385 */
+/* trace_gausslet_c + trace_parabasal_rays (ctracer.pyx:2214-2281, 2350-2385) when only_face < 0,
+ * trace_one_face_gausslet_c (ctracer.pyx:2284-2347) otherwise */
+uint64_t rpxo_trace_gausslet_ex(const rpx_scene* S, rpx_gausslet* gs, uint64_t n, double max_length,
+                                rpx_gausslet* gs_out, uint32_t* face_counts, int only_face);
+
 uint64_t rpxo_trace_gausslet(const rpx_scene* S, rpx_gausslet* gs, uint64_t n, double max_length,
                              rpx_gausslet* gs_out, uint32_t* face_counts) {
+    return rpxo_trace_gausslet_ex(S, gs, n, max_length, gs_out, face_counts, -1);
+}
+
+uint64_t rpxo_trace_gausslet_ex(const rpx_scene* S, rpx_gausslet* gs, uint64_t n, double max_length,
+                                rpx_gausslet* gs_out, uint32_t* face_counts, int only_face) {
     uint64_t n_out = 0;
     rpx_ray child[2];
     for (uint64_t i = 0; i < n; i++) {
@@ -1774,7 +1807,7 @@ uint64_t rpxo_trace_gausslet(const rpx_scene* S, rpx_gausslet* gs, uint64_t n, d
         rpx_ray* ray = &g->base_ray;
         ray->end_face_idx = (uint32_t)-1;
         vec3 point = addvv(ld3(ray->origin), multvs(ld3(ray->direction), max_length));
-        int nearest_idx = nearest_hit(S, ray, point);
+        int nearest_idx = only_face < 0 ? nearest_hit(S, ray, point) : one_face_hit(S, ray, point, only_face);
         if (nearest_idx < 0) continue;
         const rpx_face* face = &S->faces[nearest_idx];
         const rpx_face_set* fs = &S->face_sets[face->face_set];

@@ -17,7 +17,7 @@ LIB_PATH = os.environ.get("RPX_LIB") or os.path.join(_HERE, "csrc", "librpx.so")
 EXPORTS = (
     "rpx_init", "rpx_shutdown", "rpx_last_error", "rpx_abi_version", "rpx_scene_set",
     "rpx_host_alloc", "rpx_host_free", "rpx_rays_upload", "rpx_rays_download", "rpx_rays_count",
-    "rpx_rays_free", "rpx_rays_clone", "rpx_trace_device", "rpx_trace", "rpx_result_n_generations",
+    "rpx_rays_free", "rpx_rays_clone", "rpx_trace_device", "rpx_trace", "rpx_trace_sequence", "rpx_result_n_generations",
     "rpx_result_counts", "rpx_result_generation", "rpx_result_face_counts",
     "rpx_result_device_ms", "rpx_result_launches", "rpx_result_kernel_ms", "rpx_result_free",
     "rpx_stream", "rpx_unit_face_intersect", "rpx_unit_face_normal", "rpx_unit_material_eval",
@@ -74,6 +74,8 @@ def load():
     L.rpx_trace_device.restype = i32
     L.rpx_trace.argtypes = [vp, vp, u64, i32, d, i32, u32, pvp]
     L.rpx_trace.restype = i32
+    L.rpx_trace_sequence.argtypes = [vp, vp, u64, i32, d, i32, vp, i32, pvp]
+    L.rpx_trace_sequence.restype = i32
     L.rpx_result_n_generations.argtypes = [vp]
     L.rpx_result_n_generations.restype = i32
     L.rpx_result_counts.argtypes = [vp, vp]

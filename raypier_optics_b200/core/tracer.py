@@ -98,6 +98,41 @@ def trace_rays(input_rays, face_lists, recursion_limit=100, max_length=100.0, de
     return traced, all_faces
 
 
-def trace_ray_sequence(input_rays, face_sequence, recursion_limit=100, max_length=100.0):
-    """Sequential mode (core/tracer.py:50-99) is a SURVEY section 8f 'next' row."""
-    raise NotImplementedError("sequential tracing (trace_one_face_*) is not part of this build yet")
+def sequence_face_indices(face_sequence):
+    """Global face index of every step of a face sequence, numbered the way
+    trace_ray_sequence numbers them (core/tracer.py:71-80): ``all_faces`` chains the faces of
+    EVERY FaceList entry of the sequence (a FaceList listed twice contributes twice) and
+    ``f.idx`` keeps the position of its LAST occurrence."""
+    face_lists = [fl for fl, _ in face_sequence]
+    all_faces = [f for fs in face_lists for f in fs.faces]
+    last_idx = {}
+    for i, f in enumerate(all_faces):
+        last_idx[id(f)] = i
+    return [last_idx[id(fl.faces[fidx])] for fl, fidx in face_sequence]
+
+
+def trace_ray_sequence(input_rays, face_sequence, recursion_limit=100, max_length=100.0, device=0):
+    """Sequential ray-trace (raypier/core/tracer.py:50-99): ``face_sequence`` is a list of
+    ``(FaceList, face_idx)``; step s intersects the rays of generation s with that one face only.
+
+    returns - (traced_rays, all_faces) like the reference: ``traced_rays[0]`` is the input, the
+    last generation is returned as the materials left it (not intersected with anything).
+    """
+    face_sequence = list(face_sequence)
+    face_lists = [fl for fl, _ in face_sequence]
+    wavelengths, face_lists, all_faces = _prepare_faces(input_rays, face_lists, max_length)
+    seq = sequence_face_indices(face_sequence)
+    eng = get_engine(device)
+    scene = Scene(face_lists, wavelengths)
+    eng.set_scene(scene)
+    rays = input_rays.copy_as_array()
+    native = np.ascontiguousarray(rays).view(
+        A.gausslet_dtype if rays.dtype.itemsize == A.gausslet_dtype.itemsize else A.ray_dtype)
+    res = eng.trace_sequence(native, seq, max_length, recursion_limit)
+    try:
+        arrays = res.generations()
+        for f, c in zip(all_faces, res.face_counts):
+            f.count = int(c)
+    finally:
+        res.free()
+    return _wrap_generations(input_rays, arrays, wavelengths), all_faces

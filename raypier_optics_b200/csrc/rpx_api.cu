@@ -476,10 +476,25 @@ extern "C" void rpx_result_free(rpx_ctx* ctx, rpx_result* res) {
     delete res;
 }
 
-extern "C" int rpx_trace_device(rpx_ctx* ctx, rpx_rays* rays, double max_length, int recursion_limit, uint32_t flags,
-                                rpx_result** out_result) {
-    if (!ctx || !rays || !out_result) return fail(ctx, RPX_ERR_INVALID, "NULL argument");
-    if (!ctx->have_scene) return fail(ctx, RPX_ERR_STATE, "rpx_scene_set must be called before tracing");
+// The generation loop.  face_seq == NULL: non-sequential trace_rays (core/tracer.py:39-45).
+// face_seq != NULL: trace_ray_sequence (core/tracer.py:84-97): step s intersects only face
+// face_seq[s]; the generation produced by the last step is appended untraced.
+static int trace_loop(rpx_ctx* ctx, rpx_rays* rays, double max_length, int recursion_limit, uint32_t flags,
+                      const int32_t* face_seq, int n_seq, rpx_result** out_result) {
+    if (!ctx || !rays || !out_result) {
+        if (ctx && rays) rpx_rays_free(ctx, rays);
+        return fail(ctx, RPX_ERR_INVALID, "NULL argument");
+    }
+    if (!ctx->have_scene) {
+        rpx_rays_free(ctx, rays);
+        return fail(ctx, RPX_ERR_STATE, "rpx_scene_set must be called before tracing");
+    }
+    for (int s = 0; face_seq && s < n_seq; s++)
+        if (face_seq[s] < 0 || face_seq[s] >= ctx->n_traced) {
+            rpx_rays_free(ctx, rays);
+            return fail(ctx, RPX_ERR_INVALID, "face sequence entry %d (= %d) out of range", s, face_seq[s]);
+        }
+    const bool sequential = face_seq != nullptr;
     CU(ctx, cudaSetDevice(ctx->device));
     cudaStream_t st = ctx->stream;
     const int is_g = rays->is_gausslet;
@@ -522,17 +537,20 @@ extern "C" int rpx_trace_device(rpx_ctx* ctx, rpx_rays* rays, double max_length,
     }
     int count = 0;
     const int smem = ctx->scene_smem;
-    while (cur->soa.n > 0 && count < recursion_limit) {
+    // sequential mode: traced_rays starts as [input_rays] and one step runs per sequence entry
+    while (sequential ? (count < n_seq && cur->soa.n > 0) : (cur->soa.n > 0 && count < recursion_limit)) {
         const unsigned long long n = cur->soa.n;
-        res->gens.push_back(cur);
-        res->counts.push_back(n);
+        if (!sequential || count == 0) {
+            res->gens.push_back(cur);
+            res->counts.push_back(n);
+        }
         const uint32_t n_tiles = (uint32_t)((n + RPX_TILE - 1) / RPX_TILE);   // CTA tiles of k_intersect
         const uint32_t n_wtiles = n_tiles;
         // ---- nearest hit: generation 0 only (k_shade traces its children ahead)
         if (count == 0) {
             cudaEvent_t a0 = next_event(ctx), a1 = next_event(ctx);
             CUR(cudaEventRecord(a0, st));
-            CUR(launch_intersect(ctx->face_class, st, n_tiles, smem, ctx->ds, cur->soa, ml));
+            CUR(launch_intersect(ctx->face_class, st, n_tiles, smem, ctx->ds, cur->soa, ml, sequential ? face_seq[0] : -1));
             CUR(cudaEventRecord(a1, st));
             ev_i0.push_back(a0);
             ev_i1.push_back(a1);
@@ -570,6 +588,7 @@ extern "C" int rpx_trace_device(rpx_ctx* ctx, rpx_rays* rays, double max_length,
             sa.face_counts = ctx->d_face_counts;
             sa.n_tiles = n_wtiles;
             sa.smem_bytes = smem;
+            sa.ahead_face = !sequential ? -1 : (count + 1 < n_seq ? face_seq[count + 1] : -2);
             cudaError_t le = shade_launcher(is_g, ctx->face_class, ctx->mm_idx)(st, sa);
             CUR(le);
         }
@@ -581,7 +600,18 @@ extern "C" int rpx_trace_device(rpx_ctx* ctx, rpx_rays* rays, double max_length,
         CUR(cudaMemcpyAsync(ctx->h_count, ctx->d_count, sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
         CUR(cudaStreamSynchronize(st));
         child->soa.n = *ctx->h_count;
-        if (flags & RPX_TRACE_KEEP_LAST_ONLY) {
+        if (sequential) {
+            // core/tracer.py:91-97: `if (count > recursion_limit) or (rays.n_rays==0): break`
+            // comes BEFORE the append
+            if (count > recursion_limit || child->soa.n == 0) {
+                rpx_rays_free(ctx, child);
+                child = nullptr;
+                break;
+            }
+            res->gens.push_back(child);
+            res->counts.push_back(child->soa.n);
+        }
+        if ((flags & RPX_TRACE_KEEP_LAST_ONLY) && !sequential) {
             // streaming mode: the parent generation is complete (write-back done); drop it
             rpx_rays_free(ctx, res->gens.back());
             res->gens.back() = nullptr;
@@ -592,7 +622,11 @@ extern "C" int rpx_trace_device(rpx_ctx* ctx, rpx_rays* rays, double max_length,
     }
     CUR(cudaEventRecord(ev_end, st));
     // the generation that was built but never traced is not part of traced_rays
-    if (res->gens.empty() || res->gens.back() != cur) rpx_rays_free(ctx, cur);
+    if (res->gens.empty() || res->gens.back() != cur) {
+        bool owned = false;
+        for (rpx_rays* g : res->gens) owned = owned || (g == cur);
+        if (!owned) rpx_rays_free(ctx, cur);
+    }
     cur = nullptr;
     CUR(cudaMemcpyAsync(res->face_counts.data(), ctx->d_face_counts, sizeof(uint32_t) * (size_t)ctx->n_traced,
                         cudaMemcpyDeviceToHost, st));
@@ -613,6 +647,21 @@ extern "C" int rpx_trace_device(rpx_ctx* ctx, rpx_rays* rays, double max_length,
 #undef CUR
     *out_result = res;
     return RPX_OK;
+}
+
+extern "C" int rpx_trace_device(rpx_ctx* ctx, rpx_rays* rays, double max_length, int recursion_limit, uint32_t flags,
+                                rpx_result** out_result) {
+    return trace_loop(ctx, rays, max_length, recursion_limit, flags, nullptr, 0, out_result);
+}
+
+extern "C" int rpx_trace_sequence(rpx_ctx* ctx, const void* rays_aos, uint64_t n, int is_gausslet, double max_length,
+                                  int recursion_limit, const int32_t* face_seq, int n_seq, rpx_result** out_result) {
+    if (!ctx || !out_result || !face_seq || n_seq < 1) return fail(ctx, RPX_ERR_INVALID, "bad face sequence");
+    if (!ctx->have_scene) return fail(ctx, RPX_ERR_STATE, "rpx_scene_set must be called before tracing");
+    rpx_rays* r = nullptr;
+    int rc = rpx_rays_upload(ctx, rays_aos, n, is_gausslet, &r);
+    if (rc != RPX_OK) return rc;
+    return trace_loop(ctx, r, max_length, recursion_limit, 0, face_seq, n_seq, out_result);
 }
 
 extern "C" int rpx_trace(rpx_ctx* ctx, const void* rays_aos, uint64_t n, int is_gausslet, double max_length,

@@ -135,12 +135,28 @@ RPX_DEV void stage_scene(DevScene& S, unsigned char* smem, int smem_bytes) {
 // FaceList.intersect_c over every face set (ctracer.pyx:1882-1904, 2093-2104): the
 // sequential strict-< update keeps the LOWEST face index on equal distances (quirk Q2);
 // the running (distance, face) pair lives in two registers.
+// only_face >= 0 restricts the search to that one face: FaceList.intersect_one_face_c
+// (ctracer.pyx:1861-1879), the sequential-mode step of trace_one_face_segment_c (:2121-2170).
 template <int FC>
-__device__ __noinline__ void nearest_hit(const DevScene& S, vec3 o, vec3 d, double max_length,
+__device__ __noinline__ void nearest_hit(const DevScene& S, vec3 o, vec3 d, double max_length, int only_face,
                                          double* out_len, uint32_t* out_face) {
     vec3 point = o + d * max_length;
     double best = max_length;  // ray.length = max_length (ctracer.pyx:2086)
     uint32_t best_face = RPX_NO_FACE;
+    if (only_face >= 0) {
+        const rpx_face* f = &S.faces[only_face];
+        const rpx_face_set* fs = &S.sets[f->face_set];
+        vec3 p1 = transform_pt(fs->inv_trans.m, o);
+        vec3 p2 = transform_pt(fs->inv_trans.m, point);
+        double dist = face_intersect<FC>(S, f, p1, p2, 1);
+        if (f->tolerance < dist && dist < best) {
+            best = dist;
+            best_face = (uint32_t)only_face;
+        }
+        *out_len = best;
+        *out_face = best_face;
+        return;
+    }
     for (int s = 0; s < S.n_sets; s++) {
         const rpx_face_set* fs = &S.sets[s];
         vec3 p1 = transform_pt(fs->inv_trans.m, o);
@@ -163,7 +179,7 @@ __device__ __noinline__ void nearest_hit(const DevScene& S, vec3 o, vec3 d, doub
 // creates them (the thread that just built a child still has it in registers).
 template <int FC>
 __global__ void __launch_bounds__(RPX_TILE, 4)
-k_intersect(DevScene S, Soa rays, double max_length, int smem_bytes) {
+k_intersect(DevScene S, Soa rays, double max_length, int smem_bytes, int only_face) {
     extern __shared__ __align__(16) unsigned char smem[];
     stage_scene(S, smem, smem_bytes);
     const unsigned long long i = (unsigned long long)blockIdx.x * RPX_TILE + threadIdx.x;
@@ -173,7 +189,7 @@ k_intersect(DevScene S, Soa rays, double max_length, int smem_bytes) {
     vec3 d = v3(rays.f[F_DX * cap + i], rays.f[F_DY * cap + i], rays.f[F_DZ * cap + i]);
     double best;
     uint32_t best_face;
-    nearest_hit<FC>(S, o, d, max_length, &best, &best_face);
+    nearest_hit<FC>(S, o, d, max_length, only_face, &best, &best_face);
     rays.f[F_LEN * cap + i] = best;
     rays.u[U_ENDFACE * cap + i] = best_face;
 }
@@ -318,7 +334,11 @@ template <bool GAUSS, int FC, uint32_t MM>
 __global__ void __launch_bounds__(RPX_TILE, RPX_MIN_BLOCKS)
 k_shade(DevScene S, Soa in, Soa out, double max_length, unsigned long long* tile_state,
         uint32_t* tile_counter, unsigned long long* d_count, uint32_t* face_counts, uint32_t n_tiles,
-        int smem_bytes) {
+        int smem_bytes, int ahead_face) {
+    // ahead_face: -1 trace the children ahead against every face (non-sequential mode);
+    //             >= 0 only against that face (next step of a face sequence);
+    //             -2 leave them untraced (last step of a sequence: the reference appends that
+    //                generation as the material left it -- length INF, the parent's end_face_idx)
     extern __shared__ __align__(16) unsigned char smem[];
     __shared__ uint32_t s_tile;
     __shared__ uint32_t s_warp[RPX_TILE / 32];
@@ -413,15 +433,29 @@ k_shade(DevScene S, Soa in, Soa out, double max_length, unsigned long long* tile
     if (k.has_b) stage_child(cs, cu, slot_b, k, k.b, wl, parent, ident);
     __syncthreads();
     // ---- 4. trace ahead
-    for (uint32_t slot = threadIdx.x; slot < total; slot += RPX_TILE) {
-        const double* f = cs + slot;
-        vec3 o = v3(f[F_OX * RPX_SLOTS], f[F_OY * RPX_SLOTS], f[F_OZ * RPX_SLOTS]);
-        vec3 d = v3(f[F_DX * RPX_SLOTS], f[F_DY * RPX_SLOTS], f[F_DZ * RPX_SLOTS]);
-        double len;
-        uint32_t face;
-        nearest_hit<FC>(S, o, d, max_length, &len, &face);
-        cs[F_LEN * RPX_SLOTS + slot] = len;
-        cu[U_ENDFACE * RPX_SLOTS + slot] = face;
+    if (ahead_face != -2) {
+        for (uint32_t slot = threadIdx.x; slot < total; slot += RPX_TILE) {
+            const double* f = cs + slot;
+            vec3 o = v3(f[F_OX * RPX_SLOTS], f[F_OY * RPX_SLOTS], f[F_OZ * RPX_SLOTS]);
+            vec3 d = v3(f[F_DX * RPX_SLOTS], f[F_DY * RPX_SLOTS], f[F_DZ * RPX_SLOTS]);
+            double len;
+            uint32_t face;
+            nearest_hit<FC>(S, o, d, max_length, ahead_face, &len, &face);
+            cs[F_LEN * RPX_SLOTS + slot] = len;
+            cu[U_ENDFACE * RPX_SLOTS + slot] = face;
+        }
+    } else {
+        // untraced: sp_ray.length = INF (every material; gausslets: reset_length_c -> max_length),
+        // end_face_idx still the copy of the parent's (the face that was just hit)
+        const double untraced_len = GAUSS ? max_length : RPX_INF;
+        if (k.has_a) {
+            cs[F_LEN * RPX_SLOTS + slot_a] = untraced_len;
+            cu[U_ENDFACE * RPX_SLOTS + slot_a] = face_idx;
+        }
+        if (k.has_b) {
+            cs[F_LEN * RPX_SLOTS + slot_b] = untraced_len;
+            cu[U_ENDFACE * RPX_SLOTS + slot_b] = face_idx;
+        }
     }
     // ---- 5. global offset of the tile
     if (threadIdx.x < 32) {

@@ -18,6 +18,7 @@ struct ShadeArgs {
     uint32_t* face_counts;
     uint32_t n_tiles;
     int smem_bytes;
+    int ahead_face;  // -1 all faces, >= 0 one face, -2 no trace-ahead (see k_shade)
 };
 
 // one launcher per compiled variant: g = gausslets, f = face class, m = material mask index
@@ -47,7 +48,7 @@ inline ShadeLauncher shade_launcher(int gauss, int fc, int mm_idx) {
     return table[gauss ? 1 : 0][fc ? 1 : 0][mm_idx & 3];
 }
 cudaError_t launch_intersect(int fc, cudaStream_t st, unsigned n_tiles, int smem, const DevScene& S, const Soa& rays,
-                             double max_length);
+                             double max_length, int only_face);
 
 cudaError_t launch_unit_face_intersect(cudaStream_t st, const DevScene& S, int face, const double* p1,
                                        const double* p2, unsigned long long n, int is_base_ray, double* out);

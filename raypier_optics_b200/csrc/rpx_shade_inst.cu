@@ -34,7 +34,7 @@ cudaError_t RPX_CAT(RPX_I_GAUSS, RPX_I_FC, RPX_I_MM)(cudaStream_t st, const Shad
         configured = true;
     }
     kern<<<a.n_tiles, RPX_TILE, dyn, st>>>(a.S, a.in, a.out, a.max_length, a.tile_state, a.tile_counter, a.d_count,
-                                           a.face_counts, a.n_tiles, a.smem_bytes);
+                                           a.face_counts, a.n_tiles, a.smem_bytes, a.ahead_face);
     return cudaGetLastError();
 }
 

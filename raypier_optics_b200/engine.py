@@ -169,6 +169,18 @@ class Engine(object):
                                       int(recursion_limit), int(flags), C.byref(h)))
         return TraceResult(self, h, is_g)
 
+    def trace_sequence(self, rays, face_seq, max_length, recursion_limit):
+        """Sequential trace (``rpx_trace_sequence``): step s intersects only the face with
+        global index ``face_seq[s]``."""
+        rays = np.ascontiguousarray(rays)
+        is_g = self._is_gausslet(rays)
+        seq = np.ascontiguousarray(face_seq, dtype=np.int32)
+        h = C.c_void_p()
+        self._check(self._L.rpx_trace_sequence(self._ctx, rays.ctypes.data, rays.shape[0], is_g,
+                                               float(max_length), int(recursion_limit), seq.ctypes.data,
+                                               int(seq.shape[0]), C.byref(h)))
+        return TraceResult(self, h, is_g)
+
     def trace_device(self, dev_rays, max_length, recursion_limit, flags=A.TRACE_DEFAULT):
         """Inputs already resident (``rpx_trace_device``); consumes ``dev_rays``."""
         h = C.c_void_p()

@@ -1,0 +1,105 @@
+"""Sequential mode: trace_ray_sequence (raypier/core/tracer.py:50-99) over
+trace_one_face_segment_c / trace_one_face_gausslet_c (ctracer.pyx:2121-2170, 2284-2347)."""
+import numpy as np
+import pytest
+
+from raypier_optics_b200 import configs, scene as SC
+from raypier_optics_b200.core import tracer as T
+
+from util import compare_traces
+
+
+def achromat_sequence(core, n, gausslets=False):
+    """The doublet traced front to back: one FaceList listed three times (so all_faces chains its
+    faces three times and f.idx keeps the LAST occurrence, as in the reference)."""
+    cfg = configs.build(core, "config2", n=n)
+    fl = cfg['face_lists'][0]
+    rays = cfg['rays']
+    if gausslets:
+        rays = rays.copy()
+        rays['length'] = cfg['max_length']
+        rays['ray_type_id'] = 2
+        gc = core.ctracer.GaussletCollection.from_rays(rays)
+        gc.config_parabasal_rays(cfg['wavelengths'], 0.3, 0.0)
+        rays = gc.copy_as_array()
+    return cfg, [(fl, 0), (fl, 1), (fl, 2)], rays
+
+
+def mirror_sequence(core, n):
+    """Michelson arm: cube entrance face, diagonal splitter, cube exit, mirror, back."""
+    cfg = configs.build(core, "config5", n=n, gausslets=False)
+    cube, m1, m2 = cfg['face_lists']
+    return cfg, [(cube, 0), (cube, 6), (cube, 1), (m1, 0), (cube, 1)], cfg['rays']
+
+
+@pytest.mark.parametrize("which", ["achromat", "achromat_gausslets", "michelson"])
+def test_oracle_sequence_bit_exact_with_reference(refcore, which):
+    from oracle import oracle as O
+    if which == "michelson":
+        cfg, seq, rays = mirror_sequence(refcore, 1500)
+    else:
+        cfg, seq, rays = achromat_sequence(refcore, 1500, gausslets=which.endswith("gausslets"))
+    rc = O.reference_collection(refcore, rays, cfg['wavelengths'])
+    traced, all_faces = O.reference_trace_ray_sequence(refcore, rc, seq, cfg['recursion_limit'], cfg['max_length'])
+    ref = [t.copy_as_array() for t in traced]
+    sc = SC.Scene([fl for fl, _ in seq], cfg['wavelengths'])
+    gidx = T.sequence_face_indices(seq)
+    gens, counts = O.trace_ray_sequence(sc, rays, gidx, cfg['recursion_limit'], cfg['max_length'])
+    assert [len(g) for g in gens] == [len(r) for r in ref]
+    assert len(gens) >= 3
+    for gi, (g, r) in enumerate(zip(gens, ref)):
+        assert g.tobytes() == r.tobytes(), "%s generation %d not bit-identical" % (which, gi)
+    # a FaceList listed k times appears k times in all_faces (same objects): the hit counts
+    # land on the index of the LAST occurrence, which is the one Face.idx keeps
+    last = {id(f): i for i, f in enumerate(all_faces)}
+    expect = [f.count if last[id(f)] == i else 0 for i, f in enumerate(all_faces)]
+    assert counts.tolist() == expect
+
+
+def test_sequence_indices_follow_last_occurrence(core):
+    cfg, seq, _ = achromat_sequence(core, 10)
+    assert T.sequence_face_indices(seq) == [6, 7, 8]
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("which", ["achromat", "achromat_gausslets", "michelson"])
+def test_cuda_sequence_matches_oracle(engine, core, which):
+    from oracle import oracle as O
+    if which == "michelson":
+        cfg, seq, rays = mirror_sequence(core, 20000)
+    else:
+        cfg, seq, rays = achromat_sequence(core, 20000, gausslets=which.endswith("gausslets"))
+    sc = SC.Scene([fl for fl, _ in seq], cfg['wavelengths'])
+    gidx = T.sequence_face_indices(seq)
+    want, want_counts = O.trace_ray_sequence(sc, rays, gidx, cfg['recursion_limit'], cfg['max_length'])
+    engine.set_scene(sc)
+    res = engine.trace_sequence(rays, gidx, cfg['max_length'], cfg['recursion_limit'])
+    got = res.generations()
+    compare_traces(got, want, which)
+    assert np.array_equal(res.face_counts, want_counts)
+    res.free()
+
+
+@pytest.mark.gpu
+def test_drop_in_trace_functions(engine, core):
+    """The reference-facing functions with the reference's container classes."""
+    from oracle import oracle as O
+    ct = core.ctracer
+    cfg = configs.build(core, "config1", n=3000)
+    rc = ct.RayCollection.from_array(cfg['rays'])
+    rc.wavelengths = cfg['wavelengths']
+    traced, all_faces = T.trace_rays(rc, cfg['face_lists'], recursion_limit=cfg['recursion_limit'],
+                                     max_length=cfg['max_length'])
+    assert traced[0] is rc and [len(t) for t in traced] == [3000, 3000, 3000]
+    assert traced[1].parent is traced[0] and np.array_equal(traced[2].wavelengths, cfg['wavelengths'])
+    assert [f.idx for f in all_faces] == [0, 1] and [f.count for f in all_faces] == [3000, 3000]
+    sc = SC.Scene(cfg['face_lists'], cfg['wavelengths'])
+    want, _ = O.trace_rays(sc, cfg['rays'], cfg['recursion_limit'], cfg['max_length'])
+    compare_traces([t.copy_as_array() for t in traced], want, "trace_rays drop-in")
+    # sequential drop-in
+    cfg2, seq, rays = achromat_sequence(core, 2000)
+    rc2 = ct.RayCollection.from_array(rays)
+    rc2.wavelengths = cfg2['wavelengths']
+    traced2, faces2 = T.trace_ray_sequence(rc2, seq, recursion_limit=100, max_length=cfg2['max_length'])
+    assert len(traced2) == 4 and len(faces2) == 9
+    assert np.all(np.isinf(traced2[-1].length))            # the last generation is returned untraced
