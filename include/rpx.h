@@ -293,6 +293,8 @@ typedef struct rpx_result rpx_result; /* all generations of one trace         */
 #define RPX_TRACE_DEFAULT 0u
 #define RPX_TRACE_KEEP_LAST_ONLY 1u /* streaming mode: keep counts + face counts, free
                                        generation g-1 once g is built (N too big to keep) */
+#define RPX_TRACE_EXACT_SYNC 2u     /* read len(new_rays) back after every generation instead of
+                                       pipelining launches on a one-generation-old count       */
 
 /* Replaces: module import of raypier.core.ctracer (no device state exists there). */
 int rpx_init(int device, rpx_ctx** out_ctx);

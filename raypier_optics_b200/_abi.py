@@ -83,6 +83,7 @@ PARA_DEFAULT, PARA_SNELL, PARA_GRATING = 0, 1, 2
 
 TRACE_DEFAULT = 0
 TRACE_KEEP_LAST_ONLY = 1
+TRACE_EXACT_SYNC = 2
 
 RPX_OK = 0
 STATUS_NAMES = {0: "RPX_OK", -1: "RPX_ERR_INVALID", -2: "RPX_ERR_UNSUPPORTED", -3: "RPX_ERR_CUDA",

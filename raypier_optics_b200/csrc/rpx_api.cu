@@ -34,6 +34,9 @@ static_assert(sizeof(rpx_distortion) == 64, "rpx_distortion layout");
 
 static thread_local std::string g_init_error;
 
+#define RPX_MAX_PIPE_GENS 1024  /* generations a pipelined trace can hold counts for */
+#define RPX_PIPE_STATE_TILES (4u << 20) /* 32 MB of look-back state: 5e8 parents per trace without a re-zero */
+
 struct rpx_rays {
     Soa soa;
     void* block;  // single allocation backing soa.f / soa.u / soa.p
@@ -65,6 +68,12 @@ struct rpx_ctx {
     unsigned long long* d_count;
     unsigned long long* h_count;  // pinned
     uint32_t* d_face_counts;
+    unsigned long long* d_counts;  // per-generation counts of a pipelined trace (RPX_MAX_PIPE_GENS)
+    unsigned long long* h_counts;  // pinned + mapped: the kernels write len(new_rays) straight into it
+    unsigned long long* h_counts_dev;  // device alias of h_counts
+    unsigned long long* pipe_state;  // tile-state slices of a pipelined trace, zeroed ahead of use
+    size_t pipe_state_cap;           // tiles
+    uint32_t* pipe_counters;         // one ticket counter per generation
     // event pool
     std::vector<cudaEvent_t> ev_pool;
     size_t ev_used;
@@ -144,6 +153,16 @@ extern "C" int rpx_init(int device, rpx_ctx** out_ctx) {
         return RPX_ERR_CUDA;
     }
     ctx->d_face_counts = nullptr;
+    if ((e = cudaMalloc(&ctx->d_counts, sizeof(unsigned long long) * RPX_MAX_PIPE_GENS)) != cudaSuccess ||
+        (e = cudaHostAlloc(&ctx->h_counts, sizeof(unsigned long long) * RPX_MAX_PIPE_GENS, cudaHostAllocMapped)) != cudaSuccess ||
+        (e = cudaHostGetDevicePointer(&ctx->h_counts_dev, ctx->h_counts, 0)) != cudaSuccess ||
+        (e = cudaMalloc(&ctx->pipe_counters, sizeof(uint32_t) * RPX_MAX_PIPE_GENS)) != cudaSuccess ||
+        (e = cudaMalloc(&ctx->pipe_state, sizeof(unsigned long long) * RPX_PIPE_STATE_TILES)) != cudaSuccess) {
+        fail(nullptr, RPX_ERR_CUDA, "context scratch allocation failed: %s", cudaGetErrorString(e));
+        delete ctx;
+        return RPX_ERR_CUDA;
+    }
+    ctx->pipe_state_cap = RPX_PIPE_STATE_TILES;
     *out_ctx = ctx;
     return RPX_OK;
 }
@@ -157,6 +176,10 @@ extern "C" void rpx_shutdown(rpx_ctx* ctx) {
     if (ctx->tile_state) cudaFree(ctx->tile_state);
     if (ctx->d_face_counts) cudaFree(ctx->d_face_counts);
     cudaFree(ctx->tile_counter);
+    cudaFree(ctx->d_counts);
+    cudaFree(ctx->pipe_counters);
+    cudaFree(ctx->pipe_state);
+    cudaFreeHost(ctx->h_counts);
     cudaFree(ctx->d_count);
     cudaFreeHost(ctx->h_count);
     cudaStreamDestroy(ctx->stream);
@@ -476,6 +499,158 @@ extern "C" void rpx_result_free(rpx_ctx* ctx, rpx_result* res) {
     delete res;
 }
 
+// ------------------------------------------------------------------ pipelined generation loop
+// The exact loop below learns len(new_rays) with a host round trip per generation, which leaves
+// the GPU idle for ~20 us each time (14 % of a 1e6-ray achromat trace).  Here generation g's
+// kernel is enqueued as soon as the count of generation g-1 is known: its grid and its output
+// buffer are sized from the bound  n_g <= kids * n_{g-1}  and the kernel reads the real n_g from
+// device memory.  The host only ever waits for a count that is one generation old, i.e. for a
+// kernel that has already finished, so kernels run back to back.  Used for non-sequential,
+// keep-everything traces whose buffers stay small enough for the 2x over-allocation.
+static int trace_pipelined(rpx_ctx* ctx, rpx_rays* rays, double ml, int recursion_limit, rpx_result* res) {
+    cudaStream_t st = ctx->stream;
+    const int is_g = rays->is_gausslet;
+    const int smem = ctx->scene_smem;
+    const unsigned long long kids = (unsigned long long)(ctx->max_kids > 0 ? ctx->max_kids : 1);
+    std::vector<rpx_rays*> bufs;       // bufs[g] = generation g (bound-sized for g >= 1)
+    std::vector<cudaEvent_t> ev_cnt;   // ev_cnt[g]: h_counts[g] is valid once it completed
+    std::vector<cudaEvent_t> ev_i0, ev_i1, ev_s0, ev_s1;
+    bufs.push_back(rays);
+    auto bail = [&](int code) {
+        cudaStreamSynchronize(st);
+        for (rpx_rays* b : bufs) rpx_rays_free(ctx, b);
+        delete res;
+        return code;
+    };
+#define CUP(call)                                                                                  \
+    do {                                                                                           \
+        cudaError_t e_ = (call);                                                                   \
+        if (e_ != cudaSuccess)                                                                     \
+            return bail(fail(ctx, e_ == cudaErrorMemoryAllocation ? RPX_ERR_NOMEM : RPX_ERR_CUDA,   \
+                             "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__)); \
+    } while (0)
+    const int max_g = recursion_limit < RPX_MAX_PIPE_GENS - 2 ? recursion_limit : RPX_MAX_PIPE_GENS - 2;
+    cudaEvent_t ev_begin = next_event(ctx), ev_end = next_event(ctx);
+    CUP(cudaMemsetAsync(ctx->d_face_counts, 0, sizeof(uint32_t) * (size_t)(ctx->n_traced > 0 ? ctx->n_traced : 1), st));
+    CUP(cudaMemsetAsync(ctx->d_counts, 0, sizeof(unsigned long long) * RPX_MAX_PIPE_GENS, st));
+    CUP(cudaMemsetAsync(ctx->pipe_counters, 0, sizeof(uint32_t) * RPX_MAX_PIPE_GENS, st));
+    for (int i = 0; i < RPX_MAX_PIPE_GENS; i++) ctx->h_counts[i] = 0;  // a kernel that never runs leaves 0
+    size_t state_off = 0, zero_end = 0;
+    ctx->h_counts[0] = rays->soa.n;
+    CUP(cudaMemcpyAsync(ctx->d_counts, ctx->h_counts, sizeof(unsigned long long), cudaMemcpyHostToDevice, st));
+    CUP(cudaEventRecord(ev_begin, st));
+    ev_cnt.push_back(ev_begin);  // n_0 is known
+    if (is_g && rays->soa.n) {
+        k_reset_length<<<(unsigned)((rays->soa.n + 255) / 256), 256, 0, st>>>(rays->soa, ml);
+        res->launches++;
+    }
+    {   // generation 0: nearest hit
+        const uint32_t n_tiles = (uint32_t)((rays->soa.n + RPX_TILE - 1) / RPX_TILE);
+        cudaEvent_t a0 = next_event(ctx), a1 = next_event(ctx);
+        CUP(cudaEventRecord(a0, st));
+        CUP(launch_intersect(ctx->face_class, st, n_tiles, smem, ctx->ds, rays->soa, ml, -1));
+        CUP(cudaEventRecord(a1, st));
+        ev_i0.push_back(a0);
+        ev_i1.push_back(a1);
+        res->launches++;
+    }
+    // tile state: one region per launch so that no memset has to wait between kernels
+    unsigned long long bound = rays->soa.n;  // upper bound on n_g (exact for g == 0)
+    int g = 0;
+    for (; g < max_g; g++) {
+        if (g >= 1) {
+            // n_g <= kids * n_{g-1}.  n_{g-1} is ONE generation old: the kernel that produced it
+            // finished before the one now running started, so this wait never stalls the GPU.
+            CUP(cudaEventSynchronize(ev_cnt[g - 1]));
+            const unsigned long long n_prev = ctx->h_counts[g - 1];
+            if (n_prev == 0) break;  // generation g-1 is empty: nothing left to trace
+            bound = kids * n_prev;
+            if (bound > bufs[g]->soa.cap) bound = bufs[g]->soa.cap;
+        }
+        if (bound == 0) break;
+        if (kids * bound >= 0xFFFFFFFFull)
+            return bail(fail(ctx, RPX_ERR_INVALID, "generation would exceed the 32-bit parent_idx of ray_t"));
+        rpx_rays* child = nullptr;
+        {
+            int rc = rays_alloc(ctx, kids * bound, is_g, &child);
+            if (rc != RPX_OK) return bail(rc);
+        }
+        bufs.push_back(child);
+        const uint32_t n_tiles = (uint32_t)((bound + RPX_TILE - 1) / RPX_TILE);
+        // look-back state: a fresh, already-zeroed slice per generation, so that NO memset sits
+        // between two kernels; the zeroed frontier is pushed ahead in large steps
+        if (state_off + n_tiles > ctx->pipe_state_cap) {  // wrap: everything before is finished by then
+            state_off = 0;
+            zero_end = 0;
+        }
+        if (state_off + n_tiles > zero_end) {
+            size_t want = state_off + (size_t)n_tiles * 6;
+            if (want > ctx->pipe_state_cap) want = ctx->pipe_state_cap;
+            CUP(cudaMemsetAsync(ctx->pipe_state + zero_end, 0, (want - zero_end) * sizeof(unsigned long long), st));
+            zero_end = want;
+        }
+        unsigned long long* state = ctx->pipe_state + state_off;
+        state_off += n_tiles;
+        ShadeArgs sa;
+        sa.S = ctx->ds;
+        sa.in = bufs[g]->soa;
+        sa.in.n = bound;
+        sa.out = child->soa;
+        sa.max_length = ml;
+        sa.tile_state = state;
+        sa.tile_counter = ctx->pipe_counters + g;
+        sa.d_count = ctx->d_counts + (g + 1);
+        sa.face_counts = ctx->d_face_counts;
+        sa.n_tiles = n_tiles;
+        sa.smem_bytes = smem;
+        sa.ahead_face = -1;
+        sa.n_dev = ctx->d_counts + g;
+        sa.h_count = ctx->h_counts_dev + (g + 1);
+        cudaEvent_t b0 = next_event(ctx), b1 = next_event(ctx);
+        CUP(cudaEventRecord(b0, st));
+        CUP(shade_launcher(is_g, ctx->face_class, ctx->mm_idx)(st, sa));
+        CUP(cudaEventRecord(b1, st));  // also marks h_counts[g + 1] valid
+        ev_s0.push_back(b0);
+        ev_s1.push_back(b1);
+        ev_cnt.push_back(b1);
+        res->launches++;
+    }
+    CUP(cudaEventRecord(ev_end, st));
+    CUP(cudaMemcpyAsync(res->face_counts.data(), ctx->d_face_counts, sizeof(uint32_t) * (size_t)ctx->n_traced,
+                        cudaMemcpyDeviceToHost, st));
+    CUP(cudaStreamSynchronize(st));
+    // traced_rays = generations 0..G-1 with n_g > 0 and g < recursion_limit
+    const int launched = (int)bufs.size();  // bufs[0..launched-1]; counts known for all of them
+    int G = 0;
+    while (G < launched && G < recursion_limit && ctx->h_counts[G] > 0) G++;
+    for (int i = 0; i < launched; i++) {
+        if (i < G) {
+            bufs[i]->soa.n = ctx->h_counts[i];
+            res->gens.push_back(bufs[i]);
+            res->counts.push_back(ctx->h_counts[i]);
+        } else {
+            rpx_rays_free(ctx, bufs[i]);
+        }
+    }
+    bufs.clear();
+    float ms = 0;
+    cudaEventElapsedTime(&ms, ev_begin, ev_end);
+    res->device_ms = ms;
+    for (size_t i = 0; i < ev_i0.size(); i++) {
+        cudaEventElapsedTime(&ms, ev_i0[i], ev_i1[i]);
+        res->k_ms[0] += ms;
+        res->k_launches[0]++;
+    }
+    // only kernels that had work count towards the per-launch average
+    for (size_t i = 0; i < ev_s0.size() && (int)i < G; i++) {
+        cudaEventElapsedTime(&ms, ev_s0[i], ev_s1[i]);
+        res->k_ms[1] += ms;
+        res->k_launches[1]++;
+    }
+#undef CUP
+    return RPX_OK;
+}
+
 // The generation loop.  face_seq == NULL: non-sequential trace_rays (core/tracer.py:39-45).
 // face_seq != NULL: trace_ray_sequence (core/tracer.py:84-97): step s intersects only face
 // face_seq[s]; the generation produced by the last step is appended untraced.
@@ -509,6 +684,20 @@ static int trace_loop(rpx_ctx* ctx, rpx_rays* rays, double max_length, int recur
     res->face_counts.assign((size_t)ctx->n_traced, 0u);
     ctx->ev_used = 0;
     std::vector<cudaEvent_t> ev_i0, ev_i1, ev_s0, ev_s1;
+
+    // small / medium keep-everything traces: pipelined launches (no per-generation host stall)
+    {
+        const size_t rec = is_g ? RPX_GAUSSLET_BYTES : RPX_RAY_BYTES;
+        const unsigned long long kids = (unsigned long long)(ctx->max_kids > 0 ? ctx->max_kids : 1);
+        const bool fits = (double)rays->soa.n * (double)rec * (double)(kids * kids) <= 4.0e9;
+        if (!sequential && !(flags & (RPX_TRACE_KEEP_LAST_ONLY | RPX_TRACE_EXACT_SYNC)) && fits && rays->soa.n > 0 &&
+            recursion_limit <= RPX_MAX_PIPE_GENS - 2) {
+            int rc = trace_pipelined(ctx, rays, ml, recursion_limit, res);
+            if (rc != RPX_OK) return rc;
+            *out_result = res;
+            return RPX_OK;
+        }
+    }
 
     // Ownership: `rays` belongs to this call from here on (success or failure).  `cur` is
     // either the last entry of res->gens or not yet part of it; `child` likewise.
@@ -589,6 +778,8 @@ static int trace_loop(rpx_ctx* ctx, rpx_rays* rays, double max_length, int recur
             sa.n_tiles = n_wtiles;
             sa.smem_bytes = smem;
             sa.ahead_face = !sequential ? -1 : (count + 1 < n_seq ? face_seq[count + 1] : -2);
+            sa.n_dev = nullptr;
+            sa.h_count = nullptr;
             cudaError_t le = shade_launcher(is_g, ctx->face_class, ctx->mm_idx)(st, sa);
             CUR(le);
         }

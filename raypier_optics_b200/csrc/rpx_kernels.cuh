@@ -334,7 +334,10 @@ template <bool GAUSS, int FC, uint32_t MM>
 __global__ void __launch_bounds__(RPX_TILE, RPX_MIN_BLOCKS)
 k_shade(DevScene S, Soa in, Soa out, double max_length, unsigned long long* tile_state,
         uint32_t* tile_counter, unsigned long long* d_count, uint32_t* face_counts, uint32_t n_tiles,
-        int smem_bytes, int ahead_face) {
+        int smem_bytes, int ahead_face, const unsigned long long* n_dev, unsigned long long* h_count) {
+    // n_dev != NULL: the parent count is not known on the host yet (the launch was enqueued
+    // before the previous generation's kernel finished): the grid covers an upper bound and the
+    // real count is read here; surplus CTAs leave at once.
     // ahead_face: -1 trace the children ahead against every face (non-sequential mode);
     //             >= 0 only against that face (next step of a face sequence);
     //             -2 leave them untraced (last step of a sequence: the reference appends that
@@ -343,15 +346,23 @@ k_shade(DevScene S, Soa in, Soa out, double max_length, unsigned long long* tile
     __shared__ uint32_t s_tile;
     __shared__ uint32_t s_warp[RPX_TILE / 32];
     __shared__ unsigned long long s_prefix;
-    if (threadIdx.x == 0) s_tile = atomicAdd(tile_counter, 1u);
     // dynamic shared memory: [child staging][scene copy]
     double* cs = reinterpret_cast<double*>(smem);
     uint32_t* cu = reinterpret_cast<uint32_t*>(smem + RPX_SLOTS * NF * 8);
-    stage_scene(S, smem + RPX_STAGE_BYTES, smem_bytes);  // contains a __syncthreads() when it stages
+    stage_scene(S, smem + RPX_STAGE_BYTES, smem_bytes);  // once per (persistent) CTA
+    const unsigned long long n_in = n_dev ? *n_dev : in.n;
+    const uint32_t n_tiles_real = (uint32_t)((n_in + RPX_TILE - 1) / RPX_TILE);
+    (void)n_tiles;
+    const unsigned long long cap = in.cap;
+  // PERSISTENT CTA: the grid is one wave of resident CTAs; each pulls tiles from the ticket
+  // counter until the (device-resident) tile count is exhausted.
+  for (;;) {
+    __syncthreads();  // previous tile's staging buffer / s_tile fully consumed
+    if (threadIdx.x == 0) s_tile = atomicAdd(tile_counter, 1u);
     __syncthreads();
     const uint32_t tile = s_tile;
+    if (tile >= n_tiles_real) break;  // uniform per CTA; tickets are dense, so tiles [0, real) all run
     const unsigned long long i = (unsigned long long)tile * RPX_TILE + threadIdx.x;
-    const unsigned long long cap = in.cap;
 
     Kids k;
     k.has_a = false;
@@ -361,7 +372,7 @@ k_shade(DevScene S, Soa in, Soa out, double max_length, unsigned long long* tile
     double plen[RPX_NPARA];
     bool hit = false;
     RayIn r;
-    if (i < in.n) {
+    if (i < n_in) {
         // every load is issued before the first use: one DRAM round trip per tile, not two
         face_idx = in.u[U_ENDFACE * cap + i];
         r.o = v3(in.f[F_OX * cap + i], in.f[F_OY * cap + i], in.f[F_OZ * cap + i]);
@@ -462,24 +473,33 @@ k_shade(DevScene S, Soa in, Soa out, double max_length, unsigned long long* tile
         unsigned long long excl = tile_lookback(tile_state, tile, total);
         if (threadIdx.x == 0) {
             s_prefix = excl;
-            if (tile == n_tiles - 1) *d_count = excl + total;  // len(new_rays)
+            if (tile == n_tiles_real - 1) {  // len(new_rays)
+                *d_count = excl + total;
+                if (h_count) {  // pipelined loop: straight into mapped pinned host memory, no copy op
+                    *h_count = excl + total;
+                    __threadfence_system();
+                }
+            }
         }
     }
     __syncthreads();
     const unsigned long long base = s_prefix;
-    // ---- 6. coalesced copy-out
+    // ---- 6. coalesced copy-out (kept rolled: unrolling 26 fields x slots bloated the kernel
+    // by ~90 KB of SASS and cost instruction-cache misses)
     {
         const unsigned long long ocap = out.cap;
-#pragma unroll
+#pragma unroll 1
         for (int fld = 0; fld < NF; fld++) {
             double* dst = out.f + (unsigned long long)fld * ocap + base;
             const double* src = cs + fld * RPX_SLOTS;
+#pragma unroll 1
             for (uint32_t slot = threadIdx.x; slot < total; slot += RPX_TILE) dst[slot] = src[slot];
         }
-#pragma unroll
+#pragma unroll 1
         for (int fld = 0; fld < NU; fld++) {
             uint32_t* dst = out.u + (unsigned long long)fld * ocap + base;
             const uint32_t* src = cu + fld * RPX_SLOTS;
+#pragma unroll 1
             for (uint32_t slot = threadIdx.x; slot < total; slot += RPX_TILE) dst[slot] = src[slot];
         }
     }
@@ -520,6 +540,7 @@ k_shade(DevScene S, Soa in, Soa out, double max_length, unsigned long long* tile
             }
         }
     }
+  }  // persistent tile loop
 }
 
 }  // namespace rpx

@@ -19,6 +19,8 @@ struct ShadeArgs {
     uint32_t n_tiles;
     int smem_bytes;
     int ahead_face;  // -1 all faces, >= 0 one face, -2 no trace-ahead (see k_shade)
+    const unsigned long long* n_dev;  // device-resident parent count (pipelined launches) or NULL
+    unsigned long long* h_count;      // mapped host slot for len(new_rays) or NULL
 };
 
 // one launcher per compiled variant: g = gausslets, f = face class, m = material mask index

@@ -23,18 +23,24 @@ static constexpr uint32_t kMask = RPX_MM_ALL;
 #endif
 
 cudaError_t RPX_CAT(RPX_I_GAUSS, RPX_I_FC, RPX_I_MM)(cudaStream_t st, const ShadeArgs& a) {
-    // dynamic shared memory = child staging (47 KB) + the scene copy: needs the > 48 KB opt-in
-    static bool configured = false;
+    // dynamic shared memory = child staging (47 KB) + the scene copy: needs the > 48 KB opt-in.
+    // Persistent grid: one wave of resident CTAs (SMs x occupancy), never more than the tiles.
+    static int resident_ctas = 0;  // one device per process
     const int dyn = RPX_STAGE_BYTES + a.smem_bytes;
     auto kern = k_shade<(RPX_I_GAUSS != 0), RPX_I_FC, kMask>;
-    if (!configured) {
+    if (!resident_ctas) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                              RPX_STAGE_BYTES + 40 * 1024);
         if (e != cudaSuccess) return e;
-        configured = true;
+        int dev = 0, sms = 0, per_sm = 0;
+        if ((e = cudaGetDevice(&dev)) != cudaSuccess) return e;
+        if ((e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev)) != cudaSuccess) return e;
+        if ((e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, RPX_TILE, dyn)) != cudaSuccess) return e;
+        resident_ctas = sms * (per_sm < 1 ? 1 : per_sm);
     }
-    kern<<<a.n_tiles, RPX_TILE, dyn, st>>>(a.S, a.in, a.out, a.max_length, a.tile_state, a.tile_counter, a.d_count,
-                                           a.face_counts, a.n_tiles, a.smem_bytes, a.ahead_face);
+    const unsigned grid = a.n_tiles < (unsigned)resident_ctas ? a.n_tiles : (unsigned)resident_ctas;
+    kern<<<grid, RPX_TILE, dyn, st>>>(a.S, a.in, a.out, a.max_length, a.tile_state, a.tile_counter, a.d_count,
+                                      a.face_counts, a.n_tiles, a.smem_bytes, a.ahead_face, a.n_dev, a.h_count);
     return cudaGetLastError();
 }
 
