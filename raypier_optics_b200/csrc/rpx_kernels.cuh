@@ -356,13 +356,16 @@ k_shade(DevScene S, Soa in, Soa out, double max_length, unsigned long long* tile
     const unsigned long long cap = in.cap;
   // PERSISTENT CTA: the grid is one wave of resident CTAs; each pulls tiles from the ticket
   // counter until the (device-resident) tile count is exhausted.
+  if (threadIdx.x == 0) s_tile = atomicAdd(tile_counter, 1u);
   for (;;) {
-    __syncthreads();  // previous tile's staging buffer / s_tile fully consumed
-    if (threadIdx.x == 0) s_tile = atomicAdd(tile_counter, 1u);
-    __syncthreads();
+    __syncthreads();  // s_tile published; previous tile's staging buffer fully consumed
     const uint32_t tile = s_tile;
     if (tile >= n_tiles_real) break;  // uniform per CTA; tickets are dense, so tiles [0, real) all run
     const unsigned long long i = (unsigned long long)tile * RPX_TILE + threadIdx.x;
+    __syncthreads();  // everyone has read s_tile
+    // take the NEXT ticket now (its latency hides behind this tile's work) ...
+    uint32_t next_tile = 0;
+    if (threadIdx.x == 0) next_tile = atomicAdd(tile_counter, 1u);
 
     Kids k;
     k.has_a = false;
@@ -436,13 +439,35 @@ k_shade(DevScene S, Soa in, Soa out, double max_length, unsigned long long* tile
     const uint32_t cnt = (k.has_a ? 1u : 0u) + (k.has_b ? 1u : 0u);
     uint32_t total;
     const uint32_t local = block_exclusive_scan(cnt, &total, s_warp);
-    if (threadIdx.x == 0) tile_publish(tile_state, tile, total);
+    if (threadIdx.x == 0) {
+        tile_publish(tile_state, tile, total);
+        s_tile = next_tile;  // ... and hand it to the CTA (read after the next barrier)
+    }
     // ---- 3. stage children in emission order (reflected, then transmitted)
     const uint32_t parent = (uint32_t)i;
     const uint32_t slot_a = local, slot_b = local + (k.has_a ? 1u : 0u);
     if (k.has_a) stage_child(cs, cu, slot_a, k, k.a, wl, parent, ident);
     if (k.has_b) stage_child(cs, cu, slot_b, k, k.b, wl, parent, ident);
     __syncthreads();
+    {   // pull the next tile's parent records towards L2 while this tile computes
+        const uint32_t nt = s_tile;
+        if (nt < n_tiles_real) {
+            const unsigned long long ni = (unsigned long long)nt * RPX_TILE + threadIdx.x;
+            if ((threadIdx.x & 3) == 0) {  // one prefetch per 32-byte sector
+                const int pf[18] = {F_OX, F_OY, F_OZ, F_DX, F_DY, F_DZ, F_EX, F_EY, F_EZ, F_NR, F_NI,
+                                    F_E1R, F_E1I, F_E2R, F_E2I, F_LEN, F_PHASE, F_APATH};
+#pragma unroll
+                for (int q = 0; q < 18; q++)
+                    asm volatile("prefetch.global.L2 [%0];" ::"l"(in.f + (unsigned long long)pf[q] * cap + ni));
+            }
+            if ((threadIdx.x & 7) == 0) {
+                const int pu[4] = {U_WL, U_ENDFACE, U_IDENT, U_TYPE};
+#pragma unroll
+                for (int q = 0; q < 4; q++)
+                    asm volatile("prefetch.global.L2 [%0];" ::"l"(in.u + (unsigned long long)pu[q] * cap + ni));
+            }
+        }
+    }
     // ---- 4. trace ahead
     if (ahead_face != -2) {
         for (uint32_t slot = threadIdx.x; slot < total; slot += RPX_TILE) {
@@ -484,23 +509,25 @@ k_shade(DevScene S, Soa in, Soa out, double max_length, unsigned long long* tile
     }
     __syncthreads();
     const unsigned long long base = s_prefix;
-    // ---- 6. coalesced copy-out (kept rolled: unrolling 26 fields x slots bloated the kernel
-    // by ~90 KB of SASS and cost instruction-cache misses)
+    // ---- 6. coalesced copy-out: slot == consecutive addresses.  Two explicit passes (a tile has
+    // at most 2 * RPX_TILE children), each a straight line of 26 independent LDS -> STG pairs.
+    // (Letting the compiler unroll a generic slot loop bloated the kernel by ~90 KB of SASS; a
+    // fully rolled loop cost 14 % of the stall samples in branch / index overhead.)
     {
         const unsigned long long ocap = out.cap;
-#pragma unroll 1
-        for (int fld = 0; fld < NF; fld++) {
-            double* dst = out.f + (unsigned long long)fld * ocap + base;
-            const double* src = cs + fld * RPX_SLOTS;
-#pragma unroll 1
-            for (uint32_t slot = threadIdx.x; slot < total; slot += RPX_TILE) dst[slot] = src[slot];
-        }
-#pragma unroll 1
-        for (int fld = 0; fld < NU; fld++) {
-            uint32_t* dst = out.u + (unsigned long long)fld * ocap + base;
-            const uint32_t* src = cu + fld * RPX_SLOTS;
-#pragma unroll 1
-            for (uint32_t slot = threadIdx.x; slot < total; slot += RPX_TILE) dst[slot] = src[slot];
+#pragma unroll
+        for (int pass = 0; pass < 2; pass++) {
+            const uint32_t slot = threadIdx.x + pass * RPX_TILE;
+            if (slot < total) {
+                double* dst = out.f + base + slot;
+                const double* src = cs + slot;
+#pragma unroll
+                for (int fld = 0; fld < NF; fld++) dst[(unsigned long long)fld * ocap] = src[fld * RPX_SLOTS];
+                uint32_t* dstu = out.u + base + slot;
+                const uint32_t* srcu = cu + slot;
+#pragma unroll
+                for (int fld = 0; fld < NU; fld++) dstu[(unsigned long long)fld * ocap] = srcu[fld * RPX_SLOTS];
+            }
         }
     }
 
