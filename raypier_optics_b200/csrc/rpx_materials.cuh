@@ -249,21 +249,39 @@ __device__ void material_eval(const DevScene& S, const rpx_material* M, const Ra
                 n2 = ntab_get(S, M, 1, r.wl);
                 flip = -1;
             }
-            cplx sin2 = (n1 * sin1) / n2;
-            cplx cos2 = csqrt_(cx(1.0, 0.0) - sin2 * sin2);
             double P_in = n1.re * (s_amp.re * s_amp.re + s_amp.im * s_amp.im + p_amp.re * p_amp.re +
                                    p_amp.im * p_amp.im);
             if (P_in == 0.0) return;
-            cplx n2c1 = n2 * cos1, n1c2 = n1 * cos2, n2c2 = n2 * cos2, n1c1 = n1 * cos1;
-            cplx idp = crcp(n2c1 + n1c2), ids = crcp(n2c2 + n1c1);  // the two Fresnel denominators
-            cplx R_p = (-(n2c1 - n1c2)) * idp;
-            cplx R_s = (-(n2c2 - n1c1)) * ids;
-            R_s = R_s * s_amp;
-            R_p = R_p * p_amp;
-            double aspect = sqrt_(cos2.re * rcp(cos1));
-            cplx num = (n1 * (2.0 * cos1)) * aspect;
-            cplx T_p = (num * idp) * p_amp;
-            cplx T_s = (num * ids) * s_amp;
+            cplx R_s, R_p, T_s, T_p;
+            // Lossless media below the critical angle (the common case): every Fresnel term is
+            // REAL, so the complex products and reciprocals of the general form collapse to real
+            // ones.  Same formulae, same values to rounding; absorbing media and TIR take the
+            // general complex path below.
+            const double sin2r = (n1.re * sin1) * rcp(n2.re);
+            const double c2sq = 1.0 - sin2r * sin2r;
+            if (n1.im == 0.0 && n2.im == 0.0 && c2sq > 0.0) {
+                const double cos2 = sqrt_(c2sq);
+                const double n2c1 = n2.re * cos1, n1c2 = n1.re * cos2, n2c2 = n2.re * cos2, n1c1 = n1.re * cos1;
+                const double idp = rcp(n2c1 + n1c2), ids = rcp(n2c2 + n1c1);
+                R_p = p_amp * ((n1c2 - n2c1) * idp);
+                R_s = s_amp * ((n1c1 - n2c2) * ids);
+                const double num = (n1.re * (2.0 * cos1)) * sqrt_(cos2 * rcp(cos1));
+                T_p = p_amp * (num * idp);
+                T_s = s_amp * (num * ids);
+            } else {
+                cplx sin2 = (n1 * sin1) / n2;
+                cplx cos2 = csqrt_(cx(1.0, 0.0) - sin2 * sin2);
+                cplx n2c1 = n2 * cos1, n1c2 = n1 * cos2, n2c2 = n2 * cos2, n1c1 = n1 * cos1;
+                cplx idp = crcp(n2c1 + n1c2), ids = crcp(n2c2 + n1c1);  // the two Fresnel denominators
+                R_p = (-(n2c1 - n1c2)) * idp;
+                R_s = (-(n2c2 - n1c1)) * ids;
+                R_s = R_s * s_amp;
+                R_p = R_p * p_amp;
+                double aspect = sqrt_(cos2.re * rcp(cos1));
+                cplx num = (n1 * (2.0 * cos1)) * aspect;
+                T_p = (num * idp) * p_amp;
+                T_s = (num * ids) * s_amp;
+            }
             fresnel_emit(k, r, normal, in_direction, cosTheta, flip, n1, n2, R_s, R_p, T_s, T_p, P_in,
                          P[0], P[1]);
         } break;
@@ -286,51 +304,73 @@ __device__ void material_eval(const DevScene& S, const rpx_material* M, const Ra
                 n3 = ntab_get(S, M, 1, r.wl);
                 flip = -1;
             }
-            cplx n1s = n1 * sin1;
-            cplx sin2 = n1s / n2;
-            cplx cos2 = csqrt_(cx(1.0, 0.0) - sin2 * sin2);
-            cplx sin3 = n1s / n3;
-            cplx cos3 = csqrt_(cx(1.0, 0.0) - sin3 * sin3);
             double P_in = n1.re * (s_amp.re * s_amp.re + s_amp.im * s_amp.im + p_amp.re * p_amp.re +
                                    p_amp.im * p_amp.im);
             if (P_in == 0.0) return;
-            cplx n1cos1 = n1 * cos1;
-            cplx n2cos2 = n2 * cos2;
-            cplx n3cos3 = n3 * cos3;
-            double dwc = 2 * M_PI * P[2] * rcp(wavelength);
-            // phi = -I*dwc*(n2 - sin2*sin2)/cos2   (cmaterials.pyx:1098)
-            cplx phi = (cx(0.0, -dwc) * (n2 - sin2 * sin2)) / cos2;
+            const double dwc = 2 * M_PI * P[2] * rcp(wavelength);
+            cplx R_s, T_s, R_p, T_p;
+            double aspect;
             // ep1 = exp(phi) / (4 n2cos2 n3cos3),  ep2 = exp(-2 phi) = 1 / exp(phi)^2.
             // The reference multiplies every transfer-matrix entry by +-ep1 and then forms
             // R = -M00/M01 and T = M10 + M11*R (:1101-1114): ep1 cancels in R and is a common
             // factor of T, so it is applied once.  Same value to a few ulp, ~40% fewer flops.
-            cplx ephi = cexp_(phi);
-            cplx ep1 = ephi / ((n2cos2 * 4.0) * n3cos3);
-            cplx ep2 = crcp(ephi * ephi);
-            cplx R_s, T_s, R_p, T_p;
-            {
-                cplx am = n1cos1 - n2cos2, ap = n1cos1 + n2cos2;
-                cplx bm = n2cos2 - n3cos3, bp = n2cos2 + n3cos3;
-                cplx ambp = am * bp, apbm = ap * bm, ambm = am * bm, apbp = ap * bp;
-                // M00 = -ep1*X, M01 = ep1*Y, M10 = ep1*U, M11 = -ep1*V
-                cplx X = ambp + apbm * ep2, Y = ambm * ep2 + apbp;
-                cplx U = ambm + apbp * ep2, V = ambp * ep2 + apbm;
-                R_s = X / Y;
-                T_s = ep1 * (U - V * R_s);
-            }
-            {
+            //   M00 = -ep1*X, M01 = ep1*Y, M10 = ep1*U, M11 = -ep1*V
+            const double n1sr = n1.re * sin1;
+            const double sin2r = n1sr * rcp(n2.re), sin3r = n1sr * rcp(n3.re);
+            const double c2sq = 1.0 - sin2r * sin2r, c3sq = 1.0 - sin3r * sin3r;
+            if (n1.im == 0.0 && n2.im == 0.0 && n3.im == 0.0 && c2sq > 0.0 && c3sq > 0.0) {
+                // Lossless film and media, no evanescent wave in the film or the substrate (the
+                // common case): cos2, cos3 and all n*cos products are REAL and phi is purely
+                // imaginary, so exp(phi) has unit modulus, ep2 = conj(exp(phi))^2 needs no
+                // reciprocal, and the matrix entries are real + real * ep2.
+                const double cos2 = sqrt_(c2sq), cos3 = sqrt_(c3sq);
+                const double n2c2 = n2.re * cos2, n3c3 = n3.re * cos3;
+                const double a = dwc * (n2.re - sin2r * sin2r) * rcp(cos2);  // phi = -i a
+                double sa, ca;
+                sincos(a, &sa, &ca);
+                const double g = rcp((n2c2 * 4.0) * n3c3);
+                const cplx ep1 = cx(ca * g, -sa * g);
+                const double e2r = ca * ca - sa * sa, e2i = 2.0 * sa * ca;
+                auto film = [&](double am, double ap, double bm, double bp, cplx& R, cplx& T) {
+                    const double ambp = am * bp, apbm = ap * bm, ambm = am * bm, apbp = ap * bp;
+                    const cplx X = cx(ambp + apbm * e2r, apbm * e2i), Y = cx(ambm * e2r + apbp, ambm * e2i);
+                    const cplx U = cx(ambm + apbp * e2r, apbp * e2i), V = cx(ambp * e2r + apbm, ambp * e2i);
+                    R = X / Y;
+                    T = ep1 * (U - V * R);
+                };
+                const double n1c1 = n1.re * cos1;
+                film(n1c1 - n2c2, n1c1 + n2c2, n2c2 - n3c3, n2c2 + n3c3, R_s, T_s);
+                const double n1c2 = n1.re * cos2, n2c1 = n2.re * cos1, n2c3 = n2.re * cos3, n3c2 = n3.re * cos2;
+                film(n1c2 - n2c1, n1c2 + n2c1, n2c3 - n3c2, n2c3 + n3c2, R_p, T_p);
+                aspect = sqrt_(cos3 * rcp(cos1));
+            } else {
+                cplx n1s = n1 * sin1;
+                cplx sin2 = n1s / n2;
+                cplx cos2 = csqrt_(cx(1.0, 0.0) - sin2 * sin2);
+                cplx sin3 = n1s / n3;
+                cplx cos3 = csqrt_(cx(1.0, 0.0) - sin3 * sin3);
+                cplx n1cos1 = n1 * cos1;
+                cplx n2cos2 = n2 * cos2;
+                cplx n3cos3 = n3 * cos3;
+                // phi = -I*dwc*(n2 - sin2*sin2)/cos2   (cmaterials.pyx:1098)
+                cplx phi = (cx(0.0, -dwc) * (n2 - sin2 * sin2)) / cos2;
+                cplx ephi = cexp_(phi);
+                cplx ep1 = ephi / ((n2cos2 * 4.0) * n3cos3);
+                cplx ep2 = crcp(ephi * ephi);
+                auto film = [&](cplx am, cplx ap, cplx bm, cplx bp, cplx& R, cplx& T) {
+                    cplx ambp = am * bp, apbm = ap * bm, ambm = am * bm, apbp = ap * bp;
+                    cplx X = ambp + apbm * ep2, Y = ambm * ep2 + apbp;
+                    cplx U = ambm + apbp * ep2, V = ambp * ep2 + apbm;
+                    R = X / Y;
+                    T = ep1 * (U - V * R);
+                };
+                film(n1cos1 - n2cos2, n1cos1 + n2cos2, n2cos2 - n3cos3, n2cos2 + n3cos3, R_s, T_s);
                 cplx n1cos2 = n1 * cos2, n2cos1 = n2 * cos1, n2cos3 = n2 * cos3, n3cos2 = n3 * cos2;
-                cplx am = n1cos2 - n2cos1, ap = n1cos2 + n2cos1;
-                cplx bm = n2cos3 - n3cos2, bp = n2cos3 + n3cos2;
-                cplx ambp = am * bp, apbm = ap * bm, ambm = am * bm, apbp = ap * bp;
-                cplx X = ambp + apbm * ep2, Y = ambm * ep2 + apbp;
-                cplx U = ambm + apbp * ep2, V = ambp * ep2 + apbm;
-                R_p = X / Y;
-                T_p = ep1 * (U - V * R_p);
+                film(n1cos2 - n2cos1, n1cos2 + n2cos1, n2cos3 - n3cos2, n2cos3 + n3cos2, R_p, T_p);
+                aspect = sqrt_(cos3.re * rcp(cos1));
             }
             R_s = R_s * s_amp;
             R_p = R_p * p_amp;
-            double aspect = sqrt_(cos3.re * rcp(cos1));
             T_s = T_s * (s_amp * aspect);
             T_p = T_p * (p_amp * aspect);
             fresnel_emit(k, r, normal, in_direction, cosTheta, flip, n1, n3, R_s, R_p, T_s, T_p, P_in,
