@@ -372,6 +372,28 @@ void rpx_result_free(rpx_ctx* ctx, rpx_result* res);
  * with its own events); returned as void* to keep CUDA types out of the ABI. */
 void* rpx_stream(rpx_ctx* ctx);
 
+/* ---------------------------------------------------------- capture planes
+ * select_ray_intersections / select_gausslet_intersections (ctracer.pyx:1981-2058), the
+ * filter behind probes.py RayCapturePlane / GaussletCapturePlane (:119-143): every ray of every
+ * generation is re-intersected, between its origin and its traced end point, with ONE FaceList
+ * (normally a single RectangularFace); hits are appended in (generation, ray) order with
+ * length = distance to the capture face and end_face_idx = that face's idx.  Run on the device
+ * it removes the need to ship all generations to the host.                                    */
+/* The capture FaceList as a scene of its own (one face set; materials are ignored).
+ * face_ids[i] = the Python-side Face.idx of face i, written into end_face_idx of captured rays
+ * (the reference never assigns idx to capture faces, so it is whatever the caller left there);
+ * NULL = position in the table.                                                                */
+int rpx_capture_scene_set(rpx_ctx* ctx, const rpx_scene* capture_scene, const uint32_t* face_ids);
+/* Borrowed handle on generation g of a finished trace (NULL if dropped / out of range).        */
+const rpx_rays* rpx_result_rays(const rpx_result* res, int g);
+/* Filter n_gens device-resident collections.  wl_offsets[j] is added to wavelength_idx of the
+ * rays taken from collection j (the running `wl_offset` of the reference loop) and the sum is
+ * then mapped through wl_map[n_wl_map] (the `inverse` of np.unique over the concatenated
+ * wavelength lists, :2011-2014); wl_map == NULL leaves the offset index.  counts[j] (may be NULL)
+ * receives the number of rays captured from collection j.  *out owns a new device collection. */
+int rpx_capture(rpx_ctx* ctx, const rpx_rays* const* gens, int n_gens, const uint32_t* wl_offsets,
+                const uint32_t* wl_map, uint32_t n_wl_map, rpx_rays** out, uint64_t* counts);
+
 /* ---------------------------------------------------------- unit entry points
  * Batch evaluation of ONE device function over host arrays -- the GPU counterpart of the
  * reference's Python-callable test wrappers ("mostly for testing",

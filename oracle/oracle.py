@@ -41,6 +41,10 @@ def lib():
         L.rpxo_trace_segment_ex.argtypes = [vp, vp, u64, d, vp, vp, i]
         L.rpxo_trace_gausslet_ex.restype = u64
         L.rpxo_trace_gausslet_ex.argtypes = [vp, vp, u64, d, vp, vp, i]
+        L.rpxo_capture_rays.restype = u64
+        L.rpxo_capture_rays.argtypes = [vp, vp, vp, u64, u32, vp]
+        L.rpxo_capture_gausslets.restype = u64
+        L.rpxo_capture_gausslets.argtypes = [vp, vp, vp, u64, u32, vp]
         L.rpxo_face_intersect.restype = d
         L.rpxo_face_intersect.argtypes = [vp, i, vp, vp, i]
         L.rpxo_face_normal.argtypes = [vp, i, vp, vp]
@@ -172,6 +176,45 @@ def reference_trace_ray_sequence(core, input_rays, face_sequence, recursion_limi
         traced_rays.append(rays)
         count += 1
     return traced_rays, all_faces
+
+
+def select_intersections(capture_scene, collections, wavelength_lists, face_ids=None):
+    """select_ray_intersections / select_gausslet_intersections (ctracer.pyx:1981-2058) on numpy
+    arrays: ``capture_scene`` is the flattened capture FaceList, ``collections`` the ray arrays
+    (one per generation), ``wavelength_lists`` their wavelength tables.  Returns
+    (captured array, reduced wavelengths, rays captured per collection)."""
+    L = lib()
+    osc = capture_scene if isinstance(capture_scene, OracleScene) else OracleScene(capture_scene)
+    ids = None if face_ids is None else np.ascontiguousarray(face_ids, dtype=np.uint32)
+    parts, counts = [], []
+    wl_offset = 0
+    for rays, wls in zip(collections, wavelength_lists):
+        rays = np.ascontiguousarray(rays)
+        out = np.zeros(max(rays.shape[0], 1), dtype=rays.dtype)
+        fn = L.rpxo_capture_gausslets if rays.dtype == A.gausslet_dtype else L.rpxo_capture_rays
+        n = fn(osc.byref_ptr(), None if ids is None else ids.ctypes.data, rays.ctypes.data, rays.shape[0],
+               wl_offset, out.ctypes.data)
+        parts.append(out[:n])
+        counts.append(int(n))
+        wl_offset += len(wls)
+    captured = np.concatenate(parts) if parts else np.zeros(0, dtype=A.ray_dtype)
+    # np.unique re-mapping of the offset wavelength indices, ctracer.pyx:2011-2016
+    reduced, inverse = np.unique(np.concatenate([np.asarray(w, dtype=np.double) for w in wavelength_lists]),
+                                 return_inverse=True)
+    wl = captured['base_ray']['wavelength_idx'] if captured.dtype == A.gausslet_dtype else captured['wavelength_idx']
+    wl[:] = inverse[wl].astype(np.uint32)
+    return captured, reduced, counts
+
+
+def reference_select_intersections(core, face_list, collections):
+    """The REAL select_ray_intersections / select_gausslet_intersections of the reference."""
+    ct = core.ctracer
+    face_list.sync_transforms()
+    is_g = isinstance(collections[0], ct.GaussletCollection)
+    fn = ct.select_gausslet_intersections if is_g else ct.select_ray_intersections
+    rc = fn(face_list, list(collections))
+    arr = rc.copy_as_array()
+    return arr.view(A.gausslet_dtype if is_g else A.ray_dtype), np.asarray(rc.wavelengths), rc
 
 
 # ---- unit entry points (for pinning against the reference's own KATs) -------

@@ -1856,6 +1856,47 @@ uint64_t rpxo_trace_gausslet_ex(const rpx_scene* S, rpx_gausslet* gs, uint64_t n
     return n_out;
 }
 
+/* --------------------------------------------------- capture planes, ctracer.pyx:1981-2058
+ * Inner loop of select_ray_intersections (:1995-2009) / select_gausslet_intersections
+ * (:2034-2048) over ONE collection: S holds only the capture FaceList.  A COPY of each ray is
+ * intersected between its origin and origin + direction * length (FaceList.intersect_c mutates
+ * the copy: length = distance, end_face_idx = face.idx); hits are appended with
+ * wavelength_idx += wl_offset.  face_ids[i] stands for the Python attribute Face.idx of capture
+ * face i (NULL = position).  The np.unique re-mapping of wavelength_idx (:2011-2016) is table
+ * work done by the caller.  Returns the number of records appended to `out`.                  */
+uint64_t rpxo_capture_rays(const rpx_scene* S, const uint32_t* face_ids, const rpx_ray* rays, uint64_t n,
+                           uint32_t wl_offset, rpx_ray* out) {
+    uint64_t n_out = 0;
+    for (uint64_t i = 0; i < n; i++) {
+        rpx_ray ray = rays[i];
+        vec3 point = addvv(ld3(ray.origin), multvs(ld3(ray.direction), ray.length));
+        int idx = nearest_hit(S, &ray, point);
+        if (idx >= 0) {
+            ray.end_face_idx = face_ids ? face_ids[idx] : (uint32_t)idx;
+            ray.wavelength_idx += wl_offset;
+            out[n_out++] = ray;
+        }
+    }
+    return n_out;
+}
+
+uint64_t rpxo_capture_gausslets(const rpx_scene* S, const uint32_t* face_ids, const rpx_gausslet* gs, uint64_t n,
+                                uint32_t wl_offset, rpx_gausslet* out) {
+    uint64_t n_out = 0;
+    for (uint64_t i = 0; i < n; i++) {
+        rpx_gausslet g = gs[i];
+        rpx_ray* ray = &g.base_ray;
+        vec3 point = addvv(ld3(ray->origin), multvs(ld3(ray->direction), ray->length));
+        int idx = nearest_hit(S, ray, point);
+        if (idx >= 0) {
+            ray->end_face_idx = face_ids ? face_ids[idx] : (uint32_t)idx;
+            ray->wavelength_idx += wl_offset;
+            out[n_out++] = g;
+        }
+    }
+    return n_out;
+}
+
 /* -------------------------------------------- unit entry points for KAT pins */
 double rpxo_face_intersect(const rpx_scene* S, int face, const double* p1, const double* p2,
                            int is_base_ray) {

@@ -21,7 +21,7 @@ EXPORTS = (
     "rpx_result_counts", "rpx_result_generation", "rpx_result_face_counts",
     "rpx_result_device_ms", "rpx_result_launches", "rpx_result_kernel_ms", "rpx_result_free",
     "rpx_stream", "rpx_unit_face_intersect", "rpx_unit_face_normal", "rpx_unit_material_eval",
-    "rpx_unit_distortion",
+    "rpx_unit_distortion", "rpx_capture_scene_set", "rpx_result_rays", "rpx_capture",
 )
 
 
@@ -102,6 +102,12 @@ def load():
     L.rpx_unit_material_eval.restype = i32
     L.rpx_unit_distortion.argtypes = [vp, i32, vp, vp, u64, vp, vp]
     L.rpx_unit_distortion.restype = i32
+    L.rpx_capture_scene_set.argtypes = [vp, vp, vp]
+    L.rpx_capture_scene_set.restype = i32
+    L.rpx_result_rays.argtypes = [vp, i32]
+    L.rpx_result_rays.restype = vp
+    L.rpx_capture.argtypes = [vp, vp, i32, vp, vp, u32, pvp, vp]
+    L.rpx_capture.restype = i32
     if L.rpx_abi_version() != A.RPX_ABI_VERSION:
         raise RuntimeError("librpx.so ABI %d != binding ABI %d" % (L.rpx_abi_version(), A.RPX_ABI_VERSION))
     _LIB = L

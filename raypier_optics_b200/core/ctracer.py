@@ -427,3 +427,42 @@ class FaceList(object):
 
     def __getitem__(self, intidx):
         return self.faces[intidx]
+
+
+# ---- capture planes -------------------------------------------------------------------------
+def _select_intersections(face_set, ray_col_list, cls, device=0):
+    from ..engine import get_engine
+    from ..scene import Scene
+    ray_col_list = list(ray_col_list)
+    eng = get_engine(device)
+    wl_lists = [np.asarray(rc.wavelengths, dtype=np.double) for rc in ray_col_list]
+    # the geometry of the capture faces does not depend on the wavelengths; one entry keeps
+    # the flattened tables well-formed
+    cap = Scene([face_set], np.asarray([1.0]))
+    eng.set_capture_scene(cap, [int(getattr(f, "idx", 0)) for f in cap.all_faces])
+    devs = []
+    try:
+        for rc in ray_col_list:
+            a = np.ascontiguousarray(rc.copy_as_array())
+            a = a.view(gausslet_dtype if a.dtype.itemsize == gausslet_dtype.itemsize else ray_dtype)
+            devs.append(eng.upload(a))
+        arr, reduced, _ = eng.capture_collections([d._h for d in devs], wl_lists, cls is GaussletCollection)
+    finally:
+        for d in devs:
+            d.free()
+    out = cls.from_array(arr)
+    out.wavelengths = reduced
+    return out
+
+
+def select_ray_intersections(face_set, ray_col_list, device=0):
+    """ctracer.pyx:1981-2017 on the GPU: the rays of every collection that cross the capture
+    ``face_set`` between their origin and their end point, in (collection, ray) order, cut at the
+    capture face, with the wavelength tables merged.  Collections are uploaded; use
+    ``TraceResult.capture`` to filter generations that are still resident on the device."""
+    return _select_intersections(face_set, ray_col_list, RayCollection, device)
+
+
+def select_gausslet_intersections(face_set, ray_col_list, device=0):
+    """ctracer.pyx:2020-2058 on the GPU (see select_ray_intersections)."""
+    return _select_intersections(face_set, ray_col_list, GaussletCollection, device)

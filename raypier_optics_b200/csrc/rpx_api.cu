@@ -61,6 +61,13 @@ struct rpx_ctx {
     int scene_smem;     // bytes of shared memory the staged scene needs (0 = use global)
     int face_class;     // RPX_FC_SIMPLE / RPX_FC_FULL kernel variant for this scene
     int mm_idx;         // material-mask kernel variant: 0 LIGHT, 1 COATED, 2 FULLDIEL, 3 ALL
+    // capture-plane scene (rpx_capture_scene_set): a second, independent face list
+    bool have_capture;
+    DevScene cap_ds;
+    void* cap_block;
+    uint32_t* cap_face_ids;  // device copy of the Python-side Face.idx values, or NULL
+    int cap_smem;
+    int cap_face_class;
     // scratch
     unsigned long long* tile_state;
     size_t tile_state_cap;  // tiles
@@ -130,6 +137,9 @@ extern "C" int rpx_init(int device, rpx_ctx** out_ctx) {
     ctx->device = device;
     ctx->have_scene = false;
     ctx->scene_block = nullptr;
+    ctx->have_capture = false;
+    ctx->cap_block = nullptr;
+    ctx->cap_face_ids = nullptr;
     ctx->tile_state = nullptr;
     ctx->tile_state_cap = 0;
     ctx->ev_used = 0;
@@ -173,6 +183,8 @@ extern "C" void rpx_shutdown(rpx_ctx* ctx) {
     cudaStreamSynchronize(ctx->stream);
     for (cudaEvent_t ev : ctx->ev_pool) cudaEventDestroy(ev);
     if (ctx->scene_block) cudaFree(ctx->scene_block);
+    if (ctx->cap_block) cudaFree(ctx->cap_block);
+    if (ctx->cap_face_ids) cudaFree(ctx->cap_face_ids);
     if (ctx->tile_state) cudaFree(ctx->tile_state);
     if (ctx->d_face_counts) cudaFree(ctx->d_face_counts);
     cudaFree(ctx->tile_counter);
@@ -269,13 +281,10 @@ static int validate_scene(rpx_ctx* ctx, const rpx_scene* s) {
     return RPX_OK;
 }
 
-extern "C" int rpx_scene_set(rpx_ctx* ctx, const rpx_scene* s) {
-    if (!ctx || !s) return fail(ctx, RPX_ERR_INVALID, "NULL argument");
-    CU(ctx, cudaSetDevice(ctx->device));
-    int rc = validate_scene(ctx, s);
-    if (rc != RPX_OK) return rc;
-    // one block: faces | sets | materials | shape ops | implicit ops | distortions | zcoefs |
-    //            ztape | wavelengths | ntab | pool
+// Copy the flat scene tables into ONE device block and point a DevScene at them.
+// Layout: faces | sets | materials | shape ops | implicit ops | distortions | zcoefs | ztape |
+//         wavelengths | ntab | pool
+static int upload_scene(rpx_ctx* ctx, const rpx_scene* s, DevScene* out, void** block) {
     struct Part { const void* src; size_t bytes; size_t off; };
     Part parts[11] = {
         {s->faces, (size_t)s->n_faces * sizeof(rpx_face), 0},
@@ -302,14 +311,14 @@ extern "C" int rpx_scene_set(rpx_ctx* ctx, const rpx_scene* s) {
             memcpy(host.data() + p.off, p.src, p.bytes);
         }
     CU(ctx, cudaStreamSynchronize(ctx->stream));
-    if (ctx->scene_block) {
-        CU(ctx, cudaFree(ctx->scene_block));
-        ctx->scene_block = nullptr;
+    if (*block) {
+        CU(ctx, cudaFree(*block));
+        *block = nullptr;
     }
-    CU(ctx, cudaMalloc(&ctx->scene_block, total));
-    CU(ctx, cudaMemcpy(ctx->scene_block, host.data(), total, cudaMemcpyHostToDevice));
-    unsigned char* b = (unsigned char*)ctx->scene_block;
-    DevScene& d = ctx->ds;
+    CU(ctx, cudaMalloc(block, total));
+    CU(ctx, cudaMemcpy(*block, host.data(), total, cudaMemcpyHostToDevice));
+    unsigned char* b = (unsigned char*)*block;
+    DevScene& d = *out;
     d.faces = (const rpx_face*)(b + parts[0].off);
     d.sets = (const rpx_face_set*)(b + parts[1].off);
     d.mats = (const rpx_material*)(b + parts[2].off);
@@ -327,6 +336,32 @@ extern "C" int rpx_scene_set(rpx_ctx* ctx, const rpx_scene* s) {
     d.n_mats = s->n_materials;
     d.n_wl = s->n_wavelengths;
     d.n_dists = s->n_distortions;
+    return RPX_OK;
+}
+
+static int scene_face_class(const rpx_scene* s) {
+    for (int i = 0; i < s->n_faces; i++) {
+        int t = s->faces[i].type;
+        bool simple = t == RPX_FACE_CIRCULAR || t == RPX_FACE_SHAPED_PLANAR || t == RPX_FACE_ELLIPTICAL_PLANE ||
+                      t == RPX_FACE_RECTANGULAR || t == RPX_FACE_SPHERICAL || t == RPX_FACE_SHAPED_SPHERICAL ||
+                      t == RPX_FACE_EXTRUDED_PLANAR || t == RPX_FACE_POLYGON || t == RPX_FACE_ORIENTED_POLYGON;
+        if (!simple) return RPX_FC_FULL;
+    }
+    return RPX_FC_SIMPLE;
+}
+
+static int scene_smem_bytes(const rpx_scene* s) {
+    size_t smem = (size_t)s->n_faces * sizeof(rpx_face) + (size_t)s->n_face_sets * sizeof(rpx_face_set);
+    return smem <= 40 * 1024 ? (int)smem : 0;
+}
+
+extern "C" int rpx_scene_set(rpx_ctx* ctx, const rpx_scene* s) {
+    if (!ctx || !s) return fail(ctx, RPX_ERR_INVALID, "NULL argument");
+    CU(ctx, cudaSetDevice(ctx->device));
+    int rc = validate_scene(ctx, s);
+    if (rc != RPX_OK) return rc;
+    rc = upload_scene(ctx, s, &ctx->ds, &ctx->scene_block);
+    if (rc != RPX_OK) return rc;
     ctx->n_traced = s->n_traced_faces;
     ctx->max_kids = 0;
     for (int i = 0; i < s->n_traced_faces; i++) {
@@ -337,14 +372,7 @@ extern "C" int rpx_scene_set(rpx_ctx* ctx, const rpx_scene* s) {
         if (kids > ctx->max_kids) ctx->max_kids = kids;
     }
     // kernel variant: the smallest compiled face class / material mask covering the scene
-    ctx->face_class = RPX_FC_SIMPLE;
-    for (int i = 0; i < s->n_faces; i++) {
-        int t = s->faces[i].type;
-        bool simple = t == RPX_FACE_CIRCULAR || t == RPX_FACE_SHAPED_PLANAR || t == RPX_FACE_ELLIPTICAL_PLANE ||
-                      t == RPX_FACE_RECTANGULAR || t == RPX_FACE_SPHERICAL || t == RPX_FACE_SHAPED_SPHERICAL ||
-                      t == RPX_FACE_EXTRUDED_PLANAR || t == RPX_FACE_POLYGON || t == RPX_FACE_ORIENTED_POLYGON;
-        if (!simple) ctx->face_class = RPX_FC_FULL;
-    }
+    ctx->face_class = scene_face_class(s);
     uint32_t used = 0;
     for (int i = 0; i < s->n_traced_faces; i++) used |= RPX_MBIT(s->materials[s->faces[i].material].type);
     const uint32_t masks[RPX_N_MM] = {RPX_MM_LIGHT, RPX_MM_COATED, RPX_MM_FULLDIEL, RPX_MM_ALL};
@@ -354,14 +382,35 @@ extern "C" int rpx_scene_set(rpx_ctx* ctx, const rpx_scene* s) {
             ctx->mm_idx = m;
             break;
         }
-    size_t smem = (size_t)s->n_faces * sizeof(rpx_face) + (size_t)s->n_face_sets * sizeof(rpx_face_set);
-    ctx->scene_smem = smem <= 40 * 1024 ? (int)smem : 0;
+    ctx->scene_smem = scene_smem_bytes(s);
     if (ctx->d_face_counts) {
         CU(ctx, cudaFree(ctx->d_face_counts));
         ctx->d_face_counts = nullptr;
     }
     CU(ctx, cudaMalloc(&ctx->d_face_counts, sizeof(uint32_t) * (size_t)(s->n_traced_faces > 0 ? s->n_traced_faces : 1)));
     ctx->have_scene = true;
+    return RPX_OK;
+}
+
+extern "C" int rpx_capture_scene_set(rpx_ctx* ctx, const rpx_scene* s, const uint32_t* face_ids) {
+    if (!ctx || !s) return fail(ctx, RPX_ERR_INVALID, "NULL argument");
+    CU(ctx, cudaSetDevice(ctx->device));
+    int rc = validate_scene(ctx, s);
+    if (rc != RPX_OK) return rc;
+    ctx->have_capture = false;
+    rc = upload_scene(ctx, s, &ctx->cap_ds, &ctx->cap_block);
+    if (rc != RPX_OK) return rc;
+    if (ctx->cap_face_ids) {
+        CU(ctx, cudaFree(ctx->cap_face_ids));
+        ctx->cap_face_ids = nullptr;
+    }
+    if (face_ids && s->n_faces > 0) {
+        CU(ctx, cudaMalloc(&ctx->cap_face_ids, sizeof(uint32_t) * (size_t)s->n_faces));
+        CU(ctx, cudaMemcpy(ctx->cap_face_ids, face_ids, sizeof(uint32_t) * (size_t)s->n_faces, cudaMemcpyHostToDevice));
+    }
+    ctx->cap_face_class = scene_face_class(s);
+    ctx->cap_smem = scene_smem_bytes(s);
+    ctx->have_capture = true;
     return RPX_OK;
 }
 
@@ -863,6 +912,96 @@ extern "C" int rpx_trace(rpx_ctx* ctx, const void* rays_aos, uint64_t n, int is_
     int rc = rpx_rays_upload(ctx, rays_aos, n, is_gausslet, &r);
     if (rc != RPX_OK) return rc;
     return rpx_trace_device(ctx, r, max_length, recursion_limit, flags, out_result);  // owns r either way
+}
+
+// ------------------------------------------------------------------ capture planes
+extern "C" const rpx_rays* rpx_result_rays(const rpx_result* res, int g) {
+    if (!res || g < 0 || g >= (int)res->gens.size()) return nullptr;
+    return res->gens[(size_t)g];
+}
+
+extern "C" int rpx_capture(rpx_ctx* ctx, const rpx_rays* const* gens, int n_gens, const uint32_t* wl_offsets,
+                           const uint32_t* wl_map, uint32_t n_wl_map, rpx_rays** out, uint64_t* counts) {
+    if (!ctx || !gens || !out || n_gens <= 0) return fail(ctx, RPX_ERR_INVALID, "NULL / empty argument");
+    *out = nullptr;
+    if (!ctx->have_capture) return fail(ctx, RPX_ERR_STATE, "rpx_capture_scene_set has not been called");
+    CU(ctx, cudaSetDevice(ctx->device));
+    unsigned long long total = 0, tiles_total = 0;
+    for (int j = 0; j < n_gens; j++) {
+        if (!gens[j]) return fail(ctx, RPX_ERR_INVALID, "collection %d is NULL (dropped generation?)", j);
+        if (gens[j]->is_gausslet != gens[0]->is_gausslet)
+            return fail(ctx, RPX_ERR_INVALID, "collections mix rays and gausslets");
+        total += gens[j]->soa.n;
+        tiles_total += (gens[j]->soa.n + RPX_TILE - 1) / RPX_TILE;
+    }
+    const int is_g = gens[0]->is_gausslet;
+    rpx_rays* dst = nullptr;
+    int rc = rays_alloc(ctx, total, is_g, &dst);
+    if (rc != RPX_OK) return rc;
+    // scratch: [totals (n_gens + 1) u64][tile state u64 x tiles][ticket counters u32 x n_gens][wl_map u32]
+    const size_t off_state = sizeof(unsigned long long) * (size_t)(n_gens + 1);
+    const size_t off_cnt = off_state + sizeof(unsigned long long) * (size_t)tiles_total;
+    const size_t off_map = align_up(off_cnt + sizeof(uint32_t) * (size_t)n_gens, 8);
+    const size_t bytes = off_map + sizeof(uint32_t) * (size_t)(wl_map ? n_wl_map : 0) + 8;
+    unsigned char* scratch = nullptr;
+    cudaError_t e = cudaMallocAsync((void**)&scratch, bytes, ctx->stream);
+    if (e != cudaSuccess) {
+        rpx_rays_free(ctx, dst);
+        return fail(ctx, RPX_ERR_NOMEM, "capture scratch (%zu bytes): %s", bytes, cudaGetErrorString(e));
+    }
+    auto bail = [&](cudaError_t err, const char* what) {
+        cudaFreeAsync(scratch, ctx->stream);
+        rpx_rays_free(ctx, dst);
+        return fail(ctx, RPX_ERR_CUDA, "%s failed: %s", what, cudaGetErrorString(err));
+    };
+    if ((e = cudaMemsetAsync(scratch, 0, off_map, ctx->stream)) != cudaSuccess) return bail(e, "cudaMemsetAsync");
+    unsigned long long* d_totals = (unsigned long long*)scratch;
+    unsigned long long* d_state = (unsigned long long*)(scratch + off_state);
+    uint32_t* d_cnt = (uint32_t*)(scratch + off_cnt);
+    uint32_t* d_map = nullptr;
+    if (wl_map && n_wl_map) {
+        d_map = (uint32_t*)(scratch + off_map);
+        if ((e = cudaMemcpyAsync(d_map, wl_map, sizeof(uint32_t) * n_wl_map, cudaMemcpyHostToDevice, ctx->stream)) !=
+            cudaSuccess)
+            return bail(e, "cudaMemcpyAsync(wl_map)");
+    }
+    unsigned long long tile_off = 0;
+    for (int j = 0; j < n_gens; j++) {
+        const unsigned long long n = gens[j]->soa.n;
+        if (n == 0) {  // nothing to filter: carry the running total forward
+            if ((e = cudaMemcpyAsync(d_totals + j + 1, d_totals + j, sizeof(unsigned long long),
+                                     cudaMemcpyDeviceToDevice, ctx->stream)) != cudaSuccess)
+                return bail(e, "cudaMemcpyAsync(total)");
+            continue;
+        }
+        const unsigned n_tiles = (unsigned)((n + RPX_TILE - 1) / RPX_TILE);
+        CaptureArgs a;
+        a.S = ctx->cap_ds;
+        a.in = gens[j]->soa;
+        a.out = dst->soa;
+        a.tile_state = d_state + tile_off;
+        a.tile_counter = d_cnt + j;
+        a.d_base = d_totals + j;
+        a.d_next = d_totals + j + 1;
+        a.wl_offset = wl_offsets ? wl_offsets[j] : 0u;
+        a.wl_map = d_map;
+        a.face_ids = ctx->cap_face_ids;
+        a.smem_bytes = ctx->cap_smem;
+        if ((e = launch_capture(is_g, ctx->cap_face_class, ctx->stream, n_tiles, a)) != cudaSuccess)
+            return bail(e, "k_capture launch");
+        tile_off += n_tiles;
+    }
+    std::vector<unsigned long long> h_totals((size_t)n_gens + 1);
+    if ((e = cudaMemcpyAsync(h_totals.data(), d_totals, sizeof(unsigned long long) * h_totals.size(),
+                             cudaMemcpyDeviceToHost, ctx->stream)) != cudaSuccess ||
+        (e = cudaStreamSynchronize(ctx->stream)) != cudaSuccess)
+        return bail(e, "capture");
+    cudaFreeAsync(scratch, ctx->stream);
+    dst->soa.n = h_totals[(size_t)n_gens];
+    if (counts)
+        for (int j = 0; j < n_gens; j++) counts[j] = h_totals[(size_t)j + 1] - h_totals[(size_t)j];
+    *out = dst;
+    return RPX_OK;
 }
 
 extern "C" int rpx_result_n_generations(const rpx_result* res) { return res ? (int)res->counts.size() : 0; }

@@ -272,6 +272,70 @@ RPX_DEV unsigned long long tile_lookback(unsigned long long* state, uint32_t til
     return excl;
 }
 
+// ------------------------------------------------------------------ k_capture
+// select_ray_intersections / select_gausslet_intersections (ctracer.pyx:1981-2058) for ONE
+// collection: every ray is re-intersected between its origin and origin + direction * length
+// with the capture FaceList (S holds only that face list); rays that hit are appended to `out`
+// in input order (block scan + decoupled look-back, as k_shade) after the *d_base records already
+// captured from earlier collections.  The copy carries length = hit distance, end_face_idx =
+// the capture face's idx and the re-based wavelength index (:2004-2006, 2011-2014).
+template <bool GAUSS, int FC>
+__global__ void __launch_bounds__(RPX_TILE, 4)
+k_capture(DevScene S, Soa in, Soa out, unsigned long long* tile_state, uint32_t* tile_counter,
+          const unsigned long long* d_base, unsigned long long* d_next, uint32_t wl_offset, const uint32_t* wl_map,
+          const uint32_t* face_ids, int smem_bytes) {
+    extern __shared__ __align__(16) unsigned char smem[];
+    __shared__ uint32_t s_tile;
+    __shared__ uint32_t s_warp[RPX_TILE / 32];
+    __shared__ unsigned long long s_prefix;
+    stage_scene(S, smem, smem_bytes);
+    if (threadIdx.x == 0) s_tile = atomicAdd(tile_counter, 1u);  // ticket order = start order: look-back cannot deadlock
+    __syncthreads();
+    const uint32_t tile = s_tile;
+    const uint32_t n_tiles = (uint32_t)((in.n + RPX_TILE - 1) / RPX_TILE);
+    const unsigned long long i = (unsigned long long)tile * RPX_TILE + threadIdx.x;
+    const unsigned long long cap = in.cap, ocap = out.cap;
+    double len = 0.0;
+    uint32_t face = RPX_NO_FACE;
+    if (i < in.n) {
+        vec3 o = v3(in.f[F_OX * cap + i], in.f[F_OY * cap + i], in.f[F_OZ * cap + i]);
+        vec3 d = v3(in.f[F_DX * cap + i], in.f[F_DY * cap + i], in.f[F_DZ * cap + i]);
+        nearest_hit<FC>(S, o, d, in.f[F_LEN * cap + i], -1, &len, &face);
+    }
+    const bool hit = (face != RPX_NO_FACE);
+    uint32_t total;
+    const uint32_t local = block_exclusive_scan(hit ? 1u : 0u, &total, s_warp);
+    if (threadIdx.x == 0) tile_publish(tile_state, tile, total);
+    if (threadIdx.x < 32) {
+        unsigned long long excl = tile_lookback(tile_state, tile, total);
+        if (threadIdx.x == 0) {
+            s_prefix = excl;
+            if (tile == n_tiles - 1) *d_next = *d_base + excl + total;
+        }
+    }
+    __syncthreads();
+    if (!hit) return;
+    const unsigned long long pos = *d_base + s_prefix + local;
+#pragma unroll
+    for (int fld = 0; fld < NF; fld++)
+        out.f[(unsigned long long)fld * ocap + pos] = (fld == F_LEN) ? len : in.f[(unsigned long long)fld * cap + i];
+#pragma unroll
+    for (int fld = 0; fld < NU; fld++) {
+        uint32_t v = in.u[(unsigned long long)fld * cap + i];
+        if (fld == U_ENDFACE) v = face_ids ? face_ids[face] : face;
+        if (fld == U_WL) {
+            v += wl_offset;
+            if (wl_map) v = wl_map[v];
+        }
+        out.u[(unsigned long long)fld * ocap + pos] = v;
+    }
+    if (GAUSS) {
+#pragma unroll 4
+        for (int fld = 0; fld < NP; fld++)
+            out.p[(unsigned long long)fld * ocap + pos] = in.p[(unsigned long long)fld * cap + i];
+    }
+}
+
 // ------------------------------------------------------------------ child staging
 // The children of one tile (<= 2 * RPX_TILE) are assembled in shared memory, field-major
 // like the SoA generation buffer: cs[field * RPX_SLOTS + slot], cu[field * RPX_SLOTS + slot].

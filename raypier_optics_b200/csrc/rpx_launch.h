@@ -52,6 +52,21 @@ inline ShadeLauncher shade_launcher(int gauss, int fc, int mm_idx) {
 cudaError_t launch_intersect(int fc, cudaStream_t st, unsigned n_tiles, int smem, const DevScene& S, const Soa& rays,
                              double max_length, int only_face);
 
+// capture planes (rpx_capture): one launch per filtered collection
+struct CaptureArgs {
+    DevScene S;
+    Soa in, out;
+    unsigned long long* tile_state;
+    uint32_t* tile_counter;
+    const unsigned long long* d_base;
+    unsigned long long* d_next;
+    uint32_t wl_offset;
+    const uint32_t* wl_map;
+    const uint32_t* face_ids;
+    int smem_bytes;
+};
+cudaError_t launch_capture(int gauss, int fc, cudaStream_t st, unsigned n_tiles, const CaptureArgs& a);
+
 cudaError_t launch_unit_face_intersect(cudaStream_t st, const DevScene& S, int face, const double* p1,
                                        const double* p2, unsigned long long n, int is_base_ray, double* out);
 cudaError_t launch_unit_face_normal(cudaStream_t st, const DevScene& S, int face, const double* pts,

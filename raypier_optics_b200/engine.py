@@ -53,6 +53,19 @@ class TraceResult(object):
     def generations(self):
         return [self.generation(g) for g in range(self.n_generations)]
 
+    def device_generations(self):
+        """Borrowed ``rpx_rays`` handles of the generations still resident on the device
+        (input of ``Engine.capture``); valid until this result is freed."""
+        return [self._e._L.rpx_result_rays(self._h, g) for g in range(self.n_generations)]
+
+    def capture(self, wavelengths):
+        """Filter every generation through the engine's capture plane on the device
+        (``rpx_capture``) and return ``(captured array, reduced wavelengths, per-generation
+        counts)`` -- select_ray_intersections over ``traced_rays`` without shipping the
+        generations to the host."""
+        return self._e.capture_collections(self.device_generations(),
+                                           [wavelengths] * self.n_generations, self.is_gausslet)
+
     def free(self):
         if self._h is not None:
             self._e._L.rpx_result_free(self._e._ctx, self._h)
@@ -118,6 +131,37 @@ class Engine(object):
         self._check(self._L.rpx_scene_set(self._ctx, scene.byref()))
         self.scene = scene  # keeps the host tables alive
         self.n_traced_faces = scene.n_traced_faces
+
+    def set_capture_scene(self, scene, face_ids=None):
+        """The capture FaceList (flattened like a traced scene) of select_ray_intersections."""
+        ids = None
+        if face_ids is not None:
+            ids = np.ascontiguousarray(face_ids, dtype=np.uint32)
+            assert ids.shape[0] == scene.c_scene.n_faces
+        self._check(self._L.rpx_capture_scene_set(self._ctx, scene.byref(),
+                                                  None if ids is None else ids.ctypes.data))
+        self.capture_scene = scene
+
+    def capture_collections(self, handles, wavelength_lists, is_gausslet):
+        """``rpx_capture`` over device-resident collections + the reference's wavelength merge
+        (np.unique over the concatenated tables, ctracer.pyx:2011-2016)."""
+        n = len(handles)
+        arr = (C.c_void_p * n)(*handles)
+        sizes = [len(w) for w in wavelength_lists]
+        offsets = np.ascontiguousarray(np.concatenate([[0], np.cumsum(sizes)[:-1]]), dtype=np.uint32)
+        reduced, inverse = np.unique(np.concatenate([np.asarray(w, dtype=np.double) for w in wavelength_lists]),
+                                     return_inverse=True)
+        wl_map = np.ascontiguousarray(inverse, dtype=np.uint32)
+        counts = np.zeros(n, dtype=np.uint64)
+        h = C.c_void_p()
+        self._check(self._L.rpx_capture(self._ctx, arr, n, offsets.ctypes.data, wl_map.ctypes.data,
+                                        wl_map.shape[0], C.byref(h), counts.ctypes.data))
+        dev = DeviceRays(self, h, is_gausslet)
+        try:
+            out = self.download(dev)
+        finally:
+            dev.free()
+        return out, reduced, [int(c) for c in counts]
 
     # -- rays -----------------------------------------------------------------------
     @staticmethod
