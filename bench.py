@@ -39,12 +39,14 @@ import numpy as np
 METRIC = "ray-segments/sec"
 WORKLOADS = {
     "config1": dict(n=10000, kw={}),
-    "config2": dict(n=1000000, kw={}),
+    "config2": dict(n=1000000, kw={}, capture=dict(centre=(-4.86, -31.3, 0.07), direction=(0.2, 1.0, 0.1), size=(30.0, 30.0))),
     "config3": dict(n=10000000, kw={}),
     "config4_prisms": dict(n=1000000, kw={}, recursion_limit=12),
     "config4_grating": dict(n=1000000, kw={}),
-    "config5": dict(n=1000000, kw=dict(gausslets=True)),
-    "config5_rays": dict(n=1000000, kw=dict(gausslets=False)),
+    "config5": dict(n=1000000, kw=dict(gausslets=True),
+                    capture=dict(centre=(0.0, -12.0, 0.0), direction=(0.0, 1.0, 0.0), size=(12.0, 12.0))),
+    "config5_rays": dict(n=1000000, kw=dict(gausslets=False),
+                         capture=dict(centre=(0.0, -12.0, 0.0), direction=(0.0, 1.0, 0.0), size=(12.0, 12.0))),
 }
 # algorithmic bytes per ray-segment: read the parent record, write
 # back length + end_face_idx, write c children
@@ -336,6 +338,40 @@ def run_ours(args):
         dist.all_reduce(se, op=dist.ReduceOp.SUM)
     e2e_value = float(se[0]) / float(te[0])
 
+    # ---------------- optional capture-plane arm (--capture): the same e2e call, but
+    # the generations stay on the device, are filtered there (rpx_capture) and only the captured
+    # rays cross PCIe -- what a RayCapturePlane downstream of the trace actually needs
+    capture = None
+    if args.capture and "capture" in WORKLOADS[name]:
+        from raypier_optics_b200 import configs
+        cp = WORKLOADS[name]["capture"]
+        face = core.cfaces.RectangularFace(length=cp["size"][0], width=cp["size"][1], offset=0.0, z_plane=0.0)
+        fl = core.ctracer.FaceList(owner=configs.Pose(centre=cp["centre"], direction=cp["direction"]))
+        fl.faces = [face]
+        fl.sync_transforms()
+        eng.set_capture_scene(scene.Scene([fl], np.asarray([1.0])))
+
+        def step_capture():
+            res = eng.trace(pinned_in, ml, rl)
+            got, _, counts = res.capture(cfg["wavelengths"], out=pinned_out)
+            nseg = res.segments
+            res.free()
+            return nseg, len(got), counts
+
+        for _ in range(2):
+            step_capture()
+        barrier()
+        t0 = time.perf_counter()
+        cap_segs = 0
+        for _ in range(e2e_steps):
+            a, ncap, cap_counts = step_capture()
+            cap_segs += a
+        barrier()
+        cap_s = time.perf_counter() - t0
+        capture = {"value": cap_segs / cap_s, "unit": "ray-segments/s (this rank)", "captured_rays": int(ncap),
+                   "captured_per_generation": cap_counts, "h2d_bytes_per_step": int(rays.shape[0] * rec),
+                   "d2h_bytes_per_step": int(ncap * rec), "plane": cp}
+
     if rank != 0:
         if distributed:
             dist.destroy_process_group()
@@ -394,6 +430,8 @@ def run_ours(args):
         "roofline": roofline,
         "cpu_baseline": cpu,
     }
+    if capture is not None:
+        line["e2e_capture"] = capture
     print(json.dumps(line))
     if distributed:
         dist.destroy_process_group()
@@ -411,6 +449,8 @@ def main():
     ap.add_argument("--e2e-steps", type=int, default=5)
     ap.add_argument("--ref-rays-per-core", type=int, default=200000)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--capture", action="store_true",
+                    help="also time trace + device-side capture plane (adds `e2e_capture`)")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference_arm(args)

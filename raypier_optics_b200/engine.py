@@ -58,13 +58,13 @@ class TraceResult(object):
         (input of ``Engine.capture``); valid until this result is freed."""
         return [self._e._L.rpx_result_rays(self._h, g) for g in range(self.n_generations)]
 
-    def capture(self, wavelengths):
+    def capture(self, wavelengths, out=None):
         """Filter every generation through the engine's capture plane on the device
         (``rpx_capture``) and return ``(captured array, reduced wavelengths, per-generation
         counts)`` -- select_ray_intersections over ``traced_rays`` without shipping the
         generations to the host."""
         return self._e.capture_collections(self.device_generations(),
-                                           [wavelengths] * self.n_generations, self.is_gausslet)
+                                           [wavelengths] * self.n_generations, self.is_gausslet, out=out)
 
     def free(self):
         if self._h is not None:
@@ -142,7 +142,7 @@ class Engine(object):
                                                   None if ids is None else ids.ctypes.data))
         self.capture_scene = scene
 
-    def capture_collections(self, handles, wavelength_lists, is_gausslet):
+    def capture_collections(self, handles, wavelength_lists, is_gausslet, out=None):
         """``rpx_capture`` over device-resident collections + the reference's wavelength merge
         (np.unique over the concatenated tables, ctracer.pyx:2011-2016)."""
         n = len(handles)
@@ -158,7 +158,7 @@ class Engine(object):
                                         wl_map.shape[0], C.byref(h), counts.ctypes.data))
         dev = DeviceRays(self, h, is_gausslet)
         try:
-            out = self.download(dev)
+            out = self.download(dev, out=out)  # ``out``: a (pinned) staging array to fill, or None
         finally:
             dev.free()
         return out, reduced, [int(c) for c in counts]
@@ -197,11 +197,14 @@ class Engine(object):
         self._pinned.append(ptr)
         return arr
 
-    def download(self, dev_rays):
+    def download(self, dev_rays, out=None):
         n = len(dev_rays)
-        out = np.empty(n, dtype=A.gausslet_dtype if dev_rays.is_gausslet else A.ray_dtype)
-        self._check(self._L.rpx_rays_download(self._ctx, dev_rays._h, out.ctypes.data, n))
-        return out
+        dtype = A.gausslet_dtype if dev_rays.is_gausslet else A.ray_dtype
+        if out is None:
+            out = np.empty(n, dtype=dtype)
+        assert out.dtype == dtype and out.shape[0] >= n and out.flags.c_contiguous
+        self._check(self._L.rpx_rays_download(self._ctx, dev_rays._h, out.ctypes.data, out.shape[0]))
+        return out[:n]
 
     # -- tracing ----------------------------------------------------------------------
     def trace(self, rays, max_length, recursion_limit, flags=A.TRACE_DEFAULT):
