@@ -394,6 +394,35 @@ const rpx_rays* rpx_result_rays(const rpx_result* res, int g);
 int rpx_capture(rpx_ctx* ctx, const rpx_rays* const* gens, int n_gens, const uint32_t* wl_offsets,
                 const uint32_t* wl_map, uint32_t n_wl_map, rpx_rays** out, uint64_t* counts);
 
+/* ---------------------------------------------------------- E-field summation
+ * The field at a set of points as the sum of general astigmatic Gaussian modes, one per ray:
+ * raypier/core/cfields.pyx sum_gaussian_modes (:51-115) + calc_mode_U (:118-153), with the
+ * gausslet front end of raypier/core/fields.py (evaluate_neighbours_gc :114-137 ->
+ * cfields.evaluate_modes :217-228), i.e. eval_Efield_from_gausslets / EFieldSummation
+ * (fields.py:206-277).  O(N_ray x N_pt) complex exponentials in fp64.                         */
+typedef struct rpx_field rpx_field;
+/* Prepare the per-ray mode records on the device (EFieldSummation.__init__, fields.py:212-221).
+ * modes == NULL: `rays` must be gausslets; the modes (A, B, C) are fitted on the device from the
+ * six parabasal rays with the given blending.  modes != NULL: n x 3 complex128 host array, used
+ * as given with the (base) rays -- the exact argument list of sum_gaussian_modes.
+ * wavelengths[n_wavelengths] in microns (the `wavelengths` argument, indexed by wavelength_idx). */
+int rpx_field_prepare(rpx_ctx* ctx, const rpx_rays* rays, const double* modes, const double* wavelengths,
+                      int n_wavelengths, double blending, rpx_field** out);
+uint64_t rpx_field_count(const rpx_field* field);
+/* The (A, B, C) modes, n x 3 complex128 (fields.py ExtractGamma :196-203) */
+int rpx_field_modes(rpx_ctx* ctx, const rpx_field* field, double* modes_out);
+/* sum_gaussian_modes(rays, modes, wavelengths, points, time_ps): points is npt x 3 doubles, out
+ * npt x 3 complex128 (host memory; overwritten).                                               */
+int rpx_field_evaluate(rpx_ctx* ctx, rpx_field* field, const double* points, uint64_t npt, double time_ps,
+                       double* out);
+/* Same with DEVICE pointers; d_out is ACCUMULATED into (zero it first) so partial fields of
+ * several ray shards can share one buffer before an all-reduce.  Returns after the kernel ended. */
+int rpx_field_evaluate_device(rpx_ctx* ctx, rpx_field* field, const double* d_points, uint64_t npt,
+                              double time_ps, double* d_out);
+/* Device time (ms) of the last summation kernel of this field (CUDA events) */
+double rpx_field_last_ms(const rpx_field* field);
+void rpx_field_free(rpx_ctx* ctx, rpx_field* field);
+
 /* ---------------------------------------------------------- unit entry points
  * Batch evaluation of ONE device function over host arrays -- the GPU counterpart of the
  * reference's Python-callable test wrappers ("mostly for testing",

@@ -45,6 +45,9 @@ def lib():
         L.rpxo_capture_rays.argtypes = [vp, vp, vp, u64, u32, vp]
         L.rpxo_capture_gausslets.restype = u64
         L.rpxo_capture_gausslets.argtypes = [vp, vp, vp, u64, u32, vp]
+        L.rpxo_evaluate_neighbours_gc.argtypes = [vp, u64, vp, vp, vp, vp]
+        L.rpxo_evaluate_modes.argtypes = [vp, vp, vp, vp, u64, i, d, vp]
+        L.rpxo_sum_gaussian_modes.argtypes = [vp, u64, vp, vp, vp, u64, d, vp]
         L.rpxo_face_intersect.restype = d
         L.rpxo_face_intersect.argtypes = [vp, i, vp, vp, i]
         L.rpxo_face_normal.argtypes = [vp, i, vp, vp]
@@ -215,6 +218,78 @@ def reference_select_intersections(core, face_list, collections):
     rc = fn(face_list, list(collections))
     arr = rc.copy_as_array()
     return arr.view(A.gausslet_dtype if is_g else A.ray_dtype), np.asarray(rc.wavelengths), rc
+
+
+# ---- E-field summation: raypier/core/cfields.pyx + core/fields.py front end -------
+def evaluate_neighbours_gc(gausslets):
+    """core/fields.py:114-137 -> (x, y, dx, dy), each n x 6."""
+    L = lib()
+    g = np.ascontiguousarray(gausslets)
+    assert g.dtype == A.gausslet_dtype
+    n = g.shape[0]
+    x, y, dx, dy = (np.zeros((n, 6)) for _ in range(4))
+    L.rpxo_evaluate_neighbours_gc(g.ctypes.data, n, x.ctypes.data, y.ctypes.data, dx.ctypes.data, dy.ctypes.data)
+    return x, y, dx, dy
+
+
+def evaluate_modes(x, y, dx, dy, blending=1.0):
+    """cfields.evaluate_modes (cfields.pyx:217-228) -> n x 3 complex."""
+    L = lib()
+    x, y, dx, dy = (np.ascontiguousarray(a, dtype=np.double) for a in (x, y, dx, dy))
+    n, row = x.shape
+    out = np.zeros((n, 3), dtype=np.complex128)
+    L.rpxo_evaluate_modes(x.ctypes.data, y.ctypes.data, dx.ctypes.data, dy.ctypes.data, n, row, float(blending),
+                          out.ctypes.data)
+    return out
+
+
+def sum_gaussian_modes(rays, modes, wavelengths, points, time_ps=0.0):
+    """cfields.sum_gaussian_modes (cfields.pyx:51-115) -> npt x 3 complex."""
+    L = lib()
+    rays = np.ascontiguousarray(rays)
+    assert rays.dtype == A.ray_dtype
+    modes = np.ascontiguousarray(modes, dtype=np.complex128)
+    wl = np.ascontiguousarray(wavelengths, dtype=np.double)
+    pts = np.ascontiguousarray(points, dtype=np.double).reshape(-1, 3)
+    out = np.zeros((pts.shape[0], 3), dtype=np.complex128)
+    L.rpxo_sum_gaussian_modes(rays.ctypes.data, rays.shape[0], modes.ctypes.data, wl.ctypes.data, pts.ctypes.data,
+                              pts.shape[0], float(time_ps), out.ctypes.data)
+    return out
+
+
+def eval_Efield_from_gausslets(gausslets, points, wavelengths, blending=1.0, time_ps=0.0):
+    """core/fields.py:252-277 on numpy arrays."""
+    g = np.ascontiguousarray(gausslets)
+    x, y, dx, dy = evaluate_neighbours_gc(g)
+    modes = evaluate_modes(x, y, dx, dy, blending)
+    return sum_gaussian_modes(np.ascontiguousarray(g['base_ray']), modes, wavelengths, points, time_ps)
+
+
+def reference_fields(core):
+    """The reference's raypier/core/fields.py, imported in place from /root/reference (it is pure
+    Python over the compiled cfields of oracle/_ref); None where /root/reference is absent."""
+    import importlib
+    import importlib.util
+    name = core.__name__ + ".fields"
+    if name in sys.modules:
+        return sys.modules[name]
+    src = "/root/reference/raypier/core"
+    if not os.path.exists(os.path.join(src, "fields.py")):
+        return None
+    try:
+        importlib.import_module(core.__name__ + ".cfields")
+        for mod in ("utils", "fields"):
+            full = core.__name__ + "." + mod
+            if full in sys.modules:
+                continue
+            spec = importlib.util.spec_from_file_location(full, os.path.join(src, mod + ".py"))
+            m = importlib.util.module_from_spec(spec)
+            sys.modules[full] = m
+            spec.loader.exec_module(m)
+        return sys.modules[name]
+    except Exception:
+        sys.modules.pop(core.__name__ + ".fields", None)
+        return None
 
 
 # ---- unit entry points (for pinning against the reference's own KATs) -------

@@ -1954,5 +1954,145 @@ double rpxo_zernike_R_over_r(double r, int k, int n, int m, double* ws3k, int km
     zws_t ws = {{ws3k, ws3k + kmax, ws3k + 2 * kmax}};
     return zernike_R_over_r(r, k, n, m, &ws);
 }
+/* =============================================================== E-field summation
+ * raypier/core/cfields.pyx + the gausslet front end of raypier/core/fields.py.             */
+
+/* evaluate_neighbours_gc, core/fields.py:114-137 (numpy there, a loop here): the six parabasal
+ * rays of every gausslet in the (E, H) basis of its base ray.  x, y, dx, dy are n x 6.      */
+void rpxo_evaluate_neighbours_gc(const rpx_gausslet* gs, uint64_t n, double* x, double* y, double* dx,
+                                 double* dy) {
+    for (uint64_t i = 0; i < n; i++) {
+        const rpx_ray* b = &gs[i].base_ray;
+        vec3 origin = ld3(b->origin), direction = ld3(b->direction), E = ld3(b->E_vector);
+        vec3 H = cross(E, direction); /* numpy.cross(E, direction) */
+        for (int j = 0; j < RPX_NPARA; j++) {
+            const rpx_para* p = &gs[i].para[j];
+            vec3 off = subvv(ld3(p->origin), origin), nd = ld3(p->direction);
+            x[i * 6 + j] = dotprod(off, E);
+            y[i * 6 + j] = dotprod(off, H);
+            double dz = dotprod(nd, direction);
+            dx[i * 6 + j] = dotprod(nd, E) / dz;
+            dy[i * 6 + j] = dotprod(nd, H) / dz;
+        }
+    }
+}
+
+/* evaluate_one_mode, cfields.pyx:156-214: closed-form 3x3 normal equations of the least-squares
+ * fit; out[0..2] = the complex (A, B, C) of one gausslet.                                   */
+static void evaluate_one_mode(cplx* out, const double* x, const double* y, const double* dx, const double* dy,
+                              double blending, int size) {
+    double a00 = 0, a01 = 0, a02 = 0, a11 = 0, a12 = 0, a22 = 0, b0 = 0, b1 = 0, b2 = 0;
+    double im[3], re[3];
+    for (int i = 0; i < size; i++) { /* imaginary parts, :170-181 */
+        double xi2 = x[i] * x[i], yi2 = y[i] * y[i];
+        a00 += xi2 * xi2;
+        a01 += ((2 * xi2) * x[i]) * y[i];
+        a02 += xi2 * yi2;
+        a11 += (4 * xi2) * yi2;
+        a12 += ((2 * x[i]) * y[i]) * yi2;
+        a22 += yi2 * yi2;
+        b0 += xi2;
+        b1 += (2 * x[i]) * y[i];
+        b2 += yi2;
+    }
+    {
+        double den = (((((-a00) * a11) * a22) + (a00 * (a12 * a12))) + ((a01 * a01) * a22)) -
+                     (((2.0 * a01) * a02) * a12) + ((a02 * a02) * a11);
+        im[0] = (blending * ((((-b0) * ((a11 * a22) - (a12 * a12))) + (b1 * ((a01 * a22) - (a02 * a12)))) -
+                             (b2 * ((a01 * a12) - (a02 * a11))))) / den;
+        im[1] = ((-blending) * (((b0 * ((a01 * a22) - (a02 * a12))) - (b1 * ((a00 * a22) - (a02 * a02)))) +
+                                (b2 * ((a00 * a12) - (a01 * a02))))) / den;
+        im[2] = (blending * ((((-b0) * ((a01 * a12) - (a02 * a11))) + (b1 * ((a00 * a12) - (a01 * a02)))) -
+                             (b2 * ((a00 * a11) - (a01 * a01))))) / den;
+    }
+    a00 = a01 = a02 = a11 = a12 = a22 = b0 = b1 = b2 = 0;
+    for (int i = 0; i < size; i++) { /* real parts, :196-206 */
+        double xi2 = x[i] * x[i], yi2 = y[i] * y[i];
+        a00 += xi2;
+        a01 += x[i] * y[i];
+        a11 += xi2 + yi2;
+        a22 += yi2;
+        b0 += dx[i] * x[i];
+        b1 += (dx[i] * y[i]) + (dy[i] * x[i]);
+        b2 += dy[i] * y[i];
+    }
+    a12 = a01 * a01;
+    {
+        double den = ((a00 * a12) - ((a00 * a11) * a22)) + (a12 * a22);
+        re[0] = ((((-a12) * b2) + ((a01 * a22) * b1)) + (b0 * (a12 - (a11 * a22)))) / den;
+        re[1] = (-((((a00 * a01) * b2) - ((a00 * a22) * b1)) + ((a01 * a22) * b0))) / den;
+        re[2] = ((((a00 * a01) * b1) - (a12 * b0)) - (b2 * ((a00 * a11) - a12))) / den;
+    }
+    for (int k = 0; k < 3; k++) out[k] = from_parts(re[k], im[k]);
+}
+
+/* evaluate_modes, cfields.pyx:217-228; modes is n x 3 complex */
+void rpxo_evaluate_modes(const double* x, const double* y, const double* dx, const double* dy, uint64_t n,
+                         int row_size, double blending, double* modes) {
+    cplx* out = (cplx*)modes;
+    for (uint64_t i = 0; i < n; i++)
+        evaluate_one_mode(out + 3 * i, x + i * row_size, y + i * row_size, dx + i * row_size, dy + i * row_size,
+                          blending, row_size);
+}
+
+/* calc_mode_U, cfields.pyx:118-153.  Mixed real/complex operations are written the way Cython
+ * lowers them (real promoted to r + 0i, native C complex * and /; oracle/_ref/build/cfields.c). */
+static cplx calc_mode_U(cplx A, cplx B, cplx C, cplx detG0, vec3 pt, vec3 E, vec3 H, vec3 direction, cplx k,
+                        double phase, double inv_root_area, cplx rootI) {
+    double x = dotprod(pt, E), y = dotprod(pt, H), z = dotprod(pt, direction);
+    cplx denom = ((CX(1) + (CX(z) * (A + C))) + (CX(z * z) * detG0)) * CX(2);
+    cplx AA = (A + (CX(z) * detG0)) / denom;
+    cplx CC = (C + (CX(z) * detG0)) / denom;
+    cplx t1 = B * CX((2.0 * x) * y);
+    cplx U = cexp(_Complex_I *
+                  (CX(phase) + (k * (((CX(z) + (AA * CX(x * x))) + (t1 / denom)) + (CC * CX(y * y))))));
+    cplx q = csqrt((((CX(1) + (CX(z) * A)) * (CX(1) + (CX(z) * C))) - ((CX(z) * B) * (CX(z) * B))) * _Complex_I);
+    U = U / q;
+    U = U * (CX(inv_root_area) * rootI);
+    return U;
+}
+
+/* sum_gaussian_modes, cfields.pyx:51-115: E-field at npt points as the sum over rays of
+ * general astigmatic Gaussian modes.  out is npt x 3 complex, zeroed here (np.zeros, :68).
+ * Accumulation order = the reference's: rays outermost, in order.                         */
+void rpxo_sum_gaussian_modes(const rpx_ray* rays, uint64_t n_rays, const double* modes_, const double* wavelengths,
+                             const double* points, uint64_t npt, double time_ps, double* out_) {
+    const cplx* modes = (const cplx*)modes_;
+    cplx* out = (cplx*)out_;
+    const cplx rootI = csqrt(_Complex_I); /* module-level rootI, :45 */
+    double c = 0.299792458;
+    c *= time_ps;
+    for (uint64_t i = 0; i < 3 * npt; i++) out[i] = CX(0);
+    for (uint64_t iray = 0; iray < n_rays; iray++) {
+        rpx_ray ray = rays[iray];
+        vec3 E = norm(ld3(ray.E_vector));
+        vec3 dir = ld3(ray.direction);
+        vec3 H = norm(cross(dir, E));
+        double k = (2000.0 * M_PI) / wavelengths[ray.wavelength_idx];
+        double n_re = ray.refractive_index[0];
+        double phase = (ray.phase + (ray.accumulated_path * k)) - ((c * k) / n_re);
+        cplx kz = from_parts(ray.refractive_index[0], ray.refractive_index[1]);
+        kz = kz * CX(k);
+        double invk = 2. / creal(kz);
+        cplx A = modes[3 * iray], B = modes[3 * iray + 1], C = modes[3 * iray + 2];
+        double inv_root_area = sqrt(sqrt((cimag(A) * cimag(C)) - (cimag(B) * cimag(B))) * (2.0 / M_PI));
+        A = from_parts(creal(A), cimag(A) * invk); /* __Pyx_SET_CIMAG */
+        B = from_parts(creal(B), cimag(B) * invk);
+        C = from_parts(creal(C), cimag(C) * invk);
+        cplx detG0 = (A * C) - (B * B);
+        cplx E1a = from_parts(ray.E1_amp[0], ray.E1_amp[1]), E2a = from_parts(ray.E2_amp[0], ray.E2_amp[1]);
+        vec3 origin = ld3(ray.origin);
+        for (uint64_t ipt = 0; ipt < npt; ipt++) {
+            vec3 pt = subvv(ld3(points + 3 * ipt), origin);
+            cplx U = calc_mode_U(A, B, C, detG0, pt, E, H, dir, kz, phase, inv_root_area, rootI);
+            cplx E1 = E1a * U, E2 = E2a * U;
+            out[3 * ipt + 0] = out[3 * ipt + 0] + ((E1 * CX(E.x)) + (E2 * CX(H.x)));
+            out[3 * ipt + 1] = out[3 * ipt + 1] + ((E1 * CX(E.y)) + (E2 * CX(H.y)));
+            out[3 * ipt + 2] = out[3 * ipt + 2] + ((E1 * CX(E.z)) + (E2 * CX(H.z)));
+        }
+    }
+}
+
+
 int rpxo_sizeof_ray(void) { return (int)sizeof(rpx_ray); }
 int rpxo_sizeof_gausslet(void) { return (int)sizeof(rpx_gausslet); }

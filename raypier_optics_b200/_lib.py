@@ -22,6 +22,8 @@ EXPORTS = (
     "rpx_result_device_ms", "rpx_result_launches", "rpx_result_kernel_ms", "rpx_result_free",
     "rpx_stream", "rpx_unit_face_intersect", "rpx_unit_face_normal", "rpx_unit_material_eval",
     "rpx_unit_distortion", "rpx_capture_scene_set", "rpx_result_rays", "rpx_capture",
+    "rpx_field_prepare", "rpx_field_count", "rpx_field_modes", "rpx_field_evaluate",
+    "rpx_field_evaluate_device", "rpx_field_last_ms", "rpx_field_free",
 )
 
 
@@ -108,6 +110,20 @@ def load():
     L.rpx_result_rays.restype = vp
     L.rpx_capture.argtypes = [vp, vp, i32, vp, vp, u32, pvp, vp]
     L.rpx_capture.restype = i32
+    L.rpx_field_prepare.argtypes = [vp, vp, vp, vp, i32, d, pvp]
+    L.rpx_field_prepare.restype = i32
+    L.rpx_field_count.argtypes = [vp]
+    L.rpx_field_count.restype = u64
+    L.rpx_field_modes.argtypes = [vp, vp, vp]
+    L.rpx_field_modes.restype = i32
+    L.rpx_field_evaluate.argtypes = [vp, vp, vp, u64, d, vp]
+    L.rpx_field_evaluate.restype = i32
+    L.rpx_field_evaluate_device.argtypes = [vp, vp, vp, u64, d, vp]
+    L.rpx_field_evaluate_device.restype = i32
+    L.rpx_field_last_ms.argtypes = [vp]
+    L.rpx_field_last_ms.restype = d
+    L.rpx_field_free.argtypes = [vp, vp]
+    L.rpx_field_free.restype = None
     if L.rpx_abi_version() != A.RPX_ABI_VERSION:
         raise RuntimeError("librpx.so ABI %d != binding ABI %d" % (L.rpx_abi_version(), A.RPX_ABI_VERSION))
     _LIB = L

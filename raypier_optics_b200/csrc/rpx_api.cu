@@ -16,6 +16,7 @@
 #include <vector>
 
 #include "../../include/rpx.h"
+#include "rpx_internal.h"
 #include "rpx_launch.h"
 
 using namespace rpx;
@@ -34,69 +35,7 @@ static_assert(sizeof(rpx_distortion) == 64, "rpx_distortion layout");
 
 static thread_local std::string g_init_error;
 
-#define RPX_MAX_PIPE_GENS 1024  /* generations a pipelined trace can hold counts for */
-#define RPX_PIPE_STATE_TILES (4u << 20) /* 32 MB of look-back state: 5e8 parents per trace without a re-zero */
-
-struct rpx_rays {
-    Soa soa;
-    void* block;  // single allocation backing soa.f / soa.u / soa.p
-    size_t bytes;
-    int is_gausslet;
-};
-
-struct KernelStat {
-    std::vector<cudaEvent_t> start, stop;
-};
-
-struct rpx_ctx {
-    int device;
-    cudaStream_t stream;
-    std::string err;
-    // scene
-    bool have_scene;
-    DevScene ds;
-    void* scene_block;
-    int n_traced;
-    int max_kids;       // upper bound of children per hit over all materials in the scene
-    int scene_smem;     // bytes of shared memory the staged scene needs (0 = use global)
-    int face_class;     // RPX_FC_SIMPLE / RPX_FC_FULL kernel variant for this scene
-    int mm_idx;         // material-mask kernel variant: 0 LIGHT, 1 COATED, 2 FULLDIEL, 3 ALL
-    // capture-plane scene (rpx_capture_scene_set): a second, independent face list
-    bool have_capture;
-    DevScene cap_ds;
-    void* cap_block;
-    uint32_t* cap_face_ids;  // device copy of the Python-side Face.idx values, or NULL
-    int cap_smem;
-    int cap_face_class;
-    // scratch
-    unsigned long long* tile_state;
-    size_t tile_state_cap;  // tiles
-    uint32_t* tile_counter;
-    unsigned long long* d_count;
-    unsigned long long* h_count;  // pinned
-    uint32_t* d_face_counts;
-    unsigned long long* d_counts;  // per-generation counts of a pipelined trace (RPX_MAX_PIPE_GENS)
-    unsigned long long* h_counts;  // pinned + mapped: the kernels write len(new_rays) straight into it
-    unsigned long long* h_counts_dev;  // device alias of h_counts
-    unsigned long long* pipe_state;  // tile-state slices of a pipelined trace, zeroed ahead of use
-    size_t pipe_state_cap;           // tiles
-    uint32_t* pipe_counters;         // one ticket counter per generation
-    // event pool
-    std::vector<cudaEvent_t> ev_pool;
-    size_t ev_used;
-};
-
-struct rpx_result {
-    std::vector<rpx_rays*> gens;  // nullptr for generations dropped in KEEP_LAST_ONLY mode
-    std::vector<uint64_t> counts;
-    std::vector<uint32_t> face_counts;
-    double device_ms;
-    uint64_t launches;
-    double k_ms[2];
-    uint64_t k_launches[2];
-};
-
-static int fail(rpx_ctx* ctx, int code, const char* fmt, ...) {
+int rpx_fail(rpx_ctx* ctx, int code, const char* fmt, ...) {
     char buf[512];
     va_list ap;
     va_start(ap, fmt);
@@ -106,14 +45,6 @@ static int fail(rpx_ctx* ctx, int code, const char* fmt, ...) {
     else g_init_error = buf;
     return code;
 }
-
-#define CU(ctx, call)                                                                         \
-    do {                                                                                      \
-        cudaError_t e_ = (call);                                                              \
-        if (e_ != cudaSuccess)                                                                \
-            return fail(ctx, e_ == cudaErrorMemoryAllocation ? RPX_ERR_NOMEM : RPX_ERR_CUDA,   \
-                        "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
-    } while (0)
 
 extern "C" int rpx_abi_version(void) { return RPX_ABI_VERSION; }
 
@@ -415,7 +346,7 @@ extern "C" int rpx_capture_scene_set(rpx_ctx* ctx, const rpx_scene* s, const uin
 }
 
 // ------------------------------------------------------------------ ray buffers
-static int rays_alloc(rpx_ctx* ctx, unsigned long long cap_req, int is_gausslet, rpx_rays** out) {
+int rpx_rays_alloc(rpx_ctx* ctx, unsigned long long cap_req, int is_gausslet, rpx_rays** out) {
     rpx_rays* r = new (std::nothrow) rpx_rays();
     if (!r) return fail(ctx, RPX_ERR_NOMEM, "out of host memory");
     // every field array 1-KB aligned and a whole number of tiles (TMA bulk copies fetch full tiles)
@@ -457,7 +388,7 @@ extern "C" int rpx_rays_clone(rpx_ctx* ctx, const rpx_rays* rays, rpx_rays** out
     if (!ctx || !rays || !out_rays) return fail(ctx, RPX_ERR_INVALID, "NULL argument");
     CU(ctx, cudaSetDevice(ctx->device));
     rpx_rays* r = nullptr;
-    int rc = rays_alloc(ctx, rays->soa.cap, rays->is_gausslet, &r);
+    int rc = rpx_rays_alloc(ctx, rays->soa.cap, rays->is_gausslet, &r);
     if (rc != RPX_OK) return rc;
     r->soa.n = rays->soa.n;
     if (r->bytes != rays->bytes) {
@@ -489,7 +420,7 @@ extern "C" int rpx_rays_upload(rpx_ctx* ctx, const void* aos, uint64_t n, int is
         return fail(ctx, RPX_ERR_INVALID, "%llu rays per generation exceed the 32-bit parent_idx of ray_t",
                     (unsigned long long)n);
     rpx_rays* r = nullptr;
-    int rc = rays_alloc(ctx, n, is_gausslet, &r);
+    int rc = rpx_rays_alloc(ctx, n, is_gausslet, &r);
     if (rc != RPX_OK) return rc;
     r->soa.n = n;
     if (n) {
@@ -621,7 +552,7 @@ static int trace_pipelined(rpx_ctx* ctx, rpx_rays* rays, double ml, int recursio
             return bail(fail(ctx, RPX_ERR_INVALID, "generation would exceed the 32-bit parent_idx of ray_t"));
         rpx_rays* child = nullptr;
         {
-            int rc = rays_alloc(ctx, kids * bound, is_g, &child);
+            int rc = rpx_rays_alloc(ctx, kids * bound, is_g, &child);
             if (rc != RPX_OK) return bail(rc);
         }
         bufs.push_back(child);
@@ -799,7 +730,7 @@ static int trace_loop(rpx_ctx* ctx, rpx_rays* rays, double max_length, int recur
         if (cap_child >= 0xFFFFFFFFull)
             return bail(fail(ctx, RPX_ERR_INVALID, "generation would exceed the 32-bit parent_idx of ray_t"));
         {
-            int rc = rays_alloc(ctx, cap_child, is_g, &child);
+            int rc = rpx_rays_alloc(ctx, cap_child, is_g, &child);
             if (rc != RPX_OK) return bail(rc);
         }
         if (n_wtiles > ctx->tile_state_cap) {
@@ -936,7 +867,7 @@ extern "C" int rpx_capture(rpx_ctx* ctx, const rpx_rays* const* gens, int n_gens
     }
     const int is_g = gens[0]->is_gausslet;
     rpx_rays* dst = nullptr;
-    int rc = rays_alloc(ctx, total, is_g, &dst);
+    int rc = rpx_rays_alloc(ctx, total, is_g, &dst);
     if (rc != RPX_OK) return rc;
     // scratch: [totals (n_gens + 1) u64][tile state u64 x tiles][ticket counters u32 x n_gens][wl_map u32]
     const size_t off_state = sizeof(unsigned long long) * (size_t)(n_gens + 1);

@@ -99,6 +99,51 @@ class DeviceRays(object):
             pass
 
 
+class FieldModes(object):
+    """Prepared Gaussian modes of a set of rays / gausslets on the device (``rpx_field``):
+    evaluate the E-field at as many point sets as needed."""
+
+    def __init__(self, engine, handle):
+        self._e, self._h = engine, handle
+
+    def __len__(self):
+        return int(self._e._L.rpx_field_count(self._h))
+
+    @property
+    def modes(self):
+        """(A, B, C) per ray, n x 3 complex128."""
+        out = np.zeros((len(self), 3), dtype=np.complex128)
+        self._e._check(self._e._L.rpx_field_modes(self._e._ctx, self._h, out.ctypes.data))
+        return out
+
+    def evaluate(self, points, time_ps=0.0):
+        pts = np.ascontiguousarray(points, dtype=np.double).reshape(-1, 3)
+        out = np.zeros((pts.shape[0], 3), dtype=np.complex128)
+        self._e._check(self._e._L.rpx_field_evaluate(self._e._ctx, self._h, pts.ctypes.data, pts.shape[0],
+                                                     float(time_ps), out.ctypes.data))
+        return out
+
+    def evaluate_device(self, d_points, npt, d_out, time_ps=0.0):
+        """Device pointers (e.g. torch ``tensor.data_ptr()``); ``d_out`` is accumulated into."""
+        self._e._check(self._e._L.rpx_field_evaluate_device(self._e._ctx, self._h, int(d_points), int(npt),
+                                                            float(time_ps), int(d_out)))
+
+    @property
+    def last_ms(self):
+        return float(self._e._L.rpx_field_last_ms(self._h))
+
+    def free(self):
+        if self._h is not None:
+            self._e._L.rpx_field_free(self._e._ctx, self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+
 class Engine(object):
     def __init__(self, device=0):
         self._L = load()
@@ -162,6 +207,31 @@ class Engine(object):
         finally:
             dev.free()
         return out, reduced, [int(c) for c in counts]
+
+    # -- E-field summation --------------------------------------------------------------------
+    def field_prepare(self, rays, wavelengths, modes=None, blending=1.0):
+        """``rays``: a DeviceRays, a borrowed ``rpx_rays`` handle, or a host array (uploaded).
+        Gausslets with ``modes=None`` get their modes fitted on the device."""
+        own = None
+        if isinstance(rays, np.ndarray):
+            own = self.upload(rays)
+            handle = own._h
+        elif isinstance(rays, DeviceRays):
+            handle = rays._h
+        else:
+            handle = rays
+        wl = np.ascontiguousarray(wavelengths, dtype=np.double).reshape(-1)
+        m = None
+        if modes is not None:
+            m = np.ascontiguousarray(modes, dtype=np.complex128).reshape(-1, 3)
+        h = C.c_void_p()
+        try:
+            self._check(self._L.rpx_field_prepare(self._ctx, handle, None if m is None else m.ctypes.data,
+                                                  wl.ctypes.data, wl.shape[0], float(blending), C.byref(h)))
+        finally:
+            if own is not None:
+                own.free()
+        return FieldModes(self, h)
 
     # -- rays -----------------------------------------------------------------------
     @staticmethod

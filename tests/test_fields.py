@@ -1,0 +1,165 @@
+"""E-field summation: raypier/core/cfields.pyx sum_gaussian_modes / calc_mode_U /
+evaluate_modes and the gausslet front end of raypier/core/fields.py.
+
+CPU: the oracle restatement is bit-exact with the compiled reference (and with fields.py
+imported in place from /root/reference); golden vectors made from the reference are committed for
+the GPU box.  GPU: the CUDA path against the oracle and the golden vectors.
+
+Tolerance: |dE| <= 2e-10 * max|E|.  The optical phase of a mode is ~1e6 rad (k = 2000 pi / lambda
+per mm times ~100 mm of path), so ONE ulp of the path term is 1.2e-10 rad: the summation cannot be
+reproduced more tightly than that by anything that is not the same instruction stream.  The CUDA
+kernel keeps the reference's association and roundings for exactly those terms.
+"""
+import os
+
+import numpy as np
+import pytest
+
+from raypier_optics_b200 import _abi as A
+from raypier_optics_b200 import configs, scene as SC
+
+TOL_FIELD_SUM = 2e-10
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "fields_michelson.npz")
+
+
+def michelson_output(core, n=600, seed=5):
+    """Gausslets leaving the Michelson towards the output port (last generation) + a detector
+    line across the fringes and a small grid off-axis."""
+    from oracle import oracle as O
+    cfg = configs.build(core, "config5", n=n, gausslets=True, seed=seed)
+    sc = SC.Scene(cfg['face_lists'], cfg['wavelengths'])
+    gens, _ = O.trace_rays(sc, cfg['rays'], cfg['recursion_limit'], cfg['max_length'])
+    g = gens[-1]
+    out = g[g['base_ray']['direction'][:, 1] < -0.5]  # the beams travelling to -y (output port)
+    assert len(out) > n
+    xs = np.linspace(-4.0, 4.0, 41)
+    line = np.stack([xs, np.full_like(xs, -14.0), np.zeros_like(xs)], axis=1)
+    gx, gz = np.meshgrid(np.linspace(-2, 2, 5), np.linspace(-1.5, 1.5, 4))
+    grid = np.stack([gx.ravel(), np.full(gx.size, -25.0), gz.ravel()], axis=1)
+    return cfg, np.ascontiguousarray(out), np.concatenate([line, grid])
+
+
+def rel_err(got, want):
+    return float(np.abs(got - want).max() / np.abs(want).max())
+
+
+def test_oracle_fields_bit_exact_with_reference(refcore):
+    from oracle import oracle as O
+    F = O.reference_fields(refcore)
+    if F is None:
+        pytest.skip("raypier/core/fields.py not importable here")
+    from raypier.core import cfields
+    cfg, g, pts = michelson_output(refcore)
+    base, rx, ry, rdx, rdy = F.evaluate_neighbours_gc(g)
+    x, y, dx, dy = O.evaluate_neighbours_gc(g)
+    for a, b in ((rx, x), (ry, y), (rdx, dx), (rdy, dy)):
+        assert a.tobytes() == b.tobytes()
+    for blending in (1.0, 0.7):
+        rm = cfields.evaluate_modes(rx, ry, rdx, rdy, blending=blending)
+        om = O.evaluate_modes(x, y, dx, dy, blending)
+        assert rm.tobytes() == om.tobytes()
+    rc = O.reference_collection(refcore, np.ascontiguousarray(g['base_ray']), cfg['wavelengths'])
+    for t in (0.0, 3.5):
+        want = cfields.sum_gaussian_modes(rc, rm, np.asarray(cfg['wavelengths']), pts, t)
+        got = O.sum_gaussian_modes(np.ascontiguousarray(g['base_ray']), om, cfg['wavelengths'], pts, t)
+        assert np.abs(want).max() > 1e-3
+        assert got.tobytes() == want.tobytes(), "sum_gaussian_modes not bit-identical (time_ps=%g)" % t
+    # the whole chain as the reference's public function runs it
+    gc = refcore.ctracer.GaussletCollection.from_array(g.view(refcore.ctracer.gausslet_dtype))
+    gc.wavelengths = np.asarray(cfg['wavelengths'])
+    want = F.eval_Efield_from_gausslets(gc, pts, blending=0.7, time_ps=3.5)
+    got = O.eval_Efield_from_gausslets(g, pts, cfg['wavelengths'], blending=0.7, time_ps=3.5)
+    assert got.tobytes() == want.tobytes()
+
+
+def test_oracle_reproduces_golden_fields():
+    from oracle import oracle as O
+    z = np.load(GOLDEN)
+    g = z['gausslets'].view(A.gausslet_dtype).reshape(-1)
+    modes = O.evaluate_modes(*O.evaluate_neighbours_gc(g), blending=float(z['blending']))
+    assert modes.tobytes() == z['modes'].tobytes()
+    E = O.eval_Efield_from_gausslets(g, z['points'], z['wavelengths'], float(z['blending']), float(z['time_ps']))
+    assert E.tobytes() == z['E'].tobytes()
+
+
+def test_field_is_linear_in_amplitude_and_additive_over_rays():
+    """Size-independent properties of the summation (also used at full size on the GPU)."""
+    from oracle import oracle as O
+    z = np.load(GOLDEN)
+    g = z['gausslets'].view(A.gausslet_dtype).reshape(-1)
+    pts, wl = z['points'][:16], z['wavelengths']
+    E = O.eval_Efield_from_gausslets(g, pts, wl)
+    h = len(g) // 2
+    E2 = O.eval_Efield_from_gausslets(g[:h], pts, wl) + O.eval_Efield_from_gausslets(g[h:], pts, wl)
+    assert rel_err(E2, E) < 1e-13
+    g3 = g.copy()
+    g3['base_ray']['E1_amp'] *= 3.0
+    g3['base_ray']['E2_amp'] *= 3.0
+    assert rel_err(O.eval_Efield_from_gausslets(g3, pts, wl), 3.0 * E) < 1e-14
+
+
+# ------------------------------------------------------------------------------------ GPU
+@pytest.mark.gpu
+def test_cuda_fields_match_golden_reference(engine):
+    z = np.load(GOLDEN)
+    g = z['gausslets'].view(A.gausslet_dtype).reshape(-1)
+    fm = engine.field_prepare(g, z['wavelengths'], blending=float(z['blending']))
+    try:
+        modes = fm.modes
+        scale = np.abs(z['modes']).max(axis=1, keepdims=True)
+        assert float((np.abs(modes - z['modes']) / scale).max()) < 1e-10
+        E = fm.evaluate(z['points'], float(z['time_ps']))
+    finally:
+        fm.free()
+    err = rel_err(E, z['E'])
+    assert err <= TOL_FIELD_SUM, "E-field rel err %.3e" % err
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("time_ps", [0.0, 3.5])
+def test_cuda_fields_match_oracle(core, engine, time_ps):
+    from oracle import oracle as O
+    from raypier_optics_b200.core import cfields as CF, fields as FD
+    cfg, g, pts = michelson_output(core, n=900, seed=11)
+    want = O.eval_Efield_from_gausslets(g, pts, cfg['wavelengths'], 0.8, time_ps)
+    gc = core.ctracer.GaussletCollection.from_array(g)
+    gc.wavelengths = cfg['wavelengths']
+    got = FD.eval_Efield_from_gausslets(gc, pts, blending=0.8, time_ps=time_ps)
+    assert got.shape == want.shape and got.dtype == np.complex128
+    assert rel_err(got, want) <= TOL_FIELD_SUM
+    # the exact sum_gaussian_modes signature: explicit modes with the base rays
+    modes = O.evaluate_modes(*O.evaluate_neighbours_gc(g), blending=0.8)
+    got2 = CF.sum_gaussian_modes(np.ascontiguousarray(g['base_ray']), modes, cfg['wavelengths'], pts, time_ps)
+    assert rel_err(got2, want) <= TOL_FIELD_SUM
+    # EFieldSummation: prepare once, evaluate point sets of any shape
+    s = FD.EFieldSummation(gc, blending=0.8)
+    E3 = s.evaluate(pts.reshape(-1, 1, 3), time_ps)
+    assert E3.shape == (len(pts), 1, 3)
+    assert rel_err(E3.reshape(-1, 3), want) <= TOL_FIELD_SUM
+
+
+@pytest.mark.gpu
+def test_cuda_field_properties_at_size(core, engine):
+    """50k gausslets x 20k points (1e9 pairs; the oracle would need minutes): additivity over ray
+    shards -- what the multi-GPU all-reduce relies on -- linearity, and a spot check of 8 points
+    against the oracle."""
+    from oracle import oracle as O
+    cfg, g, _ = michelson_output(core, n=25000, seed=3)
+    g = g[:50000]
+    rng = np.random.default_rng(0)
+    pts = np.stack([rng.uniform(-4, 4, 20000), np.full(20000, -14.0), rng.uniform(-3, 3, 20000)], axis=1)
+    wl = cfg['wavelengths']
+    fm = engine.field_prepare(g, wl)
+    E = fm.evaluate(pts)
+    ms = fm.last_ms
+    fm.free()
+    assert ms > 0
+    h = len(g) // 3
+    parts = []
+    for part in (g[:h], g[h:]):
+        f = engine.field_prepare(part, wl)
+        parts.append(f.evaluate(pts))
+        f.free()
+    assert rel_err(parts[0] + parts[1], E) < 1e-12
+    want = O.eval_Efield_from_gausslets(g, pts[:8], wl)
+    assert np.abs(E[:8] - want).max() / np.abs(E).max() <= TOL_FIELD_SUM
