@@ -438,6 +438,122 @@ def run_ours(args):
     return 0
 
 
+def run_fields(args):
+    """--fields: the E-field summation (cfields.sum_gaussian_modes) as its own
+    measurement.  Workload: the Michelson output gausslets (config 5 traced on the GPU, rays
+    captured at the output port) summed on a square detector grid.  One "step" = one evaluation of
+    all N_ray x N_pt pairs.  Prints one JSON line (metric: mode-point pairs/s)."""
+    import torch
+    if not torch.cuda.is_available():
+        raise RuntimeError("bench.py needs a CUDA device: raypier_optics_b200 has no CPU fallback")
+    import raypier_optics_b200.core as core
+    from raypier_optics_b200 import configs, scene
+    from raypier_optics_b200.engine import Engine
+    eng = Engine(0)
+    n_src = args.rays if args.rays else 50000
+    cfg = configs.build(core, "config5", n=n_src, gausslets=True, seed=7)
+    eng.set_scene(scene.Scene(cfg["face_lists"], cfg["wavelengths"]))
+    face = core.cfaces.RectangularFace(length=12.0, width=12.0, offset=0.0, z_plane=0.0)
+    fl = core.ctracer.FaceList(owner=configs.Pose(centre=(0.0, -12.0, 0.0), direction=(0.0, 1.0, 0.0)))
+    fl.faces = [face]
+    fl.sync_transforms()
+    eng.set_capture_scene(scene.Scene([fl], np.asarray([1.0])))
+    res = eng.trace(np.ascontiguousarray(cfg["rays"]), cfg["max_length"], cfg["recursion_limit"])
+    g, _, _ = res.capture(cfg["wavelengths"])
+    res.free()
+    side = args.field_grid
+    xs = np.linspace(-4.0, 4.0, side)
+    gx, gz = np.meshgrid(xs, xs)
+    pts = np.ascontiguousarray(np.stack([gx.ravel(), np.full(gx.size, -14.0), gz.ravel()], axis=1))
+    n_ray, n_pt = len(g), len(pts)
+    dev = eng.upload(g)
+    fm = eng.field_prepare(dev, cfg["wavelengths"])
+    d_pts = torch.from_numpy(pts).cuda()
+    d_out = torch.zeros((n_pt, 6), dtype=torch.float64, device="cuda")
+    pinned_pts = torch.from_numpy(pts).pin_memory()
+    for _ in range(max(args.warmup, 3)):
+        fm.evaluate_device(d_pts.data_ptr(), n_pt, d_out.data_ptr())
+    sampler = ClockSampler(0)
+    sampler.start()
+    torch.cuda.synchronize()
+    ms = 0.0
+    for _ in range(args.steps):
+        d_out.zero_()
+        fm.evaluate_device(d_pts.data_ptr(), n_pt, d_out.data_ptr())
+        ms += fm.last_ms
+    torch.cuda.synchronize()
+    sampler.stop_flag.set()
+    sampler.join()
+    pairs = float(n_ray) * n_pt
+    value = pairs * args.steps / (ms * 1e-3)
+    # e2e: host gausslets + host points in, host field out, mode fit included
+    gp = eng.pinned_empty(len(g), g.dtype)
+    gp[:] = g
+    e2e_steps = max(1, min(args.steps, args.e2e_steps))
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        f2 = eng.field_prepare(gp, cfg["wavelengths"])
+        E = f2.evaluate(pts)
+        f2.free()
+    e2e = pairs * e2e_steps / (time.perf_counter() - t0)
+    # fp64 roofline: instructions counted from the SASS of k_field_sum per pair (see DESIGN.md),
+    # peak = measured DFMA issue rate of this GPU (profiles/microbench/fp64_latency.cu)
+    fp64_per_pair = 143.0  # DFMA+DMUL+DADD+DSETP per pair in the SASS loop of k_field_sum (286 per 2-point iteration)
+    peak_inst = 63.6 * 148 * 1.965e9 / 1e12  # T fp64 lane-instructions/s, measured
+    ach = fp64_per_pair * value / 1e12
+    cpu = None
+    if not args.no_cpu_baseline:
+        cpu = fields_cpu_baseline(g, cfg["wavelengths"], pts, args)
+    line = {"metric": "mode-point pairs/sec", "value": value, "unit": "pairs/s", "n_gpus": 1, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": "fields: Michelson output gausslets on a %dx%d detector" % (side, side),
+                       "n_rays": n_ray, "n_points": n_pt, "l2": "mode records 33 x 8 B per ray stream from L2/HBM; compute bound"},
+            "e2e": {"value": e2e, "unit": "pairs/s", "h2d_bytes_per_step": int(g.nbytes + pts.nbytes),
+                    "d2h_bytes_per_step": int(n_pt * 48), "steps": e2e_steps},
+            "gpu_launches": args.steps, "clocks": sampler.summary(),
+            "roofline": {"bound": "fp64", "kernel": "k_field_sum", "achieved": ach, "peak": peak_inst,
+                         "unit": "T fp64 inst/s", "frac": ach / peak_inst, "traffic": None,
+                         "peak_source": "measured DFMA issue rate (profiles/microbench/fp64_latency.cu)",
+                         "fp64_inst_per_pair": fp64_per_pair},
+            "cpu_baseline": cpu}
+    print(json.dumps(line))
+    return 0
+
+
+def _fields_cpu_worker(a):
+    flavour, g_bytes, wl, pts, t = a
+    from oracle import oracle as O
+    from raypier_optics_b200 import _abi as A
+    core = (O.import_reference("timing") or O.import_reference("parity")) if flavour else None
+    g = np.frombuffer(g_bytes, dtype=A.gausslet_dtype)
+    if core is not None:
+        from raypier.core import cfields
+        x, y, dx, dy = O.evaluate_neighbours_gc(g)
+        modes = cfields.evaluate_modes(x, y, dx, dy, blending=1.0)
+        rc = O.reference_collection(core, np.ascontiguousarray(g['base_ray']), wl)
+        t0 = time.perf_counter()
+        cfields.sum_gaussian_modes(rc, modes, np.asarray(wl), pts, t)
+        return time.perf_counter() - t0
+    t0 = time.perf_counter()
+    O.eval_Efield_from_gausslets(g, pts, wl)
+    return time.perf_counter() - t0
+
+
+def fields_cpu_baseline(g, wl, pts, args):
+    """The reference's cfields.sum_gaussian_modes (OpenMP prange over points inside, :98) on all
+    host cores, on a bounded sample of the same rays and points."""
+    kind = cpu_kind()
+    cores = os.cpu_count() or 1
+    n_ray = min(len(g), 2000)
+    n_pt = min(len(pts), 20000)
+    os.environ.setdefault("OMP_NUM_THREADS", str(cores))
+    dt = _fields_cpu_worker(("timing" if kind == "reference" else None, g[:n_ray].tobytes(), np.asarray(wl),
+                             np.ascontiguousarray(pts[:n_pt]), 0.0))
+    return {"value": n_ray * n_pt / dt, "unit": "pairs/s", "cores": cores, "kind": kind,
+            "sample": "%d rays x %d points, reference cfields.sum_gaussian_modes with OpenMP" % (n_ray, n_pt)}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -451,7 +567,12 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--capture", action="store_true",
                     help="also time trace + device-side capture plane (adds `e2e_capture`)")
+    ap.add_argument("--fields", action="store_true",
+                    help="measure the E-field summation (sum_gaussian_modes) instead of the trace")
+    ap.add_argument("--field-grid", type=int, default=512, help="detector grid side for --fields")
     args = ap.parse_args()
+    if args.fields:
+        return run_fields(args)
     if args.impl == "reference":
         return run_reference_arm(args)
     return run_ours(args)

@@ -112,3 +112,40 @@ def trace_sharded(trace_fn, rays, world_size, rank, device=None, group=None, gat
         if rank != gather_to:
             gathered = None
     return dict(local=local, counts_all=counts_all, face_counts=fc, gathered=gathered)
+
+
+# ---- detector field: the one reduction of the pipeline -------------------------
+def allreduce_field(E, device=None, group=None):
+    """Sum the partial E-fields of the ranks.  Every rank evaluates the modes of ITS rays at ALL
+    detector points (the sum over rays is associative), so the only exchange is one all-reduce
+    of the npt x 3 complex grid.  ``E`` may be a numpy complex128 array (copied through a tensor
+    on ``device``; gloo in the CPU tests) or a float64 torch tensor of shape (npt, 6) already on
+    the GPU (reduced in place by NCCL over NVLink -- no host round trip)."""
+    import torch
+    dist = _dist()
+    if isinstance(E, np.ndarray):
+        t = torch.from_numpy(np.ascontiguousarray(E).view(np.float64).copy())
+        if device is not None:
+            t = t.to(device)
+        dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)
+        return t.cpu().numpy().view(np.complex128).reshape(E.shape)
+    dist.all_reduce(E, op=dist.ReduceOp.SUM, group=group)
+    return E
+
+
+def field_sharded(engine, gausslets_shard, wavelengths, points, blending=1.0, time_ps=0.0, group=None):
+    """E-field of gausslets that are sharded over the ranks: mode fit + summation of the local
+    shard on this rank's GPU straight into a torch tensor, then one NCCL all-reduce of the grid.
+    Returns the (npt, 3) complex128 field, identical on every rank."""
+    import torch
+    dev = torch.device("cuda", engine.device)
+    pts = torch.from_numpy(np.ascontiguousarray(points, dtype=np.double).reshape(-1, 3)).to(dev)
+    out = torch.zeros((pts.shape[0], 6), dtype=torch.float64, device=dev)
+    if len(gausslets_shard):
+        fm = engine.field_prepare(gausslets_shard, wavelengths, blending=blending)
+        try:
+            fm.evaluate_device(pts.data_ptr(), pts.shape[0], out.data_ptr(), time_ps)
+        finally:
+            fm.free()
+    allreduce_field(out, group=group)
+    return out.cpu().numpy().view(np.complex128).reshape(-1, 3)

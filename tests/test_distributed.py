@@ -72,3 +72,41 @@ def test_two_rank_trace_equals_single_process(name, kw, rl):
     for g, (got, w) in enumerate(zip(gathered, want)):
         assert got == w.tobytes(), "generation %d differs from the single-process trace" % g
     assert face_counts == want_counts.tolist()
+
+
+def _field_worker(rank, world, port, q):
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    import torch.distributed as dist
+    from oracle import oracle as O
+    from raypier_optics_b200 import _abi as A, distributed as rd
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    z = np.load(os.path.join(ROOT, "tests", "golden", "fields_michelson.npz"))
+    g = z['gausslets'].view(A.gausslet_dtype).reshape(-1)
+    mine = rd.shard_rays(g, world, rank)
+    part = O.eval_Efield_from_gausslets(mine, z['points'], z['wavelengths'], float(z['blending']), float(z['time_ps']))
+    total = rd.allreduce_field(part)
+    if rank == 0:
+        q.put(total.tobytes())
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_two_rank_field_sum_equals_single_process():
+    """Detector field of ray shards: every rank sums ITS rays at all points, one all-reduce of
+    the grid (raypier_optics_b200.distributed.allreduce_field) gives the full field."""
+    import torch.multiprocessing as mp
+    z = np.load(os.path.join(ROOT, "tests", "golden", "fields_michelson.npz"))
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_field_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    got = np.frombuffer(q.get(timeout=300), dtype=np.complex128).reshape(-1, 3)
+    for p in procs:
+        p.join(timeout=120)
+        assert p.exitcode == 0
+    want = z['E']
+    assert np.abs(got - want).max() / np.abs(want).max() < 1e-13  # only the summation order differs
