@@ -336,6 +336,14 @@ k_capture(DevScene S, Soa in, Soa out, unsigned long long* tile_state, uint32_t*
     }
 }
 
+// Look-back before (1) or after (0) the trace-ahead work of a tile; see step 4a of k_shade.
+// Measured on B200: early is SLOWER (0.170 vs 0.133 ms per 1e6 rays) -- warp 0 then waits for the
+// slowest of 32 predecessors to even publish its aggregate (start jitter of thousands of cycles),
+// which the trace-ahead work otherwise hides.
+#ifndef RPX_LOOKBACK_EARLY
+#define RPX_LOOKBACK_EARLY 0
+#endif
+
 // ------------------------------------------------------------------ child staging
 // The children of one tile (<= 2 * RPX_TILE) are assembled in shared memory, field-major
 // like the SoA generation buffer: cs[field * RPX_SLOTS + slot], cu[field * RPX_SLOTS + slot].
@@ -532,6 +540,22 @@ k_shade(DevScene S, Soa in, Soa out, double max_length, unsigned long long* tile
             }
         }
     }
+#if RPX_LOOKBACK_EARLY
+    // ---- 4a. (experiment, off) global offset resolved by warp 0 BEFORE its share of the trace-ahead
+    if (threadIdx.x < 32) {
+        unsigned long long excl = tile_lookback(tile_state, tile, total);
+        if (threadIdx.x == 0) {
+            s_prefix = excl;
+            if (tile == n_tiles_real - 1) {  // len(new_rays)
+                *d_count = excl + total;
+                if (h_count) {  // pipelined loop: straight into mapped pinned host memory, no copy op
+                    *h_count = excl + total;
+                    __threadfence_system();
+                }
+            }
+        }
+    }
+#endif
     // ---- 4. trace ahead
     if (ahead_face != -2) {
         for (uint32_t slot = threadIdx.x; slot < total; slot += RPX_TILE) {
@@ -558,6 +582,7 @@ k_shade(DevScene S, Soa in, Soa out, double max_length, unsigned long long* tile
         }
     }
     // ---- 5. global offset of the tile
+#if !RPX_LOOKBACK_EARLY
     if (threadIdx.x < 32) {
         unsigned long long excl = tile_lookback(tile_state, tile, total);
         if (threadIdx.x == 0) {
@@ -571,6 +596,7 @@ k_shade(DevScene S, Soa in, Soa out, double max_length, unsigned long long* tile
             }
         }
     }
+#endif
     __syncthreads();
     const unsigned long long base = s_prefix;
     // ---- 6. coalesced copy-out: slot == consecutive addresses.  Two explicit passes (a tile has
