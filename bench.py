@@ -305,8 +305,9 @@ def run_ours(args):
     # output staging sized from the known generation profile (+ slack)
     out_cap = int(sum(gen_counts) * 1.05) + 1024
     pinned_out = eng.pinned_empty(out_cap, rays.dtype)
+    pinned_out2 = eng.pinned_empty(int(sum(gen_counts) * 1.05) + 1024 * (len(gen_counts) + 2), rays.dtype)
 
-    def step_e2e():
+    def step_e2e_oneshot():
         res = eng.trace(pinned_in, ml, rl)
         off = 0
         for g in range(res.n_generations):
@@ -318,6 +319,22 @@ def run_ours(args):
         nseg = res.segments
         res.free()
         return nseg, off
+
+    # the public streamed call: source cut into chunks, H2D of chunk c+1 and D2H of chunk c's
+    # generations overlap the tracing (full-duplex PCIe); byte-identical results
+    # (tests/test_parity_gpu.py::test_streamed_trace_is_identical_to_one_shot)
+    gen_caps = [int(c * 1.05) + 1024 for c in gen_counts] + [1024]
+    outs, off = [], 0
+    for c in gen_caps:
+        outs.append(pinned_out2[off:off + c])
+        off += c
+
+    def step_e2e():
+        gens, fc, _ = eng.trace_streamed(pinned_in, ml, rl, outs, chunk_rays=args.chunk_rays)
+        counts = [len(g) for g in gens]
+        if distributed:
+            rdist.exchange_counts(counts, fc, device=dev)
+        return sum(counts), sum(counts)
 
     e2e_steps = max(1, min(args.steps, args.e2e_steps))
     for _ in range(min(args.warmup, 2)):
@@ -337,6 +354,15 @@ def run_ours(args):
         dist.all_reduce(te, op=dist.ReduceOp.MAX)
         dist.all_reduce(se, op=dist.ReduceOp.SUM)
     e2e_value = float(se[0]) / float(te[0])
+    # the same through the one-shot call (upload, trace, then download generation by generation)
+    step_e2e_oneshot()
+    barrier()
+    t0 = time.perf_counter()
+    one_segs = 0
+    for _ in range(e2e_steps):
+        one_segs += step_e2e_oneshot()[0]
+    barrier()
+    e2e_oneshot = one_segs / (time.perf_counter() - t0)
 
     # ---------------- optional capture-plane arm (--capture): the same e2e call, but
     # the generations stay on the device, are filtered there (rpx_capture) and only the captured
@@ -424,7 +450,8 @@ def run_ours(args):
                    "parallelism": "source rays sharded by rank, scene replicated"},
         "e2e": {"value": e2e_value, "unit": "ray-segments/s",
                 "h2d_bytes_per_step": int(rays.shape[0] * rec), "d2h_bytes_per_step": int(d2h_records * rec),
-                "steps": e2e_steps},
+                "steps": e2e_steps, "api": "Engine.trace_streamed (rpx_trace_streamed), chunk %d rays" % args.chunk_rays,
+                "one_shot_value_this_rank": e2e_oneshot},
         "gpu_launches": int(launches_all),
         "clocks": sampler.summary(),
         "roofline": roofline,
@@ -563,6 +590,7 @@ def main():
     ap.add_argument("--workload", default="config2", choices=sorted(WORKLOADS))
     ap.add_argument("--rays", type=int, default=0, help="source rays per GPU (default: the config's)")
     ap.add_argument("--e2e-steps", type=int, default=5)
+    ap.add_argument("--chunk-rays", type=int, default=131072, help="source rays per chunk of the streamed e2e call")
     ap.add_argument("--ref-rays-per-core", type=int, default=200000)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--capture", action="store_true",

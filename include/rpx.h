@@ -372,6 +372,20 @@ void rpx_result_free(rpx_ctx* ctx, rpx_result* res);
  * with its own events); returned as void* to keep CUDA types out of the ABI. */
 void* rpx_stream(rpx_ctx* ctx);
 
+/* rpx_trace for a host-resident source cut into contiguous chunks of `chunk_rays` (0 = default):
+ * the upload of chunk c+1 and the download of chunk c's generations overlap the tracing (three
+ * streams, full-duplex PCIe), and the device holds two chunks at most -- also the way to trace a
+ * source larger than HBM.  Results are those of one rpx_trace call: out_gens[g] (caller memory,
+ * out_capacity[g] records; pinned memory for real overlap) receives generation g = the chunks'
+ * generation g concatenated in source order, parent_idx renumbered globally; out_counts[g] =
+ * len(traced_rays[g]); *n_gens = len(traced_rays) (<= max_gens, else RPX_ERR_INVALID; a too small
+ * buffer gives RPX_ERR_NOMEM); face_counts[n_traced_faces] = Face.count; *device_ms = summed
+ * device time of the generation loops.  (core/tracer.py:9-47 + the sharding of SURVEY 8e.)      */
+int rpx_trace_streamed(rpx_ctx* ctx, const void* rays_aos, uint64_t n, int is_gausslet, double max_length,
+                       int recursion_limit, uint64_t chunk_rays, void* const* out_gens,
+                       const uint64_t* out_capacity, int max_gens, uint64_t* out_counts, int* n_gens,
+                       uint32_t* face_counts, double* device_ms);
+
 /* ---------------------------------------------------------- capture planes
  * select_ray_intersections / select_gausslet_intersections (ctracer.pyx:1981-2058), the
  * filter behind probes.py RayCapturePlane / GaussletCapturePlane (:119-143): every ray of every

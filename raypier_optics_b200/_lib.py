@@ -23,7 +23,7 @@ EXPORTS = (
     "rpx_stream", "rpx_unit_face_intersect", "rpx_unit_face_normal", "rpx_unit_material_eval",
     "rpx_unit_distortion", "rpx_capture_scene_set", "rpx_result_rays", "rpx_capture",
     "rpx_field_prepare", "rpx_field_count", "rpx_field_modes", "rpx_field_evaluate",
-    "rpx_field_evaluate_device", "rpx_field_last_ms", "rpx_field_free",
+    "rpx_field_evaluate_device", "rpx_field_last_ms", "rpx_field_free", "rpx_trace_streamed",
 )
 
 
@@ -124,6 +124,8 @@ def load():
     L.rpx_field_last_ms.restype = d
     L.rpx_field_free.argtypes = [vp, vp]
     L.rpx_field_free.restype = None
+    L.rpx_trace_streamed.argtypes = [vp, vp, u64, i32, d, i32, u64, vp, vp, i32, vp, vp, vp, vp]
+    L.rpx_trace_streamed.restype = i32
     if L.rpx_abi_version() != A.RPX_ABI_VERSION:
         raise RuntimeError("librpx.so ABI %d != binding ABI %d" % (L.rpx_abi_version(), A.RPX_ABI_VERSION))
     _LIB = L

@@ -68,6 +68,9 @@ extern "C" int rpx_init(int device, rpx_ctx** out_ctx) {
     ctx->device = device;
     ctx->have_scene = false;
     ctx->scene_block = nullptr;
+    ctx->have_copy_streams = false;
+    for (int k = 0; k < 2; k++) { ctx->st_in[k] = nullptr; ctx->st_in_bytes[k] = 0; }
+    for (int k = 0; k < 4; k++) { ctx->st_out[k] = nullptr; ctx->st_out_bytes[k] = 0; ctx->st_out_busy[k] = false; }
     ctx->have_capture = false;
     ctx->cap_block = nullptr;
     ctx->cap_face_ids = nullptr;
@@ -125,6 +128,15 @@ extern "C" void rpx_shutdown(rpx_ctx* ctx) {
     cudaFreeHost(ctx->h_counts);
     cudaFree(ctx->d_count);
     cudaFreeHost(ctx->h_count);
+    if (ctx->have_copy_streams) {
+        for (int k = 0; k < 2; k++) if (ctx->st_in[k]) cudaFree(ctx->st_in[k]);
+        for (int k = 0; k < 4; k++) {
+            if (ctx->st_out[k]) cudaFree(ctx->st_out[k]);
+            cudaEventDestroy(ctx->st_out_done[k]);
+        }
+        cudaStreamDestroy(ctx->stream_in);
+        cudaStreamDestroy(ctx->stream_out);
+    }
     cudaStreamDestroy(ctx->stream);
     delete ctx;
 }
@@ -459,11 +471,11 @@ extern "C" int rpx_rays_download(rpx_ctx* ctx, const rpx_rays* rays, void* out_a
     if (rays->is_gausslet) {
         const int T = 64;
         k_soa_to_aos<RPX_WORDS_GAUSSLET, T><<<(unsigned)((n + T - 1) / T), T, T * RPX_GAUSSLET_BYTES, ctx->stream>>>(
-            rays->soa, (uint32_t*)d_aos);
+            rays->soa, (uint32_t*)d_aos, 0u);
     } else {
         const int T = 256;
         k_soa_to_aos<RPX_WORDS_RAY, T><<<(unsigned)((n + T - 1) / T), T, T * RPX_RAY_BYTES, ctx->stream>>>(
-            rays->soa, (uint32_t*)d_aos);
+            rays->soa, (uint32_t*)d_aos, 0u);
     }
     CU(ctx, cudaGetLastError());
     CU(ctx, cudaMemcpyAsync(out_aos, d_aos, n * rec, cudaMemcpyDeviceToHost, ctx->stream));
@@ -932,6 +944,185 @@ extern "C" int rpx_capture(rpx_ctx* ctx, const rpx_rays* const* gens, int n_gens
     if (counts)
         for (int j = 0; j < n_gens; j++) counts[j] = h_totals[(size_t)j + 1] - h_totals[(size_t)j];
     *out = dst;
+    return RPX_OK;
+}
+
+// ------------------------------------------------------------------ streamed trace
+// rpx_trace over a host-resident source that is cut into contiguous chunks: the upload of chunk
+// c+1 (stream_in) and the download of chunk c's generations (stream_out) overlap the tracing of
+// chunk c and each other, so PCIe runs full duplex and the device never holds more than two
+// chunks.  Same results as one rpx_trace call: generation g is the concatenation of the chunks'
+// generation g in source order (children are emitted in parent order) with parent_idx shifted
+// by the number of generation g-1 rays of earlier chunks -- the single-node form of the multi-GPU
+// sharding of SURVEY 8e.  It is also how a source larger than HBM is traced.
+static void launch_soa_to_aos(rpx_ctx* ctx, const rpx_rays* rays, void* d_aos, uint32_t parent_offset) {
+    const uint64_t n = rays->soa.n;
+    if (rays->is_gausslet) {
+        const int T = 64;
+        k_soa_to_aos<RPX_WORDS_GAUSSLET, T><<<(unsigned)((n + T - 1) / T), T, T * RPX_GAUSSLET_BYTES, ctx->stream>>>(
+            rays->soa, (uint32_t*)d_aos, parent_offset);
+    } else {
+        const int T = 256;
+        k_soa_to_aos<RPX_WORDS_RAY, T><<<(unsigned)((n + T - 1) / T), T, T * RPX_RAY_BYTES, ctx->stream>>>(
+            rays->soa, (uint32_t*)d_aos, parent_offset);
+    }
+}
+
+extern "C" int rpx_trace_streamed(rpx_ctx* ctx, const void* rays_aos, uint64_t n, int is_gausslet, double max_length,
+                                  int recursion_limit, uint64_t chunk_rays, void* const* out_gens,
+                                  const uint64_t* out_capacity, int max_gens, uint64_t* out_counts, int* n_gens,
+                                  uint32_t* face_counts, double* device_ms) {
+    if (!ctx || !out_gens || !out_capacity || !out_counts || !n_gens || max_gens <= 0 || (!rays_aos && n))
+        return fail(ctx, RPX_ERR_INVALID, "NULL argument");
+    if (!ctx->have_scene) return fail(ctx, RPX_ERR_STATE, "rpx_scene_set must be called before tracing");
+    CU(ctx, cudaSetDevice(ctx->device));
+    if (!ctx->have_copy_streams) {
+        CU(ctx, cudaStreamCreateWithFlags(&ctx->stream_in, cudaStreamNonBlocking));
+        CU(ctx, cudaStreamCreateWithFlags(&ctx->stream_out, cudaStreamNonBlocking));
+        for (int k = 0; k < 4; k++) CU(ctx, cudaEventCreateWithFlags(&ctx->st_out_done[k], cudaEventDisableTiming));
+        ctx->have_copy_streams = true;
+    }
+    if (chunk_rays == 0) chunk_rays = 262144;
+    const size_t rec = is_gausslet ? RPX_GAUSSLET_BYTES : RPX_RAY_BYTES;
+    const uint64_t n_chunks = n ? (n + chunk_rays - 1) / chunk_rays : 0;
+    for (int g = 0; g < max_gens; g++) out_counts[g] = 0;
+    *n_gens = 0;
+    std::vector<uint64_t> totals((size_t)max_gens, 0);
+    std::vector<uint32_t> fc((size_t)(ctx->n_traced > 0 ? ctx->n_traced : 1), 0);
+    double ms = 0.0;
+    void* d_in[2] = {nullptr, nullptr};
+    int ring = 0;  // next download staging buffer
+    cudaEvent_t ev_in[2], ev_used[2], ev_ready;
+    bool used_once[2] = {false, false};
+    int rc = RPX_OK;
+    cudaError_t e = cudaSuccess;
+    for (int k = 0; k < 2; k++) {
+        cudaEventCreateWithFlags(&ev_in[k], cudaEventDisableTiming);
+        cudaEventCreateWithFlags(&ev_used[k], cudaEventDisableTiming);
+    }
+    cudaEventCreateWithFlags(&ev_ready, cudaEventDisableTiming);
+    const uint64_t in_bytes = (n < chunk_rays ? n : chunk_rays) * rec;
+    if (n_chunks) {
+        for (int k = 0; k < (n_chunks > 1 ? 2 : 1) && e == cudaSuccess; k++) {
+            if (ctx->st_in_bytes[k] < in_bytes) {  // grow once; kept for later calls
+                if (ctx->st_in[k]) cudaFree(ctx->st_in[k]);
+                ctx->st_in[k] = nullptr;
+                ctx->st_in_bytes[k] = 0;
+                if ((e = cudaMalloc(&ctx->st_in[k], in_bytes)) == cudaSuccess) ctx->st_in_bytes[k] = in_bytes;
+            }
+            d_in[k] = ctx->st_in[k];
+        }
+        if (e != cudaSuccess) rc = fail(ctx, RPX_ERR_NOMEM, "chunk staging (%llu bytes): %s", (unsigned long long)in_bytes, cudaGetErrorString(e));
+    }
+    auto issue_upload = [&](uint64_t c) -> cudaError_t {
+        const int b = (int)(c & 1);
+        const uint64_t lo = c * chunk_rays, cnt = (n - lo < chunk_rays) ? n - lo : chunk_rays;
+        cudaError_t err = cudaSuccess;
+        if (used_once[b]) err = cudaStreamWaitEvent(ctx->stream_in, ev_used[b], 0);  // buffer b consumed by chunk c-2
+        if (err == cudaSuccess)
+            err = cudaMemcpyAsync(d_in[b], (const unsigned char*)rays_aos + lo * rec, cnt * rec, cudaMemcpyHostToDevice,
+                                  ctx->stream_in);
+        if (err == cudaSuccess) err = cudaEventRecord(ev_in[b], ctx->stream_in);
+        return err;
+    };
+    if (rc == RPX_OK && n_chunks && (e = issue_upload(0)) != cudaSuccess)
+        rc = fail(ctx, RPX_ERR_CUDA, "chunk upload: %s", cudaGetErrorString(e));
+    for (uint64_t c = 0; c < n_chunks && rc == RPX_OK; c++) {
+        const int b = (int)(c & 1);
+        const uint64_t lo = c * chunk_rays, cnt = (n - lo < chunk_rays) ? n - lo : chunk_rays;
+        if (c + 1 < n_chunks && (e = issue_upload(c + 1)) != cudaSuccess) {
+            rc = fail(ctx, RPX_ERR_CUDA, "chunk upload: %s", cudaGetErrorString(e));
+            break;
+        }
+        // AoS -> SoA on the compute stream once the chunk has landed
+        rpx_rays* r = nullptr;
+        if ((rc = rpx_rays_alloc(ctx, cnt, is_gausslet, &r)) != RPX_OK) break;
+        r->soa.n = cnt;
+        cudaStreamWaitEvent(ctx->stream, ev_in[b], 0);
+        if (is_gausslet) {
+            const int T = 64;
+            k_aos_to_soa<RPX_WORDS_GAUSSLET, T><<<(unsigned)((cnt + T - 1) / T), T, T * RPX_GAUSSLET_BYTES, ctx->stream>>>(
+                (const uint32_t*)d_in[b], r->soa);
+        } else {
+            const int T = 256;
+            k_aos_to_soa<RPX_WORDS_RAY, T><<<(unsigned)((cnt + T - 1) / T), T, T * RPX_RAY_BYTES, ctx->stream>>>(
+                (const uint32_t*)d_in[b], r->soa);
+        }
+        cudaEventRecord(ev_used[b], ctx->stream);
+        used_once[b] = true;
+        rpx_result* res = nullptr;
+        rc = rpx_trace_device(ctx, r, max_length, recursion_limit, RPX_TRACE_DEFAULT, &res);  // owns r
+        if (rc != RPX_OK) break;
+        ms += res->device_ms;
+        for (size_t i = 0; i < res->face_counts.size() && i < fc.size(); i++) fc[i] += res->face_counts[i];
+        const int ng = (int)res->gens.size();
+        if (ng > max_gens) {
+            rc = fail(ctx, RPX_ERR_INVALID, "trace produced %d generations, the caller provided %d output buffers", ng, max_gens);
+            rpx_result_free(ctx, res);
+            break;
+        }
+        for (int g = 0; g < ng && rc == RPX_OK; g++) {
+            const rpx_rays* gen = res->gens[(size_t)g];
+            const uint64_t m = gen ? gen->soa.n : 0;
+            if (!m) continue;
+            if (totals[(size_t)g] + m > out_capacity[g]) {
+                rc = fail(ctx, RPX_ERR_NOMEM, "output buffer of generation %d holds %llu records, needs more than %llu", g,
+                          (unsigned long long)out_capacity[g], (unsigned long long)(totals[(size_t)g] + m));
+                break;
+            }
+            // global parent index = local + rays of generation g-1 in earlier chunks (generation 0 keeps its own)
+            const uint32_t poff = g > 0 ? (uint32_t)(totals[(size_t)g - 1]) : 0u;
+            // next buffer of the download ring: wait (on the compute stream) until its previous
+            // D2H has left it, grow it if this generation is larger than anything seen so far
+            const int k = ring;
+            ring = (ring + 1) & 3;
+            if (ctx->st_out_busy[k]) cudaStreamWaitEvent(ctx->stream, ctx->st_out_done[k], 0);
+            if (ctx->st_out_bytes[k] < m * rec) {
+                if (ctx->st_out_busy[k]) cudaEventSynchronize(ctx->st_out_done[k]);
+                if (ctx->st_out[k]) cudaFree(ctx->st_out[k]);
+                ctx->st_out[k] = nullptr;
+                ctx->st_out_bytes[k] = 0;
+                const size_t want = (size_t)(m * rec) + (size_t)(m * rec) / 4;  // head room: later chunks vary
+                if ((e = cudaMalloc(&ctx->st_out[k], want)) != cudaSuccess) {
+                    rc = fail(ctx, RPX_ERR_NOMEM, "download staging (%zu bytes): %s", want, cudaGetErrorString(e));
+                    break;
+                }
+                ctx->st_out_bytes[k] = want;
+            }
+            void* d_stage = ctx->st_out[k];
+            launch_soa_to_aos(ctx, gen, d_stage, poff);
+            cudaEventRecord(ev_ready, ctx->stream);
+            cudaStreamWaitEvent(ctx->stream_out, ev_ready, 0);
+            e = cudaMemcpyAsync((unsigned char*)out_gens[g] + totals[(size_t)g] * rec, d_stage, m * rec,
+                                cudaMemcpyDeviceToHost, ctx->stream_out);
+            cudaEventRecord(ctx->st_out_done[k], ctx->stream_out);
+            ctx->st_out_busy[k] = true;
+            if (e != cudaSuccess) rc = fail(ctx, RPX_ERR_CUDA, "generation download: %s", cudaGetErrorString(e));
+        }
+        // offsets of the NEXT chunk are the totals including this one; update after all generations
+        // of this chunk used the old values for their parent offsets
+        if (rc == RPX_OK) {
+            std::vector<uint64_t> add((size_t)ng, 0);
+            for (int g = 0; g < ng; g++) add[(size_t)g] = res->gens[(size_t)g] ? res->gens[(size_t)g]->soa.n : 0;
+            for (int g = 0; g < ng; g++) totals[(size_t)g] += add[(size_t)g];
+            if (ng > *n_gens) *n_gens = ng;
+        }
+        rpx_result_free(ctx, res);  // generation buffers go back to the pool in compute-stream order
+    }
+    cudaStreamSynchronize(ctx->stream_out);
+    cudaStreamSynchronize(ctx->stream_in);
+    cudaStreamSynchronize(ctx->stream);
+    for (int k = 0; k < 4; k++) ctx->st_out_busy[k] = false;  // everything drained above
+    for (int k = 0; k < 2; k++) {
+        cudaEventDestroy(ev_in[k]);
+        cudaEventDestroy(ev_used[k]);
+    }
+    cudaEventDestroy(ev_ready);
+    if (rc != RPX_OK) return rc;
+    for (int g = 0; g < *n_gens; g++) out_counts[g] = totals[(size_t)g];
+    if (face_counts)
+        for (int i = 0; i < ctx->n_traced; i++) face_counts[i] = fc[(size_t)i];
+    if (device_ms) *device_ms = ms;
     return RPX_OK;
 }
 

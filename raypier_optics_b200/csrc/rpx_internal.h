@@ -26,6 +26,15 @@ struct KernelStat {
 struct rpx_ctx {
     int device;
     cudaStream_t stream;
+    cudaStream_t stream_in, stream_out;  // copy streams of rpx_trace_streamed (created on first use)
+    bool have_copy_streams;
+    // persistent staging of rpx_trace_streamed: 2 upload buffers, a ring of download buffers
+    void* st_in[2];
+    size_t st_in_bytes[2];
+    void* st_out[4];
+    size_t st_out_bytes[4];
+    cudaEvent_t st_out_done[4];  // D2H out of st_out[k] finished (recorded on stream_out)
+    bool st_out_busy[4];
     std::string err;
     // scene
     bool have_scene;

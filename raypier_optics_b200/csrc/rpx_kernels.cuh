@@ -71,7 +71,7 @@ __global__ void __launch_bounds__(TILE) k_aos_to_soa(const uint32_t* __restrict_
 }
 
 template <int WORDS, int TILE>
-__global__ void __launch_bounds__(TILE) k_soa_to_aos(Soa in, uint32_t* __restrict__ aos) {
+__global__ void __launch_bounds__(TILE) k_soa_to_aos(Soa in, uint32_t* __restrict__ aos, uint32_t parent_offset) {
     extern __shared__ uint32_t sm[];
     const unsigned long long base = (unsigned long long)blockIdx.x * TILE;
     const unsigned long long n = in.n;
@@ -87,7 +87,7 @@ __global__ void __launch_bounds__(TILE) k_soa_to_aos(Soa in, uint32_t* __restric
             rec[2 * k + 1] = (uint32_t)__double2hiint(v);
         }
 #pragma unroll
-        for (int k = 0; k < NU; k++) rec[2 * NF + k] = in.u[k * in.cap + i];
+        for (int k = 0; k < NU; k++) rec[2 * NF + k] = in.u[k * in.cap + i] + (k == U_PARENT ? parent_offset : 0u);
         if (WORDS == RPX_WORDS_GAUSSLET) {
 #pragma unroll 4
             for (int k = 0; k < NP; k++) {

@@ -286,6 +286,27 @@ class Engine(object):
                                       int(recursion_limit), int(flags), C.byref(h)))
         return TraceResult(self, h, is_g)
 
+    def trace_streamed(self, rays, max_length, recursion_limit, out, chunk_rays=0):
+        """``rpx_trace_streamed``: chunked trace with upload / trace / download overlapped.
+        ``out`` is a list of arrays (one per expected generation, ideally pinned) that receive the
+        generations.  Returns ``(generation views, face_counts, device_ms)``."""
+        rays = np.ascontiguousarray(rays)
+        is_g = self._is_gausslet(rays)
+        n_out = len(out)
+        for o in out:
+            assert o.dtype == rays.dtype and o.flags.c_contiguous
+        ptrs = (C.c_void_p * n_out)(*[o.ctypes.data for o in out])
+        caps = np.ascontiguousarray([o.shape[0] for o in out], dtype=np.uint64)
+        counts = np.zeros(n_out, dtype=np.uint64)
+        n_gens = C.c_int(0)
+        fc = np.zeros(max(self.n_traced_faces, 1), dtype=np.uint32)
+        ms = C.c_double(0.0)
+        self._check(self._L.rpx_trace_streamed(self._ctx, rays.ctypes.data, rays.shape[0], is_g, float(max_length),
+                                               int(recursion_limit), int(chunk_rays), ptrs, caps.ctypes.data, n_out,
+                                               counts.ctypes.data, C.byref(n_gens), fc.ctypes.data, C.byref(ms)))
+        gens = [out[g][:int(counts[g])] for g in range(n_gens.value)]
+        return gens, fc[:self.n_traced_faces].copy(), ms.value
+
     def trace_sequence(self, rays, face_seq, max_length, recursion_limit):
         """Sequential trace (``rpx_trace_sequence``): step s intersects only the face with
         global index ``face_seq[s]``."""
