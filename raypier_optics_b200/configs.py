@@ -399,7 +399,133 @@ def config4_cpc(core, n=100000, seed=45):
                 wavelengths=np.array([0.633]), max_length=120.0, recursion_limit=30)
 
 
+def config_zoo(core, n=20000, seed=17, gausslets=False):
+    """Parity "zoo": one station per face type / material class that the BASELINE configs do not
+    reach -- a row of independent optics 30 mm apart along x, lit from z = -50 by a wide strip of
+    jittered rays with three wavelengths, closed by two opaque stops.  Every face must be hit
+    (tests assert Face.count > 0), so the faces ElipticalPlane, ImplicitBoundedPlanar,
+    OrientedPolygon, OffAxisParabolic, Ellipsoidal, Saddle, Cylinderical, Axicon, ConicRevolution,
+    ExtendedPolynomial, ShapedSpherical, ShapedPlanar (with AND / OR / XOR / Invert / Polygon
+    shapes, Plane / Sphere / Cylinder / Difference / Intersection implicit surfaces) and the
+    materials Transparent, LinearPolarising, Waveplate, Dielectric, absorbing FullDielectric and
+    SingleLayerCoated (complex n: the general Fresnel / thin-film path), absorbing
+    FullDielectricDispersive, Circular / Rectangular aperture, PartiallyReflective and PEC are all
+    pinned against the reference."""
+    F, M, S, I = core.cfaces, core.cmaterials, core.cshapes, core.cimplicit_surfs
+    T = core.ctracer.Transform
+    pitch = 30.0
+    wl = np.array([0.5, 0.633, 0.85])
+    lists = []
+
+    def station(i, faces_fn, dx=0.0, **attrs):
+        owner = Pose(centre=(pitch * i + dx, 0., 0.), direction=(0., 0., 1.), **attrs)
+        lists.append(_facelist(core, owner, faces_fn(owner, (pitch * i, 0.0, 0.0))))
+
+    circ8 = S.CircleShape(radius=8.0)
+    station(0, lambda o, c: [F.ElipticalPlaneFace(owner=o, g_x=0.3, g_y=-0.2, diameter=16.0,
+                                                   material=M.PECMaterial())], diameter=16.0)
+    # inside the sphere, on one side of a plane, outside a tilted cylinder -- or in a small blob
+    # (Difference is the reference's arithmetic out -= v, cimplicit_surfs.pyx:191-194, so it is
+    # given a plane whose value stays small on the target plane)
+    boundary = I.Union(I.Intersection(I.Sphere(centre=(0., 0., 0.), radius=9.0),
+                                      I.Plane(origin=(6., 0., 0.), normal=(1., 0.2, 0.)),
+                                      I.Invert(I.Cylinder(origin=(-2., 1., 0.), axis=(0., 0.1, 1.), radius=2.5))),
+                       I.Difference(I.Sphere(centre=(7., 6., 1.), radius=2.0),
+                                    I.Plane(origin=(7., 6., 1.), normal=(0., 0., 1.))))
+    station(1, lambda o, c: [F.ImplicitBoundedPlanarFace(owner=o, target=I.Plane(origin=(0., 0., 1.), normal=(0.1, 0.05, 1.)),
+                                                         boundary=boundary, material=M.TransparentMaterial())])
+    hexagon = [(8 * math.cos(k * math.pi / 3), 8 * math.sin(k * math.pi / 3)) for k in range(6)]
+    station(2, lambda o, c: [F.OrientedPolygonFace(owner=o, origin=(0., 0., 0.5), normal=(0.2, 0.1, 1.0),
+                                                   x_axis=(1.0, 0.0, -0.2), xy_points=hexagon,
+                                                   material=M.LinearPolarisingMaterial())])
+    # off-axis paraboloid: the aperture is centred on local x = EFL, so the list sits EFL to the left
+    def oap(o, c):
+        f = F.OffAxisParabolicFace(owner=o, material=M.PECMaterial())
+        f.EFL, f.diameter, f.height = 40.0, 16.0, 25.0  # plain attributes in the reference (parabolics.py:43-47)
+        return [f]
+    station(3, oap, dx=-40.0)
+    ell = np.eye(4)
+    ell[:3, 3] = (0.0, 0.0, -20.0)  # local (0,0,0) lies on the ellipsoid (ellipse frame z = -minor)
+
+    def ellipsoid(o, c):
+        f = F.EllipsoidalFace(owner=o, material=M.PECMaterial())
+        return [f]
+    station(4, ellipsoid, ellipse_trans=_VtkLikeTransform(ell), axes=(30.0, 20.0), X_bounds=(-8.0, 8.0),
+            Y_bounds=(-8.0, 8.0), Z_bounds=(-5.0, 5.0))
+    station(5, lambda o, c: [F.SaddleFace(owner=o, shape=circ8, z_height=0.0, curvature=0.02,
+                                          material=M.DielectricMaterial(n_inside=1.5, n_outside=1.0))])
+    station(6, lambda o, c: [F.CylindericalFace(owner=o, shape=S.RectangleShape(centre=(0., 0.), width=14.0, height=12.0),
+                                                z_height=1.0, radius=40.0,
+                                                material=M.FullDielectricMaterial(n_inside=1.6 + 0.02j, n_outside=1.0,
+                                                                                  reflection_threshold=0.001,
+                                                                                  transmission_threshold=0.001))])
+    station(7, lambda o, c: [F.AxiconFace(owner=o, shape=circ8, z_height=0.0, gradient=0.08,
+                                          material=M.SingleLayerCoatedMaterial(n_inside=1.5 + 0.01j, n_outside=1.0,
+                                                                               n_coating=1.3 + 0.02j, thickness=0.12,
+                                                                               reflection_threshold=0.001,
+                                                                               transmission_threshold=0.001))])
+    r2 = math.sqrt(0.5)
+    station(8, lambda o, c: [F.ConicRevolutionFace(owner=o, shape=circ8, z_height=2.0, conic_const=-1.4, curvature=35.0,
+                                                   material=M.WaveplateMaterial(retardance=0.25, fast_axis=(r2, r2, 0.0)))])
+    coefs = np.array([[0.0, 0.0, 1e-2], [0.0, 2e-2, 0.0], [1e-2, 0.0, 0.0]])
+    station(9, lambda o, c: [F.ExtendedPolynomialFace(owner=o, shape=circ8, z_height=1.0, conic_const=-0.5, curvature=40.0,
+                                                      norm_radius=8.0, coefs=coefs,
+                                                      material=M.CircularApertureMaterial(outer_radius=8.0, radius=5.0,
+                                                                                          edge_width=1.0, origin=c))])
+    xor = S.BooleanXOR(circ8, S.RectangleShape(centre=(2.0, 0.0), width=6.0, height=4.0))
+    station(10, lambda o, c: [F.ShapedSphericalFace(owner=o, shape=xor, z_height=3.0, curvature=60.0,
+                                                    material=M.RectangularApertureMaterial(outer_width=16.0, outer_height=16.0,
+                                                                                           width=6.0, height=8.0, edge_width=1.5,
+                                                                                           origin=c))])
+    pentagon = [(8 * math.cos(0.3 + k * 2 * math.pi / 5), 8 * math.sin(0.3 + k * 2 * math.pi / 5)) for k in range(5)]
+    poly = S.PolygonShape()
+    poly.coordinates = np.ascontiguousarray(pentagon, dtype=np.double)  # the reference has no constructor keyword
+    shp = S.BooleanAND(S.InvertShape(S.CircleShape(centre=(0.0, 0.0), radius=2.0)),
+                       S.BooleanOR(poly, S.CircleShape(centre=(6.0, 0.0), radius=3.0)))
+    station(11, lambda o, c: [F.ShapedPlanarFace(owner=o, shape=shp, z_height=0.0,
+                                                 material=M.PartiallyReflectiveMaterial(reflectivity=0.3))])
+    absorbing = glass_curve(core, "N-SF11", absorption=5.0)
+    station(12, lambda o, c: [F.CircularFace(owner=o, z_plane=0.0,
+                                             material=M.FullDielectricDispersiveMaterial(
+                                                 dispersion_inside=absorbing, dispersion_outside=nondispersive(core, 1.0),
+                                                 reflection_threshold=0.001, transmission_threshold=0.001))],
+            diameter=16.0, offset=0.0)
+    n_st = 13
+    span = pitch * (n_st - 1)
+    stop_owner_back = Pose(centre=(span / 2, 0., 60.), direction=(0., 0., 1.), length=span + 80.0, width=80.0, offset=0.0)
+    stop_owner_front = Pose(centre=(span / 2, 0., -70.), direction=(0., 0., 1.), length=span + 80.0, width=80.0,
+                            offset=0.0)
+    for o in (stop_owner_back, stop_owner_front):
+        lists.append(_facelist(core, o, [F.RectangularFace(owner=o, length=span + 80.0, width=80.0, offset=0.0,
+                                                           z_plane=0.0, material=M.OpaqueMaterial())]))
+    rng = np.random.default_rng(seed)
+    rays = np.zeros(n, dtype=ray_dtype)
+    rays['origin'][:, 0] = rng.uniform(-10.0, span + 10.0, n)
+    rays['origin'][:, 1] = rng.uniform(-10.0, 10.0, n)
+    rays['origin'][:, 2] = -50.0
+    d = np.array([0.0, 0.0, 1.0])[None, :] + rng.normal(0.0, 0.01, size=(n, 3))
+    rays['direction'] = d / np.linalg.norm(d, axis=1)[:, None]
+    rays['E_vector'] = (1.0, 0.0, 0.0)
+    rays['E1_amp'] = 1.0
+    rays['E2_amp'] = 0.3 + 0.2j
+    rays['refractive_index'] = 1.0
+    rays['normal'] = (0.0, 1.0, 0.0)
+    rays['length'] = np.inf
+    rays['wavelength_idx'] = rng.integers(0, len(wl), size=n, dtype=np.uint32)
+    rays['ray_ident'] = np.arange(n, dtype=np.uint32)
+    if gausslets:
+        rays['ray_type_id'] = GAUSSLET
+        rays['length'] = 200.0
+        gc = core.ctracer.GaussletCollection.from_rays(rays)
+        gc.config_parabasal_rays(wl, 0.05, 0.0)
+        rays = gc.copy_as_array()
+    return dict(name="config_zoo", face_lists=lists, rays=rays, wavelengths=wl, max_length=200.0,
+                recursion_limit=8)
+
+
+
 CONFIGS = {
+    "zoo": config_zoo,
     "config1": config1_singlet,
     "config2": config2_achromat,
     "config3": config3_aspheric_zernike,

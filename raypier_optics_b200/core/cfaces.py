@@ -202,13 +202,15 @@ class OrientedPolygonFace(Face):
 
 
 class OffAxisParabolicFace(Face):
-    """cfaces.pyx:1224-1317"""
+    """cfaces.pyx:1224-1317.  As in the reference, EFL / diameter / height are plain public
+    attributes: the class has no __cinit__ of its own, so constructor keywords are swallowed by
+    Face and the owner assigns the attributes afterwards (raypier/parabolics.py:43-47)."""
 
     def __init__(self, **kwds):
         Face.__init__(self, **kwds)
-        self.EFL = kwds.get('EFL', 0.0)
-        self.diameter = kwds.get('diameter', 0.0)
-        self.height = kwds.get('height', 0.0)
+        self.EFL = 0.0
+        self.diameter = 0.0
+        self.height = 0.0
 
 
 class EllipsoidalFace(Face):
@@ -216,12 +218,13 @@ class EllipsoidalFace(Face):
 
     def __init__(self, **kwds):
         Face.__init__(self, **kwds)
-        self.major = kwds.get('major', 0.0)
-        self.minor = kwds.get('minor', 0.0)
+        # public attributes without constructor keywords in the reference (cfaces.pyx:1320-1342)
+        self.major = 0.0
+        self.minor = 0.0
         for b in ('x1', 'x2', 'y1', 'y2', 'z1', 'z2'):
-            setattr(self, b, kwds.get(b, 0.0))
-        self.transform = kwds.get('transform', Transform())
-        self.inverse_transform = kwds.get('inverse_transform', Transform())
+            setattr(self, b, 0.0)
+        self.transform = Transform()
+        self.inverse_transform = Transform()
 
     def update(self):
         Face.update(self)

@@ -599,6 +599,25 @@ RPX_DEV double sphere_hit(const DevScene& S, const rpx_face* f, vec3 r, vec3 p2,
 }
 
 // Face.intersect_c for the simple (non-wrapping) face classes.
+// Both roots of  qa x^2 + qb x + qc = 0  from its discriminant root sd = sqrt(qb^2 - 4 qa qc), without
+// the cancellation of the textbook form the reference uses ((-qb +- sd) / 2qa, e.g. cfaces.pyx:1262-1266):
+// the root whose numerator does not cancel comes from q = -(qb + sign(qb) sd) / 2, the other one is
+// qc / q.  For a ray that starts near the surface the reference's small root carries an error of
+// ~1e3..1e6 ulp; this one is good to a few ulp, so the CUDA result differs from the reference's by the
+// reference's own noise instead of adding to it.  *plus = (-qb + sd) / 2qa, *minus = (-qb - sd) / 2qa.
+RPX_DEV void quad_roots(double qa, double qb, double qc, double sd, double* plus, double* minus) {
+    const double q = -0.5 * (qb + copysign(sd, qb));
+    const double big = q / qa, small_ = qc / q;
+    if (q == 0.0) {  // qb == 0 and sd == 0: double root at 0 / 0 in this form -> textbook form
+        *plus = (-qb + sd) / (2 * qa);
+        *minus = (-qb - sd) / (2 * qa);
+        return;
+    }
+    // qb >= 0: q = -(qb + sd)/2 -> big = (-qb - sd)/2qa is the "minus" root
+    *plus = (qb >= 0.0) ? small_ : big;
+    *minus = (qb >= 0.0) ? big : small_;
+}
+
 template <int FC>
 __device__ double face_intersect_basic(const DevScene& S, const rpx_face* f, vec3 p1, vec3 p2,
                                        int is_base_ray) {
@@ -727,9 +746,9 @@ __device__ double face_intersect_basic(const DevScene& S, const rpx_face* f, vec
                 return a1 * sep(p1, p2);
             }
             d = sqrt_(d);
-            double a1 = (-b + d) / (2 * a);
+            double a1, a2;
+            quad_roots(a, b, c, d, &a1, &a2);
             vec3 pt1 = r + s * a1;
-            double a2 = (-b - d) / (2 * a);
             vec3 pt2 = r + s * a2;
             pt1.x -= efl;
             pt2.x -= efl;
@@ -756,8 +775,9 @@ __device__ double face_intersect_basic(const DevScene& S, const rpx_face* f, vec
             double c = A * (r.z * r.z + r.y * r.y) + B * r.x * r.x - A * B;
             double d = b * b - 4 * a * c;
             d = sqrt_(d);
-            double root1 = (-b + d) / (2 * a);
-            double root2 = (-b - d) / (2 * a);
+            double root1, root2;
+            if (d == d) quad_roots(a, b, c, d, &root1, &root2);
+            else root1 = root2 = d;  // negative discriminant: NaN roots, as in the reference (no test there)
             vec3 q2 = p1 + Sv * root2;
             vec3 q1 = p1 + Sv * root1;
             if (is_base_ray) {
@@ -794,12 +814,10 @@ __device__ double face_intersect_basic(const DevScene& S, const rpx_face* f, vec
                        2 * A * d.y * d.z * p.x + d.z * d.z;
                 if (root < 0) return RPX_NO_HIT;
                 root = sqrt_(root);
-                denom = 2 * A * (d.x * d.y);
-                a1 = a2 = -A * d.x * p.y - A * d.y * p.x + d.z;
-                a1 += root;
-                a2 -= root;
-                a1 /= denom;
-                a2 /= denom;
+                // A dx dy a^2 - t a + (A px py - pz) = 0 with t = -A dx py - A dy px + dz; the
+                // reference's (t +- root) / denom, evaluated without cancellation
+                const double t = -A * d.x * p.y - A * d.y * p.x + d.z;
+                quad_roots(A * (d.x * d.y), -t, A * (p.x * p.y) - p.z, root, &a1, &a2);
             }
             vec3 pt1 = p1 + d * a1;
             vec3 pt2 = p1 + d * a2;

@@ -31,6 +31,8 @@ GOLDEN_CASES = [
     ("config4_grating", dict(n=160), None),
     ("config5_rays", dict(n=96, gausslets=False), None),
     ("config5", dict(n=40, gausslets=True), None),
+    ("zoo_rays", dict(n=1560, gausslets=False), None),
+    ("zoo", dict(n=390, gausslets=True), None),
 ]
 
 
@@ -39,7 +41,10 @@ def main():
     core = O.import_reference("parity")
     if core is None:
         raise SystemExit("reference not built: run oracle/build_ref.sh first")
+    only = set(sys.argv[1:])  # optional: regenerate just these tags
     for tag, kw, rl in GOLDEN_CASES:
+        if only and tag not in only:
+            continue
         name = tag.replace("_lowthr", "").replace("_rays", "")
         cfg = build_case(core, name, kw, rl)
         sc = SC.Scene(cfg['face_lists'], cfg['wavelengths'])
