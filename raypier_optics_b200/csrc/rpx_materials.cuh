@@ -112,8 +112,16 @@ RPX_DEV void fresnel_emit(Kids& k, const RayIn& r, vec3 normal, vec3 in_directio
 // InterfaceMaterial.eval_child_ray_c for every material class.
 //   point           hit point, global coordinates
 //   onormal/otangent  FaceList.compute_orientation_c output (not yet normalised)
+#ifndef RPX_MAT_INLINE
+#define RPX_MAT_INLINE 0
+#endif
+#if RPX_MAT_INLINE
+#define RPX_MAT_ATTR __device__ __forceinline__
+#else
+#define RPX_MAT_ATTR __device__
+#endif
 template <uint32_t MM>
-__device__ void material_eval(const DevScene& S, const rpx_material* M, const RayIn& r, vec3 point,
+RPX_MAT_ATTR void material_eval(const DevScene& S, const rpx_material* M, const RayIn& r, vec3 point,
                               vec3 onormal, vec3 otangent, Kids& k) {
     const double* P = M->p;
     k.has_a = false;
