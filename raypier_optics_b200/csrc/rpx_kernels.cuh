@@ -361,7 +361,23 @@ k_capture(DevScene S, Soa in, Soa out, unsigned long long* tile_state, uint32_t*
 // (b) lets ANY thread of the block intersect ANY child (parents with 0 children help those
 // with 2), and (c) makes the final global stores fully coalesced (slot == consecutive
 // addresses) instead of stride-2.
+// RPX_FIXED_SLOTS=1: every thread stages its children the moment the material code has produced
+// them, into slots that depend only on the thread (reflected child: tid, transmitted child:
+// RPX_SLOT_B0 + tid), and a small map turns emission order into slot numbers for the trace-ahead
+// and the copy-out.  The ~58 registers of the two children then no longer live across the block
+// scan and its barrier.  RPX_SLOT_B0 = 136 = 128 + 8 keeps the two runs 64 B apart in the banks,
+// so a half-warp reading an a/b-interleaved run is still conflict free.
+// Measured on B200: no fewer spills (the register peak is inside the material code, not across
+// the scan) and SLOWER on config2 (0.136 vs 0.126 ms), equal on the Michelson -> off by default.
+#ifndef RPX_FIXED_SLOTS
+#define RPX_FIXED_SLOTS 0
+#endif
+#if RPX_FIXED_SLOTS
+#define RPX_SLOT_B0 (RPX_TILE + 8)
+#define RPX_SLOTS (2 * RPX_TILE + 8)
+#else
 #define RPX_SLOTS (2 * RPX_TILE)
+#endif
 #define RPX_STAGE_BYTES (RPX_SLOTS * (NF * 8 + NU * 4))
 
 RPX_DEV void stage_child(double* cs, uint32_t* cu, uint32_t slot, const Kids& k, const Kid& c, uint32_t wl,
@@ -428,6 +444,9 @@ k_shade(DevScene S, Soa in, Soa out, double max_length, unsigned long long* tile
     __shared__ uint32_t s_tile;
     __shared__ uint32_t s_warp[RPX_TILE / 32];
     __shared__ unsigned long long s_prefix;
+#if RPX_FIXED_SLOTS
+    __shared__ unsigned short s_map[2 * RPX_TILE];  // emission order -> staging slot
+#endif
     // dynamic shared memory: [child staging][scene copy]
     double* cs = reinterpret_cast<double*>(smem);
     uint32_t* cu = reinterpret_cast<uint32_t*>(smem + RPX_SLOTS * NF * 8);
@@ -517,6 +536,27 @@ k_shade(DevScene S, Soa in, Soa out, double max_length, unsigned long long* tile
         }
     }
 
+    const uint32_t parent = (uint32_t)i;
+#if RPX_FIXED_SLOTS
+    // ---- 2. stage the children at once (thread-fixed slots): nothing of them stays in registers
+    const uint32_t fix_a = threadIdx.x, fix_b = RPX_SLOT_B0 + threadIdx.x;
+    if (k.has_a) stage_child(cs, cu, fix_a, k, k.a, wl, parent, ident);
+    if (k.has_b) stage_child(cs, cu, fix_b, k, k.b, wl, parent, ident);
+    // ---- 3. counts -> emission order inside the tile (reflected, then transmitted); publish
+    const uint32_t cnt = (k.has_a ? 1u : 0u) + (k.has_b ? 1u : 0u);
+    uint32_t total;
+    const uint32_t local = block_exclusive_scan(cnt, &total, s_warp);
+    if (threadIdx.x == 0) {
+        tile_publish(tile_state, tile, total);
+        s_tile = next_tile;  // ... and hand it to the CTA (read after the next barrier)
+    }
+    const uint32_t slot_a = local, slot_b = local + (k.has_a ? 1u : 0u);  // emission positions
+    if (k.has_a) s_map[slot_a] = (unsigned short)fix_a;
+    if (k.has_b) s_map[slot_b] = (unsigned short)fix_b;
+    const uint32_t own_a = fix_a, own_b = fix_b;  // where this thread's children sit in the staging
+    __syncthreads();
+#define RPX_SRC(slot) ((uint32_t)s_map[slot])
+#else
     // ---- 2. counts -> offsets inside the tile; publish the tile aggregate
     const uint32_t cnt = (k.has_a ? 1u : 0u) + (k.has_b ? 1u : 0u);
     uint32_t total;
@@ -526,11 +566,13 @@ k_shade(DevScene S, Soa in, Soa out, double max_length, unsigned long long* tile
         s_tile = next_tile;  // ... and hand it to the CTA (read after the next barrier)
     }
     // ---- 3. stage children in emission order (reflected, then transmitted)
-    const uint32_t parent = (uint32_t)i;
     const uint32_t slot_a = local, slot_b = local + (k.has_a ? 1u : 0u);
     if (k.has_a) stage_child(cs, cu, slot_a, k, k.a, wl, parent, ident);
     if (k.has_b) stage_child(cs, cu, slot_b, k, k.b, wl, parent, ident);
+    const uint32_t own_a = slot_a, own_b = slot_b;
     __syncthreads();
+#define RPX_SRC(slot) (slot)
+#endif
     {   // pull the next tile's parent records towards L2 while this tile computes
         const uint32_t nt = s_tile;
         if (nt < n_tiles_real) {
@@ -569,26 +611,27 @@ k_shade(DevScene S, Soa in, Soa out, double max_length, unsigned long long* tile
     // ---- 4. trace ahead
     if (ahead_face != -2) {
         for (uint32_t slot = threadIdx.x; slot < total; slot += RPX_TILE) {
-            const double* f = cs + slot;
+            const uint32_t src = RPX_SRC(slot);
+            const double* f = cs + src;
             vec3 o = v3(f[F_OX * RPX_SLOTS], f[F_OY * RPX_SLOTS], f[F_OZ * RPX_SLOTS]);
             vec3 d = v3(f[F_DX * RPX_SLOTS], f[F_DY * RPX_SLOTS], f[F_DZ * RPX_SLOTS]);
             double len;
             uint32_t face;
             nearest_hit<FC>(S, o, d, max_length, ahead_face, &len, &face);
-            cs[F_LEN * RPX_SLOTS + slot] = len;
-            cu[U_ENDFACE * RPX_SLOTS + slot] = face;
+            cs[F_LEN * RPX_SLOTS + src] = len;
+            cu[U_ENDFACE * RPX_SLOTS + src] = face;
         }
     } else {
         // untraced: sp_ray.length = INF (every material; gausslets: reset_length_c -> max_length),
         // end_face_idx still the copy of the parent's (the face that was just hit)
         const double untraced_len = GAUSS ? max_length : RPX_INF;
         if (k.has_a) {
-            cs[F_LEN * RPX_SLOTS + slot_a] = untraced_len;
-            cu[U_ENDFACE * RPX_SLOTS + slot_a] = face_idx;
+            cs[F_LEN * RPX_SLOTS + own_a] = untraced_len;
+            cu[U_ENDFACE * RPX_SLOTS + own_a] = face_idx;
         }
         if (k.has_b) {
-            cs[F_LEN * RPX_SLOTS + slot_b] = untraced_len;
-            cu[U_ENDFACE * RPX_SLOTS + slot_b] = face_idx;
+            cs[F_LEN * RPX_SLOTS + own_b] = untraced_len;
+            cu[U_ENDFACE * RPX_SLOTS + own_b] = face_idx;
         }
     }
     // ---- 5. global offset of the tile
@@ -619,12 +662,13 @@ k_shade(DevScene S, Soa in, Soa out, double max_length, unsigned long long* tile
         for (int pass = 0; pass < 2; pass++) {
             const uint32_t slot = threadIdx.x + pass * RPX_TILE;
             if (slot < total) {
+                const uint32_t from = RPX_SRC(slot);
                 double* dst = out.f + base + slot;
-                const double* src = cs + slot;
+                const double* src = cs + from;
 #pragma unroll
                 for (int fld = 0; fld < NF; fld++) dst[(unsigned long long)fld * ocap] = src[fld * RPX_SLOTS];
                 uint32_t* dstu = out.u + base + slot;
-                const uint32_t* srcu = cu + slot;
+                const uint32_t* srcu = cu + from;
 #pragma unroll
                 for (int fld = 0; fld < NU; fld++) dstu[(unsigned long long)fld * ocap] = srcu[fld * RPX_SLOTS];
             }
