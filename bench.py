@@ -525,7 +525,7 @@ def run_fields(args):
     e2e = pairs * e2e_steps / (time.perf_counter() - t0)
     # fp64 roofline: instructions counted from the SASS of k_field_sum per pair,
     # peak = measured DFMA issue rate of this GPU (profiles/microbench/fp64_latency.cu)
-    fp64_per_pair = 143.0  # DFMA+DMUL+DADD+DSETP per pair in the SASS loop of k_field_sum (286 per 2-point iteration)
+    fp64_per_pair = 142.0  # DFMA+DMUL+DADD+DSETP per pair in the SASS loop of k_field_sum (284 per 2-point iteration of 431)
     peak_inst = 63.6 * 148 * 1.965e9 / 1e12  # T fp64 lane-instructions/s, measured
     ach = fp64_per_pair * value / 1e12
     cpu = None

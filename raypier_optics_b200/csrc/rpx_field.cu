@@ -40,6 +40,9 @@ enum {
 };
 static_assert(M_NF == 33, "mode record");
 
+#ifndef FIELD_LIBM
+#define FIELD_LIBM 0  // 1: library sincos / exp instead of the constant-bank versions below
+#endif
 #define FIELD_THREADS 128
 #define FIELD_PTS 2    // points per thread
 #define FIELD_STAGE 32 // mode records per shared-memory stage
@@ -154,6 +157,58 @@ __global__ void k_field_prepare(Soa in, const double* modes_in, const double* wa
 }
 
 // ------------------------------------------------------------------ the N_ray x N_pt sum
+// ---- sin / cos / exp of the inner loop ----------------------------------------------------------
+// The library sincos + exp are 30 % of k_field_sum (measured by stubbing them out), a good part of
+// it UMOV traffic that materialises their polynomial coefficients.  These versions keep the
+// coefficients in the constant bank (DFMA takes a c[][] operand directly) and fold the argument
+// reduction of the optical phase (|w| up to ~1e7 rad) into the quadrant reduction:
+//   n = rint(w * 2/pi);  r = w - n*pi/2 with pi/2 = hi + lo and exact products in the FMAs
+//   (|error| < 3e-16 rad for |n| < 2^30);  sin / cos on |r| <= pi/4 by the fdlibm minimax kernels
+//   (__kernel_sin / __kernel_cos coefficients, < 1 ulp);  exp(x) = 2^n * P13(x - n ln2), Taylor to
+//   degree 13 on |r| <= ln2 / 2 (truncation 4e-18), n clamped so underflow -> 0 and overflow -> inf.
+__constant__ double c_sin[6] = {-1.66666666666666324348e-01, 8.33333333332248946124e-03, -1.98412698298579493134e-04,
+                                2.75573137070700676789e-06, -2.50507602534068634195e-08, 1.58969099521155010221e-10};
+__constant__ double c_cos[6] = {4.16666666666666019037e-02, -1.38888888888741095749e-03, 2.48015872894767294178e-05,
+                                -2.75573143513906633035e-07, 2.08757232129817482790e-09, -1.13596475577881948265e-11};
+__constant__ double c_exp[12] = {1.0 / 2, 1.0 / 6, 1.0 / 24, 1.0 / 120, 1.0 / 720, 1.0 / 5040, 1.0 / 40320,
+                                 1.0 / 362880, 1.0 / 3628800, 1.0 / 39916800, 1.0 / 479001600, 1.0 / 6227020800.0};
+
+__device__ __forceinline__ void sincos_phase(double w, double* sn, double* cs) {
+    const double n = rint(w * 0.63661977236758138);  // 2 / pi
+    double r = fma(-n, 1.5707963267948966, w);
+    r = fma(-n, 6.123233995736766e-17, r);
+    const double z = r * r;
+    double ps = c_sin[5];
+    double pc = c_cos[5];
+#pragma unroll
+    for (int k = 4; k >= 0; k--) {
+        ps = fma(ps, z, c_sin[k]);
+        pc = fma(pc, z, c_cos[k]);
+    }
+    const double s = fma(r * z, ps, r);               // r + r^3 (S1 + ...)
+    const double c = fma(z * z, pc, fma(z, -0.5, 1.0));  // 1 - z/2 + z^2 (C1 + ...)
+    const int q = (int)(long long)n;                  // |n| < 2^31 for any physical phase
+    const double a = (q & 1) ? c : s;
+    const double b = (q & 1) ? s : c;
+    *sn = (q & 2) ? -a : a;
+    *cs = ((q + 1) & 2) ? -b : b;
+}
+
+__device__ __forceinline__ double exp_fast(double x) {
+    x = fmin(fmax(x, -746.0), 710.0);
+    const double n = rint(x * 1.4426950408889634);  // log2(e)
+    double r = fma(-n, 6.93147180369123816490e-01, x);  // ln2 hi (fdlibm split: low 32 bits zero)
+    r = fma(-n, 1.90821492927058770002e-10, r);     // ln2 lo
+    double p = c_exp[11];
+#pragma unroll
+    for (int k = 10; k >= 0; k--) p = fma(p, r, c_exp[k]);
+    p = fma(r * r, p, r + 1.0);                        // 1 + r + r^2 (1/2 + r/6 + ...)
+    // 2^n in two factors so that the result may be subnormal or overflow to inf like exp() does
+    const int ni = (int)n, h = ni / 2;
+    const double f1 = __hiloint2double((1023 + h) << 20, 0), f2 = __hiloint2double((1023 + ni - h) << 20, 0);
+    return p * f1 * f2;
+}
+
 // One (ray, point) pair: calc_mode_U (cfields.pyx:118-153) + the accumulation of :104-110.
 __device__ __forceinline__ void field_pair(const double* __restrict__ R, double Px, double Py, double Pz, double* acc) {
     const double px = Px - R[M_OX], py = Py - R[M_OY], pz = Pz - R[M_OZ];
@@ -184,11 +239,15 @@ __device__ __forceinline__ void field_pair(const double* __restrict__ R, double 
     const double kr = R[M_KR], ki = R[M_KI];
     const double wr = __dadd_rn(R[M_PH], __dsub_rn(__dmul_rn(kr, ar), __dmul_rn(ki, ai)));
     const double wi = fma(kr, ai, ki * ar);
+    double sn, cs;
+#if FIELD_LIBM
     const double nrot = rint(wr * 0.15915494309189535);  // 1 / (2 pi)
     double red = fma(-nrot, 6.283185307179586, wr);      // 2 pi = hi + lo, exact products in the FMAs
     red = fma(-nrot, 2.4492935982947064e-16, red);
-    double sn, cs;
     sincos(red, &sn, &cs);
+#else
+    sincos_phase(wr, &sn, &cs);
+#endif
     // U /= csqrt(i M):  s = csqrt(w), w = (-Mi, Mr), |w| = |M|;  1/s = conj(s) / |M|
     const double rabs = m2 * rinv;
     const double a = -Mi, b = Mr;
@@ -197,7 +256,11 @@ __device__ __forceinline__ void field_pair(const double* __restrict__ R, double 
     const double t = q * ti, u = 0.5 * b * ti;
     const double sr = (a >= 0.0) ? t : fabs(u);
     const double si = (a >= 0.0) ? u : copysign(t, b);
+#if FIELD_LIBM
     const double g = exp(-wi) * rinv;
+#else
+    const double g = exp_fast(-wi) * rinv;
+#endif
     // U' = g (cs + i sn) (sr - i si)
     const double ur = g * (cs * sr + sn * si), ui = g * (sn * sr - cs * si);
     // out[c] += U' * V[c]   (V = E1*W*E + E2*W*H: the E1*U*E.x + E2*U*H.x of :108-110, factored)
