@@ -166,33 +166,8 @@ __global__ void k_field_prepare(Soa in, const double* modes_in, const double* wa
 //   (|error| < 3e-16 rad for |n| < 2^30);  sin / cos on |r| <= pi/4 by the fdlibm minimax kernels
 //   (__kernel_sin / __kernel_cos coefficients, < 1 ulp);  exp(x) = 2^n * P13(x - n ln2), Taylor to
 //   degree 13 on |r| <= ln2 / 2 (truncation 4e-18), n clamped so underflow -> 0 and overflow -> inf.
-__constant__ double c_sin[6] = {-1.66666666666666324348e-01, 8.33333333332248946124e-03, -1.98412698298579493134e-04,
-                                2.75573137070700676789e-06, -2.50507602534068634195e-08, 1.58969099521155010221e-10};
-__constant__ double c_cos[6] = {4.16666666666666019037e-02, -1.38888888888741095749e-03, 2.48015872894767294178e-05,
-                                -2.75573143513906633035e-07, 2.08757232129817482790e-09, -1.13596475577881948265e-11};
 __constant__ double c_exp[12] = {1.0 / 2, 1.0 / 6, 1.0 / 24, 1.0 / 120, 1.0 / 720, 1.0 / 5040, 1.0 / 40320,
                                  1.0 / 362880, 1.0 / 3628800, 1.0 / 39916800, 1.0 / 479001600, 1.0 / 6227020800.0};
-
-__device__ __forceinline__ void sincos_phase(double w, double* sn, double* cs) {
-    const double n = rint(w * 0.63661977236758138);  // 2 / pi
-    double r = fma(-n, 1.5707963267948966, w);
-    r = fma(-n, 6.123233995736766e-17, r);
-    const double z = r * r;
-    double ps = c_sin[5];
-    double pc = c_cos[5];
-#pragma unroll
-    for (int k = 4; k >= 0; k--) {
-        ps = fma(ps, z, c_sin[k]);
-        pc = fma(pc, z, c_cos[k]);
-    }
-    const double s = fma(r * z, ps, r);               // r + r^3 (S1 + ...)
-    const double c = fma(z * z, pc, fma(z, -0.5, 1.0));  // 1 - z/2 + z^2 (C1 + ...)
-    const int q = (int)(long long)n;                  // |n| < 2^31 for any physical phase
-    const double a = (q & 1) ? c : s;
-    const double b = (q & 1) ? s : c;
-    *sn = (q & 2) ? -a : a;
-    *cs = ((q + 1) & 2) ? -b : b;
-}
 
 __device__ __forceinline__ double exp_fast(double x) {
     x = fmin(fmax(x, -746.0), 710.0);
@@ -246,7 +221,7 @@ __device__ __forceinline__ void field_pair(const double* __restrict__ R, double 
     red = fma(-nrot, 2.4492935982947064e-16, red);
     sincos(red, &sn, &cs);
 #else
-    sincos_phase(wr, &sn, &cs);
+    rpx::sincos_phase(wr, &sn, &cs);
 #endif
     // U /= csqrt(i M):  s = csqrt(w), w = (-Mi, Mr), |w| = |M|;  1/s = conj(s) / |M|
     const double rabs = m2 * rinv;

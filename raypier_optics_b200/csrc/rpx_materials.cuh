@@ -335,7 +335,7 @@ RPX_MAT_ATTR void material_eval(const DevScene& S, const rpx_material* M, const 
                 const double n2c2 = n2.re * cos2, n3c3 = n3.re * cos3;
                 const double a = dwc * (n2.re - sin2r * sin2r) * rcp(cos2);  // phi = -i a
                 double sa, ca;
-                sincos(a, &sa, &ca);
+                sincos_phase(a, &sa, &ca);
                 const double g = rcp((n2c2 * 4.0) * n3c3);
                 const cplx ep1 = cx(ca * g, -sa * g);
                 const double e2r = ca * ca - sa * sa, e2i = 2.0 * sa * ca;

@@ -145,9 +145,38 @@ RPX_DEV cplx csqrt_(cplx z) {
     if (x > 0.0) return cx(t, u);
     return cx(fabs(u), copysign(t, y));
 }
+// sin and cos of a large-magnitude phase: quadrant reduction with an exact-product FMA step
+// (pi/2 = hi + lo; |error| < 3e-16 rad for |n| < 2^30), then the fdlibm minimax kernels on
+// |r| <= pi/4 with the coefficients in the constant bank (no UMOV pairs, no Payne-Hanek path).
+static __constant__ double c_sin[6] = {-1.66666666666666324348e-01, 8.33333333332248946124e-03, -1.98412698298579493134e-04,
+                                2.75573137070700676789e-06, -2.50507602534068634195e-08, 1.58969099521155010221e-10};
+static __constant__ double c_cos[6] = {4.16666666666666019037e-02, -1.38888888888741095749e-03, 2.48015872894767294178e-05,
+                                -2.75573143513906633035e-07, 2.08757232129817482790e-09, -1.13596475577881948265e-11};
+RPX_DEV void sincos_phase(double w, double* sn, double* cs) {
+    const double n = rint(w * 0.63661977236758138);  // 2 / pi
+    double r = fma(-n, 1.5707963267948966, w);
+    r = fma(-n, 6.123233995736766e-17, r);
+    const double z = r * r;
+    double ps = c_sin[5];
+    double pc = c_cos[5];
+#pragma unroll
+    for (int k = 4; k >= 0; k--) {
+        ps = fma(ps, z, c_sin[k]);
+        pc = fma(pc, z, c_cos[k]);
+    }
+    const double s = fma(r * z, ps, r);               // r + r^3 (S1 + ...)
+    const double c = fma(z * z, pc, fma(z, -0.5, 1.0));  // 1 - z/2 + z^2 (C1 + ...)
+    const int q = (int)(long long)n;                  // |n| < 2^31 for any physical phase
+    const double a = (q & 1) ? c : s;
+    const double b = (q & 1) ? s : c;
+    *sn = (q & 2) ? -a : a;
+    *cs = ((q + 1) & 2) ? -b : b;
+}
+
+
 RPX_DEV cplx cexp_(cplx z) {
     double s, c;
-    sincos(z.im, &s, &c);
+    sincos_phase(z.im, &s, &c);
     if (z.re == 0.0) return cx(c, s);  // lossless media: the film phase is purely imaginary
     double e = exp(z.re);
     return cx(e * c, e * s);
