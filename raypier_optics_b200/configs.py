@@ -292,6 +292,31 @@ def config5_michelson(core, n=20000, seed=5, gausslets=True, radius=3.0):
     return out
 
 
+def config_big_scene(core, n=3000, seed=55, gausslets=False, n_baffles=250):
+    """The Michelson of config 5 inside a cage of `n_baffles` opaque ring-shaped stops (ShapedPlanarFace,
+    Circle AND NOT Circle): > 232 faces, i.e. scene tables beyond the 40 KB the kernels stage in
+    shared memory, so the trace runs the global-memory kernel instantiations (SS=false).  The stops sit
+    along both arms with apertures wider than the beam; the stray reflections of the cube faces end on
+    them."""
+    F, M, S = core.cfaces, core.cmaterials, core.cshapes
+    cfg = config5_michelson(core, n=n, seed=seed, gausslets=gausslets, radius=5.0)
+    face_lists = cfg['face_lists']
+    opaque = M.OpaqueMaterial()
+    ring = S.CircleShape(radius=9.0) & ~S.CircleShape(radius=4.0)
+    k = 0
+    for arm, (axis, lo, hi) in enumerate((((0., 1., 0.), 6.0, 19.0), ((1., 0., 0.), 6.0, 19.0))):
+        m = n_baffles // 2 if arm == 0 else n_baffles - n_baffles // 2
+        for j in range(m):
+            pos = lo + (hi - lo) * (j + 0.5) / m
+            centre = tuple(pos * a for a in axis)
+            owner = Pose(centre=centre, direction=axis)
+            face = F.ShapedPlanarFace(owner=owner, shape=ring, z_height=0.0, material=opaque)
+            face_lists.append(_facelist(core, owner, [face]))
+            k += 1
+    cfg['name'] = "config_big_scene" + ("" if gausslets else "_rays")
+    return cfg
+
+
 def config4_prisms(core, n=100000, seed=4):
     """Config 4 (TIR part): a rhomboid + a right-angle (Dove-like) prism built as
     extrusions with FullDielectricMaterial (examples/ctracer_demo_prisms.py), low
@@ -533,6 +558,7 @@ CONFIGS = {
     "config4_grating": config4_grating,
     "config4_cpc": config4_cpc,
     "config5": config5_michelson,
+    "big_scene": config_big_scene,
 }
 
 

@@ -293,8 +293,11 @@ static int scene_face_class(const rpx_scene* s) {
     return RPX_FC_SIMPLE;
 }
 
+// Bytes of scene tables the kernels stage in shared memory (faces, face-set transforms, materials);
+// 0 = they do not fit: the SS=false kernel instantiations read them from global memory instead.
 static int scene_smem_bytes(const rpx_scene* s) {
-    size_t smem = (size_t)s->n_faces * sizeof(rpx_face) + (size_t)s->n_face_sets * sizeof(rpx_face_set);
+    size_t smem = (size_t)s->n_faces * sizeof(rpx_face) + (size_t)s->n_face_sets * sizeof(rpx_face_set) +
+                  (size_t)s->n_materials * sizeof(rpx_material);
     return smem <= 40 * 1024 ? (int)smem : 0;
 }
 
@@ -571,18 +574,19 @@ static int trace_pipelined(rpx_ctx* ctx, rpx_rays* rays, double ml, int recursio
         const uint32_t n_tiles = (uint32_t)((bound + RPX_TILE - 1) / RPX_TILE);
         // look-back state: a fresh, already-zeroed slice per generation, so that NO memset sits
         // between two kernels; the zeroed frontier is pushed ahead in large steps
-        if (state_off + n_tiles > ctx->pipe_state_cap) {  // wrap: everything before is finished by then
+        const size_t state_words = rpx_state_words(n_tiles);
+        if (state_off + state_words > ctx->pipe_state_cap) {  // wrap: everything before is finished by then
             state_off = 0;
             zero_end = 0;
         }
-        if (state_off + n_tiles > zero_end) {
-            size_t want = state_off + (size_t)n_tiles * 6;
+        if (state_off + state_words > zero_end) {
+            size_t want = state_off + state_words * 6;
             if (want > ctx->pipe_state_cap) want = ctx->pipe_state_cap;
             CUP(cudaMemsetAsync(ctx->pipe_state + zero_end, 0, (want - zero_end) * sizeof(unsigned long long), st));
             zero_end = want;
         }
         unsigned long long* state = ctx->pipe_state + state_off;
-        state_off += n_tiles;
+        state_off += state_words;
         ShadeArgs sa;
         sa.S = ctx->ds;
         sa.in = bufs[g]->soa;
@@ -600,7 +604,7 @@ static int trace_pipelined(rpx_ctx* ctx, rpx_rays* rays, double ml, int recursio
         sa.h_count = ctx->h_counts_dev + (g + 1);
         cudaEvent_t b0 = next_event(ctx), b1 = next_event(ctx);
         CUP(cudaEventRecord(b0, st));
-        CUP(shade_launcher(is_g, ctx->face_class, ctx->mm_idx)(st, sa));
+        CUP(shade_launcher(is_g, ctx->face_class, ctx->mm_idx, smem > 0)(st, sa));
         CUP(cudaEventRecord(b1, st));  // also marks h_counts[g + 1] valid
         ev_s0.push_back(b0);
         ev_s1.push_back(b1);
@@ -745,15 +749,16 @@ static int trace_loop(rpx_ctx* ctx, rpx_rays* rays, double max_length, int recur
             int rc = rpx_rays_alloc(ctx, cap_child, is_g, &child);
             if (rc != RPX_OK) return bail(rc);
         }
-        if (n_wtiles > ctx->tile_state_cap) {
+        const size_t state_words = rpx_state_words(n_wtiles);
+        if (state_words > ctx->tile_state_cap) {
             if (ctx->tile_state) CUR(cudaFree(ctx->tile_state));
             ctx->tile_state = nullptr;
             ctx->tile_state_cap = 0;
-            size_t cap_t = (size_t)n_wtiles * 2;
+            size_t cap_t = state_words * 2;
             CUR(cudaMalloc(&ctx->tile_state, cap_t * sizeof(unsigned long long)));
             ctx->tile_state_cap = cap_t;
         }
-        CUR(cudaMemsetAsync(ctx->tile_state, 0, (size_t)n_wtiles * sizeof(unsigned long long), st));
+        CUR(cudaMemsetAsync(ctx->tile_state, 0, state_words * sizeof(unsigned long long), st));
         CUR(cudaMemsetAsync(ctx->tile_counter, 0, sizeof(uint32_t), st));
         cudaEvent_t b0 = next_event(ctx), b1 = next_event(ctx);
         CUR(cudaEventRecord(b0, st));
@@ -772,7 +777,7 @@ static int trace_loop(rpx_ctx* ctx, rpx_rays* rays, double max_length, int recur
             sa.ahead_face = !sequential ? -1 : (count + 1 < n_seq ? face_seq[count + 1] : -2);
             sa.n_dev = nullptr;
             sa.h_count = nullptr;
-            cudaError_t le = shade_launcher(is_g, ctx->face_class, ctx->mm_idx)(st, sa);
+            cudaError_t le = shade_launcher(is_g, ctx->face_class, ctx->mm_idx, smem > 0)(st, sa);
             CUR(le);
         }
         CUR(cudaEventRecord(b1, st));

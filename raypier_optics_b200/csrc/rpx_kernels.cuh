@@ -114,21 +114,30 @@ static __global__ void k_reset_length(Soa rays, double max_length) {
 }
 
 // ------------------------------------------------------------------ scene staging
-// Copy the face table and the face-set transforms into shared memory and re-point the
-// DevScene at them.  Falls back to global memory when the scene does not fit.
-RPX_DEV void stage_scene(DevScene& S, unsigned char* smem, int smem_bytes) {
+// Copy the face table, the face-set transforms and the material table into shared memory and
+// re-point the DevScene at them.  SS (scene-in-shared) is a template parameter and the copy is
+// unconditional, so the compiler can PROVE that S.faces / S.sets / S.mats point into shared memory
+// and emits LDS instead of generic LD (143 static LD -> 0 in k_shade; k_intersect 53 -> 47 us per
+// 1e6 rays).  The host guarantees the fit; a scene whose tables exceed the budget runs the SS=false
+// instantiations, which read the tables from global memory (compiled for the widest face class /
+// material mask only).
+template <bool SS>
+RPX_DEV void stage_scene(DevScene& S, unsigned char* smem) {
+    if (!SS) return;
     const int face_bytes = S.n_faces * (int)sizeof(rpx_face);
     const int set_bytes = S.n_sets * (int)sizeof(rpx_face_set);
-    if (face_bytes + set_bytes > smem_bytes) return;  // uniform across the grid
     uint32_t* dst = reinterpret_cast<uint32_t*>(smem);
     const uint32_t* srcf = reinterpret_cast<const uint32_t*>(S.faces);
     const uint32_t* srcs = reinterpret_cast<const uint32_t*>(S.sets);
-    const int fw = face_bytes / 4, sw = set_bytes / 4;
+    const uint32_t* srcm = reinterpret_cast<const uint32_t*>(S.mats);
+    const int fw = face_bytes / 4, sw = set_bytes / 4, mw = S.n_mats * (int)sizeof(rpx_material) / 4;
     for (int w = threadIdx.x; w < fw; w += blockDim.x) dst[w] = srcf[w];
     for (int w = threadIdx.x; w < sw; w += blockDim.x) dst[fw + w] = srcs[w];
+    for (int w = threadIdx.x; w < mw; w += blockDim.x) dst[fw + sw + w] = srcm[w];
     __syncthreads();
     S.faces = reinterpret_cast<const rpx_face*>(smem);
     S.sets = reinterpret_cast<const rpx_face_set*>(smem + face_bytes);
+    S.mats = reinterpret_cast<const rpx_material*>(smem + face_bytes + set_bytes);
 }
 
 // ------------------------------------------------------------------ nearest hit
@@ -187,11 +196,11 @@ __device__ __noinline__ void nearest_hit(
 // ------------------------------------------------------------------ k_intersect
 // Generation 0 only: later generations get their nearest hit from the k_shade launch that
 // creates them (the thread that just built a child still has it in registers).
-template <int FC>
+template <int FC, bool SS>
 __global__ void __launch_bounds__(RPX_TILE, 4)
-k_intersect(DevScene S, Soa rays, double max_length, int smem_bytes, int only_face) {
+k_intersect(DevScene S, Soa rays, double max_length, int only_face) {
     extern __shared__ __align__(16) unsigned char smem[];
-    stage_scene(S, smem, smem_bytes);
+    stage_scene<SS>(S, smem);
     const unsigned long long i = (unsigned long long)blockIdx.x * RPX_TILE + threadIdx.x;
     if (i >= rays.n) return;
     const unsigned long long cap = rays.cap;
@@ -282,6 +291,103 @@ RPX_DEV unsigned long long tile_lookback(unsigned long long* state, uint32_t til
     return excl;
 }
 
+// Two-level look-back (k_shade).  With a persistent grid ~600 tiles are in flight at once and they
+// run almost in lock step, so the nearest predecessor holding an inclusive PREFIX is usually a whole
+// wave back: the flat look-back above walks ~19 windows of 32 tiles, one L2 round trip each.  Here
+// every tile also adds its aggregate to the AGG word of its GROUP of 32 consecutive tiles
+// (bits 61..56 = tiles that have contributed, low 48 bits = their sum; one fire-and-forget atomic),
+// and the last tile of a group stores the group's inclusive PREFIX in a second word.  A look-back is
+// then three loads in flight together: the predecessors inside the own group, and the AGG / PREFIX
+// words of the 32 preceding GROUPS (1024 tiles) -- one round trip unless a predecessor has not
+// published yet.
+// State layout: [n_tiles tile words][n_groups AGG words][n_groups PREFIX words], all zero at launch.
+#ifndef RPX_LOOKBACK_GROUPS
+#define RPX_LOOKBACK_GROUPS 1
+#endif
+#ifndef RPX_GROUPS_GAUSS
+#define RPX_GROUPS_GAUSS 0
+#endif
+__host__ __device__ inline size_t rpx_state_words(size_t n_tiles) {
+#if RPX_LOOKBACK_GROUPS
+    return n_tiles + 2 * ((n_tiles + 31) / 32);
+#else
+    return n_tiles;
+#endif
+}
+#define RPX_GROUP_ONE (1ull << 56)
+#define RPX_GROUP_SUM_MASK ((1ull << 48) - 1)
+
+RPX_DEV void tile_publish_grouped(unsigned long long* state, unsigned long long* gagg, uint32_t tile, uint32_t total) {
+    st_relaxed(&state[tile], (tile == 0 ? RPX_FLAG_PREFIX : RPX_FLAG_AGG) | (unsigned long long)total);
+    atomicAdd(&gagg[tile >> 5], RPX_GROUP_ONE | (unsigned long long)total);
+}
+
+RPX_DEV unsigned long long tile_lookback_grouped(unsigned long long* state, unsigned long long* gagg,
+                                                 unsigned long long* gpre, uint32_t tile, uint32_t total) {
+    const int lane = threadIdx.x & 31;
+    const uint32_t g = tile >> 5, j = tile & 31u;
+    unsigned long long excl = 0;
+    if (tile != 0) {
+        // (A) predecessors inside the own group: lane l looks at tile - 1 - l
+        const bool own = (uint32_t)lane < j;
+        const unsigned long long* pa = &state[tile - 1 - (own ? lane : 0)];
+        // (B) preceding groups: lane l looks at group g - 1 - l; before group 0 = an empty PREFIX
+        long long gi = (long long)g - 1 - lane;
+        unsigned long long a = own ? ld_relaxed(pa) : RPX_FLAG_AGG;
+        unsigned long long bp = (gi >= 0) ? ld_relaxed(&gpre[gi]) : RPX_FLAG_PREFIX;
+        unsigned long long ba = (gi >= 0) ? ld_relaxed(&gagg[gi]) : 0ull;
+        // only the entries in front of the nearest PREFIX have to be there: wait for exactly those
+        unsigned pref_a;
+        for (;;) {
+            pref_a = __ballot_sync(0xffffffffu, own && (a >> 62) == 2);
+            const unsigned have = __ballot_sync(0xffffffffu, (a >> 62) != 0);
+            const unsigned need = pref_a ? ((1u << (__ffs(pref_a) - 1)) - 1u) : 0xffffffffu;
+            if ((have & need) == need) break;
+            if ((a >> 62) == 0) a = ld_relaxed(pa);
+        }
+        unsigned long long v = own ? (a & RPX_VAL_MASK) : 0ull;
+        if (pref_a) {
+            if (lane > __ffs(pref_a) - 1) v = 0;
+        }
+        bool done = (pref_a != 0);
+        while (!done) {
+            // a group is usable once its PREFIX is stored or all 32 of its tiles have contributed
+            unsigned pref_b;
+            for (;;) {
+                const bool is_pref = (bp >> 62) == 2;
+                const bool usable = is_pref || (ba >> 56) == 32ull;
+                pref_b = __ballot_sync(0xffffffffu, is_pref);
+                const unsigned have = __ballot_sync(0xffffffffu, usable);
+                const unsigned need = pref_b ? ((1u << (__ffs(pref_b) - 1)) - 1u) : 0xffffffffu;
+                if ((have & need) == need) break;
+                if (!usable) {
+                    bp = ld_relaxed(&gpre[gi]);
+                    ba = ld_relaxed(&gagg[gi]);
+                }
+            }
+            unsigned long long w = ((bp >> 62) == 2) ? (bp & RPX_VAL_MASK) : (ba & RPX_GROUP_SUM_MASK);
+            if (pref_b) {
+                if (lane > __ffs(pref_b) - 1) w = 0;
+                done = true;
+            }
+            v += w;
+            gi -= 32;
+            if (!done) {
+                bp = (gi >= 0) ? ld_relaxed(&gpre[gi]) : RPX_FLAG_PREFIX;
+                ba = (gi >= 0) ? ld_relaxed(&gagg[gi]) : 0ull;
+            }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        excl = v;
+    }
+    if (lane == 0) {
+        st_relaxed(&state[tile], RPX_FLAG_PREFIX | (excl + total));
+        if (j == 31u) st_relaxed(&gpre[g], RPX_FLAG_PREFIX | (excl + total));
+    }
+    return excl;
+}
+
 // ------------------------------------------------------------------ k_capture
 // select_ray_intersections / select_gausslet_intersections (ctracer.pyx:1981-2058) for ONE
 // collection: every ray is re-intersected between its origin and origin + direction * length
@@ -289,16 +395,16 @@ RPX_DEV unsigned long long tile_lookback(unsigned long long* state, uint32_t til
 // in input order (block scan + decoupled look-back, as k_shade) after the *d_base records already
 // captured from earlier collections.  The copy carries length = hit distance, end_face_idx =
 // the capture face's idx and the re-based wavelength index (:2004-2006, 2011-2014).
-template <bool GAUSS, int FC>
+template <bool GAUSS, int FC, bool SS>
 __global__ void __launch_bounds__(RPX_TILE, 4)
 k_capture(DevScene S, Soa in, Soa out, unsigned long long* tile_state, uint32_t* tile_counter,
           const unsigned long long* d_base, unsigned long long* d_next, uint32_t wl_offset, const uint32_t* wl_map,
-          const uint32_t* face_ids, int smem_bytes) {
+          const uint32_t* face_ids) {
     extern __shared__ __align__(16) unsigned char smem[];
     __shared__ uint32_t s_tile;
     __shared__ uint32_t s_warp[RPX_TILE / 32];
     __shared__ unsigned long long s_prefix;
-    stage_scene(S, smem, smem_bytes);
+    stage_scene<SS>(S, smem);
     if (threadIdx.x == 0) s_tile = atomicAdd(tile_counter, 1u);  // ticket order = start order: look-back cannot deadlock
     __syncthreads();
     const uint32_t tile = s_tile;
@@ -428,11 +534,11 @@ RPX_DEV void stage_child(double* cs, uint32_t* cu, uint32_t slot, const Kids& k,
 #ifndef RPX_MIN_BLOCKS
 #define RPX_MIN_BLOCKS 4
 #endif
-template <bool GAUSS, int FC, uint32_t MM>
+template <bool GAUSS, int FC, uint32_t MM, bool SS>
 __global__ void __launch_bounds__(RPX_TILE, RPX_MIN_BLOCKS)
 k_shade(DevScene S, Soa in, Soa out, double max_length, unsigned long long* tile_state,
         uint32_t* tile_counter, unsigned long long* d_count, uint32_t* face_counts, uint32_t n_tiles,
-        int smem_bytes, int ahead_face, const unsigned long long* n_dev, unsigned long long* h_count) {
+        int ahead_face, const unsigned long long* n_dev, unsigned long long* h_count) {
     // n_dev != NULL: the parent count is not known on the host yet (the launch was enqueued
     // before the previous generation's kernel finished): the grid covers an upper bound and the
     // real count is read here; surplus CTAs leave at once.
@@ -450,10 +556,10 @@ k_shade(DevScene S, Soa in, Soa out, double max_length, unsigned long long* tile
     // dynamic shared memory: [child staging][scene copy]
     double* cs = reinterpret_cast<double*>(smem);
     uint32_t* cu = reinterpret_cast<uint32_t*>(smem + RPX_SLOTS * NF * 8);
-    stage_scene(S, smem + RPX_STAGE_BYTES, smem_bytes);  // once per (persistent) CTA
+    stage_scene<SS>(S, smem + RPX_STAGE_BYTES);  // once per (persistent) CTA
     const unsigned long long n_in = n_dev ? *n_dev : in.n;
     const uint32_t n_tiles_real = (uint32_t)((n_in + RPX_TILE - 1) / RPX_TILE);
-    (void)n_tiles;
+    constexpr bool kGrouped = RPX_LOOKBACK_GROUPS && (!GAUSS || RPX_GROUPS_GAUSS);
     const unsigned long long cap = in.cap;
   // PERSISTENT CTA: the grid is one wave of resident CTAs; each pulls tiles from the ticket
   // counter until the (device-resident) tile count is exhausted.
@@ -464,8 +570,8 @@ k_shade(DevScene S, Soa in, Soa out, double max_length, unsigned long long* tile
     if (tile >= n_tiles_real) break;  // uniform per CTA; tickets are dense, so tiles [0, real) all run
     const unsigned long long i = (unsigned long long)tile * RPX_TILE + threadIdx.x;
     __syncthreads();  // everyone has read s_tile
-    // take the NEXT ticket now (its latency hides behind this tile's work) ...
     uint32_t next_tile = 0;
+    // take the NEXT ticket now (its latency hides behind this tile's work) ...
     if (threadIdx.x == 0) next_tile = atomicAdd(tile_counter, 1u);
 
     Kids k;
@@ -547,7 +653,10 @@ k_shade(DevScene S, Soa in, Soa out, double max_length, unsigned long long* tile
     uint32_t total;
     const uint32_t local = block_exclusive_scan(cnt, &total, s_warp);
     if (threadIdx.x == 0) {
-        tile_publish(tile_state, tile, total);
+        if (kGrouped)
+            tile_publish_grouped(tile_state, tile_state + n_tiles, tile, total);
+        else
+            tile_publish(tile_state, tile, total);
         s_tile = next_tile;  // ... and hand it to the CTA (read after the next barrier)
     }
     const uint32_t slot_a = local, slot_b = local + (k.has_a ? 1u : 0u);  // emission positions
@@ -562,7 +671,10 @@ k_shade(DevScene S, Soa in, Soa out, double max_length, unsigned long long* tile
     uint32_t total;
     const uint32_t local = block_exclusive_scan(cnt, &total, s_warp);
     if (threadIdx.x == 0) {
-        tile_publish(tile_state, tile, total);
+        if (kGrouped)
+            tile_publish_grouped(tile_state, tile_state + n_tiles, tile, total);
+        else
+            tile_publish(tile_state, tile, total);
         s_tile = next_tile;  // ... and hand it to the CTA (read after the next barrier)
     }
     // ---- 3. stage children in emission order (reflected, then transmitted)
@@ -637,7 +749,10 @@ k_shade(DevScene S, Soa in, Soa out, double max_length, unsigned long long* tile
     // ---- 5. global offset of the tile
 #if !RPX_LOOKBACK_EARLY
     if (threadIdx.x < 32) {
-        unsigned long long excl = tile_lookback(tile_state, tile, total);
+        const unsigned long long excl =
+            kGrouped ? tile_lookback_grouped(tile_state, tile_state + n_tiles,
+                                             tile_state + n_tiles + (n_tiles + 31) / 32, tile, total)
+                     : tile_lookback(tile_state, tile, total);
         if (threadIdx.x == 0) {
             s_prefix = excl;
             if (tile == n_tiles_real - 1) {  // len(new_rays)

@@ -17,7 +17,7 @@ struct ShadeArgs {
     unsigned long long* d_count;
     uint32_t* face_counts;
     uint32_t n_tiles;
-    int smem_bytes;
+    int smem_bytes;  // staged scene tables (0: the scene does not fit -> SS=false kernels)
     int ahead_face;  // -1 all faces, >= 0 one face, -2 no trace-ahead (see k_shade)
     const unsigned long long* n_dev;  // device-resident parent count (pipelined launches) or NULL
     unsigned long long* h_count;      // mapped host slot for len(new_rays) or NULL
@@ -40,8 +40,12 @@ cudaError_t launch_shade_g1_f1_m0(cudaStream_t st, const ShadeArgs& a);
 cudaError_t launch_shade_g1_f1_m1(cudaStream_t st, const ShadeArgs& a);
 cudaError_t launch_shade_g1_f1_m2(cudaStream_t st, const ShadeArgs& a);
 cudaError_t launch_shade_g1_f1_m3(cudaStream_t st, const ShadeArgs& a);
+// scene tables too large for shared memory: widest face class / material mask, tables in global memory
+cudaError_t launch_shade_g0_f1_m3_nss(cudaStream_t st, const ShadeArgs& a);
+cudaError_t launch_shade_g1_f1_m3_nss(cudaStream_t st, const ShadeArgs& a);
 typedef cudaError_t (*ShadeLauncher)(cudaStream_t, const ShadeArgs&);
-inline ShadeLauncher shade_launcher(int gauss, int fc, int mm_idx) {
+inline ShadeLauncher shade_launcher(int gauss, int fc, int mm_idx, bool scene_shared) {
+    if (!scene_shared) return gauss ? launch_shade_g1_f1_m3_nss : launch_shade_g0_f1_m3_nss;
     static const ShadeLauncher table[2][2][4] = {
         {{launch_shade_g0_f0_m0, launch_shade_g0_f0_m1, launch_shade_g0_f0_m2, launch_shade_g0_f0_m3},
          {launch_shade_g0_f1_m0, launch_shade_g0_f1_m1, launch_shade_g0_f1_m2, launch_shade_g0_f1_m3}},
@@ -49,6 +53,7 @@ inline ShadeLauncher shade_launcher(int gauss, int fc, int mm_idx) {
          {launch_shade_g1_f1_m0, launch_shade_g1_f1_m1, launch_shade_g1_f1_m2, launch_shade_g1_f1_m3}}};
     return table[gauss ? 1 : 0][fc ? 1 : 0][mm_idx & 3];
 }
+// smem == 0 selects the SS=false instantiation (face class FULL, tables in global memory)
 cudaError_t launch_intersect(int fc, cudaStream_t st, unsigned n_tiles, int smem, const DevScene& S, const Soa& rays,
                              double max_length, int only_face);
 

@@ -7,7 +7,15 @@
 #error "compile with -DRPX_I_GAUSS=0|1 -DRPX_I_FC=0|1 -DRPX_I_MM=0..3"
 #endif
 
+// RPX_I_SS=0: the instantiation for scenes whose tables do not fit in shared memory (suffix _nss)
+#ifndef RPX_I_SS
+#define RPX_I_SS 1
+#endif
+#if RPX_I_SS
 #define RPX_CAT_(a, b, c) launch_shade_g##a##_f##b##_m##c
+#else
+#define RPX_CAT_(a, b, c) launch_shade_g##a##_f##b##_m##c##_nss
+#endif
 #define RPX_CAT(a, b, c) RPX_CAT_(a, b, c)
 
 namespace rpx {
@@ -26,21 +34,28 @@ cudaError_t RPX_CAT(RPX_I_GAUSS, RPX_I_FC, RPX_I_MM)(cudaStream_t st, const Shad
     // dynamic shared memory = child staging (47 KB) + the scene copy: needs the > 48 KB opt-in.
     // Persistent grid: one wave of resident CTAs (SMs x occupancy), never more than the tiles.
     static int resident_ctas = 0;  // one device per process
-    const int dyn = RPX_STAGE_BYTES + a.smem_bytes;
-    auto kern = k_shade<(RPX_I_GAUSS != 0), RPX_I_FC, kMask>;
-    if (!resident_ctas) {
+    static int resident_dyn = -1;  // ... recomputed when another scene changes the shared-memory footprint
+    static bool attr_set = false;
+    const int dyn = RPX_STAGE_BYTES + (RPX_I_SS ? a.smem_bytes : 0);
+    auto kern = k_shade<(RPX_I_GAUSS != 0), RPX_I_FC, kMask, (RPX_I_SS != 0)>;
+    if (!attr_set) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                              RPX_STAGE_BYTES + 40 * 1024);
         if (e != cudaSuccess) return e;
+        attr_set = true;
+    }
+    if (resident_dyn != dyn) {
+        cudaError_t e;
         int dev = 0, sms = 0, per_sm = 0;
         if ((e = cudaGetDevice(&dev)) != cudaSuccess) return e;
         if ((e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev)) != cudaSuccess) return e;
         if ((e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, RPX_TILE, dyn)) != cudaSuccess) return e;
         resident_ctas = sms * (per_sm < 1 ? 1 : per_sm);
+        resident_dyn = dyn;
     }
     const unsigned grid = a.n_tiles < (unsigned)resident_ctas ? a.n_tiles : (unsigned)resident_ctas;
     kern<<<grid, RPX_TILE, dyn, st>>>(a.S, a.in, a.out, a.max_length, a.tile_state, a.tile_counter, a.d_count,
-                                      a.face_counts, a.n_tiles, a.smem_bytes, a.ahead_face, a.n_dev, a.h_count);
+                                      a.face_counts, a.n_tiles, a.ahead_face, a.n_dev, a.h_count);
     return cudaGetLastError();
 }
 

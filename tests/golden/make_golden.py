@@ -33,6 +33,9 @@ GOLDEN_CASES = [
     ("config5", dict(n=40, gausslets=True), None),
     ("zoo_rays", dict(n=1560, gausslets=False), None),
     ("zoo", dict(n=390, gausslets=True), None),
+    # > 232 faces: scene tables beyond the shared-memory staging budget (SS=false kernels)
+    ("big_scene_rays", dict(n=96, gausslets=False), None),
+    ("big_scene", dict(n=40, gausslets=True), None),
 ]
 
 

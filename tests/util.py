@@ -199,6 +199,10 @@ PARITY_CASES = [
     # every face type / material class the BASELINE configs do not reach (configs.config_zoo)
     ("zoo", dict(n=12000, gausslets=False), None),
     ("zoo", dict(n=6000, gausslets=True), None),
+    # Michelson in a cage of 250 stops: scene tables too large for shared-memory staging, so the CUDA
+    # path runs its global-memory (SS=false) kernel instantiations
+    ("big_scene", dict(n=3000, gausslets=False), None),
+    ("big_scene", dict(n=2000, gausslets=True), None),
 ]
 
 
