@@ -422,6 +422,26 @@ typedef struct rpx_field rpx_field;
  * wavelengths[n_wavelengths] in microns (the `wavelengths` argument, indexed by wavelength_idx). */
 int rpx_field_prepare(rpx_ctx* ctx, const rpx_rays* rays, const double* modes, const double* wavelengths,
                       int n_wavelengths, double blending, rpx_field** out);
+/* The plain-ray front end, eval_Efield_from_rays (raypier/core/fields.py:206-229):
+ *   project_to_sphere (fields.py:50-77) on a device-resident collection of plain rays, IN PLACE: every
+ *   ray whose line meets the sphere (centre[3], radius) is moved to the intersection with the most
+ *   negative path and its accumulated_path corrected by alpha * n.real.  selector (host, n bytes, may
+ *   be NULL) receives the reference's boolean `selector`; *n_selected (may be NULL) its sum.  The
+ *   reference returns rays[selector]; rays with selector 0 are left untouched here.              */
+int rpx_rays_project_to_sphere(rpx_ctx* ctx, rpx_rays* rays, const double* centre, double radius, uint8_t* selector,
+                               uint64_t* n_selected);
+/*   evaluate_neighbours (fields.py:80-111) -> cfields.evaluate_modes (cfields.pyx:217-228) -> mode
+ *   records: neighbours is the n x row_size int32 host array of RayCollection.neighbours
+ *   (ctracer.pyx:1084-1131; -1 = no neighbour; row_size must be 6); rays lacking a neighbour are
+ *   dropped (`mask`, fields.py:97), so rpx_field_count() = number of kept rays.  xy_out (host, may be
+ *   NULL) receives x, y, dx, dy of the kept rays as four consecutive n_kept x 6 blocks.           */
+int rpx_field_prepare_neighbours(rpx_ctx* ctx, const rpx_rays* rays, const int32_t* neighbours, int row_size,
+                                 const double* wavelengths, int n_wavelengths, double blending, double* xy_out,
+                                 rpx_field** out);
+/*   cfields.evaluate_modes(x, y, dx, dy, blending) (cfields.pyx:217-228) on explicit n x 6 host arrays;
+ *   modes_out is n x 3 complex128.                                                                 */
+int rpx_unit_evaluate_modes(rpx_ctx* ctx, const double* x, const double* y, const double* dx, const double* dy,
+                            uint64_t n, int row_size, double blending, double* modes_out);
 uint64_t rpx_field_count(const rpx_field* field);
 /* The (A, B, C) modes, n x 3 complex128 (fields.py ExtractGamma :196-203) */
 int rpx_field_modes(rpx_ctx* ctx, const rpx_field* field, double* modes_out);

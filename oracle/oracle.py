@@ -48,6 +48,10 @@ def lib():
         L.rpxo_evaluate_neighbours_gc.argtypes = [vp, u64, vp, vp, vp, vp]
         L.rpxo_evaluate_modes.argtypes = [vp, vp, vp, vp, u64, i, d, vp]
         L.rpxo_sum_gaussian_modes.argtypes = [vp, u64, vp, vp, vp, u64, d, vp]
+        L.rpxo_project_to_sphere.restype = u64
+        L.rpxo_project_to_sphere.argtypes = [vp, u64, vp, d, vp]
+        L.rpxo_evaluate_neighbours.restype = u64
+        L.rpxo_evaluate_neighbours.argtypes = [vp, u64, vp, i, vp, vp, vp, vp, vp]
         L.rpxo_face_intersect.restype = d
         L.rpxo_face_intersect.argtypes = [vp, i, vp, vp, i]
         L.rpxo_face_normal.argtypes = [vp, i, vp, vp]
@@ -263,6 +267,45 @@ def eval_Efield_from_gausslets(gausslets, points, wavelengths, blending=1.0, tim
     x, y, dx, dy = evaluate_neighbours_gc(g)
     modes = evaluate_modes(x, y, dx, dy, blending)
     return sum_gaussian_modes(np.ascontiguousarray(g['base_ray']), modes, wavelengths, points, time_ps)
+
+
+def project_to_sphere(rays, centre=(0, 0, 0), radius=10.0):
+    """core/fields.py:50-77 -> the selected rays, moved to the sphere (a copy, like rays[selector])."""
+    L = lib()
+    r = np.array(rays, dtype=A.ray_dtype, copy=True)
+    c = np.ascontiguousarray(centre, dtype=np.double).reshape(3)
+    sel = np.zeros(len(r), dtype=np.uint8)
+    L.rpxo_project_to_sphere(r.ctypes.data, len(r), c.ctypes.data, float(radius), sel.ctypes.data)
+    return r[sel.astype(bool)]
+
+
+def evaluate_neighbours(rays, neighbours_idx):
+    """core/fields.py:80-111 -> (rays[mask], x, y, dx, dy)."""
+    L = lib()
+    r = np.ascontiguousarray(rays)
+    assert r.dtype == A.ray_dtype
+    nb = np.ascontiguousarray(neighbours_idx, dtype=np.int32)
+    n, row = nb.shape
+    if n != len(r):  # numpy: boolean index did not match indexed array
+        raise IndexError("neighbours_idx has %d rows for %d rays" % (n, len(r)))
+    if nb.max(initial=-1) >= len(r):
+        raise IndexError("neighbour index out of bounds")
+    x, y, dx, dy = (np.zeros((n, row)) for _ in range(4))
+    mask = np.zeros(n, dtype=np.uint8)
+    k = L.rpxo_evaluate_neighbours(r.ctypes.data, n, nb.ctypes.data, row, x.ctypes.data, y.ctypes.data, dx.ctypes.data,
+                                   dy.ctypes.data, mask.ctypes.data)
+    return r[mask.astype(bool)], x[:k], y[:k], dx[:k], dy[:k]
+
+
+def eval_Efield_from_rays(rays, neighbours_idx, points, wavelengths, blending=1.0, time_ps=0.0,
+                          exit_pupil_offset=0.0, exit_pupil_centre=(0.0, 0.0, 0.0)):
+    """core/fields.py:206-229 on numpy arrays (rays = ray_collection.copy_as_array(), neighbours_idx =
+    ray_collection.neighbours)."""
+    rays = np.ascontiguousarray(rays)
+    projected = project_to_sphere(rays, exit_pupil_centre, exit_pupil_offset) if exit_pupil_offset else rays
+    kept, x, y, dx, dy = evaluate_neighbours(projected, neighbours_idx)
+    modes = evaluate_modes(x, y, dx, dy, blending)
+    return sum_gaussian_modes(np.ascontiguousarray(kept), modes, wavelengths, points, time_ps)
 
 
 def reference_fields(core):

@@ -2094,5 +2094,65 @@ void rpxo_sum_gaussian_modes(const rpx_ray* rays, uint64_t n_rays, const double*
 }
 
 
+/* ---- the plain-ray front end of the E-field summation: fields.py eval_Efield_from_rays (:206-229) */
+
+/* project_to_sphere, core/fields.py:50-77 (numpy there, a loop here with numpy's own association:
+ * .sum(axis=1) over three components is ((a0 + a1) + a2); a = 1 is folded as in the source).
+ * Rays are updated IN PLACE where the ray line meets the sphere (selector[i] = 1); rays with a negative
+ * discriminant are left untouched (selector[i] = 0; the reference returns rays[selector]).
+ * Returns the number of selected rays.                                                         */
+uint64_t rpxo_project_to_sphere(rpx_ray* rays, uint64_t n, const double* centre, double radius, uint8_t* selector) {
+    uint64_t kept = 0;
+    for (uint64_t i = 0; i < n; i++) {
+        rpx_ray* r = &rays[i];
+        double ox = r->origin[0] - centre[0], oy = r->origin[1] - centre[1], oz = r->origin[2] - centre[2];
+        double dx = r->direction[0], dy = r->direction[1], dz = r->direction[2];
+        double c = ((ox * ox + oy * oy) + oz * oz) - (radius * radius);
+        double b = 2 * ((dx * ox + dy * oy) + dz * oz);
+        double d = b * b - 4 * c;
+        selector[i] = (d >= 0.0);
+        if (!(d >= 0.0)) continue;
+        d = sqrt(d);
+        double root1 = (-b + d) / 2, root2 = (-b - d) / 2;
+        double alpha = root2 < root1 ? root2 : root1; /* .min(axis=1): most negative path */
+        r->origin[0] += alpha * dx;
+        r->origin[1] += alpha * dy;
+        r->origin[2] += alpha * dz;
+        r->accumulated_path += alpha * r->refractive_index[0];
+        kept++;
+    }
+    return kept;
+}
+
+/* evaluate_neighbours, core/fields.py:80-111: every ray with all `row` neighbours present (mask) gets the
+ * (x, y) of its neighbours projected along THEIR direction onto the plane through its own origin, in its
+ * (E, H = E x direction) basis, and the direction differences (dx, dy).  x, y, dx, dy are n_kept x row,
+ * written for the kept rays in order; mask is n bytes.  Returns n_kept.                         */
+uint64_t rpxo_evaluate_neighbours(const rpx_ray* rays, uint64_t n, const int32_t* nb, int row, double* x, double* y,
+                                  double* dx, double* dy, uint8_t* mask) {
+    uint64_t k = 0;
+    for (uint64_t i = 0; i < n; i++) {
+        int all = 1;
+        for (int j = 0; j < row; j++) all = all && (nb[i * row + j] >= 0);
+        mask[i] = (uint8_t)all;
+        if (!all) continue;
+        vec3 origin = ld3(rays[i].origin), direction = ld3(rays[i].direction), E = ld3(rays[i].E_vector);
+        vec3 H = cross(E, direction);
+        for (int j = 0; j < row; j++) {
+            const rpx_ray* q = &rays[nb[i * row + j]];
+            vec3 off = subvv(ld3(q->origin), origin), nd = ld3(q->direction);
+            double alpha = -dotprod(off, direction) / dotprod(nd, direction);
+            vec3 proj = addvv(off, multvs(nd, alpha));
+            x[k * row + j] = dotprod(proj, E);
+            y[k * row + j] = dotprod(proj, H);
+            double dz = dotprod(nd, direction);
+            dx[k * row + j] = dotprod(nd, E) / dz;
+            dy[k * row + j] = dotprod(nd, H) / dz;
+        }
+        k++;
+    }
+    return k;
+}
+
 int rpxo_sizeof_ray(void) { return (int)sizeof(rpx_ray); }
 int rpxo_sizeof_gausslet(void) { return (int)sizeof(rpx_gausslet); }

@@ -24,6 +24,7 @@ EXPORTS = (
     "rpx_unit_distortion", "rpx_capture_scene_set", "rpx_result_rays", "rpx_capture",
     "rpx_field_prepare", "rpx_field_count", "rpx_field_modes", "rpx_field_evaluate",
     "rpx_field_evaluate_device", "rpx_field_last_ms", "rpx_field_free", "rpx_trace_streamed",
+    "rpx_rays_project_to_sphere", "rpx_field_prepare_neighbours", "rpx_unit_evaluate_modes",
 )
 
 
@@ -112,6 +113,12 @@ def load():
     L.rpx_capture.restype = i32
     L.rpx_field_prepare.argtypes = [vp, vp, vp, vp, i32, d, pvp]
     L.rpx_field_prepare.restype = i32
+    L.rpx_rays_project_to_sphere.argtypes = [vp, vp, vp, d, vp, vp]
+    L.rpx_rays_project_to_sphere.restype = i32
+    L.rpx_field_prepare_neighbours.argtypes = [vp, vp, vp, i32, vp, i32, d, vp, pvp]
+    L.rpx_field_prepare_neighbours.restype = i32
+    L.rpx_unit_evaluate_modes.argtypes = [vp, vp, vp, vp, vp, u64, i32, d, vp]
+    L.rpx_unit_evaluate_modes.restype = i32
     L.rpx_field_count.argtypes = [vp]
     L.rpx_field_count.restype = u64
     L.rpx_field_modes.argtypes = [vp, vp, vp]

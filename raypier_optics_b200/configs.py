@@ -147,6 +147,42 @@ def disc_source(n, centre, axis, radius, seed, n_wavelengths=1, E_vector=None, E
     return rays
 
 
+def hex_grid_source(n_side=21, pitch=0.4, focus=80.0, wavelength_idx=0):
+    """Plain rays on a hexagonal lattice with their six-neighbour lists -- the input of
+    eval_Efield_from_rays (core/fields.py:206-229; HexagonalRayFieldSource-like, sources.py): a slightly
+    converging spherical wavefront (focus at z = `focus`), elliptical polarisation, rim rays with
+    missing neighbours (-1).  Returns (ray_dtype array, int32 N x 6 neighbour indices)."""
+    from ._abi import ray_dtype
+    idx = np.arange(n_side * n_side).reshape(n_side, n_side)
+    n = n_side * n_side
+    rays = np.zeros(n, dtype=ray_dtype)
+    nb = -np.ones((n, 6), dtype=np.int32)
+    offs = [(1, 0), (0, 1), (-1, 1), (-1, 0), (0, -1), (1, -1)]
+    for i in range(n_side):
+        for j in range(n_side):
+            k = idx[i, j]
+            x = pitch * (i + 0.5 * j - 0.75 * n_side)
+            y = pitch * (np.sqrt(3) / 2 * j - 0.43 * n_side)
+            rays['origin'][k] = (x, y, 0.0)
+            d = np.array([-x, -y, focus])
+            d /= np.sqrt((d ** 2).sum())
+            rays['direction'][k] = d
+            e = np.cross(d, np.cross([1.0, 0.0, 0.0], d))
+            rays['E_vector'][k] = e / np.sqrt((e ** 2).sum())
+            for m, (di, dj) in enumerate(offs):
+                ii, jj = i + di, j + dj
+                if 0 <= ii < n_side and 0 <= jj < n_side:
+                    nb[k, m] = idx[ii, jj]
+    rays['refractive_index'] = 1.0 + 0j
+    rays['E1_amp'] = 1.0
+    rays['E2_amp'] = 0.3j
+    rays['length'] = 100.0
+    rays['wavelength_idx'] = wavelength_idx
+    rays['accumulated_path'] = np.linspace(0.0, 0.01, n)
+    rays['end_face_idx'] = 0xFFFFFFFF
+    return rays, nb
+
+
 # ---------------------------------------------------------------------------------
 # Config builders.  Each returns a dict:
 #   face_lists, rays (ray_dtype | gausslet_dtype array), wavelengths, max_length,

@@ -38,3 +38,9 @@ def gausslet_modes(gausslets, blending=1.0, device=0):
         return fm.modes
     finally:
         fm.free()
+
+
+def evaluate_modes(neighbour_x, neighbour_y, dx, dy, blending=1.0, device=0):
+    """cfields.pyx:217-228: for N rays with the (x, y) of their six neighbours and the direction
+    differences (dx, dy), all N x 6, the N x 3 complex (A, B, C) of the fitted astigmatic Gaussian modes."""
+    return get_engine(device).evaluate_modes(neighbour_x, neighbour_y, dx, dy, blending)

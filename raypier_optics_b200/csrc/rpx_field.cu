@@ -24,6 +24,8 @@
 // with a two-constant FMA Cody-Waite step (|error| < 4e-16 rad for |x| < 2^40) so the library
 // sincos stays on its fast path instead of Payne-Hanek.
 #include <cstdio>
+#include <new>
+#include <vector>
 
 #include "rpx_internal.h"
 
@@ -88,8 +90,52 @@ __device__ void evaluate_one_mode(const double* x, const double* y, const double
     out[2] = cx((a00 * a01 * b1 - a12 * b0 - b2 * (a00 * a11 - a12)) / den, im2);
 }
 
-// The per-ray part of sum_gaussian_modes (cfields.pyx:74-97) plus, for gausslets, the mode fit
-// (fields.py:114-137 + cfields.pyx:217-228).
+// The per-ray part of sum_gaussian_modes (cfields.pyx:74-97): everything the inner loop needs of ray i
+// (already loaded: o, d, e) and its mode M, written as record `io`.
+__device__ void write_mode_record(const Soa& in, unsigned long long i, unsigned long long io, vec3 o, vec3 d, vec3 e,
+                                  double apath, const cplx* M, const double* wavelengths, int n_wl, double* rec,
+                                  double* modes_out) {
+    const unsigned long long cap = in.cap;
+    for (int k = 0; k < 3; k++) {
+        modes_out[io * 6 + 2 * k] = M[k].re;
+        modes_out[io * 6 + 2 * k + 1] = M[k].im;
+    }
+    // IEEE sqrt / division here: per-ray work, accuracy over speed
+    const double einv = 1.0 / sqrt(mag_sq(e));
+    const vec3 E = v3(e.x * einv, e.y * einv, e.z * einv);  // norm_(ray.E_vector)
+    vec3 H = cross(d, E);                                   // norm_(cross_(ray.direction, E))
+    const double hinv = 1.0 / sqrt(mag_sq(H));
+    H = v3(H.x * hinv, H.y * hinv, H.z * hinv);
+    const uint32_t wl = in.u[U_WL * cap + i];
+    const double k = (wl < (uint32_t)n_wl) ? (2000.0 * M_PI) / wavelengths[wl] : __longlong_as_double(0x7ff8000000000000LL);
+    const double n_re = in.f[F_NR * cap + i], n_im = in.f[F_NI * cap + i];
+    // phase = ray.phase + accumulated_path*k  (the - c*k/n term carries time_ps: applied per evaluate)
+    const double ph0 = __dadd_rn(in.f[F_PHASE * cap + i], __dmul_rn(apath, k));
+    const double kr = n_re * k, ki = n_im * k;
+    const double invk = 2.0 / kr;
+    const double inv_root_area = sqrt(sqrt(M[0].im * M[2].im - M[1].im * M[1].im) * (2.0 / M_PI));
+    const cplx A = cx(M[0].re, M[0].im * invk), B = cx(M[1].re, M[1].im * invk), C = cx(M[2].re, M[2].im * invk);
+    const cplx G = A * C - B * B;  // detG0
+    const cplx S = A + C;
+    const double rt = sqrt(0.5);   // rootI = csqrt(i) = (sqrt(1/2), sqrt(1/2))
+    const cplx W = cx(inv_root_area * rt, inv_root_area * rt);
+    const cplx W1 = cx(in.f[F_E1R * cap + i], in.f[F_E1I * cap + i]) * W;
+    const cplx W2 = cx(in.f[F_E2R * cap + i], in.f[F_E2I * cap + i]) * W;
+    double* r = rec + io * M_NF;
+    r[M_EX] = E.x; r[M_EY] = E.y; r[M_EZ] = E.z;
+    r[M_HX] = H.x; r[M_HY] = H.y; r[M_HZ] = H.z;
+    r[M_DX] = d.x; r[M_DY] = d.y; r[M_DZ] = d.z;
+    r[M_OX] = o.x; r[M_OY] = o.y; r[M_OZ] = o.z;
+    r[M_KR] = kr; r[M_KI] = ki; r[M_PH] = ph0; r[M_K] = k; r[M_NRE] = n_re;
+    r[M_AR] = A.re; r[M_AI] = A.im; r[M_BR] = B.re; r[M_BI] = B.im; r[M_CR] = C.re; r[M_CI] = C.im;
+    r[M_GR] = G.re; r[M_GI] = G.im; r[M_SR] = S.re; r[M_SI] = S.im;
+    r[M_V0R] = W1.re * E.x + W2.re * H.x; r[M_V0I] = W1.im * E.x + W2.im * H.x;
+    r[M_V1R] = W1.re * E.y + W2.re * H.y; r[M_V1I] = W1.im * E.y + W2.im * H.y;
+    r[M_V2R] = W1.re * E.z + W2.re * H.z; r[M_V2I] = W1.im * E.z + W2.im * H.z;
+}
+
+// Mode records of a whole collection; for gausslets the mode is fitted first (fields.py:114-137 +
+// cfields.pyx:217-228).
 template <bool FROM_PARA>
 __global__ void k_field_prepare(Soa in, const double* modes_in, const double* wavelengths, int n_wl, double blending,
                                 double* rec, double* modes_out) {
@@ -118,42 +164,95 @@ __global__ void k_field_prepare(Soa in, const double* modes_in, const double* wa
     } else {
         for (int k = 0; k < 3; k++) M[k] = cx(modes_in[i * 6 + 2 * k], modes_in[i * 6 + 2 * k + 1]);
     }
+    write_mode_record(in, i, i, o, d, e, in.f[F_APATH * cap + i], M, wavelengths, n_wl, rec, modes_out);
+}
+
+// ---- plain rays with neighbour lists: eval_Efield_from_rays (core/fields.py:206-229) -------------
+// project_to_sphere (fields.py:50-77), in place on the SoA collection: origin += alpha * direction,
+// accumulated_path += alpha * n.real with alpha the most negative root of the ray-line / sphere
+// quadratic; rays that miss the sphere are left alone and flagged 0 in `selector`.
+__global__ void k_project_to_sphere(Soa rays, double cx_, double cy_, double cz_, double radius, unsigned char* selector,
+                                    unsigned long long* n_selected) {
+    const unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= rays.n) return;
+    const unsigned long long cap = rays.cap;
+    const double ox = rays.f[F_OX * cap + i] - cx_, oy = rays.f[F_OY * cap + i] - cy_, oz = rays.f[F_OZ * cap + i] - cz_;
+    const double dx = rays.f[F_DX * cap + i], dy = rays.f[F_DY * cap + i], dz = rays.f[F_DZ * cap + i];
+    const double c = ((ox * ox + oy * oy) + oz * oz) - radius * radius;
+    const double b = 2 * ((dx * ox + dy * oy) + dz * oz);
+    double disc = b * b - 4 * c;
+    const bool ok = disc >= 0.0;
+    selector[i] = ok ? 1 : 0;
+    if (!ok) return;
+    disc = sqrt(disc);
+    const double alpha = fmin((-b + disc) / 2, (-b - disc) / 2);
+    rays.f[F_OX * cap + i] += alpha * dx;
+    rays.f[F_OY * cap + i] += alpha * dy;
+    rays.f[F_OZ * cap + i] += alpha * dz;
+    rays.f[F_APATH * cap + i] += alpha * rays.f[F_NR * cap + i];
+    atomicAdd(n_selected, 1ull);
+}
+
+// evaluate_neighbours (fields.py:80-111) -> evaluate_modes (cfields.pyx:217-228) -> mode record, one
+// thread per ray; pos[i] = index among the rays that have all six neighbours, or -1 (dropped, :97).
+// xy (may be NULL) receives x, y, dx, dy of the kept rays as four n_kept x 6 blocks.
+__global__ void k_field_prepare_nb(Soa in, const int* nb, const long long* pos, unsigned long long n_kept,
+                                   const double* wavelengths, int n_wl, double blending, double* rec, double* modes_out,
+                                   double* xy) {
+    const unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= in.n) return;
+    const long long io = pos[i];
+    if (io < 0) return;
+    const unsigned long long cap = in.cap;
+    const vec3 o = v3(in.f[F_OX * cap + i], in.f[F_OY * cap + i], in.f[F_OZ * cap + i]);
+    const vec3 d = v3(in.f[F_DX * cap + i], in.f[F_DY * cap + i], in.f[F_DZ * cap + i]);
+    const vec3 e = v3(in.f[F_EX * cap + i], in.f[F_EY * cap + i], in.f[F_EZ * cap + i]);
+    const vec3 H0 = cross(e, d);  // numpy.cross(E, direction), fields.py:101
+    double x[RPX_NPARA], y[RPX_NPARA], dx[RPX_NPARA], dy[RPX_NPARA];
+#pragma unroll
+    for (int j = 0; j < RPX_NPARA; j++) {
+        const unsigned long long q = (unsigned long long)nb[i * RPX_NPARA + j];
+        const vec3 off = v3(in.f[F_OX * cap + q], in.f[F_OY * cap + q], in.f[F_OZ * cap + q]) - o;
+        const vec3 nd = v3(in.f[F_DX * cap + q], in.f[F_DY * cap + q], in.f[F_DZ * cap + q]);
+        const double dz = dot(nd, d);
+        const double alpha = -dot(off, d) / dz;
+        const vec3 proj = off + nd * alpha;
+        x[j] = dot(proj, e);
+        y[j] = dot(proj, H0);
+        dx[j] = dot(nd, e) / dz;
+        dy[j] = dot(nd, H0) / dz;
+        if (xy) {
+            const unsigned long long blk = n_kept * RPX_NPARA, at = (unsigned long long)io * RPX_NPARA + j;
+            xy[at] = x[j];
+            xy[blk + at] = y[j];
+            xy[2 * blk + at] = dx[j];
+            xy[3 * blk + at] = dy[j];
+        }
+    }
+    cplx M[3];
+    evaluate_one_mode(x, y, dx, dy, blending, M);
+    write_mode_record(in, i, (unsigned long long)io, o, d, e, in.f[F_APATH * cap + i], M, wavelengths, n_wl, rec, modes_out);
+}
+
+// cfields.evaluate_modes (cfields.pyx:217-228) on explicit n x 6 arrays
+__global__ void k_evaluate_modes(const double* x, const double* y, const double* dx, const double* dy, unsigned long long n,
+                                 double blending, double* modes_out) {
+    const unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    double xs[RPX_NPARA], ys[RPX_NPARA], dxs[RPX_NPARA], dys[RPX_NPARA];
+#pragma unroll
+    for (int j = 0; j < RPX_NPARA; j++) {
+        xs[j] = x[i * RPX_NPARA + j];
+        ys[j] = y[i * RPX_NPARA + j];
+        dxs[j] = dx[i * RPX_NPARA + j];
+        dys[j] = dy[i * RPX_NPARA + j];
+    }
+    cplx M[3];
+    evaluate_one_mode(xs, ys, dxs, dys, blending, M);
     for (int k = 0; k < 3; k++) {
         modes_out[i * 6 + 2 * k] = M[k].re;
         modes_out[i * 6 + 2 * k + 1] = M[k].im;
     }
-    // IEEE sqrt / division here: per-ray work, accuracy over speed
-    const double einv = 1.0 / sqrt(mag_sq(e));
-    const vec3 E = v3(e.x * einv, e.y * einv, e.z * einv);  // norm_(ray.E_vector)
-    vec3 H = cross(d, E);                                   // norm_(cross_(ray.direction, E))
-    const double hinv = 1.0 / sqrt(mag_sq(H));
-    H = v3(H.x * hinv, H.y * hinv, H.z * hinv);
-    const uint32_t wl = in.u[U_WL * cap + i];
-    const double k = (wl < (uint32_t)n_wl) ? (2000.0 * M_PI) / wavelengths[wl] : __longlong_as_double(0x7ff8000000000000LL);
-    const double n_re = in.f[F_NR * cap + i], n_im = in.f[F_NI * cap + i];
-    // phase = ray.phase + accumulated_path*k  (the - c*k/n term carries time_ps: applied per evaluate)
-    const double ph0 = __dadd_rn(in.f[F_PHASE * cap + i], __dmul_rn(in.f[F_APATH * cap + i], k));
-    const double kr = n_re * k, ki = n_im * k;
-    const double invk = 2.0 / kr;
-    const double inv_root_area = sqrt(sqrt(M[0].im * M[2].im - M[1].im * M[1].im) * (2.0 / M_PI));
-    const cplx A = cx(M[0].re, M[0].im * invk), B = cx(M[1].re, M[1].im * invk), C = cx(M[2].re, M[2].im * invk);
-    const cplx G = A * C - B * B;  // detG0
-    const cplx S = A + C;
-    const double rt = sqrt(0.5);   // rootI = csqrt(i) = (sqrt(1/2), sqrt(1/2))
-    const cplx W = cx(inv_root_area * rt, inv_root_area * rt);
-    const cplx W1 = cx(in.f[F_E1R * cap + i], in.f[F_E1I * cap + i]) * W;
-    const cplx W2 = cx(in.f[F_E2R * cap + i], in.f[F_E2I * cap + i]) * W;
-    double* r = rec + i * M_NF;
-    r[M_EX] = E.x; r[M_EY] = E.y; r[M_EZ] = E.z;
-    r[M_HX] = H.x; r[M_HY] = H.y; r[M_HZ] = H.z;
-    r[M_DX] = d.x; r[M_DY] = d.y; r[M_DZ] = d.z;
-    r[M_OX] = o.x; r[M_OY] = o.y; r[M_OZ] = o.z;
-    r[M_KR] = kr; r[M_KI] = ki; r[M_PH] = ph0; r[M_K] = k; r[M_NRE] = n_re;
-    r[M_AR] = A.re; r[M_AI] = A.im; r[M_BR] = B.re; r[M_BI] = B.im; r[M_CR] = C.re; r[M_CI] = C.im;
-    r[M_GR] = G.re; r[M_GI] = G.im; r[M_SR] = S.re; r[M_SI] = S.im;
-    r[M_V0R] = W1.re * E.x + W2.re * H.x; r[M_V0I] = W1.im * E.x + W2.im * H.x;
-    r[M_V1R] = W1.re * E.y + W2.re * H.y; r[M_V1I] = W1.im * E.y + W2.im * H.y;
-    r[M_V2R] = W1.re * E.z + W2.re * H.z; r[M_V2I] = W1.im * E.z + W2.im * H.z;
 }
 
 // ------------------------------------------------------------------ the N_ray x N_pt sum
@@ -357,6 +456,142 @@ extern "C" int rpx_field_prepare(rpx_ctx* ctx, const rpx_rays* rays, const doubl
     d_modes_in = nullptr;
     if ((e = cudaStreamSynchronize(ctx->stream)) != cudaSuccess) return bail(e, "k_field_prepare");
     *out = f;
+    return RPX_OK;
+}
+
+extern "C" int rpx_rays_project_to_sphere(rpx_ctx* ctx, rpx_rays* rays, const double* centre, double radius,
+                                          uint8_t* selector, uint64_t* n_selected) {
+    if (!ctx || !rays || !centre) return fail(ctx, RPX_ERR_INVALID, "NULL argument");
+    if (rays->is_gausslet) return fail(ctx, RPX_ERR_INVALID, "project_to_sphere takes plain rays (ray_t)");
+    CU(ctx, cudaSetDevice(ctx->device));
+    const uint64_t n = rays->soa.n;
+    if (n_selected) *n_selected = 0;
+    if (!n) return RPX_OK;
+    unsigned char* d_sel = nullptr;
+    unsigned long long* d_cnt = nullptr;
+    CU(ctx, cudaMallocAsync((void**)&d_sel, n + sizeof(unsigned long long) + 8, ctx->stream));
+    d_cnt = reinterpret_cast<unsigned long long*>(d_sel + ((n + 7) / 8) * 8);
+    cudaError_t e = cudaMemsetAsync(d_cnt, 0, sizeof(unsigned long long), ctx->stream);
+    if (e == cudaSuccess) {
+        k_project_to_sphere<<<(unsigned)((n + 127) / 128), 128, 0, ctx->stream>>>(rays->soa, centre[0], centre[1], centre[2],
+                                                                                  radius, d_sel, d_cnt);
+        e = cudaGetLastError();
+    }
+    unsigned long long cnt = 0;
+    if (e == cudaSuccess) e = cudaMemcpyAsync(&cnt, d_cnt, sizeof(cnt), cudaMemcpyDeviceToHost, ctx->stream);
+    if (e == cudaSuccess && selector) e = cudaMemcpyAsync(selector, d_sel, n, cudaMemcpyDeviceToHost, ctx->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    cudaFreeAsync(d_sel, ctx->stream);
+    if (e != cudaSuccess) return fail(ctx, RPX_ERR_CUDA, "project_to_sphere failed: %s", cudaGetErrorString(e));
+    if (n_selected) *n_selected = cnt;
+    return RPX_OK;
+}
+
+extern "C" int rpx_field_prepare_neighbours(rpx_ctx* ctx, const rpx_rays* rays, const int32_t* neighbours, int row_size,
+                                            const double* wavelengths, int n_wavelengths, double blending,
+                                            double* xy_out, rpx_field** out) {
+    if (!ctx || !rays || !wavelengths || !out || n_wavelengths <= 0 || (!neighbours && rays->soa.n))
+        return fail(ctx, RPX_ERR_INVALID, "NULL argument");
+    *out = nullptr;
+    if (rays->is_gausslet) return fail(ctx, RPX_ERR_INVALID, "neighbour lists belong to plain rays (ray_t)");
+    if (row_size != RPX_NPARA)
+        return fail(ctx, RPX_ERR_UNSUPPORTED, "neighbour lists of %d entries per ray (only 6 are supported)", row_size);
+    CU(ctx, cudaSetDevice(ctx->device));
+    const uint64_t n = rays->soa.n;
+    // mask = (neighbours_idx >= 0).all(axis=1) and the position of every kept ray (fields.py:97)
+    std::vector<long long> pos(n ? n : 1);
+    uint64_t kept = 0;
+    for (uint64_t i = 0; i < n; i++) {
+        bool all = true;
+        for (int j = 0; j < RPX_NPARA; j++) {
+            const int32_t q = neighbours[i * RPX_NPARA + j];
+            if (q >= 0 && (uint64_t)q >= n)
+                return fail(ctx, RPX_ERR_INVALID, "neighbour index %d of ray %llu is out of bounds for %llu rays", q,
+                            (unsigned long long)i, (unsigned long long)n);
+            all = all && q >= 0;
+        }
+        pos[i] = all ? (long long)kept++ : -1;
+    }
+    rpx_field* f = new (std::nothrow) rpx_field();
+    if (!f) return fail(ctx, RPX_ERR_NOMEM, "out of host memory");
+    f->n = kept;
+    f->rec = nullptr;
+    f->modes = nullptr;
+    f->last_ms = 0.f;
+    const size_t nk = kept ? kept : 1, nn = n ? n : 1;
+    double* d_wl = nullptr;
+    double* d_xy = nullptr;
+    int* d_nb = nullptr;
+    long long* d_pos = nullptr;
+    cudaError_t e;
+    auto release = [&]() {
+        if (d_wl) cudaFreeAsync(d_wl, ctx->stream);
+        if (d_xy) cudaFreeAsync(d_xy, ctx->stream);
+        if (d_nb) cudaFreeAsync(d_nb, ctx->stream);
+        if (d_pos) cudaFreeAsync(d_pos, ctx->stream);
+    };
+    auto bail = [&](cudaError_t err, const char* what) {
+        if (f->rec) cudaFreeAsync(f->rec, ctx->stream);
+        if (f->modes) cudaFreeAsync(f->modes, ctx->stream);
+        release();
+        delete f;
+        return fail(ctx, err == cudaErrorMemoryAllocation ? RPX_ERR_NOMEM : RPX_ERR_CUDA, "%s failed: %s", what,
+                    cudaGetErrorString(err));
+    };
+    if ((e = cudaMallocAsync((void**)&f->rec, nk * M_NF * sizeof(double), ctx->stream)) != cudaSuccess ||
+        (e = cudaMallocAsync((void**)&f->modes, nk * 6 * sizeof(double), ctx->stream)) != cudaSuccess ||
+        (e = cudaMallocAsync((void**)&d_wl, sizeof(double) * (size_t)n_wavelengths, ctx->stream)) != cudaSuccess ||
+        (e = cudaMallocAsync((void**)&d_nb, nn * RPX_NPARA * sizeof(int), ctx->stream)) != cudaSuccess ||
+        (e = cudaMallocAsync((void**)&d_pos, nn * sizeof(long long), ctx->stream)) != cudaSuccess ||
+        (xy_out && (e = cudaMallocAsync((void**)&d_xy, nk * 4 * RPX_NPARA * sizeof(double), ctx->stream)) != cudaSuccess))
+        return bail(e, "cudaMallocAsync");
+    if ((e = cudaMemcpyAsync(d_wl, wavelengths, sizeof(double) * (size_t)n_wavelengths, cudaMemcpyHostToDevice,
+                             ctx->stream)) != cudaSuccess)
+        return bail(e, "cudaMemcpyAsync(wavelengths)");
+    if (n) {
+        if ((e = cudaMemcpyAsync(d_nb, neighbours, n * RPX_NPARA * sizeof(int), cudaMemcpyHostToDevice, ctx->stream)) !=
+                cudaSuccess ||
+            (e = cudaMemcpyAsync(d_pos, pos.data(), n * sizeof(long long), cudaMemcpyHostToDevice, ctx->stream)) != cudaSuccess)
+            return bail(e, "neighbour upload");
+        k_field_prepare_nb<<<(unsigned)((n + 127) / 128), 128, 0, ctx->stream>>>(rays->soa, d_nb, d_pos, kept, d_wl,
+                                                                                 n_wavelengths, blending, f->rec, f->modes,
+                                                                                 d_xy);
+        if ((e = cudaGetLastError()) != cudaSuccess) return bail(e, "k_field_prepare_nb launch");
+        if (xy_out && kept &&
+            (e = cudaMemcpyAsync(xy_out, d_xy, kept * 4 * RPX_NPARA * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream)) !=
+                cudaSuccess)
+            return bail(e, "neighbour coordinates download");
+    }
+    if ((e = cudaStreamSynchronize(ctx->stream)) != cudaSuccess) return bail(e, "k_field_prepare_nb");  // pos / nb stay alive
+    release();
+    *out = f;
+    return RPX_OK;
+}
+
+extern "C" int rpx_unit_evaluate_modes(rpx_ctx* ctx, const double* x, const double* y, const double* dx, const double* dy,
+                                       uint64_t n, int row_size, double blending, double* modes_out) {
+    if (!ctx || ((!x || !y || !dx || !dy || !modes_out) && n)) return fail(ctx, RPX_ERR_INVALID, "NULL argument");
+    if (row_size != RPX_NPARA)
+        return fail(ctx, RPX_ERR_UNSUPPORTED, "%d neighbours per ray (only 6 are supported)", row_size);
+    if (!n) return RPX_OK;
+    CU(ctx, cudaSetDevice(ctx->device));
+    double* d_in = nullptr;
+    const size_t blk = n * RPX_NPARA;
+    CU(ctx, cudaMallocAsync((void**)&d_in, (4 * blk + n * 6) * sizeof(double), ctx->stream));
+    double* d_modes = d_in + 4 * blk;
+    const double* src[4] = {x, y, dx, dy};
+    cudaError_t e = cudaSuccess;
+    for (int k = 0; k < 4 && e == cudaSuccess; k++)
+        e = cudaMemcpyAsync(d_in + k * blk, src[k], blk * sizeof(double), cudaMemcpyHostToDevice, ctx->stream);
+    if (e == cudaSuccess) {
+        k_evaluate_modes<<<(unsigned)((n + 127) / 128), 128, 0, ctx->stream>>>(d_in, d_in + blk, d_in + 2 * blk, d_in + 3 * blk,
+                                                                               n, blending, d_modes);
+        e = cudaGetLastError();
+    }
+    if (e == cudaSuccess) e = cudaMemcpyAsync(modes_out, d_modes, n * 6 * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    cudaFreeAsync(d_in, ctx->stream);
+    if (e != cudaSuccess) return fail(ctx, RPX_ERR_CUDA, "evaluate_modes failed: %s", cudaGetErrorString(e));
     return RPX_OK;
 }
 

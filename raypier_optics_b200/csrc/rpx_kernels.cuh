@@ -196,8 +196,10 @@ __device__ __noinline__ void nearest_hit(
 // ------------------------------------------------------------------ k_intersect
 // Generation 0 only: later generations get their nearest hit from the k_shade launch that
 // creates them (the thread that just built a child still has it in registers).
+// Simple face classes fit 80 registers (6 CTAs / SM: 0.047 -> 0.045 ms per 1e6 rays, prisms 0.084 -> 0.078);
+// the Newton / quadric code of the full class keeps 128.
 template <int FC, bool SS>
-__global__ void __launch_bounds__(RPX_TILE, 4)
+__global__ void __launch_bounds__(RPX_TILE, FC == RPX_FC_SIMPLE ? 6 : 4)
 k_intersect(DevScene S, Soa rays, double max_length, int only_face) {
     extern __shared__ __align__(16) unsigned char smem[];
     stage_scene<SS>(S, smem);
@@ -534,6 +536,9 @@ RPX_DEV void stage_child(double* cs, uint32_t* cu, uint32_t slot, const Kids& k,
 #ifndef RPX_MIN_BLOCKS
 #define RPX_MIN_BLOCKS 4
 #endif
+#ifndef RPX_BULK_PREFETCH
+#define RPX_BULK_PREFETCH 1
+#endif
 template <bool GAUSS, int FC, uint32_t MM, bool SS>
 __global__ void __launch_bounds__(RPX_TILE, RPX_MIN_BLOCKS)
 k_shade(DevScene S, Soa in, Soa out, double max_length, unsigned long long* tile_state,
@@ -569,7 +574,7 @@ k_shade(DevScene S, Soa in, Soa out, double max_length, unsigned long long* tile
     const uint32_t tile = s_tile;
     if (tile >= n_tiles_real) break;  // uniform per CTA; tickets are dense, so tiles [0, real) all run
     const unsigned long long i = (unsigned long long)tile * RPX_TILE + threadIdx.x;
-    __syncthreads();  // everyone has read s_tile
+    // (s_tile is next written by thread 0 after the barrier inside the block scan: no barrier needed here)
     uint32_t next_tile = 0;
     // take the NEXT ticket now (its latency hides behind this tile's work) ...
     if (threadIdx.x == 0) next_tile = atomicAdd(tile_counter, 1u);
@@ -687,7 +692,26 @@ k_shade(DevScene S, Soa in, Soa out, double max_length, unsigned long long* tile
 #endif
     {   // pull the next tile's parent records towards L2 while this tile computes
         const uint32_t nt = s_tile;
+#if RPX_BULK_PREFETCH
+        // one bulk L2 prefetch per field row (1 KB of doubles / 512 B of u32), issued by 22 threads of
+        // warp 3 (the warp that does NOT run the look-back): 22 instructions per tile instead of ~90
+        if (nt < n_tiles_real && threadIdx.x >= 96 && threadIdx.x < 96 + 22) {
+            const uint32_t q = threadIdx.x - 96;
+            const unsigned long long nb = (unsigned long long)nt * RPX_TILE;
+            if (q < 18) {
+                const uint32_t fld = q < 6 ? q : q + 3;  // every double field but the parent normal
+                asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(in.f + (unsigned long long)fld * cap + nb),
+                             "r"(RPX_TILE * 8));
+            } else {
+                const uint32_t w = q - 18, fld = w + (w ? 1u : 0u);  // WL, ENDFACE, IDENT, TYPE
+                asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(in.u + (unsigned long long)fld * cap + nb),
+                             "r"(RPX_TILE * 4));
+            }
+        }
+        if (false) {
+#else
         if (nt < n_tiles_real) {
+#endif
             const unsigned long long ni = (unsigned long long)nt * RPX_TILE + threadIdx.x;
             if ((threadIdx.x & 3) == 0) {  // one prefetch per 32-byte sector
                 const int pf[18] = {F_OX, F_OY, F_OZ, F_DX, F_DY, F_DZ, F_EX, F_EY, F_EZ, F_NR, F_NI,

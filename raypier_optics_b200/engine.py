@@ -233,6 +233,56 @@ class Engine(object):
                 own.free()
         return FieldModes(self, h)
 
+    def project_to_sphere(self, dev_rays, centre=(0.0, 0.0, 0.0), radius=10.0):
+        """fields.py:50-77 in place on a DeviceRays of plain rays; returns the boolean ``selector``."""
+        c = np.ascontiguousarray(centre, dtype=np.double).reshape(3)
+        sel = np.zeros(len(dev_rays), dtype=np.uint8)
+        n_sel = C.c_uint64(0)
+        self._check(self._L.rpx_rays_project_to_sphere(self._ctx, dev_rays._h, c.ctypes.data, float(radius),
+                                                       sel.ctypes.data, C.byref(n_sel)))
+        assert int(n_sel.value) == int(sel.sum())
+        return sel.astype(bool)
+
+    def field_prepare_neighbours(self, rays, neighbours_idx, wavelengths, blending=1.0, want_xy=False):
+        """evaluate_neighbours -> evaluate_modes -> mode records (fields.py:80-111, cfields.pyx:217-228) for
+        plain rays with their ``RayCollection.neighbours`` array.  Returns FieldModes, or
+        (FieldModes, (x, y, dx, dy)) with ``want_xy``."""
+        own = None
+        if isinstance(rays, np.ndarray):
+            own = self.upload(rays)
+            handle = own._h
+            n = len(own)
+        else:
+            handle = rays._h
+            n = len(rays)
+        nb = np.ascontiguousarray(neighbours_idx, dtype=np.int32)
+        if nb.ndim != 2 or nb.shape[0] != n:  # numpy: boolean index did not match indexed array (fields.py:99)
+            if own is not None:
+                own.free()
+            raise IndexError("neighbours_idx has shape %s for %d rays" % (nb.shape, n))
+        wl = np.ascontiguousarray(wavelengths, dtype=np.double).reshape(-1)
+        kept = int((nb >= 0).all(axis=1).sum())
+        xy = np.zeros((4, kept, nb.shape[1])) if want_xy else None
+        h = C.c_void_p()
+        try:
+            self._check(self._L.rpx_field_prepare_neighbours(self._ctx, handle, nb.ctypes.data, nb.shape[1], wl.ctypes.data,
+                                                             wl.shape[0], float(blending),
+                                                             None if xy is None else xy.ctypes.data, C.byref(h)))
+        finally:
+            if own is not None:
+                own.free()
+        fm = FieldModes(self, h)
+        return (fm, tuple(xy)) if want_xy else fm
+
+    def evaluate_modes(self, x, y, dx, dy, blending=1.0):
+        """cfields.evaluate_modes (cfields.pyx:217-228) on explicit n x 6 arrays -> n x 3 complex128."""
+        x, y, dx, dy = (np.ascontiguousarray(a, dtype=np.double) for a in (x, y, dx, dy))
+        n, row = x.shape
+        out = np.zeros((n, 3), dtype=np.complex128)
+        self._check(self._L.rpx_unit_evaluate_modes(self._ctx, x.ctypes.data, y.ctypes.data, dx.ctypes.data, dy.ctypes.data,
+                                                    n, row, float(blending), out.ctypes.data))
+        return out
+
     # -- rays -----------------------------------------------------------------------
     @staticmethod
     def _is_gausslet(arr):

@@ -40,6 +40,16 @@ def michelson_output(core, n=600, seed=5):
     return cfg, np.ascontiguousarray(out), np.concatenate([line, grid])
 
 
+GOLDEN_HEX = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "fields_hexgrid.npz")
+
+
+def hexgrid_points():
+    """A line through the focus of configs.hex_grid_source and a few points beside it."""
+    xs = np.linspace(-0.5, 0.5, 25)
+    line = np.stack([xs, np.zeros_like(xs), np.full_like(xs, 79.0)], axis=1)
+    return np.concatenate([line, np.array([[0.1, 0.2, 60.0], [-0.3, 0.1, 85.0], [0.0, 0.0, 80.0]])])
+
+
 def rel_err(got, want):
     return float(np.abs(got - want).max() / np.abs(want).max())
 
@@ -99,7 +109,120 @@ def test_field_is_linear_in_amplitude_and_additive_over_rays():
     assert rel_err(O.eval_Efield_from_gausslets(g3, pts, wl), 3.0 * E) < 1e-14
 
 
+def test_oracle_ray_front_end_bit_exact_with_reference(refcore):
+    """project_to_sphere / evaluate_neighbours / eval_Efield_from_rays (fields.py:50-111, 206-229): the
+    oracle's loops against the reference's numpy, bit for bit."""
+    from oracle import oracle as O
+    F = O.reference_fields(refcore)
+    if F is None:
+        pytest.skip("raypier/core/fields.py not importable here")
+    rays, nb = configs.hex_grid_source(n_side=15)
+    wl, pts = np.array([1.0]), hexgrid_points()
+    assert (nb < 0).any() and (nb >= 0).all(axis=1).sum() > 100
+    for centre, radius in (((0, 0, 0), 0.0), ((0.3, -0.2, 80.0), 90.0)):
+        proj = rays
+        if radius:
+            proj = F.project_to_sphere(rays.copy(), centre, radius)
+            assert O.project_to_sphere(rays, centre, radius).tobytes() == proj.tobytes()
+            assert np.abs(proj['origin'] - rays['origin']).max() > 1.0  # really moved
+        want = F.evaluate_neighbours(proj.copy(), nb)
+        got = O.evaluate_neighbours(proj, nb)
+        for a, b in zip(want, got):
+            assert a.tobytes() == b.tobytes()
+        rc = O.reference_collection(refcore, rays.copy(), wl)
+        rc.neighbours = nb
+        E = F.eval_Efield_from_rays(rc, pts, wl, blending=0.8, time_ps=1.5, exit_pupil_offset=radius,
+                                    exit_pupil_centre=centre)
+        assert np.abs(E).max() > 1.0
+        assert O.eval_Efield_from_rays(rays, nb, pts, wl, 0.8, 1.5, radius, centre).tobytes() == E.tobytes()
+    # a ray that misses the sphere: the reference's own indexing raises, and so does the restatement
+    far = rays.copy()
+    far['origin'][3] = (500.0, 0.0, 0.0)
+    far['direction'][3] = (0.0, 0.0, 1.0)
+    rc = O.reference_collection(refcore, far.copy(), wl)
+    rc.neighbours = nb
+    with pytest.raises(IndexError):
+        F.eval_Efield_from_rays(rc, pts, wl, exit_pupil_offset=90.0, exit_pupil_centre=(0.3, -0.2, 80.0))
+    with pytest.raises(IndexError):
+        O.eval_Efield_from_rays(far, nb, pts, wl, exit_pupil_offset=90.0, exit_pupil_centre=(0.3, -0.2, 80.0))
+
+
+def test_oracle_reproduces_golden_hexgrid_fields():
+    from oracle import oracle as O
+    z = np.load(GOLDEN_HEX)
+    rays = z['rays'].view(A.ray_dtype).reshape(-1)
+    nb, wl, pts = z['neighbours'], z['wavelengths'], z['points']
+    centre, radius, blending, time_ps = z['centre'], float(z['radius']), float(z['blending']), float(z['time_ps'])
+    proj = O.project_to_sphere(rays, centre, radius)
+    assert proj.tobytes() == z['projected'].tobytes()
+    kept, x, y, dx, dy = O.evaluate_neighbours(proj, nb)
+    for a, k in ((x, 'x'), (y, 'y'), (dx, 'dx'), (dy, 'dy')):
+        assert a.tobytes() == z[k].tobytes()
+    assert O.evaluate_modes(x, y, dx, dy, blending).tobytes() == z['modes'].tobytes()
+    assert O.eval_Efield_from_rays(rays, nb, pts, wl, blending, time_ps).tobytes() == z['E_plain'].tobytes()
+    assert O.eval_Efield_from_rays(rays, nb, pts, wl, blending, time_ps, radius, centre).tobytes() == z['E_sphere'].tobytes()
+
+
 # ------------------------------------------------------------------------------------ GPU
+@pytest.mark.gpu
+def test_cuda_ray_front_end_matches_golden_reference(core, engine):
+    """The mirrors of fields.project_to_sphere / evaluate_neighbours / cfields.evaluate_modes /
+    fields.eval_Efield_from_rays (CUDA through the C ABI) against vectors made by the reference."""
+    from raypier_optics_b200.core import cfields as CF, fields as FD
+    z = np.load(GOLDEN_HEX)
+    rays = z['rays'].view(A.ray_dtype).reshape(-1)
+    nb, wl, pts = z['neighbours'], z['wavelengths'], z['points']
+    centre, radius, blending, time_ps = z['centre'], float(z['radius']), float(z['blending']), float(z['time_ps'])
+    want_proj = z['projected'].view(A.ray_dtype).reshape(-1)
+    proj = FD.project_to_sphere(rays, centre, radius)
+    assert len(proj) == len(want_proj)
+    for name in ('direction', 'E_vector', 'E1_amp', 'E2_amp', 'wavelength_idx', 'parent_idx', 'ray_type_id'):
+        assert np.array_equal(proj[name], want_proj[name])
+    assert np.abs(proj['origin'] - want_proj['origin']).max() <= 1e-9 * np.abs(want_proj['origin']).max()
+    assert np.abs(proj['accumulated_path'] - want_proj['accumulated_path']).max() <= 1e-9 * 100.0
+    kept, x, y, dx, dy = FD.evaluate_neighbours(want_proj, nb)
+    assert kept.tobytes() == want_proj[(nb >= 0).all(axis=1)].tobytes()
+    for got, k in ((x, 'x'), (y, 'y'), (dx, 'dx'), (dy, 'dy')):
+        assert got.shape == z[k].shape
+        assert np.abs(got - z[k]).max() <= 1e-10 * max(np.abs(z[k]).max(), 1.0)
+    modes = CF.evaluate_modes(z['x'], z['y'], z['dx'], z['dy'], blending=blending)
+    scale = np.abs(z['modes']).max(axis=1, keepdims=True)
+    assert float((np.abs(modes - z['modes']) / scale).max()) < 1e-10
+    rc = core.ctracer.RayCollection.from_array(rays)
+    rc.neighbours = nb
+    E = FD.eval_Efield_from_rays(rc, pts, wl, blending=blending, time_ps=time_ps)
+    assert rel_err(E, z['E_plain']) <= TOL_FIELD_SUM
+    E = FD.eval_Efield_from_rays(rc, pts, wl, blending=blending, time_ps=time_ps, exit_pupil_offset=radius,
+                                 exit_pupil_centre=centre)
+    assert rel_err(E, z['E_sphere']) <= TOL_FIELD_SUM
+    # the reference raises when a ray misses the exit-pupil sphere (its neighbour indexing breaks)
+    far = rays.copy()
+    far['origin'][3] = (500.0, 0.0, 0.0)
+    far['direction'][3] = (0.0, 0.0, 1.0)
+    rc = core.ctracer.RayCollection.from_array(far)
+    rc.neighbours = nb
+    with pytest.raises(IndexError):
+        FD.eval_Efield_from_rays(rc, pts, wl, exit_pupil_offset=radius, exit_pupil_centre=centre)
+
+
+@pytest.mark.gpu
+def test_cuda_ray_front_end_matches_oracle_at_size(core, engine):
+    """201 x 201 rays (38k with six neighbours) x 28 points against the oracle."""
+    from oracle import oracle as O
+    from raypier_optics_b200.core import fields as FD
+    rays, nb = configs.hex_grid_source(n_side=201, pitch=0.04)
+    wl, pts = np.array([0.8, 1.0]), hexgrid_points()
+    rays['wavelength_idx'] = np.arange(len(rays)) % 2
+    rc = core.ctracer.RayCollection.from_array(rays)
+    rc.neighbours = nb
+    for radius in (0.0, 95.0):
+        want = O.eval_Efield_from_rays(rays, nb, pts, wl, 0.9, 0.5, radius, (0.0, 0.1, 80.0))
+        got = FD.eval_Efield_from_rays(rc, pts, wl, blending=0.9, time_ps=0.5, exit_pupil_offset=radius,
+                                       exit_pupil_centre=(0.0, 0.1, 80.0))
+        assert np.abs(want).max() > 1.0
+        assert rel_err(got, want) <= TOL_FIELD_SUM
+
+
 @pytest.mark.gpu
 def test_cuda_fields_match_golden_reference(engine):
     z = np.load(GOLDEN)
