@@ -271,13 +271,16 @@ RPX_DEV unsigned long long tile_lookback(unsigned long long* state, uint32_t til
     while (true) {
         const long long t = t0 - lane;
         const bool valid = (t >= 0);
-        unsigned long long s = 0;
-        if (valid) {
-            do {
-                s = ld_relaxed(&state[t]);
-            } while ((s >> 62) == 0);
+        // only the entries in front of the nearest PREFIX have to be there: wait for exactly those
+        unsigned long long s = valid ? ld_relaxed(&state[t]) : RPX_FLAG_AGG;
+        unsigned pref;
+        for (;;) {
+            pref = __ballot_sync(0xffffffffu, valid && ((s >> 62) == 2));
+            const unsigned have = __ballot_sync(0xffffffffu, (s >> 62) != 0);
+            const unsigned need = pref ? ((1u << (__ffs(pref) - 1)) - 1u) : 0xffffffffu;
+            if ((have & need) == need) break;
+            if ((s >> 62) == 0) s = ld_relaxed(&state[t]);
         }
-        const unsigned pref = __ballot_sync(0xffffffffu, valid && ((s >> 62) == 2));
         unsigned long long v = valid ? (s & RPX_VAL_MASK) : 0ull;
         if (pref) {
             const int first = __ffs(pref) - 1;  // nearest predecessor holding a full prefix
