@@ -106,8 +106,20 @@ typedef enum rpx_face_type {
     RPX_FACE_EXT_POLY = 18,        /* :2130 p: R(=-curvature), beta(=1+k), norm_radius, z_height,
                                               atol, invert_normals ; aux = coefs[Nx][Ny] (pool)     */
     RPX_FACE_DISTORTION = 19,      /* :2323 p: accuracy ; base_face, aux = distortion idx ; shape   */
-    RPX_FACE_EXTRUDED_BEZIER = 20  /* :795  p: z_height_1, z_height_2, mincorner[2], maxcorner[2];
+    RPX_FACE_EXTRUDED_BEZIER = 20, /* :795  p: z_height_1, z_height_2, mincorner[2], maxcorner[2];
                                               aux = cubic Bezier segments [n][4][2] (pool)          */
+    RPX_FACE_MESH = 21             /* obbtree.pyx:880-946 OBBTreeFace over an OBBTree (:200-400): a
+                                      triangle mesh.  p: tree tolerance (OBBTree.tolerance, 0.1);
+                                      aux_off = mesh block in pool, aux_n = cells, aux_m = BVH nodes.
+                                      Block (doubles): header[8] = n_points, n_cells, n_nodes,
+                                      off_points, off_cells, off_tris, off_nodes (relative to aux_off),
+                                      tolerance; points[n_points][3]; cells[n_cells][3] (vertex ids);
+                                      tris[n_cells][16] in BVH leaf order = p1, v1 = p2 - p1,
+                                      v2 = p3 - p1, n = v1 x v2, cell id, 3 pad; nodes[n_nodes][8] =
+                                      box min[3], box max[3], then (left, right) child ids for an inner
+                                      node or (-(first tri) - 1, count) for a leaf.  The reference's OBB
+                                      tree is an acceleration structure (its node test only prunes); this
+                                      library carries its own BVH, built by the host side.             */
 } rpx_face_type;
 
 #define RPX_FACE_NPARAM 16

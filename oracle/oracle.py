@@ -438,6 +438,10 @@ def import_reference(flavour="parity"):
         core = importlib.import_module("raypier.core")
         for name in ("ctracer", "cfaces", "cmaterials", "cshapes", "cdistortions", "cimplicit_surfs"):
             importlib.import_module("raypier.core." + name)
+        try:  # triangle-mesh faces (needs PIL at import time: obbtree.pyx:6); optional
+            importlib.import_module("raypier.core.obbtree")
+        except Exception:
+            pass
         return core
     except Exception:
         return None

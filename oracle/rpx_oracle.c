@@ -520,9 +520,74 @@ static int bz_pnt_in_hull(flat2 p, flat2 A, flat2 B, flat2 C, flat2 D) { /* cfac
     return i && k;
 }
 
+/* ---- triangle meshes: OBBTree / OBBTreeFace, raypier/core/obbtree.pyx -------------------------
+ * intersect_t.piece_idx (ctracer.pxd:77-80) travels from Face.intersect_c to compute_normal_c in the
+ * reference; every other face class ignores it.  This scalar restatement keeps it in two statics:
+ * s_piece = piece of the last face_intersect call, s_hit_piece = piece of the accepted hit.     */
+static int s_piece = 0, s_hit_piece = 0;
+
+/* Mesh block in the pool (scene.py::_mesh_block): header of 8 doubles, then the raw points / cells
+ * (what the reference object holds) and, for the CUDA path only, BVH-ordered triangle records and
+ * nodes.  The oracle reads ONLY the raw points and cells.                                        */
+#define MESH_HDR 8
+
+/* OBBTree.line_intersects_cell_c, obbtree.pyx:310-343 */
+static double mesh_line_intersects_cell(const double* points, const double* cells, long cell_idx, vec3 o, vec3 d) {
+    const double* c = cells + 3 * cell_idx;
+    vec3 p1 = ld3(points + 3 * (long)c[0]), p2 = ld3(points + 3 * (long)c[1]), p3 = ld3(points + 3 * (long)c[2]);
+    vec3 v1 = subvv(p2, p1), v2 = subvv(p3, p1);
+    vec3 n = cross(v1, v2);
+    double det = -dotprod(d, n);
+    if (det == 0.0) return -1;
+    double invdet = 1.0 / det;
+    vec3 a0 = subvv(o, p1);
+    vec3 da0 = cross(a0, d);
+    double u = dotprod(v2, da0) * invdet;
+    double v = -dotprod(v1, da0) * invdet;
+    double alpha = dotprod(a0, n) * invdet;
+    if ((u + v > 1.0) | (u < 0) | (v < 0) | (alpha < 0)) return -1.0;
+    return alpha;
+}
+
+/* OBBTree.intersect_with_line_c (obbtree.pyx:367-400) + OBBTreeFace.intersect_c (:913-932).  The OBB
+ * tree only prunes (line_intersects_node_c, :271-296, is a conservative interval test with a positive
+ * margin), so the result is the nearest cell with tol <= alpha < 1 over ALL cells; on exactly equal
+ * alpha the reference keeps the cell its traversal meets first, this loop the lowest cell index.  */
+static double mesh_intersect(const rpx_scene* S, const rpx_face* f, vec3 p1, vec3 p2, int* piece) {
+    const double* H = S->pool + f->aux_off;
+    const long n_cells = (long)H[1];
+    const double* points = H + (long)H[3];
+    const double* cells = H + (long)H[4];
+    vec3 d = subvv(p2, p1);
+    double tol = H[7] / mag(d);
+    double best = 1.0;
+    long best_cell = -1;
+    for (long i = 0; i < n_cells; i++) {
+        double alpha = mesh_line_intersects_cell(points, cells, i, p1, d);
+        if ((alpha >= tol) && (alpha < best)) {
+            best = alpha;
+            best_cell = i;
+        }
+    }
+    if (best_cell < 0) best = -1.0;
+    *piece = (int)best_cell;
+    return best * mag(subvv(p2, p1));
+}
+
+/* OBBTreeFace.__cinit__ (:898-908) + compute_normal_c (:935-946): the flat normal of cell `piece` */
+static vec3 mesh_normal(const rpx_scene* S, const rpx_face* f, int piece) {
+    const double* H = S->pool + f->aux_off;
+    const double* points = H + (long)H[3];
+    const double* c = H + (long)H[4] + 3 * (long)piece;
+    vec3 p1 = ld3(points + 3 * (long)c[0]), p2 = ld3(points + 3 * (long)c[1]), p3 = ld3(points + 3 * (long)c[2]);
+    return norm(cross(subvv(p2, p1), subvv(p3, p1)));
+}
+
 /* Face.intersect_c for every concrete class: distance along p1->p2, or <= 0 / -1 */
 static double face_intersect(const rpx_scene* S, const rpx_face* f, vec3 p1, vec3 p2,
                              int is_base_ray) {
+    s_piece = 0;
+    if (f->type == RPX_FACE_MESH) return mesh_intersect(S, f, p1, p2, &s_piece);
     const double* P = f->p;
     const double tol = f->tolerance;
     switch (f->type) {
@@ -1016,6 +1081,7 @@ static double face_intersect(const rpx_scene* S, const rpx_face* f, vec3 p1, vec
 /* Face.compute_normal_c (local coordinates) */
 static vec3 face_normal(const rpx_scene* S, const rpx_face* f, vec3 p) {
     const double* P = f->p;
+    if (f->type == RPX_FACE_MESH) return mesh_normal(S, f, s_hit_piece);
     switch (f->type) {
         case RPX_FACE_CIRCULAR: return v3(0, 0, P[3] != 0.0 ? 1 : -1); /* :180-191 */
         case RPX_FACE_SHAPED_PLANAR: return v3(0, 0, 1);               /* :228-236 */
@@ -1732,6 +1798,7 @@ static int nearest_hit(const rpx_scene* S, rpx_ray* ray, vec3 point) {
                 ray->length = dist;
                 ray->end_face_idx = (uint32_t)i;
                 nearest_idx = i;
+                s_hit_piece = s_piece;
             }
         }
     }
@@ -1748,6 +1815,7 @@ static int one_face_hit(const rpx_scene* S, rpx_ray* ray, vec3 point, int face_i
     if (f->tolerance < dist && dist < ray->length) {
         ray->length = dist;
         ray->end_face_idx = (uint32_t)face_idx;
+        s_hit_piece = s_piece;
         return face_idx;
     }
     return -1;
@@ -1830,6 +1898,7 @@ uint64_t rpxo_trace_gausslet_ex(const rpx_scene* S, rpx_gausslet* gs, uint64_t n
             double dist = face_intersect(S, face, p1, p2, 0);
             if (face->tolerance < dist && dist < pr->length) {
                 pr->length = dist;
+                s_hit_piece = s_piece; /* the parabasal ray's own piece (intersect_para_c returns its intersect_t) */
             } else {
                 ok = 0;
                 break;

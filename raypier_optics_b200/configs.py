@@ -353,6 +353,93 @@ def config_big_scene(core, n=3000, seed=55, gausslets=False, n_baffles=250):
     return cfg
 
 
+def icosphere(radius=5.0, subdivisions=2):
+    """Triangulated sphere (outward-facing triangles): points N x 3, cells M x 3 int32."""
+    t = (1.0 + np.sqrt(5.0)) / 2.0
+    v = [(-1, t, 0), (1, t, 0), (-1, -t, 0), (1, -t, 0), (0, -1, t), (0, 1, t), (0, -1, -t), (0, 1, -t),
+         (t, 0, -1), (t, 0, 1), (-t, 0, -1), (-t, 0, 1)]
+    f = [(0, 11, 5), (0, 5, 1), (0, 1, 7), (0, 7, 10), (0, 10, 11), (1, 5, 9), (5, 11, 4), (11, 10, 2),
+         (10, 7, 6), (7, 1, 8), (3, 9, 4), (3, 4, 2), (3, 2, 6), (3, 6, 8), (3, 8, 9), (4, 9, 5), (2, 4, 11),
+         (6, 2, 10), (8, 6, 7), (9, 8, 1)]
+    pts = [np.array(p, dtype=np.double) / np.sqrt(1 + t * t) for p in v]
+    for _ in range(subdivisions):
+        cache, nf = {}, []
+
+        def mid(a, b):
+            key = (min(a, b), max(a, b))
+            if key not in cache:
+                m = pts[a] + pts[b]
+                pts.append(m / np.sqrt((m ** 2).sum()))
+                cache[key] = len(pts) - 1
+            return cache[key]
+        for a, b, c in f:
+            ab, bc, ca = mid(a, b), mid(b, c), mid(c, a)
+            nf += [(a, ab, ca), (b, bc, ab), (c, ca, bc), (ab, bc, ca)]
+        f = nf
+    return np.array(pts) * radius, np.array(f, dtype=np.int32)
+
+
+def bowl_mesh(half_width=10.0, n=24, focal=20.0):
+    """Triangulated paraboloid z = r^2 / (4 f) on an n x n grid (normals towards +z)."""
+    xs = np.linspace(-half_width, half_width, n)
+    X, Y = np.meshgrid(xs, xs, indexing='ij')
+    Z = (X ** 2 + Y ** 2) / (4.0 * focal)
+    pts = np.stack([X.ravel(), Y.ravel(), Z.ravel()], axis=1)
+    cells = []
+    for i in range(n - 1):
+        for j in range(n - 1):
+            a, b, c, d = i * n + j, (i + 1) * n + j, (i + 1) * n + j + 1, i * n + j + 1
+            cells += [(a, b, c), (a, c, d)]
+    return pts, np.array(cells, dtype=np.int32)
+
+
+def config_mesh(core, n=20000, seed=61, gausslets=False, mesh_n=40):
+    """Triangle-mesh optics (raypier/meshes.py:16-67 builds OBBTreeFace from an STL file).
+    Plain rays: a glass ball lens as an icosphere (FullDielectricMaterial: refraction, Fresnel reflections,
+    TIR between facets) over a tilted faceted paraboloid mirror (PEC), both OBBTreeFace over an OBBTree.
+    Gausslets: the faceted mirror under a flat PEC mirror (the beam bounces between them).  The dielectric
+    ball is left out there on purpose: a parabasal ray that misses (or goes NaN by TIR) makes the REFERENCE
+    read an uninitialised intersect_t.face_idx (OBBTreeFace.intersect_c, obbtree.pyx:913-932, never sets
+    it), so its behaviour for such gausslets is undefined; this package drops them like every other face
+    does (quirk Q16)."""
+    import importlib
+    OB = importlib.import_module(core.__name__ + ".obbtree")
+    M, F = core.cmaterials, core.cfaces
+    wl = np.array([0.633])
+
+    def mesh_face(owner, pts, cells, material):
+        tree = OB.OBBTree(np.ascontiguousarray(pts, dtype=np.double).copy(), np.ascontiguousarray(cells, dtype=np.int32).copy())
+        tree.max_level = 100
+        tree.number_of_cells_per_node = 6
+        owner.mesh_points, owner.mesh_cells = pts, cells  # a reference OBBTree keeps its mesh private
+        return OB.OBBTreeFace(tree=tree, material=material, owner=owner)
+
+    mirror = Pose(centre=(0.0, 0.0, -25.0), direction=(0.1, -0.05, 1.0))
+    pts, cells = bowl_mesh(half_width=60.0, n=mesh_n, focal=30.0)
+    fl_mirror = _facelist(core, mirror, [mesh_face(mirror, pts, cells, M.PECMaterial())])
+    if gausslets:
+        flat = Pose(centre=(0.0, 0.0, 45.0), direction=(0.0, 0.0, 1.0), diameter=150.0, offset=0.0)
+        fl_top = _facelist(core, flat, [F.CircularFace(owner=flat, diameter=150.0, material=M.PECMaterial())])
+        face_lists = [fl_top, fl_mirror]
+    else:
+        ball = Pose(centre=(0.3, -0.2, 0.0), direction=(0.05, 0.02, 1.0))
+        pts, cells = icosphere(radius=5.0, subdivisions=2)
+        glass = M.FullDielectricMaterial(n_inside=1.5, n_outside=1.0)
+        face_lists = [_facelist(core, ball, [mesh_face(ball, pts, cells, glass)]), fl_mirror]
+    rays = disc_source(n, centre=(0., 0., 30.), axis=(0., 0., -1.), radius=4.0, seed=seed, E_vector=(1., 0., 0.),
+                       E1=1.0, E2=0.4j, ray_type_id=GAUSSLET if gausslets else 0)
+    out = dict(name="config_mesh" + ("" if gausslets else "_rays"), face_lists=face_lists, wavelengths=wl,
+               max_length=120.0, recursion_limit=5)
+    if gausslets:
+        rays['length'] = 120.0
+        gc = core.ctracer.GaussletCollection.from_rays(rays)
+        gc.config_parabasal_rays(wl, 0.05, 0.0)
+        out['rays'] = gc.copy_as_array()
+    else:
+        out['rays'] = rays
+    return out
+
+
 def config4_prisms(core, n=100000, seed=4):
     """Config 4 (TIR part): a rhomboid + a right-angle (Dove-like) prism built as
     extrusions with FullDielectricMaterial (examples/ctracer_demo_prisms.py), low
@@ -595,6 +682,7 @@ CONFIGS = {
     "config4_cpc": config4_cpc,
     "config5": config5_michelson,
     "big_scene": config_big_scene,
+    "mesh": config_mesh,
 }
 
 

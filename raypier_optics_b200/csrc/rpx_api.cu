@@ -162,7 +162,7 @@ static int validate_scene(rpx_ctx* ctx, const rpx_scene* s) {
         return fail(ctx, RPX_ERR_INVALID, "bad face counts");
     for (int i = 0; i < s->n_faces; i++) {
         const rpx_face& f = s->faces[i];
-        if (f.type < RPX_FACE_CIRCULAR || f.type > RPX_FACE_EXTRUDED_BEZIER)
+        if (f.type < RPX_FACE_CIRCULAR || f.type > RPX_FACE_MESH)
             return fail(ctx, RPX_ERR_UNSUPPORTED, "face %d: unsupported face type %d", i, f.type);
         if (f.face_set < 0 || f.face_set >= s->n_face_sets)
             return fail(ctx, RPX_ERR_INVALID, "face %d: face_set %d out of range", i, f.face_set);
@@ -184,6 +184,29 @@ static int validate_scene(rpx_ctx* ctx, const rpx_scene* s) {
             return fail(ctx, RPX_ERR_INVALID, "face %d: polygon points out of range", i);
         if (f.type == RPX_FACE_EXT_POLY && (f.aux_off < 0 || f.aux_off + f.aux_n * f.aux_m > s->n_pool))
             return fail(ctx, RPX_ERR_INVALID, "face %d: coefficient table out of range", i);
+        if (f.type == RPX_FACE_MESH) {
+            if (f.aux_off < 0 || f.aux_n < 1 || f.aux_m < 1 || f.aux_off + 8 > s->n_pool)
+                return fail(ctx, RPX_ERR_INVALID, "face %d: mesh block out of range", i);
+            const double* H = s->pool + f.aux_off;
+            const long long n_pts = (long long)H[0], n_cells = (long long)H[1], n_nodes = (long long)H[2];
+            const long long end = f.aux_off + 8 + 3 * n_pts + 3 * n_cells + 16 * n_cells + 8 * n_nodes;
+            if (n_cells != f.aux_n || n_nodes != f.aux_m || n_pts < 3 || end > s->n_pool || (long long)H[3] != 8 ||
+                (long long)H[4] != 8 + 3 * n_pts || (long long)H[5] != 8 + 3 * n_pts + 3 * n_cells ||
+                (long long)H[6] != 8 + 3 * n_pts + 19 * n_cells)
+                return fail(ctx, RPX_ERR_INVALID, "face %d: inconsistent mesh block header", i);
+            // the device traversal trusts the node links: check them here, once
+            const double* cells = H + (long long)H[4];
+            for (long long c = 0; c < 3 * n_cells; c++)
+                if (!(cells[c] >= 0 && cells[c] < (double)n_pts))
+                    return fail(ctx, RPX_ERR_INVALID, "face %d: mesh cell refers to a missing point", i);
+            const double* nodes = H + (long long)H[6];
+            for (long long k = 0; k < n_nodes; k++) {
+                const double a = nodes[8 * k + 6], b = nodes[8 * k + 7];
+                const bool ok = a >= 0 ? (a > (double)k && a < (double)n_nodes && b > (double)k && b < (double)n_nodes)
+                                       : (-a - 1 >= 0 && b >= 1 && (-a - 1) + b <= (double)n_cells);
+                if (!ok) return fail(ctx, RPX_ERR_INVALID, "face %d: bad BVH node %lld", i, k);
+            }
+        }
         if (f.type == RPX_FACE_EXTRUDED_BEZIER && (f.aux_off < 0 || f.aux_n < 1 || f.aux_off + 8 * f.aux_n > s->n_pool))
             return fail(ctx, RPX_ERR_INVALID, "face %d: Bezier control points out of range", i);
         if (f.type == RPX_FACE_ELLIPSOIDAL && (f.aux_off < 0 || f.aux_off + 24 > s->n_pool))

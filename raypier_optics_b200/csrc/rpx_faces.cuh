@@ -1140,15 +1140,103 @@ static __device__ __noinline__ double distortion_intersect(const DevScene& S, co
     return a1;
 }
 
+// ------------------------------------------------------------------ triangle meshes (obbtree.pyx)
+// OBBTreeFace.intersect_c (obbtree.pyx:913-932) over OBBTree.intersect_with_line_c (:367-400): the
+// nearest triangle with tolerance / |p2 - p1| <= alpha < 1.  The reference prunes with its OBB tree
+// (line_intersects_node_c, :271-296: a conservative interval test); here the pruning structure is a
+// BVH of padded axis-aligned boxes built by the host (include/rpx.h, RPX_FACE_MESH): an explicit
+// stack in local memory, slab test of the segment clipped to the best alpha so far, nearest child
+// order not needed (the clip does the pruning).  The triangle test is line_intersects_cell_c
+// (:310-343) on records that hold p1, v1, v2 and n = v1 x v2 ready-made.  Exactly equal alpha (a ray
+// through a shared edge): the lowest cell id wins, whatever the traversal order.
+// *piece = cell id of the hit (intersect_t.piece_idx), -1 on a miss.
+static __device__ __noinline__ double mesh_intersect(const DevScene& S, const rpx_face* f, vec3 p1, vec3 p2, int* piece) {
+    const double* H = S.pool + f->aux_off;
+    const double* tris = H + (long long)H[5];
+    const double* nodes = H + (long long)H[6];
+    const vec3 d = p2 - p1;
+    const double dmag = sqrt(d.x * d.x + d.y * d.y + d.z * d.z);  // mag_(d): IEEE, it scales the result
+    const double tol = H[7] / dmag;
+    const double ix = 1.0 / d.x, iy = 1.0 / d.y, iz = 1.0 / d.z;  // +-inf for an axis-parallel segment
+    double best = 1.0;
+    long long best_id = -1;
+    int stack[64];
+    int sp = 0;
+    stack[sp++] = 0;
+    while (sp > 0) {
+        const double* nd = nodes + 8 * (long long)stack[--sp];
+        // fmin / fmax drop a NaN operand (0 * inf when the segment lies in a box plane): conservative
+        const double ax = (nd[0] - p1.x) * ix, bx = (nd[3] - p1.x) * ix;
+        const double ay = (nd[1] - p1.y) * iy, by = (nd[4] - p1.y) * iy;
+        const double az = (nd[2] - p1.z) * iz, bz = (nd[5] - p1.z) * iz;
+        const double tmin = fmax(fmax(fmin(ax, bx), fmin(ay, by)), fmax(fmin(az, bz), 0.0));
+        const double tmax = fmin(fmin(fmax(ax, bx), fmax(ay, by)), fmin(fmax(az, bz), best));
+        if (!(tmin <= tmax)) continue;
+        const double a = nd[6], b = nd[7];
+        if (a >= 0.0) {
+            if (sp <= 62) {
+                stack[sp++] = (int)b;
+                stack[sp++] = (int)a;
+            }
+            continue;
+        }
+        const double* t = tris + 16 * (long long)(-a - 1.0);
+        const int count = (int)b;
+        for (int c = 0; c < count; c++, t += 16) {
+            const vec3 tp = v3(t[0], t[1], t[2]), v1 = v3(t[3], t[4], t[5]), v2 = v3(t[6], t[7], t[8]);
+            const vec3 n = v3(t[9], t[10], t[11]);
+            const double det = -dot(d, n);
+            if (det == 0.0) continue;
+            const double invdet = 1.0 / det;
+            const vec3 a0 = p1 - tp;
+            const vec3 da0 = cross(a0, d);
+            const double u = dot(v2, da0) * invdet;
+            const double v = -dot(v1, da0) * invdet;
+            const double alpha = dot(a0, n) * invdet;
+            if ((u + v > 1.0) | (u < 0) | (v < 0) | (alpha < 0)) continue;
+            const long long id = (long long)t[12];
+            if (alpha >= tol && (alpha < best || (alpha == best && id < best_id))) {
+                best = alpha;
+                best_id = id;
+            }
+        }
+    }
+    *piece = (int)best_id;
+    if (best_id < 0) best = -1.0;
+    return best * dmag;
+}
+
+// OBBTreeFace.__cinit__ (:898-908) + compute_normal_c (:935-946): the flat normal of cell `piece`
+static __device__ __noinline__ vec3 mesh_normal(const DevScene& S, const rpx_face* f, int piece) {
+    const double* H = S.pool + f->aux_off;
+    const double* pts = H + (long long)H[3];
+    const double* c = H + (long long)H[4] + 3 * (long long)piece;
+    const double* q1 = pts + 3 * (long long)c[0];
+    const double* q2 = pts + 3 * (long long)c[1];
+    const double* q3 = pts + 3 * (long long)c[2];
+    const vec3 a = v3(q1[0], q1[1], q1[2]);
+    return norm(cross(v3(q2[0], q2[1], q2[2]) - a, v3(q3[0], q3[1], q3[2]) - a));
+}
+
+// piece (may be NULL): intersect_t.piece_idx of the hit -- only mesh faces have pieces, 0 otherwise
 template <int FC>
-RPX_DEV double face_intersect(const DevScene& S, const rpx_face* f, vec3 p1, vec3 p2, int is_base_ray) {
+RPX_DEV double face_intersect(const DevScene& S, const rpx_face* f, vec3 p1, vec3 p2, int is_base_ray,
+                              int* piece = nullptr) {
+    if (FC == RPX_FC_FULL && f->type == RPX_FACE_MESH) {
+        int pc;
+        const double dist = mesh_intersect(S, f, p1, p2, &pc);
+        if (piece) *piece = pc;
+        return dist;
+    }
+    if (piece) *piece = 0;
     if (FC == RPX_FC_FULL && f->type == RPX_FACE_DISTORTION) return distortion_intersect(S, f, p1, p2);
     if (FC == RPX_FC_FULL && f->type == RPX_FACE_EXTRUDED_BEZIER) return bezier_intersect(S, f, p1, p2);
     return face_intersect_basic<FC>(S, f, p1, p2, is_base_ray);
 }
 
 template <int FC>
-__device__ vec3 face_normal(const DevScene& S, const rpx_face* f, vec3 p) {
+__device__ vec3 face_normal(const DevScene& S, const rpx_face* f, vec3 p, int piece = 0) {
+    if (FC == RPX_FC_FULL && f->type == RPX_FACE_MESH) return mesh_normal(S, f, piece);
     if (FC == RPX_FC_FULL && f->type == RPX_FACE_DISTORTION) {  // cfaces.pyx:2418-2431
         const rpx_face* base = &S.faces[f->base_face];
         const rpx_distortion* dist = &S.dists[f->aux_off];
@@ -1176,10 +1264,10 @@ RPX_DEV vec3 face_tangent(const rpx_face* f) {
 // FaceList.compute_orientation_c, ctracer.pyx:1939-1953
 template <int FC>
 RPX_DEV void compute_orientation(const DevScene& S, const rpx_face* f, vec3 point, vec3* normal,
-                                 vec3* tangent) {
+                                 vec3* tangent, int piece = 0) {
     const rpx_face_set* fs = &S.sets[f->face_set];
     point = transform_pt(fs->inv_trans.m, point);
-    vec3 n = face_normal<FC>(S, f, point);
+    vec3 n = face_normal<FC>(S, f, point, piece);
     vec3 t = face_tangent(f);
     if (f->invert_normal) {
         n = neg(n);

@@ -588,6 +588,7 @@ k_shade(DevScene S, Soa in, Soa out, double max_length, unsigned long long* tile
     uint32_t wl = 0, ident = 0;
     uint32_t face_idx = RPX_NO_FACE;
     double plen[RPX_NPARA];
+    int ppiece[FC == RPX_FC_FULL ? RPX_NPARA : 1];  // piece_idx of the parabasal hits (mesh faces)
     bool hit = false;
     RayIn r;
     if (i < n_in) {
@@ -616,7 +617,16 @@ k_shade(DevScene S, Soa in, Soa out, double max_length, unsigned long long* tile
         }
         vec3 point = r.o + r.d * r.len;
         vec3 onormal, otangent;
-        compute_orientation<FC>(S, face, point, &onormal, &otangent);
+        int piece = 0;
+        if (FC == RPX_FC_FULL && face->type == RPX_FACE_MESH) {
+            // intersect_t.piece_idx (which triangle) is not part of the ray record: the hit is found
+            // again from the same inputs the trace-ahead / k_intersect pass used, so it is the same hit
+            const rpx_face_set* mfs = &S.sets[face->face_set];
+            face_intersect<FC>(S, face, transform_pt(mfs->inv_trans.m, r.o),
+                               transform_pt(mfs->inv_trans.m, r.o + r.d * max_length), 1, &piece);
+            if (piece < 0) piece = 0;
+        }
+        compute_orientation<FC>(S, face, point, &onormal, &otangent, piece);
         material_eval<MM>(S, &S.mats[face->material], r, point, onormal, otangent, k);
 
         if (GAUSS) {
@@ -634,7 +644,9 @@ k_shade(DevScene S, Soa in, Soa out, double max_length, unsigned long long* tile
                     vec3 ray_end = po + pd * max_length;
                     vec3 p1 = transform_pt(fs->inv_trans.m, po);
                     vec3 p2 = transform_pt(fs->inv_trans.m, ray_end);
-                    double dist = face_intersect<FC>(S, face, p1, p2, 0);
+                    int pc = 0;
+                    double dist = face_intersect<FC>(S, face, p1, p2, 0, FC == RPX_FC_FULL ? &pc : nullptr);
+                    if (FC == RPX_FC_FULL) ppiece[j] = pc;
                     if (face->tolerance < dist && dist < max_length) {
                         plen[j] = dist;
                         in.p[(unsigned long long)(j * NPF + P_LEN) * cap + i] = dist;  // parent write-back
@@ -833,7 +845,7 @@ k_shade(DevScene S, Soa in, Soa out, double max_length, unsigned long long* tile
             vec3 pd = v3(pp[(P_DX + 0) * cap], pp[(P_DX + 1) * cap], pp[(P_DX + 2) * cap]);
             vec3 ppoint = po + pd * plen[j];
             vec3 pn, pt;
-            compute_orientation<FC>(S, face, ppoint, &pn, &pt);
+            compute_orientation<FC>(S, face, ppoint, &pn, &pt, FC == RPX_FC_FULL ? ppiece[j] : 0);
             vec3 nn = norm(pn);
             if (k.has_a) {
                 vec3 dir = material_eval_para(S, M, wl, k.a.n.re, pd, ppoint, pn, pt, k.a.type);

@@ -227,8 +227,37 @@ class Scene:
     # -- pool helpers ---------------------------------------------------------
     def _pool_add(self, values):
         off = len(self._pool)
-        self._pool.extend(float(v) for v in np.asarray(values, dtype=np.double).reshape(-1))
+        self._pool.extend(np.asarray(values, dtype=np.double).reshape(-1).tolist())
         return off
+
+    def _mesh_block(self, points, cells, tolerance):
+        """The pool block of a triangle mesh (include/rpx.h, RPX_FACE_MESH): header, the raw points and
+        cells (all the reference object holds, obbtree.pyx:204-223), then triangle records in BVH leaf
+        order and the BVH nodes for the device traversal.  Returns (offset, n_cells, n_nodes)."""
+        from .core.obbtree import build_bvh, triangle_records
+        points = np.ascontiguousarray(points, dtype=np.double).reshape(-1, 3)
+        cells = np.ascontiguousarray(cells, dtype=np.int64).reshape(-1, 3)
+        if len(cells) < 1 or len(points) < 3:
+            raise ValueError("a mesh face needs at least one triangle")
+        if cells.min() < 0 or cells.max() >= len(points):
+            raise IndexError("mesh cell refers to a missing point")
+        order, nodes = build_bvh(points, cells)
+        p1, v1, v2, n = triangle_records(points, cells)
+        tris = np.zeros((len(cells), 16))
+        tris[:, 0:3], tris[:, 3:6], tris[:, 6:9], tris[:, 9:12] = p1[order], v1[order], v2[order], n[order]
+        tris[:, 12] = order
+        n_pts, n_cells, n_nodes = len(points), len(cells), len(nodes)
+        off_points = 8
+        off_cells = off_points + 3 * n_pts
+        off_tris = off_cells + 3 * n_cells
+        off_nodes = off_tris + 16 * n_cells
+        header = [n_pts, n_cells, n_nodes, off_points, off_cells, off_tris, off_nodes, float(tolerance)]
+        off = self._pool_add(header)
+        self._pool_add(points)
+        self._pool_add(cells.astype(np.double))
+        self._pool_add(tris)
+        self._pool_add(nodes)
+        return off, n_cells, n_nodes
 
     # -- shapes ---------------------------------------------------------------
     def _emit_shape(self, shape):
@@ -571,6 +600,21 @@ class Scene:
             p[0:6] = (z1, z2, pts[:, 0].min(), pts[:, 1].min(), pts[:, 0].max(), pts[:, 1].max())
             f['aux_off'] = self._pool_add(curves)
             f['aux_n'] = curves.shape[0]
+        elif name == "OBBTreeFace":
+            f['type'] = A.FACE_MESH
+            tree = face.obbtree
+            if hasattr(tree, "points") and hasattr(tree, "cells"):
+                points, cells = tree.points, tree.cells
+            else:  # reference object: OBBTree.points / .cells are private cdef members (obbtree.pxd);
+                # the owner that built the tree (raypier.meshes.STLFileMesh, meshes.py:49-67) still has them
+                o = face.owner
+                if not (hasattr(o, "mesh_points") and hasattr(o, "mesh_cells")):
+                    raise UnsupportedSceneError(
+                        "a genuine raypier OBBTree does not expose its mesh: give the owner mesh_points (N x 3) "
+                        "and mesh_cells (M x 3) attributes, or build the face from raypier_optics_b200.core.obbtree")
+                points, cells = o.mesh_points, o.mesh_cells
+            p[0] = tree.tolerance
+            f['aux_off'], f['aux_n'], f['aux_m'] = self._mesh_block(points, cells, tree.tolerance)
         elif name == "DistortionFace":
             f['type'] = A.FACE_DISTORTION
             p[0] = face.accuracy

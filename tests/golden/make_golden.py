@@ -36,6 +36,9 @@ GOLDEN_CASES = [
     # > 232 faces: scene tables beyond the shared-memory staging budget (SS=false kernels)
     ("big_scene_rays", dict(n=96, gausslets=False), None),
     ("big_scene", dict(n=40, gausslets=True), None),
+    # OBBTreeFace triangle meshes (coarser mirror mesh: the scene tables travel with the fixture)
+    ("mesh_rays", dict(n=160, gausslets=False, mesh_n=14), None),
+    ("mesh", dict(n=40, gausslets=True, mesh_n=14), None),
 ]
 
 

@@ -130,3 +130,32 @@ def test_parent_offsets():
     counts_all = np.array([[4, 4, 7], [3, 5, 5]])
     assert distributed.parent_offsets(counts_all, 0).tolist() == [0, 0, 0]
     assert distributed.parent_offsets(counts_all, 1).tolist() == [4, 4, 7]
+
+
+def test_mesh_bvh_covers_every_triangle_once():
+    """The BVH the host builds for OBBTreeFace meshes (core/obbtree.py::build_bvh): every cell in exactly
+    one leaf, children numbered after their parent (what rpx_scene_set validates), every box contains
+    the triangles below it."""
+    import numpy as np
+    from raypier_optics_b200 import configs
+    from raypier_optics_b200.core.obbtree import LEAF_CELLS, build_bvh
+    for pts, cells in (configs.icosphere(5.0, 2), configs.bowl_mesh(60.0, 17, 30.0), configs.icosphere(1.0, 0)):
+        order, nodes = build_bvh(pts, cells)
+        assert sorted(order.tolist()) == list(range(len(cells)))
+        cover = np.zeros(len(cells), dtype=int)
+
+        def check(k, lo, hi):
+            n = nodes[k]
+            assert (n[0:3] >= lo - 1e-12).all() and (n[3:6] <= hi + 1e-12).all()  # nested boxes
+            if n[6] >= 0:
+                assert n[6] > k and n[7] > k
+                check(int(n[6]), n[0:3], n[3:6])
+                check(int(n[7]), n[0:3], n[3:6])
+            else:
+                first, count = int(-n[6] - 1), int(n[7])
+                assert 1 <= count <= LEAF_CELLS
+                cover[first:first + count] += 1
+                tri = pts[cells[order[first:first + count]]].reshape(-1, 3)
+                assert (tri >= n[0:3]).all() and (tri <= n[3:6]).all()
+        check(0, np.full(3, -np.inf), np.full(3, np.inf))
+        assert (cover == 1).all()

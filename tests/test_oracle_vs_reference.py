@@ -13,6 +13,8 @@ from util import PARITY_CASES, build_case
 def test_oracle_bit_exact_with_reference(refcore, name, kw, rl):
     from oracle import oracle as O
     kw = dict(kw, n=min(kw.get("n", 2000), 4000))
+    if name == "mesh" and not hasattr(refcore, "obbtree"):
+        pytest.skip("the reference's obbtree module is not importable here (it needs PIL at import time)")
     cfg = build_case(refcore, name, kw, rl)
     rc = O.reference_collection(refcore, cfg['rays'], cfg['wavelengths'])
     traced, all_faces = O.reference_trace_rays(refcore, rc, cfg['face_lists'], cfg['recursion_limit'],

@@ -203,6 +203,10 @@ PARITY_CASES = [
     # path runs its global-memory (SS=false) kernel instantiations
     ("big_scene", dict(n=3000, gausslets=False), None),
     ("big_scene", dict(n=2000, gausslets=True), None),
+    # triangle-mesh optics (OBBTreeFace): icosphere ball lens + faceted mirror; gausslets
+    # between a faceted and a flat mirror (see configs.config_mesh for why no dielectric there)
+    ("mesh", dict(n=4000, gausslets=False), None),
+    ("mesh", dict(n=1500, gausslets=True), None),
 ]
 
 
