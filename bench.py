@@ -45,6 +45,8 @@ WORKLOADS = {
     "config4_grating": dict(n=1000000, kw={}),
     "config5": dict(n=1000000, kw=dict(gausslets=True),
                     capture=dict(centre=(0.0, -12.0, 0.0), direction=(0.0, 1.0, 0.0), size=(12.0, 12.0))),
+    # triangle-mesh optics: 20480-facet ball lens + 50562-facet mirror, BVH traversal
+    "mesh": dict(n=1000000, kw=dict(gausslets=False, ball_subdiv=5, mesh_n=160)),
     "config5_rays": dict(n=1000000, kw=dict(gausslets=False),
                          capture=dict(centre=(0.0, -12.0, 0.0), direction=(0.0, 1.0, 0.0), size=(12.0, 12.0))),
 }

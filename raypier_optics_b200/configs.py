@@ -393,7 +393,7 @@ def bowl_mesh(half_width=10.0, n=24, focal=20.0):
     return pts, np.array(cells, dtype=np.int32)
 
 
-def config_mesh(core, n=20000, seed=61, gausslets=False, mesh_n=40):
+def config_mesh(core, n=20000, seed=61, gausslets=False, mesh_n=40, ball_subdiv=2):
     """Triangle-mesh optics (raypier/meshes.py:16-67 builds OBBTreeFace from an STL file).
     Plain rays: a glass ball lens as an icosphere (FullDielectricMaterial: refraction, Fresnel reflections,
     TIR between facets) over a tilted faceted paraboloid mirror (PEC), both OBBTreeFace over an OBBTree.
@@ -423,7 +423,7 @@ def config_mesh(core, n=20000, seed=61, gausslets=False, mesh_n=40):
         face_lists = [fl_top, fl_mirror]
     else:
         ball = Pose(centre=(0.3, -0.2, 0.0), direction=(0.05, 0.02, 1.0))
-        pts, cells = icosphere(radius=5.0, subdivisions=2)
+        pts, cells = icosphere(radius=5.0, subdivisions=ball_subdiv)
         glass = M.FullDielectricMaterial(n_inside=1.5, n_outside=1.0)
         face_lists = [_facelist(core, ball, [mesh_face(ball, pts, cells, glass)]), fl_mirror]
     rays = disc_source(n, centre=(0., 0., 30.), axis=(0., 0., -1.), radius=4.0, seed=seed, E_vector=(1., 0., 0.),
