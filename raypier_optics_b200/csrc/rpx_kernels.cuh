@@ -146,17 +146,10 @@ RPX_DEV void stage_scene(DevScene& S, unsigned char* smem) {
 // the running (distance, face) pair lives in two registers.
 // only_face >= 0 restricts the search to that one face: FaceList.intersect_one_face_c
 // (ctracer.pyx:1861-1879), the sequential-mode step of trace_one_face_segment_c (:2121-2170).
+// Forced inline into its call sites: as a real call it cost 230 B of extra stack / spill traffic per
+// thread for the ABI (measured: k_shade 0.132 -> 0.125 ms, gausslets 1.107 -> 0.983 ms).
 template <int FC>
-// nearest_hit inlined into its two call sites: as a real call it cost 230 B of extra stack / spill
-// traffic per thread for the ABI (measured: k_shade 0.132 -> 0.125 ms, gausslets 1.107 -> 0.983 ms).
-#ifndef RPX_HIT_INLINE
-#define RPX_HIT_INLINE 1
-#endif
-#if RPX_HIT_INLINE
 __device__ __forceinline__ void nearest_hit(
-#else
-__device__ __noinline__ void nearest_hit(
-#endif
     const DevScene& S, vec3 o, vec3 d, double max_length, int only_face,
                                          double* out_len, uint32_t* out_face) {
     vec3 point = o + d * max_length;
@@ -457,14 +450,6 @@ k_capture(DevScene S, Soa in, Soa out, unsigned long long* tile_state, uint32_t*
     }
 }
 
-// Look-back before (1) or after (0) the trace-ahead work of a tile; see step 4a of k_shade.
-// Measured on B200: early is SLOWER (0.170 vs 0.133 ms per 1e6 rays) -- warp 0 then waits for the
-// slowest of 32 predecessors to even publish its aggregate (start jitter of thousands of cycles),
-// which the trace-ahead work otherwise hides.
-#ifndef RPX_LOOKBACK_EARLY
-#define RPX_LOOKBACK_EARLY 0
-#endif
-
 // ------------------------------------------------------------------ child staging
 // The children of one tile (<= 2 * RPX_TILE) are assembled in shared memory, field-major
 // like the SoA generation buffer: cs[field * RPX_SLOTS + slot], cu[field * RPX_SLOTS + slot].
@@ -472,23 +457,9 @@ k_capture(DevScene S, Soa in, Soa out, unsigned long long* tile_state, uint32_t*
 // (b) lets ANY thread of the block intersect ANY child (parents with 0 children help those
 // with 2), and (c) makes the final global stores fully coalesced (slot == consecutive
 // addresses) instead of stride-2.
-// RPX_FIXED_SLOTS=1: every thread stages its children the moment the material code has produced
-// them, into slots that depend only on the thread (reflected child: tid, transmitted child:
-// RPX_SLOT_B0 + tid), and a small map turns emission order into slot numbers for the trace-ahead
-// and the copy-out.  The ~58 registers of the two children then no longer live across the block
-// scan and its barrier.  RPX_SLOT_B0 = 136 = 128 + 8 keeps the two runs 64 B apart in the banks,
-// so a half-warp reading an a/b-interleaved run is still conflict free.
-// Measured on B200: no fewer spills (the register peak is inside the material code, not across
-// the scan) and SLOWER on config2 (0.136 vs 0.126 ms), equal on the Michelson -> off by default.
-#ifndef RPX_FIXED_SLOTS
-#define RPX_FIXED_SLOTS 0
-#endif
-#if RPX_FIXED_SLOTS
-#define RPX_SLOT_B0 (RPX_TILE + 8)
-#define RPX_SLOTS (2 * RPX_TILE + 8)
-#else
+// (Tried and measured slower, see profiles/r01_notes.md: thread-fixed staging slots with a
+// compaction map; the look-back before the trace-ahead instead of after it.)
 #define RPX_SLOTS (2 * RPX_TILE)
-#endif
 #define RPX_STAGE_BYTES (RPX_SLOTS * (NF * 8 + NU * 4))
 
 RPX_DEV void stage_child(double* cs, uint32_t* cu, uint32_t slot, const Kids& k, const Kid& c, uint32_t wl,
@@ -558,9 +529,6 @@ k_shade(DevScene S, Soa in, Soa out, double max_length, unsigned long long* tile
     __shared__ uint32_t s_tile;
     __shared__ uint32_t s_warp[RPX_TILE / 32];
     __shared__ unsigned long long s_prefix;
-#if RPX_FIXED_SLOTS
-    __shared__ unsigned short s_map[2 * RPX_TILE];  // emission order -> staging slot
-#endif
     // dynamic shared memory: [child staging][scene copy]
     double* cs = reinterpret_cast<double*>(smem);
     uint32_t* cu = reinterpret_cast<uint32_t*>(smem + RPX_SLOTS * NF * 8);
@@ -663,29 +631,6 @@ k_shade(DevScene S, Soa in, Soa out, double max_length, unsigned long long* tile
     }
 
     const uint32_t parent = (uint32_t)i;
-#if RPX_FIXED_SLOTS
-    // ---- 2. stage the children at once (thread-fixed slots): nothing of them stays in registers
-    const uint32_t fix_a = threadIdx.x, fix_b = RPX_SLOT_B0 + threadIdx.x;
-    if (k.has_a) stage_child(cs, cu, fix_a, k, k.a, wl, parent, ident);
-    if (k.has_b) stage_child(cs, cu, fix_b, k, k.b, wl, parent, ident);
-    // ---- 3. counts -> emission order inside the tile (reflected, then transmitted); publish
-    const uint32_t cnt = (k.has_a ? 1u : 0u) + (k.has_b ? 1u : 0u);
-    uint32_t total;
-    const uint32_t local = block_exclusive_scan(cnt, &total, s_warp);
-    if (threadIdx.x == 0) {
-        if (kGrouped)
-            tile_publish_grouped(tile_state, tile_state + n_tiles, tile, total);
-        else
-            tile_publish(tile_state, tile, total);
-        s_tile = next_tile;  // ... and hand it to the CTA (read after the next barrier)
-    }
-    const uint32_t slot_a = local, slot_b = local + (k.has_a ? 1u : 0u);  // emission positions
-    if (k.has_a) s_map[slot_a] = (unsigned short)fix_a;
-    if (k.has_b) s_map[slot_b] = (unsigned short)fix_b;
-    const uint32_t own_a = fix_a, own_b = fix_b;  // where this thread's children sit in the staging
-    __syncthreads();
-#define RPX_SRC(slot) ((uint32_t)s_map[slot])
-#else
     // ---- 2. counts -> offsets inside the tile; publish the tile aggregate
     const uint32_t cnt = (k.has_a ? 1u : 0u) + (k.has_b ? 1u : 0u);
     uint32_t total;
@@ -703,8 +648,6 @@ k_shade(DevScene S, Soa in, Soa out, double max_length, unsigned long long* tile
     if (k.has_b) stage_child(cs, cu, slot_b, k, k.b, wl, parent, ident);
     const uint32_t own_a = slot_a, own_b = slot_b;
     __syncthreads();
-#define RPX_SRC(slot) (slot)
-#endif
     {   // pull the next tile's parent records towards L2 while this tile computes
         const uint32_t nt = s_tile;
 #if RPX_BULK_PREFETCH
@@ -743,26 +686,10 @@ k_shade(DevScene S, Soa in, Soa out, double max_length, unsigned long long* tile
             }
         }
     }
-#if RPX_LOOKBACK_EARLY
-    // ---- 4a. (experiment, off) global offset resolved by warp 0 BEFORE its share of the trace-ahead
-    if (threadIdx.x < 32) {
-        unsigned long long excl = tile_lookback(tile_state, tile, total);
-        if (threadIdx.x == 0) {
-            s_prefix = excl;
-            if (tile == n_tiles_real - 1) {  // len(new_rays)
-                *d_count = excl + total;
-                if (h_count) {  // pipelined loop: straight into mapped pinned host memory, no copy op
-                    *h_count = excl + total;
-                    __threadfence_system();
-                }
-            }
-        }
-    }
-#endif
     // ---- 4. trace ahead
     if (ahead_face != -2) {
         for (uint32_t slot = threadIdx.x; slot < total; slot += RPX_TILE) {
-            const uint32_t src = RPX_SRC(slot);
+            const uint32_t src = slot;
             const double* f = cs + src;
             vec3 o = v3(f[F_OX * RPX_SLOTS], f[F_OY * RPX_SLOTS], f[F_OZ * RPX_SLOTS]);
             vec3 d = v3(f[F_DX * RPX_SLOTS], f[F_DY * RPX_SLOTS], f[F_DZ * RPX_SLOTS]);
@@ -786,7 +713,6 @@ k_shade(DevScene S, Soa in, Soa out, double max_length, unsigned long long* tile
         }
     }
     // ---- 5. global offset of the tile
-#if !RPX_LOOKBACK_EARLY
     if (threadIdx.x < 32) {
         const unsigned long long excl =
             kGrouped ? tile_lookback_grouped(tile_state, tile_state + n_tiles,
@@ -803,7 +729,6 @@ k_shade(DevScene S, Soa in, Soa out, double max_length, unsigned long long* tile
             }
         }
     }
-#endif
     __syncthreads();
     const unsigned long long base = s_prefix;
     // ---- 6. coalesced copy-out: slot == consecutive addresses.  Two explicit passes (a tile has
@@ -816,7 +741,7 @@ k_shade(DevScene S, Soa in, Soa out, double max_length, unsigned long long* tile
         for (int pass = 0; pass < 2; pass++) {
             const uint32_t slot = threadIdx.x + pass * RPX_TILE;
             if (slot < total) {
-                const uint32_t from = RPX_SRC(slot);
+                const uint32_t from = slot;
                 double* dst = out.f + base + slot;
                 const double* src = cs + from;
 #pragma unroll
