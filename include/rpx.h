@@ -476,7 +476,9 @@ void rpx_field_free(rpx_ctx* ctx, rpx_field* field);
 /* Face.intersect(p1, p2, is_base_ray) (ctracer.pyx:1769-1777): p1/p2 are n x 3 local points */
 int rpx_unit_face_intersect(rpx_ctx* ctx, int face, const double* p1, const double* p2, uint64_t n,
                             int is_base_ray, double* out_dist);
-/* FaceList.compute_orientation(face, point) (ctracer.pyx:1955-1964): n x 3 GLOBAL points */
+/* FaceList.compute_orientation(face, point) (ctracer.pyx:1955-1964): n x 3 GLOBAL points.  The
+ * reference's wrapper also takes a `piece`; this entry evaluates piece 0 (for RPX_FACE_MESH: the facet
+ * normal of cell 0 -- the trace itself uses the piece that was hit).                              */
 int rpx_unit_face_normal(rpx_ctx* ctx, int face, const double* points, uint64_t n,
                          double* out_normal, double* out_tangent);
 /* InterfaceMaterial.eval_child_ray(ray, idx, point, normal, tangent, new_rays)
