@@ -220,14 +220,17 @@ class Scene:
         self._zcoefs = []
         self._ztape = []
         self._ntab = []
-        self._pool = []
+        self._pool = []      # numpy chunks (a mesh block is millions of doubles: no Python float lists)
+        self._pool_len = 0
         self._build()
         self._finalise()
 
     # -- pool helpers ---------------------------------------------------------
     def _pool_add(self, values):
-        off = len(self._pool)
-        self._pool.extend(np.asarray(values, dtype=np.double).reshape(-1).tolist())
+        off = self._pool_len
+        chunk = np.array(values, dtype=np.double).reshape(-1)  # a private copy
+        self._pool.append(chunk)
+        self._pool_len += chunk.shape[0]
         return off
 
     def _mesh_block(self, points, cells, tolerance):
@@ -665,7 +668,7 @@ class Scene:
         self.ztape = self._stack(self._ztape, A.ztape_op_dtype)
         self.ntab = (np.array(self._ntab, dtype=np.complex128) if self._ntab
                      else np.zeros(1, dtype=np.complex128))
-        self.pool = (np.array(self._pool, dtype=np.double) if self._pool
+        self.pool = (np.ascontiguousarray(np.concatenate(self._pool)) if self._pool_len
                      else np.zeros(1, dtype=np.double))
         wl = self.wavelengths if len(self.wavelengths) else np.zeros(1)
         self._wl_buf = np.ascontiguousarray(wl, dtype=np.double)
@@ -682,7 +685,7 @@ class Scene:
         s.n_ztape = len(self._ztape)
         s.n_wavelengths = len(self.wavelengths)
         s.n_ntab = len(self._ntab)
-        s.n_pool = len(self._pool)
+        s.n_pool = self._pool_len
         for name, arr in (("faces", self.faces), ("face_sets", self.face_sets),
                           ("materials", self.materials), ("shape_ops", self.shape_ops),
                           ("implicit_ops", self.implicit_ops), ("distortions", self.distortions),
