@@ -460,7 +460,75 @@ k_capture(DevScene S, Soa in, Soa out, unsigned long long* tile_state, uint32_t*
 // (Tried and measured slower, see profiles/r01_notes.md: thread-fixed staging slots with a
 // compaction map; the look-back before the trace-ahead instead of after it.)
 #define RPX_SLOTS (2 * RPX_TILE)
+// RPX_LEAN_STAGE=1 (experiment prepared for the next round, NOT yet measured or parity-tested on a
+// GPU; default 0): the two children of a parent share origin, normal, E_vector, phase, accumulated
+// path, wavelength index and ray ident -- store those ONCE per parent (11 doubles + 2 words x
+// RPX_TILE) and only direction, n, E1, E2, length, type, end face per child (10 doubles + 2 words x
+// RPX_SLOTS), plus a byte map slot -> parent.  35 KB instead of 47 KB per CTA: room for 5 CTAs / SM
+// (at 96 registers, RPX_MIN_BLOCKS=5) where registers and shared memory both capped it at 4.
+#ifndef RPX_LEAN_STAGE
+#define RPX_LEAN_STAGE 0
+#endif
+#if RPX_LEAN_STAGE
+enum { LP_OX = 0, LP_OY, LP_OZ, LP_NX, LP_NY, LP_NZ, LP_EX, LP_EY, LP_EZ, LP_PHASE, LP_APATH, LP_NF = 11 };
+enum { LC_DX = 0, LC_DY, LC_DZ, LC_NR, LC_NI, LC_E1R, LC_E1I, LC_E2R, LC_E2I, LC_LEN, LC_NF = 10 };
+enum { LPU_WL = 0, LPU_IDENT, LPU_NU = 2 };
+enum { LCU_TYPE = 0, LCU_ENDFACE, LCU_NU = 2 };
+#define RPX_LEAN_PAR_F 0                                                   /* doubles [LP_NF][RPX_TILE]   */
+#define RPX_LEAN_CH_F (RPX_LEAN_PAR_F + LP_NF * RPX_TILE * 8)              /* doubles [LC_NF][RPX_SLOTS]  */
+#define RPX_LEAN_PAR_U (RPX_LEAN_CH_F + LC_NF * RPX_SLOTS * 8)             /* words   [LPU_NU][RPX_TILE]  */
+#define RPX_LEAN_CH_U (RPX_LEAN_PAR_U + LPU_NU * RPX_TILE * 4)             /* words   [LCU_NU][RPX_SLOTS] */
+#define RPX_LEAN_MAP (RPX_LEAN_CH_U + LCU_NU * RPX_SLOTS * 4)              /* bytes   [RPX_SLOTS]         */
+#define RPX_STAGE_BYTES (((RPX_LEAN_MAP + RPX_SLOTS) + 15) / 16 * 16)
+struct LeanStage {
+    double* pf;         // per-parent doubles
+    double* cf;         // per-child doubles
+    uint32_t* pu;       // per-parent words
+    uint32_t* cu;       // per-child words
+    unsigned char* map; // slot -> parent (thread) index
+};
+RPX_DEV LeanStage lean_stage(unsigned char* smem) {
+    LeanStage L;
+    L.pf = reinterpret_cast<double*>(smem + RPX_LEAN_PAR_F);
+    L.cf = reinterpret_cast<double*>(smem + RPX_LEAN_CH_F);
+    L.pu = reinterpret_cast<uint32_t*>(smem + RPX_LEAN_PAR_U);
+    L.cu = reinterpret_cast<uint32_t*>(smem + RPX_LEAN_CH_U);
+    L.map = smem + RPX_LEAN_MAP;
+    return L;
+}
+RPX_DEV void lean_stage_parent(const LeanStage& L, uint32_t p, const Kids& k, uint32_t wl, uint32_t ident) {
+    double* f = L.pf + p;
+    f[LP_OX * RPX_TILE] = k.origin.x;
+    f[LP_OY * RPX_TILE] = k.origin.y;
+    f[LP_OZ * RPX_TILE] = k.origin.z;
+    f[LP_NX * RPX_TILE] = k.normal.x;
+    f[LP_NY * RPX_TILE] = k.normal.y;
+    f[LP_NZ * RPX_TILE] = k.normal.z;
+    f[LP_EX * RPX_TILE] = k.evec.x;
+    f[LP_EY * RPX_TILE] = k.evec.y;
+    f[LP_EZ * RPX_TILE] = k.evec.z;
+    f[LP_PHASE * RPX_TILE] = k.phase;
+    f[LP_APATH * RPX_TILE] = k.apath;
+    L.pu[LPU_WL * RPX_TILE + p] = wl;
+    L.pu[LPU_IDENT * RPX_TILE + p] = ident;
+}
+RPX_DEV void lean_stage_child(const LeanStage& L, uint32_t slot, uint32_t p, const Kid& c) {
+    double* f = L.cf + slot;
+    f[LC_DX * RPX_SLOTS] = c.dir.x;
+    f[LC_DY * RPX_SLOTS] = c.dir.y;
+    f[LC_DZ * RPX_SLOTS] = c.dir.z;
+    f[LC_NR * RPX_SLOTS] = c.n.re;
+    f[LC_NI * RPX_SLOTS] = c.n.im;
+    f[LC_E1R * RPX_SLOTS] = c.e1.re;
+    f[LC_E1I * RPX_SLOTS] = c.e1.im;
+    f[LC_E2R * RPX_SLOTS] = c.e2.re;
+    f[LC_E2I * RPX_SLOTS] = c.e2.im;
+    L.cu[LCU_TYPE * RPX_SLOTS + slot] = c.type;
+    L.map[slot] = (unsigned char)p;
+}
+#else
 #define RPX_STAGE_BYTES (RPX_SLOTS * (NF * 8 + NU * 4))
+#endif
 
 RPX_DEV void stage_child(double* cs, uint32_t* cu, uint32_t slot, const Kids& k, const Kid& c, uint32_t wl,
                          uint32_t parent, uint32_t ident) {
@@ -508,7 +576,7 @@ RPX_DEV void stage_child(double* cs, uint32_t* cu, uint32_t slot, const Kids& k,
 // bulk copies and warp-granular tiles were both tried and were slower -- 22 sub-KB bulk copies
 // per tile serialise in the TMA unit, and 4x more tiles mean 4x more look-backs.
 #ifndef RPX_MIN_BLOCKS
-#define RPX_MIN_BLOCKS 4
+#define RPX_MIN_BLOCKS 4  // build the lean-staging experiment with -DRPX_LEAN_STAGE=1 -DRPX_MIN_BLOCKS=5
 #endif
 #ifndef RPX_BULK_PREFETCH
 #define RPX_BULK_PREFETCH 1
@@ -530,8 +598,12 @@ k_shade(DevScene S, Soa in, Soa out, double max_length, unsigned long long* tile
     __shared__ uint32_t s_warp[RPX_TILE / 32];
     __shared__ unsigned long long s_prefix;
     // dynamic shared memory: [child staging][scene copy]
+#if RPX_LEAN_STAGE
+    const LeanStage L = lean_stage(smem);
+#else
     double* cs = reinterpret_cast<double*>(smem);
     uint32_t* cu = reinterpret_cast<uint32_t*>(smem + RPX_SLOTS * NF * 8);
+#endif
     stage_scene<SS>(S, smem + RPX_STAGE_BYTES);  // once per (persistent) CTA
     const unsigned long long n_in = n_dev ? *n_dev : in.n;
     const uint32_t n_tiles_real = (uint32_t)((n_in + RPX_TILE - 1) / RPX_TILE);
@@ -644,8 +716,14 @@ k_shade(DevScene S, Soa in, Soa out, double max_length, unsigned long long* tile
     }
     // ---- 3. stage children in emission order (reflected, then transmitted)
     const uint32_t slot_a = local, slot_b = local + (k.has_a ? 1u : 0u);
+#if RPX_LEAN_STAGE
+    if (cnt) lean_stage_parent(L, threadIdx.x, k, wl, ident);
+    if (k.has_a) lean_stage_child(L, slot_a, threadIdx.x, k.a);
+    if (k.has_b) lean_stage_child(L, slot_b, threadIdx.x, k.b);
+#else
     if (k.has_a) stage_child(cs, cu, slot_a, k, k.a, wl, parent, ident);
     if (k.has_b) stage_child(cs, cu, slot_b, k, k.b, wl, parent, ident);
+#endif
     const uint32_t own_a = slot_a, own_b = slot_b;
     __syncthreads();
     {   // pull the next tile's parent records towards L2 while this tile computes
@@ -689,20 +767,42 @@ k_shade(DevScene S, Soa in, Soa out, double max_length, unsigned long long* tile
     // ---- 4. trace ahead
     if (ahead_face != -2) {
         for (uint32_t slot = threadIdx.x; slot < total; slot += RPX_TILE) {
+#if RPX_LEAN_STAGE
+            const double* fp = L.pf + L.map[slot];
+            const double* fc = L.cf + slot;
+            vec3 o = v3(fp[LP_OX * RPX_TILE], fp[LP_OY * RPX_TILE], fp[LP_OZ * RPX_TILE]);
+            vec3 d = v3(fc[LC_DX * RPX_SLOTS], fc[LC_DY * RPX_SLOTS], fc[LC_DZ * RPX_SLOTS]);
+#else
             const uint32_t src = slot;
             const double* f = cs + src;
             vec3 o = v3(f[F_OX * RPX_SLOTS], f[F_OY * RPX_SLOTS], f[F_OZ * RPX_SLOTS]);
             vec3 d = v3(f[F_DX * RPX_SLOTS], f[F_DY * RPX_SLOTS], f[F_DZ * RPX_SLOTS]);
+#endif
             double len;
             uint32_t face;
             nearest_hit<FC>(S, o, d, max_length, ahead_face, &len, &face);
+#if RPX_LEAN_STAGE
+            L.cf[LC_LEN * RPX_SLOTS + slot] = len;
+            L.cu[LCU_ENDFACE * RPX_SLOTS + slot] = face;
+#else
             cs[F_LEN * RPX_SLOTS + src] = len;
             cu[U_ENDFACE * RPX_SLOTS + src] = face;
+#endif
         }
     } else {
         // untraced: sp_ray.length = INF (every material; gausslets: reset_length_c -> max_length),
         // end_face_idx still the copy of the parent's (the face that was just hit)
         const double untraced_len = GAUSS ? max_length : RPX_INF;
+#if RPX_LEAN_STAGE
+        if (k.has_a) {
+            L.cf[LC_LEN * RPX_SLOTS + own_a] = untraced_len;
+            L.cu[LCU_ENDFACE * RPX_SLOTS + own_a] = face_idx;
+        }
+        if (k.has_b) {
+            L.cf[LC_LEN * RPX_SLOTS + own_b] = untraced_len;
+            L.cu[LCU_ENDFACE * RPX_SLOTS + own_b] = face_idx;
+        }
+#else
         if (k.has_a) {
             cs[F_LEN * RPX_SLOTS + own_a] = untraced_len;
             cu[U_ENDFACE * RPX_SLOTS + own_a] = face_idx;
@@ -711,6 +811,7 @@ k_shade(DevScene S, Soa in, Soa out, double max_length, unsigned long long* tile
             cs[F_LEN * RPX_SLOTS + own_b] = untraced_len;
             cu[U_ENDFACE * RPX_SLOTS + own_b] = face_idx;
         }
+#endif
     }
     // ---- 5. global offset of the tile
     if (threadIdx.x < 32) {
@@ -741,15 +842,35 @@ k_shade(DevScene S, Soa in, Soa out, double max_length, unsigned long long* tile
         for (int pass = 0; pass < 2; pass++) {
             const uint32_t slot = threadIdx.x + pass * RPX_TILE;
             if (slot < total) {
-                const uint32_t from = slot;
                 double* dst = out.f + base + slot;
+                uint32_t* dstu = out.u + base + slot;
+#if RPX_LEAN_STAGE
+                const uint32_t p = L.map[slot];
+                const double* sp = L.pf + p;
+                const double* sc = L.cf + slot;
+                // SoA field <- (per-parent | per-child) staging row
+                constexpr int kParRow[NF] = {LP_OX, LP_OY, LP_OZ, -1, -1, -1, LP_NX, LP_NY, LP_NZ, LP_EX, LP_EY, LP_EZ,
+                                             -1, -1, -1, -1, -1, -1, -1, LP_PHASE, LP_APATH};
+                constexpr int kChRow[NF] = {-1, -1, -1, LC_DX, LC_DY, LC_DZ, -1, -1, -1, -1, -1, -1,
+                                            LC_NR, LC_NI, LC_E1R, LC_E1I, LC_E2R, LC_E2I, LC_LEN, -1, -1};
+#pragma unroll
+                for (int fld = 0; fld < NF; fld++)
+                    dst[(unsigned long long)fld * ocap] =
+                        kParRow[fld] >= 0 ? sp[kParRow[fld] * RPX_TILE] : sc[kChRow[fld] * RPX_SLOTS];
+                dstu[(unsigned long long)U_WL * ocap] = L.pu[LPU_WL * RPX_TILE + p];
+                dstu[(unsigned long long)U_PARENT * ocap] = tile * RPX_TILE + p;
+                dstu[(unsigned long long)U_ENDFACE * ocap] = L.cu[LCU_ENDFACE * RPX_SLOTS + slot];
+                dstu[(unsigned long long)U_IDENT * ocap] = L.pu[LPU_IDENT * RPX_TILE + p];
+                dstu[(unsigned long long)U_TYPE * ocap] = L.cu[LCU_TYPE * RPX_SLOTS + slot];
+#else
+                const uint32_t from = slot;
                 const double* src = cs + from;
 #pragma unroll
                 for (int fld = 0; fld < NF; fld++) dst[(unsigned long long)fld * ocap] = src[fld * RPX_SLOTS];
-                uint32_t* dstu = out.u + base + slot;
                 const uint32_t* srcu = cu + from;
 #pragma unroll
                 for (int fld = 0; fld < NU; fld++) dstu[(unsigned long long)fld * ocap] = srcu[fld * RPX_SLOTS];
+#endif
             }
         }
     }
