@@ -311,15 +311,80 @@ class GaussletCollection(_Collection):
                 g['para_rays']['normal'][:, jj] = b['normal']
                 g['para_rays']['length'][:, jj] = b['length']
 
+    def project_to_plane(self, origin, direction):
+        """ctracer.pyx:1391-1420: move every base ray and its six parabasal rays along their own
+        directions onto the plane through ``origin`` with normal ``direction``; the base ray's
+        accumulated_path grows by Re(n) * distance.  Vectorised with the per-element operation order of
+        the reference's loop (dotprod_ = x*x' + y*y' + z*z', left to right)."""
+        g = self._data
+        if g.shape[0] == 0:
+            return
+        o = np.array([float(v) for v in origin], dtype=np.double)
+        d = np.array([float(v) for v in direction], dtype=np.double)
+        d = d / math.sqrt(d[0] * d[0] + d[1] * d[1] + d[2] * d[2])  # norm_
+
+        def dot(a):  # dotprod_(a, d) over the last axis
+            return a[..., 0] * d[0] + a[..., 1] * d[1] + a[..., 2] * d[2]
+
+        b = g['base_ray']
+        a = dot(o - b['origin']) / dot(b['direction'])
+        b['origin'] = b['origin'] + b['direction'] * a[:, None]
+        b['accumulated_path'] += b['refractive_index'].real * a
+        p = g['para_rays']
+        a = dot(o - p['origin']) / dot(p['direction'])
+        p['origin'] = p['origin'] + p['direction'] * a[..., None]
+
+    @property
+    def lagrange_invariant(self):
+        """ctracer.pyx:1347-1389: the (normalised) Lagrange invariant of every gausslet, 1 for a
+        diffraction-limited fundamental mode."""
+        g = self._data
+        b, p = g['base_ray'], g['para_rays']
+        e = b['E_vector']
+        axis1 = e / np.sqrt(e[:, 0] * e[:, 0] + e[:, 1] * e[:, 1] + e[:, 2] * e[:, 2])[:, None]
+        dd = b['direction']
+        axis2 = np.stack([axis1[:, 1] * dd[:, 2] - axis1[:, 2] * dd[:, 1],
+                          axis1[:, 2] * dd[:, 0] - axis1[:, 0] * dd[:, 2],
+                          axis1[:, 0] * dd[:, 1] - axis1[:, 1] * dd[:, 0]], axis=1)
+
+        def dot3(a, c):
+            return a[..., 0] * c[..., 0] + a[..., 1] * c[..., 1] + a[..., 2] * c[..., 2]
+
+        off = p['origin'] - b['origin'][:, None, :]
+        hx, hy = dot3(off, axis1[:, None, :]), dot3(off, axis2[:, None, :])
+        ux, uy = dot3(p['direction'], axis1[:, None, :]), dot3(p['direction'], axis2[:, None, :])
+
+        def term(i, j):  # (h_i . u_j - h_j . u_i)^2 with the z components zero
+            hu = hx[:, i] * ux[:, j] + hy[:, i] * uy[:, j] + 0.0 * 0.0
+            uh = hx[:, j] * ux[:, i] + hy[:, j] * uy[:, i] + 0.0 * 0.0
+            return (hu - uh) ** 2
+
+        v = np.zeros(g.shape[0])
+        for i, j in ((0, 5), (1, 2), (3, 4), (1, 4), (0, 3), (2, 5)):
+            v = v + term(i, j)
+        wavelen = np.asarray(self.wavelengths, dtype=np.double)
+        return 1000 * np.sqrt(v / 6) / wavelen[b['wavelength_idx']]
+
+    def extend(self, gc):
+        """ctracer.pyx:1294-1303: append the gausslets of another collection."""
+        self._data = np.concatenate([self._data, np.asarray(gc.copy_as_array()).view(gausslet_dtype)])
+
     def scale_amplitude(self, scale):
         self._data['base_ray']['E1_amp'] *= scale
         self._data['base_ray']['E2_amp'] *= scale
 
     @property
     def total_power(self):
+        # ctracer.pyx:1487-1502: four terms per ray added in sequence (cumsum keeps the loop's order,
+        # np.sum would add pairwise)
         b = self._data['base_ray']
+        if b.shape[0] == 0:
+            return 0.0
         n = b['refractive_index'].real
-        return float(np.sum((abs(b['E1_amp']) ** 2 + abs(b['E2_amp']) ** 2) * n))
+        e1, e2 = b['E1_amp'], b['E2_amp']
+        terms = np.stack([(e1.real * e1.real) * n, (e1.imag * e1.imag) * n,
+                          (e2.real * e2.real) * n, (e2.imag * e2.imag) * n], axis=1).reshape(-1)
+        return float(np.cumsum(terms)[-1])
 
     @property
     def para_origin(self):

@@ -63,3 +63,30 @@ def test_reference_bezier_face_is_broken_here(refcore):
     rc = O.reference_collection(refcore, cfg['rays'], cfg['wavelengths'])
     with pytest.raises(TypeError):
         O.reference_trace_rays(refcore, rc, cfg['face_lists'], cfg['recursion_limit'], cfg['max_length'])
+
+
+def test_gausslet_collection_helpers_match_reference(refcore, core):
+    """GaussletCollection.project_to_plane / lagrange_invariant / total_power / extend of the host mirror
+    (ctracer.pyx:1347-1420, 1487-1502, 1294-1303) against the reference's own, bit for bit, on the
+    gausslets leaving the Michelson."""
+    from oracle import oracle as O
+    from raypier_optics_b200 import configs
+    cfg = configs.build(core, "config5", n=300, gausslets=True)
+    sc = SC.Scene(cfg['face_lists'], cfg['wavelengths'])
+    gens, _ = O.trace_rays(sc, cfg['rays'], cfg['recursion_limit'], cfg['max_length'])
+    g = np.ascontiguousarray(gens[-1])
+    wl = np.asarray(cfg['wavelengths'])
+    ref = refcore.ctracer.GaussletCollection.from_array(g.view(refcore.ctracer.gausslet_dtype).copy())
+    mir = core.ctracer.GaussletCollection.from_array(g.copy())
+    ref.wavelengths = wl
+    mir.wavelengths = wl
+    assert np.asarray(ref.lagrange_invariant).tobytes() == np.asarray(mir.lagrange_invariant).tobytes()
+    assert ref.total_power == mir.total_power
+    for origin, direction in (((0., -14., 0.), (0., 1., 0.)), ((1., -20., 0.5), (0.1, -1., 0.2))):
+        ref.project_to_plane(origin, direction)
+        mir.project_to_plane(origin, direction)
+        assert ref.copy_as_array().tobytes() == mir.copy_as_array().tobytes()
+    other = core.ctracer.GaussletCollection.from_array(g[:7].copy())
+    n0 = len(mir)
+    mir.extend(other)
+    assert len(mir) == n0 + 7 and mir.copy_as_array()[n0:].tobytes() == g[:7].tobytes()
