@@ -227,14 +227,27 @@ for _name in ray_dtype.names:
 
 
 class GaussletBaseRayView(object):
+    """ctracer.pyx:1157-1183: the base rays of a GaussletCollection seen through the RayArrayView API
+    (ctracer.pyx:717-969): ``len``, ``copy_as_array`` and one array property per ray_t member --
+    e.g. ``gausslets.base_rays.end_face_idx``, which BaseRaySource.set_face_sequence (sources.py:138-155)
+    reads for every traced generation."""
+
     def __init__(self, owner):
         self.owner = owner
 
     def __len__(self):
         return self.owner.n_rays
 
+    def _base(self):
+        return self.owner._data['base_ray']
+
     def copy_as_array(self):
         return np.ascontiguousarray(self.owner._data['base_ray']).copy()
+
+    @property
+    def termination(self):
+        d = self._base()
+        return d['origin'] + d['direction'] * d['length'][:, None]
 
 
 class GaussletCollection(_Collection):
@@ -401,6 +414,7 @@ class GaussletCollection(_Collection):
 
 for _name in ray_dtype.names:
     setattr(GaussletCollection, _name, _ray_field(_name))
+    setattr(GaussletBaseRayView, _name, _ray_field(_name))
 
 
 class InterfaceMaterial(object):

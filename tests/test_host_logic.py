@@ -159,3 +159,33 @@ def test_mesh_bvh_covers_every_triangle_once():
                 assert (tri >= n[0:3]).all() and (tri <= n[3:6]).all()
         check(0, np.full(3, -np.inf), np.full(3, np.inf))
         assert (cover == 1).all()
+
+
+def test_face_sequence_inference_works_on_mirror_collections(core):
+    """BaseRaySource.set_face_sequence (raypier/sources.py:138-155) reads ``rays.base_rays.end_face_idx`` of
+    every traced generation and takes the most common face; the host collections must offer that API for
+    rays AND gausslets (GaussletBaseRayView is a RayArrayView in the reference, ctracer.pyx:1157)."""
+    import numpy as np
+    from oracle import oracle as O
+    from raypier_optics_b200 import configs, scene as SC
+    for gausslets in (False, True):
+        cfg = configs.build(core, "config5", n=200, gausslets=gausslets)
+        sc = SC.Scene(cfg['face_lists'], cfg['wavelengths'])
+        gens, _ = O.trace_rays(sc, cfg['rays'], cfg['recursion_limit'], cfg['max_length'])
+        cls = core.ctracer.GaussletCollection if gausslets else core.ctracer.RayCollection
+        traced = [cls.from_array(np.ascontiguousarray(g)) for g in gens]
+        all_faces = [f for fl in cfg['face_lists'] for f in fl.faces]
+        # the reference's own lines
+        global_map = {face: i for i, face in enumerate(all_faces)}
+        face_map = {global_map[face]: (fl, fi) for fl in cfg['face_lists'] for fi, face in enumerate(fl.faces)}
+        seq = []
+        for rays in traced:
+            ids, counts = np.unique(rays.base_rays.end_face_idx, return_counts=True)
+            most_common = ids[counts.argmax()]
+            if most_common not in face_map:
+                break
+            seq.append(face_map[most_common])
+        assert len(seq) >= 4 and seq[0][0] is cfg['face_lists'][0]
+        view = traced[1].base_rays
+        assert len(view) == len(traced[1]) and view.origin.shape == (len(view), 3)
+        assert view.termination.shape == (len(view), 3)
