@@ -13,6 +13,8 @@
 #include <cstring>
 #include <new>
 #include <string>
+#include <cstddef>
+#include <cstring>
 #include <vector>
 
 #include "../../include/rpx.h"
@@ -71,6 +73,8 @@ extern "C" int rpx_init(int device, rpx_ctx** out_ctx) {
     ctx->have_copy_streams = false;
     for (int k = 0; k < 2; k++) { ctx->st_in[k] = nullptr; ctx->st_in_bytes[k] = 0; }
     for (int k = 0; k < 4; k++) { ctx->st_out[k] = nullptr; ctx->st_out_bytes[k] = 0; ctx->st_out_busy[k] = false; }
+    ctx->h_wb = nullptr;
+    ctx->h_wb_bytes = 0;
     ctx->have_capture = false;
     ctx->cap_block = nullptr;
     ctx->cap_face_ids = nullptr;
@@ -126,6 +130,7 @@ extern "C" void rpx_shutdown(rpx_ctx* ctx) {
     cudaFree(ctx->pipe_counters);
     cudaFree(ctx->pipe_state);
     cudaFreeHost(ctx->h_counts);
+    if (ctx->h_wb) cudaFreeHost(ctx->h_wb);
     cudaFree(ctx->d_count);
     cudaFreeHost(ctx->h_count);
     if (ctx->have_copy_streams) {
@@ -1029,8 +1034,50 @@ extern "C" int rpx_trace_streamed(rpx_ctx* ctx, const void* rays_aos, uint64_t n
         cudaEventCreateWithFlags(&ev_used[k], cudaEventDisableTiming);
     }
     cudaEventCreateWithFlags(&ev_ready, cudaEventDisableTiming);
+    // In-place tracing (out_gens[0] IS the source array, the reference's own semantics: traced_rays[0] is
+    // input_rays, mutated in place, ctracer.pyx:2086-2087 / 1900-1903): generation 0 then differs from
+    // what the caller already holds only in `length` and `end_face_idx`, so only those 12 of the 188
+    // bytes per ray come back over PCIe; they land in a pinned scratch area and are scattered into the
+    // caller's records by this thread while later chunks are in flight.  (Plain rays only: a gausslet
+    // also gets its six parabasal lengths back and generation 0 is 5 % of its download anyway.)
+    const bool inplace0 = n_chunks && !is_gausslet && out_gens[0] == rays_aos;
+    struct PendingWb {
+        cudaEvent_t ev;
+        uint64_t lo, m;
+    };
+    std::vector<PendingWb> pending;
+    size_t pending_done = 0;
+    auto drain_writebacks = [&](bool wait) {
+        unsigned char* dst = (unsigned char*)out_gens[0];
+        while (pending_done < pending.size()) {
+            PendingWb& w = pending[pending_done];
+            if (wait) {
+                if (cudaEventSynchronize(w.ev) != cudaSuccess) break;
+            } else if (cudaEventQuery(w.ev) != cudaSuccess) {
+                break;
+            }
+            const unsigned char* len = ctx->h_wb + w.lo * 12;
+            const unsigned char* face = len + w.m * 8;
+            for (uint64_t i = 0; i < w.m; i++) {
+                unsigned char* recp = dst + (w.lo + i) * RPX_RAY_BYTES;
+                memcpy(recp + offsetof(rpx_ray, length), len + i * 8, 8);
+                memcpy(recp + offsetof(rpx_ray, end_face_idx), face + i * 4, 4);
+            }
+            cudaEventDestroy(w.ev);
+            pending_done++;
+        }
+    };
+    if (inplace0 && ctx->h_wb_bytes < n * 12) {
+        if (ctx->h_wb) cudaFreeHost(ctx->h_wb);
+        ctx->h_wb = nullptr;
+        ctx->h_wb_bytes = 0;
+        if ((e = cudaHostAlloc((void**)&ctx->h_wb, n * 12, cudaHostAllocDefault)) != cudaSuccess)
+            rc = fail(ctx, RPX_ERR_NOMEM, "write-back scratch (%llu bytes): %s", (unsigned long long)(n * 12), cudaGetErrorString(e));
+        else
+            ctx->h_wb_bytes = n * 12;
+    }
     const uint64_t in_bytes = (n < chunk_rays ? n : chunk_rays) * rec;
-    if (n_chunks) {
+    if (n_chunks && rc == RPX_OK) {
         for (int k = 0; k < (n_chunks > 1 ? 2 : 1) && e == cudaSuccess; k++) {
             if (ctx->st_in_bytes[k] < in_bytes) {  // grow once; kept for later calls
                 if (ctx->st_in[k]) cudaFree(ctx->st_in[k]);
@@ -1058,6 +1105,7 @@ extern "C" int rpx_trace_streamed(rpx_ctx* ctx, const void* rays_aos, uint64_t n
     for (uint64_t c = 0; c < n_chunks && rc == RPX_OK; c++) {
         const int b = (int)(c & 1);
         const uint64_t lo = c * chunk_rays, cnt = (n - lo < chunk_rays) ? n - lo : chunk_rays;
+        if (inplace0) drain_writebacks(false);
         if (c + 1 < n_chunks && (e = issue_upload(c + 1)) != cudaSuccess) {
             rc = fail(ctx, RPX_ERR_CUDA, "chunk upload: %s", cudaGetErrorString(e));
             break;
@@ -1118,6 +1166,33 @@ extern "C" int rpx_trace_streamed(rpx_ctx* ctx, const void* rays_aos, uint64_t n
                 ctx->st_out_bytes[k] = want;
             }
             void* d_stage = ctx->st_out[k];
+            if (g == 0 && inplace0) {
+                // the two write-back rows of the SoA generation, packed [m doubles][m words], through the
+                // same staging ring (the generation buffer itself goes back to the pool right after)
+                const unsigned long long cap0 = gen->soa.cap;
+                e = cudaMemcpyAsync(d_stage, gen->soa.f + (unsigned long long)F_LEN * cap0, m * 8, cudaMemcpyDeviceToDevice,
+                                    ctx->stream);
+                if (e == cudaSuccess)
+                    e = cudaMemcpyAsync((unsigned char*)d_stage + m * 8, gen->soa.u + (unsigned long long)U_ENDFACE * cap0,
+                                        m * 4, cudaMemcpyDeviceToDevice, ctx->stream);
+                cudaEventRecord(ev_ready, ctx->stream);
+                cudaStreamWaitEvent(ctx->stream_out, ev_ready, 0);
+                if (e == cudaSuccess)
+                    e = cudaMemcpyAsync(ctx->h_wb + lo * 12, d_stage, m * 12, cudaMemcpyDeviceToHost, ctx->stream_out);
+                cudaEventRecord(ctx->st_out_done[k], ctx->stream_out);
+                ctx->st_out_busy[k] = true;
+                PendingWb w;
+                w.lo = lo;
+                w.m = m;
+                if (e == cudaSuccess) e = cudaEventCreateWithFlags(&w.ev, cudaEventDisableTiming);
+                if (e == cudaSuccess) {
+                    cudaEventRecord(w.ev, ctx->stream_out);
+                    pending.push_back(w);
+                } else {
+                    rc = fail(ctx, RPX_ERR_CUDA, "generation 0 write-back: %s", cudaGetErrorString(e));
+                }
+                continue;
+            }
             launch_soa_to_aos(ctx, gen, d_stage, poff);
             cudaEventRecord(ev_ready, ctx->stream);
             cudaStreamWaitEvent(ctx->stream_out, ev_ready, 0);
@@ -1140,6 +1215,10 @@ extern "C" int rpx_trace_streamed(rpx_ctx* ctx, const void* rays_aos, uint64_t n
     cudaStreamSynchronize(ctx->stream_out);
     cudaStreamSynchronize(ctx->stream_in);
     cudaStreamSynchronize(ctx->stream);
+    if (inplace0) {
+        drain_writebacks(true);
+        for (; pending_done < pending.size(); pending_done++) cudaEventDestroy(pending[pending_done].ev);  // after an error
+    }
     for (int k = 0; k < 4; k++) ctx->st_out_busy[k] = false;  // everything drained above
     for (int k = 0; k < 2; k++) {
         cudaEventDestroy(ev_in[k]);
