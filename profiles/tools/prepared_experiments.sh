@@ -6,6 +6,7 @@
 #   3. read gpurun_out/prepared.log
 #
 # build: librpx_lean.so = -DRPX_LEAN_STAGE=1 -DRPX_MIN_BLOCKS=5 (lean child staging, 5 CTAs / SM)
+#        librpx_mo.so   = -DRPX_MESH_ORDERED=1 (near-child-first BVH walk for triangle meshes)
 # run:   (a) parity + golden suites under the lean library, (b) A/B of the two libraries on config2 /
 #        prisms / Michelson gausslets, (c) the prepared GPU tests (in-place generation 0 of
 #        rpx_trace_streamed), (d) the e2e arm with and without --e2e-inplace.
@@ -16,6 +17,8 @@ case "${1:-}" in
 build)
     make -C $CSRC -j"$(nproc)" OBJDIR=obj_lean LIB=librpx_lean.so RPX_EXTRA="-DRPX_LEAN_STAGE=1 -DRPX_MIN_BLOCKS=5" \
         2>&1 | grep -iE "error|warning" ; ls -la $CSRC/librpx_lean.so
+    make -C $CSRC -j"$(nproc)" OBJDIR=obj_mo LIB=librpx_mo.so RPX_EXTRA="-DRPX_MESH_ORDERED=1" \
+        2>&1 | grep -iE "error|warning" ; ls -la $CSRC/librpx_mo.so
     ;;
 run)
     mkdir -p gpurun_out
@@ -26,6 +29,10 @@ run)
         echo "== (b) A/B default vs lean"
         bash profiles/tools/ab1.sh "librpx.so librpx_lean.so librpx.so librpx_lean.so" "config2"
         bash profiles/tools/ab1.sh "librpx.so librpx_lean.so" "config4_prisms config5"
+        echo "== (b2) ordered mesh walk: parity of the mesh cases, then A/B on the 71k-facet scene"
+        RPX_LIB=$PWD/$CSRC/librpx_mo.so timeout 200 python -m pytest tests/test_parity_gpu.py tests/test_golden.py \
+            -m gpu -x -q -k "mesh" 2>&1 | tail -3
+        bash profiles/tools/ab1.sh "librpx.so librpx_mo.so" "mesh"
         echo "== (c) prepared GPU tests"
         timeout 200 python -m pytest tests -m gpu_prepared -x -q 2>&1 | tail -3
         echo "== (d) e2e, separate buffers vs in place"

@@ -1150,6 +1150,9 @@ static __device__ __noinline__ double distortion_intersect(const DevScene& S, co
 // (:310-343) on records that hold p1, v1, v2 and n = v1 x v2 ready-made.  Exactly equal alpha (a ray
 // through a shared edge): the lowest cell id wins, whatever the traversal order.
 // *piece = cell id of the hit (intersect_t.piece_idx), -1 on a miss.
+#ifndef RPX_MESH_ORDERED
+#define RPX_MESH_ORDERED 0
+#endif
 static __device__ __noinline__ double mesh_intersect(const DevScene& S, const rpx_face* f, vec3 p1, vec3 p2, int* piece) {
     const double* H = S.pool + f->aux_off;
     const double* tris = H + (long long)H[5];
@@ -1160,6 +1163,80 @@ static __device__ __noinline__ double mesh_intersect(const DevScene& S, const rp
     const double ix = 1.0 / d.x, iy = 1.0 / d.y, iz = 1.0 / d.z;  // +-inf for an axis-parallel segment
     double best = 1.0;
     long long best_id = -1;
+#if RPX_MESH_ORDERED
+    // Near child first (prepared for round 2, not yet run on a GPU; CPU emulation: 55 -> 34 box tests and
+    // 10.6 -> 5.6 triangle tests per ray through a closed 5120-facet ball, no change on an open surface):
+    // a node is tested when its parent is expanded, pushed with its entry parameter, and skipped on pop
+    // when the best alpha has moved in front of it meanwhile.
+    {
+        auto slab = [&](const double* nd, double* t0) -> bool {
+            const double ax = (nd[0] - p1.x) * ix, bx = (nd[3] - p1.x) * ix;
+            const double ay = (nd[1] - p1.y) * iy, by = (nd[4] - p1.y) * iy;
+            const double az = (nd[2] - p1.z) * iz, bz = (nd[5] - p1.z) * iz;
+            const double tmin = fmax(fmax(fmin(ax, bx), fmin(ay, by)), fmax(fmin(az, bz), 0.0));
+            const double tmax = fmin(fmin(fmax(ax, bx), fmax(ay, by)), fmin(fmax(az, bz), best));
+            *t0 = tmin;
+            return tmin <= tmax;
+        };
+        int sid[64];
+        double st0[64];
+        int sp = 0;
+        double t0;
+        if (slab(nodes, &t0)) {
+            sid[0] = 0;
+            st0[0] = t0;
+            sp = 1;
+        }
+        while (sp > 0) {
+            --sp;
+            if (st0[sp] > best) continue;
+            const double* nd = nodes + 8 * (long long)sid[sp];
+            const double a = nd[6], b = nd[7];
+            if (a >= 0.0) {
+                double tl, tr;
+                const bool hl = slab(nodes + 8 * (long long)a, &tl), hr = slab(nodes + 8 * (long long)b, &tr);
+                if (sp > 61) continue;  // cannot happen below 2^60 triangles; never overrun the stack
+                if (hl && hr) {
+                    const bool left_first = tl <= tr;
+                    sid[sp] = left_first ? (int)b : (int)a;
+                    st0[sp++] = left_first ? tr : tl;
+                    sid[sp] = left_first ? (int)a : (int)b;
+                    st0[sp++] = left_first ? tl : tr;
+                } else if (hl) {
+                    sid[sp] = (int)a;
+                    st0[sp++] = tl;
+                } else if (hr) {
+                    sid[sp] = (int)b;
+                    st0[sp++] = tr;
+                }
+                continue;
+            }
+            const double* t = tris + 16 * (long long)(-a - 1.0);
+            const int count = (int)b;
+            for (int c = 0; c < count; c++, t += 16) {
+                const vec3 tp = v3(t[0], t[1], t[2]), v1 = v3(t[3], t[4], t[5]), v2 = v3(t[6], t[7], t[8]);
+                const vec3 n = v3(t[9], t[10], t[11]);
+                const double det = -dot(d, n);
+                if (det == 0.0) continue;
+                const double invdet = 1.0 / det;
+                const vec3 a0 = p1 - tp;
+                const vec3 da0 = cross(a0, d);
+                const double u = dot(v2, da0) * invdet;
+                const double v = -dot(v1, da0) * invdet;
+                const double alpha = dot(a0, n) * invdet;
+                if ((u + v > 1.0) | (u < 0) | (v < 0) | (alpha < 0)) continue;
+                const long long id = (long long)t[12];
+                if (alpha >= tol && (alpha < best || (alpha == best && id < best_id))) {
+                    best = alpha;
+                    best_id = id;
+                }
+            }
+        }
+        *piece = (int)best_id;
+        if (best_id < 0) best = -1.0;
+        return best * dmag;
+    }
+#endif
     int stack[64];
     int sp = 0;
     stack[sp++] = 0;
