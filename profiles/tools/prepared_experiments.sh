@@ -7,6 +7,7 @@
 #
 # build: librpx_lean.so = -DRPX_LEAN_STAGE=1 -DRPX_MIN_BLOCKS=5 (lean child staging, 5 CTAs / SM)
 #        librpx_mo.so   = -DRPX_MESH_ORDERED=1 (near-child-first BVH walk for triangle meshes)
+#        librpx_t64.so  = -DRPX_TILE=64 -DRPX_MIN_BLOCKS=8 (64-ray tiles, 8 CTAs / SM)
 # run:   (a) parity + golden suites under the lean library, (b) A/B of the two libraries on config2 /
 #        prisms / Michelson gausslets, (c) the prepared GPU tests (in-place generation 0 of
 #        rpx_trace_streamed), (d) the e2e arm with and without --e2e-inplace.
@@ -17,6 +18,8 @@ case "${1:-}" in
 build)
     make -C $CSRC -j"$(nproc)" OBJDIR=obj_lean LIB=librpx_lean.so RPX_EXTRA="-DRPX_LEAN_STAGE=1 -DRPX_MIN_BLOCKS=5" \
         2>&1 | grep -iE "error|warning" ; ls -la $CSRC/librpx_lean.so
+    make -C $CSRC -j"$(nproc)" OBJDIR=obj_t64 LIB=librpx_t64.so RPX_EXTRA="-DRPX_TILE=64 -DRPX_MIN_BLOCKS=8" \
+        2>&1 | grep -iE "error|warning" ; ls -la $CSRC/librpx_t64.so
     make -C $CSRC -j"$(nproc)" OBJDIR=obj_mo LIB=librpx_mo.so RPX_EXTRA="-DRPX_MESH_ORDERED=1" \
         2>&1 | grep -iE "error|warning" ; ls -la $CSRC/librpx_mo.so
     ;;
@@ -27,8 +30,11 @@ run)
         RPX_LIB=$PWD/$CSRC/librpx_lean.so timeout 200 python -m pytest tests/test_parity_gpu.py tests/test_golden.py \
             tests/test_properties_gpu.py -m gpu -x -q 2>&1 | tail -3
         echo "== (b) A/B default vs lean"
-        bash profiles/tools/ab1.sh "librpx.so librpx_lean.so librpx.so librpx_lean.so" "config2"
-        bash profiles/tools/ab1.sh "librpx.so librpx_lean.so" "config4_prisms config5"
+        bash profiles/tools/ab1.sh "librpx.so librpx_lean.so librpx_t64.so librpx.so librpx_lean.so librpx_t64.so" "config2"
+        bash profiles/tools/ab1.sh "librpx.so librpx_lean.so librpx_t64.so" "config4_prisms config5"
+        echo "== (a2) parity under the 64-ray-tile library"
+        RPX_LIB=$PWD/$CSRC/librpx_t64.so timeout 200 python -m pytest tests/test_parity_gpu.py tests/test_golden.py \
+            -m gpu -x -q 2>&1 | tail -3
         echo "== (b2) ordered mesh walk: parity of the mesh cases, then A/B on the 71k-facet scene"
         RPX_LIB=$PWD/$CSRC/librpx_mo.so timeout 200 python -m pytest tests/test_parity_gpu.py tests/test_golden.py \
             -m gpu -x -q -k "mesh" 2>&1 | tail -3

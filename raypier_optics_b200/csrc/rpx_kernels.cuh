@@ -33,7 +33,12 @@ struct Soa {
     unsigned long long n, cap;
 };
 
+// Rays per tile = threads per CTA.  128 is what ships; -DRPX_TILE=64 -DRPX_MIN_BLOCKS=8 (same warps per SM,
+// half the barrier domain, twice the look-backs -- cheap since the grouped look-back) is prepared for
+// the next round and has not run on a GPU.  The lean staging map is a byte: RPX_TILE <= 256.
+#ifndef RPX_TILE
 #define RPX_TILE 128
+#endif
 #define RPX_WORDS_RAY 47        // 188 / 4
 #define RPX_WORDS_GAUSSLET 167  // 668 / 4
 
@@ -192,7 +197,7 @@ __device__ __forceinline__ void nearest_hit(
 // Simple face classes fit 80 registers (6 CTAs / SM: 0.047 -> 0.045 ms per 1e6 rays, prisms 0.084 -> 0.078);
 // the Newton / quadric code of the full class keeps 128.
 template <int FC, bool SS>
-__global__ void __launch_bounds__(RPX_TILE, FC == RPX_FC_SIMPLE ? 6 : 4)
+__global__ void __launch_bounds__(RPX_TILE, (FC == RPX_FC_SIMPLE ? 6 : 4) * 128 / RPX_TILE)
 k_intersect(DevScene S, Soa rays, double max_length, int only_face) {
     extern __shared__ __align__(16) unsigned char smem[];
     stage_scene<SS>(S, smem);
@@ -394,7 +399,7 @@ RPX_DEV unsigned long long tile_lookback_grouped(unsigned long long* state, unsi
 // captured from earlier collections.  The copy carries length = hit distance, end_face_idx =
 // the capture face's idx and the re-based wavelength index (:2004-2006, 2011-2014).
 template <bool GAUSS, int FC, bool SS>
-__global__ void __launch_bounds__(RPX_TILE, 4)
+__global__ void __launch_bounds__(RPX_TILE, 4 * 128 / RPX_TILE)
 k_capture(DevScene S, Soa in, Soa out, unsigned long long* tile_state, uint32_t* tile_counter,
           const unsigned long long* d_base, unsigned long long* d_next, uint32_t wl_offset, const uint32_t* wl_map,
           const uint32_t* face_ids) {
@@ -730,9 +735,9 @@ k_shade(DevScene S, Soa in, Soa out, double max_length, unsigned long long* tile
         const uint32_t nt = s_tile;
 #if RPX_BULK_PREFETCH
         // one bulk L2 prefetch per field row (1 KB of doubles / 512 B of u32), issued by 22 threads of
-        // warp 3 (the warp that does NOT run the look-back): 22 instructions per tile instead of ~90
-        if (nt < n_tiles_real && threadIdx.x >= 96 && threadIdx.x < 96 + 22) {
-            const uint32_t q = threadIdx.x - 96;
+        // the LAST warp (warp 0 runs the look-back): 22 instructions per tile instead of ~90
+        if (nt < n_tiles_real && threadIdx.x >= RPX_TILE - 32 && threadIdx.x < RPX_TILE - 32 + 22) {
+            const uint32_t q = threadIdx.x - (RPX_TILE - 32);
             const unsigned long long nb = (unsigned long long)nt * RPX_TILE;
             if (q < 18) {
                 const uint32_t fld = q < 6 ? q : q + 3;  // every double field but the parent normal
