@@ -3,8 +3,10 @@
  *
  * A scalar, single-threaded, plain-C99 restatement of the reference's
  * non-sequential trace (raypier/core: ctracer.pyx, cfaces.pyx, cmaterials.pyx,
- * cshapes.pyx, cdistortions.pyx, cimplicit_surfs.pyx) over the flattened scene
- * tables of include/rpx.h.  It exists so the CUDA path can be checked on the GPU
+ * cshapes.pyx, cdistortions.pyx, cimplicit_surfs.pyx, the OBBTreeFace of
+ * obbtree.pyx) and of the consumers next to it (capture planes, sequential mode,
+ * cfields.pyx + core/fields.py: the E-field summation with its gausslet and
+ * plain-ray front ends) over the flattened scene tables of include/rpx.h.  It exists so the CUDA path can be checked on the GPU
  * box, where /root/reference does not exist.
  *
  * Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline leg may load
