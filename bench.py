@@ -331,11 +331,6 @@ def run_ours(args):
         outs.append(pinned_out2[off:off + c])
         off += c
 
-    if args.e2e_inplace and not is_g:
-        # the reference's own calling convention: traced_rays[0] IS input_rays, mutated in place -- the
-        # library then returns only the 12-byte write-back of generation 0 (see rpx_trace_streamed)
-        outs[0] = pinned_in
-
     def step_e2e():
         gens, fc, _ = eng.trace_streamed(pinned_in, ml, rl, outs, chunk_rays=args.chunk_rays)
         counts = [len(g) for g in gens]
@@ -457,9 +452,7 @@ def run_ours(args):
                    "parallelism": "source rays sharded by rank, scene replicated"},
         "e2e": {"value": e2e_value, "unit": "ray-segments/s",
                 "h2d_bytes_per_step": int(rays.shape[0] * rec),
-                "d2h_bytes_per_step": int(d2h_records * rec - ((rec - 12) * rays.shape[0]
-                                                              if (args.e2e_inplace and not is_g) else 0)),
-                "inplace_generation0": bool(args.e2e_inplace and not is_g),
+                "d2h_bytes_per_step": int(d2h_records * rec),
                 "steps": e2e_steps, "api": "Engine.trace_streamed (rpx_trace_streamed), chunk %d rays" % args.chunk_rays,
                 "one_shot_value_this_rank": e2e_oneshot},
         "gpu_launches": int(launches_all),
@@ -600,9 +593,6 @@ def main():
     ap.add_argument("--workload", default="config2", choices=sorted(WORKLOADS))
     ap.add_argument("--rays", type=int, default=0, help="source rays per GPU (default: the config's)")
     ap.add_argument("--e2e-steps", type=int, default=5)
-    ap.add_argument("--e2e-inplace", action="store_true",
-                    help="e2e arm traces in place (out[0] is the source array): generation 0 comes back as a "
-                         "12-byte write-back.  Prepared in round 1, not yet measured on a GPU; default off")
     ap.add_argument("--chunk-rays", type=int, default=131072, help="source rays per chunk of the streamed e2e call")
     ap.add_argument("--ref-rays-per-core", type=int, default=200000)
     ap.add_argument("--no-cpu-baseline", action="store_true")

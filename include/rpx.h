@@ -393,10 +393,8 @@ void* rpx_stream(rpx_ctx* ctx);
  * len(traced_rays[g]); *n_gens = len(traced_rays) (<= max_gens, else RPX_ERR_INVALID; a too small
  * buffer gives RPX_ERR_NOMEM); face_counts[n_traced_faces] = Face.count; *device_ms = summed
  * device time of the generation loops.  (core/tracer.py:9-47 + the sharding of SURVEY 8e.)
- * In-place tracing: out_gens[0] == rays_aos (plain rays) is the reference's own convention --
- * traced_rays[0] IS input_rays, with `length` and `end_face_idx` written back (ctracer.pyx:2086-2087,
- * 1900-1903).  Only those 12 bytes per ray then cross PCIe for generation 0; the calling thread
- * scatters them into the caller's records while later chunks are in flight.                      */
+ * In-place tracing: out_gens[0] == rays_aos is allowed -- the reference's own convention, traced_rays[0]
+ * IS input_rays with `length` and `end_face_idx` written back (ctracer.pyx:2086-2087, 1900-1903).        */
 int rpx_trace_streamed(rpx_ctx* ctx, const void* rays_aos, uint64_t n, int is_gausslet, double max_length,
                        int recursion_limit, uint64_t chunk_rays, void* const* out_gens,
                        const uint64_t* out_capacity, int max_gens, uint64_t* out_counts, int* n_gens,

@@ -133,6 +133,43 @@ def trace_rays(scene, input_rays, recursion_limit=100, max_length=100.0):
     return traced, counts[:scene.c_scene.n_traced_faces]
 
 
+def trace_rays_blocks(scene, input_rays, recursion_limit=100, max_length=100.0, block=65536, workers=None):
+    """The same trace as ``trace_rays`` for BASELINE-size sources: the source is cut into
+    contiguous blocks that are traced independently on ``workers`` host threads (the C oracle
+    releases the GIL and keeps no shared state).  Yields ``(lo, hi, generations, face_counts)``
+    per block as blocks complete, in no particular order; a ray never interacts with another
+    ray and children are appended in parent order (ctracer.pyx:2084-2117), so generation g of
+    the whole trace is the blocks' generation g concatenated in source order with
+    ``parent_idx`` shifted by the generation g-1 rays of earlier blocks."""
+    import concurrent.futures as cf
+    import os
+    osc = scene if isinstance(scene, OracleScene) else OracleScene(scene)
+    sc = osc.scene
+    n = input_rays.shape[0]
+    bounds = [(lo, min(lo + block, n)) for lo in range(0, n, block)]
+    workers = workers or min(len(bounds), os.cpu_count() or 1) or 1
+
+    def one(b):
+        lo, hi = b
+        gens, fc = trace_rays(sc, input_rays[lo:hi], recursion_limit, max_length)
+        return lo, hi, gens, fc
+
+    with cf.ThreadPoolExecutor(workers) as ex:
+        # keep at most 2 * workers blocks in flight so that the finished ones do not pile up
+        pending, it = set(), iter(bounds)
+        for b in it:
+            pending.add(ex.submit(one, b))
+            if len(pending) >= 2 * workers:
+                break
+        while pending:
+            done, pending = cf.wait(pending, return_when=cf.FIRST_COMPLETED)
+            for f in done:
+                yield f.result()
+                nxt = next(it, None)
+                if nxt is not None:
+                    pending.add(ex.submit(one, nxt))
+
+
 def trace_ray_sequence(scene, input_rays, face_seq, recursion_limit=100, max_length=100.0):
     """raypier.core.tracer.trace_ray_sequence (core/tracer.py:50-99) on numpy arrays;
     ``face_seq`` holds the global face index of every step."""

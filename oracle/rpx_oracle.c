@@ -525,8 +525,9 @@ static int bz_pnt_in_hull(flat2 p, flat2 A, flat2 B, flat2 C, flat2 D) { /* cfac
 /* ---- triangle meshes: OBBTree / OBBTreeFace, raypier/core/obbtree.pyx -------------------------
  * intersect_t.piece_idx (ctracer.pxd:77-80) travels from Face.intersect_c to compute_normal_c in the
  * reference; every other face class ignores it.  This scalar restatement keeps it in two statics:
- * s_piece = piece of the last face_intersect call, s_hit_piece = piece of the accepted hit.     */
-static int s_piece = 0, s_hit_piece = 0;
+ * s_piece = piece of the last face_intersect call, s_hit_piece = piece of the accepted hit.
+ * Thread-local: the full-size parity tests run independent shards of one trace on several host threads. */
+static __thread int s_piece = 0, s_hit_piece = 0;
 
 /* Mesh block in the pool (scene.py::_mesh_block): header of 8 doubles, then the raw points / cells
  * (what the reference object holds) and, for the CUDA path only, BVH-ordered triangle records and

@@ -38,34 +38,52 @@ def _prepare_faces(input_rays, face_lists, max_length):
     return wavelengths, face_lists, all_faces
 
 
+def _assign_in_place(input_rays, arr, ref_array):
+    """Overwrite the records of ``input_rays`` with ``arr`` WITHOUT replacing the object: the
+    reference mutates its parent collection in place (``length`` / ``end_face_idx`` write-back,
+    ctracer.pyx:2086-2087, 1900-1903; gausslets also the six parabasal lengths, :2371) and callers
+    rely on ``traced_rays[0] is input_rays`` (SURVEY 8b).  Host mirrors re-point their array;
+    genuine ``raypier.core`` collections own malloc'd memory with no bulk setter, so their records
+    are replaced through the collection's own C-speed list API."""
+    if hasattr(input_rays, "_assign_array"):
+        input_rays._assign_array(arr)
+        return
+    cls = type(input_rays)
+    fresh = cls.from_array(ref_array(arr))
+    input_rays.clear_ray_list()
+    if hasattr(input_rays, "extend"):          # GaussletCollection.extend: one memcpy (ctracer.pyx:1294-1302)
+        input_rays.extend(fresh)
+    else:                                      # RayCollection: Cython loops over Ray objects (:1030-1046, 743-753)
+        input_rays.add_ray_list(fresh.get_ray_list())
+
+
 def _wrap_generations(input_rays, arrays, wavelengths):
     """Return the reference's container classes around the device results.
     ``traced_rays[0] is input_rays`` (mutated in place), each later generation's
     ``.parent`` is the previous one."""
     cls = type(input_rays)
-    dtype = getattr(cls, "_dtype", None)
+    native = getattr(cls, "_dtype", None) is not None  # this package's host mirrors
+
+    def ref_array(arr):
+        if native:
+            return arr
+        # genuine reference collection: from_array checks the identity of its own dtype object
+        mod = __import__(cls.__module__, fromlist=["ray_dtype"])
+        ref_dtype = mod.gausslet_dtype if arr.dtype == A.gausslet_dtype else mod.ray_dtype
+        a = np.empty(arr.shape[0], dtype=ref_dtype)
+        a.view(np.uint8)[:] = arr.view(np.uint8)
+        return a
+
     out = []
     prev = None
     for g, arr in enumerate(arrays):
-        if g == 0 and hasattr(input_rays, "_assign_array"):
-            input_rays._assign_array(arr)
+        if g == 0:
+            _assign_in_place(input_rays, arr, ref_array)
             rc = input_rays
         else:
-            if dtype is None:  # genuine reference collection: from_array checks its own dtype object
-                mod = __import__(cls.__module__, fromlist=["ray_dtype"])
-                ref_dtype = mod.gausslet_dtype if arr.dtype == A.gausslet_dtype else mod.ray_dtype
-                a = np.empty(arr.shape[0], dtype=ref_dtype)
-                a.view(np.uint8)[:] = arr.view(np.uint8)
-                rc = cls.from_array(a)
-            else:
-                rc = cls.from_array(arr)
-            if g == 0:
-                # a reference collection cannot be re-pointed at new memory: copy the write-back
-                # fields the reference mutates (length, end_face_idx) through its public API
-                rc.wavelengths = wavelengths
-            else:
-                rc.wavelengths = wavelengths
-                rc.parent = prev
+            rc = cls.from_array(ref_array(arr))
+            rc.wavelengths = wavelengths
+            rc.parent = prev
         out.append(rc)
         prev = rc
     return out
@@ -135,4 +153,6 @@ def trace_ray_sequence(input_rays, face_sequence, recursion_limit=100, max_lengt
             f.count = int(c)
     finally:
         res.free()
+    if not arrays:  # empty input: the reference still returns [input_rays] (core/tracer.py:66)
+        return [input_rays], all_faces
     return _wrap_generations(input_rays, arrays, wavelengths), all_faces

@@ -73,8 +73,6 @@ extern "C" int rpx_init(int device, rpx_ctx** out_ctx) {
     ctx->have_copy_streams = false;
     for (int k = 0; k < 2; k++) { ctx->st_in[k] = nullptr; ctx->st_in_bytes[k] = 0; }
     for (int k = 0; k < 4; k++) { ctx->st_out[k] = nullptr; ctx->st_out_bytes[k] = 0; ctx->st_out_busy[k] = false; }
-    ctx->h_wb = nullptr;
-    ctx->h_wb_bytes = 0;
     ctx->have_capture = false;
     ctx->cap_block = nullptr;
     ctx->cap_face_ids = nullptr;
@@ -130,7 +128,6 @@ extern "C" void rpx_shutdown(rpx_ctx* ctx) {
     cudaFree(ctx->pipe_counters);
     cudaFree(ctx->pipe_state);
     cudaFreeHost(ctx->h_counts);
-    if (ctx->h_wb) cudaFreeHost(ctx->h_wb);
     cudaFree(ctx->d_count);
     cudaFreeHost(ctx->h_count);
     if (ctx->have_copy_streams) {
@@ -210,6 +207,17 @@ static int validate_scene(rpx_ctx* ctx, const rpx_scene* s) {
                 const bool ok = a >= 0 ? (a > (double)k && a < (double)n_nodes && b > (double)k && b < (double)n_nodes)
                                        : (-a - 1 >= 0 && b >= 1 && (-a - 1) + b <= (double)n_cells);
                 if (!ok) return fail(ctx, RPX_ERR_INVALID, "face %d: bad BVH node %lld", i, k);
+            }
+            // the device walk keeps an explicit stack of 64 entries (one per level + 1): children have
+            // larger ids than their parent (checked above), so one backward pass gives every subtree height
+            {
+                std::vector<int> height((size_t)n_nodes, 1);
+                for (long long k = n_nodes - 1; k >= 0; k--) {
+                    const double a = nodes[8 * k + 6], b = nodes[8 * k + 7];
+                    if (a >= 0) height[(size_t)k] = 1 + (height[(size_t)a] > height[(size_t)b] ? height[(size_t)a] : height[(size_t)b]);
+                }
+                if (height[0] > 60)
+                    return fail(ctx, RPX_ERR_UNSUPPORTED, "face %d: BVH depth %d exceeds the device traversal stack (60)", i, height[0]);
             }
         }
         if (f.type == RPX_FACE_EXTRUDED_BEZIER && (f.aux_off < 0 || f.aux_n < 1 || f.aux_off + 8 * f.aux_n > s->n_pool))
@@ -1034,48 +1042,11 @@ extern "C" int rpx_trace_streamed(rpx_ctx* ctx, const void* rays_aos, uint64_t n
         cudaEventCreateWithFlags(&ev_used[k], cudaEventDisableTiming);
     }
     cudaEventCreateWithFlags(&ev_ready, cudaEventDisableTiming);
-    // In-place tracing (out_gens[0] IS the source array, the reference's own semantics: traced_rays[0] is
-    // input_rays, mutated in place, ctracer.pyx:2086-2087 / 1900-1903): generation 0 then differs from
-    // what the caller already holds only in `length` and `end_face_idx`, so only those 12 of the 188
-    // bytes per ray come back over PCIe; they land in a pinned scratch area and are scattered into the
-    // caller's records by this thread while later chunks are in flight.  (Plain rays only: a gausslet
-    // also gets its six parabasal lengths back and generation 0 is 5 % of its download anyway.)
-    const bool inplace0 = n_chunks && !is_gausslet && out_gens[0] == rays_aos;
-    struct PendingWb {
-        cudaEvent_t ev;
-        uint64_t lo, m;
-    };
-    std::vector<PendingWb> pending;
-    size_t pending_done = 0;
-    auto drain_writebacks = [&](bool wait) {
-        unsigned char* dst = (unsigned char*)out_gens[0];
-        while (pending_done < pending.size()) {
-            PendingWb& w = pending[pending_done];
-            if (wait) {
-                if (cudaEventSynchronize(w.ev) != cudaSuccess) break;
-            } else if (cudaEventQuery(w.ev) != cudaSuccess) {
-                break;
-            }
-            const unsigned char* len = ctx->h_wb + w.lo * 12;
-            const unsigned char* face = len + w.m * 8;
-            for (uint64_t i = 0; i < w.m; i++) {
-                unsigned char* recp = dst + (w.lo + i) * RPX_RAY_BYTES;
-                memcpy(recp + offsetof(rpx_ray, length), len + i * 8, 8);
-                memcpy(recp + offsetof(rpx_ray, end_face_idx), face + i * 4, 4);
-            }
-            cudaEventDestroy(w.ev);
-            pending_done++;
-        }
-    };
-    if (inplace0 && ctx->h_wb_bytes < n * 12) {
-        if (ctx->h_wb) cudaFreeHost(ctx->h_wb);
-        ctx->h_wb = nullptr;
-        ctx->h_wb_bytes = 0;
-        if ((e = cudaHostAlloc((void**)&ctx->h_wb, n * 12, cudaHostAllocDefault)) != cudaSuccess)
-            rc = fail(ctx, RPX_ERR_NOMEM, "write-back scratch (%llu bytes): %s", (unsigned long long)(n * 12), cudaGetErrorString(e));
-        else
-            ctx->h_wb_bytes = n * 12;
-    }
+    // out_gens[0] may alias rays_aos (the reference's convention: traced_rays[0] IS input_rays, mutated in
+    // place, ctracer.pyx:2086-2087 / 1900-1903): chunk c's generation 0 lands on the records chunk c was
+    // uploaded from, after that upload has completed.  (A 12-byte write-back + host-side scatter instead of
+    // the 188-byte record was measured SLOWER on B200: 1.69e8 vs 2.51e8 seg/s end to end, the scatter loop
+    // on the calling thread being the bottleneck -- profiles/r02_notes.md; removed.)
     const uint64_t in_bytes = (n < chunk_rays ? n : chunk_rays) * rec;
     if (n_chunks && rc == RPX_OK) {
         for (int k = 0; k < (n_chunks > 1 ? 2 : 1) && e == cudaSuccess; k++) {
@@ -1105,7 +1076,6 @@ extern "C" int rpx_trace_streamed(rpx_ctx* ctx, const void* rays_aos, uint64_t n
     for (uint64_t c = 0; c < n_chunks && rc == RPX_OK; c++) {
         const int b = (int)(c & 1);
         const uint64_t lo = c * chunk_rays, cnt = (n - lo < chunk_rays) ? n - lo : chunk_rays;
-        if (inplace0) drain_writebacks(false);
         if (c + 1 < n_chunks && (e = issue_upload(c + 1)) != cudaSuccess) {
             rc = fail(ctx, RPX_ERR_CUDA, "chunk upload: %s", cudaGetErrorString(e));
             break;
@@ -1146,7 +1116,13 @@ extern "C" int rpx_trace_streamed(rpx_ctx* ctx, const void* rays_aos, uint64_t n
                           (unsigned long long)out_capacity[g], (unsigned long long)(totals[(size_t)g] + m));
                 break;
             }
-            // global parent index = local + rays of generation g-1 in earlier chunks (generation 0 keeps its own)
+            // global parent index = local + rays of generation g-1 in earlier chunks (generation 0 keeps its own);
+            // ray_t.parent_idx is 32 bits wide: a generation beyond that cannot be numbered
+            if (totals[(size_t)g] + m >= 0xFFFFFFFFull) {
+                rc = fail(ctx, RPX_ERR_INVALID, "generation %d would exceed the 32-bit parent_idx of ray_t (%llu rays)", g,
+                          (unsigned long long)(totals[(size_t)g] + m));
+                break;
+            }
             const uint32_t poff = g > 0 ? (uint32_t)(totals[(size_t)g - 1]) : 0u;
             // next buffer of the download ring: wait (on the compute stream) until its previous
             // D2H has left it, grow it if this generation is larger than anything seen so far
@@ -1166,33 +1142,6 @@ extern "C" int rpx_trace_streamed(rpx_ctx* ctx, const void* rays_aos, uint64_t n
                 ctx->st_out_bytes[k] = want;
             }
             void* d_stage = ctx->st_out[k];
-            if (g == 0 && inplace0) {
-                // the two write-back rows of the SoA generation, packed [m doubles][m words], through the
-                // same staging ring (the generation buffer itself goes back to the pool right after)
-                const unsigned long long cap0 = gen->soa.cap;
-                e = cudaMemcpyAsync(d_stage, gen->soa.f + (unsigned long long)F_LEN * cap0, m * 8, cudaMemcpyDeviceToDevice,
-                                    ctx->stream);
-                if (e == cudaSuccess)
-                    e = cudaMemcpyAsync((unsigned char*)d_stage + m * 8, gen->soa.u + (unsigned long long)U_ENDFACE * cap0,
-                                        m * 4, cudaMemcpyDeviceToDevice, ctx->stream);
-                cudaEventRecord(ev_ready, ctx->stream);
-                cudaStreamWaitEvent(ctx->stream_out, ev_ready, 0);
-                if (e == cudaSuccess)
-                    e = cudaMemcpyAsync(ctx->h_wb + lo * 12, d_stage, m * 12, cudaMemcpyDeviceToHost, ctx->stream_out);
-                cudaEventRecord(ctx->st_out_done[k], ctx->stream_out);
-                ctx->st_out_busy[k] = true;
-                PendingWb w;
-                w.lo = lo;
-                w.m = m;
-                if (e == cudaSuccess) e = cudaEventCreateWithFlags(&w.ev, cudaEventDisableTiming);
-                if (e == cudaSuccess) {
-                    cudaEventRecord(w.ev, ctx->stream_out);
-                    pending.push_back(w);
-                } else {
-                    rc = fail(ctx, RPX_ERR_CUDA, "generation 0 write-back: %s", cudaGetErrorString(e));
-                }
-                continue;
-            }
             launch_soa_to_aos(ctx, gen, d_stage, poff);
             cudaEventRecord(ev_ready, ctx->stream);
             cudaStreamWaitEvent(ctx->stream_out, ev_ready, 0);
@@ -1215,10 +1164,6 @@ extern "C" int rpx_trace_streamed(rpx_ctx* ctx, const void* rays_aos, uint64_t n
     cudaStreamSynchronize(ctx->stream_out);
     cudaStreamSynchronize(ctx->stream_in);
     cudaStreamSynchronize(ctx->stream);
-    if (inplace0) {
-        drain_writebacks(true);
-        for (; pending_done < pending.size(); pending_done++) cudaEventDestroy(pending[pending_done].ev);  // after an error
-    }
     for (int k = 0; k < 4; k++) ctx->st_out_busy[k] = false;  // everything drained above
     for (int k = 0; k < 2; k++) {
         cudaEventDestroy(ev_in[k]);

@@ -35,10 +35,6 @@ struct rpx_ctx {
     size_t st_out_bytes[4];
     cudaEvent_t st_out_done[4];  // D2H out of st_out[k] finished (recorded on stream_out)
     bool st_out_busy[4];
-    // in-place generation 0 of rpx_trace_streamed: pinned landing zone of the (length, end_face_idx)
-    // write-back, 12 bytes per source ray
-    unsigned char* h_wb;
-    size_t h_wb_bytes;
     std::string err;
     // scene
     bool have_scene;

@@ -586,8 +586,21 @@ RPX_DEV void stage_child(double* cs, uint32_t* cu, uint32_t slot, const Kids& k,
 #ifndef RPX_BULK_PREFETCH
 #define RPX_BULK_PREFETCH 1
 #endif
+// Gausslets: the origins and directions of the six parabasal rays of every hit parent (36 doubles per
+// ray, 36 KB per tile) are fetched with cp.async (LDGSTS, no register, no scoreboard) into a per-thread
+// column of shared memory while the base ray's orientation / material code runs; both parabasal loops
+// then read shared memory.  Without it the first loop is six dependent global round trips (the loads
+// of ray j+1 are guarded by the hit test of ray j) and the second loop re-reads everything through L2.
+#ifndef RPX_PARA_SMEM
+#define RPX_PARA_SMEM 0
+#endif
+#define RPX_PARA_ROWS 36
+#define RPX_PARA_SMEM_BYTES (RPX_PARA_SMEM ? RPX_PARA_ROWS * RPX_TILE * 8 : 0)
+#ifndef RPX_MIN_BLOCKS_G
+#define RPX_MIN_BLOCKS_G RPX_MIN_BLOCKS
+#endif
 template <bool GAUSS, int FC, uint32_t MM, bool SS>
-__global__ void __launch_bounds__(RPX_TILE, RPX_MIN_BLOCKS)
+__global__ void __launch_bounds__(RPX_TILE, GAUSS ? RPX_MIN_BLOCKS_G : RPX_MIN_BLOCKS)
 k_shade(DevScene S, Soa in, Soa out, double max_length, unsigned long long* tile_state,
         uint32_t* tile_counter, unsigned long long* d_count, uint32_t* face_counts, uint32_t n_tiles,
         int ahead_face, const unsigned long long* n_dev, unsigned long long* h_count) {
@@ -609,7 +622,11 @@ k_shade(DevScene S, Soa in, Soa out, double max_length, unsigned long long* tile
     double* cs = reinterpret_cast<double*>(smem);
     uint32_t* cu = reinterpret_cast<uint32_t*>(smem + RPX_SLOTS * NF * 8);
 #endif
-    stage_scene<SS>(S, smem + RPX_STAGE_BYTES);  // once per (persistent) CTA
+    // gausslets: [child staging][parabasal columns][scene copy]
+    constexpr bool kParaSmem = GAUSS && RPX_PARA_SMEM;
+    double* ps = reinterpret_cast<double*>(smem + RPX_STAGE_BYTES) + threadIdx.x;  // ps[row * RPX_TILE]
+    (void)ps;
+    stage_scene<SS>(S, smem + RPX_STAGE_BYTES + (GAUSS ? RPX_PARA_SMEM_BYTES : 0));  // once per (persistent) CTA
     const unsigned long long n_in = n_dev ? *n_dev : in.n;
     const uint32_t n_tiles_real = (uint32_t)((n_in + RPX_TILE - 1) / RPX_TILE);
     constexpr bool kGrouped = RPX_LOOKBACK_GROUPS && (!GAUSS || RPX_GROUPS_GAUSS);
@@ -652,6 +669,20 @@ k_shade(DevScene S, Soa in, Soa out, double max_length, unsigned long long* tile
         r.ident = ident = in.u[U_IDENT * cap + i];
         r.type = in.u[U_TYPE * cap + i];
         hit = (face_idx != RPX_NO_FACE);
+        if (kParaSmem && hit) {
+            // rows 0..35 = (origin xyz, direction xyz) of parabasal ray 0..5; own column only, so the
+            // only synchronisation is this thread's own wait_group below
+            const unsigned sbase = (unsigned)__cvta_generic_to_shared(ps);
+#pragma unroll
+            for (int j = 0; j < RPX_NPARA; j++) {
+#pragma unroll
+                for (int c = 0; c < 6; c++)
+                    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(sbase + (unsigned)((j * 6 + c) * RPX_TILE * 8)),
+                                 "l"(in.p + (unsigned long long)(j * NPF + c) * cap + i)
+                                 : "memory");
+            }
+            asm volatile("cp.async.commit_group;" ::: "memory");
+        }
     }
     if (hit) {
         const rpx_face* face = &S.faces[face_idx];
@@ -679,13 +710,17 @@ k_shade(DevScene S, Soa in, Soa out, double max_length, unsigned long long* tile
             // must hit the SAME face (is_base_ray = 0); any miss drops the children (Q16).
             const rpx_face_set* fs = &S.sets[face->face_set];
             bool ok = true;
+            if (kParaSmem) asm volatile("cp.async.wait_group 0;" ::: "memory");
 #pragma unroll
             for (int j = 0; j < RPX_NPARA; j++) {
                 plen[j] = max_length;
                 if (ok) {
                     const double* pp = in.p + (unsigned long long)(j * NPF) * cap + i;
-                    vec3 po = v3(pp[(P_OX + 0) * cap], pp[(P_OX + 1) * cap], pp[(P_OX + 2) * cap]);
-                    vec3 pd = v3(pp[(P_DX + 0) * cap], pp[(P_DX + 1) * cap], pp[(P_DX + 2) * cap]);
+                    const double* sp = ps + j * 6 * RPX_TILE;
+                    vec3 po = kParaSmem ? v3(sp[0], sp[RPX_TILE], sp[2 * RPX_TILE])
+                                        : v3(pp[(P_OX + 0) * cap], pp[(P_OX + 1) * cap], pp[(P_OX + 2) * cap]);
+                    vec3 pd = kParaSmem ? v3(sp[3 * RPX_TILE], sp[4 * RPX_TILE], sp[5 * RPX_TILE])
+                                        : v3(pp[(P_DX + 0) * cap], pp[(P_DX + 1) * cap], pp[(P_DX + 2) * cap]);
                     vec3 ray_end = po + pd * max_length;
                     vec3 p1 = transform_pt(fs->inv_trans.m, po);
                     vec3 p2 = transform_pt(fs->inv_trans.m, ray_end);
@@ -892,8 +927,11 @@ k_shade(DevScene S, Soa in, Soa out, double max_length, unsigned long long* tile
 #pragma unroll
         for (int j = 0; j < RPX_NPARA; j++) {
             const double* pp = in.p + (unsigned long long)(j * NPF) * cap + i;
-            vec3 po = v3(pp[(P_OX + 0) * cap], pp[(P_OX + 1) * cap], pp[(P_OX + 2) * cap]);
-            vec3 pd = v3(pp[(P_DX + 0) * cap], pp[(P_DX + 1) * cap], pp[(P_DX + 2) * cap]);
+            const double* sp = ps + j * 6 * RPX_TILE;
+            vec3 po = kParaSmem ? v3(sp[0], sp[RPX_TILE], sp[2 * RPX_TILE])
+                                : v3(pp[(P_OX + 0) * cap], pp[(P_OX + 1) * cap], pp[(P_OX + 2) * cap]);
+            vec3 pd = kParaSmem ? v3(sp[3 * RPX_TILE], sp[4 * RPX_TILE], sp[5 * RPX_TILE])
+                                : v3(pp[(P_DX + 0) * cap], pp[(P_DX + 1) * cap], pp[(P_DX + 2) * cap]);
             vec3 ppoint = po + pd * plen[j];
             vec3 pn, pt;
             compute_orientation<FC>(S, face, ppoint, &pn, &pt, FC == RPX_FC_FULL ? ppiece[j] : 0);

@@ -6,6 +6,8 @@
 
 #include "rpx_kernels.cuh"
 
+#define RPX_MAX_DEVICES 64
+
 namespace rpx {
 
 struct ShadeArgs {

@@ -10,9 +10,6 @@ if ROOT not in sys.path:
 
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
-    config.addinivalue_line("markers", "gpu_prepared: needs a CUDA device AND has never been run on one yet "
-                                       "(written after a round's GPU minutes ran out); run with -m gpu_prepared, "
-                                       "then move the test to the gpu marker")
 
 
 @pytest.fixture(scope="session")

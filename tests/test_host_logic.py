@@ -189,3 +189,46 @@ def test_face_sequence_inference_works_on_mirror_collections(core):
         view = traced[1].base_rays
         assert len(view) == len(traced[1]) and view.origin.shape == (len(view), 3)
         assert view.termination.shape == (len(view), 3)
+
+
+def test_blocked_oracle_equals_whole_oracle(core):
+    """The harness of tests/test_parity_fullsize_gpu.py (blocks of the source traced on host threads,
+    slices of the whole trace located through the parent chain) on the oracle itself."""
+    import numpy as np
+    from oracle import oracle as O
+    from raypier_optics_b200 import scene as SC
+    from util import build_case
+    from test_parity_fullsize_gpu import check_against_blocked_oracle
+    for name, kw, rl in (("config4_prisms", dict(n=6000), 12), ("config5", dict(n=1500, gausslets=True), None)):
+        cfg = build_case(core, name, kw, rl)
+        sc = SC.Scene(cfg['face_lists'], cfg['wavelengths'])
+        gens, fc = O.trace_rays(sc, np.ascontiguousarray(cfg['rays']), cfg['recursion_limit'], cfg['max_length'])
+        worst = check_against_blocked_oracle(None, cfg, name, block=701, got=(gens, fc))
+        assert worst == 0.0
+
+
+def test_wrap_generations_mutates_genuine_reference_collections_in_place(refcore):
+    """traced_rays[0] IS input_rays, with the write-back visible through it, also when the
+    caller hands in genuine raypier.core collections (which own malloc'd memory)."""
+    import numpy as np
+    from raypier_optics_b200 import _abi as A, configs
+    from raypier_optics_b200.core.tracer import _wrap_generations
+    ct = refcore.ctracer
+    for gauss in (False, True):
+        cfg = configs.build(refcore, "config5", n=257, gausslets=gauss)
+        rays = np.ascontiguousarray(cfg['rays'])
+        cls = ct.GaussletCollection if gauss else ct.RayCollection
+        rc = cls.from_array(rays.view(ct.gausslet_dtype if gauss else ct.ray_dtype).copy())
+        rc.wavelengths = np.asarray(cfg['wavelengths'])
+        g0 = rays.copy()
+        b = g0['base_ray'] if gauss else g0
+        b['length'] = np.linspace(1.0, 2.0, len(g0))
+        b['end_face_idx'] = np.arange(len(g0)) % 7
+        if gauss:
+            g0['para_rays']['length'][:] = 3.25
+        g1 = rays[:100].copy()
+        out = _wrap_generations(rc, [g0, g1], np.asarray(cfg['wavelengths']))
+        assert out[0] is rc and len(rc) == len(g0)
+        assert rc.copy_as_array().tobytes() == g0.tobytes()
+        assert type(out[1]) is cls and out[1].parent is rc and len(out[1]) == 100
+        assert np.array_equal(out[1].wavelengths, cfg['wavelengths'])

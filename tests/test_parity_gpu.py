@@ -70,3 +70,26 @@ def test_streamed_trace_is_identical_to_one_shot(core, engine, name, kw, rl, chu
     small = [engine.pinned_empty(8, rays.dtype) for _ in out]
     with pytest.raises(RpxError):
         engine.trace_streamed(rays, cfg['max_length'], cfg['recursion_limit'], small, chunk_rays=chunk)
+
+
+@pytest.mark.parametrize("name,kw,rl,chunk", [
+    ("config2", dict(n=20000, reflection_threshold=1e-3, transmission_threshold=1e-3), 6, 4096),
+    ("config4_prisms", dict(n=5000), 12, 777),
+])
+def test_streamed_trace_in_place_returns_the_same_generation_0(core, engine, name, kw, rl, chunk):
+    """rpx_trace_streamed with out[0] aliasing the source (the reference's in-place convention,
+    traced_rays[0] is input_rays): every generation byte-identical to the one-shot trace."""
+    cfg = build_case(core, name, kw, rl)
+    engine.set_scene(SC.Scene(cfg['face_lists'], cfg['wavelengths']))
+    rays = np.ascontiguousarray(cfg['rays'])
+    res = engine.trace(rays, cfg['max_length'], cfg['recursion_limit'])
+    want = res.generations()
+    res.free()
+    src = engine.pinned_empty(len(rays), rays.dtype)
+    src[:] = rays
+    out = [src] + [engine.pinned_empty(len(g) + 64, rays.dtype) for g in want[1:]] + [engine.pinned_empty(64, rays.dtype)]
+    gens, fc, ms = engine.trace_streamed(src, cfg['max_length'], cfg['recursion_limit'], out, chunk_rays=chunk)
+    assert [len(g) for g in gens] == [len(g) for g in want]
+    assert gens[0].ctypes.data == src.ctypes.data
+    for g, (a, b) in enumerate(zip(gens, want)):
+        assert a.tobytes() == b.tobytes(), "generation %d differs from the one-shot trace" % g

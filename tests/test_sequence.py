@@ -103,3 +103,49 @@ def test_drop_in_trace_functions(engine, core):
     traced2, faces2 = T.trace_ray_sequence(rc2, seq, recursion_limit=100, max_length=cfg2['max_length'])
     assert len(traced2) == 4 and len(faces2) == 9
     assert np.all(np.isinf(traced2[-1].length))            # the last generation is returned untraced
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name,kw", [("config2", dict(n=20000)), ("config5", dict(n=3000, gausslets=True)),
+                                     ("config4_prisms", dict(n=4000))])
+def test_drop_in_trace_rays_with_genuine_reference_objects(engine, name, kw):
+    """trace_rays fed with GENUINE raypier.core objects (RayCollection / GaussletCollection, FaceList,
+    faces and materials built from oracle/_ref, which travels to the GPU box): the scene is flattened
+    from the reference's own attributes, the result comes back in the reference's own container
+    classes, traced_rays[0] is input_rays (mutated in place) and every generation matches the
+    reference's own Cython trace of the same objects (core/tracer.py:9-47)."""
+    from oracle import oracle as O
+    refcore = O.import_reference("parity")
+    if refcore is None:
+        pytest.skip("oracle/_ref is not present on this machine")
+    ct = refcore.ctracer
+    gauss = bool(kw.get("gausslets"))
+    cls = ct.GaussletCollection if gauss else ct.RayCollection
+    rl = 12 if name == "config4_prisms" else None
+
+    def build():
+        cfg = configs.build(refcore, name, **kw)
+        if rl:
+            cfg['recursion_limit'] = rl
+        rc = O.reference_collection(refcore, cfg['rays'], cfg['wavelengths'])
+        assert type(rc) is cls
+        return cfg, rc
+
+    cfg, rc = build()
+    want, want_faces = O.reference_trace_rays(refcore, rc, cfg['face_lists'], cfg['recursion_limit'], cfg['max_length'])
+    want = [w.copy_as_array() for w in want]
+    want_counts = [f.count for f in want_faces]
+    cfg, rc = build()   # fresh objects: the reference trace mutated the first set
+    traced, all_faces = T.trace_rays(rc, cfg['face_lists'], recursion_limit=cfg['recursion_limit'],
+                                     max_length=cfg['max_length'])
+    assert traced[0] is rc
+    assert all(type(t) is cls for t in traced)
+    assert [len(t) for t in traced] == [len(w) for w in want]
+    assert all(traced[g].parent is traced[g - 1] for g in range(1, len(traced)))
+    assert [f.idx for f in all_faces] == list(range(len(all_faces)))
+    assert [f.count for f in all_faces] == want_counts
+    from raypier_optics_b200 import _abi as A
+    native = A.gausslet_dtype if gauss else A.ray_dtype
+    got = [np.ascontiguousarray(t.copy_as_array()).view(native) for t in traced]
+    worst = compare_traces(got, [np.ascontiguousarray(w).view(native) for w in want], name + " (genuine reference objects)")
+    print("%s with genuine raypier.core objects: %s, worst rel err %.2e" % (name, [len(t) for t in traced], worst))
