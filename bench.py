@@ -1,25 +1,35 @@
 #!/usr/bin/env python
 """bench.py -- ray-segments/s of the non-sequential trace (BASELINE.json's metric).
 
-A "step" is one complete trace (all generations) of one batch of synthetic source rays
-through one of the BASELINE configs.  Default workload: configs[1], the EdmundOptic45805
-achromatic doublet with AR coating, 1e6 polarised rays over 5 wavelengths with glass
-dispersion (188 MB of ray records per generation: larger than the 126 MB L2, so no L2
-flush is needed between steps).
+A "step" is one complete trace (all generations) of one batch of synthetic source rays through one of
+the BASELINE configs.  Default workload = the north-star run: configs[4], the Michelson
+interferometer with a Gaussian source of 1.25e8 gausslets PER GPU (1e9 over the 8 GPUs of a box), far
+too large to keep: the source is traced in chunks by `rpx_trace_consume` and every generation is
+consumed on the device and freed.  (The 83.5 GB source is 668 MB per generation-chunk row: every
+buffer is larger than the 126 MB L2, no flush needed.)
 
     python bench.py --gpus N --steps K --warmup W            # our CUDA path
     python bench.py --impl reference --steps K --warmup W    # the reference's CPU path
 
-  value     whole-job ray-segments/s, inputs resident in HBM, device-timed (CUDA events on
-            the engine's stream around every generation loop), max over ranks
-  e2e       same metric through the reference-facing call with HOST buffers: pinned H2D of
-            the source rays + trace + D2H of every generation (what trace_rays returns)
-  roofline  dominant kernel (k_shade) achieved algorithmic GB/s vs MEASURED_PEAKS.json
-  cpu_baseline  the reference's own Cython trace (oracle/_ref) on the box's host cores
+  value     whole-job ray-segments/s of the trace, source resident in HBM (packed ray_t / gausslet_t
+            records, as they arrive from the host), device-timed with CUDA events on the engine's stream
+            from the first to the last operation of the step (AoS->SoA transposition of every chunk
+            included), max over ranks
+  e2e       the same metric through the reference-facing call with the source in pinned HOST memory:
+            H2D of every chunk (overlapped with the tracing of the previous one) + trace + the
+            device-side consumers of the reference's own Michelson example (GaussletCapturePlane at the
+            output port -> EFieldPlane: capture filter + E-field summation on a detector grid) + D2H
+            of the field and the counts; wall clock, max over ranks
+  roofline  dominant kernel (k_shade) achieved algorithmic GB/s vs MEASURED_PEAKS.json (HBM-bound
+            workloads), or FP64 instruction rate vs the measured DFMA issue peak (config3)
+  cpu_baseline  the reference's own Cython trace (oracle/_ref) on the box's host cores, bounded sample
 
-Under torchrun every rank traces its own shard of the source (weak scaling: per-GPU work
-fixed); no collective inside the generation loop, one NCCL all-gather of the per-generation
-counts + all-reduce of Face.count at the end of each step (raypier_optics_b200.distributed).
+Smaller workloads (`--workload config2` ...) keep every generation on the device (`rpx_trace_device`)
+and ship all of them back in the e2e arm (`rpx_trace_streamed`), as in round 1.
+
+Under torchrun every rank traces its own shard of the source (weak scaling: per-GPU work fixed); no
+collective inside the generation loop; per step one NCCL all-gather of the per-generation counts, an
+all-reduce of Face.count and (consume mode) an all-reduce of the detector field.
 """
 import argparse
 import json
@@ -38,16 +48,23 @@ import numpy as np
 
 METRIC = "ray-segments/sec"
 WORKLOADS = {
+    # the north-star run (BASELINE configs[4]): 1.25e8 gausslets per GPU = 1e9 over 8 GPUs, streamed
+    "config5": dict(n=125000000, kw=dict(gausslets=True), mode="consume", block=1 << 21,
+                    capture=dict(centre=(0.0, -12.0, 0.0), direction=(0.0, 1.0, 0.0), size=(12.0, 12.0)),
+                    detector=dict(y=-14.0, half_width=4.0)),
+    # BASELINE configs[3] at its quoted size on one GPU (TIR prism chain, plain rays), streamed
+    "config4": dict(n=100000000, kw={}, mode="consume", block=1 << 22, recursion_limit=12, builder="config4_prisms",
+                    capture=dict(centre=(0.0, 0.0, 0.0), direction=(1.0, 0.3, 0.0), size=(400.0, 400.0))),
     "config1": dict(n=10000, kw={}),
     "config2": dict(n=1000000, kw={}, capture=dict(centre=(-4.86, -31.3, 0.07), direction=(0.2, 1.0, 0.1), size=(30.0, 30.0))),
     "config3": dict(n=10000000, kw={}),
     "config4_prisms": dict(n=1000000, kw={}, recursion_limit=12),
     "config4_grating": dict(n=1000000, kw={}),
-    "config5": dict(n=1000000, kw=dict(gausslets=True),
-                    capture=dict(centre=(0.0, -12.0, 0.0), direction=(0.0, 1.0, 0.0), size=(12.0, 12.0))),
+    "config5_1e6": dict(n=1000000, kw=dict(gausslets=True), builder="config5",
+                        capture=dict(centre=(0.0, -12.0, 0.0), direction=(0.0, 1.0, 0.0), size=(12.0, 12.0))),
     # triangle-mesh optics: 20480-facet ball lens + 50562-facet mirror, BVH traversal
     "mesh": dict(n=1000000, kw=dict(gausslets=False, ball_subdiv=5, mesh_n=160)),
-    "config5_rays": dict(n=1000000, kw=dict(gausslets=False),
+    "config5_rays": dict(n=1000000, kw=dict(gausslets=False), builder="config5",
                          capture=dict(centre=(0.0, -12.0, 0.0), direction=(0.0, 1.0, 0.0), size=(12.0, 12.0))),
 }
 # algorithmic bytes per ray-segment: read the parent record, write
@@ -59,7 +76,7 @@ BYTES_GAUSSLET = (668, 60, 668)
 def workload_cfg(core, name, n, seed):
     from raypier_optics_b200 import configs
     w = WORKLOADS[name]
-    key = "config5" if name.startswith("config5") else name
+    key = w.get("builder", name)
     kw = dict(w["kw"])
     kw["n"] = n
     kw["seed"] = seed
@@ -140,6 +157,30 @@ def _cpu_worker(args):
     return sum(len(g) for g in gens), dt
 
 
+_POOL = None
+
+
+def _close_pool():
+    global _POOL
+    if _POOL is not None:
+        _POOL.close()
+        _POOL.join()
+        _POOL = None
+
+
+import atexit
+atexit.register(_close_pool)
+
+
+def cpu_pool(cores):
+    """One pool of worker processes for the whole run (spawning 16 interpreters per step would cost
+    more than the step)."""
+    global _POOL
+    if _POOL is None and cores > 1:
+        _POOL = mp.get_context("spawn").Pool(cores)
+    return _POOL
+
+
 def cpu_trace(name, n_total, cores, kind, seed=1234):
     """Shard n_total source rays over ``cores`` independent worker processes (each with its
     own scene copy; the reference loop is single-threaded under the GIL).  Returns
@@ -149,9 +190,7 @@ def cpu_trace(name, n_total, cores, kind, seed=1234):
     if cores == 1:
         res = [_cpu_worker(jobs[0])]
     else:
-        ctx = mp.get_context("spawn")
-        with ctx.Pool(cores) as pool:
-            res = pool.map(_cpu_worker, jobs)
+        res = cpu_pool(cores).map(_cpu_worker, jobs)
     segs = sum(r[0] for r in res)
     wall = max(r[1] for r in res)
     return segs, wall
@@ -162,6 +201,34 @@ def cpu_kind():
     return "reference" if (O.import_reference("timing") or O.import_reference("parity")) else "port"
 
 
+def cpu_sample_rays(name, args, cores):
+    """Bounded sample of the workload for the CPU arms: ~1-3 s of host work per step."""
+    per_core = args.ref_rays_per_core
+    if WORKLOADS[name]["kw"].get("gausslets"):
+        per_core = max(per_core // 8, 1000)  # 18 segments of 668-byte records per source gausslet
+    return min(WORKLOADS[name]["n"], per_core * cores)
+
+
+def bench_config(name, n, args):
+    """The `config` object of the JSON line: static description of the workload, identical for our arm
+    and the reference arm (the driver compares them)."""
+    w = WORKLOADS[name]
+    is_g = bool(w["kw"].get("gausslets"))
+    rec = 668 if is_g else 188
+    cfg = {"workload": name, "rays_per_gpu": int(n), "record_bytes": rec,
+           "record": "gausslet_t" if is_g else "ray_t",
+           "mode": w.get("mode", "keep"),
+           "parallelism": "source rays sharded by rank, scene replicated",
+           "l2": "inputs larger than L2 (%.0f MB per generation)" % (n * rec / 1e6) if n * rec > 126e6
+                 else "inputs smaller than L2: not flushed"}
+    if w.get("mode") == "consume":
+        cfg["chunk_rays"] = int(args.chunk_rays or ((1 << 20) if is_g else (1 << 22)))
+        cfg["consumers"] = "capture plane" + (" + %dx%d detector field" % (args.detector_grid, args.detector_grid)
+                                              if "detector" in w else "")
+        cfg["source"] = "seeded block of %d records repeated to %d" % (min(w["block"], n), n)
+    return cfg
+
+
 def run_reference_arm(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -169,9 +236,9 @@ def run_reference_arm(args):
     kind = cpu_kind()
     cores = os.cpu_count() or 1
     name = args.workload
-    # bounded sample: ~2e5 source rays per core per step keeps a step at a few seconds
-    n_sample = min(WORKLOADS[name]["n"], args.ref_rays_per_core * cores)
-    for _ in range(args.warmup):
+    n = args.rays if args.rays else WORKLOADS[name]["n"]
+    n_sample = cpu_sample_rays(name, args, cores)
+    for _ in range(min(args.warmup, 2)):
         cpu_trace(name, max(n_sample // 8, cores), cores, kind)
     segs_total, t_total = 0, 0.0
     for k in range(args.steps):
@@ -184,11 +251,12 @@ def run_reference_arm(args):
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": 1e3 * t_total / max(args.steps, 1), "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": name, "rays_per_step": n_sample,
-                   "note": "reference Cython trace_rays on host cores, source sharded over "
-                           "independent worker processes (the reference loop is single-threaded)"},
+        "config": bench_config(name, n, args),
+        "note": "reference Cython trace_rays on host cores, source sharded over independent worker "
+                "processes (the reference loop is single-threaded); each step a bounded sample of the workload",
         "cpu_baseline": {"value": value, "unit": "ray-segments/s", "cores": cores, "kind": kind,
-                         "sample": "%d source rays of %s per step, %d steps" % (n_sample, name, args.steps)},
+                         "sample": "%d source rays of %s per step, %d steps (the rate does not depend on the "
+                                   "source size: rays are independent)" % (n_sample, name, args.steps)},
         "e2e": {"value": value, "unit": "ray-segments/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -206,6 +274,18 @@ def load_peaks():
         except Exception:
             pass
     return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+FP64_PEAK_TINST = 63.6 * 148 * 1.965e9 / 1e12  # T fp64 lane-instructions/s, measured (profiles/microbench/fp64_latency.cu)
+
+
+def load_fp64(workload):
+    """fp64 instruction counts per launch of the FP64-bound workloads, from the committed ncu capture."""
+    p = os.path.join(ROOT, "profiles", "roofline_latest.json")
+    try:
+        return json.load(open(p)).get("fp64", {}).get(workload)
+    except Exception:
+        return None
 
 
 def load_traffic(workload, kernel):
@@ -429,13 +509,37 @@ def run_ours(args):
                 "per_launch_ms": {"k_shade": shade_ms_avg, "k_intersect": isect_ms_avg},
                 "generation": {"achieved": gen_ach, "frac": gen_ach / peak,
                                "note": "388 B/segment model over k_intersect + k_shade together"}}
+    fp64 = load_fp64(name)
+    if fp64 is not None:
+        # FP64-bound workload (config3: Newton on the asphere, secant + Zernike tape on the distorted face):
+        # fp64 instructions per ray counted by ncu (smsp__sass_thread_inst_executed_op_d{add,mul,fma}_pred_on,
+        # profiles/roofline_latest.json) x rays / kernel time, against the measured DFMA issue peak
+        n0 = float(gen_counts[0])
+        k_time = {"k_shade": shade_ms_avg, "k_intersect": isect_ms_avg}
+        per = {}
+        for kname in ("k_intersect", "k_shade"):
+            e = fp64.get(kname)
+            if e and k_time[kname] > 0:
+                inst = e["dadd"] + e["dmul"] + e["dfma"]
+                per[kname] = {"fp64_inst_per_ray": inst / e["rays"], "flop_per_ray": (e["dadd"] + e["dmul"] + 2 * e["dfma"]) / e["rays"],
+                              "achieved_tinst_s": inst / e["rays"] * n0 / (k_time[kname] * 1e-3) / 1e12,
+                              "achieved_tflops": (e["dadd"] + e["dmul"] + 2 * e["dfma"]) / e["rays"] * n0 / (k_time[kname] * 1e-3) / 1e12}
+        if dominant in per:
+            peak_inst = FP64_PEAK_TINST
+            roofline = {"bound": "fp64", "kernel": dominant, "achieved": per[dominant]["achieved_tinst_s"], "peak": peak_inst,
+                        "unit": "T fp64 inst/s", "frac": per[dominant]["achieved_tinst_s"] / peak_inst,
+                        "traffic": traffic, "peak_source": "measured DFMA issue rate, 63.6 lanes/clk/SM x 148 SMs x 1.965 GHz "
+                        "(profiles/microbench/fp64_latency.cu) = 36.4 TFLOP/s",
+                        "tflops": per[dominant]["achieved_tflops"], "tflops_peak": 2 * peak_inst,
+                        "per_kernel": per, "per_launch_ms": k_time,
+                        "hbm": {"achieved": ach, "peak": peak, "frac": ach / peak, "unit": "GB/s"}}
 
     # ---------------- CPU baseline (rank 0, N=1 only, bounded sample)
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
         kind = cpu_kind()
         cores = os.cpu_count() or 1
-        n_sample = min(WORKLOADS[name]["n"], args.ref_rays_per_core * cores)
+        n_sample = cpu_sample_rays(name, args, cores)
         csegs, cwall = cpu_trace(name, n_sample, cores, kind)
         cpu = {"value": csegs / cwall, "unit": "ray-segments/s", "cores": cores, "kind": kind,
                "sample": "%d source rays of %s sharded over %d worker processes" % (n_sample, name, cores)}
@@ -445,11 +549,8 @@ def run_ours(args):
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": dev_ms_max / args.steps,
         "wall_ms_per_step": wall_ms_max / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": name, "rays_per_gpu": int(rays.shape[0]), "generations": gen_counts,
-                   "segments_per_step_per_gpu": int(per_step_parents), "record_bytes": rec,
-                   "l2": "inputs larger than L2 (%.0f MB per generation)" % (rays.shape[0] * rec / 1e6)
-                   if rays.shape[0] * rec > 126e6 else "inputs smaller than L2: not flushed",
-                   "parallelism": "source rays sharded by rank, scene replicated"},
+        "config": bench_config(name, int(rays.shape[0]), args),
+        "trace": {"generations": gen_counts, "segments_per_step_per_gpu": int(per_step_parents)},
         "e2e": {"value": e2e_value, "unit": "ray-segments/s",
                 "h2d_bytes_per_step": int(rays.shape[0] * rec),
                 "d2h_bytes_per_step": int(d2h_records * rec),
@@ -462,6 +563,286 @@ def run_ours(args):
     }
     if capture is not None:
         line["e2e_capture"] = capture
+    print(json.dumps(line))
+    if distributed:
+        dist.destroy_process_group()
+    return 0
+
+
+def _mem_available_bytes():
+    try:
+        for line in open("/proc/meminfo"):
+            if line.startswith("MemAvailable:"):
+                return int(line.split()[1]) * 1024
+    except Exception:
+        pass
+    return 64 << 30
+
+
+def _fill_repeating(dst_u8, block_u8, threads=8):
+    """dst := block repeated (numpy releases the GIL in copies: a few threads saturate host DRAM)."""
+    import concurrent.futures as cf
+    B, n = block_u8.shape[0], dst_u8.shape[0]
+    jobs = [(lo, min(lo + B, n)) for lo in range(0, n, B)]
+
+    def one(j):
+        lo, hi = j
+        dst_u8[lo:hi] = block_u8[:hi - lo]
+
+    with cf.ThreadPoolExecutor(threads) as ex:
+        list(ex.map(one, jobs))
+
+
+def run_consume(args):
+    """The north-star workloads: sources too large to keep (1e8 rays / 1.25e8 gausslets per GPU), traced in
+    chunks by rpx_trace_consume with device-side consumers."""
+    import torch
+    import torch.distributed as dist
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    local_world = int(os.environ.get("LOCAL_WORLD_SIZE", str(world)))
+    distributed = world > 1
+    if not torch.cuda.is_available():
+        raise RuntimeError("bench.py needs a CUDA device: raypier_optics_b200 has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    if distributed:
+        dist.init_process_group(backend="nccl", device_id=torch.device("cuda", local_rank))
+    dev = torch.device("cuda", local_rank)
+
+    import raypier_optics_b200.core as core
+    from raypier_optics_b200 import configs, scene
+    from raypier_optics_b200 import distributed as rdist
+    from raypier_optics_b200.engine import Engine
+
+    name = args.workload
+    w = WORKLOADS[name]
+    n_req = args.rays if args.rays else w["n"]
+    is_g = bool(w["kw"].get("gausslets"))
+    rec = 668 if is_g else 188
+    chunk = int(args.chunk_rays or ((1 << 20) if is_g else (1 << 22)))
+    # HBM budget: the resident source + the working set of two chunks (bound-sized generation buffers of the
+    # pipelined loop, ~64 chunk-sized buffers for a branching trace, + the capture output)
+    free_b, _total_b = torch.cuda.mem_get_info(dev)
+    working = 80 * chunk * rec + (2 << 30)
+    n = int(min(n_req, max((free_b * 0.94 - working) // rec, chunk)))
+    block_n = int(min(w["block"], n))
+    t_setup = time.perf_counter()
+    cfg = workload_cfg(core, name, block_n, seed=100 + rank)  # every rank traces its own shard
+    block = np.ascontiguousarray(cfg["rays"])
+    assert block.dtype.itemsize == rec
+    sc = scene.Scene(cfg["face_lists"], cfg["wavelengths"])
+    eng = Engine(local_rank)
+    eng.set_scene(sc)
+    ml, rl = cfg["max_length"], cfg["recursion_limit"]
+    cp = w["capture"]
+    face = core.cfaces.RectangularFace(length=cp["size"][0], width=cp["size"][1], offset=0.0, z_plane=0.0)
+    fl = core.ctracer.FaceList(owner=configs.Pose(centre=cp["centre"], direction=cp["direction"]))
+    fl.faces = [face]
+    fl.sync_transforms()
+    eng.set_capture_scene(scene.Scene([fl], np.asarray([1.0])))
+    det, npt = None, 0
+    if "detector" in w:
+        side = args.detector_grid
+        xs = np.linspace(-w["detector"]["half_width"], w["detector"]["half_width"], side)
+        gx, gz = np.meshgrid(xs, xs)
+        pts = np.ascontiguousarray(np.stack([gx.ravel(), np.full(gx.size, w["detector"]["y"]), gz.ravel()], axis=1))
+        det = eng.detector(pts, cfg["wavelengths"])
+        npt = len(pts)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if distributed:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---------------- the source, resident in HBM as packed records (the seeded block repeated)
+    blk_u8 = torch.from_numpy(block.view(np.uint8).reshape(-1)).to(dev)
+    src = torch.empty(n * rec, dtype=torch.uint8, device=dev)
+    B = blk_u8.numel()
+    reps = (n * rec) // B
+    if reps:
+        src[:reps * B].view(reps, B).copy_(blk_u8.unsqueeze(0).expand(reps, B))
+    if n * rec > reps * B:
+        src[reps * B:].copy_(blk_u8[:n * rec - reps * B])
+    torch.cuda.synchronize()
+    del blk_u8
+
+    def collectives(counts, fc, with_field):
+        if not distributed:
+            return
+        rdist.exchange_counts(counts, fc, device=dev)
+        if with_field and det is not None:
+            rdist.allreduce_detector(eng, det)
+
+    def step_resident(consumers):
+        if det is not None and consumers:
+            det.reset()
+        r = eng.trace_consume(src.data_ptr(), ml, rl, n=n, is_gausslet=is_g, chunk_rays=chunk, capture=consumers,
+                              detector=det if consumers else None)
+        collectives(r.counts, r.face_counts, consumers)
+        return r
+
+    for _ in range(args.warmup):
+        step_resident(False)
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    barrier()
+    t0 = time.perf_counter()
+    dev_ms, trace_ms, segs, launches = 0.0, 0.0, 0, 0
+    k_ms = {"intersect": [0.0, 0], "shade": [0.0, 0]}
+    gen_counts = None
+    for _ in range(args.steps):
+        r = step_resident(False)
+        dev_ms += r.device_ms
+        trace_ms += r.trace_ms
+        segs += r.segments
+        launches += r.launches
+        for k in k_ms:
+            k_ms[k][0] += r.kernel_ms[k][0]
+            k_ms[k][1] += r.kernel_ms[k][1]
+        gen_counts = r.counts
+    barrier()
+    wall_ms = 1e3 * (time.perf_counter() - t0)
+    if rank == 0:
+        sampler.stop_flag.set()
+        sampler.join()
+    t = torch.tensor([dev_ms, wall_ms, trace_ms], dtype=torch.float64, device=dev)
+    sm = torch.tensor([segs, launches], dtype=torch.float64, device=dev)
+    if distributed:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dist.all_reduce(sm, op=dist.ReduceOp.SUM)
+    dev_ms_max, wall_ms_max, trace_ms_max = float(t[0]), float(t[1]), float(t[2])
+    segs_all, launches_all = float(sm[0]), float(sm[1])
+    value = segs_all / (dev_ms_max * 1e-3)
+
+    # the same, consumers on (capture plane + detector field), device-timed: one step
+    step_resident(True)
+    barrier()
+    rc = step_resident(True)
+    barrier()
+    with_consumers = {"value_this_rank": rc.segments / (rc.device_ms * 1e-3), "device_ms": rc.device_ms,
+                      "captured_rays": rc.n_captured, "detector_ms": det.ms if det is not None else None,
+                      "detector_points": npt}
+    del src
+    torch.cuda.empty_cache()
+
+    # ---------------- end-to-end arm: source in pinned HOST memory, every chunk crosses PCIe
+    avail = _mem_available_bytes()
+    budget = args.host_source_gb * (1 << 30) if args.host_source_gb else 0.45 * avail / max(local_world, 1)
+    n_host = int(max(min(n, budget // rec), min(n, chunk)))
+    pinned = eng.pinned_empty(n_host, block.dtype)
+    _fill_repeating(pinned.view(np.uint8).reshape(-1), block.view(np.uint8).reshape(-1))
+    passes = [(lo, min(lo + n_host, n)) for lo in range(0, n, n_host)]
+    setup_s = time.perf_counter() - t_setup
+
+    def step_e2e(consumers=True):
+        if det is not None and consumers:
+            det.reset()
+        nseg, ncap, counts, fc = 0, 0, None, None
+        for lo, hi in passes:
+            r = eng.trace_consume(pinned[:hi - lo], ml, rl, chunk_rays=chunk, capture=consumers,
+                                  detector=det if consumers else None)
+            nseg += r.segments
+            ncap += r.n_captured
+            counts = r.counts if counts is None else [a + b for a, b in zip(counts, r.counts)]
+            fc = r.face_counts if fc is None else fc + r.face_counts
+        collectives(counts, fc, consumers)
+        E = det.read() if (det is not None and consumers) else None   # D2H of the step's result
+        return nseg, ncap, E
+
+    e2e_steps = max(1, min(args.steps, args.e2e_steps))
+    step_e2e()
+    barrier()
+    t0 = time.perf_counter()
+    e2e_segs = 0
+    for _ in range(e2e_steps):
+        a, ncap, E = step_e2e()
+        e2e_segs += a
+    barrier()
+    e2e_s = time.perf_counter() - t0
+    # trace only (no consumers): H2D + trace + D2H of the counts
+    barrier()
+    t0 = time.perf_counter()
+    a_only, _, _ = step_e2e(False)
+    barrier()
+    e2e_only_s = time.perf_counter() - t0
+    te = torch.tensor([e2e_s, e2e_only_s], dtype=torch.float64, device=dev)
+    se = torch.tensor([e2e_segs, a_only], dtype=torch.float64, device=dev)
+    if distributed:
+        dist.all_reduce(te, op=dist.ReduceOp.MAX)
+        dist.all_reduce(se, op=dist.ReduceOp.SUM)
+    e2e_value = float(se[0]) / float(te[0])
+    e2e_only_value = float(se[1]) / float(te[1])
+    field_power = float((np.abs(E) ** 2).sum()) if E is not None else None
+
+    if rank != 0:
+        if distributed:
+            dist.destroy_process_group()
+        return 0
+
+    # ---------------- roofline of the dominant kernel
+    peak, peak_src = load_peaks()
+    b_in, b_wb, b_child = BYTES_GAUSSLET if is_g else BYTES_RAY
+    parents = sum(gen_counts)
+    children = sum(gen_counts[1:])
+    shade_ms_avg = k_ms["shade"][0] / max(k_ms["shade"][1], 1)
+    isect_ms_avg = k_ms["intersect"][0] / max(k_ms["intersect"][1], 1)
+    shade_launches_per_step = k_ms["shade"][1] / args.steps
+    shade_bytes_per_launch = (b_in * parents + b_child * children) / max(shade_launches_per_step, 1)
+    ach = shade_bytes_per_launch / (shade_ms_avg * 1e-3) / 1e9
+    gen_bytes = (b_in + b_wb) * parents + b_child * children
+    gen_ach = gen_bytes / ((k_ms["shade"][0] + k_ms["intersect"][0]) / args.steps * 1e-3) / 1e9
+    step_ach = gen_bytes / (dev_ms_max / args.steps * 1e-3) / 1e9
+    roofline = {"bound": "hbm", "kernel": "k_shade", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
+                "traffic": load_traffic(name, "k_shade"), "peak_source": peak_src,
+                "units_per_launch": parents / max(shade_launches_per_step, 1),
+                "per_launch_ms": {"k_shade": shade_ms_avg, "k_intersect": isect_ms_avg},
+                "kernel_share_of_step": {"k_shade": k_ms["shade"][0] / (dev_ms if dev_ms else 1),
+                                         "k_intersect": k_ms["intersect"][0] / (dev_ms if dev_ms else 1)},
+                "generation": {"achieved": gen_ach, "frac": gen_ach / peak,
+                               "note": "%d B/segment model over k_intersect + k_shade together" % (b_in + b_wb + b_child)},
+                "step": {"achieved": step_ach, "frac": step_ach / peak,
+                         "note": "same bytes over the whole device-timed step (transposition of every chunk included)"}}
+
+    cpu = None
+    if world == 1 and not args.no_cpu_baseline:
+        kind = cpu_kind()
+        cores = os.cpu_count() or 1
+        n_sample = cpu_sample_rays(name, args, cores)
+        csegs, cwall = cpu_trace(name, n_sample, cores, kind)
+        cpu = {"value": csegs / cwall, "unit": "ray-segments/s", "cores": cores, "kind": kind,
+               "sample": "%d source rays of %s sharded over %d worker processes (the rate does not depend on the "
+                         "source size: rays are independent; the full workload is %d x this sample)"
+                         % (n_sample, name, cores, max(n // max(n_sample, 1), 1))}
+
+    config = bench_config(name, n, args)
+    if n != n_req:
+        config["rays_per_gpu_requested"] = int(n_req)
+    line = {
+        "metric": METRIC, "value": value, "unit": "ray-segments/s", "n_gpus": world,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": dev_ms_max / args.steps,
+        "wall_ms_per_step": wall_ms_max / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": config,
+        "trace": {"generations": gen_counts, "segments_per_step_per_gpu": int(parents), "chunks_per_step": int(rc.n_chunks),
+                  "generation_loop_ms_per_step": trace_ms_max / args.steps, "setup_s": setup_s},
+        "value_with_consumers": with_consumers,
+        "e2e": {"value": e2e_value, "unit": "ray-segments/s",
+                "h2d_bytes_per_step": int(n * rec),
+                "d2h_bytes_per_step": int(npt * 48 + 8 * len(gen_counts) + 4 * sc.n_traced_faces),
+                "steps": e2e_steps, "captured_rays_per_step": int(ncap), "detector_points": npt,
+                "field_power": field_power,
+                "host_source_rays": n_host, "passes_per_step": len(passes),
+                "api": "Engine.trace_consume (rpx_trace_consume): pinned host source, chunk %d, capture plane%s, "
+                       "D2H = field + counts" % (chunk, " + detector field" if det is not None else ""),
+                "trace_only_value": e2e_only_value},
+        "gpu_launches": int(launches_all),
+        "clocks": sampler.summary(),
+        "roofline": roofline,
+        "cpu_baseline": cpu,
+    }
     print(json.dumps(line))
     if distributed:
         dist.destroy_process_group()
@@ -501,6 +882,7 @@ def run_fields(args):
     d_pts = torch.from_numpy(pts).cuda()
     d_out = torch.zeros((n_pt, 6), dtype=torch.float64, device="cuda")
     pinned_pts = torch.from_numpy(pts).pin_memory()
+    torch.cuda.synchronize()  # d_pts / d_out were produced on torch's stream, the library runs on its own
     for _ in range(max(args.warmup, 3)):
         fm.evaluate_device(d_pts.data_ptr(), n_pt, d_out.data_ptr())
     sampler = ClockSampler(0)
@@ -509,6 +891,7 @@ def run_fields(args):
     ms = 0.0
     for _ in range(args.steps):
         d_out.zero_()
+        torch.cuda.current_stream().synchronize()
         fm.evaluate_device(d_pts.data_ptr(), n_pt, d_out.data_ptr())
         ms += fm.last_ms
     torch.cuda.synchronize()
@@ -590,10 +973,14 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="config2", choices=sorted(WORKLOADS))
+    ap.add_argument("--workload", default="config5", choices=sorted(WORKLOADS))
     ap.add_argument("--rays", type=int, default=0, help="source rays per GPU (default: the config's)")
     ap.add_argument("--e2e-steps", type=int, default=5)
-    ap.add_argument("--chunk-rays", type=int, default=131072, help="source rays per chunk of the streamed e2e call")
+    ap.add_argument("--chunk-rays", type=int, default=0,
+                    help="source rays per chunk (0: 131072 for rpx_trace_streamed, 2^20 gausslets / 2^22 rays for rpx_trace_consume)")
+    ap.add_argument("--detector-grid", type=int, default=16, help="side of the detector grid of the consume-mode e2e arm")
+    ap.add_argument("--host-source-gb", type=float, default=0.0,
+                    help="cap of the pinned host source of the consume-mode e2e arm (0: 45%% of MemAvailable per local rank)")
     ap.add_argument("--ref-rays-per-core", type=int, default=200000)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--capture", action="store_true",
@@ -606,6 +993,10 @@ def main():
         return run_fields(args)
     if args.impl == "reference":
         return run_reference_arm(args)
+    if WORKLOADS[args.workload].get("mode") == "consume":
+        return run_consume(args)
+    if not args.chunk_rays:
+        args.chunk_rays = 131072
     return run_ours(args)
 
 

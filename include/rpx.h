@@ -353,6 +353,16 @@ int rpx_trace(rpx_ctx* ctx, const void* rays_aos, uint64_t n, int is_gausslet,
               double max_length, int recursion_limit, uint32_t flags,
               rpx_result** out_result);
 
+/* ONE generation (trace_segment_c / trace_gausslet_c, ctracer.pyx:2062-2118, 2214-2281) for traces that
+ * need the host between generations: ResampleGaussletMaterial (cmaterials.pyx:1766-1831) hands the
+ * gausslets that reached it to a Python callback and appends what it returns to the new generation
+ * (eval_decomposed_rays_c, ctracer.pyx:2274-2278).  `rays` (still owned by the caller) is intersected
+ * with every face and written back in place; *out_children owns the new generation, NOT yet intersected
+ * (the next step does that; length = INF, or max_length for gausslets, :2280).  face_counts[n_traced_faces]
+ * (may be NULL) is ADDED to: Face.count accumulates over the generations of a trace (:2108).          */
+int rpx_trace_step(rpx_ctx* ctx, rpx_rays* rays, double max_length, rpx_rays** out_children,
+                   uint32_t* face_counts);
+
 /* Replaces trace_ray_sequence (core/tracer.py:50-99) over trace_one_face_segment_c /
  * trace_one_face_gausslet_c (ctracer.pyx:2121-2170, 2284-2347): step s intersects ONLY the
  * face with global index face_seq[s] (FaceList.intersect_one_face_c, ctracer.pyx:1861-1879).
@@ -464,12 +474,105 @@ int rpx_field_modes(rpx_ctx* ctx, const rpx_field* field, double* modes_out);
 int rpx_field_evaluate(rpx_ctx* ctx, rpx_field* field, const double* points, uint64_t npt, double time_ps,
                        double* out);
 /* Same with DEVICE pointers; d_out is ACCUMULATED into (zero it first) so partial fields of
- * several ray shards can share one buffer before an all-reduce.  Returns after the kernel ended. */
+ * several ray shards can share one buffer before an all-reduce.  Returns after the kernel ended.
+ * The kernel runs on rpx_stream(ctx), a NON-BLOCKING stream: a caller that produced d_points / d_out
+ * on another stream (a torch tensor's zero fill, say) must synchronise that stream first.          */
 int rpx_field_evaluate_device(rpx_ctx* ctx, rpx_field* field, const double* d_points, uint64_t npt,
                               double time_ps, double* d_out);
 /* Device time (ms) of the last summation kernel of this field (CUDA events) */
 double rpx_field_last_ms(const rpx_field* field);
 void rpx_field_free(rpx_ctx* ctx, rpx_field* field);
+
+/* ---------------------------------------------------------- terminal rays
+ * The rays a trace ends with: rays that hit nothing -- end_face_idx left at (unsigned)-1 by the write-back
+ * of trace_segment_c / FaceList.intersect_c (ctracer.pyx:2086-2087, 1900-1903) -- and / or rays that end
+ * on chosen faces (absorbers and detectors: BeamStop, an OpaqueMaterial target).  A device filter over
+ * device-resident generations; selected records are appended unchanged in (collection, ray) order.
+ * face_select: n_traced_faces bytes, non-zero = rays ending on that face are selected (NULL = none).
+ * counts[j] (may be NULL) = rays selected from collection j.  *out owns a new device collection.        */
+int rpx_select_terminal(rpx_ctx* ctx, const rpx_rays* const* gens, int n_gens, int select_unterminated,
+                        const uint8_t* face_select, rpx_rays** out, uint64_t* counts);
+/* Device-resident AoS export / import of a collection (the packed ray_t / gausslet_t records of
+ * copy_as_array / from_array, ctracer.pyx:1048-1054, 1142-1154) into / from CALLER-OWNED DEVICE memory,
+ * e.g. a torch tensor: what an NCCL gather of terminal rays sends and receives, with no host bounce.
+ * d_aos must be 4-byte aligned and hold `capacity` records; both calls return after the copy finished. */
+int rpx_rays_export_device(rpx_ctx* ctx, const rpx_rays* rays, void* d_aos, uint64_t capacity);
+int rpx_rays_import_device(rpx_ctx* ctx, const void* d_aos, uint64_t n, int is_gausslet, rpx_rays** out_rays);
+
+/* ---------------------------------------------------------- detector (accumulating E-field)
+ * EFieldSummation / eval_Efield_from_gausslets (fields.py:206-277) as a long-lived device object: a fixed
+ * set of points and a complex field that gausslet collections are summed INTO, one collection after the
+ * other (the sum over rays is associative), so that a trace too large to keep can feed it chunk by chunk.
+ * The partial fields of several GPUs are combined with one all-reduce of rpx_detector_field_device().   */
+typedef struct rpx_detector rpx_detector;
+int rpx_detector_create(rpx_ctx* ctx, const double* points, uint64_t npt, const double* wavelengths, int n_wavelengths,
+                        double blending, double time_ps, rpx_detector** out);
+/* field := 0, modes := 0 */
+int rpx_detector_reset(rpx_ctx* ctx, rpx_detector* det);
+/* Fit the modes of a device-resident gausslet collection and add their field at every point. */
+int rpx_detector_accumulate(rpx_ctx* ctx, rpx_detector* det, const rpx_rays* gausslets);
+/* npt x 3 complex128 into host memory */
+int rpx_detector_read(rpx_ctx* ctx, rpx_detector* det, double* field_out);
+/* device pointer of the npt x 6 doubles (re, im interleaved), e.g. for ncclAllReduce */
+void* rpx_detector_field_device(rpx_detector* det);
+uint64_t rpx_detector_npoints(const rpx_detector* det);
+/* gausslets summed since the last reset / device time (ms, CUDA events) of the summation kernels since then */
+uint64_t rpx_detector_modes(const rpx_detector* det);
+double rpx_detector_ms(rpx_ctx* ctx, rpx_detector* det);
+void rpx_detector_free(rpx_ctx* ctx, rpx_detector* det);
+
+/* ---------------------------------------------------------- streamed trace with device-side consumers
+ * trace_rays (core/tracer.py:9-47) for sources whose generations cannot be kept or shipped: the BASELINE
+ * configs at 1e8 - 1e9 rays (one generation of 1e9 gausslets is 668 GB).  The source -- host memory, or
+ * device memory with RPX_CONSUME_SOURCE_ON_DEVICE -- is cut into contiguous chunks; every chunk is traced
+ * through all its generations on the device (the upload of the next chunk overlaps), handed to the
+ * consumers below, and freed.  What survives a chunk is what the reference's post-trace consumers keep:
+ *   - len(traced_rays[g]) and Face.count, summed over chunks (always);
+ *   - RPX_CONSUME_TERMINAL: the terminal rays (rpx_select_terminal) of every generation;
+ *   - RPX_CONSUME_CAPTURE: the rays crossing the capture plane set with rpx_capture_scene_set
+ *     (select_ray_intersections / select_gausslet_intersections, ctracer.pyx:1981-2058);
+ *   - RPX_CONSUME_FIELD (gausslets, needs RPX_CONSUME_CAPTURE): the captured gausslets summed into
+ *     `detector` (cfields.pyx:51-117), then dropped unless captured_capacity asks to keep them.
+ * Kept collections stay on the device (*terminal / *captured, to download, export or feed onwards) in
+ * (chunk, generation, ray) order with parent_idx numbered globally as in rpx_trace_streamed;
+ * per_chunk_* (optional, n_chunks x max_gens entries, row-major) give the piece sizes needed to restore
+ * the reference's (generation, ray) order.  A capacity of 0 counts without keeping; a selection larger
+ * than a non-zero capacity is RPX_ERR_NOMEM.                                                            */
+#define RPX_CONSUME_SOURCE_ON_DEVICE 1u
+#define RPX_CONSUME_TERMINAL 2u       /* rays that hit nothing ...                       */
+#define RPX_CONSUME_CAPTURE 4u
+#define RPX_CONSUME_FIELD 8u
+#define RPX_CONSUME_MAX_GENS 256
+
+typedef struct rpx_consume_opts {
+    uint64_t chunk_rays;           /* source rays per chunk; 0 = default (2^20 gausslets / 2^22 rays)   */
+    uint32_t flags;                /* RPX_CONSUME_*                                                      */
+    int32_t max_gens;              /* row length of per_chunk_* (<= RPX_CONSUME_MAX_GENS)                */
+    const uint8_t* terminal_faces; /* ... and rays ending on these faces (n_traced_faces bytes or NULL)  */
+    uint64_t terminal_capacity;    /* records of terminal rays to keep on the device                     */
+    uint64_t captured_capacity;    /* records of captured rays to keep on the device                     */
+    rpx_detector* detector;        /* RPX_CONSUME_FIELD                                                  */
+    uint64_t* per_chunk_terminal;  /* optional outputs, n_chunks x max_gens                              */
+    uint64_t* per_chunk_captured;
+} rpx_consume_opts;
+
+typedef struct rpx_consume_result {
+    int32_t n_gens;                /* len(traced_rays)                                                   */
+    int32_t n_chunks;
+    uint64_t counts[RPX_CONSUME_MAX_GENS]; /* len(traced_rays[g])                                        */
+    uint64_t n_terminal, n_captured;       /* rays selected (kept or not)                                */
+    rpx_rays* terminal;            /* kept terminal rays (NULL when terminal_capacity == 0)              */
+    rpx_rays* captured;            /* kept captured rays (NULL when captured_capacity == 0)              */
+    double device_ms;              /* first to last device operation of the call on the tracing stream   */
+    double trace_ms;               /* summed device time of the generation loops                         */
+    double shade_ms, intersect_ms; /* summed device time per kernel family ...                           */
+    uint64_t shade_launches, intersect_launches; /* ... and their launch counts                          */
+    uint64_t launches;             /* every kernel launched by this call                                 */
+} rpx_consume_result;
+
+int rpx_trace_consume(rpx_ctx* ctx, const void* rays_aos, uint64_t n, int is_gausslet, double max_length,
+                      int recursion_limit, const rpx_consume_opts* opts, uint32_t* face_counts,
+                      rpx_consume_result* result);
 
 /* ---------------------------------------------------------- unit entry points
  * Batch evaluation of ONE device function over host arrays -- the GPU counterpart of the

@@ -142,3 +142,30 @@ class rpx_scene(C.Structure):
 
 
 assert C.sizeof(rpx_scene) == 144
+
+
+# ---- rpx_trace_consume (include/rpx.h) ----------------------------------------
+CONSUME_SOURCE_ON_DEVICE = 1
+CONSUME_TERMINAL = 2
+CONSUME_CAPTURE = 4
+CONSUME_FIELD = 8
+CONSUME_MAX_GENS = 256
+
+
+class rpx_consume_opts(C.Structure):
+    _fields_ = [("chunk_rays", C.c_uint64), ("flags", C.c_uint32), ("max_gens", C.c_int32),
+                ("terminal_faces", C.c_void_p), ("terminal_capacity", C.c_uint64),
+                ("captured_capacity", C.c_uint64), ("detector", C.c_void_p),
+                ("per_chunk_terminal", C.c_void_p), ("per_chunk_captured", C.c_void_p)]
+
+
+class rpx_consume_result(C.Structure):
+    _fields_ = [("n_gens", C.c_int32), ("n_chunks", C.c_int32), ("counts", C.c_uint64 * CONSUME_MAX_GENS),
+                ("n_terminal", C.c_uint64), ("n_captured", C.c_uint64), ("terminal", C.c_void_p),
+                ("captured", C.c_void_p), ("device_ms", C.c_double), ("trace_ms", C.c_double),
+                ("shade_ms", C.c_double), ("intersect_ms", C.c_double), ("shade_launches", C.c_uint64),
+                ("intersect_launches", C.c_uint64), ("launches", C.c_uint64)]
+
+
+assert C.sizeof(rpx_consume_opts) == 64
+assert C.sizeof(rpx_consume_result) == 8 + 8 * CONSUME_MAX_GENS + 16 + 16 + 32 + 24

@@ -25,6 +25,10 @@ EXPORTS = (
     "rpx_field_prepare", "rpx_field_count", "rpx_field_modes", "rpx_field_evaluate",
     "rpx_field_evaluate_device", "rpx_field_last_ms", "rpx_field_free", "rpx_trace_streamed",
     "rpx_rays_project_to_sphere", "rpx_field_prepare_neighbours", "rpx_unit_evaluate_modes",
+    "rpx_select_terminal", "rpx_rays_export_device", "rpx_rays_import_device",
+    "rpx_detector_create", "rpx_detector_reset", "rpx_detector_accumulate", "rpx_detector_read",
+    "rpx_detector_field_device", "rpx_detector_npoints", "rpx_detector_modes", "rpx_detector_ms",
+    "rpx_detector_free", "rpx_trace_consume", "rpx_trace_step",
 )
 
 
@@ -133,6 +137,34 @@ def load():
     L.rpx_field_free.restype = None
     L.rpx_trace_streamed.argtypes = [vp, vp, u64, i32, d, i32, u64, vp, vp, i32, vp, vp, vp, vp]
     L.rpx_trace_streamed.restype = i32
+    L.rpx_select_terminal.argtypes = [vp, vp, i32, i32, vp, pvp, vp]
+    L.rpx_select_terminal.restype = i32
+    L.rpx_rays_export_device.argtypes = [vp, vp, vp, u64]
+    L.rpx_rays_export_device.restype = i32
+    L.rpx_rays_import_device.argtypes = [vp, vp, u64, i32, pvp]
+    L.rpx_rays_import_device.restype = i32
+    L.rpx_detector_create.argtypes = [vp, vp, u64, vp, i32, d, d, pvp]
+    L.rpx_detector_create.restype = i32
+    L.rpx_detector_reset.argtypes = [vp, vp]
+    L.rpx_detector_reset.restype = i32
+    L.rpx_detector_accumulate.argtypes = [vp, vp, vp]
+    L.rpx_detector_accumulate.restype = i32
+    L.rpx_detector_read.argtypes = [vp, vp, vp]
+    L.rpx_detector_read.restype = i32
+    L.rpx_detector_field_device.argtypes = [vp]
+    L.rpx_detector_field_device.restype = vp
+    L.rpx_detector_npoints.argtypes = [vp]
+    L.rpx_detector_npoints.restype = u64
+    L.rpx_detector_modes.argtypes = [vp]
+    L.rpx_detector_modes.restype = u64
+    L.rpx_detector_ms.argtypes = [vp, vp]
+    L.rpx_detector_ms.restype = d
+    L.rpx_detector_free.argtypes = [vp, vp]
+    L.rpx_detector_free.restype = None
+    L.rpx_trace_step.argtypes = [vp, vp, d, pvp, vp]
+    L.rpx_trace_step.restype = i32
+    L.rpx_trace_consume.argtypes = [vp, vp, u64, i32, d, i32, vp, vp, vp]
+    L.rpx_trace_consume.restype = i32
     if L.rpx_abi_version() != A.RPX_ABI_VERSION:
         raise RuntimeError("librpx.so ABI %d != binding ABI %d" % (L.rpx_abi_version(), A.RPX_ABI_VERSION))
     _LIB = L

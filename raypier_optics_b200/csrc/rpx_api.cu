@@ -898,6 +898,79 @@ extern "C" int rpx_trace(rpx_ctx* ctx, const void* rays_aos, uint64_t n, int is_
     return rpx_trace_device(ctx, r, max_length, recursion_limit, flags, out_result);  // owns r either way
 }
 
+// ------------------------------------------------------------------ one generation at a time
+// trace_segment_c / trace_gausslet_c as ONE call (ctracer.pyx:2062-2118, 2214-2281) for traces that
+// need the host between generations: ResampleGaussletMaterial hands the gausslets that reached it to a
+// Python callback and appends what it returns to the new generation (cmaterials.pyx:1766-1831,
+// ctracer.pyx:2274-2278).  `rays` is intersected with every face and written back in place (length,
+// end_face_idx, parabasal lengths); the children come back un-intersected, as the materials left them
+// (length INF, or max_length for gausslets: reset_length_c, :2280) -- the next step intersects them.
+extern "C" int rpx_trace_step(rpx_ctx* ctx, rpx_rays* rays, double max_length, rpx_rays** out_children,
+                              uint32_t* face_counts) {
+    if (!ctx || !rays || !out_children) return fail(ctx, RPX_ERR_INVALID, "NULL argument");
+    *out_children = nullptr;
+    if (!ctx->have_scene) return fail(ctx, RPX_ERR_STATE, "rpx_scene_set must be called before tracing");
+    CU(ctx, cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->stream;
+    const int is_g = rays->is_gausslet;
+    const double ml = is_g ? max_length : (double)(float)max_length;  // `float max_length`, ctracer.pyx:2066
+    const unsigned long long n = rays->soa.n;
+    const unsigned long long kids = (unsigned long long)(ctx->max_kids > 0 ? ctx->max_kids : 1);
+    if (n * kids >= 0xFFFFFFFFull) return fail(ctx, RPX_ERR_INVALID, "generation would exceed the 32-bit parent_idx of ray_t");
+    rpx_rays* child = nullptr;
+    int rc = rpx_rays_alloc(ctx, n * kids, is_g, &child);
+    if (rc != RPX_OK) return rc;
+    if (n == 0) {
+        *out_children = child;
+        return RPX_OK;
+    }
+    auto bail = [&](cudaError_t e, const char* what) {
+        rpx_rays_free(ctx, child);
+        return fail(ctx, e == cudaErrorMemoryAllocation ? RPX_ERR_NOMEM : RPX_ERR_CUDA, "%s failed: %s", what, cudaGetErrorString(e));
+    };
+    const uint32_t n_tiles = (uint32_t)((n + RPX_TILE - 1) / RPX_TILE);
+    const size_t state_words = rpx_state_words(n_tiles);
+    cudaError_t e;
+    if (state_words > ctx->tile_state_cap) {
+        if (ctx->tile_state) cudaFree(ctx->tile_state);
+        ctx->tile_state = nullptr;
+        ctx->tile_state_cap = 0;
+        if ((e = cudaMalloc(&ctx->tile_state, state_words * 2 * sizeof(unsigned long long))) != cudaSuccess) return bail(e, "cudaMalloc(tile state)");
+        ctx->tile_state_cap = state_words * 2;
+    }
+    const size_t nfc = (size_t)(ctx->n_traced > 0 ? ctx->n_traced : 1);
+    std::vector<uint32_t> fc(nfc, 0u);
+    if ((e = cudaMemsetAsync(ctx->d_face_counts, 0, sizeof(uint32_t) * nfc, st)) != cudaSuccess ||
+        (e = cudaMemsetAsync(ctx->tile_state, 0, state_words * sizeof(unsigned long long), st)) != cudaSuccess ||
+        (e = cudaMemsetAsync(ctx->tile_counter, 0, sizeof(uint32_t), st)) != cudaSuccess ||
+        (e = launch_intersect(ctx->face_class, st, n_tiles, ctx->scene_smem, ctx->ds, rays->soa, ml, -1)) != cudaSuccess)
+        return bail(e, "k_intersect");
+    ShadeArgs sa;
+    sa.S = ctx->ds;
+    sa.in = rays->soa;
+    sa.out = child->soa;
+    sa.max_length = ml;
+    sa.tile_state = ctx->tile_state;
+    sa.tile_counter = ctx->tile_counter;
+    sa.d_count = ctx->d_count;
+    sa.face_counts = ctx->d_face_counts;
+    sa.n_tiles = n_tiles;
+    sa.smem_bytes = ctx->scene_smem;
+    sa.ahead_face = -2;  // children stay un-intersected
+    sa.n_dev = nullptr;
+    sa.h_count = nullptr;
+    if ((e = shade_launcher(is_g, ctx->face_class, ctx->mm_idx, ctx->scene_smem > 0)(st, sa)) != cudaSuccess ||
+        (e = cudaMemcpyAsync(ctx->h_count, ctx->d_count, sizeof(unsigned long long), cudaMemcpyDeviceToHost, st)) != cudaSuccess ||
+        (e = cudaMemcpyAsync(fc.data(), ctx->d_face_counts, sizeof(uint32_t) * (size_t)ctx->n_traced, cudaMemcpyDeviceToHost, st)) != cudaSuccess ||
+        (e = cudaStreamSynchronize(st)) != cudaSuccess)
+        return bail(e, "k_shade");
+    child->soa.n = *ctx->h_count;
+    if (face_counts)
+        for (int i = 0; i < ctx->n_traced; i++) face_counts[i] += fc[(size_t)i];
+    *out_children = child;
+    return RPX_OK;
+}
+
 // ------------------------------------------------------------------ capture planes
 extern "C" const rpx_rays* rpx_result_rays(const rpx_result* res, int g) {
     if (!res || g < 0 || g >= (int)res->gens.size()) return nullptr;
@@ -916,7 +989,7 @@ extern "C" int rpx_capture(rpx_ctx* ctx, const rpx_rays* const* gens, int n_gens
         if (gens[j]->is_gausslet != gens[0]->is_gausslet)
             return fail(ctx, RPX_ERR_INVALID, "collections mix rays and gausslets");
         total += gens[j]->soa.n;
-        tiles_total += (gens[j]->soa.n + RPX_TILE - 1) / RPX_TILE;
+        tiles_total += rpx_state_words((gens[j]->soa.n + RPX_TILE - 1) / RPX_TILE);  // grouped look-back state
     }
     const int is_g = gens[0]->is_gausslet;
     rpx_rays* dst = nullptr;
@@ -973,7 +1046,7 @@ extern "C" int rpx_capture(rpx_ctx* ctx, const rpx_rays* const* gens, int n_gens
         a.smem_bytes = ctx->cap_smem;
         if ((e = launch_capture(is_g, ctx->cap_face_class, ctx->stream, n_tiles, a)) != cudaSuccess)
             return bail(e, "k_capture launch");
-        tile_off += n_tiles;
+        tile_off += rpx_state_words(n_tiles);
     }
     std::vector<unsigned long long> h_totals((size_t)n_gens + 1);
     if ((e = cudaMemcpyAsync(h_totals.data(), d_totals, sizeof(unsigned long long) * h_totals.size(),

@@ -686,3 +686,149 @@ extern "C" void rpx_field_free(rpx_ctx* ctx, rpx_field* f) {
     }
     delete f;
 }
+
+// ------------------------------------------------------------------ detector (accumulating field)
+// EFieldSummation (fields.py:206-249) as a long-lived device object: points and wavelengths uploaded once,
+// gausslet collections summed into one field buffer collection after collection, nothing synchronised
+// until the field is read -- the consumer at the end of rpx_trace_consume's chunk pipeline.
+struct rpx_detector {
+    double* d_points;
+    double* d_field;  // npt x 6
+    double* d_wl;
+    int n_wl;
+    uint64_t npt;
+    double blending, time_ps;
+    uint64_t modes;
+    double ms_done;
+    std::vector<cudaEvent_t> ev;  // start / stop pairs not yet harvested
+};
+
+static void detector_harvest(rpx_detector* det, bool wait) {
+    size_t keep = 0;
+    for (size_t i = 0; i + 1 < det->ev.size(); i += 2) {
+        const bool done = wait ? (cudaEventSynchronize(det->ev[i + 1]) == cudaSuccess)
+                               : (cudaEventQuery(det->ev[i + 1]) == cudaSuccess);
+        if (done) {
+            float ms = 0.f;
+            if (cudaEventElapsedTime(&ms, det->ev[i], det->ev[i + 1]) == cudaSuccess) det->ms_done += ms;
+            cudaEventDestroy(det->ev[i]);
+            cudaEventDestroy(det->ev[i + 1]);
+        } else {
+            det->ev[keep++] = det->ev[i];
+            det->ev[keep++] = det->ev[i + 1];
+        }
+    }
+    det->ev.resize(keep);
+}
+
+extern "C" int rpx_detector_create(rpx_ctx* ctx, const double* points, uint64_t npt, const double* wavelengths,
+                                   int n_wavelengths, double blending, double time_ps, rpx_detector** out) {
+    if (!ctx || !out || (!points && npt) || !wavelengths || n_wavelengths <= 0)
+        return fail(ctx, RPX_ERR_INVALID, "NULL argument");
+    *out = nullptr;
+    CU(ctx, cudaSetDevice(ctx->device));
+    rpx_detector* det = new (std::nothrow) rpx_detector();
+    if (!det) return fail(ctx, RPX_ERR_NOMEM, "out of host memory");
+    det->d_points = det->d_field = det->d_wl = nullptr;
+    det->n_wl = n_wavelengths;
+    det->npt = npt;
+    det->blending = blending;
+    det->time_ps = time_ps;
+    det->modes = 0;
+    det->ms_done = 0.0;
+    const size_t np_ = npt ? npt : 1;
+    cudaError_t e;
+    if ((e = cudaMalloc((void**)&det->d_points, np_ * 3 * sizeof(double))) != cudaSuccess ||
+        (e = cudaMalloc((void**)&det->d_field, np_ * 6 * sizeof(double))) != cudaSuccess ||
+        (e = cudaMalloc((void**)&det->d_wl, sizeof(double) * (size_t)n_wavelengths)) != cudaSuccess ||
+        (npt && (e = cudaMemcpyAsync(det->d_points, points, npt * 3 * sizeof(double), cudaMemcpyHostToDevice, ctx->stream)) != cudaSuccess) ||
+        (e = cudaMemcpyAsync(det->d_wl, wavelengths, sizeof(double) * (size_t)n_wavelengths, cudaMemcpyHostToDevice, ctx->stream)) != cudaSuccess ||
+        (e = cudaMemsetAsync(det->d_field, 0, np_ * 6 * sizeof(double), ctx->stream)) != cudaSuccess ||
+        (e = cudaStreamSynchronize(ctx->stream)) != cudaSuccess) {
+        if (det->d_points) cudaFree(det->d_points);
+        if (det->d_field) cudaFree(det->d_field);
+        if (det->d_wl) cudaFree(det->d_wl);
+        delete det;
+        return fail(ctx, e == cudaErrorMemoryAllocation ? RPX_ERR_NOMEM : RPX_ERR_CUDA, "detector set-up: %s", cudaGetErrorString(e));
+    }
+    *out = det;
+    return RPX_OK;
+}
+
+extern "C" int rpx_detector_reset(rpx_ctx* ctx, rpx_detector* det) {
+    if (!ctx || !det) return fail(ctx, RPX_ERR_INVALID, "NULL argument");
+    CU(ctx, cudaSetDevice(ctx->device));
+    detector_harvest(det, true);
+    CU(ctx, cudaMemsetAsync(det->d_field, 0, (det->npt ? det->npt : 1) * 6 * sizeof(double), ctx->stream));
+    det->modes = 0;
+    det->ms_done = 0.0;
+    return RPX_OK;
+}
+
+// No host synchronisation: the mode records live in the stream-ordered pool for exactly two kernels.
+extern "C" int rpx_detector_accumulate(rpx_ctx* ctx, rpx_detector* det, const rpx_rays* rays) {
+    if (!ctx || !det || !rays) return fail(ctx, RPX_ERR_INVALID, "NULL argument");
+    if (!rays->is_gausslet)
+        return fail(ctx, RPX_ERR_INVALID, "a detector sums gausslets (plain rays carry no parabasal rays to fit a mode to)");
+    const uint64_t n = rays->soa.n;
+    if (!n || !det->npt) return RPX_OK;
+    CU(ctx, cudaSetDevice(ctx->device));
+    detector_harvest(det, false);
+    rpx_field f;
+    f.n = n;
+    f.rec = f.modes = nullptr;
+    f.last_ms = 0.f;
+    cudaError_t e;
+    if ((e = cudaMallocAsync((void**)&f.rec, n * M_NF * sizeof(double), ctx->stream)) != cudaSuccess ||
+        (e = cudaMallocAsync((void**)&f.modes, n * 6 * sizeof(double), ctx->stream)) != cudaSuccess) {
+        if (f.rec) cudaFreeAsync(f.rec, ctx->stream);
+        return fail(ctx, RPX_ERR_NOMEM, "mode records of %llu gausslets: %s", (unsigned long long)n, cudaGetErrorString(e));
+    }
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    cudaEventCreate(&ev0);
+    cudaEventCreate(&ev1);
+    cudaEventRecord(ev0, ctx->stream);
+    const unsigned T = 128, G = (unsigned)((n + T - 1) / T);
+    k_field_prepare<true><<<G, T, 0, ctx->stream>>>(rays->soa, nullptr, det->d_wl, det->n_wl, det->blending, f.rec, f.modes);
+    int rc = (e = cudaGetLastError()) == cudaSuccess ? field_launch(ctx, &f, det->d_points, det->npt, det->time_ps, det->d_field, nullptr, nullptr)
+                                                     : fail(ctx, RPX_ERR_CUDA, "k_field_prepare launch: %s", cudaGetErrorString(e));
+    cudaEventRecord(ev1, ctx->stream);
+    det->ev.push_back(ev0);
+    det->ev.push_back(ev1);
+    cudaFreeAsync(f.rec, ctx->stream);
+    cudaFreeAsync(f.modes, ctx->stream);
+    if (rc == RPX_OK) det->modes += n;
+    return rc;
+}
+
+extern "C" int rpx_detector_read(rpx_ctx* ctx, rpx_detector* det, double* field_out) {
+    if (!ctx || !det || (!field_out && det->npt)) return fail(ctx, RPX_ERR_INVALID, "NULL argument");
+    CU(ctx, cudaSetDevice(ctx->device));
+    if (det->npt) CU(ctx, cudaMemcpyAsync(field_out, det->d_field, det->npt * 6 * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    CU(ctx, cudaStreamSynchronize(ctx->stream));
+    return RPX_OK;
+}
+
+extern "C" void* rpx_detector_field_device(rpx_detector* det) { return det ? (void*)det->d_field : nullptr; }
+extern "C" uint64_t rpx_detector_npoints(const rpx_detector* det) { return det ? det->npt : 0; }
+extern "C" uint64_t rpx_detector_modes(const rpx_detector* det) { return det ? det->modes : 0; }
+
+extern "C" double rpx_detector_ms(rpx_ctx* ctx, rpx_detector* det) {
+    if (!ctx || !det) return 0.0;
+    cudaSetDevice(ctx->device);
+    detector_harvest(det, true);
+    return det->ms_done;
+}
+
+extern "C" void rpx_detector_free(rpx_ctx* ctx, rpx_detector* det) {
+    if (!det) return;
+    if (ctx) {
+        cudaSetDevice(ctx->device);
+        cudaStreamSynchronize(ctx->stream);
+        detector_harvest(det, true);
+        cudaFree(det->d_points);
+        cudaFree(det->d_field);
+        cudaFree(det->d_wl);
+    }
+    delete det;
+}

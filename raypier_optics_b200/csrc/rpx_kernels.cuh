@@ -424,9 +424,13 @@ k_capture(DevScene S, Soa in, Soa out, unsigned long long* tile_state, uint32_t*
     const bool hit = (face != RPX_NO_FACE);
     uint32_t total;
     const uint32_t local = block_exclusive_scan(hit ? 1u : 0u, &total, s_warp);
-    if (threadIdx.x == 0) tile_publish(tile_state, tile, total);
+    // grouped look-back (one round trip): the per-tile work is a single plane test, so thousands of tiles
+    // run in lock step and the flat walk would be the whole kernel (state = rpx_state_words(n_tiles) words)
+    unsigned long long* gagg = tile_state + n_tiles;
+    unsigned long long* gpre = gagg + (n_tiles + 31) / 32;
+    if (threadIdx.x == 0) tile_publish_grouped(tile_state, gagg, tile, total);
     if (threadIdx.x < 32) {
-        unsigned long long excl = tile_lookback(tile_state, tile, total);
+        unsigned long long excl = tile_lookback_grouped(tile_state, gagg, gpre, tile, total);
         if (threadIdx.x == 0) {
             s_prefix = excl;
             if (tile == n_tiles - 1) *d_next = *d_base + excl + total;

@@ -67,9 +67,63 @@ def globalize_generation(arr, g, offsets):
     return arr
 
 
+def gather_records(local, n_local, itemsize, dst=None, group=None):
+    """Gather variable-length runs of packed records that already live in torch tensors ON THE
+    COLLECTIVE'S DEVICE (CUDA tensors under NCCL: the transfer is GPU to GPU over NVLink / NVSwitch with
+    no host bounce; CPU tensors under gloo in the tests).  ``local``: uint8 tensor holding this rank's
+    ``n_local`` records of ``itemsize`` bytes.  Returns ``(records, counts)``: the ranks' records
+    concatenated in rank order as one uint8 tensor on the same device -- on every rank when ``dst`` is
+    None (all-gather), else on rank ``dst`` only (None elsewhere) -- and the per-rank record counts."""
+    import torch
+    dist = _dist()
+    world, rank = dist.get_world_size(group), dist.get_rank(group)
+    dev = local.device
+    cnt = torch.tensor([int(n_local)], dtype=torch.int64, device=dev)
+    all_cnt = [torch.zeros_like(cnt) for _ in range(world)]
+    dist.all_gather(all_cnt, cnt, group=group)
+    counts = [int(c.item()) for c in all_cnt]
+    nmax = max(counts) if counts else 0
+    pad = torch.zeros(max(nmax * itemsize, 1), dtype=torch.uint8, device=dev)
+    pad[:int(n_local) * itemsize] = local[:int(n_local) * itemsize]
+    if dst is None:
+        parts = [torch.empty_like(pad) for _ in range(world)]
+        dist.all_gather(parts, pad, group=group)
+    elif rank == dst:
+        parts = [torch.empty_like(pad) for _ in range(world)]
+        dist.gather(pad, parts, dst=dst, group=group)
+    else:
+        dist.gather(pad, None, dst=dst, group=group)
+        return None, counts
+    out = torch.cat([p[:c * itemsize] for p, c in zip(parts, counts)]) if sum(counts) else pad[:0]
+    return out, counts
+
+
+def gather_terminal(engine, dev_rays, dst=None, group=None):
+    """The end-of-trace gather of SURVEY 8e, device resident: this rank's terminal rays (a DeviceRays, e.g.
+    from ``Engine.select_terminal`` or ``trace_consume(..., terminal=True)``) are written as packed
+    ray_t / gausslet_t records into a CUDA tensor (``rpx_rays_export_device``), gathered with NCCL, and
+    the concatenation is handed back to the library as a device collection (``rpx_rays_import_device``).
+    Returns ``(DeviceRays or None, counts per rank)``.  ``parent_idx`` keeps each rank's numbering."""
+    import torch
+    from . import _abi as A
+    dev = torch.device("cuda", engine.device)
+    itemsize = A.gausslet_dtype.itemsize if dev_rays.is_gausslet else A.ray_dtype.itemsize
+    n = len(dev_rays)
+    send = torch.empty(max(n * itemsize, 4), dtype=torch.uint8, device=dev)
+    engine.export_device(dev_rays, send.data_ptr(), n)  # returns after the copy finished on the library's stream
+    out, counts = gather_records(send, n, itemsize, dst=dst, group=group)
+    if out is None:
+        return None, counts
+    torch.cuda.current_stream(dev).synchronize()  # the library imports on its own (non-blocking) stream
+    total = sum(counts)
+    return engine.import_device(out.data_ptr() if total else send.data_ptr(), total, dev_rays.is_gausslet), counts
+
+
 def gather_generation(arr, counts_g, dst=0, device=None, group=None):
-    """Gather one (globalized) generation to ``dst`` in rank order.  ``counts_g[r]`` is the
-    size of rank r's part.  Returns the concatenated array on ``dst`` and None elsewhere."""
+    """Gather one (globalized) generation to ``dst`` in rank order, HOST arrays in and out (the
+    reference-facing convenience for small traces; large traces gather terminal rays on the device with
+    ``gather_terminal``).  ``counts_g[r]`` is the size of rank r's part.  Returns the concatenated array
+    on ``dst`` and None elsewhere."""
     import torch
     dist = _dist()
     world, rank = dist.get_world_size(group), dist.get_rank(group)
@@ -141,6 +195,9 @@ def field_sharded(engine, gausslets_shard, wavelengths, points, blending=1.0, ti
     dev = torch.device("cuda", engine.device)
     pts = torch.from_numpy(np.ascontiguousarray(points, dtype=np.double).reshape(-1, 3)).to(dev)
     out = torch.zeros((pts.shape[0], 6), dtype=torch.float64, device=dev)
+    # the zero fill and the points upload run on torch's stream; the library accumulates on its own
+    # non-blocking stream (rpx_stream): order the two before handing the pointers over
+    torch.cuda.current_stream(dev).synchronize()
     if len(gausslets_shard):
         fm = engine.field_prepare(gausslets_shard, wavelengths, blending=blending)
         try:
@@ -149,3 +206,26 @@ def field_sharded(engine, gausslets_shard, wavelengths, points, blending=1.0, ti
             fm.free()
     allreduce_field(out, group=group)
     return out.cpu().numpy().view(np.complex128).reshape(-1, 3)
+
+
+class _DeviceBuffer(object):
+    """Zero-copy view of library-owned device memory for torch (``__cuda_array_interface__`` v3)."""
+
+    def __init__(self, ptr, n_doubles):
+        self.__cuda_array_interface__ = {"shape": (int(n_doubles),), "typestr": "<f8", "data": (int(ptr), False),
+                                         "version": 3, "strides": None}
+
+
+def allreduce_detector(engine, detector, group=None):
+    """Sum the partial detector fields of the ranks IN PLACE in the library's own device buffer: one NCCL
+    all-reduce of npt x 6 doubles over NVLink, no copy and no host round trip ("probe/detector
+    results at the end of a trace").  The detector's summation kernels run on the library's stream; they
+    are waited for first (``Detector.ms`` synchronises on their events)."""
+    import torch
+    dist = _dist()
+    _ = detector.ms  # waits for every accumulate enqueued so far
+    dev = torch.device("cuda", engine.device)
+    t = torch.as_tensor(_DeviceBuffer(detector.field_device_ptr, max(detector.npt, 1) * 6), device=dev)
+    dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)
+    torch.cuda.current_stream(dev).synchronize()  # the library reads the buffer on its own stream next
+    return t

@@ -144,6 +144,99 @@ class FieldModes(object):
             pass
 
 
+class Detector(object):
+    """A fixed set of points with an accumulating complex E-field on the device (``rpx_detector``):
+    gausslet collections are summed into it one after the other (EFieldSummation, fields.py:206-249)."""
+
+    def __init__(self, engine, points, wavelengths, blending=1.0, time_ps=0.0):
+        self._e = engine
+        pts = np.ascontiguousarray(points, dtype=np.double).reshape(-1, 3)
+        wl = np.ascontiguousarray(wavelengths, dtype=np.double).reshape(-1)
+        h = C.c_void_p()
+        engine._check(engine._L.rpx_detector_create(engine._ctx, pts.ctypes.data, pts.shape[0], wl.ctypes.data,
+                                                    wl.shape[0], float(blending), float(time_ps), C.byref(h)))
+        self._h = h
+        self.npt = pts.shape[0]
+
+    def reset(self):
+        self._e._check(self._e._L.rpx_detector_reset(self._e._ctx, self._h))
+
+    def accumulate(self, dev_rays):
+        handle = dev_rays._h if isinstance(dev_rays, DeviceRays) else dev_rays
+        self._e._check(self._e._L.rpx_detector_accumulate(self._e._ctx, self._h, handle))
+
+    def read(self):
+        """The accumulated field, (npt, 3) complex128."""
+        out = np.zeros((self.npt, 3), dtype=np.complex128)
+        self._e._check(self._e._L.rpx_detector_read(self._e._ctx, self._h, out.ctypes.data))
+        return out
+
+    @property
+    def field_device_ptr(self):
+        """Device address of the npt x 6 doubles (for an in-place NCCL all-reduce)."""
+        return int(self._e._L.rpx_detector_field_device(self._h))
+
+    @property
+    def modes(self):
+        return int(self._e._L.rpx_detector_modes(self._h))
+
+    @property
+    def ms(self):
+        return float(self._e._L.rpx_detector_ms(self._e._ctx, self._h))
+
+    def free(self):
+        if self._h is not None:
+            self._e._L.rpx_detector_free(self._e._ctx, self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+
+class ConsumeResult(object):
+    """What a streamed trace with device-side consumers leaves behind (``rpx_consume_result``)."""
+
+    def __init__(self, engine, r, face_counts, is_gausslet, per_chunk_terminal, per_chunk_captured):
+        self.counts = [int(r.counts[g]) for g in range(r.n_gens)]
+        self.n_chunks = int(r.n_chunks)
+        self.n_terminal, self.n_captured = int(r.n_terminal), int(r.n_captured)
+        self.terminal = DeviceRays(engine, C.c_void_p(r.terminal), is_gausslet) if r.terminal else None
+        self.captured = DeviceRays(engine, C.c_void_p(r.captured), is_gausslet) if r.captured else None
+        self.device_ms, self.trace_ms = float(r.device_ms), float(r.trace_ms)
+        self.kernel_ms = {"intersect": (float(r.intersect_ms), int(r.intersect_launches)),
+                          "shade": (float(r.shade_ms), int(r.shade_launches))}
+        self.launches = int(r.launches)
+        self.face_counts = face_counts
+        self.per_chunk_terminal = per_chunk_terminal
+        self.per_chunk_captured = per_chunk_captured
+
+    @property
+    def segments(self):
+        return int(sum(self.counts))
+
+    @staticmethod
+    def reference_order(arr, per_chunk):
+        """Kept records come in (chunk, generation, ray) order; the reference's consumers
+        (select_ray_intersections, ctracer.pyx:1999-2010) produce (generation, ray) order."""
+        n_chunks, n_g = per_chunk.shape
+        starts = np.concatenate([[0], np.cumsum(per_chunk.reshape(-1))]).astype(np.int64)
+        pieces = []
+        for g in range(n_g):
+            for c in range(n_chunks):
+                k = c * n_g + g
+                pieces.append(arr[starts[k]:starts[k + 1]])
+        return np.concatenate(pieces) if pieces else arr[:0]
+
+    def free(self):
+        for d in (self.terminal, self.captured):
+            if d is not None:
+                d.free()
+        self.terminal = self.captured = None
+
+
 class Engine(object):
     def __init__(self, device=0):
         self._L = load()
@@ -207,6 +300,83 @@ class Engine(object):
         finally:
             dev.free()
         return out, reduced, [int(c) for c in counts]
+
+    # -- terminal rays / device-resident AoS -----------------------------------------
+    def select_terminal(self, handles, is_gausslet, unterminated=True, faces=None):
+        """``rpx_select_terminal`` over device-resident collections -> (DeviceRays, per-collection counts).
+        ``faces``: indices of the faces whose hits count as terminal (absorbers, detectors)."""
+        n = len(handles)
+        arr = (C.c_void_p * n)(*handles)
+        sel = None
+        if faces is not None:
+            sel = np.zeros(max(self.n_traced_faces, 1), dtype=np.uint8)
+            sel[np.asarray(list(faces), dtype=np.int64)] = 1
+        counts = np.zeros(n, dtype=np.uint64)
+        h = C.c_void_p()
+        self._check(self._L.rpx_select_terminal(self._ctx, arr, n, 1 if unterminated else 0,
+                                                None if sel is None else sel.ctypes.data, C.byref(h), counts.ctypes.data))
+        return DeviceRays(self, h, is_gausslet), [int(c) for c in counts]
+
+    def export_device(self, dev_rays, d_ptr, capacity):
+        """Packed AoS records of a device collection into caller-owned DEVICE memory (e.g. a torch uint8
+        tensor's ``data_ptr()``): the send buffer of an NCCL gather."""
+        self._check(self._L.rpx_rays_export_device(self._ctx, dev_rays._h, int(d_ptr), int(capacity)))
+
+    def import_device(self, d_ptr, n, is_gausslet):
+        h = C.c_void_p()
+        self._check(self._L.rpx_rays_import_device(self._ctx, int(d_ptr), int(n), 1 if is_gausslet else 0, C.byref(h)))
+        return DeviceRays(self, h, is_gausslet)
+
+    def detector(self, points, wavelengths, blending=1.0, time_ps=0.0):
+        return Detector(self, points, wavelengths, blending, time_ps)
+
+    def trace_consume(self, rays, max_length, recursion_limit, n=None, is_gausslet=None, chunk_rays=0, terminal=False,
+                      terminal_faces=None, terminal_capacity=0, capture=False, captured_capacity=0, detector=None,
+                      per_chunk=False):
+        """``rpx_trace_consume``: chunked trace whose generations stay on the device and are handed to the
+        consumers (terminal-ray selection, capture plane, detector field).  ``rays``: a host array, or an
+        integer DEVICE address of packed AoS records (then ``n`` and ``is_gausslet`` are required)."""
+        flags = 0
+        if isinstance(rays, np.ndarray):
+            rays = np.ascontiguousarray(rays)
+            is_g = self._is_gausslet(rays)
+            ptr, n = rays.ctypes.data, rays.shape[0]
+        else:
+            ptr, is_g = int(rays), 1 if is_gausslet else 0
+            flags |= A.CONSUME_SOURCE_ON_DEVICE
+        if terminal:
+            flags |= A.CONSUME_TERMINAL
+        if capture:
+            flags |= A.CONSUME_CAPTURE
+        if detector is not None:
+            flags |= A.CONSUME_FIELD | A.CONSUME_CAPTURE
+        o = A.rpx_consume_opts()
+        o.chunk_rays = int(chunk_rays)
+        o.flags = flags
+        sel = None
+        if terminal_faces is not None:
+            sel = np.zeros(max(self.n_traced_faces, 1), dtype=np.uint8)
+            sel[np.asarray(list(terminal_faces), dtype=np.int64)] = 1
+            o.terminal_faces = sel.ctypes.data
+        o.terminal_capacity = int(terminal_capacity)
+        o.captured_capacity = int(captured_capacity)
+        o.detector = detector._h if detector is not None else None
+        pct = pcc = None
+        if per_chunk:
+            default_chunk = (1 << 20) if is_g else (1 << 22)
+            n_chunks = max(1, -(-int(n) // int(chunk_rays or default_chunk)))
+            o.max_gens = A.CONSUME_MAX_GENS
+            pct = np.zeros((n_chunks, A.CONSUME_MAX_GENS), dtype=np.uint64)
+            pcc = np.zeros((n_chunks, A.CONSUME_MAX_GENS), dtype=np.uint64)
+            o.per_chunk_terminal = pct.ctypes.data
+            o.per_chunk_captured = pcc.ctypes.data
+        r = A.rpx_consume_result()
+        fc = np.zeros(max(self.n_traced_faces, 1), dtype=np.uint32)
+        self._check(self._L.rpx_trace_consume(self._ctx, ptr, int(n), is_g, float(max_length), int(recursion_limit),
+                                              C.byref(o), fc.ctypes.data, C.byref(r)))
+        ng = int(r.n_gens)
+        return ConsumeResult(self, r, fc[:self.n_traced_faces].copy(), is_g,
+                             None if pct is None else pct[:, :ng].copy(), None if pcc is None else pcc[:, :ng].copy())
 
     # -- E-field summation --------------------------------------------------------------------
     def field_prepare(self, rays, wavelengths, modes=None, blending=1.0):
@@ -368,6 +538,18 @@ class Engine(object):
                                                float(max_length), int(recursion_limit), seq.ctypes.data,
                                                int(seq.shape[0]), C.byref(h)))
         return TraceResult(self, h, is_g)
+
+    def trace_step(self, dev_rays, max_length, face_counts=None):
+        """``rpx_trace_step``: one generation.  ``dev_rays`` is written back in place and stays the
+        caller's; returns the (un-intersected) children as a new DeviceRays.  ``face_counts`` (uint32
+        array of n_traced_faces) is added to."""
+        h = C.c_void_p()
+        fc = None
+        if face_counts is not None:
+            assert face_counts.dtype == np.uint32 and face_counts.shape[0] >= self.n_traced_faces
+            fc = face_counts.ctypes.data
+        self._check(self._L.rpx_trace_step(self._ctx, dev_rays._h, float(max_length), C.byref(h), fc))
+        return DeviceRays(self, h, dev_rays.is_gausslet)
 
     def trace_device(self, dev_rays, max_length, recursion_limit, flags=A.TRACE_DEFAULT):
         """Inputs already resident (``rpx_trace_device``); consumes ``dev_rays``."""

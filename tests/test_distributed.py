@@ -110,3 +110,51 @@ def test_two_rank_field_sum_equals_single_process():
         assert p.exitcode == 0
     want = z['E']
     assert np.abs(got - want).max() / np.abs(want).max() < 1e-13  # only the summation order differs
+
+
+def _records_worker(rank, world, port, q):
+    sys.path.insert(0, ROOT)
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    import torch
+    import torch.distributed as dist
+    from raypier_optics_b200 import _abi as A, distributed as rd
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    # rank r holds 3 + 5 r "terminal rays" with a recognisable ident; rank 1 of the ragged case holds none
+    for ragged in (False, True):
+        n = 0 if (ragged and rank == 1) else 3 + 5 * rank
+        rec = np.zeros(n, dtype=A.ray_dtype)
+        rec['ray_ident'] = 1000 * rank + np.arange(n)
+        rec['length'] = rank + 0.5
+        local = torch.from_numpy(rec.view(np.uint8).reshape(-1).copy()) if n else torch.zeros(4, dtype=torch.uint8)
+        everywhere, counts = rd.gather_records(local, n, A.ray_dtype.itemsize, dst=None)
+        on0, counts0 = rd.gather_records(local, n, A.ray_dtype.itemsize, dst=0)
+        assert counts == counts0
+        assert (on0 is None) == (rank != 0)
+        if rank == 0:
+            assert torch.equal(on0, everywhere)
+            q.put((ragged, counts, everywhere.numpy().tobytes()))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_two_rank_gather_of_terminal_records():
+    """distributed.gather_records (the collective behind gather_terminal): variable-length runs of
+    packed ray records concatenated in rank order, an empty rank included."""
+    import torch.multiprocessing as mp
+    from raypier_optics_b200 import _abi as A
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_records_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    results = [q.get(timeout=300) for _ in range(2)]
+    for p in procs:
+        p.join(timeout=120)
+        assert p.exitcode == 0
+    for ragged, counts, raw in results:
+        rec = np.frombuffer(raw, dtype=A.ray_dtype)
+        assert counts == ([3, 0] if ragged else [3, 8])
+        want_ident = list(range(3)) + ([] if ragged else [1000 + i for i in range(8)])
+        assert rec['ray_ident'].tolist() == want_ident
+        assert rec['length'].tolist() == [0.5] * 3 + ([] if ragged else [1.5] * 8)
