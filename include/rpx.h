@@ -108,7 +108,7 @@ typedef enum rpx_face_type {
     RPX_FACE_DISTORTION = 19,      /* :2323 p: accuracy ; base_face, aux = distortion idx ; shape   */
     RPX_FACE_EXTRUDED_BEZIER = 20, /* :795  p: z_height_1, z_height_2, mincorner[2], maxcorner[2];
                                               aux = cubic Bezier segments [n][4][2] (pool)          */
-    RPX_FACE_MESH = 21             /* obbtree.pyx:880-946 OBBTreeFace over an OBBTree (:200-400): a
+    RPX_FACE_MESH = 21,            /* obbtree.pyx:880-946 OBBTreeFace over an OBBTree (:200-400): a
                                       triangle mesh.  p: tree tolerance (OBBTree.tolerance, 0.1);
                                       aux_off = mesh block in pool, aux_n = cells, aux_m = BVH nodes.
                                       Block (doubles): header[8] = n_points, n_cells, n_nodes,
@@ -120,6 +120,16 @@ typedef enum rpx_face_type {
                                       node or (-(first tri) - 1, count) for a leaf.  The reference's OBB
                                       tree is an acceleration structure (its node test only prunes); this
                                       library carries its own BVH, built by the host side.             */
+    RPX_FACE_UVPATCH = 22          /* cbezier.pyx:391-550 UVPatchFace over a BezierPatch (:200-286) or BSplinePatch
+                                      (:290-388).  p: atol, invert_normals, patch kind (0 Bezier, 1 B-spline),
+                                      N, M (orders: (N+1) x (M+1) control points), u_degree, v_degree, offset of
+                                      the patch block in the pool, number of u knots, number of v knots.
+                                      aux_off / aux_n / aux_m = mesh block of the patch's (u_res x v_res)
+                                      tessellation (get_mesh, :153-197) exactly as for RPX_FACE_MESH.  Patch block
+                                      (doubles): uvs[n_points][2] (the vertex (u, v) of the tessellation),
+                                      ctrl[N+1][M+1][3], then binom_n[N+1], binom_m[M+1] (Bezier) or
+                                      u_knots[], v_knots[] (B-spline).  The nearest facet seeds a Newton
+                                      iteration on the patch itself (<= 100 steps, |du|, |dv| < atol).         */
 } rpx_face_type;
 
 #define RPX_FACE_NPARAM 16

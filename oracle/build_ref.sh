@@ -31,7 +31,7 @@ CC=${RPX_REF_CC:-/usr/bin/gcc}
 PYINC=$($PY -c "import sysconfig; print(sysconfig.get_paths()['include'])")
 NPINC=$($PY -c "import numpy; print(numpy.get_include())")
 EXT=$($PY -c "import sysconfig; print(sysconfig.get_config_var('EXT_SUFFIX'))")
-MODS="ctracer cfaces cmaterials cshapes cdistortions cimplicit_surfs cfields obbtree"
+MODS="ctracer cfaces cmaterials cshapes cdistortions cimplicit_surfs cfields obbtree cbezier"
 mkdir -p "$OUT/build"
 # 1. cythonize (once; shared by both flavours)
 for m in $MODS; do

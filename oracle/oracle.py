@@ -111,9 +111,17 @@ class OracleScene:
         return C.cast(C.pointer(self.scene.c_scene), C.c_void_p)
 
 
-def trace_rays(scene, input_rays, recursion_limit=100, max_length=100.0):
+def trace_rays(scene, input_rays, recursion_limit=100, max_length=100.0, decomp=None):
     """The generation loop of raypier.core.tracer.trace_rays (core/tracer.py:9-47) on
-    numpy arrays.  Returns (list of generation arrays, face_counts)."""
+    numpy arrays.  Returns (list of generation arrays, face_counts).
+
+    ``decomp``: {face index: callable(gausslet array) -> gausslet array} for faces that carry a
+    ResampleGaussletMaterial (cmaterials.pyx:1766-1831; the C oracle treats the face as an absorber, which
+    is all eval_child_ray_c does to the ray itself).  After the ray loop of a generation, for each such
+    face that was hit (ctracer.pyx:2274-2278): the gausslets captured by it -- copies taken when they hit,
+    base ray written back, parabasal lengths still max_length -- go through the callable, the result is
+    appended to the new generation, the face's count is zeroed; then every length of the new generation
+    is reset to max_length (:2280)."""
     osc = scene if isinstance(scene, OracleScene) else OracleScene(scene)
     rays = np.ascontiguousarray(input_rays).copy()
     is_g = rays.dtype == A.gausslet_dtype
@@ -128,7 +136,24 @@ def trace_rays(scene, input_rays, recursion_limit=100, max_length=100.0):
     count = 0
     while rays.shape[0] > 0 and count < recursion_limit:
         traced.append(rays)
+        before = counts.copy()
+        parents = rays
         rays = trace_generation(osc, rays, max_length, counts)
+        if decomp and is_g:
+            extra = []
+            ef = parents['base_ray']['end_face_idx']
+            for j in sorted(decomp):
+                if counts[j] == before[j]:
+                    continue
+                sel = (ef == j) & ((parents['base_ray']['ray_type_id'] & A.GAUSSLET) != 0)
+                cap = parents[sel].copy()
+                cap['para_rays']['length'] = max_length
+                extra.append(np.ascontiguousarray(decomp[j](cap)).view(A.gausslet_dtype))
+                counts[j] = 0
+            if extra:
+                rays = np.concatenate([rays] + extra)
+                rays['base_ray']['length'] = max_length
+                rays['para_rays']['length'] = max_length
         count += 1
     return traced, counts[:scene.c_scene.n_traced_faces]
 
@@ -477,6 +502,14 @@ def import_reference(flavour="parity"):
             importlib.import_module("raypier.core." + name)
         try:  # triangle-mesh faces (needs PIL at import time: obbtree.pyx:6); optional
             importlib.import_module("raypier.core.obbtree")
+            # UV patch faces.  cbezier.pyx:16 does `from numpy import math`, an alias numpy >= 2 (the only
+            # numpy in this image) no longer has.  The reference SOURCE is built unmodified; the missing
+            # alias is supplied at run time, in this process only, before the module is imported:
+            import math
+            import numpy
+            if not hasattr(numpy, "math"):
+                numpy.math = math
+            importlib.import_module("raypier.core.cbezier")
         except Exception:
             pass
         return core

@@ -528,6 +528,8 @@ static int bz_pnt_in_hull(flat2 p, flat2 A, flat2 B, flat2 C, flat2 D) { /* cfac
  * s_piece = piece of the last face_intersect call, s_hit_piece = piece of the accepted hit.
  * Thread-local: the full-size parity tests run independent shards of one trace on several host threads. */
 static __thread int s_piece = 0, s_hit_piece = 0;
+/* intersect_t.uv (ctracer.pxd:74-81) travels the same way for UVPatchFace (cbezier.pyx:514-516, 538-539) */
+static __thread double s_u = 0, s_v = 0, s_hit_u = 0, s_hit_v = 0;
 
 /* Mesh block in the pool (scene.py::_mesh_block): header of 8 doubles, then the raw points / cells
  * (what the reference object holds) and, for the CUDA path only, BVH-ordered triangle records and
@@ -556,7 +558,13 @@ static double mesh_line_intersects_cell(const double* points, const double* cell
  * tree only prunes (line_intersects_node_c, :271-296, is a conservative interval test with a positive
  * margin), so the result is the nearest cell with tol <= alpha < 1 over ALL cells; on exactly equal
  * alpha the reference keeps the cell its traversal meets first, this loop the lowest cell index.  */
+static double mesh_nearest(const rpx_scene* S, const rpx_face* f, vec3 p1, vec3 p2, int* piece);
 static double mesh_intersect(const rpx_scene* S, const rpx_face* f, vec3 p1, vec3 p2, int* piece) {
+    return mesh_nearest(S, f, p1, p2, piece) * mag(subvv(p2, p1));
+}
+
+/* OBBTree.intersect_with_line_c itself: alpha of the nearest cell, -1 if there is none */
+static double mesh_nearest(const rpx_scene* S, const rpx_face* f, vec3 p1, vec3 p2, int* piece) {
     const double* H = S->pool + f->aux_off;
     const long n_cells = (long)H[1];
     const double* points = H + (long)H[3];
@@ -574,7 +582,7 @@ static double mesh_intersect(const rpx_scene* S, const rpx_face* f, vec3 p1, vec
     }
     if (best_cell < 0) best = -1.0;
     *piece = (int)best_cell;
-    return best * mag(subvv(p2, p1));
+    return best;
 }
 
 /* OBBTreeFace.__cinit__ (:898-908) + compute_normal_c (:935-946): the flat normal of cell `piece` */
@@ -586,11 +594,195 @@ static vec3 mesh_normal(const rpx_scene* S, const rpx_face* f, int piece) {
     return norm(cross(subvv(p2, p1), subvv(p3, p1)));
 }
 
+/* ---- UV patch faces: raypier/core/cbezier.pyx -------------------------------------------------
+ * UVPatchFace (:391-550) over a BezierPatch (:200-286) or BSplinePatch (:290-388).  Face record:
+ * p[0] atol, p[1] invert_normals, p[2] patch kind (0 Bezier, 1 B-spline), p[3] N, p[4] M (orders:
+ * (N+1) x (M+1) control points), p[5] u_degree, p[6] v_degree, p[7] offset of the patch block in the
+ * pool, p[8] / p[9] number of u / v knots.  aux_off = mesh block of the (u_res x v_res) tessellation
+ * (get_mesh, :153-197), the same layout as RPX_FACE_MESH.  Patch block: uvs[n_points][2],
+ * ctrl[N+1][M+1][3], then binom_n[N+1], binom_m[M+1] (Bezier) or u_knots, v_knots (B-spline).     */
+typedef struct { vec3 p, dpdu, dpdv; } vec3x3;
+
+/* _N_basis, cbezier.pyx:47-70 */
+static double bs_basis(double t, int p, int idx, const double* knots) {
+    if (p == 0) return ((knots[idx] <= t) && (t < knots[idx + 1])) ? 1.0 : 0.0;
+    double out;
+    double denom = knots[idx + p] - knots[idx];
+    if (denom == 0.0) out = 0.0;
+    else out = ((t - knots[idx]) / denom) * bs_basis(t, p - 1, idx, knots);
+    denom = knots[idx + p + 1] - knots[idx + 1];
+    if (denom != 0.0) out += ((knots[idx + p + 1] - t) / denom) * bs_basis(t, p - 1, idx + 1, knots);
+    return out;
+}
+
+/* _N_basis_grad, cbezier.pyx:73-104 */
+typedef struct { double N, dNdt; } basis_val;
+static basis_val bs_basis_grad(double t, int p, int idx, const double* knots) {
+    basis_val out, prev;
+    if (p == 0) {
+        out.N = ((knots[idx] <= t) && (t < knots[idx + 1])) ? 1.0 : 0.0;
+        out.dNdt = 0.0;
+        return out;
+    }
+    double denom = knots[idx + p] - knots[idx], nom;
+    if (denom == 0.0) {
+        out.N = 0.0;
+        out.dNdt = 0.0;
+    } else {
+        prev = bs_basis_grad(t, p - 1, idx, knots);
+        nom = ((t - knots[idx]) / denom);
+        out.N = nom * prev.N;
+        out.dNdt = (1. / denom) * prev.N + nom * prev.dNdt;
+    }
+    denom = knots[idx + p + 1] - knots[idx + 1];
+    if (denom != 0.0) {
+        prev = bs_basis_grad(t, p - 1, idx + 1, knots);
+        nom = ((knots[idx + p + 1] - t) / denom);
+        out.N += nom * prev.N;
+        out.dNdt += (-1 / denom) * prev.N + nom * prev.dNdt;
+    }
+    return out;
+}
+
+typedef struct {
+    int kind, N, M, udeg, vdeg;
+    const double *uvs, *ctrl, *a, *b; /* a, b: binomials (Bezier) or knots (B-spline) */
+} uvpatch_t;
+
+static uvpatch_t uvpatch_of(const rpx_scene* S, const rpx_face* f) {
+    uvpatch_t P;
+    const double* H = S->pool + f->aux_off;
+    const long n_points = (long)H[0];
+    P.kind = (int)f->p[2];
+    P.N = (int)f->p[3];
+    P.M = (int)f->p[4];
+    P.udeg = (int)f->p[5];
+    P.vdeg = (int)f->p[6];
+    P.uvs = S->pool + (long)f->p[7];
+    P.ctrl = P.uvs + 2 * n_points;
+    P.a = P.ctrl + 3 * (P.N + 1) * (P.M + 1);
+    P.b = P.a + (P.kind == 0 ? P.N + 1 : (long)f->p[8]);
+    return P;
+}
+
+/* BezierPatch._eval_pt (:232-254) / BSplinePatch._eval_pt (:335-358) */
+static vec3 uvpatch_eval(const uvpatch_t* P, double u, double v) {
+    vec3 out = v3(0, 0, 0);
+    const int N = P->N, M = P->M;
+    for (int i = 0; i < N + 1; i++)
+        for (int j = 0; j < M + 1; j++) {
+            const double* c = P->ctrl + 3 * (i * (M + 1) + j);
+            if (P->kind == 0) {
+                double coef = P->a[i] * pow(u, (double)i) * pow(1 - u, (double)(N - i)) * P->b[j] * pow(v, (double)j) *
+                              pow(1 - v, (double)(M - j));
+                out.x += coef * c[0];
+                out.y += coef * c[1];
+                out.z += coef * c[2];
+            } else {
+                double coef1 = bs_basis(u, P->udeg, i, P->a);
+                double coef2 = bs_basis(v, P->vdeg, j, P->b);
+                out.x += coef1 * coef2 * c[0];
+                out.y += coef1 * coef2 * c[1];
+                out.z += coef1 * coef2 * c[2];
+            }
+        }
+    return out;
+}
+
+/* BezierPatch._eval_pt_and_grads (:259-286) / BSplinePatch._eval_pt_and_grads (:363-388) */
+static vec3x3 uvpatch_eval_grads(const uvpatch_t* P, double u, double v) {
+    vec3x3 out;
+    out.p = out.dpdu = out.dpdv = v3(0, 0, 0);
+    const int N = P->N, M = P->M;
+    for (int i = 0; i < N + 1; i++)
+        for (int j = 0; j < M + 1; j++) {
+            const double* c = P->ctrl + 3 * (i * (M + 1) + j);
+            if (P->kind == 0) {
+                double u_term = P->a[i] * pow(u, (double)i) * pow(1 - u, (double)(N - i));
+                double v_term = P->b[j] * pow(v, (double)j) * pow(1 - v, (double)(M - j));
+                double coef = u_term * v_term;
+                out.p.x += coef * c[0];
+                out.p.y += coef * c[1];
+                out.p.z += coef * c[2];
+                coef = P->a[i] * (i - N * u) * pow(u, (double)(i - 1)) * pow(1 - u, (double)(N - 1 - i)) * v_term;
+                out.dpdu.x += coef * c[0];
+                out.dpdu.y += coef * c[1];
+                out.dpdu.z += coef * c[2];
+                coef = u_term * P->b[j] * (j - M * v) * pow(v, (double)(j - 1)) * pow(1 - v, (double)(M - 1 - j));
+                out.dpdv.x += coef * c[0];
+                out.dpdv.y += coef * c[1];
+                out.dpdv.z += coef * c[2];
+            } else {
+                basis_val uc = bs_basis_grad(u, P->udeg, i, P->a);
+                basis_val vc = bs_basis_grad(v, P->vdeg, j, P->b);
+                out.p.x += uc.N * vc.N * c[0];
+                out.p.y += uc.N * vc.N * c[1];
+                out.p.z += uc.N * vc.N * c[2];
+                out.dpdu.x += uc.dNdt * vc.N * c[0];
+                out.dpdu.y += uc.dNdt * vc.N * c[1];
+                out.dpdu.z += uc.dNdt * vc.N * c[2];
+                out.dpdv.x += vc.dNdt * uc.N * c[0];
+                out.dpdv.y += vc.dNdt * uc.N * c[1];
+                out.dpdv.z += vc.dNdt * uc.N * c[2];
+            }
+        }
+    return out;
+}
+
+/* UVPatchFace.intersect_c (:459-528) with interpolate_cell_c (:421-456) */
+static double uvpatch_intersect(const rpx_scene* S, const rpx_face* f, vec3 p1, vec3 p2) {
+    int cell_idx;
+    const double* H = S->pool + f->aux_off;
+    const double* points = H + (long)H[3];
+    const double* cells = H + (long)H[4];
+    double alpha = mesh_nearest(S, f, p1, p2, &cell_idx);
+    if (alpha < f->tolerance) return NO_HIT;
+    const uvpatch_t P = uvpatch_of(S, f);
+    const double tol = f->p[0] * f->p[0];
+    vec3 d = norm(subvv(p2, p1));
+    vec3 pt = addvv(multvs(p2, alpha), multvs(p1, 1.0 - alpha));
+    /* barycentric interpolation of the vertex uv's */
+    const double* c = cells + 3 * (long)cell_idx;
+    const long i0 = (long)c[0], i1 = (long)c[1], i2 = (long)c[2];
+    vec3 q1 = ld3(points + 3 * i0), q2 = ld3(points + 3 * i1), q3 = ld3(points + 3 * i2);
+    vec3 edge1 = subvv(q2, q1), edge2 = subvv(q3, q1);
+    vec3 en1 = norm(edge1);
+    vec3 en2 = norm(cross(en1, cross(edge1, edge2)));
+    double x2 = mag(edge1), x3 = dotprod(edge2, en1), y3 = dotprod(edge2, en2);
+    pt = subvv(pt, q1);
+    double px = dotprod(pt, en1), py = dotprod(pt, en2);
+    double alpha2 = (x2 * y3);
+    double alpha1 = py * x3 - px * y3;
+    double alpha0 = (alpha1 - py * x2 + x2 * y3) / alpha2;
+    alpha1 = -alpha1 / alpha2;
+    alpha2 = py / y3;
+    double u = alpha0 * P.uvs[2 * i0] + alpha1 * P.uvs[2 * i1] + alpha2 * P.uvs[2 * i2];
+    double v = alpha0 * P.uvs[2 * i0 + 1] + alpha1 * P.uvs[2 * i1 + 1] + alpha2 * P.uvs[2 * i2 + 1];
+    int i;
+    for (i = 0; i < 100; i++) {
+        vec3x3 g = uvpatch_eval_grads(&P, u, v);
+        vec3 normal = norm(cross(g.dpdu, g.dpdv));
+        double dist = dotprod(subvv(g.p, p1), normal) / dotprod(d, normal);
+        vec3 dp = subvv(addvv(p1, multvs(d, dist)), g.p);
+        double du = dotprod(g.dpdu, dp) / mag_sq(g.dpdu);
+        double dv = dotprod(g.dpdv, dp) / mag_sq(g.dpdv);
+        u += du;
+        v += dv;
+        if ((du * du < tol) && (dv * dv < tol)) break;
+    }
+    if (i == 100) return NO_HIT;
+    pt = uvpatch_eval(&P, u, v);
+    s_u = u;
+    s_v = v;
+    return mag(subvv(pt, p1));
+}
+
 /* Face.intersect_c for every concrete class: distance along p1->p2, or <= 0 / -1 */
 static double face_intersect(const rpx_scene* S, const rpx_face* f, vec3 p1, vec3 p2,
                              int is_base_ray) {
     s_piece = 0;
     if (f->type == RPX_FACE_MESH) return mesh_intersect(S, f, p1, p2, &s_piece);
+    if (f->type == RPX_FACE_UVPATCH) return uvpatch_intersect(S, f, p1, p2);
     const double* P = f->p;
     const double tol = f->tolerance;
     switch (f->type) {
@@ -1085,6 +1277,12 @@ static double face_intersect(const rpx_scene* S, const rpx_face* f, vec3 p1, vec
 static vec3 face_normal(const rpx_scene* S, const rpx_face* f, vec3 p) {
     const double* P = f->p;
     if (f->type == RPX_FACE_MESH) return mesh_normal(S, f, s_hit_piece);
+    if (f->type == RPX_FACE_UVPATCH) { /* compute_normal_and_tangent_c, cbezier.pyx:533-550 */
+        const uvpatch_t UP = uvpatch_of(S, f);
+        vec3x3 g = uvpatch_eval_grads(&UP, s_hit_u, s_hit_v);
+        vec3 n = norm(cross(g.dpdu, g.dpdv));
+        return (P[1] != 0.0) ? invert(n) : n;
+    }
     switch (f->type) {
         case RPX_FACE_CIRCULAR: return v3(0, 0, P[3] != 0.0 ? 1 : -1); /* :180-191 */
         case RPX_FACE_SHAPED_PLANAR: return v3(0, 0, 1);               /* :228-236 */
@@ -1265,7 +1463,11 @@ static vec3 face_normal(const rpx_scene* S, const rpx_face* f, vec3 p) {
 }
 
 /* Face.compute_tangent_c: default (1,0,0) ctracer.pyx:1786-1791 */
-static vec3 face_tangent(const rpx_face* f) {
+static vec3 face_tangent(const rpx_scene* S, const rpx_face* f) {
+    if (f->type == RPX_FACE_UVPATCH) { /* tangent = norm(dpdu), cbezier.pyx:550 */
+        const uvpatch_t UP = uvpatch_of(S, f);
+        return norm(uvpatch_eval_grads(&UP, s_hit_u, s_hit_v).dpdu);
+    }
     switch (f->type) {
         case RPX_FACE_EXTRUDED_PLANAR: return v3(0.0, 0.0, 1.0);    /* cfaces.pyx:704-709 */
         case RPX_FACE_ORIENTED_POLYGON: return ld3(f->p + 6);       /* :1186-1187 */
@@ -1279,7 +1481,7 @@ static orient_t compute_orientation(const rpx_scene* S, const rpx_face* f, vec3 
     orient_t out;
     point = transform_pt(&fs->inv_trans, point);
     out.normal = face_normal(S, f, point);
-    out.tangent = face_tangent(f);
+    out.tangent = face_tangent(S, f);
     if (f->invert_normal) {
         out.normal = invert(out.normal);
         out.tangent = invert(out.tangent);
@@ -1801,7 +2003,7 @@ static int nearest_hit(const rpx_scene* S, rpx_ray* ray, vec3 point) {
                 ray->length = dist;
                 ray->end_face_idx = (uint32_t)i;
                 nearest_idx = i;
-                s_hit_piece = s_piece;
+                s_hit_piece = s_piece, s_hit_u = s_u, s_hit_v = s_v;
             }
         }
     }
@@ -1818,7 +2020,7 @@ static int one_face_hit(const rpx_scene* S, rpx_ray* ray, vec3 point, int face_i
     if (f->tolerance < dist && dist < ray->length) {
         ray->length = dist;
         ray->end_face_idx = (uint32_t)face_idx;
-        s_hit_piece = s_piece;
+        s_hit_piece = s_piece, s_hit_u = s_u, s_hit_v = s_v;
         return face_idx;
     }
     return -1;
@@ -1901,7 +2103,7 @@ uint64_t rpxo_trace_gausslet_ex(const rpx_scene* S, rpx_gausslet* gs, uint64_t n
             double dist = face_intersect(S, face, p1, p2, 0);
             if (face->tolerance < dist && dist < pr->length) {
                 pr->length = dist;
-                s_hit_piece = s_piece; /* the parabasal ray's own piece (intersect_para_c returns its intersect_t) */
+                s_hit_piece = s_piece, s_hit_u = s_u, s_hit_v = s_v; /* the parabasal ray's own piece / uv (intersect_para_c returns its intersect_t) */
             } else {
                 ok = 0;
                 break;

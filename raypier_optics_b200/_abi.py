@@ -60,6 +60,7 @@ FACE_EXT_POLY = 18
 FACE_DISTORTION = 19
 FACE_EXTRUDED_BEZIER = 20
 FACE_MESH = 21
+FACE_UVPATCH = 22
 
 SHAPE_TRUE, SHAPE_CIRCLE, SHAPE_RECT, SHAPE_POLYGON, SHAPE_NOT, SHAPE_AND, SHAPE_OR, SHAPE_XOR = range(8)
 IMPL_NULL, IMPL_PLANE, IMPL_SPHERE, IMPL_CYLINDER, IMPL_NEG, IMPL_MIN, IMPL_MAX, IMPL_SUB = range(8)

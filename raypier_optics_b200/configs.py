@@ -465,6 +465,108 @@ def config4_prisms(core, n=100000, seed=4):
                 wavelengths=np.array([0.633]), max_length=300.0, recursion_limit=200)
 
 
+def resample_relaunch(arr, max_length=80.0):
+    """A deterministic stand-in for the decomposition callbacks of raypier/decompositions.py
+    (PositionDecompositionPlane.evaluate_decomposed_rays): every SECOND captured gausslet is re-launched
+    from the point where it met the plane, amplitudes halved, with a small deterministic tilt; pure numpy
+    on a gausslet_dtype array, so the same function serves the reference (wrapped in GaussletCollection),
+    the oracle and the CUDA path."""
+    g = np.ascontiguousarray(arr[::2]).copy()
+    b = g['base_ray']
+    end = b['origin'] + b['direction'] * b['length'][:, None]
+    shift = end - b['origin']
+    tilt = np.array([0.0, 0.0, 0.01])
+    d = b['direction'] + tilt[None, :]
+    d /= np.sqrt((d * d).sum(axis=1))[:, None]
+    g['base_ray']['origin'] = end
+    g['base_ray']['direction'] = d
+    g['base_ray']['accumulated_path'] = b['accumulated_path'] + b['length'] * b['refractive_index'].real
+    g['base_ray']['E1_amp'] = b['E1_amp'] * 0.5
+    g['base_ray']['E2_amp'] = b['E2_amp'] * 0.5
+    g['base_ray']['parent_idx'] = np.arange(len(g), dtype=np.uint32)
+    g['base_ray']['length'] = max_length
+    g['para_rays']['origin'] = g['para_rays']['origin'] + shift[:, None, :]
+    pd = g['para_rays']['direction'] + tilt[None, None, :]
+    pd /= np.sqrt((pd * pd).sum(axis=2))[:, :, None]
+    g['para_rays']['direction'] = pd
+    g['para_rays']['length'] = max_length
+    return g
+
+
+def config_resample(core, n=2000, seed=71):
+    """A decomposition plane in a beam path (raypier/decompositions.py: a CircularFace carrying a
+    ResampleGaussletMaterial): gausslets pass a beamsplitter plate; the transmitted arm meets the
+    decomposition plane (captured, handed to the callback, re-launched), then a curved mirror and a lens
+    face; the reflected arm meets a plane mirror.  The callback's output joins generation 2 AFTER the
+    regular children, and its rays are traced on like any others."""
+    F, M, S = core.cfaces, core.cmaterials, core.cshapes
+    plate = Pose(centre=(0., 0., 0.), direction=(1., 0., 1.), diameter=30.0, offset=0.0)
+    fl_plate = _facelist(core, plate, [F.CircularFace(owner=plate, diameter=30.0,
+                                                      material=M.PartiallyReflectiveMaterial(reflectivity=0.4))])
+    dec = Pose(centre=(0., 0., 20.), direction=(0., 0., -1.), diameter=25.0, offset=0.0)
+    mat = M.ResampleGaussletMaterial(eval_func=None)
+    fl_dec = _facelist(core, dec, [F.CircularFace(owner=dec, diameter=25.0, material=mat)])
+    shape = S.CircleShape(radius=12.0)
+    mir = Pose(centre=(0., 0., 45.), direction=(0., 0., -1.))
+    fl_mir = _facelist(core, mir, [F.ShapedSphericalFace(owner=mir, shape=shape, z_height=0.0, curvature=-400.0,
+                                                         material=M.PECMaterial())])
+    side = Pose(centre=(25., 0., 0.), direction=(-1., 0., 0.))
+    fl_side = _facelist(core, side, [F.ShapedPlanarFace(owner=side, shape=shape, z_height=0.0,
+                                                        material=M.PECMaterial())])
+    wl = np.array([1.0])
+    rays = disc_source(n, centre=(0., 0., -25.), axis=(0., 0., 1.), radius=3.0, seed=seed,
+                       E_vector=(0., 1., 0.), gaussian_sigma=4.0, ray_type_id=GAUSSLET)
+    rays['length'] = 80.0
+    gc = core.ctracer.GaussletCollection.from_rays(rays)
+    gc.config_parabasal_rays(wl, 0.4, 0.0)
+    return dict(name="config_resample", face_lists=[fl_plate, fl_dec, fl_mir, fl_side], rays=gc.copy_as_array(),
+                wavelengths=wl, max_length=80.0, recursion_limit=8, decomp_material=mat)
+
+
+def config_uvpatch(core, n=4000, seed=81, gausslets=False, u_res=14, v_res=12):
+    """UV patch faces (raypier/core/cbezier.pyx): a cubic-by-quadratic BezierPatch as a
+    free-form mirror and a quadratic B-spline patch as a second one, a tilted collimated source (so the
+    Newton iteration on the patch really iterates), and a plane absorber."""
+    B, F, M = core.cbezier, core.cfaces, core.cmaterials
+    import contextlib
+    import io
+    quiet = contextlib.redirect_stdout(io.StringIO())  # the reference's control_pts setter prints
+    bez = B.BezierPatch(3, 2)
+    xs, ys = np.linspace(-12., 12., 4), np.linspace(-10., 10., 3)
+    X, Y = np.meshgrid(xs, ys, indexing='ij')
+    Z = 0.012 * X * X - 0.02 * Y * Y + 0.4 * np.sin(X / 6.0) + 0.05 * X
+    with quiet:
+        bez.control_pts = np.ascontiguousarray(np.stack([X, Y, Z], axis=-1))
+    own1 = Pose(centre=(0., 0., 30.), direction=(0., 0.2, 1.), u_res=u_res, v_res=v_res)
+    f1 = B.UVPatchFace(owner=own1, patch=bez, u_res=u_res, v_res=v_res, material=M.PECMaterial())
+    bsp = B.BSplinePatch(4, 3)
+    xs, ys = np.linspace(-14., 14., 5), np.linspace(-12., 12., 4)
+    X, Y = np.meshgrid(xs, ys, indexing='ij')
+    Z = -0.01 * (X * X + Y * Y) + 0.3 * np.cos(Y / 5.0)
+    with quiet:
+        bsp.control_pts = np.ascontiguousarray(np.stack([X, Y, Z], axis=-1))
+    bsp.u_degree, bsp.v_degree = 2, 2
+    bsp.u_knots = np.array([0., 0., 0., 1. / 3, 2. / 3, 1., 1., 1.]) * 1.0000001  # open uniform; the last basis
+    bsp.v_knots = np.array([0., 0., 0., 0.5, 1., 1., 1.]) * 1.0000001             # function is 0 AT the end knot
+    own2 = Pose(centre=(0., -8., 2.), direction=(0., 0.35, 1.), u_res=u_res, v_res=v_res)
+    f2 = B.UVPatchFace(owner=own2, patch=bsp, u_res=u_res, v_res=v_res, invert_normals=1, material=M.PECMaterial())
+    stop = Pose(centre=(0., -20., 40.), direction=(0., 0.4, -1.), diameter=80.0, offset=0.0)
+    f3 = F.CircularFace(owner=stop, diameter=80.0, material=M.OpaqueMaterial())
+    fls = [_facelist(core, own1, [f1]), _facelist(core, own2, [f2]), _facelist(core, stop, [f3])]
+    wl = np.array([0.8])
+    rays = disc_source(n, centre=(0.5, -1., 0.), axis=(0.03, 0.05, 1.), radius=5.0, seed=seed, E_vector=(1., 0., 0.),
+                       E1=1.0, E2=0.2j, ray_type_id=GAUSSLET if gausslets else 0)
+    out = dict(name="config_uvpatch", face_lists=fls, wavelengths=wl, max_length=120.0, recursion_limit=6)
+    if gausslets:
+        rays['length'] = 120.0
+        gc = core.ctracer.GaussletCollection.from_rays(rays)
+        gc.config_parabasal_rays(wl, 0.3, 0.0)
+        out['rays'] = gc.copy_as_array()
+    else:
+        out['rays'] = rays
+    return out
+
+
 def config4_grating(core, n=100000, seed=44, n_wavelengths=260):
     """Config 4 (grating part): the diffraction-grating dispersion compensator
     (examples/grating_dispersion_compensator_example.py:19-50): RectangularGrating
@@ -683,6 +785,8 @@ CONFIGS = {
     "config5": config5_michelson,
     "big_scene": config_big_scene,
     "mesh": config_mesh,
+    "resample": config_resample,
+    "uvpatch": config_uvpatch,
 }
 
 

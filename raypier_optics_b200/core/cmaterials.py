@@ -266,12 +266,31 @@ class RectangularApertureMaterial(InterfaceMaterial):
 
 
 class ResampleGaussletMaterial(InterfaceMaterial):
-    """cmaterials.pyx:1766-1831 -- calls a Python function between generations; it is
-    not traced on the device (trace_rays raises UnsupportedSceneError for it)."""
+    """cmaterials.pyx:1766-1831 -- a pseudo-material: gausslets that reach it are captured and, once the
+    generation is complete, handed to ``eval_func`` (a callable taking a GaussletCollection and returning
+    the new outgoing GaussletCollection), whose result is appended to the new generation
+    (ctracer.pyx:2274-2278).  On the device the face absorbs; the capture, the callback and the append
+    are done by the host between generations (core/tracer.py)."""
 
     def __init__(self, **kwds):
         InterfaceMaterial.__init__(self)
-        self.eval_func = kwds.get("eval_func", None)
+        from .ctracer import GaussletCollection
+        self.capture_count = 0
+        self.captured_rays = GaussletCollection(kwds.get("size", 2))
+        self._evaluation_func = None
+        func = kwds.get("eval_func", None)
+        if func is not None:
+            self.eval_func = func
+
+    @property
+    def eval_func(self):
+        return self._evaluation_func
+
+    @eval_func.setter
+    def eval_func(self, obj):
+        if not callable(obj):
+            raise ValueError("The eval_func property must be a callable.")
+        self._evaluation_func = obj
 
     def is_decomp_material(self):
         return True

@@ -27,12 +27,6 @@ def _prepare_faces(input_rays, face_lists, max_length):
         f.update()
         f.material.wavelengths = wavelengths
         f.max_length = max_length
-    for f in all_faces:
-        if f.material.is_decomp_material():
-            from ..scene import UnsupportedSceneError
-            raise UnsupportedSceneError(
-                "%s calls back into Python between generations; it is not traced on the device"
-                % type(f.material).__name__)
     for fs in face_lists:
         fs.sync_transforms()
     return wavelengths, face_lists, all_faces
@@ -89,6 +83,78 @@ def _wrap_generations(input_rays, arrays, wavelengths):
     return out
 
 
+def _ref_array_for(cls):
+    """numpy dtype bridge for genuine reference collections (their from_array checks their own dtype)."""
+    if getattr(cls, "_dtype", None) is not None:
+        return lambda arr: arr
+    mod = __import__(cls.__module__, fromlist=["ray_dtype"])
+
+    def conv(arr):
+        ref_dtype = mod.gausslet_dtype if arr.dtype.itemsize == A.gausslet_dtype.itemsize else mod.ray_dtype
+        a = np.empty(arr.shape[0], dtype=ref_dtype)
+        a.view(np.uint8)[:] = np.ascontiguousarray(arr).view(np.uint8)
+        return a
+    return conv
+
+
+def _trace_with_decomposition(eng, input_rays, native, all_faces, wavelengths, recursion_limit, max_length):
+    """The generation loop of trace_rays (core/tracer.py:39-45) when a face carries a decomposition
+    material (ResampleGaussletMaterial, cmaterials.pyx:1766-1831): one device step per generation
+    (``rpx_trace_step``), and between two steps what trace_gausslet_c does after its ray loop
+    (ctracer.pyx:2274-2280): for every decomposition face that was hit, hand the gausslets it captured
+    -- copies of the parents taken when they hit, i.e. with the base ray's length / end_face_idx written
+    back and the parabasal lengths still at max_length -- to the material's Python callback, append what
+    it returns to the new generation AFTER the regular children, zero that face's count, and reset every
+    length of the new generation to max_length.  Only generations in which a decomposition face was hit
+    make the round trip through the host."""
+    cls = type(input_rays)
+    to_ref = _ref_array_for(cls)
+    n_faces = len(all_faces)
+    decomp = [j for j, f in enumerate(all_faces) if f.material.is_decomp_material()]
+    fc = np.zeros(max(n_faces, 1), dtype=np.uint32)
+    arrays = []
+    cur = eng.upload(native)
+    count = 0
+    try:
+        while len(cur) > 0 and count < recursion_limit:
+            fc_gen = np.zeros_like(fc)
+            children = eng.trace_step(cur, max_length, fc_gen)
+            arr = eng.download(cur)
+            cur.free()
+            cur = children
+            arrays.append(arr)
+            fc += fc_gen
+            extra = []
+            for j in decomp:
+                if not fc_gen[j]:
+                    continue
+                mat = all_faces[j].material
+                base = arr['base_ray']
+                sel = (base['end_face_idx'] == j) & ((base['ray_type_id'] & A.GAUSSLET) != 0)
+                cap = arr[sel].copy()
+                cap['para_rays']['length'] = max_length  # captured before trace_parabasal_rays wrote them
+                mat.captured_rays.clear_ray_list()
+                mat.captured_rays.extend(cls.from_array(to_ref(cap)))
+                mat.captured_rays.wavelengths = wavelengths
+                mat.capture_count += int(sel.sum())
+                out = mat.eval_func(mat.captured_rays)
+                mat.captured_rays.clear_ray_list()
+                new = np.ascontiguousarray(out.copy_as_array()).view(A.gausslet_dtype).copy()
+                extra.append(new)
+                fc[j] = 0  # `face.count = 0` (ctracer.pyx:2277)
+            if extra:
+                kids = eng.download(cur)
+                cur.free()
+                allk = np.concatenate([kids] + extra)
+                allk['base_ray']['length'] = max_length  # new_gausslets.reset_length_c (:2280)
+                allk['para_rays']['length'] = max_length
+                cur = eng.upload(allk)
+            count += 1
+    finally:
+        cur.free()
+    return arrays, fc[:n_faces]
+
+
 def trace_rays(input_rays, face_lists, recursion_limit=100, max_length=100.0, device=0):
     """Core ray-tracing routine: traces a RayCollection or GaussletCollection
     non-sequentially through the given list of FaceList objects.
@@ -104,6 +170,15 @@ def trace_rays(input_rays, face_lists, recursion_limit=100, max_length=100.0, de
     rays = input_rays.copy_as_array()
     native = np.ascontiguousarray(rays).view(
         A.gausslet_dtype if rays.dtype.itemsize == A.gausslet_dtype.itemsize else A.ray_dtype)
+    if native.dtype == A.gausslet_dtype and any(f.material.is_decomp_material() for f in all_faces):
+        # (plain rays never trigger a decomposition: eval_child_ray_c captures gausslets only and
+        # trace_segment_c has no callback step -- for them the face simply absorbs)
+        arrays, counts = _trace_with_decomposition(eng, input_rays, native, all_faces, wavelengths, recursion_limit,
+                                                   max_length)
+        for f, c in zip(all_faces, counts):
+            f.count = int(c)
+        trace_rays.last_device_ms = None
+        return _wrap_generations(input_rays, arrays, wavelengths), all_faces
     res = eng.trace(native, max_length, recursion_limit)
     try:
         arrays = res.generations()

@@ -164,7 +164,7 @@ static int validate_scene(rpx_ctx* ctx, const rpx_scene* s) {
         return fail(ctx, RPX_ERR_INVALID, "bad face counts");
     for (int i = 0; i < s->n_faces; i++) {
         const rpx_face& f = s->faces[i];
-        if (f.type < RPX_FACE_CIRCULAR || f.type > RPX_FACE_MESH)
+        if (f.type < RPX_FACE_CIRCULAR || f.type > RPX_FACE_UVPATCH)
             return fail(ctx, RPX_ERR_UNSUPPORTED, "face %d: unsupported face type %d", i, f.type);
         if (f.face_set < 0 || f.face_set >= s->n_face_sets)
             return fail(ctx, RPX_ERR_INVALID, "face %d: face_set %d out of range", i, f.face_set);
@@ -186,7 +186,7 @@ static int validate_scene(rpx_ctx* ctx, const rpx_scene* s) {
             return fail(ctx, RPX_ERR_INVALID, "face %d: polygon points out of range", i);
         if (f.type == RPX_FACE_EXT_POLY && (f.aux_off < 0 || f.aux_off + f.aux_n * f.aux_m > s->n_pool))
             return fail(ctx, RPX_ERR_INVALID, "face %d: coefficient table out of range", i);
-        if (f.type == RPX_FACE_MESH) {
+        if (f.type == RPX_FACE_MESH || f.type == RPX_FACE_UVPATCH) {
             if (f.aux_off < 0 || f.aux_n < 1 || f.aux_m < 1 || f.aux_off + 8 > s->n_pool)
                 return fail(ctx, RPX_ERR_INVALID, "face %d: mesh block out of range", i);
             const double* H = s->pool + f.aux_off;
@@ -219,6 +219,19 @@ static int validate_scene(rpx_ctx* ctx, const rpx_scene* s) {
                 if (height[0] > 60)
                     return fail(ctx, RPX_ERR_UNSUPPORTED, "face %d: BVH depth %d exceeds the device traversal stack (60)", i, height[0]);
             }
+        }
+        if (f.type == RPX_FACE_UVPATCH) {
+            const long long N = (long long)f.p[3], M = (long long)f.p[4], off = (long long)f.p[7];
+            const long long n_pts = (long long)s->pool[f.aux_off];
+            const long long na = (long long)f.p[8], nb = (long long)f.p[9];
+            const int kind = (int)f.p[2];
+            if (N < 0 || M < 0 || N > 64 || M > 64 || off < 0 || na < 0 || nb < 0 || (kind != 0 && kind != 1) ||
+                off + 2 * n_pts + 3 * (N + 1) * (M + 1) + na + nb > s->n_pool)
+                return fail(ctx, RPX_ERR_INVALID, "face %d: patch block out of range", i);
+            if (kind == 0 ? (na != N + 1 || nb != M + 1)
+                          : (f.p[5] < 0 || f.p[6] < 0 || f.p[5] > 8 || f.p[6] > 8 || na < N + (long long)f.p[5] + 2 ||
+                             nb < M + (long long)f.p[6] + 2))
+                return fail(ctx, RPX_ERR_INVALID, "face %d: patch tables inconsistent with its orders / degrees", i);
         }
         if (f.type == RPX_FACE_EXTRUDED_BEZIER && (f.aux_off < 0 || f.aux_n < 1 || f.aux_off + 8 * f.aux_n > s->n_pool))
             return fail(ctx, RPX_ERR_INVALID, "face %d: Bezier control points out of range", i);
@@ -319,6 +332,8 @@ static int upload_scene(rpx_ctx* ctx, const rpx_scene* s, DevScene* out, void** 
 }
 
 static int scene_face_class(const rpx_scene* s) {
+    for (int i = 0; i < s->n_faces; i++)
+        if (s->faces[i].type == RPX_FACE_MESH || s->faces[i].type == RPX_FACE_UVPATCH) return RPX_FC_MESH;
     for (int i = 0; i < s->n_faces; i++) {
         int t = s->faces[i].type;
         bool simple = t == RPX_FACE_CIRCULAR || t == RPX_FACE_SHAPED_PLANAR || t == RPX_FACE_ELLIPTICAL_PLANE ||
@@ -989,7 +1004,7 @@ extern "C" int rpx_capture(rpx_ctx* ctx, const rpx_rays* const* gens, int n_gens
         if (gens[j]->is_gausslet != gens[0]->is_gausslet)
             return fail(ctx, RPX_ERR_INVALID, "collections mix rays and gausslets");
         total += gens[j]->soa.n;
-        tiles_total += rpx_state_words((gens[j]->soa.n + RPX_TILE - 1) / RPX_TILE);  // grouped look-back state
+        tiles_total += rpx_state_words((gens[j]->soa.n + RPX_FILTER_TILE - 1) / RPX_FILTER_TILE);  // grouped look-back state
     }
     const int is_g = gens[0]->is_gausslet;
     rpx_rays* dst = nullptr;
@@ -1031,7 +1046,7 @@ extern "C" int rpx_capture(rpx_ctx* ctx, const rpx_rays* const* gens, int n_gens
                 return bail(e, "cudaMemcpyAsync(total)");
             continue;
         }
-        const unsigned n_tiles = (unsigned)((n + RPX_TILE - 1) / RPX_TILE);
+        const unsigned n_tiles = (unsigned)((n + RPX_FILTER_TILE - 1) / RPX_FILTER_TILE);
         CaptureArgs a;
         a.S = ctx->cap_ds;
         a.in = gens[j]->soa;

@@ -24,7 +24,7 @@ namespace {
 // ------------------------------------------------------------------ k_select
 // Ordered compaction of the rays of one collection whose end_face_idx marks them terminal:
 // RPX_NO_FACE (nothing was hit: ctracer.pyx:2086-2087 leaves (unsigned)-1) when `unterminated`, or a
-// face with face_select[idx] != 0.  Same block scan + decoupled look-back as k_capture; records are
+// face with face_select[idx] != 0.  Same ordered compaction as k_capture (filter_positions); records are
 // copied unchanged except for parent_idx, which gets `parent_offset` added (global numbering across the
 // chunks of rpx_trace_consume).  *d_base = records already in `out`; the last tile writes *d_next.
 template <bool GAUSS>
@@ -33,46 +33,44 @@ k_select(Soa in, Soa out, unsigned long long* tile_state, uint32_t* tile_counter
          unsigned long long* d_next, int unterminated, const unsigned char* face_select, uint32_t parent_offset,
          int copy) {
     __shared__ uint32_t s_tile;
-    __shared__ uint32_t s_warp[RPX_TILE / 32];
-    __shared__ unsigned long long s_prefix;
     if (threadIdx.x == 0) s_tile = atomicAdd(tile_counter, 1u);  // ticket order = start order: look-back cannot deadlock
     __syncthreads();
     const uint32_t tile = s_tile;
-    const uint32_t n_tiles = (uint32_t)((in.n + RPX_TILE - 1) / RPX_TILE);
-    const unsigned long long i = (unsigned long long)tile * RPX_TILE + threadIdx.x;
+    const uint32_t n_tiles = (uint32_t)((in.n + RPX_FILTER_TILE - 1) / RPX_FILTER_TILE);
+    const unsigned long long first = (unsigned long long)tile * RPX_FILTER_TILE + threadIdx.x;
     const unsigned long long cap = in.cap, ocap = out.cap;
-    bool sel = false;
-    if (i < in.n) {
-        const uint32_t face = in.u[U_ENDFACE * cap + i];
-        sel = (face == RPX_NO_FACE) ? (unterminated != 0) : (face_select != nullptr && face_select[face] != 0);
-    }
-    uint32_t total;
-    const uint32_t local = block_exclusive_scan(sel ? 1u : 0u, &total, s_warp);
-    unsigned long long* gagg = tile_state + n_tiles;  // grouped look-back: see k_capture
-    unsigned long long* gpre = gagg + (n_tiles + 31) / 32;
-    if (threadIdx.x == 0) tile_publish_grouped(tile_state, gagg, tile, total);
-    if (threadIdx.x < 32) {
-        unsigned long long excl = tile_lookback_grouped(tile_state, gagg, gpre, tile, total);
-        if (threadIdx.x == 0) {
-            s_prefix = excl;
-            if (tile == n_tiles - 1) *d_next = *d_base + excl + total;
+    bool sel[RPX_FILTER_R];
+#pragma unroll
+    for (int r = 0; r < RPX_FILTER_R; r++) {
+        const unsigned long long i = first + (unsigned long long)r * RPX_TILE;
+        sel[r] = false;
+        if (i < in.n) {
+            const uint32_t face = in.u[U_ENDFACE * cap + i];
+            sel[r] = (face == RPX_NO_FACE) ? (unterminated != 0) : (face_select != nullptr && face_select[face] != 0);
         }
     }
-    __syncthreads();
-    if (!sel || !copy) return;
-    const unsigned long long pos = *d_base + s_prefix + local;
-    if (pos >= ocap) return;  // capacity overrun: reported by the host from *d_next, never written
+    FilterSlots slots;
+    filter_positions(sel, tile_state, tile, n_tiles, *d_base, &slots);
+    if (threadIdx.x == 0 && tile == n_tiles - 1) *d_next = slots.end;
+    if (!copy) return;
+#pragma unroll 1
+    for (int r = 0; r < RPX_FILTER_R; r++) {
+        if (!sel[r]) continue;
+        const unsigned long long i = first + (unsigned long long)r * RPX_TILE;
+        const unsigned long long pos = slots.pos[r];
+        if (pos >= ocap) continue;  // capacity overrun: reported by the host from *d_next, never written
 #pragma unroll
-    for (int fld = 0; fld < NF; fld++) out.f[(unsigned long long)fld * ocap + pos] = in.f[(unsigned long long)fld * cap + i];
+        for (int fld = 0; fld < NF; fld++) out.f[(unsigned long long)fld * ocap + pos] = in.f[(unsigned long long)fld * cap + i];
 #pragma unroll
-    for (int fld = 0; fld < NU; fld++) {
-        uint32_t v = in.u[(unsigned long long)fld * cap + i];
-        if (fld == U_PARENT) v += parent_offset;
-        out.u[(unsigned long long)fld * ocap + pos] = v;
-    }
-    if (GAUSS) {
+        for (int fld = 0; fld < NU; fld++) {
+            uint32_t v = in.u[(unsigned long long)fld * cap + i];
+            if (fld == U_PARENT) v += parent_offset;
+            out.u[(unsigned long long)fld * ocap + pos] = v;
+        }
+        if (GAUSS) {
 #pragma unroll 4
-        for (int fld = 0; fld < NP; fld++) out.p[(unsigned long long)fld * ocap + pos] = in.p[(unsigned long long)fld * cap + i];
+            for (int fld = 0; fld < NP; fld++) out.p[(unsigned long long)fld * ocap + pos] = in.p[(unsigned long long)fld * cap + i];
+        }
     }
 }
 
@@ -132,7 +130,7 @@ struct SelectPlan {
 SelectPlan select_plan(const rpx_rays* const* gens, int n_gens) {
     unsigned long long tiles = 0;
     for (int j = 0; j < n_gens; j++)
-        if (gens[j]) tiles += rpx_state_words((gens[j]->soa.n + RPX_TILE - 1) / RPX_TILE);
+        if (gens[j]) tiles += rpx_state_words((gens[j]->soa.n + RPX_FILTER_TILE - 1) / RPX_FILTER_TILE);
     SelectPlan p;
     p.state_bytes = sizeof(unsigned long long) * (size_t)(tiles ? tiles : 1);
     p.cnt_bytes = sizeof(uint32_t) * (size_t)(n_gens + 2);
@@ -159,7 +157,7 @@ int enqueue_select(rpx_ctx* ctx, const rpx_rays* const* gens, int n_gens, int un
                 return RPX_ERR_CUDA;
             continue;
         }
-        const unsigned n_tiles = (unsigned)((n + RPX_TILE - 1) / RPX_TILE);
+        const unsigned n_tiles = (unsigned)((n + RPX_FILTER_TILE - 1) / RPX_FILTER_TILE);
         const uint32_t poff = parent_offsets ? parent_offsets[j] : 0u;
         if (gens[j]->is_gausslet)
             k_select<true><<<n_tiles, RPX_TILE, 0, st>>>(gens[j]->soa, dst->soa, d_state + tile_off, d_cnt + j, d_totals + j,

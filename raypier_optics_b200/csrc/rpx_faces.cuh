@@ -36,6 +36,10 @@ struct DevScene {
 // holds.  The host picks the variant from the face types present (rpx_scene_set).
 #define RPX_FC_SIMPLE 0
 #define RPX_FC_FULL 1
+// ... and a third class for scenes with triangle-mesh / UV-patch faces: their BVH walk (explicit stacks in
+// local memory) and Newton-on-a-patch code stay out of the kernels the BASELINE configs run (config3's
+// k_shade: 2400 -> 1600 B of stack, fewer spills)
+#define RPX_FC_MESH 2
 RPX_DEV bool face_type_is_simple(int t) {
     return t == RPX_FACE_CIRCULAR || t == RPX_FACE_SHAPED_PLANAR || t == RPX_FACE_ELLIPTICAL_PLANE ||
            t == RPX_FACE_RECTANGULAR || t == RPX_FACE_SPHERICAL || t == RPX_FACE_SHAPED_SPHERICAL ||
@@ -1245,26 +1249,199 @@ static __device__ __noinline__ vec3 mesh_normal(const DevScene& S, const rpx_fac
     return norm(cross(v3(q2[0], q2[1], q2[2]) - a, v3(q3[0], q3[1], q3[2]) - a));
 }
 
-// piece (may be NULL): intersect_t.piece_idx of the hit -- only mesh faces have pieces, 0 otherwise
+// ------------------------------------------------------------------ UV patch faces (cbezier.pyx)
+// UVPatchFace.intersect_c (cbezier.pyx:459-528): the nearest facet of the patch's tessellation (the mesh
+// walk above) gives a seed (u, v) by barycentric interpolation of the vertex parameters
+// (interpolate_cell_c, :421-456); a Newton iteration on the patch itself (<= 100 steps, both steps below
+// atol) polishes it; the hit is the patch point at the final (u, v).  BezierPatch (:200-286) is evaluated
+// with the reference's pow() products, BSplinePatch (:290-388) with the Cox - de Boor recursion
+// (iterative here: a triangular table per direction instead of the reference's exponential recursion).
+struct HitAux {
+    int piece;    // intersect_t.piece_idx: the facet of a mesh face
+    double u, v;  // intersect_t.uv: the patch parameters of a UVPatchFace hit
+};
+
+struct UVPatch {
+    int kind, N, M, udeg, vdeg;
+    const double *uvs, *ctrl, *a, *b;  // a, b: binomials (Bezier) or knots (B-spline)
+};
+
+RPX_DEV UVPatch uvpatch_of(const DevScene& S, const rpx_face* f) {
+    UVPatch P;
+    const double* H = S.pool + f->aux_off;
+    const long long n_points = (long long)H[0];
+    P.kind = (int)f->p[2];
+    P.N = (int)f->p[3];
+    P.M = (int)f->p[4];
+    P.udeg = (int)f->p[5];
+    P.vdeg = (int)f->p[6];
+    P.uvs = S.pool + (long long)f->p[7];
+    P.ctrl = P.uvs + 2 * n_points;
+    P.a = P.ctrl + 3 * (P.N + 1) * (P.M + 1);
+    P.b = P.a + (P.kind == 0 ? P.N + 1 : (long long)f->p[8]);
+    return P;
+}
+
+// B-spline basis N_{idx,p}(t) and its derivative for ONE idx (cbezier.pyx:47-104), bottom-up: the
+// recursion only ever touches N_{k,q} for idx <= k <= idx + p - q.
+#define RPX_BSPLINE_MAX_DEG 8
+static __device__ __noinline__ void bspline_basis(double t, int p, int idx, const double* knots, double* N_out,
+                                                  double* dN_out) {
+    double N[RPX_BSPLINE_MAX_DEG + 1], D[RPX_BSPLINE_MAX_DEG + 1];
+    for (int k = 0; k <= p; k++) {
+        N[k] = (knots[idx + k] <= t && t < knots[idx + k + 1]) ? 1.0 : 0.0;
+        D[k] = 0.0;
+    }
+    for (int q = 1; q <= p; q++)
+        for (int k = 0; k <= p - q; k++) {
+            const int i = idx + k;
+            double n = 0.0, d = 0.0;
+            double denom = knots[i + q] - knots[i];
+            if (denom != 0.0) {
+                const double nom = (t - knots[i]) / denom;
+                n = nom * N[k];
+                d = (1.0 / denom) * N[k] + nom * D[k];
+            }
+            denom = knots[i + q + 1] - knots[i + 1];
+            if (denom != 0.0) {
+                const double nom = (knots[i + q + 1] - t) / denom;
+                n += nom * N[k + 1];
+                d += (-1.0 / denom) * N[k + 1] + nom * D[k + 1];
+            }
+            N[k] = n;
+            D[k] = d;
+        }
+    *N_out = N[0];
+    *dN_out = D[0];
+}
+
+// _eval_pt_and_grads (:259-286, :363-388); grads == false: _eval_pt (:232-254, :335-358)
+static __device__ __noinline__ void uvpatch_eval(const UVPatch& P, double u, double v, bool grads, vec3* p_out,
+                                                 vec3* du_out, vec3* dv_out) {
+    vec3 p = v3(0, 0, 0), pu = v3(0, 0, 0), pv = v3(0, 0, 0);
+    const int N = P.N, M = P.M;
+    for (int i = 0; i <= N; i++) {
+        double ut, dut = 0.0;
+        if (P.kind == 0) {
+            ut = P.a[i] * pow(u, (double)i) * pow(1 - u, (double)(N - i));
+            if (grads) dut = P.a[i] * (i - N * u) * pow(u, (double)(i - 1)) * pow(1 - u, (double)(N - 1 - i));
+        } else {
+            bspline_basis(u, P.udeg, i, P.a, &ut, &dut);
+        }
+        for (int j = 0; j <= M; j++) {
+            double vt, dvt = 0.0;
+            if (P.kind == 0) {
+                vt = P.b[j] * pow(v, (double)j) * pow(1 - v, (double)(M - j));
+                if (grads) dvt = P.b[j] * (j - M * v) * pow(v, (double)(j - 1)) * pow(1 - v, (double)(M - 1 - j));
+            } else {
+                bspline_basis(v, P.vdeg, j, P.b, &vt, &dvt);
+            }
+            const vec3 c = ld3(P.ctrl + 3 * (i * (M + 1) + j));
+            p = p + c * (ut * vt);
+            if (grads) {
+                pu = pu + c * (dut * vt);
+                pv = pv + c * (ut * dvt);
+            }
+        }
+    }
+    *p_out = p;
+    if (grads) {
+        *du_out = pu;
+        *dv_out = pv;
+    }
+}
+
+static __device__ __noinline__ double uvpatch_intersect(const DevScene& S, const rpx_face* f, vec3 p1, vec3 p2, HitAux* aux) {
+    int cell = -1;
+    const double dist_mesh = mesh_intersect(S, f, p1, p2, &cell);
+    const vec3 seg = p2 - p1;
+    const double dmag = sqrt(seg.x * seg.x + seg.y * seg.y + seg.z * seg.z);
+    const double alpha = (cell < 0) ? -1.0 : dist_mesh / dmag;
+    if (alpha < f->tolerance) return -1.0;
+    const double* H = S.pool + f->aux_off;
+    const double* pts = H + (long long)H[3];
+    const double* c = H + (long long)H[4] + 3 * (long long)cell;
+    const long long i0 = (long long)c[0], i1 = (long long)c[1], i2 = (long long)c[2];
+    const UVPatch P = uvpatch_of(S, f);
+    const double tol = f->p[0] * f->p[0];
+    const vec3 d = seg * (1.0 / dmag);
+    vec3 pt = p2 * alpha + p1 * (1.0 - alpha);
+    const vec3 q1 = ld3(pts + 3 * i0);
+    const vec3 edge1 = ld3(pts + 3 * i1) - q1, edge2 = ld3(pts + 3 * i2) - q1;
+    const double x2 = sqrt(dot(edge1, edge1));
+    const vec3 en1 = edge1 * (1.0 / x2);
+    vec3 en2 = cross(en1, cross(edge1, edge2));
+    en2 = en2 * (1.0 / sqrt(dot(en2, en2)));
+    const double x3 = dot(edge2, en1), y3 = dot(edge2, en2);
+    pt = pt - q1;
+    const double px = dot(pt, en1), py = dot(pt, en2);
+    double a2 = x2 * y3;
+    double a1 = py * x3 - px * y3;
+    const double a0 = (a1 - py * x2 + x2 * y3) / a2;
+    a1 = -a1 / a2;
+    a2 = py / y3;
+    double u = a0 * P.uvs[2 * i0] + a1 * P.uvs[2 * i1] + a2 * P.uvs[2 * i2];
+    double v = a0 * P.uvs[2 * i0 + 1] + a1 * P.uvs[2 * i1 + 1] + a2 * P.uvs[2 * i2 + 1];
+    int it = 0;
+    for (; it < 100; it++) {
+        vec3 p, pu, pv;
+        uvpatch_eval(P, u, v, true, &p, &pu, &pv);
+        vec3 n = cross(pu, pv);
+        n = n * (1.0 / sqrt(dot(n, n)));
+        const double dist = dot(p - p1, n) / dot(d, n);
+        const vec3 dp = (p1 + d * dist) - p;
+        const double du = dot(pu, dp) / dot(pu, pu);
+        const double dv = dot(pv, dp) / dot(pv, pv);
+        u += du;
+        v += dv;
+        if (du * du < tol && dv * dv < tol) break;
+    }
+    if (it == 100) return -1.0;
+    vec3 p, unused1, unused2;
+    uvpatch_eval(P, u, v, false, &p, &unused1, &unused2);
+    if (aux) {
+        aux->u = u;
+        aux->v = v;
+    }
+    const vec3 r = p - p1;
+    return sqrt(dot(r, r));
+}
+
+// compute_normal_and_tangent_c (cbezier.pyx:533-550)
+static __device__ __noinline__ void uvpatch_orientation(const DevScene& S, const rpx_face* f, const HitAux& aux, vec3* normal,
+                                                        vec3* tangent) {
+    const UVPatch P = uvpatch_of(S, f);
+    vec3 p, pu, pv;
+    uvpatch_eval(P, aux.u, aux.v, true, &p, &pu, &pv);
+    vec3 n = cross(pu, pv);
+    n = n * (1.0 / sqrt(dot(n, n)));
+    *normal = (f->p[1] != 0.0) ? neg(n) : n;
+    *tangent = pu * (1.0 / sqrt(dot(pu, pu)));
+}
+
+// aux (may be NULL): the part of intersect_t that travels from Face.intersect_c to
+// compute_normal_and_tangent_c -- piece_idx for mesh faces, uv for UV patch faces
+
 template <int FC>
 RPX_DEV double face_intersect(const DevScene& S, const rpx_face* f, vec3 p1, vec3 p2, int is_base_ray,
-                              int* piece = nullptr) {
-    if (FC == RPX_FC_FULL && f->type == RPX_FACE_MESH) {
+                              HitAux* aux = nullptr) {
+    if (FC == RPX_FC_MESH && f->type == RPX_FACE_MESH) {
         int pc;
         const double dist = mesh_intersect(S, f, p1, p2, &pc);
-        if (piece) *piece = pc;
+        if (aux) aux->piece = pc;
         return dist;
     }
-    if (piece) *piece = 0;
-    if (FC == RPX_FC_FULL && f->type == RPX_FACE_DISTORTION) return distortion_intersect(S, f, p1, p2);
-    if (FC == RPX_FC_FULL && f->type == RPX_FACE_EXTRUDED_BEZIER) return bezier_intersect(S, f, p1, p2);
+    if (aux) aux->piece = 0;
+    if (FC == RPX_FC_MESH && f->type == RPX_FACE_UVPATCH) return uvpatch_intersect(S, f, p1, p2, aux);
+    if (FC >= RPX_FC_FULL && f->type == RPX_FACE_DISTORTION) return distortion_intersect(S, f, p1, p2);
+    if (FC >= RPX_FC_FULL && f->type == RPX_FACE_EXTRUDED_BEZIER) return bezier_intersect(S, f, p1, p2);
     return face_intersect_basic<FC>(S, f, p1, p2, is_base_ray);
 }
 
 template <int FC>
 __device__ vec3 face_normal(const DevScene& S, const rpx_face* f, vec3 p, int piece = 0) {
-    if (FC == RPX_FC_FULL && f->type == RPX_FACE_MESH) return mesh_normal(S, f, piece);
-    if (FC == RPX_FC_FULL && f->type == RPX_FACE_DISTORTION) {  // cfaces.pyx:2418-2431
+    if (FC == RPX_FC_MESH && f->type == RPX_FACE_MESH) return mesh_normal(S, f, piece);
+    if (FC >= RPX_FC_FULL && f->type == RPX_FACE_DISTORTION) {  // cfaces.pyx:2418-2431
         const rpx_face* base = &S.faces[f->base_face];
         const rpx_distortion* dist = &S.dists[f->aux_off];
         vec3 dxdyz = distortion_zgrad(S, dist, p.x, p.y);
@@ -1278,7 +1455,7 @@ __device__ vec3 face_normal(const DevScene& S, const rpx_face* f, vec3 p, int pi
         n.y -= dxdyz.y;
         return norm(n);
     }
-    if (FC == RPX_FC_FULL && f->type == RPX_FACE_EXTRUDED_BEZIER) return bezier_normal(S, f, p);
+    if (FC >= RPX_FC_FULL && f->type == RPX_FACE_EXTRUDED_BEZIER) return bezier_normal(S, f, p);
     return face_normal_basic<FC>(S, f, p);
 }
 
@@ -1291,11 +1468,19 @@ RPX_DEV vec3 face_tangent(const rpx_face* f) {
 // FaceList.compute_orientation_c, ctracer.pyx:1939-1953
 template <int FC>
 RPX_DEV void compute_orientation(const DevScene& S, const rpx_face* f, vec3 point, vec3* normal,
-                                 vec3* tangent, int piece = 0) {
+                                 vec3* tangent, const HitAux* aux = nullptr) {
     const rpx_face_set* fs = &S.sets[f->face_set];
     point = transform_pt(fs->inv_trans.m, point);
-    vec3 n = face_normal<FC>(S, f, point, piece);
-    vec3 t = face_tangent(f);
+    vec3 n, t;
+    if (FC == RPX_FC_MESH && f->type == RPX_FACE_UVPATCH) {
+        HitAux zero;
+        zero.piece = 0;
+        zero.u = zero.v = 0.0;
+        uvpatch_orientation(S, f, aux ? *aux : zero, &n, &t);
+    } else {
+        n = face_normal<FC>(S, f, point, aux ? aux->piece : 0);
+        t = face_tangent(f);
+    }
     if (f->invert_normal) {
         n = neg(n);
         t = neg(t);

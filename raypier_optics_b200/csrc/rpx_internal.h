@@ -43,7 +43,7 @@ struct rpx_ctx {
     int n_traced;
     int max_kids;       // upper bound of children per hit over all materials in the scene
     int scene_smem;     // bytes of shared memory the staged scene needs (0 = use global)
-    int face_class;     // RPX_FC_SIMPLE / RPX_FC_FULL kernel variant for this scene
+    int face_class;     // RPX_FC_SIMPLE / RPX_FC_FULL / RPX_FC_MESH kernel variant for this scene
     int mm_idx;         // material-mask kernel variant: 0 LIGHT, 1 COATED, 2 FULLDIEL, 3 ALL
     // capture-plane scene (rpx_capture_scene_set): a second, independent face list
     bool have_capture;

@@ -391,13 +391,74 @@ RPX_DEV unsigned long long tile_lookback_grouped(unsigned long long* state, unsi
     return excl;
 }
 
+// ------------------------------------------------------------------ ordered compaction of a filter
+// k_capture / k_select keep a subset of a collection IN INPUT ORDER.  The per-ray work of such a filter
+// is tiny (one plane test, or one compare), so the tile must be large or the kernel is bound by CTA
+// scheduling and look-backs (measured on B200 with 128-ray CTAs: 0.47 ms per launch of 2.25e6 gausslets,
+// 6x the HBM time): a CTA of RPX_TILE threads takes RPX_FILTER_R consecutive sub-tiles of RPX_TILE rays
+// (coalesced loads), counts the kept rays per (sub-tile, warp) with ballots, scans those RPX_FILTER_R x
+// warps counts once, and does ONE publish + grouped look-back per RPX_FILTER_R * RPX_TILE rays.
+#define RPX_FILTER_R 8
+#define RPX_FILTER_TILE (RPX_FILTER_R * RPX_TILE)
+struct FilterSlots {
+    unsigned long long pos[RPX_FILTER_R];  // output position of the thread's ray of sub-tile r (if kept)
+    unsigned long long end;                // records in the output after this tile
+};
+// keep[r]: this thread's ray of sub-tile r is kept.  state: rpx_state_words(n_tiles) zeroed words.
+// Returns false for the threads of a CTA that has nothing to copy.
+RPX_DEV void filter_positions(const bool (&keep)[RPX_FILTER_R], unsigned long long* tile_state, uint32_t tile,
+                              uint32_t n_tiles, unsigned long long base0, FilterSlots* out) {
+    constexpr int W = RPX_TILE / 32;
+    __shared__ uint32_t s_cnt[RPX_FILTER_R * W];
+    __shared__ uint32_t s_off[RPX_FILTER_R * W];
+    __shared__ unsigned long long s_prefix;
+    __shared__ uint32_t s_total;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    uint32_t rank[RPX_FILTER_R];
+#pragma unroll
+    for (int r = 0; r < RPX_FILTER_R; r++) {
+        const unsigned b = __ballot_sync(0xffffffffu, keep[r]);
+        rank[r] = (uint32_t)__popc(b & ((1u << lane) - 1u));
+        if (lane == 0) s_cnt[r * W + warp] = (uint32_t)__popc(b);
+    }
+    __syncthreads();
+    if (warp == 0) {
+        // exclusive scan of the RPX_FILTER_R * W counts in (sub-tile, warp) order = ray order
+        static_assert(RPX_FILTER_R * W <= 64, "two entries per lane");
+        const int k0 = 2 * lane, k1 = 2 * lane + 1;
+        const uint32_t c0 = k0 < RPX_FILTER_R * W ? s_cnt[k0] : 0u, c1 = k1 < RPX_FILTER_R * W ? s_cnt[k1] : 0u;
+        uint32_t incl = c0 + c1;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += t;
+        }
+        const uint32_t excl = incl - (c0 + c1);
+        if (k0 < RPX_FILTER_R * W) s_off[k0] = excl;
+        if (k1 < RPX_FILTER_R * W) s_off[k1] = excl + c0;
+        const uint32_t total = __shfl_sync(0xffffffffu, incl, 31);
+        unsigned long long* gagg = tile_state + n_tiles;
+        unsigned long long* gpre = gagg + (n_tiles + 31) / 32;
+        if (lane == 0) tile_publish_grouped(tile_state, gagg, tile, total);
+        const unsigned long long before = tile_lookback_grouped(tile_state, gagg, gpre, tile, total);
+        if (lane == 0) {
+            s_prefix = before;
+            s_total = total;
+        }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int r = 0; r < RPX_FILTER_R; r++) out->pos[r] = base0 + s_prefix + s_off[r * W + warp] + rank[r];
+    out->end = base0 + s_prefix + s_total;
+}
+
 // ------------------------------------------------------------------ k_capture
 // select_ray_intersections / select_gausslet_intersections (ctracer.pyx:1981-2058) for ONE
 // collection: every ray is re-intersected between its origin and origin + direction * length
 // with the capture FaceList (S holds only that face list); rays that hit are appended to `out`
-// in input order (block scan + decoupled look-back, as k_shade) after the *d_base records already
-// captured from earlier collections.  The copy carries length = hit distance, end_face_idx =
-// the capture face's idx and the re-based wavelength index (:2004-2006, 2011-2014).
+// in input order after the *d_base records already captured from earlier collections.  The copy
+// carries length = hit distance, end_face_idx = the capture face's idx and the re-based wavelength
+// index (:2004-2006, 2011-2014).  Grid = ceil(n / RPX_FILTER_TILE) CTAs.
 template <bool GAUSS, int FC, bool SS>
 __global__ void __launch_bounds__(RPX_TILE, 4 * 128 / RPX_TILE)
 k_capture(DevScene S, Soa in, Soa out, unsigned long long* tile_state, uint32_t* tile_counter,
@@ -405,57 +466,54 @@ k_capture(DevScene S, Soa in, Soa out, unsigned long long* tile_state, uint32_t*
           const uint32_t* face_ids) {
     extern __shared__ __align__(16) unsigned char smem[];
     __shared__ uint32_t s_tile;
-    __shared__ uint32_t s_warp[RPX_TILE / 32];
-    __shared__ unsigned long long s_prefix;
     stage_scene<SS>(S, smem);
     if (threadIdx.x == 0) s_tile = atomicAdd(tile_counter, 1u);  // ticket order = start order: look-back cannot deadlock
     __syncthreads();
     const uint32_t tile = s_tile;
-    const uint32_t n_tiles = (uint32_t)((in.n + RPX_TILE - 1) / RPX_TILE);
-    const unsigned long long i = (unsigned long long)tile * RPX_TILE + threadIdx.x;
+    const uint32_t n_tiles = (uint32_t)((in.n + RPX_FILTER_TILE - 1) / RPX_FILTER_TILE);
+    const unsigned long long first = (unsigned long long)tile * RPX_FILTER_TILE + threadIdx.x;
     const unsigned long long cap = in.cap, ocap = out.cap;
-    double len = 0.0;
-    uint32_t face = RPX_NO_FACE;
-    if (i < in.n) {
-        vec3 o = v3(in.f[F_OX * cap + i], in.f[F_OY * cap + i], in.f[F_OZ * cap + i]);
-        vec3 d = v3(in.f[F_DX * cap + i], in.f[F_DY * cap + i], in.f[F_DZ * cap + i]);
-        nearest_hit<FC>(S, o, d, in.f[F_LEN * cap + i], -1, &len, &face);
-    }
-    const bool hit = (face != RPX_NO_FACE);
-    uint32_t total;
-    const uint32_t local = block_exclusive_scan(hit ? 1u : 0u, &total, s_warp);
-    // grouped look-back (one round trip): the per-tile work is a single plane test, so thousands of tiles
-    // run in lock step and the flat walk would be the whole kernel (state = rpx_state_words(n_tiles) words)
-    unsigned long long* gagg = tile_state + n_tiles;
-    unsigned long long* gpre = gagg + (n_tiles + 31) / 32;
-    if (threadIdx.x == 0) tile_publish_grouped(tile_state, gagg, tile, total);
-    if (threadIdx.x < 32) {
-        unsigned long long excl = tile_lookback_grouped(tile_state, gagg, gpre, tile, total);
-        if (threadIdx.x == 0) {
-            s_prefix = excl;
-            if (tile == n_tiles - 1) *d_next = *d_base + excl + total;
-        }
-    }
-    __syncthreads();
-    if (!hit) return;
-    const unsigned long long pos = *d_base + s_prefix + local;
+    double len[RPX_FILTER_R];
+    uint32_t face[RPX_FILTER_R];
+    bool hit[RPX_FILTER_R];
 #pragma unroll
-    for (int fld = 0; fld < NF; fld++)
-        out.f[(unsigned long long)fld * ocap + pos] = (fld == F_LEN) ? len : in.f[(unsigned long long)fld * cap + i];
-#pragma unroll
-    for (int fld = 0; fld < NU; fld++) {
-        uint32_t v = in.u[(unsigned long long)fld * cap + i];
-        if (fld == U_ENDFACE) v = face_ids ? face_ids[face] : face;
-        if (fld == U_WL) {
-            v += wl_offset;
-            if (wl_map) v = wl_map[v];
+    for (int r = 0; r < RPX_FILTER_R; r++) {
+        const unsigned long long i = first + (unsigned long long)r * RPX_TILE;
+        len[r] = 0.0;
+        face[r] = RPX_NO_FACE;
+        if (i < in.n) {
+            vec3 o = v3(in.f[F_OX * cap + i], in.f[F_OY * cap + i], in.f[F_OZ * cap + i]);
+            vec3 d = v3(in.f[F_DX * cap + i], in.f[F_DY * cap + i], in.f[F_DZ * cap + i]);
+            nearest_hit<FC>(S, o, d, in.f[F_LEN * cap + i], -1, &len[r], &face[r]);
         }
-        out.u[(unsigned long long)fld * ocap + pos] = v;
+        hit[r] = (face[r] != RPX_NO_FACE);
     }
-    if (GAUSS) {
+    FilterSlots slots;
+    filter_positions(hit, tile_state, tile, n_tiles, *d_base, &slots);
+    if (threadIdx.x == 0 && tile == n_tiles - 1) *d_next = slots.end;
+#pragma unroll 1
+    for (int r = 0; r < RPX_FILTER_R; r++) {
+        if (!hit[r]) continue;
+        const unsigned long long i = first + (unsigned long long)r * RPX_TILE;
+        const unsigned long long pos = slots.pos[r];
+#pragma unroll
+        for (int fld = 0; fld < NF; fld++)
+            out.f[(unsigned long long)fld * ocap + pos] = (fld == F_LEN) ? len[r] : in.f[(unsigned long long)fld * cap + i];
+#pragma unroll
+        for (int fld = 0; fld < NU; fld++) {
+            uint32_t v = in.u[(unsigned long long)fld * cap + i];
+            if (fld == U_ENDFACE) v = face_ids ? face_ids[face[r]] : face[r];
+            if (fld == U_WL) {
+                v += wl_offset;
+                if (wl_map) v = wl_map[v];
+            }
+            out.u[(unsigned long long)fld * ocap + pos] = v;
+        }
+        if (GAUSS) {
 #pragma unroll 4
-        for (int fld = 0; fld < NP; fld++)
-            out.p[(unsigned long long)fld * ocap + pos] = in.p[(unsigned long long)fld * cap + i];
+            for (int fld = 0; fld < NP; fld++)
+                out.p[(unsigned long long)fld * ocap + pos] = in.p[(unsigned long long)fld * cap + i];
+        }
     }
 }
 
@@ -654,7 +712,7 @@ k_shade(DevScene S, Soa in, Soa out, double max_length, unsigned long long* tile
     uint32_t wl = 0, ident = 0;
     uint32_t face_idx = RPX_NO_FACE;
     double plen[RPX_NPARA];
-    int ppiece[FC == RPX_FC_FULL ? RPX_NPARA : 1];  // piece_idx of the parabasal hits (mesh faces)
+    HitAux paux[FC == RPX_FC_MESH ? RPX_NPARA : 1];  // piece_idx / uv of the parabasal hits (mesh, UV patch faces)
     bool hit = false;
     RayIn r;
     if (i < n_in) {
@@ -697,16 +755,19 @@ k_shade(DevScene S, Soa in, Soa out, double max_length, unsigned long long* tile
         }
         vec3 point = r.o + r.d * r.len;
         vec3 onormal, otangent;
-        int piece = 0;
-        if (FC == RPX_FC_FULL && face->type == RPX_FACE_MESH) {
-            // intersect_t.piece_idx (which triangle) is not part of the ray record: the hit is found
-            // again from the same inputs the trace-ahead / k_intersect pass used, so it is the same hit
+        HitAux aux;
+        aux.piece = 0;
+        aux.u = aux.v = 0.0;
+        if (FC == RPX_FC_MESH && (face->type == RPX_FACE_MESH || face->type == RPX_FACE_UVPATCH)) {
+            // intersect_t.piece_idx (which triangle) / .uv (patch parameters) are not part of the ray
+            // record: the hit is found again from the same inputs the trace-ahead / k_intersect pass
+            // used, so it is the same hit
             const rpx_face_set* mfs = &S.sets[face->face_set];
             face_intersect<FC>(S, face, transform_pt(mfs->inv_trans.m, r.o),
-                               transform_pt(mfs->inv_trans.m, r.o + r.d * max_length), 1, &piece);
-            if (piece < 0) piece = 0;
+                               transform_pt(mfs->inv_trans.m, r.o + r.d * max_length), 1, &aux);
+            if (aux.piece < 0) aux.piece = 0;
         }
-        compute_orientation<FC>(S, face, point, &onormal, &otangent, piece);
+        compute_orientation<FC>(S, face, point, &onormal, &otangent, &aux);
         material_eval<MM>(S, &S.mats[face->material], r, point, onormal, otangent, k);
 
         if (GAUSS) {
@@ -728,9 +789,11 @@ k_shade(DevScene S, Soa in, Soa out, double max_length, unsigned long long* tile
                     vec3 ray_end = po + pd * max_length;
                     vec3 p1 = transform_pt(fs->inv_trans.m, po);
                     vec3 p2 = transform_pt(fs->inv_trans.m, ray_end);
-                    int pc = 0;
-                    double dist = face_intersect<FC>(S, face, p1, p2, 0, FC == RPX_FC_FULL ? &pc : nullptr);
-                    if (FC == RPX_FC_FULL) ppiece[j] = pc;
+                    HitAux pa;
+                    pa.piece = 0;
+                    pa.u = pa.v = 0.0;
+                    double dist = face_intersect<FC>(S, face, p1, p2, 0, FC == RPX_FC_MESH ? &pa : nullptr);
+                    if (FC == RPX_FC_MESH) paux[j] = pa;
                     if (face->tolerance < dist && dist < max_length) {
                         plen[j] = dist;
                         in.p[(unsigned long long)(j * NPF + P_LEN) * cap + i] = dist;  // parent write-back
@@ -938,7 +1001,7 @@ k_shade(DevScene S, Soa in, Soa out, double max_length, unsigned long long* tile
                                 : v3(pp[(P_DX + 0) * cap], pp[(P_DX + 1) * cap], pp[(P_DX + 2) * cap]);
             vec3 ppoint = po + pd * plen[j];
             vec3 pn, pt;
-            compute_orientation<FC>(S, face, ppoint, &pn, &pt, FC == RPX_FC_FULL ? ppiece[j] : 0);
+            compute_orientation<FC>(S, face, ppoint, &pn, &pt, FC == RPX_FC_MESH ? &paux[j] : nullptr);
             vec3 nn = norm(pn);
             if (k.has_a) {
                 vec3 dir = material_eval_para(S, M, wl, k.a.n.re, pd, ppoint, pn, pt, k.a.type);

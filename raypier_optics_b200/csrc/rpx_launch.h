@@ -34,6 +34,10 @@ cudaError_t launch_shade_g0_f1_m0(cudaStream_t st, const ShadeArgs& a);
 cudaError_t launch_shade_g0_f1_m1(cudaStream_t st, const ShadeArgs& a);
 cudaError_t launch_shade_g0_f1_m2(cudaStream_t st, const ShadeArgs& a);
 cudaError_t launch_shade_g0_f1_m3(cudaStream_t st, const ShadeArgs& a);
+cudaError_t launch_shade_g0_f2_m0(cudaStream_t st, const ShadeArgs& a);
+cudaError_t launch_shade_g0_f2_m1(cudaStream_t st, const ShadeArgs& a);
+cudaError_t launch_shade_g0_f2_m2(cudaStream_t st, const ShadeArgs& a);
+cudaError_t launch_shade_g0_f2_m3(cudaStream_t st, const ShadeArgs& a);
 cudaError_t launch_shade_g1_f0_m0(cudaStream_t st, const ShadeArgs& a);
 cudaError_t launch_shade_g1_f0_m1(cudaStream_t st, const ShadeArgs& a);
 cudaError_t launch_shade_g1_f0_m2(cudaStream_t st, const ShadeArgs& a);
@@ -42,18 +46,24 @@ cudaError_t launch_shade_g1_f1_m0(cudaStream_t st, const ShadeArgs& a);
 cudaError_t launch_shade_g1_f1_m1(cudaStream_t st, const ShadeArgs& a);
 cudaError_t launch_shade_g1_f1_m2(cudaStream_t st, const ShadeArgs& a);
 cudaError_t launch_shade_g1_f1_m3(cudaStream_t st, const ShadeArgs& a);
+cudaError_t launch_shade_g1_f2_m0(cudaStream_t st, const ShadeArgs& a);
+cudaError_t launch_shade_g1_f2_m1(cudaStream_t st, const ShadeArgs& a);
+cudaError_t launch_shade_g1_f2_m2(cudaStream_t st, const ShadeArgs& a);
+cudaError_t launch_shade_g1_f2_m3(cudaStream_t st, const ShadeArgs& a);
 // scene tables too large for shared memory: widest face class / material mask, tables in global memory
-cudaError_t launch_shade_g0_f1_m3_nss(cudaStream_t st, const ShadeArgs& a);
-cudaError_t launch_shade_g1_f1_m3_nss(cudaStream_t st, const ShadeArgs& a);
+cudaError_t launch_shade_g0_f2_m3_nss(cudaStream_t st, const ShadeArgs& a);
+cudaError_t launch_shade_g1_f2_m3_nss(cudaStream_t st, const ShadeArgs& a);
 typedef cudaError_t (*ShadeLauncher)(cudaStream_t, const ShadeArgs&);
 inline ShadeLauncher shade_launcher(int gauss, int fc, int mm_idx, bool scene_shared) {
-    if (!scene_shared) return gauss ? launch_shade_g1_f1_m3_nss : launch_shade_g0_f1_m3_nss;
-    static const ShadeLauncher table[2][2][4] = {
+    if (!scene_shared) return gauss ? launch_shade_g1_f2_m3_nss : launch_shade_g0_f2_m3_nss;
+    static const ShadeLauncher table[2][3][4] = {
         {{launch_shade_g0_f0_m0, launch_shade_g0_f0_m1, launch_shade_g0_f0_m2, launch_shade_g0_f0_m3},
-         {launch_shade_g0_f1_m0, launch_shade_g0_f1_m1, launch_shade_g0_f1_m2, launch_shade_g0_f1_m3}},
+         {launch_shade_g0_f1_m0, launch_shade_g0_f1_m1, launch_shade_g0_f1_m2, launch_shade_g0_f1_m3},
+         {launch_shade_g0_f2_m0, launch_shade_g0_f2_m1, launch_shade_g0_f2_m2, launch_shade_g0_f2_m3}},
         {{launch_shade_g1_f0_m0, launch_shade_g1_f0_m1, launch_shade_g1_f0_m2, launch_shade_g1_f0_m3},
-         {launch_shade_g1_f1_m0, launch_shade_g1_f1_m1, launch_shade_g1_f1_m2, launch_shade_g1_f1_m3}}};
-    return table[gauss ? 1 : 0][fc ? 1 : 0][mm_idx & 3];
+         {launch_shade_g1_f1_m0, launch_shade_g1_f1_m1, launch_shade_g1_f1_m2, launch_shade_g1_f1_m3},
+         {launch_shade_g1_f2_m0, launch_shade_g1_f2_m1, launch_shade_g1_f2_m2, launch_shade_g1_f2_m3}}};
+    return table[gauss ? 1 : 0][fc < 0 ? 0 : (fc > 2 ? 2 : fc)][mm_idx & 3];
 }
 // smem == 0 selects the SS=false instantiation (face class FULL, tables in global memory)
 cudaError_t launch_intersect(int fc, cudaStream_t st, unsigned n_tiles, int smem, const DevScene& S, const Soa& rays,

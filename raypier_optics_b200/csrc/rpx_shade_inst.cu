@@ -6,7 +6,7 @@
 #include "rpx_launch.h"
 
 #if !defined(RPX_I_GAUSS) || !defined(RPX_I_FC) || !defined(RPX_I_MM)
-#error "compile with -DRPX_I_GAUSS=0|1 -DRPX_I_FC=0|1 -DRPX_I_MM=0..3"
+#error "compile with -DRPX_I_GAUSS=0|1 -DRPX_I_FC=0|1|2 -DRPX_I_MM=0..3"
 #endif
 
 // RPX_I_SS=0: the instantiation for scenes whose tables do not fit in shared memory (suffix _nss)

@@ -19,7 +19,7 @@ static __global__ void k_unit_face_intersect(DevScene S, int face, const double*
                                       unsigned long long n, int is_base_ray, double* out) {
     unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
-    out[i] = face_intersect<RPX_FC_FULL>(S, &S.faces[face], ld3(p1 + 3 * i), ld3(p2 + 3 * i), is_base_ray);
+    out[i] = face_intersect<RPX_FC_MESH>(S, &S.faces[face], ld3(p1 + 3 * i), ld3(p2 + 3 * i), is_base_ray);
 }
 
 static __global__ void k_unit_face_normal(DevScene S, int face, const double* pts, unsigned long long n,
@@ -27,7 +27,7 @@ static __global__ void k_unit_face_normal(DevScene S, int face, const double* pt
     unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     vec3 nn, tt;
-    compute_orientation<RPX_FC_FULL>(S, &S.faces[face], ld3(pts + 3 * i), &nn, &tt);
+    compute_orientation<RPX_FC_MESH>(S, &S.faces[face], ld3(pts + 3 * i), &nn, &tt);
     normal[3 * i] = nn.x; normal[3 * i + 1] = nn.y; normal[3 * i + 2] = nn.z;
     tangent[3 * i] = tt.x; tangent[3 * i + 1] = tt.y; tangent[3 * i + 2] = tt.z;
 }

@@ -467,10 +467,12 @@ class Scene:
             p[0], p[1], p[2], p[3] = mat.outer_width, mat.outer_height, mat.width, mat.height
             p[4], p[5] = mat.edge_width, int(mat.invert)
             p[6:9] = mat.origin
+        elif name == "ResampleGaussletMaterial":
+            # eval_child_ray_c only captures (cmaterials.pyx:1808-1821): no child ray.  The capture, the
+            # Python callback and the append happen on the host between generations (core/tracer.py)
+            m['type'] = A.MAT_OPAQUE
         else:
-            raise UnsupportedSceneError(
-                "%s needs a host callback between generations and is not traced on the device"
-                % name)
+            raise UnsupportedSceneError("material class %s is not supported" % name)
         self._materials.append(m)
         self._mat_index[key] = len(self._materials) - 1
         return self._mat_index[key]
@@ -618,6 +620,47 @@ class Scene:
                 points, cells = o.mesh_points, o.mesh_cells
             p[0] = tree.tolerance
             f['aux_off'], f['aux_n'], f['aux_m'] = self._mesh_block(points, cells, tree.tolerance)
+        elif name == "UVPatchFace":
+            f['type'] = A.FACE_UVPATCH
+            patch = face.patch
+            # the tessellation the face traces first (cbezier.pyx:408-418).  u_res / v_res are private cdef
+            # members of a genuine raypier UVPatchFace: take them from the face (host mirror) or its owner
+            u_res = getattr(face, "u_res", None) or getattr(getattr(face, "owner", None), "u_res", None)
+            v_res = getattr(face, "v_res", None) or getattr(getattr(face, "owner", None), "v_res", None)
+            if not u_res or not v_res:
+                raise UnsupportedSceneError(
+                    "a genuine raypier UVPatchFace does not expose its mesh resolution: give its owner u_res / "
+                    "v_res attributes, or build the face from raypier_optics_b200.core.cbezier")
+            points, cells, uvs = patch.get_mesh(int(u_res), int(v_res))
+            tree = face.obbtree
+            f['aux_off'], f['aux_n'], f['aux_m'] = self._mesh_block(points, cells, tree.tolerance)
+            ctrl = np.ascontiguousarray(patch.control_pts, dtype=np.double)
+            N, M = int(patch.order_n), int(patch.order_m)
+            if ctrl.shape != (N + 1, M + 1, 3):
+                raise ValueError("patch control points must have shape (%d, %d, 3)" % (N + 1, M + 1))
+            pname = type(patch).__name__
+            if pname == "BezierPatch":
+                kind = 0
+                fct = math.factorial  # binomial(), cbezier.pyx:120-122
+                a = [fct(N) / (fct(i) * fct(N - i)) for i in range(N + 1)]
+                b = [fct(M) / (fct(i) * fct(M - i)) for i in range(M + 1)]
+                udeg = vdeg = 0
+            elif pname == "BSplinePatch":
+                kind = 1
+                a = np.asarray(patch.u_knots, dtype=np.double)
+                b = np.asarray(patch.v_knots, dtype=np.double)
+                udeg, vdeg = int(patch.u_degree), int(patch.v_degree)
+                if len(a) < N + udeg + 2 or len(b) < M + vdeg + 2:
+                    raise ValueError("a B-spline patch needs (degree + n + 2) knots per direction")
+                if udeg > 8 or vdeg > 8:
+                    raise UnsupportedSceneError("B-spline degree > 8")
+            else:
+                raise UnsupportedSceneError("patch class %s is not supported" % pname)
+            off = self._pool_add(np.asarray(uvs, dtype=np.double).reshape(-1, 2))
+            self._pool_add(ctrl)
+            self._pool_add(a)
+            self._pool_add(b)
+            p[0:10] = (face.atol, 1.0 if face.invert_normals else 0.0, kind, N, M, udeg, vdeg, off, len(a), len(b))
         elif name == "DistortionFace":
             f['type'] = A.FACE_DISTORTION
             p[0] = face.accuracy

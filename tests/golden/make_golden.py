@@ -39,6 +39,9 @@ GOLDEN_CASES = [
     # OBBTreeFace triangle meshes (coarser mirror mesh: the scene tables travel with the fixture)
     ("mesh_rays", dict(n=160, gausslets=False, mesh_n=14), None),
     ("mesh", dict(n=40, gausslets=True, mesh_n=14), None),
+    # UVPatchFace over a Bezier and a B-spline patch (cbezier.pyx; imported with the numpy.math alias)
+    ("uvpatch_rays", dict(n=200, gausslets=False), None),
+    ("uvpatch", dict(n=60, gausslets=True), None),
 ]
 
 
@@ -55,8 +58,11 @@ def main():
         cfg = build_case(core, name, kw, rl)
         sc = SC.Scene(cfg['face_lists'], cfg['wavelengths'])
         rc = O.reference_collection(core, cfg['rays'], cfg['wavelengths'])
-        traced, all_faces = O.reference_trace_rays(core, rc, cfg['face_lists'], cfg['recursion_limit'],
-                                                   cfg['max_length'])
+        import contextlib
+        import io
+        with contextlib.redirect_stdout(io.StringIO()):  # UVPatchFace.intersect_c prints a line per hit (:524)
+            traced, all_faces = O.reference_trace_rays(core, rc, cfg['face_lists'], cfg['recursion_limit'],
+                                                       cfg['max_length'])
         out = {"input": cfg['rays'], "max_length": np.array(cfg['max_length']),
                "recursion_limit": np.array(cfg['recursion_limit']),
                "face_counts": np.array([f.count for f in all_faces], dtype=np.uint32),

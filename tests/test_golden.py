@@ -71,6 +71,7 @@ MIRROR_CASES = {
     "config4_grating": ("config4_grating", dict(n=160), None),
     "config5_rays": ("config5", dict(n=96, gausslets=False), None),
     "config5": ("config5", dict(n=40, gausslets=True), None),
+    "uvpatch_rays": ("uvpatch", dict(n=200, gausslets=False), None),
 }
 
 

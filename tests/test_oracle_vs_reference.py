@@ -15,10 +15,15 @@ def test_oracle_bit_exact_with_reference(refcore, name, kw, rl):
     kw = dict(kw, n=min(kw.get("n", 2000), 4000))
     if name == "mesh" and not hasattr(refcore, "obbtree"):
         pytest.skip("the reference's obbtree module is not importable here (it needs PIL at import time)")
+    if name == "uvpatch" and not hasattr(refcore, "cbezier"):
+        pytest.skip("the reference's cbezier module is not importable here")
     cfg = build_case(refcore, name, kw, rl)
     rc = O.reference_collection(refcore, cfg['rays'], cfg['wavelengths'])
-    traced, all_faces = O.reference_trace_rays(refcore, rc, cfg['face_lists'], cfg['recursion_limit'],
-                                               cfg['max_length'])
+    import contextlib
+    import io
+    with contextlib.redirect_stdout(io.StringIO()):  # UVPatchFace.intersect_c prints a line per hit (cbezier.pyx:524)
+        traced, all_faces = O.reference_trace_rays(refcore, rc, cfg['face_lists'], cfg['recursion_limit'],
+                                                   cfg['max_length'])
     ref = [t.copy_as_array() for t in traced]
     sc = SC.Scene(cfg['face_lists'], cfg['wavelengths'])
     gens, counts = O.trace_rays(sc, cfg['rays'], cfg['recursion_limit'], cfg['max_length'])
@@ -90,3 +95,39 @@ def test_gausslet_collection_helpers_match_reference(refcore, core):
     n0 = len(mir)
     mir.extend(other)
     assert len(mir) == n0 + 7 and mir.copy_as_array()[n0:].tobytes() == g[:7].tobytes()
+
+
+def _relaunch_for(corelib, max_length):
+    """configs.resample_relaunch wrapped as a ResampleGaussletMaterial.eval_func for ``corelib``'s
+    GaussletCollection class (the genuine reference's or the host mirror's)."""
+    from raypier_optics_b200 import _abi as A, configs
+    ct = corelib.ctracer
+
+    def f(gc):
+        a = np.ascontiguousarray(gc.copy_as_array()).view(A.gausslet_dtype)
+        out = configs.resample_relaunch(a, max_length)
+        o = np.empty(len(out), dtype=ct.gausslet_dtype)
+        o.view(np.uint8)[:] = out.view(np.uint8)
+        return ct.GaussletCollection.from_array(o)
+    return f
+
+
+def test_oracle_decomposition_loop_bit_exact_with_reference(refcore):
+    """ResampleGaussletMaterial (cmaterials.pyx:1766-1831) + the decomposition step of trace_gausslet_c
+    (ctracer.pyx:2274-2280): the oracle's restatement of capture -> callback -> append -> count reset ->
+    length reset against the genuine reference driving the same callback."""
+    from oracle import oracle as O
+    from raypier_optics_b200 import configs
+    cfg = configs.build(refcore, "resample", n=1200)
+    mat = cfg['decomp_material']
+    mat.eval_func = _relaunch_for(refcore, cfg['max_length'])
+    rc = O.reference_collection(refcore, cfg['rays'], cfg['wavelengths'])
+    traced, faces = O.reference_trace_rays(refcore, rc, cfg['face_lists'], cfg['recursion_limit'], cfg['max_length'])
+    sc = SC.Scene(cfg['face_lists'], cfg['wavelengths'])
+    gens, counts = O.trace_rays(sc, cfg['rays'], cfg['recursion_limit'], cfg['max_length'],
+                                decomp={1: lambda a: configs.resample_relaunch(a, cfg['max_length'])})
+    assert [len(g) for g in gens] == [len(t) for t in traced] and len(gens) == 8
+    assert mat.capture_count > 0 and len(gens[2]) > 0
+    for gi, (g, t) in enumerate(zip(gens, traced)):
+        assert g.tobytes() == t.copy_as_array().tobytes(), "generation %d is not bit-identical" % gi
+    assert counts.tolist() == [f.count for f in faces] and counts[1] == 0  # a decomposition face ends at 0

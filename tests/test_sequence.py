@@ -149,3 +149,39 @@ def test_drop_in_trace_rays_with_genuine_reference_objects(engine, name, kw):
     got = [np.ascontiguousarray(t.copy_as_array()).view(native) for t in traced]
     worst = compare_traces(got, [np.ascontiguousarray(w).view(native) for w in want], name + " (genuine reference objects)")
     print("%s with genuine raypier.core objects: %s, worst rel err %.2e" % (name, [len(t) for t in traced], worst))
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("genuine", [False, True])
+def test_drop_in_trace_rays_with_a_decomposition_plane(engine, core, genuine):
+    """ResampleGaussletMaterial (cmaterials.pyx:1766-1831): the face absorbs on the device, and between
+    generations the host hands the captured gausslets to the material's Python callback and appends the
+    result (ctracer.pyx:2274-2280).  Against the oracle's decomposition loop, which is pinned bit-exact to
+    the reference (test_oracle_decomposition_loop_bit_exact_with_reference); with the host mirrors and with
+    genuine raypier.core objects."""
+    from oracle import oracle as O
+    from test_oracle_vs_reference import _relaunch_for
+    lib = core
+    if genuine:
+        lib = O.import_reference("parity")
+        if lib is None:
+            pytest.skip("oracle/_ref is not present on this machine")
+    cfg = configs.build(lib, "resample", n=3000)
+    mat = cfg['decomp_material']
+    mat.eval_func = _relaunch_for(lib, cfg['max_length'])
+    sc = SC.Scene(cfg['face_lists'], cfg['wavelengths'])
+    want, want_counts = O.trace_rays(sc, cfg['rays'], cfg['recursion_limit'], cfg['max_length'],
+                                     decomp={1: lambda a: configs.resample_relaunch(a, cfg['max_length'])})
+    rc = O.reference_collection(lib, cfg['rays'], cfg['wavelengths']) if genuine else \
+        lib.ctracer.GaussletCollection.from_array(cfg['rays'])
+    rc.wavelengths = cfg['wavelengths']
+    traced, all_faces = T.trace_rays(rc, cfg['face_lists'], recursion_limit=cfg['recursion_limit'],
+                                     max_length=cfg['max_length'])
+    assert traced[0] is rc and [len(t) for t in traced] == [len(w) for w in want] and len(traced) == 8
+    assert [f.count for f in all_faces] == want_counts.tolist() and all_faces[1].count == 0
+    assert mat.capture_count == sum(int((w['base_ray']['end_face_idx'] == 1).sum()) for w in want)
+    from raypier_optics_b200 import _abi as A
+    got = [np.ascontiguousarray(t.copy_as_array()).view(A.gausslet_dtype) for t in traced]
+    worst = compare_traces(got, want, "decomposition plane")
+    print("decomposition plane (%s objects): %s, worst rel err %.2e"
+          % ("genuine" if genuine else "mirror", [len(t) for t in traced], worst))

@@ -207,6 +207,10 @@ PARITY_CASES = [
     # between a faceted and a flat mirror (see configs.config_mesh for why no dielectric there)
     ("mesh", dict(n=4000, gausslets=False), None),
     ("mesh", dict(n=1500, gausslets=True), None),
+    # UV patch faces (UVPatchFace over a BezierPatch and a BSplinePatch): facet walk + Newton
+    # iteration on the patch.  The reference module imports with a run-time numpy.math alias (oracle.py)
+    ("uvpatch", dict(n=3000, gausslets=False), None),
+    ("uvpatch", dict(n=1200, gausslets=True), None),
 ]
 
 
