@@ -516,14 +516,17 @@ def run_ours(args):
         # profiles/roofline_latest.json) x rays / kernel time, against the measured DFMA issue peak
         n0 = float(gen_counts[0])
         k_time = {"k_shade": shade_ms_avg, "k_intersect": isect_ms_avg}
+        k_step_ms = {"k_shade": k_ms["shade"][0] / args.steps, "k_intersect": k_ms["intersect"][0] / args.steps}
         per = {}
         for kname in ("k_intersect", "k_shade"):
-            e = fp64.get(kname)
-            if e and k_time[kname] > 0:
-                inst = e["dadd"] + e["dmul"] + e["dfma"]
-                per[kname] = {"fp64_inst_per_ray": inst / e["rays"], "flop_per_ray": (e["dadd"] + e["dmul"] + 2 * e["dfma"]) / e["rays"],
-                              "achieved_tinst_s": inst / e["rays"] * n0 / (k_time[kname] * 1e-3) / 1e12,
-                              "achieved_tflops": (e["dadd"] + e["dmul"] + 2 * e["dfma"]) / e["rays"] * n0 / (k_time[kname] * 1e-3) / 1e12}
+            e = fp64.get(kname)  # instruction totals over ALL launches of that kernel in one trace of e["rays"] source rays
+            if e and k_step_ms[kname] > 0:
+                inst = (e["dadd"] + e["dmul"] + e["dfma"]) / e["rays"] * n0
+                flop = (e["dadd"] + e["dmul"] + 2 * e["dfma"]) / e["rays"] * n0
+                per[kname] = {"fp64_inst_per_source_ray": inst / n0, "flop_per_source_ray": flop / n0,
+                              "achieved_tinst_s": inst / (k_step_ms[kname] * 1e-3) / 1e12,
+                              "achieved_tflops": flop / (k_step_ms[kname] * 1e-3) / 1e12,
+                              "fp64_pipe_pct_ncu": e.get("fp64_pipe_pct")}
         if dominant in per:
             peak_inst = FP64_PEAK_TINST
             roofline = {"bound": "fp64", "kernel": dominant, "achieved": per[dominant]["achieved_tinst_s"], "peak": peak_inst,
@@ -615,6 +618,7 @@ def run_consume(args):
     from raypier_optics_b200 import distributed as rdist
     from raypier_optics_b200.engine import Engine
 
+    numa_cores = rdist.bind_to_gpu_numa(local_rank)  # before any pinned allocation (first touch)
     name = args.workload
     w = WORKLOADS[name]
     n_req = args.rays if args.rays else w["n"]
@@ -806,6 +810,25 @@ def run_consume(args):
                 "step": {"achieved": step_ach, "frac": step_ach / peak,
                          "note": "same bytes over the whole device-timed step (transposition of every chunk included)"}}
 
+    # ---------------- the Python drop-in itself (core.tracer.trace_rays with collection objects in and out:
+    # flatten + upload + trace + download of EVERY generation + container objects), bounded size
+    from raypier_optics_b200.core import tracer as T
+    n_drop = int(min(args.dropin_rays, block_n))
+    cls = core.ctracer.GaussletCollection if is_g else core.ctracer.RayCollection
+
+    def step_dropin():
+        rc_ = cls.from_array(block[:n_drop])
+        rc_.wavelengths = cfg["wavelengths"]
+        traced, _ = T.trace_rays(rc_, cfg["face_lists"], recursion_limit=rl, max_length=ml, device=local_rank)
+        return sum(len(t_) for t_ in traced)
+
+    step_dropin()
+    t0 = time.perf_counter()
+    drop_segs = step_dropin()
+    dropin = {"value": drop_segs / (time.perf_counter() - t0), "unit": "ray-segments/s (this rank)", "rays": n_drop,
+              "api": "raypier_optics_b200.core.tracer.trace_rays (collections in, list of collections out; every "
+                     "generation crosses PCIe through pageable memory)"}
+
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
         kind = cpu_kind()
@@ -829,12 +852,14 @@ def run_consume(args):
         "trace": {"generations": gen_counts, "segments_per_step_per_gpu": int(parents), "chunks_per_step": int(rc.n_chunks),
                   "generation_loop_ms_per_step": trace_ms_max / args.steps, "setup_s": setup_s},
         "value_with_consumers": with_consumers,
+        "e2e_dropin": dropin,
         "e2e": {"value": e2e_value, "unit": "ray-segments/s",
                 "h2d_bytes_per_step": int(n * rec),
                 "d2h_bytes_per_step": int(npt * 48 + 8 * len(gen_counts) + 4 * sc.n_traced_faces),
                 "steps": e2e_steps, "captured_rays_per_step": int(ncap), "detector_points": npt,
                 "field_power": field_power,
                 "host_source_rays": n_host, "passes_per_step": len(passes),
+                "numa_bound_cores": len(numa_cores) if numa_cores else None,
                 "api": "Engine.trace_consume (rpx_trace_consume): pinned host source, chunk %d, capture plane%s, "
                        "D2H = field + counts" % (chunk, " + detector field" if det is not None else ""),
                 "trace_only_value": e2e_only_value},
@@ -978,6 +1003,8 @@ def main():
     ap.add_argument("--e2e-steps", type=int, default=5)
     ap.add_argument("--chunk-rays", type=int, default=0,
                     help="source rays per chunk (0: 131072 for rpx_trace_streamed, 2^20 gausslets / 2^22 rays for rpx_trace_consume)")
+    ap.add_argument("--dropin-rays", type=int, default=200000,
+                    help="source rays of the timed trace_rays drop-in call (consume-mode workloads)")
     ap.add_argument("--detector-grid", type=int, default=16, help="side of the detector grid of the consume-mode e2e arm")
     ap.add_argument("--host-source-gb", type=float, default=0.0,
                     help="cap of the pinned host source of the consume-mode e2e arm (0: 45%% of MemAvailable per local rank)")

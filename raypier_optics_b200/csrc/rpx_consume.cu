@@ -52,13 +52,18 @@ k_select(Soa in, Soa out, unsigned long long* tile_state, uint32_t* tile_counter
     FilterSlots slots;
     filter_positions(sel, tile_state, tile, n_tiles, *d_base, &slots);
     if (threadIdx.x == 0 && tile == n_tiles - 1) *d_next = slots.end;
-    if (!copy) return;
-#pragma unroll 1
-    for (int r = 0; r < RPX_FILTER_R; r++) {
-        if (!sel[r]) continue;
-        const unsigned long long i = first + (unsigned long long)r * RPX_TILE;
-        const unsigned long long pos = slots.pos[r];
-        if (pos >= ocap) continue;  // capacity overrun: reported by the host from *d_next, never written
+    const uint32_t total = (uint32_t)(slots.end - slots.begin);
+    if (!copy || total == 0) return;  // uniform per CTA
+    __shared__ FilterStage st;
+#pragma unroll
+    for (int r = 0; r < RPX_FILTER_R; r++)
+        if (sel[r]) st.src[(uint32_t)(slots.pos[r] - slots.begin)] = (uint16_t)(r * RPX_TILE + threadIdx.x);
+    __syncthreads();
+    const unsigned long long tile0 = (unsigned long long)tile * RPX_FILTER_TILE;
+    for (uint32_t sl = threadIdx.x; sl < total; sl += RPX_TILE) {
+        const unsigned long long i = tile0 + st.src[sl];
+        const unsigned long long pos = slots.begin + sl;
+        if (pos >= ocap) break;  // capacity overrun: reported by the host from *d_next, never written
 #pragma unroll
         for (int fld = 0; fld < NF; fld++) out.f[(unsigned long long)fld * ocap + pos] = in.f[(unsigned long long)fld * cap + i];
 #pragma unroll
@@ -68,7 +73,7 @@ k_select(Soa in, Soa out, unsigned long long* tile_state, uint32_t* tile_counter
             out.u[(unsigned long long)fld * ocap + pos] = v;
         }
         if (GAUSS) {
-#pragma unroll 4
+#pragma unroll 12
             for (int fld = 0; fld < NP; fld++) out.p[(unsigned long long)fld * ocap + pos] = in.p[(unsigned long long)fld * cap + i];
         }
     }

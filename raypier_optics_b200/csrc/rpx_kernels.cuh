@@ -402,7 +402,7 @@ RPX_DEV unsigned long long tile_lookback_grouped(unsigned long long* state, unsi
 #define RPX_FILTER_TILE (RPX_FILTER_R * RPX_TILE)
 struct FilterSlots {
     unsigned long long pos[RPX_FILTER_R];  // output position of the thread's ray of sub-tile r (if kept)
-    unsigned long long end;                // records in the output after this tile
+    unsigned long long begin, end;         // the tile's records are out[begin, end)
 };
 // keep[r]: this thread's ray of sub-tile r is kept.  state: rpx_state_words(n_tiles) zeroed words.
 // Returns false for the threads of a CTA that has nothing to copy.
@@ -449,8 +449,18 @@ RPX_DEV void filter_positions(const bool (&keep)[RPX_FILTER_R], unsigned long lo
     __syncthreads();
 #pragma unroll
     for (int r = 0; r < RPX_FILTER_R; r++) out->pos[r] = base0 + s_prefix + s_off[r * W + warp] + rank[r];
+    out->begin = base0 + s_prefix;
     out->end = base0 + s_prefix + s_total;
 }
+
+// Copy-out of a filter tile: the kept rays' source indices (relative to the tile) are scattered to shared
+// memory by output slot, then ALL threads of the CTA copy row by row with consecutive threads on
+// consecutive output slots -- coalesced stores, every lane busy whatever the hit pattern, and each thread
+// has a dozen independent loads in flight.  (The first version let every kept ray's own thread copy its 86
+// values: 2.4 ms for the 2e6 captured gausslets of a 4e6-gausslet launch, 1.1 TB/s; see profiles/r02_notes.md.)
+struct FilterStage {
+    uint16_t src[RPX_FILTER_TILE];  // slot -> ray index inside the tile
+};
 
 // ------------------------------------------------------------------ k_capture
 // select_ray_intersections / select_gausslet_intersections (ctracer.pyx:1981-2058) for ONE
@@ -491,18 +501,30 @@ k_capture(DevScene S, Soa in, Soa out, unsigned long long* tile_state, uint32_t*
     FilterSlots slots;
     filter_positions(hit, tile_state, tile, n_tiles, *d_base, &slots);
     if (threadIdx.x == 0 && tile == n_tiles - 1) *d_next = slots.end;
-#pragma unroll 1
-    for (int r = 0; r < RPX_FILTER_R; r++) {
-        if (!hit[r]) continue;
-        const unsigned long long i = first + (unsigned long long)r * RPX_TILE;
-        const unsigned long long pos = slots.pos[r];
+    const uint32_t total = (uint32_t)(slots.end - slots.begin);
+    if (total == 0) return;  // uniform per CTA
+    __shared__ FilterStage st;
+    __shared__ double s_len[RPX_FILTER_TILE];
+    __shared__ uint32_t s_face[RPX_FILTER_TILE];
+#pragma unroll
+    for (int r = 0; r < RPX_FILTER_R; r++)
+        if (hit[r]) {
+            const uint32_t ls = (uint32_t)(slots.pos[r] - slots.begin);
+            st.src[ls] = (uint16_t)(r * RPX_TILE + threadIdx.x);
+            s_len[ls] = len[r];
+            s_face[ls] = face_ids ? face_ids[face[r]] : face[r];
+        }
+    __syncthreads();
+    const unsigned long long tile0 = (unsigned long long)tile * RPX_FILTER_TILE;
+    for (uint32_t sl = threadIdx.x; sl < total; sl += RPX_TILE) {
+        const unsigned long long i = tile0 + st.src[sl];
+        const unsigned long long pos = slots.begin + sl;
 #pragma unroll
         for (int fld = 0; fld < NF; fld++)
-            out.f[(unsigned long long)fld * ocap + pos] = (fld == F_LEN) ? len[r] : in.f[(unsigned long long)fld * cap + i];
+            out.f[(unsigned long long)fld * ocap + pos] = (fld == F_LEN) ? s_len[sl] : in.f[(unsigned long long)fld * cap + i];
 #pragma unroll
         for (int fld = 0; fld < NU; fld++) {
-            uint32_t v = in.u[(unsigned long long)fld * cap + i];
-            if (fld == U_ENDFACE) v = face_ids ? face_ids[face[r]] : face[r];
+            uint32_t v = (fld == U_ENDFACE) ? s_face[sl] : in.u[(unsigned long long)fld * cap + i];
             if (fld == U_WL) {
                 v += wl_offset;
                 if (wl_map) v = wl_map[v];
@@ -510,7 +532,7 @@ k_capture(DevScene S, Soa in, Soa out, unsigned long long* tile_state, uint32_t*
             out.u[(unsigned long long)fld * ocap + pos] = v;
         }
         if (GAUSS) {
-#pragma unroll 4
+#pragma unroll 12
             for (int fld = 0; fld < NP; fld++)
                 out.p[(unsigned long long)fld * ocap + pos] = in.p[(unsigned long long)fld * cap + i];
         }
@@ -648,16 +670,6 @@ RPX_DEV void stage_child(double* cs, uint32_t* cu, uint32_t slot, const Kids& k,
 #ifndef RPX_BULK_PREFETCH
 #define RPX_BULK_PREFETCH 1
 #endif
-// Gausslets: the origins and directions of the six parabasal rays of every hit parent (36 doubles per
-// ray, 36 KB per tile) are fetched with cp.async (LDGSTS, no register, no scoreboard) into a per-thread
-// column of shared memory while the base ray's orientation / material code runs; both parabasal loops
-// then read shared memory.  Without it the first loop is six dependent global round trips (the loads
-// of ray j+1 are guarded by the hit test of ray j) and the second loop re-reads everything through L2.
-#ifndef RPX_PARA_SMEM
-#define RPX_PARA_SMEM 0
-#endif
-#define RPX_PARA_ROWS 36
-#define RPX_PARA_SMEM_BYTES (RPX_PARA_SMEM ? RPX_PARA_ROWS * RPX_TILE * 8 : 0)
 #ifndef RPX_MIN_BLOCKS_G
 #define RPX_MIN_BLOCKS_G RPX_MIN_BLOCKS
 #endif
@@ -684,11 +696,7 @@ k_shade(DevScene S, Soa in, Soa out, double max_length, unsigned long long* tile
     double* cs = reinterpret_cast<double*>(smem);
     uint32_t* cu = reinterpret_cast<uint32_t*>(smem + RPX_SLOTS * NF * 8);
 #endif
-    // gausslets: [child staging][parabasal columns][scene copy]
-    constexpr bool kParaSmem = GAUSS && RPX_PARA_SMEM;
-    double* ps = reinterpret_cast<double*>(smem + RPX_STAGE_BYTES) + threadIdx.x;  // ps[row * RPX_TILE]
-    (void)ps;
-    stage_scene<SS>(S, smem + RPX_STAGE_BYTES + (GAUSS ? RPX_PARA_SMEM_BYTES : 0));  // once per (persistent) CTA
+    stage_scene<SS>(S, smem + RPX_STAGE_BYTES);  // once per (persistent) CTA
     const unsigned long long n_in = n_dev ? *n_dev : in.n;
     const uint32_t n_tiles_real = (uint32_t)((n_in + RPX_TILE - 1) / RPX_TILE);
     constexpr bool kGrouped = RPX_LOOKBACK_GROUPS && (!GAUSS || RPX_GROUPS_GAUSS);
@@ -731,20 +739,6 @@ k_shade(DevScene S, Soa in, Soa out, double max_length, unsigned long long* tile
         r.ident = ident = in.u[U_IDENT * cap + i];
         r.type = in.u[U_TYPE * cap + i];
         hit = (face_idx != RPX_NO_FACE);
-        if (kParaSmem && hit) {
-            // rows 0..35 = (origin xyz, direction xyz) of parabasal ray 0..5; own column only, so the
-            // only synchronisation is this thread's own wait_group below
-            const unsigned sbase = (unsigned)__cvta_generic_to_shared(ps);
-#pragma unroll
-            for (int j = 0; j < RPX_NPARA; j++) {
-#pragma unroll
-                for (int c = 0; c < 6; c++)
-                    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(sbase + (unsigned)((j * 6 + c) * RPX_TILE * 8)),
-                                 "l"(in.p + (unsigned long long)(j * NPF + c) * cap + i)
-                                 : "memory");
-            }
-            asm volatile("cp.async.commit_group;" ::: "memory");
-        }
     }
     if (hit) {
         const rpx_face* face = &S.faces[face_idx];
@@ -775,17 +769,13 @@ k_shade(DevScene S, Soa in, Soa out, double max_length, unsigned long long* tile
             // must hit the SAME face (is_base_ray = 0); any miss drops the children (Q16).
             const rpx_face_set* fs = &S.sets[face->face_set];
             bool ok = true;
-            if (kParaSmem) asm volatile("cp.async.wait_group 0;" ::: "memory");
 #pragma unroll
             for (int j = 0; j < RPX_NPARA; j++) {
                 plen[j] = max_length;
                 if (ok) {
                     const double* pp = in.p + (unsigned long long)(j * NPF) * cap + i;
-                    const double* sp = ps + j * 6 * RPX_TILE;
-                    vec3 po = kParaSmem ? v3(sp[0], sp[RPX_TILE], sp[2 * RPX_TILE])
-                                        : v3(pp[(P_OX + 0) * cap], pp[(P_OX + 1) * cap], pp[(P_OX + 2) * cap]);
-                    vec3 pd = kParaSmem ? v3(sp[3 * RPX_TILE], sp[4 * RPX_TILE], sp[5 * RPX_TILE])
-                                        : v3(pp[(P_DX + 0) * cap], pp[(P_DX + 1) * cap], pp[(P_DX + 2) * cap]);
+                    vec3 po = v3(pp[(P_OX + 0) * cap], pp[(P_OX + 1) * cap], pp[(P_OX + 2) * cap]);
+                    vec3 pd = v3(pp[(P_DX + 0) * cap], pp[(P_DX + 1) * cap], pp[(P_DX + 2) * cap]);
                     vec3 ray_end = po + pd * max_length;
                     vec3 p1 = transform_pt(fs->inv_trans.m, po);
                     vec3 p2 = transform_pt(fs->inv_trans.m, ray_end);
@@ -994,11 +984,8 @@ k_shade(DevScene S, Soa in, Soa out, double max_length, unsigned long long* tile
 #pragma unroll
         for (int j = 0; j < RPX_NPARA; j++) {
             const double* pp = in.p + (unsigned long long)(j * NPF) * cap + i;
-            const double* sp = ps + j * 6 * RPX_TILE;
-            vec3 po = kParaSmem ? v3(sp[0], sp[RPX_TILE], sp[2 * RPX_TILE])
-                                : v3(pp[(P_OX + 0) * cap], pp[(P_OX + 1) * cap], pp[(P_OX + 2) * cap]);
-            vec3 pd = kParaSmem ? v3(sp[3 * RPX_TILE], sp[4 * RPX_TILE], sp[5 * RPX_TILE])
-                                : v3(pp[(P_DX + 0) * cap], pp[(P_DX + 1) * cap], pp[(P_DX + 2) * cap]);
+            vec3 po = v3(pp[(P_OX + 0) * cap], pp[(P_OX + 1) * cap], pp[(P_OX + 2) * cap]);
+            vec3 pd = v3(pp[(P_DX + 0) * cap], pp[(P_DX + 1) * cap], pp[(P_DX + 2) * cap]);
             vec3 ppoint = po + pd * plen[j];
             vec3 pn, pt;
             compute_orientation<FC>(S, face, ppoint, &pn, &pt, FC == RPX_FC_MESH ? &paux[j] : nullptr);

@@ -44,7 +44,7 @@ cudaError_t RPX_CAT(RPX_I_GAUSS, RPX_I_FC, RPX_I_MM)(cudaStream_t st, const Shad
     };
     static DevState states[RPX_MAX_DEVICES];
     static std::mutex mu;
-    const int dyn = RPX_STAGE_BYTES + (RPX_I_GAUSS ? RPX_PARA_SMEM_BYTES : 0) + (RPX_I_SS ? a.smem_bytes : 0);
+    const int dyn = RPX_STAGE_BYTES + (RPX_I_SS ? a.smem_bytes : 0);
     auto kern = k_shade<(RPX_I_GAUSS != 0), RPX_I_FC, kMask, (RPX_I_SS != 0)>;
     int dev = 0;
     cudaError_t e;
@@ -56,7 +56,7 @@ cudaError_t RPX_CAT(RPX_I_GAUSS, RPX_I_FC, RPX_I_MM)(cudaStream_t st, const Shad
         DevState& ds = states[dev];
         if (!ds.attr_set) {
             e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                     RPX_STAGE_BYTES + (RPX_I_GAUSS ? RPX_PARA_SMEM_BYTES : 0) + 40 * 1024);
+                                     RPX_STAGE_BYTES + 40 * 1024);
             if (e != cudaSuccess) return e;
             ds.attr_set = true;
         }

@@ -229,3 +229,32 @@ def allreduce_detector(engine, detector, group=None):
     dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)
     torch.cuda.current_stream(dev).synchronize()  # the library reads the buffer on its own stream next
     return t
+
+
+def bind_to_gpu_numa(device_index):
+    """Pin this process (and, by first-touch, the pinned staging memory it allocates next) to the CPU cores
+    of the NUMA node the GPU hangs off: with one rank per GPU streaming its source through pinned host
+    memory, a rank on the wrong socket moves every byte across the inter-socket link.  Reads
+    /sys/bus/pci/devices/<bus id>/local_cpulist; returns the core list, or None when the topology is not
+    visible (containers often hide it) or has a single node -- never an error."""
+    import os
+    try:
+        import torch
+        bus = torch.cuda.get_device_properties(device_index).pci_bus_id
+        dom = getattr(torch.cuda.get_device_properties(device_index), "pci_domain_id", 0)
+        dev = getattr(torch.cuda.get_device_properties(device_index), "pci_device_id", 0)
+        path = "/sys/bus/pci/devices/%04x:%02x:%02x.0/local_cpulist" % (dom, bus, dev)
+        spec = open(path).read().strip()
+        cores = []
+        for part in spec.split(","):
+            if not part:
+                continue
+            lo, _, hi = part.partition("-")
+            cores.extend(range(int(lo), int(hi or lo) + 1))
+        allowed = sorted(set(cores) & set(os.sched_getaffinity(0)))
+        if not allowed or len(allowed) == len(os.sched_getaffinity(0)):
+            return None
+        os.sched_setaffinity(0, allowed)
+        return allowed
+    except Exception:
+        return None

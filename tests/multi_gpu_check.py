@@ -6,6 +6,10 @@
 Every rank traces its contiguous shard of the Michelson gausslets on its own GPU, captures the
 output port on the device, and the detector field of the sharded gausslets is reduced with one
 NCCL all-reduce (distributed.field_sharded).  Rank 0 repeats everything on one GPU and compares.
+Then the round-2 paths: the streamed trace with device-side consumers (rpx_trace_consume) feeding a
+detector that is all-reduced IN PLACE in the library's device buffer (distributed.allreduce_detector),
+and the device-resident NCCL gather of the terminal rays (distributed.gather_terminal) with
+its measured rate.
 """
 import os
 import sys
@@ -68,6 +72,41 @@ def main():
         print("multi_gpu_check: world=%d segments %d/%d captured %d/%d face counts %s field rel err %.2e -> %s"
               % (world, int(t[0]), segs1, int(t[1]), len(g1), fct.cpu().numpy().tolist() == fc1.tolist(), err,
                  "OK" if ok else "FAIL"))
+    # ---- streamed trace + consumers, detector all-reduced in place (no host bounce)
+    det = eng.detector(pts[:1024], cfg["wavelengths"])
+    out = eng.trace_consume(np.ascontiguousarray(mine), cfg["max_length"], cfg["recursion_limit"], chunk_rays=4096,
+                            terminal=True, terminal_capacity=8 * len(mine) + 64, capture=True, detector=det)
+    rd.allreduce_detector(eng, det)
+    E2 = det.read()
+    tt = torch.tensor([out.segments, out.n_captured, out.n_terminal], dtype=torch.int64, device="cuda")
+    dist.all_reduce(tt)
+    # ---- device-resident gather of the terminal rays (all ranks get all of them), timed
+    torch.cuda.synchronize()
+    dist.barrier()
+    import time
+    t0 = time.perf_counter()
+    allterm, counts = rd.gather_terminal(eng, out.terminal, dst=None)
+    torch.cuda.synchronize()
+    dt = time.perf_counter() - t0
+    n_term_all = len(allterm)
+    idents = eng.download(allterm)['base_ray']['ray_ident']
+    allterm.free()
+    out.free()
+    det.free()
+    if rank == 0:
+        err2 = float(np.abs(E2 - E1[:1024]).max() / np.abs(E1).max())
+        res1 = eng.trace(np.ascontiguousarray(cfg["rays"]), cfg["max_length"], cfg["recursion_limit"])
+        term1, tcounts = eng.select_terminal(res1.device_generations(), True)
+        want_idents = np.sort(eng.download(term1)['base_ray']['ray_ident'])
+        term1.free()
+        res1.free()
+        ok2 = (int(tt[0]) == segs1 and int(tt[1]) == len(g1) and int(tt[2]) == n_term_all == len(want_idents)
+               and sum(counts) == n_term_all and np.array_equal(np.sort(idents), want_idents) and err2 < 1e-12)
+        ok = ok and ok2
+        print("multi_gpu_check: consume path segments %d captured %d terminal %d (per rank %s), detector all-reduced "
+              "in place rel err %.2e, terminal gather %.1f MB in %.2f ms = %.1f GB/s into every rank -> %s"
+              % (int(tt[0]), int(tt[1]), int(tt[2]), counts, err2, n_term_all * 668 / 1e6, dt * 1e3,
+                 n_term_all * 668 / dt / 1e9, "OK" if ok2 else "FAIL"))
     dist.barrier()
     dist.destroy_process_group()
     return 0 if ok else 1
