@@ -58,16 +58,7 @@ def _wrap_generations(input_rays, arrays, wavelengths):
     cls = type(input_rays)
     native = getattr(cls, "_dtype", None) is not None  # this package's host mirrors
 
-    def ref_array(arr):
-        if native:
-            return arr
-        # genuine reference collection: from_array checks the identity of its own dtype object
-        mod = __import__(cls.__module__, fromlist=["ray_dtype"])
-        ref_dtype = mod.gausslet_dtype if arr.dtype == A.gausslet_dtype else mod.ray_dtype
-        a = np.empty(arr.shape[0], dtype=ref_dtype)
-        a.view(np.uint8)[:] = arr.view(np.uint8)
-        return a
-
+    ref_array = _ref_array_for(cls)
     out = []
     prev = None
     for g, arr in enumerate(arrays):
@@ -75,7 +66,11 @@ def _wrap_generations(input_rays, arrays, wavelengths):
             _assign_in_place(input_rays, arr, ref_array)
             rc = input_rays
         else:
-            rc = cls.from_array(ref_array(arr))
+            if native:  # the array came fresh from the device: adopt it, no second copy
+                rc = cls(0)
+                rc._assign_array(arr)
+            else:
+                rc = cls.from_array(ref_array(arr))
             rc.wavelengths = wavelengths
             rc.parent = prev
         out.append(rc)
@@ -90,10 +85,10 @@ def _ref_array_for(cls):
     mod = __import__(cls.__module__, fromlist=["ray_dtype"])
 
     def conv(arr):
+        # from_array checks the IDENTITY of the reference's own dtype object (ctracer.pyx:1150): a view with
+        # that very object passes it without copying (the layouts are byte-identical, tests/test_abi.py)
         ref_dtype = mod.gausslet_dtype if arr.dtype.itemsize == A.gausslet_dtype.itemsize else mod.ray_dtype
-        a = np.empty(arr.shape[0], dtype=ref_dtype)
-        a.view(np.uint8)[:] = np.ascontiguousarray(arr).view(np.uint8)
-        return a
+        return np.ascontiguousarray(arr).view(ref_dtype)
     return conv
 
 

@@ -65,6 +65,7 @@ struct rpx_ctx {
     unsigned long long* pipe_state;  // tile-state slices of a pipelined trace, zeroed ahead of use
     size_t pipe_state_cap;           // tiles
     uint32_t* pipe_counters;         // one ticket counter per generation
+    uint32_t* pipe_hits;             // pipe_hits[g] != 0: some ray of generation g hit a face (set by the launch that built it)
     // event pool
     std::vector<cudaEvent_t> ev_pool;
     size_t ev_used;

@@ -673,11 +673,37 @@ RPX_DEV void stage_child(double* cs, uint32_t* cu, uint32_t slot, const Kids& k,
 #ifndef RPX_MIN_BLOCKS_G
 #define RPX_MIN_BLOCKS_G RPX_MIN_BLOCKS
 #endif
+// Gausslet tiles take their next ticket at the END of the current tile (plain rays: at its start, so that the
+// next tile's rows can be L2-prefetched).  A gausslet tile is ~100 us long: a CTA that already holds ticket T
+// while it still works on its previous tile keeps every tile > T polling in the look-back for T's aggregate
+// (ncu: 20 % of the executed instructions of k_shade<GAUSS> were that poll, and launches fell into a slow mode
+// -- 592 / 1161 / 2334 us instead of 487 / 924 / 1821 us for the 1e6 / 2e6 / 4e6-gausslet generations of the
+// Michelson trace).  With the late ticket a tile publishes its aggregate one material phase after taking its
+// ticket, before any later tile can reach its look-back.  Measured (profiles/r02_notes.md): +9 % on one box,
+// neutral on another, never the slow mode under ncu.
+#ifndef RPX_TICKET_END_G
+#define RPX_TICKET_END_G 1
+#endif
 template <bool GAUSS, int FC, uint32_t MM, bool SS>
 __global__ void __launch_bounds__(RPX_TILE, GAUSS ? RPX_MIN_BLOCKS_G : RPX_MIN_BLOCKS)
 k_shade(DevScene S, Soa in, Soa out, double max_length, unsigned long long* tile_state,
         uint32_t* tile_counter, unsigned long long* d_count, uint32_t* face_counts, uint32_t n_tiles,
-        int ahead_face, const unsigned long long* n_dev, unsigned long long* h_count) {
+        int ahead_face, const unsigned long long* n_dev, unsigned long long* h_count, const uint32_t* hits_in,
+        uint32_t* hits_out) {
+    // hits_in != NULL: set by the launch that built this generation iff its trace-ahead found ANY hit.  A
+    // generation nobody hit anything in (the last one of every finite trace: 15 % of the achromat and
+    // Michelson steps went into reading it, ncu r02_div_*.csv) has no child, no count and no write-back
+    // left to produce: the whole grid leaves at once.  hits_out: the same flag for the generation built here.
+    if (hits_in != nullptr && *hits_in == 0u) {
+        if (blockIdx.x == 0 && threadIdx.x == 0) {
+            *d_count = 0ull;
+            if (h_count) {
+                *h_count = 0ull;
+                __threadfence_system();
+            }
+        }
+        return;
+    }
     // n_dev != NULL: the parent count is not known on the host yet (the launch was enqueued
     // before the previous generation's kernel finished): the grid covers an upper bound and the
     // real count is read here; surplus CTAs leave at once.
@@ -712,7 +738,9 @@ k_shade(DevScene S, Soa in, Soa out, double max_length, unsigned long long* tile
     // (s_tile is next written by thread 0 after the barrier inside the block scan: no barrier needed here)
     uint32_t next_tile = 0;
     // take the NEXT ticket now (its latency hides behind this tile's work) ...
-    if (threadIdx.x == 0) next_tile = atomicAdd(tile_counter, 1u);
+    // (gausslets: at the END of the tile, see RPX_TICKET_END_G)
+    constexpr bool kLateTicket = GAUSS && RPX_TICKET_END_G;
+    if (threadIdx.x == 0 && !kLateTicket) next_tile = atomicAdd(tile_counter, 1u);
 
     Kids k;
     k.has_a = false;
@@ -809,7 +837,7 @@ k_shade(DevScene S, Soa in, Soa out, double max_length, unsigned long long* tile
             tile_publish_grouped(tile_state, tile_state + n_tiles, tile, total);
         else
             tile_publish(tile_state, tile, total);
-        s_tile = next_tile;  // ... and hand it to the CTA (read after the next barrier)
+        if (!kLateTicket) s_tile = next_tile;  // ... and hand it to the CTA (read after the next barrier)
     }
     // ---- 3. stage children in emission order (reflected, then transmitted)
     const uint32_t slot_a = local, slot_b = local + (k.has_a ? 1u : 0u);
@@ -824,7 +852,7 @@ k_shade(DevScene S, Soa in, Soa out, double max_length, unsigned long long* tile
     const uint32_t own_a = slot_a, own_b = slot_b;
     __syncthreads();
     {   // pull the next tile's parent records towards L2 while this tile computes
-        const uint32_t nt = s_tile;
+        const uint32_t nt = kLateTicket ? n_tiles_real : s_tile;  // late ticket: the next tile is not known yet
 #if RPX_BULK_PREFETCH
         // one bulk L2 prefetch per field row (1 KB of doubles / 512 B of u32), issued by 22 threads of
         // the LAST warp (warp 0 runs the look-back): 22 instructions per tile instead of ~90
@@ -862,6 +890,7 @@ k_shade(DevScene S, Soa in, Soa out, double max_length, unsigned long long* tile
         }
     }
     // ---- 4. trace ahead
+    bool any_hit = false;
     if (ahead_face != -2) {
         for (uint32_t slot = threadIdx.x; slot < total; slot += RPX_TILE) {
 #if RPX_LEAN_STAGE
@@ -878,6 +907,7 @@ k_shade(DevScene S, Soa in, Soa out, double max_length, unsigned long long* tile
             double len;
             uint32_t face;
             nearest_hit<FC>(S, o, d, max_length, ahead_face, &len, &face);
+            any_hit = any_hit || (face != RPX_NO_FACE);
 #if RPX_LEAN_STAGE
             L.cf[LC_LEN * RPX_SLOTS + slot] = len;
             L.cu[LCU_ENDFACE * RPX_SLOTS + slot] = face;
@@ -927,7 +957,8 @@ k_shade(DevScene S, Soa in, Soa out, double max_length, unsigned long long* tile
             }
         }
     }
-    __syncthreads();
+    const int tile_hit = __syncthreads_or(any_hit ? 1 : 0);
+    if (threadIdx.x == 0 && tile_hit && hits_out != nullptr) *hits_out = 1u;  // idempotent, one store per tile
     const unsigned long long base = s_prefix;
     // ---- 6. coalesced copy-out: slot == consecutive addresses.  Two explicit passes (a tile has
     // at most 2 * RPX_TILE children), each a straight line of 26 independent LDS -> STG pairs.
@@ -1008,6 +1039,7 @@ k_shade(DevScene S, Soa in, Soa out, double max_length, unsigned long long* tile
             }
         }
     }
+    if (kLateTicket && threadIdx.x == 0) s_tile = atomicAdd(tile_counter, 1u);
   }  // persistent tile loop
 }
 

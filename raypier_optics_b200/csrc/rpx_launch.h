@@ -23,6 +23,8 @@ struct ShadeArgs {
     int ahead_face;  // -1 all faces, >= 0 one face, -2 no trace-ahead (see k_shade)
     const unsigned long long* n_dev;  // device-resident parent count (pipelined launches) or NULL
     unsigned long long* h_count;      // mapped host slot for len(new_rays) or NULL
+    const uint32_t* hits_in = nullptr;  // "some ray of this generation hit something" (NULL: unknown, run)
+    uint32_t* hits_out = nullptr;       // the same flag for the generation built by this launch (NULL: not wanted)
 };
 
 // one launcher per compiled variant: g = gausslets, f = face class, m = material mask index

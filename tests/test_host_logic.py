@@ -68,15 +68,37 @@ def test_zernike_tape_matches_recursive_oracle(core):
 
 
 def test_unsupported_types_are_reported(core):
-    class UVPatchFace(core.ctracer.Face):
+    """Content the flattener does not know is reported, never skipped."""
+    class HolographicFace(core.ctracer.Face):          # no such class in raypier.core
         pass
     fl = core.ctracer.FaceList()
-    fl.faces = [UVPatchFace()]
+    fl.faces = [HolographicFace()]
     with pytest.raises(SC.UnsupportedSceneError):
         SC.Scene([fl], np.array([1.0]))
-    fl.faces = [core.cfaces.CircularFace(material=core.cmaterials.ResampleGaussletMaterial())]
+
+    class MagicMaterial(core.ctracer.InterfaceMaterial):
+        pass
+    fl.faces = [core.cfaces.CircularFace(material=MagicMaterial())]
     with pytest.raises(SC.UnsupportedSceneError):
         SC.Scene([fl], np.array([1.0]))
+
+    # a UVPatchFace whose mesh resolution cannot be read (a genuine raypier one keeps u_res / v_res private)
+    cfg = configs.build(core, "uvpatch", n=4)
+    face = cfg['face_lists'][0].faces[0]
+    face.u_res = None
+    face.owner.u_res = None
+    with pytest.raises(SC.UnsupportedSceneError):
+        SC.Scene(cfg['face_lists'], cfg['wavelengths'])
+
+
+def test_decomposition_material_flattens_as_an_absorber(core):
+    """ResampleGaussletMaterial: eval_child_ray_c only captures (cmaterials.pyx:1808-1821), so the device
+    sees an absorber; the callback runs on the host between generations (core/tracer.py)."""
+    fl = core.ctracer.FaceList()
+    fl.faces = [core.cfaces.CircularFace(material=core.cmaterials.ResampleGaussletMaterial(eval_func=lambda gc: gc))]
+    sc = SC.Scene([fl], np.array([1.0]))
+    assert sc.materials[0]['type'] == A.MAT_OPAQUE
+    assert fl.faces[0].material.is_decomp_material() and fl.faces[0].material.capture_count == 0
 
 
 def test_subclasses_resolve_through_mro(core):
