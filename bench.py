@@ -573,13 +573,24 @@ def run_ours(args):
 
 
 def _mem_available_bytes():
+    """Host memory this process may count on: MemAvailable, capped by the container's cgroup limit."""
+    avail = 64 << 30
     try:
         for line in open("/proc/meminfo"):
             if line.startswith("MemAvailable:"):
-                return int(line.split()[1]) * 1024
+                avail = int(line.split()[1]) * 1024
     except Exception:
         pass
-    return 64 << 30
+    for path, used in (("/sys/fs/cgroup/memory.max", "/sys/fs/cgroup/memory.current"),
+                       ("/sys/fs/cgroup/memory/memory.limit_in_bytes", "/sys/fs/cgroup/memory/memory.usage_in_bytes")):
+        try:
+            lim = open(path).read().strip()
+            if lim.isdigit() and int(lim) < (1 << 60):
+                cur = int(open(used).read().strip())
+                avail = min(avail, max(int(lim) - cur, 0))
+        except Exception:
+            pass
+    return avail
 
 
 def _fill_repeating(dst_u8, block_u8, threads=8):
@@ -736,7 +747,14 @@ def run_consume(args):
     avail = _mem_available_bytes()
     budget = args.host_source_gb * (1 << 30) if args.host_source_gb else 0.45 * avail / max(local_world, 1)
     n_host = int(max(min(n, budget // rec), min(n, chunk)))
-    pinned = eng.pinned_empty(n_host, block.dtype)
+    pinned = None
+    while pinned is None:
+        try:
+            pinned = eng.pinned_empty(n_host, block.dtype)
+        except MemoryError:  # page-locking refused (ulimit / cgroup): stream a smaller host source in more passes
+            if n_host <= chunk:
+                raise
+            n_host = max(n_host // 2, min(n, chunk))
     _fill_repeating(pinned.view(np.uint8).reshape(-1), block.view(np.uint8).reshape(-1))
     passes = [(lo, min(lo + n_host, n)) for lo in range(0, n, n_host)]
     setup_s = time.perf_counter() - t_setup

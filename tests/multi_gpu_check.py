@@ -80,10 +80,12 @@ def main():
     E2 = det.read()
     tt = torch.tensor([out.segments, out.n_captured, out.n_terminal], dtype=torch.int64, device="cuda")
     dist.all_reduce(tt)
-    # ---- device-resident gather of the terminal rays (all ranks get all of them), timed
+    # ---- device-resident gather of the terminal rays (all ranks get all of them); the second call is timed
+    import time
+    warm, _ = rd.gather_terminal(eng, out.terminal, dst=None)
+    warm.free()
     torch.cuda.synchronize()
     dist.barrier()
-    import time
     t0 = time.perf_counter()
     allterm, counts = rd.gather_terminal(eng, out.terminal, dst=None)
     torch.cuda.synchronize()
@@ -107,6 +109,25 @@ def main():
               "in place rel err %.2e, terminal gather %.1f MB in %.2f ms = %.1f GB/s into every rank -> %s"
               % (int(tt[0]), int(tt[1]), int(tt[2]), counts, err2, n_term_all * 668 / 1e6, dt * 1e3,
                  n_term_all * 668 / dt / 1e9, "OK" if ok2 else "FAIL"))
+    # ---- the same gather at a size where the transfer dominates: 5e5 gausslets per rank -> 1e6 terminal rays each
+    big = configs.build(core, "config5", n=500000, gausslets=True, seed=11 + rank)
+    outb = eng.trace_consume(np.ascontiguousarray(big["rays"]), big["max_length"], big["recursion_limit"], terminal=True,
+                             terminal_capacity=2 * len(big["rays"]) + 64)
+    torch.cuda.synchronize()
+    dist.barrier()
+    t0 = time.perf_counter()
+    allb, countsb = rd.gather_terminal(eng, outb.terminal, dst=None)
+    torch.cuda.synchronize()
+    dtb = time.perf_counter() - t0
+    nb = len(allb)
+    allb.free()
+    outb.free()
+    if rank == 0:
+        okb = nb == sum(countsb) == world * 2 * len(big["rays"])
+        ok = ok and okb
+        print("multi_gpu_check: terminal gather of %d gausslets (%.0f MB into every rank, %d ranks) in %.1f ms = %.1f GB/s "
+              "received per rank (export + NCCL all-gather + import) -> %s"
+              % (nb, nb * 668 / 1e6, world, dtb * 1e3, nb * 668 / dtb / 1e9, "OK" if okb else "FAIL"))
     dist.barrier()
     dist.destroy_process_group()
     return 0 if ok else 1

@@ -181,3 +181,45 @@ def test_trace_consume_matches_oracle(engine, core, name, kw, rl, chunk, plane, 
     with pytest.raises(RpxError):
         engine.trace_consume(src, cfg['max_length'], cfg['recursion_limit'], n=len(rays), is_gausslet=is_g,
                              chunk_rays=chunk, capture=True, captured_capacity=max(len(want_cap) // 3, 1))
+
+
+def test_trace_consume_edge_cases(engine, core):
+    """Empty and ragged sources, a chunk larger than the source, and the misuse errors of rpx_trace_consume."""
+    from raypier_optics_b200._lib import RpxError
+    cfg = configs.build(core, "config1", n=1000)
+    sc = SC.Scene(cfg['face_lists'], cfg['wavelengths'])
+    engine.set_scene(sc)
+    rays = np.ascontiguousarray(cfg['rays'])
+    empty = engine.trace_consume(rays[:0], cfg['max_length'], cfg['recursion_limit'], terminal=True)
+    assert empty.counts == [] and empty.n_chunks == 0 and empty.n_terminal == 0 and empty.segments == 0
+    for n, chunk in ((1, 0), (129, 128), (1000, 4096), (1000, 1)):
+        if chunk == 1 and n > 64:
+            n = 64  # one ray per chunk: 64 chunks
+        r = engine.trace_consume(np.ascontiguousarray(rays[:n]), cfg['max_length'], cfg['recursion_limit'], chunk_rays=chunk,
+                                 terminal=True, terminal_capacity=n + 8)
+        assert r.counts == [n, n, n] and r.n_terminal == n == len(r.terminal)   # every ray leaves through the lens
+        got = engine.download(r.terminal)
+        assert np.all(got['end_face_idx'] == A.NO_FACE) and np.array_equal(np.sort(got['ray_ident']), np.arange(n))
+        r.free()
+    # terminal faces: rays ending on face 1 (the second lens surface) are generation 1
+    r = engine.trace_consume(rays, cfg['max_length'], cfg['recursion_limit'], terminal_faces=[1], terminal_capacity=2000)
+    assert r.n_terminal == 1000 and np.all(engine.download(r.terminal)['end_face_idx'] == 1)
+    r.free()
+    with pytest.raises(RpxError):   # a detector needs gausslets
+        det = engine.detector(np.zeros((4, 3)), cfg['wavelengths'])
+        try:
+            engine.trace_consume(rays, cfg['max_length'], cfg['recursion_limit'], detector=det)
+        finally:
+            det.free()
+    # zero-length export / import
+    import torch
+    res = engine.trace(rays, cfg['max_length'], cfg['recursion_limit'])
+    dev, counts = engine.select_terminal(res.device_generations()[:1], False, unterminated=True)  # all of generation 0 hit the lens
+    res.free()
+    assert counts == [0] and len(dev) == 0
+    t = torch.empty(8, dtype=torch.uint8, device="cuda")
+    engine.export_device(dev, t.data_ptr(), 0)
+    back = engine.import_device(t.data_ptr(), 0, False)
+    assert len(back) == 0
+    back.free()
+    dev.free()
