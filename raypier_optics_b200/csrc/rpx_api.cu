@@ -104,6 +104,7 @@ extern "C" int rpx_init(int device, rpx_ctx** out_ctx) {
         (e = cudaHostGetDevicePointer(&ctx->h_counts_dev, ctx->h_counts, 0)) != cudaSuccess ||
         (e = cudaMalloc(&ctx->pipe_counters, sizeof(uint32_t) * RPX_MAX_PIPE_GENS)) != cudaSuccess ||
         (e = cudaMalloc(&ctx->pipe_hits, sizeof(uint32_t) * RPX_MAX_PIPE_GENS)) != cudaSuccess ||
+        (e = cudaMalloc(&ctx->pipe_miss, sizeof(uint32_t) * RPX_MAX_PIPE_GENS)) != cudaSuccess ||
         (e = cudaMalloc(&ctx->pipe_state, sizeof(unsigned long long) * RPX_PIPE_STATE_TILES)) != cudaSuccess) {
         fail(nullptr, RPX_ERR_CUDA, "context scratch allocation failed: %s", cudaGetErrorString(e));
         delete ctx;
@@ -128,6 +129,7 @@ extern "C" void rpx_shutdown(rpx_ctx* ctx) {
     cudaFree(ctx->d_counts);
     cudaFree(ctx->pipe_counters);
     cudaFree(ctx->pipe_hits);
+    cudaFree(ctx->pipe_miss);
     cudaFree(ctx->pipe_state);
     cudaFreeHost(ctx->h_counts);
     cudaFree(ctx->d_count);
@@ -583,6 +585,7 @@ static int trace_pipelined(rpx_ctx* ctx, rpx_rays* rays, double ml, int recursio
     CUP(cudaMemsetAsync(ctx->d_counts, 0, sizeof(unsigned long long) * RPX_MAX_PIPE_GENS, st));
     CUP(cudaMemsetAsync(ctx->pipe_counters, 0, sizeof(uint32_t) * RPX_MAX_PIPE_GENS, st));
     CUP(cudaMemsetAsync(ctx->pipe_hits, 0, sizeof(uint32_t) * RPX_MAX_PIPE_GENS, st));
+    CUP(cudaMemsetAsync(ctx->pipe_miss, 0, sizeof(uint32_t) * RPX_MAX_PIPE_GENS, st));
     for (int i = 0; i < RPX_MAX_PIPE_GENS; i++) ctx->h_counts[i] = 0;  // a kernel that never runs leaves 0
     size_t state_off = 0, zero_end = 0;
     ctx->h_counts[0] = rays->soa.n;
@@ -658,6 +661,8 @@ static int trace_pipelined(rpx_ctx* ctx, rpx_rays* rays, double ml, int recursio
         sa.h_count = ctx->h_counts_dev + (g + 1);
         sa.hits_in = g >= 1 ? ctx->pipe_hits + g : nullptr;  // generation 0 was intersected by k_intersect
         sa.hits_out = ctx->pipe_hits + (g + 1);
+        sa.miss_in = g >= 1 ? ctx->pipe_miss + g : nullptr;
+        sa.miss_out = ctx->pipe_miss + (g + 1);
         cudaEvent_t b0 = next_event(ctx), b1 = next_event(ctx);
         CUP(cudaEventRecord(b0, st));
         CUP(shade_launcher(is_g, ctx->face_class, ctx->mm_idx, smem > 0)(st, sa));
@@ -772,6 +777,7 @@ static int trace_loop(rpx_ctx* ctx, rpx_rays* rays, double max_length, int recur
     cudaEvent_t ev_begin = next_event(ctx), ev_end = next_event(ctx);
     CUR(cudaMemsetAsync(ctx->d_face_counts, 0, sizeof(uint32_t) * (size_t)(ctx->n_traced > 0 ? ctx->n_traced : 1), st));
     CUR(cudaMemsetAsync(ctx->pipe_hits, 0, sizeof(uint32_t) * RPX_MAX_PIPE_GENS, st));
+    CUR(cudaMemsetAsync(ctx->pipe_miss, 0, sizeof(uint32_t) * RPX_MAX_PIPE_GENS, st));
     CUR(cudaEventRecord(ev_begin, st));
     if (is_g && cur->soa.n) {  // input_rays.reset_length(max_length), core/tracer.py:22
         k_reset_length<<<(unsigned)((cur->soa.n + 255) / 256), 256, 0, st>>>(cur->soa, ml);
@@ -837,6 +843,8 @@ static int trace_loop(rpx_ctx* ctx, rpx_rays* rays, double max_length, int recur
             if (!sequential && count + 1 < RPX_MAX_PIPE_GENS) {  // (a sequence's last step leaves its children untraced)
                 sa.hits_in = count >= 1 ? ctx->pipe_hits + count : nullptr;
                 sa.hits_out = ctx->pipe_hits + (count + 1);
+                sa.miss_in = count >= 1 ? ctx->pipe_miss + count : nullptr;
+                sa.miss_out = ctx->pipe_miss + (count + 1);
             }
             cudaError_t le = shade_launcher(is_g, ctx->face_class, ctx->mm_idx, smem > 0)(st, sa);
             CUR(le);

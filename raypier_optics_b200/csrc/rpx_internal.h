@@ -66,6 +66,7 @@ struct rpx_ctx {
     size_t pipe_state_cap;           // tiles
     uint32_t* pipe_counters;         // one ticket counter per generation
     uint32_t* pipe_hits;             // pipe_hits[g] != 0: some ray of generation g hit a face (set by the launch that built it)
+    uint32_t* pipe_miss;             // pipe_miss[g] = rays of generation g that hit nothing (drives the tile-local compaction)
     // event pool
     std::vector<cudaEvent_t> ev_pool;
     size_t ev_used;

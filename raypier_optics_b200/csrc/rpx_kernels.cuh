@@ -681,6 +681,24 @@ RPX_DEV void stage_child(double* cs, uint32_t* cu, uint32_t slot, const Kids& k,
 // Michelson trace).  With the late ticket a tile publishes its aggregate one material phase after taking its
 // ticket, before any later tile can reach its look-back.  Measured (profiles/r02_notes.md): +9 % on one box,
 // neutral on another, never the slow mode under ncu.
+#ifndef RPX_TILE_COMPACT
+#define RPX_TILE_COMPACT 0  // tile-local compaction of the hit rays: measured (profiles/r02_notes.md section 7), +1.4 % on
+                            // prisms, -0.6 % on the achromat / Michelson / grating, -4.6 % on gausslets -> off; -DRPX_TILE_COMPACT=1 builds it
+#endif
+// Gausslet experiments (A/B via RPX_EXTRA): L2 prefetch of the tile's parabasal columns at the start of the tile,
+// 16-byte stores of the two children's parabasal rays, unconditional parabasal loads in the first loop.
+#ifndef RPX_PARA_PREFETCH
+#define RPX_PARA_PREFETCH 0
+#endif
+#ifndef RPX_PARA_V2
+#define RPX_PARA_V2 0
+#endif
+#ifndef RPX_PARA_FIRST
+#define RPX_PARA_FIRST 0
+#endif
+#ifndef RPX_PARA_UNCOND
+#define RPX_PARA_UNCOND 0
+#endif
 #ifndef RPX_TICKET_END_G
 #define RPX_TICKET_END_G 1
 #endif
@@ -689,7 +707,7 @@ __global__ void __launch_bounds__(RPX_TILE, GAUSS ? RPX_MIN_BLOCKS_G : RPX_MIN_B
 k_shade(DevScene S, Soa in, Soa out, double max_length, unsigned long long* tile_state,
         uint32_t* tile_counter, unsigned long long* d_count, uint32_t* face_counts, uint32_t n_tiles,
         int ahead_face, const unsigned long long* n_dev, unsigned long long* h_count, const uint32_t* hits_in,
-        uint32_t* hits_out) {
+        uint32_t* hits_out, const uint32_t* miss_in, uint32_t* miss_out) {
     // hits_in != NULL: set by the launch that built this generation iff its trace-ahead found ANY hit.  A
     // generation nobody hit anything in (the last one of every finite trace: 15 % of the achromat and
     // Michelson steps went into reading it, ncu r02_div_*.csv) has no child, no count and no write-back
@@ -727,6 +745,25 @@ k_shade(DevScene S, Soa in, Soa out, double max_length, unsigned long long* tile
     const uint32_t n_tiles_real = (uint32_t)((n_in + RPX_TILE - 1) / RPX_TILE);
     constexpr bool kGrouped = RPX_LOOKBACK_GROUPS && (!GAUSS || RPX_GROUPS_GAUSS);
     const unsigned long long cap = in.cap;
+    // TILE-LOCAL COMPACTION OF THE HIT RAYS (the north star's "binning / compaction pass", done inside the
+    // tile so that it costs no HBM traffic and no second permutation).  In branching scenes half of a
+    // generation can be rays that left the system (prisms: every reflected partner of a transmitted ray);
+    // they sit interleaved with the rays that hit something, so every warp runs the material code half
+    // empty (ncu: 23.4 of 32 threads per instruction on the prism scene).  When the launch that built this
+    // generation counted >= 1/8 rays without a hit (*miss_in), the tile first reads end_face_idx alone,
+    // ballot-compacts the indices of the hit rays IN ORDER into shared memory, and thread t then takes the
+    // t-th hit ray: the material code runs on full warps, the rest of the CTA's warps skip it, and because
+    // the compaction keeps the order, the parent-ordered child slots still come out of the same thread-order
+    // scan.  Uniform per launch, so scenes without misses (achromat, Michelson) keep the direct path.
+    // MEASURED on B200 and switched off (RPX_TILE_COMPACT=0): the kernel is latency-bound, not issue-bound, so
+    // full warps in the material code buy +1.4 % on prisms while the bookkeeping costs 0.6 - 4.6 % elsewhere.
+#if RPX_TILE_COMPACT
+    __shared__ uint32_t s_hcnt[RPX_TILE / 32];
+    __shared__ unsigned char s_src[RPX_TILE];
+    __shared__ uint32_t s_nmiss;
+    const bool compact = miss_in != nullptr && (unsigned long long)(*miss_in) * 8ull >= n_in && n_in > 0;
+    if (threadIdx.x == 0) s_nmiss = 0u;
+#endif
   // PERSISTENT CTA: the grid is one wave of resident CTAs; each pulls tiles from the ticket
   // counter until the (device-resident) tile count is exhausted.
   if (threadIdx.x == 0) s_tile = atomicAdd(tile_counter, 1u);
@@ -734,13 +771,51 @@ k_shade(DevScene S, Soa in, Soa out, double max_length, unsigned long long* tile
     __syncthreads();  // s_tile published; previous tile's staging buffer fully consumed
     const uint32_t tile = s_tile;
     if (tile >= n_tiles_real) break;  // uniform per CTA; tickets are dense, so tiles [0, real) all run
-    const unsigned long long i = (unsigned long long)tile * RPX_TILE + threadIdx.x;
+    unsigned long long i = (unsigned long long)tile * RPX_TILE + threadIdx.x;  // the parent this thread shades
+    bool have = i < n_in;
+#if RPX_TILE_COMPACT
+    if (compact) {
+        const uint32_t f0 = have ? in.u[U_ENDFACE * cap + i] : RPX_NO_FACE;
+        const bool h0 = (f0 != RPX_NO_FACE);
+        const unsigned b = __ballot_sync(0xffffffffu, h0);
+        const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+        if (lane == 0) s_hcnt[warp] = (uint32_t)__popc(b);
+        __syncthreads();
+        uint32_t off = 0, n_hit = 0;
+#pragma unroll
+        for (int w = 0; w < RPX_TILE / 32; w++) {
+            const uint32_t c = s_hcnt[w];
+            if (w < warp) off += c;
+            n_hit += c;
+        }
+        if (h0) s_src[off + (uint32_t)__popc(b & ((1u << lane) - 1u))] = (unsigned char)threadIdx.x;
+        __syncthreads();
+        have = threadIdx.x < n_hit;
+        i = (unsigned long long)tile * RPX_TILE + (have ? (uint32_t)s_src[threadIdx.x] : 0u);
+    }
+#endif
+#if RPX_TILE_COMPACT
+    const bool compact_on = compact;
+#else
+    constexpr bool compact_on = false;
+#endif
     // (s_tile is next written by thread 0 after the barrier inside the block scan: no barrier needed here)
     uint32_t next_tile = 0;
     // take the NEXT ticket now (its latency hides behind this tile's work) ...
     // (gausslets: at the END of the tile, see RPX_TICKET_END_G)
     constexpr bool kLateTicket = GAUSS && RPX_TICKET_END_G;
     if (threadIdx.x == 0 && !kLateTicket) next_tile = atomicAdd(tile_counter, 1u);
+#if RPX_PARA_PREFETCH
+    if (GAUSS && !compact_on && threadIdx.x >= RPX_TILE - 36) {
+        // the six serial (origin, direction) loads of the first parabasal loop then find their rows in L2:
+        // one 1 KB bulk prefetch per row, 36 rows, one instruction each in the last two warps
+        const uint32_t q = threadIdx.x - (RPX_TILE - 36);
+        const uint32_t row = (q / 6u) * NPF + (q % 6u);
+        asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(in.p + (unsigned long long)row * cap +
+                                                                          (unsigned long long)tile * RPX_TILE),
+                     "r"(RPX_TILE * 8));
+    }
+#endif
 
     Kids k;
     k.has_a = false;
@@ -751,7 +826,7 @@ k_shade(DevScene S, Soa in, Soa out, double max_length, unsigned long long* tile
     HitAux paux[FC == RPX_FC_MESH ? RPX_NPARA : 1];  // piece_idx / uv of the parabasal hits (mesh, UV patch faces)
     bool hit = false;
     RayIn r;
-    if (i < n_in) {
+    if (have) {
         // every load is issued before the first use: one DRAM round trip per tile, not two
         face_idx = in.u[U_ENDFACE * cap + i];
         r.o = v3(in.f[F_OX * cap + i], in.f[F_OY * cap + i], in.f[F_OZ * cap + i]);
@@ -789,21 +864,27 @@ k_shade(DevScene S, Soa in, Soa out, double max_length, unsigned long long* tile
                                transform_pt(mfs->inv_trans.m, r.o + r.d * max_length), 1, &aux);
             if (aux.piece < 0) aux.piece = 0;
         }
-        compute_orientation<FC>(S, face, point, &onormal, &otangent, &aux);
-        material_eval<MM>(S, &S.mats[face->material], r, point, onormal, otangent, k);
-
-        if (GAUSS) {
+        // trace_parabasal_rays, first loop, as a local function so that it can run before or after the material
+        auto para_hits = [&]() -> bool {
+            bool ok = true;
             // trace_parabasal_rays, first loop (ctracer.pyx:2363-2373): every parabasal ray
             // must hit the SAME face (is_base_ray = 0); any miss drops the children (Q16).
             const rpx_face_set* fs = &S.sets[face->face_set];
-            bool ok = true;
 #pragma unroll
             for (int j = 0; j < RPX_NPARA; j++) {
                 plen[j] = max_length;
+#if RPX_PARA_UNCOND
+                // loads outside the `ok` test: the compiler may issue the rows of several parabasal rays together
+                const double* pp = in.p + (unsigned long long)(j * NPF) * cap + i;
+                const vec3 po = v3(pp[(P_OX + 0) * cap], pp[(P_OX + 1) * cap], pp[(P_OX + 2) * cap]);
+                const vec3 pd = v3(pp[(P_DX + 0) * cap], pp[(P_DX + 1) * cap], pp[(P_DX + 2) * cap]);
+                if (ok) {
+#else
                 if (ok) {
                     const double* pp = in.p + (unsigned long long)(j * NPF) * cap + i;
                     vec3 po = v3(pp[(P_OX + 0) * cap], pp[(P_OX + 1) * cap], pp[(P_OX + 2) * cap]);
                     vec3 pd = v3(pp[(P_DX + 0) * cap], pp[(P_DX + 1) * cap], pp[(P_DX + 2) * cap]);
+#endif
                     vec3 ray_end = po + pd * max_length;
                     vec3 p1 = transform_pt(fs->inv_trans.m, po);
                     vec3 p2 = transform_pt(fs->inv_trans.m, ray_end);
@@ -820,11 +901,23 @@ k_shade(DevScene S, Soa in, Soa out, double max_length, unsigned long long* tile
                     }
                 }
             }
-            if (!ok) {
-                k.has_a = false;
-                k.has_b = false;
-            }
+            return ok;
+        };
+#if RPX_PARA_FIRST
+        // the parabasal rays are intersected BEFORE the material is evaluated: the 31 doubles of the children
+        // are then not live across the six intersections, and a dropped gausslet (Q16) skips the material
+        if (!GAUSS || para_hits()) {
+            compute_orientation<FC>(S, face, point, &onormal, &otangent, &aux);
+            material_eval<MM>(S, &S.mats[face->material], r, point, onormal, otangent, k);
         }
+#else
+        compute_orientation<FC>(S, face, point, &onormal, &otangent, &aux);
+        material_eval<MM>(S, &S.mats[face->material], r, point, onormal, otangent, k);
+        if (GAUSS && !para_hits()) {
+            k.has_a = false;
+            k.has_b = false;
+        }
+#endif
     }
 
     const uint32_t parent = (uint32_t)i;
@@ -891,6 +984,9 @@ k_shade(DevScene S, Soa in, Soa out, double max_length, unsigned long long* tile
     }
     // ---- 4. trace ahead
     bool any_hit = false;
+#if RPX_TILE_COMPACT
+    uint32_t n_miss = 0;
+#endif
     if (ahead_face != -2) {
         for (uint32_t slot = threadIdx.x; slot < total; slot += RPX_TILE) {
 #if RPX_LEAN_STAGE
@@ -908,6 +1004,9 @@ k_shade(DevScene S, Soa in, Soa out, double max_length, unsigned long long* tile
             uint32_t face;
             nearest_hit<FC>(S, o, d, max_length, ahead_face, &len, &face);
             any_hit = any_hit || (face != RPX_NO_FACE);
+#if RPX_TILE_COMPACT
+            if (face == RPX_NO_FACE) n_miss++;
+#endif
 #if RPX_LEAN_STAGE
             L.cf[LC_LEN * RPX_SLOTS + slot] = len;
             L.cu[LCU_ENDFACE * RPX_SLOTS + slot] = face;
@@ -957,8 +1056,19 @@ k_shade(DevScene S, Soa in, Soa out, double max_length, unsigned long long* tile
             }
         }
     }
+#if RPX_TILE_COMPACT
+    if (n_miss && miss_out != nullptr) atomicAdd(&s_nmiss, n_miss);
+#endif
     const int tile_hit = __syncthreads_or(any_hit ? 1 : 0);
-    if (threadIdx.x == 0 && tile_hit && hits_out != nullptr) *hits_out = 1u;  // idempotent, one store per tile
+    if (threadIdx.x == 0) {
+        if (tile_hit && hits_out != nullptr) *hits_out = 1u;  // idempotent, one store per tile
+#if RPX_TILE_COMPACT
+        if (miss_out != nullptr && s_nmiss) {                  // rays of the new generation that hit nothing
+            atomicAdd(miss_out, s_nmiss);
+            s_nmiss = 0u;  // next added to after the next tile's barriers
+        }
+#endif
+    }
     const unsigned long long base = s_prefix;
     // ---- 6. coalesced copy-out: slot == consecutive addresses.  Two explicit passes (a tile has
     // at most 2 * RPX_TILE children), each a straight line of 26 independent LDS -> STG pairs.
@@ -1012,6 +1122,9 @@ k_shade(DevScene S, Soa in, Soa out, double max_length, unsigned long long* tile
         const rpx_material* M = &S.mats[face->material];
         const unsigned long long ocap = out.cap;
         const unsigned long long pos_a = base + slot_a, pos_b = base + slot_b;
+#if RPX_PARA_V2
+        const bool pair_ok = ((pos_a | ocap) & 1ull) == 0 && (reinterpret_cast<unsigned long long>(out.p) & 15ull) == 0;
+#endif
 #pragma unroll
         for (int j = 0; j < RPX_NPARA; j++) {
             const double* pp = in.p + (unsigned long long)(j * NPF) * cap + i;
@@ -1021,6 +1134,24 @@ k_shade(DevScene S, Soa in, Soa out, double max_length, unsigned long long* tile
             vec3 pn, pt;
             compute_orientation<FC>(S, face, ppoint, &pn, &pt, FC == RPX_FC_MESH ? &paux[j] : nullptr);
             vec3 nn = norm(pn);
+#if RPX_PARA_V2
+            // both children, first one on an even position (every tile of a generation in which every parent
+            // has two children: the Michelson beam splitter): the pair of every row is ONE 16-byte store
+            // instead of two 8-byte stores at stride 2 (ncu, round 1: DRAM traffic 1.18x algorithmic there)
+            if (k.has_a && k.has_b && pair_ok) {
+                const vec3 da = material_eval_para(S, M, wl, k.a.n.re, pd, ppoint, pn, pt, k.a.type);
+                const vec3 db = material_eval_para(S, M, wl, k.b.n.re, pd, ppoint, pn, pt, k.b.type);
+                double* q = out.p + (unsigned long long)(j * NPF) * ocap + pos_a;
+                auto st2 = [&](int row, double x, double y) {
+                    *reinterpret_cast<double2*>(q + (unsigned long long)row * ocap) = make_double2(x, y);
+                };
+                st2(0, ppoint.x, ppoint.x); st2(1, ppoint.y, ppoint.y); st2(2, ppoint.z, ppoint.z);
+                st2(3, da.x, db.x); st2(4, da.y, db.y); st2(5, da.z, db.z);
+                st2(6, nn.x, nn.x); st2(7, nn.y, nn.y); st2(8, nn.z, nn.z);
+                st2(9, max_length, max_length);
+                continue;
+            }
+#endif
             if (k.has_a) {
                 vec3 dir = material_eval_para(S, M, wl, k.a.n.re, pd, ppoint, pn, pt, k.a.type);
                 double* q = out.p + (unsigned long long)(j * NPF) * ocap + pos_a;

@@ -25,6 +25,8 @@ struct ShadeArgs {
     unsigned long long* h_count;      // mapped host slot for len(new_rays) or NULL
     const uint32_t* hits_in = nullptr;  // "some ray of this generation hit something" (NULL: unknown, run)
     uint32_t* hits_out = nullptr;       // the same flag for the generation built by this launch (NULL: not wanted)
+    const uint32_t* miss_in = nullptr;  // number of rays of this generation that hit NOTHING (NULL: unknown, no compaction)
+    uint32_t* miss_out = nullptr;       // the same count for the generation built by this launch
 };
 
 // one launcher per compiled variant: g = gausslets, f = face class, m = material mask index

@@ -71,7 +71,8 @@ cudaError_t RPX_CAT(RPX_I_GAUSS, RPX_I_FC, RPX_I_MM)(cudaStream_t st, const Shad
     }
     const unsigned grid = a.n_tiles < (unsigned)resident_ctas ? a.n_tiles : (unsigned)resident_ctas;
     kern<<<grid, RPX_TILE, dyn, st>>>(a.S, a.in, a.out, a.max_length, a.tile_state, a.tile_counter, a.d_count,
-                                      a.face_counts, a.n_tiles, a.ahead_face, a.n_dev, a.h_count, a.hits_in, a.hits_out);
+                                      a.face_counts, a.n_tiles, a.ahead_face, a.n_dev, a.h_count, a.hits_in, a.hits_out, a.miss_in,
+                                      a.miss_out);
     return cudaGetLastError();
 }
 
