@@ -4,6 +4,6 @@
 set -u
 cd "$(dirname "$0")/../.."
 mkdir -p gpurun_out
-L="librpx.so librpx_e1.so librpx_e2.so librpx_e4.so librpx_e5.so librpx_e15.so librpx_e124.so librpx_e1245.so"
+L="librpx.so librpx_e1.so librpx_e2.so librpx_e5.so librpx_e1245.so"
 bash profiles/tools/ab1.sh "$L $L" "config5_1e6" > gpurun_out/r02_c13_ab.log 2>&1
 cat gpurun_out/r02_c13_ab.log
