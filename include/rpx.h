@@ -119,7 +119,13 @@ typedef enum rpx_face_type {
                                       box min[3], box max[3], then (left, right) child ids for an inner
                                       node or (-(first tri) - 1, count) for a leaf.  The reference's OBB
                                       tree is an acceleration structure (its node test only prunes); this
-                                      library carries its own BVH, built by the host side.             */
+                                      library carries its own BVH, built by the host side.  rpx_scene_set
+                                      repacks it for the device walk (64-byte nodes with both children's
+                                      boxes in outward-rounded fp32; triangle tests stay fp64 on these
+                                      records, so hits are bit-identical to a walk of the fp64 nodes) and
+                                      validates links and depth.  The facet a ray hit travels with the device
+                                      collection in a side array (intersect_t.piece_idx, ctracer.pxd), so the
+                                      generation that shades the ray does not walk the tree again.          */
     RPX_FACE_UVPATCH = 22          /* cbezier.pyx:391-550 UVPatchFace over a BezierPatch (:200-286) or BSplinePatch
                                       (:290-388).  p: atol, invert_normals, patch kind (0 Bezier, 1 B-spline),
                                       N, M (orders: (N+1) x (M+1) control points), u_degree, v_degree, offset of

@@ -8,11 +8,14 @@ triangles, obbtree.pyx:204-223) and ``OBBTreeFace(tree=..., material=...)`` is t
 split, built in :func:`build_bvh` when the scene is flattened), so ``build_tree`` here has nothing to
 compute; ``max_level`` / ``number_of_cells_per_node`` are kept for interface compatibility.
 """
+import os
+
 import numpy as np
 
 from .ctracer import Face
 
-LEAF_CELLS = 4
+# triangles per BVH leaf (RPX_BVH_LEAF: developer override for measurements; 1..8, the packed device nodes hold <= 8)
+LEAF_CELLS = min(8, max(1, int(os.environ.get("RPX_BVH_LEAF", "4"))))
 
 
 class OBBTree(object):

@@ -277,12 +277,99 @@ static int validate_scene(rpx_ctx* ctx, const rpx_scene* s) {
     return RPX_OK;
 }
 
+// The BVH of every mesh / UV patch face repacked for the device walk (rpx_faces.cuh::mesh_intersect): one 64-byte
+// node per INNER node of the tree, holding both children's boxes as fp32 rounded outwards and two child references
+// (>= 0: packed node, < 0: leaf -(first * 8 + count - 1) - 1, RPX_BVH32_NONE: no child).  A tree the packed format
+// cannot hold (a leaf of more than 8 triangles, 2^27 triangles, depth over 46) keeps off[face] = -1 and is walked
+// through its fp64 nodes.  RPX_MESH_F64=1 in the environment forces that for every face (A/B measurements).
+static float f32_down(double x) {
+    float f = (float)x;
+    if ((double)f > x) f = nextafterf(f, -INFINITY);
+    return f;
+}
+static float f32_up(double x) {
+    float f = (float)x;
+    if ((double)f < x) f = nextafterf(f, INFINITY);
+    return f;
+}
+static void pack_mesh_bvh(const rpx_scene* s, std::vector<float>& packed, std::vector<int>& off) {
+    off.assign((size_t)(s->n_faces > 0 ? s->n_faces : 1), -1);
+    const char* env = getenv("RPX_MESH_F64");
+    if (env && env[0] == '1') return;
+    for (int i = 0; i < s->n_faces; i++) {
+        const rpx_face& f = s->faces[i];
+        if (f.type != RPX_FACE_MESH && f.type != RPX_FACE_UVPATCH) continue;
+        const double* H = s->pool + f.aux_off;
+        const long long n_cells = (long long)H[1], n_nodes = (long long)H[2];
+        const double* nodes = H + (long long)H[6];
+        if (n_cells >= (1ll << 27)) continue;
+        bool ok = true;
+        std::vector<int> height((size_t)n_nodes, 1);
+        for (long long k = n_nodes - 1; k >= 0 && ok; k--) {
+            const double a = nodes[8 * k + 6], b = nodes[8 * k + 7];
+            if (a >= 0)
+                height[(size_t)k] = 1 + std::max(height[(size_t)a], height[(size_t)b]);
+            else if (b > 8)
+                ok = false;
+        }
+        if (!ok || height[0] > 46) continue;
+        // inner nodes -> packed ids in index order (children have larger ids than their parent)
+        std::vector<int> pid((size_t)n_nodes, -1);
+        int n_inner = 0;
+        for (long long k = 0; k < n_nodes; k++)
+            if (nodes[8 * k + 6] >= 0) pid[(size_t)k] = n_inner++;
+        const size_t base = packed.size() / 16;
+        const bool root_leaf = nodes[6] < 0;
+        packed.resize(packed.size() + 16 * (size_t)(root_leaf ? 1 : n_inner), 0.0f);
+        auto ref_of = [&](long long k) -> int {
+            const double a = nodes[8 * k + 6], b = nodes[8 * k + 7];
+            if (a >= 0) return pid[(size_t)k];
+            return -(int)((long long)(-a - 1) * 8 + ((long long)b - 1)) - 1;
+        };
+        auto put = [&](float* n, int slot, long long k) {  // child `slot` of packed node n := tree node k
+            float* lo = slot == 0 ? n + 0 : n + 6;
+            float* hi = lo + 3;
+            for (int c = 0; c < 3; c++) {
+                lo[c] = f32_down(nodes[8 * k + c]);
+                hi[c] = f32_up(nodes[8 * k + 3 + c]);
+            }
+            const int r = ref_of(k);
+            memcpy(n + 12 + slot, &r, 4);
+        };
+        auto put_none = [&](float* n, int slot) {
+            float* lo = slot == 0 ? n + 0 : n + 6;
+            for (int c = 0; c < 6; c++) lo[c] = 3.0e38f;
+            const int r = RPX_BVH32_NONE;
+            memcpy(n + 12 + slot, &r, 4);
+        };
+        float* P = packed.data() + 16 * base;
+        if (root_leaf) {
+            put(P, 0, 0);
+            put_none(P, 1);
+        } else {
+            for (long long k = 0; k < n_nodes; k++) {
+                if (pid[(size_t)k] < 0) continue;
+                float* n = P + 16 * (size_t)pid[(size_t)k];
+                put(n, 0, (long long)nodes[8 * k + 6]);
+                put(n, 1, (long long)nodes[8 * k + 7]);
+            }
+        }
+        double m = 0.0;  // largest |coordinate| of the root box: scales the padding of the fp32 slab test
+        for (int c = 0; c < 6; c++) m = std::max(m, fabs(nodes[c]));
+        P[14] = f32_up(m);
+        off[(size_t)i] = (int)base;
+    }
+}
+
 // Copy the flat scene tables into ONE device block and point a DevScene at them.
 // Layout: faces | sets | materials | shape ops | implicit ops | distortions | zcoefs | ztape |
 //         wavelengths | ntab | pool
 static int upload_scene(rpx_ctx* ctx, const rpx_scene* s, DevScene* out, void** block) {
     struct Part { const void* src; size_t bytes; size_t off; };
-    Part parts[11] = {
+    std::vector<float> bvh32;
+    std::vector<int> mesh32_off;
+    pack_mesh_bvh(s, bvh32, mesh32_off);
+    Part parts[13] = {
         {s->faces, (size_t)s->n_faces * sizeof(rpx_face), 0},
         {s->face_sets, (size_t)s->n_face_sets * sizeof(rpx_face_set), 0},
         {s->materials, (size_t)s->n_materials * sizeof(rpx_material), 0},
@@ -294,6 +381,8 @@ static int upload_scene(rpx_ctx* ctx, const rpx_scene* s, DevScene* out, void** 
         {s->wavelengths, (size_t)s->n_wavelengths * sizeof(double), 0},
         {s->ntab, (size_t)s->n_ntab * 2 * sizeof(double), 0},
         {s->pool, (size_t)s->n_pool * sizeof(double), 0},
+        {bvh32.data(), bvh32.size() * sizeof(float), 0},
+        {mesh32_off.data(), mesh32_off.size() * sizeof(int), 0},
     };
     size_t total = 0;
     for (Part& p : parts) {
@@ -326,6 +415,8 @@ static int upload_scene(rpx_ctx* ctx, const rpx_scene* s, DevScene* out, void** 
     d.wavelengths = (const double*)(b + parts[8].off);
     d.ntab = (const double*)(b + parts[9].off);
     d.pool = (const double*)(b + parts[10].off);
+    d.bvh32 = (const float4*)(b + parts[11].off);
+    d.mesh32_off = (const int*)(b + parts[12].off);
     d.n_traced = s->n_traced_faces;
     d.n_faces = s->n_faces;
     d.n_sets = s->n_face_sets;
@@ -425,18 +516,20 @@ int rpx_rays_alloc(rpx_ctx* ctx, unsigned long long cap_req, int is_gausslet, rp
     size_t fb = (size_t)NF * cap * sizeof(double);
     size_t ub = (size_t)NU * cap * sizeof(uint32_t);
     size_t pb = is_gausslet ? (size_t)NP * cap * sizeof(double) : 0;
-    r->bytes = fb + ub + pb;
+    size_t qb = (size_t)cap * sizeof(uint32_t);  // facet record of the hit (mesh / UV patch scenes; untouched otherwise)
+    r->bytes = fb + ub + pb + qb;
     r->is_gausslet = is_gausslet;
     cudaError_t e = cudaMallocAsync(&r->block, r->bytes, ctx->stream);
     if (e != cudaSuccess) {
         delete r;
-        return fail(ctx, RPX_ERR_NOMEM, "cannot allocate %zu bytes for a generation of %llu %s: %s", fb + ub + pb,
+        return fail(ctx, RPX_ERR_NOMEM, "cannot allocate %zu bytes for a generation of %llu %s: %s", fb + ub + pb + qb,
                     cap, is_gausslet ? "gausslets" : "rays", cudaGetErrorString(e));
     }
     unsigned char* b = (unsigned char*)r->block;
     r->soa.f = (double*)b;
     r->soa.p = is_gausslet ? (double*)(b + fb) : nullptr;
     r->soa.u = (uint32_t*)(b + fb + pb);
+    r->soa.piece = (uint32_t*)(b + fb + pb + ub);
     r->soa.n = 0;
     r->soa.cap = cap;
     *out = r;

@@ -27,8 +27,14 @@ struct DevScene {
     const double* wavelengths;
     const double* ntab;  // interleaved re, im
     const double* pool;
+    // mesh / UV patch faces: the BVH repacked by rpx_scene_set for the device walk (mesh_intersect): 64-byte nodes
+    // holding BOTH children's boxes in conservatively rounded fp32; mesh32_off[face] = first node of the face's
+    // tree in bvh32 (in nodes), -1 = none (the walk then uses the fp64 nodes of the pool)
+    const float4* bvh32;
+    const int* mesh32_off;
     int n_traced, n_faces, n_sets, n_mats, n_wl, n_dists;
 };
+#define RPX_BVH32_NONE (-2147483647 - 1)   /* child slot without a child */
 
 // Face-class specialisation of the kernels.  A scene made only of planes, spheres,
 // extrusions and polygons runs kernels compiled WITHOUT the Newton / quadric / distortion
@@ -1153,7 +1159,8 @@ static __device__ __noinline__ double distortion_intersect(const DevScene& S, co
 // (:310-343) on records that hold p1, v1, v2 and n = v1 x v2 ready-made.  Exactly equal alpha (a ray
 // through a shared edge): the lowest cell id wins, whatever the traversal order.
 // *piece = cell id of the hit (intersect_t.piece_idx), -1 on a miss.
-static __device__ __noinline__ double mesh_intersect(const DevScene& S, const rpx_face* f, vec3 p1, vec3 p2, int* piece) {
+static __device__ __noinline__ double mesh_intersect_f64(const DevScene& S, const rpx_face* f, vec3 p1, vec3 p2, int* piece,
+                                                        int* rec_out = nullptr) {
     const double* H = S.pool + f->aux_off;
     const double* tris = H + (long long)H[5];
     const double* nodes = H + (long long)H[6];
@@ -1163,6 +1170,7 @@ static __device__ __noinline__ double mesh_intersect(const DevScene& S, const rp
     const double ix = 1.0 / d.x, iy = 1.0 / d.y, iz = 1.0 / d.z;  // +-inf for an axis-parallel segment
     double best = 1.0;
     long long best_id = -1;
+    int best_rec = -1;  // position of the winning record in tris[] (leaf order)
     // Near child first (measured on B200, 71k-facet scene: k_intersect 3.58 -> 1.91 ms, k_shade 4.76 -> 3.77 ms
     // per 1e6 rays against the unordered walk; 55 -> 34 box tests and 10.6 -> 5.6 triangle tests per ray
     // through a closed 5120-facet ball): a node is tested when its parent is expanded, pushed with its entry
@@ -1210,7 +1218,8 @@ static __device__ __noinline__ double mesh_intersect(const DevScene& S, const rp
                 }
                 continue;
             }
-            const double* t = tris + 16 * (long long)(-a - 1.0);
+            const int first = (int)(-a - 1.0);
+            const double* t = tris + 16 * (long long)first;
             const int count = (int)b;
             for (int c = 0; c < count; c++, t += 16) {
                 const vec3 tp = v3(t[0], t[1], t[2]), v1 = v3(t[3], t[4], t[5]), v2 = v3(t[6], t[7], t[8]);
@@ -1228,13 +1237,147 @@ static __device__ __noinline__ double mesh_intersect(const DevScene& S, const rp
                 if (alpha >= tol && (alpha < best || (alpha == best && id < best_id))) {
                     best = alpha;
                     best_id = id;
+                    best_rec = first + c;
                 }
             }
         }
         *piece = (int)best_id;
+        if (rec_out) *rec_out = best_rec;
         if (best_id < 0) best = -1.0;
         return best * dmag;
     }
+}
+
+// The walk that ships (measured on B200, profiles/r02_notes.md): the tree repacked by rpx_scene_set into 64-byte
+// nodes that hold BOTH children's boxes as fp32 rounded outwards -- one 64-byte load per step instead of three
+// dependent 64-byte fp64 nodes, slab tests on the fp32 pipe, 8-byte stack entries.  The fp32 test is CONSERVATIVE:
+// the segment is taken in fp32 (origin and direction rounded to nearest) and every box is widened by
+// delta_c = 2^-19 (|p1_c| + |d_c| + the largest box coordinate), 32x the worst-case sum of the rounding errors of
+// the conversion and of the six operations of the slab test, so a box the exact segment touches is never
+// rejected; the running bound is the fp64 best alpha rounded UP.  The triangle test itself is the fp64 code of
+// the fp64 walk, on the same records, with the same tie rule -- the result is bit-identical, only fewer / cheaper
+// box tests are made.  Leaf reference: -(first * 8 + count - 1) - 1 (count <= 8).
+static __device__ __noinline__ double mesh_intersect(const DevScene& S, const rpx_face* f, vec3 p1, vec3 p2, int* piece,
+                                                    int* rec_out = nullptr) {
+    const int root = S.mesh32_off ? S.mesh32_off[(int)(f - S.faces)] : -1;
+    if (root < 0) return mesh_intersect_f64(S, f, p1, p2, piece, rec_out);
+    const double* H = S.pool + f->aux_off;
+    const double* tris = H + (long long)H[5];
+    const float4* nodes = S.bvh32 + 4 * (long long)root;
+    const vec3 d = p2 - p1;
+    const double dmag = sqrt(d.x * d.x + d.y * d.y + d.z * d.z);  // mag_(d): IEEE, it scales the result
+    const double tol = H[7] / dmag;
+    double best = 1.0;
+    long long best_id = -1;
+    int best_rec = -1;
+    float best_f = 1.0f;
+    // the fp32 segment and its padding
+    const float ox = (float)p1.x, oy = (float)p1.y, oz = (float)p1.z;
+    const float dx = (float)d.x, dy = (float)d.y, dz = (float)d.z;
+    const float ix = 1.0f / dx, iy = 1.0f / dy, iz = 1.0f / dz;  // +-inf for an axis-parallel segment
+    const float mx = __int_as_float(__float_as_int(nodes[3].z));  // largest |coordinate| of the root box
+    const float k = 1.9073486328125e-6f;                           // 2^-19
+    const float ex = k * (fabsf(ox) + fabsf(dx) + mx), ey = k * (fabsf(oy) + fabsf(dy) + mx), ez = k * (fabsf(oz) + fabsf(dz) + mx);
+    const float omx = ox + ex, omy = oy + ey, omz = oz + ez;  // box.lo - delta - o = box.lo - om
+    const float opx = ox - ex, opy = oy - ey, opz = oz - ez;  // box.hi + delta - o = box.hi - op
+    auto slab = [&](float lx, float ly, float lz, float hx, float hy, float hz, float* t0) -> bool {
+        const float ax = (lx - omx) * ix, bx = (hx - opx) * ix;
+        const float ay = (ly - omy) * iy, by = (hy - opy) * iy;
+        const float az = (lz - omz) * iz, bz = (hz - opz) * iz;
+        const float tmin = fmaxf(fmaxf(fminf(ax, bx), fminf(ay, by)), fmaxf(fminf(az, bz), 0.0f));
+        const float tmax = fminf(fminf(fmaxf(ax, bx), fmaxf(ay, by)), fminf(fmaxf(az, bz), best_f));
+        *t0 = tmin;
+        return tmin <= tmax;
+    };
+    auto leaf = [&](int ref) {
+        const int code = -ref - 1;
+        const int first = code >> 3, count = (code & 7) + 1;
+        const double* t = tris + 16 * (long long)first;
+        for (int c = 0; c < count; c++, t += 16) {
+            const vec3 tp = v3(t[0], t[1], t[2]), v1 = v3(t[3], t[4], t[5]), v2 = v3(t[6], t[7], t[8]);
+            const vec3 n = v3(t[9], t[10], t[11]);
+            const double det = -dot(d, n);
+            if (det == 0.0) continue;
+            const double invdet = 1.0 / det;
+            const vec3 a0 = p1 - tp;
+            const vec3 da0 = cross(a0, d);
+            const double u = dot(v2, da0) * invdet;
+            const double v = -dot(v1, da0) * invdet;
+            const double alpha = dot(a0, n) * invdet;
+            if ((u + v > 1.0) | (u < 0) | (v < 0) | (alpha < 0)) continue;
+            const long long id = (long long)t[12];
+            if (alpha >= tol && (alpha < best || (alpha == best && id < best_id))) {
+                best = alpha;
+                best_id = id;
+                best_rec = first + c;
+                best_f = __double2float_ru(alpha);
+            }
+        }
+    };
+    int2 stk[48];  // (child reference, entry parameter as float bits): one 8-byte local access per push / pop
+    int sp = 0;
+    int cur = 0;
+    for (;;) {
+        const float4* nd = nodes + 4 * (long long)cur;
+        const float4 A = nd[0], B = nd[1], C = nd[2], D = nd[3];
+        // A = lo0.xyz hi0.x | B = hi0.yz lo1.xy | C = lo1.z hi1.xyz | D = ref0 ref1 (bits) . .
+        float ta, tb;
+        int ra = __float_as_int(D.x), rb = __float_as_int(D.y);
+        bool ha = slab(A.x, A.y, A.z, A.w, B.x, B.y, &ta) && ra != RPX_BVH32_NONE;
+        bool hb = slab(B.z, B.w, C.x, C.y, C.z, C.w, &tb) && rb != RPX_BVH32_NONE;
+        if (ha && hb && tb < ta) {  // (a) = the nearer child
+            const float tt = ta; ta = tb; tb = tt;
+            const int rr = ra; ra = rb; rb = rr;
+        } else if (!ha && hb) {
+            ta = tb; ra = rb; ha = true; hb = false;
+        }
+        int next = RPX_BVH32_NONE;
+        if (ha) {
+            if (ra < 0) leaf(ra); else next = ra;
+        }
+        if (hb) {
+            if (next != RPX_BVH32_NONE) {
+                if (sp < 48) stk[sp++] = make_int2(rb, __float_as_int(tb));  // depth checked by rpx_scene_set
+            } else if (tb <= best_f) {  // the near child was a leaf: the bound may have moved in front of (b)
+                if (rb < 0) leaf(rb); else next = rb;
+            }
+        }
+        while (next == RPX_BVH32_NONE && sp > 0) {
+            const int2 e = stk[--sp];
+            if (__int_as_float(e.y) > best_f) continue;
+            if (e.x < 0) leaf(e.x); else next = e.x;
+        }
+        if (next == RPX_BVH32_NONE) break;
+        cur = next;
+    }
+    *piece = (int)best_id;
+    if (rec_out) *rec_out = best_rec;
+    if (best_id < 0) best = -1.0;
+    return best * dmag;
+}
+
+// the triangle test of mesh_intersect on ONE known record (the facet the trace-ahead found): same arithmetic, so
+// the same alpha; *piece = its cell id, -1 if the segment does not cross it (cannot happen for a recorded hit)
+static __device__ __noinline__ double mesh_single(const DevScene& S, const rpx_face* f, vec3 p1, vec3 p2, int rec, int* piece) {
+    const double* H = S.pool + f->aux_off;
+    const double* t = H + (long long)H[5] + 16 * (long long)rec;
+    const vec3 d = p2 - p1;
+    const double dmag = sqrt(d.x * d.x + d.y * d.y + d.z * d.z);
+    const double tol = H[7] / dmag;
+    *piece = -1;
+    const vec3 tp = v3(t[0], t[1], t[2]), v1 = v3(t[3], t[4], t[5]), v2 = v3(t[6], t[7], t[8]);
+    const vec3 n = v3(t[9], t[10], t[11]);
+    const double det = -dot(d, n);
+    if (det == 0.0) return -dmag;
+    const double invdet = 1.0 / det;
+    const vec3 a0 = p1 - tp;
+    const vec3 da0 = cross(a0, d);
+    const double u = dot(v2, da0) * invdet;
+    const double v = -dot(v1, da0) * invdet;
+    const double alpha = dot(a0, n) * invdet;
+    if ((u + v > 1.0) | (u < 0) | (v < 0) | (alpha < 0) | !(alpha >= tol) | !(alpha < 1.0)) return -dmag;
+    *piece = (int)t[12];
+    return alpha * dmag;
 }
 
 // OBBTreeFace.__cinit__ (:898-908) + compute_normal_c (:935-946): the flat normal of cell `piece`
@@ -1257,6 +1400,7 @@ static __device__ __noinline__ vec3 mesh_normal(const DevScene& S, const rpx_fac
 // with the reference's pow() products, BSplinePatch (:290-388) with the Cox - de Boor recursion
 // (iterative here: a triangular table per direction instead of the reference's exponential recursion).
 struct HitAux {
+    int rec;      // position of the hit facet's record in the mesh block (-1: none); carried in the rays' side array
     int piece;    // intersect_t.piece_idx: the facet of a mesh face
     double u, v;  // intersect_t.uv: the patch parameters of a UVPatchFace hit
 };
@@ -1351,9 +1495,19 @@ static __device__ __noinline__ void uvpatch_eval(const UVPatch& P, double u, dou
     }
 }
 
-static __device__ __noinline__ double uvpatch_intersect(const DevScene& S, const rpx_face* f, vec3 p1, vec3 p2, HitAux* aux) {
-    int cell = -1;
-    const double dist_mesh = mesh_intersect(S, f, p1, p2, &cell);
+// known_rec >= 0: the facet was found by the launch that traced this ray ahead (side array of the collection):
+// its record gives the same alpha and cell without walking the BVH again
+static __device__ __noinline__ double uvpatch_intersect(const DevScene& S, const rpx_face* f, vec3 p1, vec3 p2, HitAux* aux,
+                                                        int known_rec = -1) {
+    int cell = -1, rec = -1;
+    double dist_mesh;
+    if (known_rec >= 0) {
+        dist_mesh = mesh_single(S, f, p1, p2, known_rec, &cell);
+        rec = known_rec;
+    } else {
+        dist_mesh = mesh_intersect(S, f, p1, p2, &cell, &rec);
+    }
+    if (aux) aux->rec = rec;
     const vec3 seg = p2 - p1;
     const double dmag = sqrt(seg.x * seg.x + seg.y * seg.y + seg.z * seg.z);
     const double alpha = (cell < 0) ? -1.0 : dist_mesh / dmag;
@@ -1426,16 +1580,37 @@ template <int FC>
 RPX_DEV double face_intersect(const DevScene& S, const rpx_face* f, vec3 p1, vec3 p2, int is_base_ray,
                               HitAux* aux = nullptr) {
     if (FC == RPX_FC_MESH && f->type == RPX_FACE_MESH) {
-        int pc;
-        const double dist = mesh_intersect(S, f, p1, p2, &pc);
-        if (aux) aux->piece = pc;
+        int pc, rec;
+        const double dist = mesh_intersect(S, f, p1, p2, &pc, &rec);
+        if (aux) {
+            aux->piece = pc;
+            aux->rec = rec;
+        }
         return dist;
     }
-    if (aux) aux->piece = 0;
+    if (aux) {
+        aux->piece = 0;
+        aux->rec = -1;
+    }
     if (FC == RPX_FC_MESH && f->type == RPX_FACE_UVPATCH) return uvpatch_intersect(S, f, p1, p2, aux);
     if (FC >= RPX_FC_FULL && f->type == RPX_FACE_DISTORTION) return distortion_intersect(S, f, p1, p2);
     if (FC >= RPX_FC_FULL && f->type == RPX_FACE_EXTRUDED_BEZIER) return bezier_intersect(S, f, p1, p2);
     return face_intersect_basic<FC>(S, f, p1, p2, is_base_ray);
+}
+
+// What Face.intersect_c left in intersect_t for compute_normal_and_tangent_c, rebuilt from the facet record the
+// trace-ahead stored for this ray (no second BVH walk): the cell id of a mesh face, the converged (u, v) of a patch
+// face.  p1, p2: the segment in the face's local frame, as the trace-ahead saw it.
+RPX_DEV void face_aux_from_rec(const DevScene& S, const rpx_face* f, vec3 p1, vec3 p2, int rec, HitAux* aux) {
+    aux->rec = rec;
+    aux->piece = 0;
+    aux->u = aux->v = 0.0;
+    if (f->type == RPX_FACE_MESH) {
+        const double* H = S.pool + f->aux_off;
+        aux->piece = (int)H[(long long)H[5] + 16 * (long long)rec + 12];
+    } else if (f->type == RPX_FACE_UVPATCH) {
+        uvpatch_intersect(S, f, p1, p2, aux, rec);
+    }
 }
 
 template <int FC>
@@ -1474,6 +1649,7 @@ RPX_DEV void compute_orientation(const DevScene& S, const rpx_face* f, vec3 poin
     vec3 n, t;
     if (FC == RPX_FC_MESH && f->type == RPX_FACE_UVPATCH) {
         HitAux zero;
+        zero.rec = -1;
         zero.piece = 0;
         zero.u = zero.v = 0.0;
         uvpatch_orientation(S, f, aux ? *aux : zero, &n, &t);

@@ -30,6 +30,10 @@ struct Soa {
     double* f;
     uint32_t* u;
     double* p;  // nullptr for plain rays
+    // mesh / UV patch scenes only: facet record (+ 1; 0 = none) of the hit stored in end_face_idx, written by the
+    // launch that found it (k_intersect, trace-ahead of k_shade) so that k_shade need not walk the BVH again for
+    // intersect_t.piece_idx / .uv.  NULL when the collection's hits were not found on the device (imported rays).
+    uint32_t* piece;
     unsigned long long n, cap;
 };
 
@@ -156,22 +160,27 @@ RPX_DEV void stage_scene(DevScene& S, unsigned char* smem) {
 template <int FC>
 __device__ __forceinline__ void nearest_hit(
     const DevScene& S, vec3 o, vec3 d, double max_length, int only_face,
-                                         double* out_len, uint32_t* out_face) {
+                                         double* out_len, uint32_t* out_face, uint32_t* out_rec = nullptr) {
     vec3 point = o + d * max_length;
     double best = max_length;  // ray.length = max_length (ctracer.pyx:2086)
     uint32_t best_face = RPX_NO_FACE;
+    uint32_t best_rec = 0;  // mesh class: facet record + 1 of the best hit
     if (only_face >= 0) {
         const rpx_face* f = &S.faces[only_face];
         const rpx_face_set* fs = &S.sets[f->face_set];
         vec3 p1 = transform_pt(fs->inv_trans.m, o);
         vec3 p2 = transform_pt(fs->inv_trans.m, point);
-        double dist = face_intersect<FC>(S, f, p1, p2, 1);
+        HitAux ha;
+        ha.rec = -1;
+        double dist = face_intersect<FC>(S, f, p1, p2, 1, FC == RPX_FC_MESH ? &ha : nullptr);
         if (f->tolerance < dist && dist < best) {
             best = dist;
             best_face = (uint32_t)only_face;
+            if (FC == RPX_FC_MESH) best_rec = (uint32_t)(ha.rec + 1);
         }
         *out_len = best;
         *out_face = best_face;
+        if (FC == RPX_FC_MESH && out_rec) *out_rec = best_rec;
         return;
     }
     for (int s = 0; s < S.n_sets; s++) {
@@ -180,15 +189,19 @@ __device__ __forceinline__ void nearest_hit(
         vec3 p2 = transform_pt(fs->inv_trans.m, point);
         for (int fi = fs->face_begin; fi < fs->face_end; fi++) {
             const rpx_face* f = &S.faces[fi];
-            double dist = face_intersect<FC>(S, f, p1, p2, 1);
+            HitAux ha;
+            ha.rec = -1;
+            double dist = face_intersect<FC>(S, f, p1, p2, 1, FC == RPX_FC_MESH ? &ha : nullptr);
             if (f->tolerance < dist && dist < best) {
                 best = dist;
                 best_face = (uint32_t)fi;
+                if (FC == RPX_FC_MESH) best_rec = (uint32_t)(ha.rec + 1);
             }
         }
     }
     *out_len = best;
     *out_face = best_face;
+    if (FC == RPX_FC_MESH && out_rec) *out_rec = best_rec;
 }
 
 // ------------------------------------------------------------------ k_intersect
@@ -208,9 +221,11 @@ k_intersect(DevScene S, Soa rays, double max_length, int only_face) {
     vec3 d = v3(rays.f[F_DX * cap + i], rays.f[F_DY * cap + i], rays.f[F_DZ * cap + i]);
     double best;
     uint32_t best_face;
-    nearest_hit<FC>(S, o, d, max_length, only_face, &best, &best_face);
+    uint32_t best_rec = 0;
+    nearest_hit<FC>(S, o, d, max_length, only_face, &best, &best_face, &best_rec);
     rays.f[F_LEN * cap + i] = best;
     rays.u[U_ENDFACE * cap + i] = best_face;
+    if (FC == RPX_FC_MESH && rays.piece) rays.piece[i] = best_rec;
 }
 
 // ------------------------------------------------------------------ ordered emission
@@ -685,19 +700,8 @@ RPX_DEV void stage_child(double* cs, uint32_t* cu, uint32_t slot, const Kids& k,
 #define RPX_TILE_COMPACT 0  // tile-local compaction of the hit rays: measured (profiles/r02_notes.md section 7), +1.4 % on
                             // prisms, -0.6 % on the achromat / Michelson / grating, -4.6 % on gausslets -> off; -DRPX_TILE_COMPACT=1 builds it
 #endif
-// Gausslet experiments (A/B via RPX_EXTRA): L2 prefetch of the tile's parabasal columns at the start of the tile,
-// 16-byte stores of the two children's parabasal rays, unconditional parabasal loads in the first loop.
-#ifndef RPX_PARA_PREFETCH
-#define RPX_PARA_PREFETCH 0
-#endif
-#ifndef RPX_PARA_V2
-#define RPX_PARA_V2 0
-#endif
 #ifndef RPX_PARA_FIRST
-#define RPX_PARA_FIRST 0
-#endif
-#ifndef RPX_PARA_UNCOND
-#define RPX_PARA_UNCOND 0
+#define RPX_PARA_FIRST 1
 #endif
 #ifndef RPX_TICKET_END_G
 #define RPX_TICKET_END_G 1
@@ -733,6 +737,7 @@ k_shade(DevScene S, Soa in, Soa out, double max_length, unsigned long long* tile
     __shared__ uint32_t s_tile;
     __shared__ uint32_t s_warp[RPX_TILE / 32];
     __shared__ unsigned long long s_prefix;
+    __shared__ uint32_t s_piece[FC == RPX_FC_MESH ? RPX_SLOTS : 1];  // facet records of the staged children's hits
     // dynamic shared memory: [child staging][scene copy]
 #if RPX_LEAN_STAGE
     const LeanStage L = lean_stage(smem);
@@ -794,28 +799,12 @@ k_shade(DevScene S, Soa in, Soa out, double max_length, unsigned long long* tile
         i = (unsigned long long)tile * RPX_TILE + (have ? (uint32_t)s_src[threadIdx.x] : 0u);
     }
 #endif
-#if RPX_TILE_COMPACT
-    const bool compact_on = compact;
-#else
-    constexpr bool compact_on = false;
-#endif
     // (s_tile is next written by thread 0 after the barrier inside the block scan: no barrier needed here)
     uint32_t next_tile = 0;
     // take the NEXT ticket now (its latency hides behind this tile's work) ...
     // (gausslets: at the END of the tile, see RPX_TICKET_END_G)
     constexpr bool kLateTicket = GAUSS && RPX_TICKET_END_G;
     if (threadIdx.x == 0 && !kLateTicket) next_tile = atomicAdd(tile_counter, 1u);
-#if RPX_PARA_PREFETCH
-    if (GAUSS && !compact_on && threadIdx.x >= RPX_TILE - 36) {
-        // the six serial (origin, direction) loads of the first parabasal loop then find their rows in L2:
-        // one 1 KB bulk prefetch per row, 36 rows, one instruction each in the last two warps
-        const uint32_t q = threadIdx.x - (RPX_TILE - 36);
-        const uint32_t row = (q / 6u) * NPF + (q % 6u);
-        asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(in.p + (unsigned long long)row * cap +
-                                                                          (unsigned long long)tile * RPX_TILE),
-                     "r"(RPX_TILE * 8));
-    }
-#endif
 
     Kids k;
     k.has_a = false;
@@ -826,9 +815,12 @@ k_shade(DevScene S, Soa in, Soa out, double max_length, unsigned long long* tile
     HitAux paux[FC == RPX_FC_MESH ? RPX_NPARA : 1];  // piece_idx / uv of the parabasal hits (mesh, UV patch faces)
     bool hit = false;
     RayIn r;
-    if (have) {
-        // every load is issued before the first use: one DRAM round trip per tile, not two
-        face_idx = in.u[U_ENDFACE * cap + i];
+    // gausslets (RPX_PARA_FIRST, shipped): the parabasal rays are intersected BEFORE orientation + material -- their six
+    // serial (origin, direction) round trips then overlap the base ray's own loads, the 31 doubles of the children
+    // are not live across the six intersections, and a dropped gausslet (Q16) skips the material.  Measured on three
+    // B200s: +3.5 / +4.5 / +6.3 % on the Michelson gausslets (profiles/r02_notes.md section 8).
+    constexpr int kParaFirst = GAUSS ? RPX_PARA_FIRST : 0;
+    auto load_r = [&]() {
         r.o = v3(in.f[F_OX * cap + i], in.f[F_OY * cap + i], in.f[F_OZ * cap + i]);
         r.d = v3(in.f[F_DX * cap + i], in.f[F_DY * cap + i], in.f[F_DZ * cap + i]);
         r.e = v3(in.f[F_EX * cap + i], in.f[F_EY * cap + i], in.f[F_EZ * cap + i]);
@@ -841,6 +833,11 @@ k_shade(DevScene S, Soa in, Soa out, double max_length, unsigned long long* tile
         r.wl = wl = in.u[U_WL * cap + i];
         r.ident = ident = in.u[U_IDENT * cap + i];
         r.type = in.u[U_TYPE * cap + i];
+    };
+    if (have) {
+        // every load is issued before the first use: one DRAM round trip per tile, not two
+        face_idx = in.u[U_ENDFACE * cap + i];
+        load_r();
         hit = (face_idx != RPX_NO_FACE);
     }
     if (hit) {
@@ -850,45 +847,24 @@ k_shade(DevScene S, Soa in, Soa out, double max_length, unsigned long long* tile
             if ((int)(threadIdx.x & 31) == __ffs(peers) - 1)
                 atomicAdd(&face_counts[face_idx], (uint32_t)__popc(peers));
         }
-        vec3 point = r.o + r.d * r.len;
-        vec3 onormal, otangent;
-        HitAux aux;
-        aux.piece = 0;
-        aux.u = aux.v = 0.0;
-        if (FC == RPX_FC_MESH && (face->type == RPX_FACE_MESH || face->type == RPX_FACE_UVPATCH)) {
-            // intersect_t.piece_idx (which triangle) / .uv (patch parameters) are not part of the ray
-            // record: the hit is found again from the same inputs the trace-ahead / k_intersect pass
-            // used, so it is the same hit
-            const rpx_face_set* mfs = &S.sets[face->face_set];
-            face_intersect<FC>(S, face, transform_pt(mfs->inv_trans.m, r.o),
-                               transform_pt(mfs->inv_trans.m, r.o + r.d * max_length), 1, &aux);
-            if (aux.piece < 0) aux.piece = 0;
-        }
-        // trace_parabasal_rays, first loop, as a local function so that it can run before or after the material
+        // trace_parabasal_rays, first loop (ctracer.pyx:2363-2373): every parabasal ray must hit the SAME face
+        // (is_base_ray = 0); any miss drops the children (Q16).  A local function so that it can run before
+        // (RPX_PARA_FIRST) or after the material.
         auto para_hits = [&]() -> bool {
             bool ok = true;
-            // trace_parabasal_rays, first loop (ctracer.pyx:2363-2373): every parabasal ray
-            // must hit the SAME face (is_base_ray = 0); any miss drops the children (Q16).
             const rpx_face_set* fs = &S.sets[face->face_set];
 #pragma unroll
             for (int j = 0; j < RPX_NPARA; j++) {
                 plen[j] = max_length;
-#if RPX_PARA_UNCOND
-                // loads outside the `ok` test: the compiler may issue the rows of several parabasal rays together
-                const double* pp = in.p + (unsigned long long)(j * NPF) * cap + i;
-                const vec3 po = v3(pp[(P_OX + 0) * cap], pp[(P_OX + 1) * cap], pp[(P_OX + 2) * cap]);
-                const vec3 pd = v3(pp[(P_DX + 0) * cap], pp[(P_DX + 1) * cap], pp[(P_DX + 2) * cap]);
-                if (ok) {
-#else
                 if (ok) {
                     const double* pp = in.p + (unsigned long long)(j * NPF) * cap + i;
                     vec3 po = v3(pp[(P_OX + 0) * cap], pp[(P_OX + 1) * cap], pp[(P_OX + 2) * cap]);
                     vec3 pd = v3(pp[(P_DX + 0) * cap], pp[(P_DX + 1) * cap], pp[(P_DX + 2) * cap]);
-#endif
                     vec3 ray_end = po + pd * max_length;
                     vec3 p1 = transform_pt(fs->inv_trans.m, po);
                     vec3 p2 = transform_pt(fs->inv_trans.m, ray_end);
                     HitAux pa;
+                    pa.rec = -1;
                     pa.piece = 0;
                     pa.u = pa.v = 0.0;
                     double dist = face_intersect<FC>(S, face, p1, p2, 0, FC == RPX_FC_MESH ? &pa : nullptr);
@@ -903,21 +879,37 @@ k_shade(DevScene S, Soa in, Soa out, double max_length, unsigned long long* tile
             }
             return ok;
         };
-#if RPX_PARA_FIRST
-        // the parabasal rays are intersected BEFORE the material is evaluated: the 31 doubles of the children
-        // are then not live across the six intersections, and a dropped gausslet (Q16) skips the material
-        if (!GAUSS || para_hits()) {
+        bool ok = true;
+        if (kParaFirst) ok = para_hits();
+        if (ok) {
+            vec3 point = r.o + r.d * r.len;
+            vec3 onormal, otangent;
+            HitAux aux;
+            aux.rec = -1;
+            aux.piece = 0;
+            aux.u = aux.v = 0.0;
+            if (FC == RPX_FC_MESH && (face->type == RPX_FACE_MESH || face->type == RPX_FACE_UVPATCH)) {
+                // intersect_t.piece_idx (which triangle) / .uv (patch parameters) are not part of the ray
+                // record: the hit is found again from the same inputs the trace-ahead / k_intersect pass
+                // used, so it is the same hit
+                // -- unless the launch that found it left the facet record in the side array
+                const rpx_face_set* mfs = &S.sets[face->face_set];
+                const vec3 q1 = transform_pt(mfs->inv_trans.m, r.o);
+                const vec3 q2 = transform_pt(mfs->inv_trans.m, r.o + r.d * max_length);
+                const uint32_t rec1 = in.piece ? in.piece[i] : 0u;
+                if (rec1 != 0u)
+                    face_aux_from_rec(S, face, q1, q2, (int)rec1 - 1, &aux);
+                else
+                    face_intersect<FC>(S, face, q1, q2, 1, &aux);
+                if (aux.piece < 0) aux.piece = 0;
+            }
             compute_orientation<FC>(S, face, point, &onormal, &otangent, &aux);
             material_eval<MM>(S, &S.mats[face->material], r, point, onormal, otangent, k);
+            if (GAUSS && !kParaFirst && !para_hits()) {
+                k.has_a = false;
+                k.has_b = false;
+            }
         }
-#else
-        compute_orientation<FC>(S, face, point, &onormal, &otangent, &aux);
-        material_eval<MM>(S, &S.mats[face->material], r, point, onormal, otangent, k);
-        if (GAUSS && !para_hits()) {
-            k.has_a = false;
-            k.has_b = false;
-        }
-#endif
     }
 
     const uint32_t parent = (uint32_t)i;
@@ -1002,7 +994,9 @@ k_shade(DevScene S, Soa in, Soa out, double max_length, unsigned long long* tile
 #endif
             double len;
             uint32_t face;
-            nearest_hit<FC>(S, o, d, max_length, ahead_face, &len, &face);
+            uint32_t hit_rec = 0;
+            nearest_hit<FC>(S, o, d, max_length, ahead_face, &len, &face, &hit_rec);
+            if (FC == RPX_FC_MESH) s_piece[slot] = hit_rec;
             any_hit = any_hit || (face != RPX_NO_FACE);
 #if RPX_TILE_COMPACT
             if (face == RPX_NO_FACE) n_miss++;
@@ -1109,6 +1103,7 @@ k_shade(DevScene S, Soa in, Soa out, double max_length, unsigned long long* tile
 #pragma unroll
                 for (int fld = 0; fld < NU; fld++) dstu[(unsigned long long)fld * ocap] = srcu[fld * RPX_SLOTS];
 #endif
+                if (FC == RPX_FC_MESH && out.piece && ahead_face != -2) out.piece[base + slot] = s_piece[slot];
             }
         }
     }
@@ -1122,9 +1117,6 @@ k_shade(DevScene S, Soa in, Soa out, double max_length, unsigned long long* tile
         const rpx_material* M = &S.mats[face->material];
         const unsigned long long ocap = out.cap;
         const unsigned long long pos_a = base + slot_a, pos_b = base + slot_b;
-#if RPX_PARA_V2
-        const bool pair_ok = ((pos_a | ocap) & 1ull) == 0 && (reinterpret_cast<unsigned long long>(out.p) & 15ull) == 0;
-#endif
 #pragma unroll
         for (int j = 0; j < RPX_NPARA; j++) {
             const double* pp = in.p + (unsigned long long)(j * NPF) * cap + i;
@@ -1134,24 +1126,6 @@ k_shade(DevScene S, Soa in, Soa out, double max_length, unsigned long long* tile
             vec3 pn, pt;
             compute_orientation<FC>(S, face, ppoint, &pn, &pt, FC == RPX_FC_MESH ? &paux[j] : nullptr);
             vec3 nn = norm(pn);
-#if RPX_PARA_V2
-            // both children, first one on an even position (every tile of a generation in which every parent
-            // has two children: the Michelson beam splitter): the pair of every row is ONE 16-byte store
-            // instead of two 8-byte stores at stride 2 (ncu, round 1: DRAM traffic 1.18x algorithmic there)
-            if (k.has_a && k.has_b && pair_ok) {
-                const vec3 da = material_eval_para(S, M, wl, k.a.n.re, pd, ppoint, pn, pt, k.a.type);
-                const vec3 db = material_eval_para(S, M, wl, k.b.n.re, pd, ppoint, pn, pt, k.b.type);
-                double* q = out.p + (unsigned long long)(j * NPF) * ocap + pos_a;
-                auto st2 = [&](int row, double x, double y) {
-                    *reinterpret_cast<double2*>(q + (unsigned long long)row * ocap) = make_double2(x, y);
-                };
-                st2(0, ppoint.x, ppoint.x); st2(1, ppoint.y, ppoint.y); st2(2, ppoint.z, ppoint.z);
-                st2(3, da.x, db.x); st2(4, da.y, db.y); st2(5, da.z, db.z);
-                st2(6, nn.x, nn.x); st2(7, nn.y, nn.y); st2(8, nn.z, nn.z);
-                st2(9, max_length, max_length);
-                continue;
-            }
-#endif
             if (k.has_a) {
                 vec3 dir = material_eval_para(S, M, wl, k.a.n.re, pd, ppoint, pn, pt, k.a.type);
                 double* q = out.p + (unsigned long long)(j * NPF) * ocap + pos_a;
