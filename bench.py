@@ -64,6 +64,8 @@ WORKLOADS = {
                         capture=dict(centre=(0.0, -12.0, 0.0), direction=(0.0, 1.0, 0.0), size=(12.0, 12.0))),
     # triangle-mesh optics: 20480-facet ball lens + 50562-facet mirror, BVH traversal
     "mesh": dict(n=1000000, kw=dict(gausslets=False, ball_subdiv=5, mesh_n=160)),
+    # the same optics at STL size: 81920-facet ball lens + 498002-facet mirror
+    "mesh_large": dict(n=1000000, kw=dict(gausslets=False, ball_subdiv=6, mesh_n=500), builder="mesh"),
     "config5_rays": dict(n=1000000, kw=dict(gausslets=False), builder="config5",
                          capture=dict(centre=(0.0, -12.0, 0.0), direction=(0.0, 1.0, 0.0), size=(12.0, 12.0))),
 }

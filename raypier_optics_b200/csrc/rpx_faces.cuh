@@ -1316,39 +1316,42 @@ static __device__ __noinline__ double mesh_intersect(const DevScene& S, const rp
     };
     int2 stk[48];  // (child reference, entry parameter as float bits): one 8-byte local access per push / pop
     int sp = 0;
+    // entries whose box starts behind the best hit so far are dropped on pop
+    auto pop = [&]() -> int {
+        while (sp > 0) {
+            const int2 e = stk[--sp];
+            if (__int_as_float(e.y) <= best_f) return e.x;
+        }
+        return RPX_BVH32_NONE;
+    };
+    // "while-while" walk: all lanes of a warp descend through inner nodes together until each holds a leaf (or is
+    // finished), then all test their leaf together -- ONE site for the box code and ONE for the fp64 triangle code
+    // (ncu of the first version, which tested leaves where it met them: 9.2 of 32 threads per instruction)
     int cur = 0;
     for (;;) {
-        const float4* nd = nodes + 4 * (long long)cur;
-        const float4 A = nd[0], B = nd[1], C = nd[2], D = nd[3];
-        // A = lo0.xyz hi0.x | B = hi0.yz lo1.xy | C = lo1.z hi1.xyz | D = ref0 ref1 (bits) . .
-        float ta, tb;
-        int ra = __float_as_int(D.x), rb = __float_as_int(D.y);
-        bool ha = slab(A.x, A.y, A.z, A.w, B.x, B.y, &ta) && ra != RPX_BVH32_NONE;
-        bool hb = slab(B.z, B.w, C.x, C.y, C.z, C.w, &tb) && rb != RPX_BVH32_NONE;
-        if (ha && hb && tb < ta) {  // (a) = the nearer child
-            const float tt = ta; ta = tb; tb = tt;
-            const int rr = ra; ra = rb; rb = rr;
-        } else if (!ha && hb) {
-            ta = tb; ra = rb; ha = true; hb = false;
-        }
-        int next = RPX_BVH32_NONE;
-        if (ha) {
-            if (ra < 0) leaf(ra); else next = ra;
-        }
-        if (hb) {
-            if (next != RPX_BVH32_NONE) {
-                if (sp < 48) stk[sp++] = make_int2(rb, __float_as_int(tb));  // depth checked by rpx_scene_set
-            } else if (tb <= best_f) {  // the near child was a leaf: the bound may have moved in front of (b)
-                if (rb < 0) leaf(rb); else next = rb;
+        while (cur >= 0) {
+            const float4* nd = nodes + 4 * (long long)cur;
+            const float4 A = nd[0], B = nd[1], C = nd[2], D = nd[3];
+            // A = lo0.xyz hi0.x | B = hi0.yz lo1.xy | C = lo1.z hi1.xyz | D = ref0 ref1 (bits) . .
+            float ta, tb;
+            int ra = __float_as_int(D.x), rb = __float_as_int(D.y);
+            const bool ha = slab(A.x, A.y, A.z, A.w, B.x, B.y, &ta) && ra != RPX_BVH32_NONE;
+            const bool hb = slab(B.z, B.w, C.x, C.y, C.z, C.w, &tb) && rb != RPX_BVH32_NONE;
+            if (ha && hb) {
+                const bool a_first = ta <= tb;  // near child next, far child on the stack
+                if (sp < 48) stk[sp++] = a_first ? make_int2(rb, __float_as_int(tb)) : make_int2(ra, __float_as_int(ta));
+                cur = a_first ? ra : rb;        // (depth checked by rpx_scene_set)
+            } else if (ha) {
+                cur = ra;
+            } else if (hb) {
+                cur = rb;
+            } else {
+                cur = pop();
             }
         }
-        while (next == RPX_BVH32_NONE && sp > 0) {
-            const int2 e = stk[--sp];
-            if (__int_as_float(e.y) > best_f) continue;
-            if (e.x < 0) leaf(e.x); else next = e.x;
-        }
-        if (next == RPX_BVH32_NONE) break;
-        cur = next;
+        if (cur == RPX_BVH32_NONE) break;
+        leaf(cur);
+        cur = pop();
     }
     *piece = (int)best_id;
     if (rec_out) *rec_out = best_rec;
