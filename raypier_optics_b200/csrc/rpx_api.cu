@@ -835,8 +835,15 @@ static int trace_loop(rpx_ctx* ctx, rpx_rays* rays, double max_length, int recur
     ctx->ev_used = 0;
     std::vector<cudaEvent_t> ev_i0, ev_i1, ev_s0, ev_s1;
 
+    // Mesh / UV patch scenes run UNFUSED: k_shade leaves its children untraced and k_intersect finds every
+    // generation's nearest hits.  The BVH walk lives on L1 hits (upper tree levels, per-thread stacks); inside
+    // k_shade the 47 KB of child staging per CTA leave it ~60 KB of L1 per SM (ncu: 58 % L1 hit rate against 79 % in
+    // k_intersect), and the walk cost 1.21 ms per 1e6 rays there against 0.75 ms in k_intersect -- far more than the
+    // 60 bytes per ray the extra pass moves.  RPX_MESH_FUSED=1 keeps the fused trace-ahead (A/B measurements).
+    static const bool mesh_fused = [] { const char* e = getenv("RPX_MESH_FUSED"); return e && e[0] == '1'; }();
+    const bool unfused = ctx->face_class == RPX_FC_MESH && !mesh_fused;
     // small / medium keep-everything traces: pipelined launches (no per-generation host stall)
-    {
+    if (!unfused) {
         const size_t rec = is_g ? RPX_GAUSSLET_BYTES : RPX_RAY_BYTES;
         const unsigned long long kids = (unsigned long long)(ctx->max_kids > 0 ? ctx->max_kids : 1);
         const bool fits = (double)rays->soa.n * (double)rec * (double)(kids * kids) <= 4.0e9;
@@ -887,11 +894,11 @@ static int trace_loop(rpx_ctx* ctx, rpx_rays* rays, double max_length, int recur
         }
         const uint32_t n_tiles = (uint32_t)((n + RPX_TILE - 1) / RPX_TILE);   // CTA tiles of k_intersect
         const uint32_t n_wtiles = n_tiles;
-        // ---- nearest hit: generation 0 only (k_shade traces its children ahead)
-        if (count == 0) {
+        // ---- nearest hit: generation 0 only (k_shade traces its children ahead), every generation when unfused
+        if (count == 0 || unfused) {
             cudaEvent_t a0 = next_event(ctx), a1 = next_event(ctx);
             CUR(cudaEventRecord(a0, st));
-            CUR(launch_intersect(ctx->face_class, st, n_tiles, smem, ctx->ds, cur->soa, ml, sequential ? face_seq[0] : -1));
+            CUR(launch_intersect(ctx->face_class, st, n_tiles, smem, ctx->ds, cur->soa, ml, sequential ? face_seq[count] : -1));
             CUR(cudaEventRecord(a1, st));
             ev_i0.push_back(a0);
             ev_i1.push_back(a1);
@@ -930,10 +937,10 @@ static int trace_loop(rpx_ctx* ctx, rpx_rays* rays, double max_length, int recur
             sa.face_counts = ctx->d_face_counts;
             sa.n_tiles = n_wtiles;
             sa.smem_bytes = smem;
-            sa.ahead_face = !sequential ? -1 : (count + 1 < n_seq ? face_seq[count + 1] : -2);
+            sa.ahead_face = unfused ? -2 : !sequential ? -1 : (count + 1 < n_seq ? face_seq[count + 1] : -2);
             sa.n_dev = nullptr;
             sa.h_count = nullptr;
-            if (!sequential && count + 1 < RPX_MAX_PIPE_GENS) {  // (a sequence's last step leaves its children untraced)
+            if (!sequential && !unfused && count + 1 < RPX_MAX_PIPE_GENS) {  // (a sequence's last step leaves its children untraced)
                 sa.hits_in = count >= 1 ? ctx->pipe_hits + count : nullptr;
                 sa.hits_out = ctx->pipe_hits + (count + 1);
                 sa.miss_in = count >= 1 ? ctx->pipe_miss + count : nullptr;

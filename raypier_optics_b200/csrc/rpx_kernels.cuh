@@ -209,8 +209,13 @@ __device__ __forceinline__ void nearest_hit(
 // creates them (the thread that just built a child still has it in registers).
 // Simple face classes fit 80 registers (6 CTAs / SM: 0.047 -> 0.045 ms per 1e6 rays, prisms 0.084 -> 0.078);
 // the Newton / quadric code of the full class keeps 128.
+// Mesh class: the BVH walk is bound by the latency of its dependent node loads (ncu: issue slots 35 % used, fp64
+// pipe 2 %), so resident warps count more than spill-free Newton code: RPX_MESH_IBLOCKS CTAs / SM.
+#ifndef RPX_MESH_IBLOCKS
+#define RPX_MESH_IBLOCKS 6  /* measured: 4 -> 8.7e8, 6 -> 9.5e8, 8 -> 8.6e8 seg/s on the 71k-facet scene */
+#endif
 template <int FC, bool SS>
-__global__ void __launch_bounds__(RPX_TILE, (FC == RPX_FC_SIMPLE ? 6 : 4) * 128 / RPX_TILE)
+__global__ void __launch_bounds__(RPX_TILE, (FC == RPX_FC_SIMPLE ? 6 : FC == RPX_FC_MESH ? RPX_MESH_IBLOCKS : 4) * 128 / RPX_TILE)
 k_intersect(DevScene S, Soa rays, double max_length, int only_face) {
     extern __shared__ __align__(16) unsigned char smem[];
     stage_scene<SS>(S, smem);
