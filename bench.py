@@ -747,8 +747,13 @@ def run_consume(args):
 
     # ---------------- end-to-end arm: source in pinned HOST memory, every chunk crosses PCIe
     avail = _mem_available_bytes()
-    budget = args.host_source_gb * (1 << 30) if args.host_source_gb else 0.45 * avail / max(local_world, 1)
+    # default: at most 32 GB of page-locked source per rank (8 ranks page-locking 83.5 GB each would spend minutes
+    # of set-up in the kernel's page pinning); a smaller host source is streamed in several passes per step --
+    # the bytes crossing PCIe per step are the same, `host_source_rays` / `passes_per_step` say what was done
+    budget = args.host_source_gb * (1 << 30) if args.host_source_gb else min(0.45 * avail / max(local_world, 1), 32 << 30)
     n_host = int(max(min(n, budget // rec), min(n, chunk)))
+    if chunk <= n_host < n:
+        n_host = n_host // chunk * chunk  # whole chunks per pass
     pinned = None
     while pinned is None:
         try:
@@ -842,12 +847,16 @@ def run_consume(args):
         traced, _ = T.trace_rays(rc_, cfg["face_lists"], recursion_limit=rl, max_length=ml, device=local_rank)
         return sum(len(t_) for t_ in traced)
 
-    step_dropin()
     t0 = time.perf_counter()
-    drop_segs = step_dropin()
+    step_dropin()  # first call of the process: page-locks the result blocks (raypier_optics_b200/_hostpool.py)
+    first_s = time.perf_counter() - t0
+    t0 = time.perf_counter()
+    drop_segs = step_dropin() + step_dropin()
+    from raypier_optics_b200._hostpool import get_pool
     dropin = {"value": drop_segs / (time.perf_counter() - t0), "unit": "ray-segments/s (this rank)", "rays": n_drop,
+              "first_call_value": drop_segs / 2 / first_s, "result_pool": get_pool(None).stats(),
               "api": "raypier_optics_b200.core.tracer.trace_rays (collections in, list of collections out; every "
-                     "generation crosses PCIe through pageable memory)"}
+                     "generation crosses PCIe into pooled page-locked result arrays, the source through pageable memory)"}
 
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
@@ -1027,7 +1036,7 @@ def main():
                     help="source rays of the timed trace_rays drop-in call (consume-mode workloads)")
     ap.add_argument("--detector-grid", type=int, default=16, help="side of the detector grid of the consume-mode e2e arm")
     ap.add_argument("--host-source-gb", type=float, default=0.0,
-                    help="cap of the pinned host source of the consume-mode e2e arm (0: 45%% of MemAvailable per local rank)")
+                    help="cap of the pinned host source of the consume-mode e2e arm (0: min(32 GB, 45%% of MemAvailable per local rank))")
     ap.add_argument("--ref-rays-per-core", type=int, default=200000)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--capture", action="store_true",

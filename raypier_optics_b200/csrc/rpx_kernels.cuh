@@ -711,6 +711,16 @@ RPX_DEV void stage_child(double* cs, uint32_t* cu, uint32_t slot, const Kids& k,
 #ifndef RPX_TICKET_END_G
 #define RPX_TICKET_END_G 1
 #endif
+// One-shot parent reads through L2 only (ld.global.cg): the 22 / 82 rows of a tile are used once, while the kernel's
+// spill slots (150 - 900 B / thread) want to stay in what is left of the L1 beside the shared-memory carve-out.
+#ifndef RPX_LDCG
+#define RPX_LDCG 0
+#endif
+#if RPX_LDCG
+#define RPX_LD(p) __ldcg(p)
+#else
+#define RPX_LD(p) (*(p))
+#endif
 template <bool GAUSS, int FC, uint32_t MM, bool SS>
 __global__ void __launch_bounds__(RPX_TILE, GAUSS ? RPX_MIN_BLOCKS_G : RPX_MIN_BLOCKS)
 k_shade(DevScene S, Soa in, Soa out, double max_length, unsigned long long* tile_state,
@@ -826,22 +836,24 @@ k_shade(DevScene S, Soa in, Soa out, double max_length, unsigned long long* tile
     // B200s: +3.5 / +4.5 / +6.3 % on the Michelson gausslets (profiles/r02_notes.md section 8).
     constexpr int kParaFirst = GAUSS ? RPX_PARA_FIRST : 0;
     auto load_r = [&]() {
-        r.o = v3(in.f[F_OX * cap + i], in.f[F_OY * cap + i], in.f[F_OZ * cap + i]);
-        r.d = v3(in.f[F_DX * cap + i], in.f[F_DY * cap + i], in.f[F_DZ * cap + i]);
-        r.e = v3(in.f[F_EX * cap + i], in.f[F_EY * cap + i], in.f[F_EZ * cap + i]);
-        r.n = cx(in.f[F_NR * cap + i], in.f[F_NI * cap + i]);
-        r.e1 = cx(in.f[F_E1R * cap + i], in.f[F_E1I * cap + i]);
-        r.e2 = cx(in.f[F_E2R * cap + i], in.f[F_E2I * cap + i]);
-        r.len = in.f[F_LEN * cap + i];
-        r.phase = in.f[F_PHASE * cap + i];
-        r.apath = in.f[F_APATH * cap + i];
-        r.wl = wl = in.u[U_WL * cap + i];
-        r.ident = ident = in.u[U_IDENT * cap + i];
-        r.type = in.u[U_TYPE * cap + i];
+        const double* fi = in.f + i;
+        const uint32_t* ui = in.u + i;
+        r.o = v3(RPX_LD(fi + F_OX * cap), RPX_LD(fi + F_OY * cap), RPX_LD(fi + F_OZ * cap));
+        r.d = v3(RPX_LD(fi + F_DX * cap), RPX_LD(fi + F_DY * cap), RPX_LD(fi + F_DZ * cap));
+        r.e = v3(RPX_LD(fi + F_EX * cap), RPX_LD(fi + F_EY * cap), RPX_LD(fi + F_EZ * cap));
+        r.n = cx(RPX_LD(fi + F_NR * cap), RPX_LD(fi + F_NI * cap));
+        r.e1 = cx(RPX_LD(fi + F_E1R * cap), RPX_LD(fi + F_E1I * cap));
+        r.e2 = cx(RPX_LD(fi + F_E2R * cap), RPX_LD(fi + F_E2I * cap));
+        r.len = RPX_LD(fi + F_LEN * cap);
+        r.phase = RPX_LD(fi + F_PHASE * cap);
+        r.apath = RPX_LD(fi + F_APATH * cap);
+        r.wl = wl = RPX_LD(ui + U_WL * cap);
+        r.ident = ident = RPX_LD(ui + U_IDENT * cap);
+        r.type = RPX_LD(ui + U_TYPE * cap);
     };
     if (have) {
         // every load is issued before the first use: one DRAM round trip per tile, not two
-        face_idx = in.u[U_ENDFACE * cap + i];
+        face_idx = RPX_LD(in.u + U_ENDFACE * cap + i);
         load_r();
         hit = (face_idx != RPX_NO_FACE);
     }
@@ -863,8 +875,8 @@ k_shade(DevScene S, Soa in, Soa out, double max_length, unsigned long long* tile
                 plen[j] = max_length;
                 if (ok) {
                     const double* pp = in.p + (unsigned long long)(j * NPF) * cap + i;
-                    vec3 po = v3(pp[(P_OX + 0) * cap], pp[(P_OX + 1) * cap], pp[(P_OX + 2) * cap]);
-                    vec3 pd = v3(pp[(P_DX + 0) * cap], pp[(P_DX + 1) * cap], pp[(P_DX + 2) * cap]);
+                    vec3 po = v3(RPX_LD(pp + (P_OX + 0) * cap), RPX_LD(pp + (P_OX + 1) * cap), RPX_LD(pp + (P_OX + 2) * cap));
+                    vec3 pd = v3(RPX_LD(pp + (P_DX + 0) * cap), RPX_LD(pp + (P_DX + 1) * cap), RPX_LD(pp + (P_DX + 2) * cap));
                     vec3 ray_end = po + pd * max_length;
                     vec3 p1 = transform_pt(fs->inv_trans.m, po);
                     vec3 p2 = transform_pt(fs->inv_trans.m, ray_end);
@@ -1125,8 +1137,8 @@ k_shade(DevScene S, Soa in, Soa out, double max_length, unsigned long long* tile
 #pragma unroll
         for (int j = 0; j < RPX_NPARA; j++) {
             const double* pp = in.p + (unsigned long long)(j * NPF) * cap + i;
-            vec3 po = v3(pp[(P_OX + 0) * cap], pp[(P_OX + 1) * cap], pp[(P_OX + 2) * cap]);
-            vec3 pd = v3(pp[(P_DX + 0) * cap], pp[(P_DX + 1) * cap], pp[(P_DX + 2) * cap]);
+            vec3 po = v3(RPX_LD(pp + (P_OX + 0) * cap), RPX_LD(pp + (P_OX + 1) * cap), RPX_LD(pp + (P_OX + 2) * cap));
+            vec3 pd = v3(RPX_LD(pp + (P_DX + 0) * cap), RPX_LD(pp + (P_DX + 1) * cap), RPX_LD(pp + (P_DX + 2) * cap));
             vec3 ppoint = po + pd * plen[j];
             vec3 pn, pt;
             compute_orientation<FC>(S, face, ppoint, &pn, &pt, FC == RPX_FC_MESH ? &paux[j] : nullptr);

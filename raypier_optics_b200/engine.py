@@ -5,6 +5,7 @@ import numpy as np
 
 from . import _abi as A
 from ._lib import RpxError, load
+from ._hostpool import get_pool
 
 
 class TraceResult(object):
@@ -44,7 +45,7 @@ class TraceResult(object):
         dtype = A.gausslet_dtype if self.is_gausslet else A.ray_dtype
         n = self.counts[g]
         if out is None:
-            out = np.empty(n, dtype=dtype)
+            out = self._e.result_empty(n, dtype)  # pooled page-locked block (see _hostpool.py)
         assert out.dtype == dtype and out.shape[0] >= n and out.flags.c_contiguous
         self._e._check(self._e._L.rpx_result_generation(self._e._ctx, self._h, g, out.ctypes.data,
                                                          out.shape[0]))
@@ -474,6 +475,11 @@ class Engine(object):
         self._check(self._L.rpx_rays_clone(self._ctx, dev_rays._h, C.byref(h)))
         return DeviceRays(self, h, dev_rays.is_gausslet)
 
+    def result_empty(self, n, dtype):
+        """Array for a result the caller keeps (a generation, a captured collection): a pooled page-locked
+        block when the result is large -- no first-touch page faults, D2H at PCIe speed -- else numpy.empty."""
+        return get_pool(self._L).empty(n, dtype)
+
     def pinned_empty(self, n, dtype):
         """numpy array over page-locked host memory (rpx_host_alloc)."""
         dtype = np.dtype(dtype)
@@ -491,7 +497,7 @@ class Engine(object):
         n = len(dev_rays)
         dtype = A.gausslet_dtype if dev_rays.is_gausslet else A.ray_dtype
         if out is None:
-            out = np.empty(n, dtype=dtype)
+            out = self.result_empty(n, dtype)
         assert out.dtype == dtype and out.shape[0] >= n and out.flags.c_contiguous
         self._check(self._L.rpx_rays_download(self._ctx, dev_rays._h, out.ctypes.data, out.shape[0]))
         return out[:n]

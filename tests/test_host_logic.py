@@ -1,5 +1,6 @@
 """Host-side logic that needs no GPU: Zernike tape construction, scene validation errors,
 collection containers, sharding arithmetic."""
+import os
 import numpy as np
 import pytest
 
@@ -254,3 +255,91 @@ def test_wrap_generations_mutates_genuine_reference_collections_in_place(refcore
         assert rc.copy_as_array().tobytes() == g0.tobytes()
         assert type(out[1]) is cls and out[1].parent is rc and len(out[1]) == 100
         assert np.array_equal(out[1].wavelengths, cfg['wavelengths'])
+
+
+class _FakeHostLib(object):
+    """malloc / free behind the names of the page-locked allocator (no CUDA on the CPU suite)."""
+
+    def __init__(self, refuse_above=None):
+        import ctypes as C
+        self._libc = C.CDLL(None)
+        self._libc.malloc.restype = C.c_void_p
+        self._libc.malloc.argtypes = [C.c_size_t]
+        self._libc.free.argtypes = [C.c_void_p]
+        self.live = {}
+        self.refuse_above = refuse_above
+
+    def rpx_host_alloc(self, nbytes):
+        if self.refuse_above is not None and nbytes > self.refuse_above:
+            return None
+        p = self._libc.malloc(nbytes)
+        self.live[p] = nbytes
+        return p
+
+    def rpx_host_free(self, p):
+        del self.live[p]
+        self._libc.free(p)
+
+
+def test_host_pool_recycles_blocks_when_the_last_view_dies():
+    import gc
+    from raypier_optics_b200 import _abi as A
+    from raypier_optics_b200._hostpool import HostPool, MIN_BYTES
+    lib = _FakeHostLib()
+    pool = HostPool(lib)
+    pool.idle_cap, pool.max_bytes = 64 << 20, 256 << 20
+    n = 20000  # 13 MB of gausslets
+    a = pool.empty(n, A.gausslet_dtype)
+    assert a.shape == (n,) and a.dtype == A.gausslet_dtype and a.flags.writeable and a.flags.c_contiguous
+    a['base_ray']['length'] = 3.0
+    view = a[5:10]
+    ptr = a.ctypes.data
+    assert ptr in lib.live and pool.stats()["out_bytes"] >= a.nbytes
+    del a
+    gc.collect()
+    assert pool.stats()["idle_bytes"] == 0  # a view is still alive
+    assert float(view['base_ray']['length'][0]) == 3.0
+    del view
+    gc.collect()
+    st = pool.stats()
+    assert st["out_bytes"] == 0 and st["idle_bytes"] >= n * 668
+    b = pool.empty(n - 7, A.gausslet_dtype)  # nearly the same size: the idle block is reused
+    assert b.ctypes.data == ptr and pool.stats()["hits"] == 1
+    small = pool.empty(10, A.ray_dtype)      # small results stay plain numpy
+    assert small.nbytes < MIN_BYTES and small.ctypes.data not in lib.live
+    del b
+    gc.collect()
+    pool.trim()
+    assert not lib.live and pool.stats()["idle_bytes"] == 0
+
+
+def test_host_pool_falls_back_to_numpy_when_page_locking_is_refused_or_capped():
+    import gc
+    from raypier_optics_b200 import _abi as A
+    from raypier_optics_b200._hostpool import HostPool
+    lib = _FakeHostLib(refuse_above=0)
+    pool = HostPool(lib)
+    a = pool.empty(100000, A.ray_dtype)
+    assert a.shape == (100000,) and not lib.live and pool.stats()["fallbacks"] == 1 and pool.stats()["out_bytes"] == 0
+    lib2 = _FakeHostLib()
+    pool2 = HostPool(lib2)
+    pool2.idle_cap, pool2.max_bytes = 64 << 20, 40 << 20
+    x = pool2.empty(100000, A.ray_dtype)   # 18.8 MB page-locked
+    y = pool2.empty(100000, A.ray_dtype)   # would exceed the 40 MB cap together with its size-class slack? no: fits
+    z = pool2.empty(100000, A.ray_dtype)   # this one does not
+    assert len(lib2.live) == 2 and pool2.stats()["fallbacks"] == 1
+    del x, y, z
+    gc.collect()
+    # over the cap with only IDLE blocks in the way: they are given back to make room
+    w = pool2.empty(200000, A.ray_dtype)   # 37.6 MB
+    assert w.ctypes.data in lib2.live and len(lib2.live) == 1
+    del w
+    gc.collect()
+    pool2.trim()
+    assert not lib2.live
+    os.environ["RPX_PINNED_RESULTS"] = "0"
+    try:
+        pool3 = HostPool(_FakeHostLib())
+        assert pool3.empty(100000, A.ray_dtype).shape == (100000,) and pool3.stats()["misses"] == 0
+    finally:
+        del os.environ["RPX_PINNED_RESULTS"]
