@@ -841,10 +841,12 @@ def run_consume(args):
     n_drop = int(min(args.dropin_rays, block_n))
     cls = core.ctracer.GaussletCollection if is_g else core.ctracer.RayCollection
 
+    rc_ = cls.from_array(block[:n_drop])  # the caller's source collection, re-traced like a model does on every change
+    rc_.wavelengths = cfg["wavelengths"]
+
     def step_dropin():
-        rc_ = cls.from_array(block[:n_drop])
-        rc_.wavelengths = cfg["wavelengths"]
         traced, _ = T.trace_rays(rc_, cfg["face_lists"], recursion_limit=rl, max_length=ml, device=local_rank)
+        assert traced[0] is rc_
         return sum(len(t_) for t_ in traced)
 
     t0 = time.perf_counter()

@@ -32,6 +32,15 @@ def _prepare_faces(input_rays, face_lists, max_length):
     return wavelengths, face_lists, all_faces
 
 
+def _records_of(input_rays):
+    """The packed records of a collection, read-only for the upload.  Host mirrors lend their array (after a
+    first trace that is the page-locked block generation 0 came back in, so the next upload of the same
+    collection runs at PCIe speed); genuine ``raypier.core`` collections only offer ``copy_as_array``."""
+    if hasattr(input_rays, "_assign_array"):
+        return input_rays._data
+    return input_rays.copy_as_array()
+
+
 def _assign_in_place(input_rays, arr, ref_array):
     """Overwrite the records of ``input_rays`` with ``arr`` WITHOUT replacing the object: the
     reference mutates its parent collection in place (``length`` / ``end_face_idx`` write-back,
@@ -162,7 +171,7 @@ def trace_rays(input_rays, face_lists, recursion_limit=100, max_length=100.0, de
     eng = get_engine(device)
     scene = Scene(face_lists, wavelengths)
     eng.set_scene(scene)
-    rays = input_rays.copy_as_array()
+    rays = _records_of(input_rays)
     native = np.ascontiguousarray(rays).view(
         A.gausslet_dtype if rays.dtype.itemsize == A.gausslet_dtype.itemsize else A.ray_dtype)
     if native.dtype == A.gausslet_dtype and any(f.material.is_decomp_material() for f in all_faces):
@@ -213,7 +222,7 @@ def trace_ray_sequence(input_rays, face_sequence, recursion_limit=100, max_lengt
     eng = get_engine(device)
     scene = Scene(face_lists, wavelengths)
     eng.set_scene(scene)
-    rays = input_rays.copy_as_array()
+    rays = _records_of(input_rays)
     native = np.ascontiguousarray(rays).view(
         A.gausslet_dtype if rays.dtype.itemsize == A.gausslet_dtype.itemsize else A.ray_dtype)
     res = eng.trace_sequence(native, seq, max_length, recursion_limit)

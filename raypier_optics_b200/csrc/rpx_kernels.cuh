@@ -711,6 +711,18 @@ RPX_DEV void stage_child(double* cs, uint32_t* cu, uint32_t slot, const Kids& k,
 #ifndef RPX_TICKET_END_G
 #define RPX_TICKET_END_G 1
 #endif
+// Gausslets: unroll factor of the two six-ray parabasal loops.  Fully unrolled (6) they were 110 KB of the kernel's
+// 205 KB of SASS (six inlined copies of the face intersection, twelve of the parabasal material code); instructions
+// beyond the 32 KB L1.5 stream from L2, and with the 16 warps of an SM each in another phase of its tile ncu showed
+// 1.5 - 10 % of the stall samples as "no instruction" -- how many depended on the code LAYOUT: two changes that
+// removed work from the second loop made the kernel 16 % slower.  Rolled, the loop bodies are re-used from the
+// instruction cache.  Measured on B200 (Michelson, 1e6 gausslets, profiles/r02_notes.md section 9):
+// unroll 6: 2.616e9 seg/s, 1: 2.648e9, 2: 2.770e9 (shipped), 3: 2.729e9; software-pipelining the loads of ray j + 1
+// on top: +1.4 % at unroll 1, -4 % at unroll 2 (registers).
+#ifndef RPX_PARA_UNROLL
+#define RPX_PARA_UNROLL 2
+#endif
+static constexpr int kParaUnroll = RPX_PARA_UNROLL;
 // One-shot parent reads through L2 only (ld.global.cg): the 22 / 82 rows of a tile are used once, while the kernel's
 // spill slots (150 - 900 B / thread) want to stay in what is left of the L1 beside the shared-memory carve-out.
 #ifndef RPX_LDCG
@@ -868,9 +880,10 @@ k_shade(DevScene S, Soa in, Soa out, double max_length, unsigned long long* tile
         // (is_base_ray = 0); any miss drops the children (Q16).  A local function so that it can run before
         // (RPX_PARA_FIRST) or after the material.
         auto para_hits = [&]() -> bool {
+
             bool ok = true;
             const rpx_face_set* fs = &S.sets[face->face_set];
-#pragma unroll
+#pragma unroll kParaUnroll
             for (int j = 0; j < RPX_NPARA; j++) {
                 plen[j] = max_length;
                 if (ok) {
@@ -1134,7 +1147,8 @@ k_shade(DevScene S, Soa in, Soa out, double max_length, unsigned long long* tile
         const rpx_material* M = &S.mats[face->material];
         const unsigned long long ocap = out.cap;
         const unsigned long long pos_a = base + slot_a, pos_b = base + slot_b;
-#pragma unroll
+        const ParaSnell ps = para_snell_setup(S, M, wl);
+#pragma unroll kParaUnroll
         for (int j = 0; j < RPX_NPARA; j++) {
             const double* pp = in.p + (unsigned long long)(j * NPF) * cap + i;
             vec3 po = v3(RPX_LD(pp + (P_OX + 0) * cap), RPX_LD(pp + (P_OX + 1) * cap), RPX_LD(pp + (P_OX + 2) * cap));
@@ -1144,7 +1158,7 @@ k_shade(DevScene S, Soa in, Soa out, double max_length, unsigned long long* tile
             compute_orientation<FC>(S, face, ppoint, &pn, &pt, FC == RPX_FC_MESH ? &paux[j] : nullptr);
             vec3 nn = norm(pn);
             if (k.has_a) {
-                vec3 dir = material_eval_para(S, M, wl, k.a.n.re, pd, ppoint, pn, pt, k.a.type);
+                vec3 dir = material_eval_para(S, M, wl, k.a.n.re, pd, ppoint, pn, pt, k.a.type, ps);
                 double* q = out.p + (unsigned long long)(j * NPF) * ocap + pos_a;
                 q[0 * ocap] = ppoint.x; q[1 * ocap] = ppoint.y; q[2 * ocap] = ppoint.z;
                 q[3 * ocap] = dir.x; q[4 * ocap] = dir.y; q[5 * ocap] = dir.z;
@@ -1152,7 +1166,7 @@ k_shade(DevScene S, Soa in, Soa out, double max_length, unsigned long long* tile
                 q[9 * ocap] = max_length;
             }
             if (k.has_b) {
-                vec3 dir = material_eval_para(S, M, wl, k.b.n.re, pd, ppoint, pn, pt, k.b.type);
+                vec3 dir = material_eval_para(S, M, wl, k.b.n.re, pd, ppoint, pn, pt, k.b.type, ps);
                 double* q = out.p + (unsigned long long)(j * NPF) * ocap + pos_b;
                 q[0 * ocap] = ppoint.x; q[1 * ocap] = ppoint.y; q[2 * ocap] = ppoint.z;
                 q[3 * ocap] = dir.x; q[4 * ocap] = dir.y; q[5 * ocap] = dir.z;

@@ -451,28 +451,39 @@ RPX_MAT_ATTR void material_eval(const DevScene& S, const rpx_material* M, const 
 
 // InterfaceMaterial.eval_parabasal_ray_c -> outgoing parabasal direction.
 // (origin = point, normal = norm(orient.normal), length = INF are set by the caller.)
+// What the Snell model needs of the material per (thread, wavelength): the two index ratios n1 / n2 it can form.
+// The twelve calls of one gausslet (six parabasal rays x two children) share them, so the caller reads the two
+// table entries (global memory) and does the two IEEE divisions ONCE instead of twelve times each -- the loads sat
+// between the parabasal stores, where ptxas cannot hoist them itself (ncu: 8.7 % of the stall samples of a
+// two-children generation waited on them).  Same operands, same IEEE division: bit-identical directions.
+struct ParaSnell {
+    double ratio_neg;  // cosTheta <  0: n1 = row 1, n2 = row 0
+    double ratio_pos;  // cosTheta >= 0: n1 = row 0, n2 = row 1
+};
+RPX_DEV ParaSnell para_snell_setup(const DevScene& S, const rpx_material* M, uint32_t wl) {
+    ParaSnell ps;
+    ps.ratio_neg = ps.ratio_pos = 0.0;
+    if (M->para_model == RPX_PARA_SNELL) {
+        const double a = ntab_get(S, M, 0, wl).re, b = ntab_get(S, M, 1, wl).re;
+        ps.ratio_neg = b / a;
+        ps.ratio_pos = a / b;
+    }
+    return ps;
+}
+
 RPX_DEV vec3 material_eval_para(const DevScene& S, const rpx_material* M, uint32_t wl, double base_n_re,
                                 vec3 direction, vec3 point, vec3 onormal, vec3 otangent,
-                                uint32_t ray_type_id) {
+                                uint32_t ray_type_id, const ParaSnell& ps) {
     vec3 normal = norm(onormal);
     if (M->para_model == RPX_PARA_SNELL) {  // cmaterials.pyx:683-724, 1393-1434
         direction = norm(direction);
         double cosTheta = dot(normal, direction);
         vec3 cosThetaNormal = normal * cosTheta;
-        double n1, n2;
-        int flip;
-        if (cosTheta < 0.0) {
-            n1 = ntab_get(S, M, 1, wl).re;
-            n2 = ntab_get(S, M, 0, wl).re;
-            flip = 1;
-        } else {
-            n1 = ntab_get(S, M, 0, wl).re;
-            n2 = ntab_get(S, M, 1, wl).re;
-            flip = -1;
-        }
+        const double n1_over_n2 = (cosTheta < 0.0) ? ps.ratio_neg : ps.ratio_pos;
+        const int flip = (cosTheta < 0.0) ? 1 : -1;
         if (ray_type_id & RPX_REFL_RAY) return direction - cosThetaNormal * 2.0;
         vec3 tangent = direction - cosThetaNormal;
-        vec3 tg2 = tangent * (n1 / n2);
+        vec3 tg2 = tangent * n1_over_n2;
         double tan_mag_sq = mag_sq(tg2);
         double c2 = sqrt_(1 - tan_mag_sq);
         return tg2 - normal * (c2 * flip);
