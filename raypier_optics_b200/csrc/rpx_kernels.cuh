@@ -717,12 +717,18 @@ RPX_DEV void stage_child(double* cs, uint32_t* cu, uint32_t slot, const Kids& k,
 // 1.5 - 10 % of the stall samples as "no instruction" -- how many depended on the code LAYOUT: two changes that
 // removed work from the second loop made the kernel 16 % slower.  Rolled, the loop bodies are re-used from the
 // instruction cache.  Measured on B200 (Michelson, 1e6 gausslets, profiles/r02_notes.md section 9):
-// unroll 6: 2.616e9 seg/s, 1: 2.648e9, 2: 2.770e9 (shipped), 3: 2.729e9; software-pipelining the loads of ray j + 1
+// unroll 6: 2.616e9 seg/s, 1: 2.648e9, 2: 2.770e9, 3: 2.729e9 (both loops alike); software-pipelining the loads of ray j + 1
 // on top: +1.4 % at unroll 1, -4 % at unroll 2 (registers).
+// Chosen per loop (first = intersections, second = parabasal children), same workload: 1/2: 2.681e9, 2/1: 2.740e9,
+// 2/2: 2.773e9, 2/3: 2.696e9, **3/2: 2.800e9 (shipped)**.
 #ifndef RPX_PARA_UNROLL
-#define RPX_PARA_UNROLL 2
+#define RPX_PARA_UNROLL 3
 #endif
-static constexpr int kParaUnroll = RPX_PARA_UNROLL;
+#ifndef RPX_PARA_UNROLL2
+#define RPX_PARA_UNROLL2 2
+#endif
+static constexpr int kParaUnroll = RPX_PARA_UNROLL;    // first loop (intersections)
+static constexpr int kParaUnroll2 = RPX_PARA_UNROLL2;  // second loop (parabasal children)
 // One-shot parent reads through L2 only (ld.global.cg): the 22 / 82 rows of a tile are used once, while the kernel's
 // spill slots (150 - 900 B / thread) want to stay in what is left of the L1 beside the shared-memory carve-out.
 #ifndef RPX_LDCG
@@ -1148,7 +1154,7 @@ k_shade(DevScene S, Soa in, Soa out, double max_length, unsigned long long* tile
         const unsigned long long ocap = out.cap;
         const unsigned long long pos_a = base + slot_a, pos_b = base + slot_b;
         const ParaSnell ps = para_snell_setup(S, M, wl);
-#pragma unroll kParaUnroll
+#pragma unroll kParaUnroll2
         for (int j = 0; j < RPX_NPARA; j++) {
             const double* pp = in.p + (unsigned long long)(j * NPF) * cap + i;
             vec3 po = v3(RPX_LD(pp + (P_OX + 0) * cap), RPX_LD(pp + (P_OX + 1) * cap), RPX_LD(pp + (P_OX + 2) * cap));
