@@ -109,10 +109,11 @@ def main():
               "in place rel err %.2e, terminal gather %.1f MB in %.2f ms = %.1f GB/s into every rank -> %s"
               % (int(tt[0]), int(tt[1]), int(tt[2]), counts, err2, n_term_all * 668 / 1e6, dt * 1e3,
                  n_term_all * 668 / dt / 1e9, "OK" if ok2 else "FAIL"))
-    # ---- the same gather at a size where the transfer dominates: 5e5 gausslets per rank -> 1e6 terminal rays each
+    # ---- the same gather at a size where the transfer dominates: 5e5 gausslets per rank -> 2e6 terminal rays each
+    # (four per source gausslet: both output ports of both arms)
     big = configs.build(core, "config5", n=500000, gausslets=True, seed=11 + rank)
     outb = eng.trace_consume(np.ascontiguousarray(big["rays"]), big["max_length"], big["recursion_limit"], terminal=True,
-                             terminal_capacity=2 * len(big["rays"]) + 64)
+                             terminal_capacity=4 * len(big["rays"]) + 64)
     torch.cuda.synchronize()
     dist.barrier()
     t0 = time.perf_counter()
@@ -123,7 +124,7 @@ def main():
     allb.free()
     outb.free()
     if rank == 0:
-        okb = nb == sum(countsb) == world * 2 * len(big["rays"])
+        okb = nb == sum(countsb) == world * 4 * len(big["rays"])
         ok = ok and okb
         print("multi_gpu_check: terminal gather of %d gausslets (%.0f MB into every rank, %d ranks) in %.1f ms = %.1f GB/s "
               "received per rank (export + NCCL all-gather + import) -> %s"
