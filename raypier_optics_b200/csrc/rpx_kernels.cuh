@@ -569,14 +569,17 @@ k_capture(DevScene S, Soa in, Soa out, unsigned long long* tile_state, uint32_t*
 // (Tried and measured slower, see profiles/r01_notes.md: thread-fixed staging slots with a
 // compaction map; the look-back before the trace-ahead instead of after it.)
 #define RPX_SLOTS (2 * RPX_TILE)
-// RPX_LEAN_STAGE=1 (experiment prepared for the next round, NOT yet measured or parity-tested on a
-// GPU; default 0): the two children of a parent share origin, normal, E_vector, phase, accumulated
-// path, wavelength index and ray ident -- store those ONCE per parent (11 doubles + 2 words x
-// RPX_TILE) and only direction, n, E1, E2, length, type, end face per child (10 doubles + 2 words x
-// RPX_SLOTS), plus a byte map slot -> parent.  35 KB instead of 47 KB per CTA: room for 5 CTAs / SM
-// (at 96 registers, RPX_MIN_BLOCKS=5) where registers and shared memory both capped it at 4.
+// Lean staging (RPX_LEAN_STAGE=1, what ships): the two children of a parent share origin, normal, E_vector, phase,
+// accumulated path, wavelength index and ray ident -- stored ONCE per parent (11 doubles + 2 words x RPX_TILE), only
+// direction, n, E1, E2, length, type, end face per child (10 doubles + 2 words x RPX_SLOTS), plus a byte map
+// slot -> parent.  35 KB instead of 47 KB per CTA: at the same 4 CTAs / SM the shared-memory carve-out drops from 228
+// to 164 KB and the L1 -- where the spill slots live -- triples.  Measured on B200 (profiles/r02_notes.md section 9):
+// +0.9 .. +3.1 % on every plain-ray workload, +4.3 % on gausslets (2.776e9 -> 2.895e9 seg/s) once the parabasal loops
+// were rolled; on the fully unrolled, instruction-cache-bound gausslet kernel the same change had measured -13 %, and
+// at 5 CTAs / SM (96 registers, what round 1 prepared it for) it loses to the spills.  RPX_LEAN_STAGE=0 builds the
+// full staging (every field per child slot).
 #ifndef RPX_LEAN_STAGE
-#define RPX_LEAN_STAGE 0
+#define RPX_LEAN_STAGE 1
 #endif
 #if RPX_LEAN_STAGE
 enum { LP_OX = 0, LP_OY, LP_OZ, LP_NX, LP_NY, LP_NZ, LP_EX, LP_EY, LP_EZ, LP_PHASE, LP_APATH, LP_NF = 11 };
@@ -685,7 +688,7 @@ RPX_DEV void stage_child(double* cs, uint32_t* cu, uint32_t slot, const Kids& k,
 // bulk copies and warp-granular tiles were both tried and were slower -- 22 sub-KB bulk copies
 // per tile serialise in the TMA unit, and 4x more tiles mean 4x more look-backs.
 #ifndef RPX_MIN_BLOCKS
-#define RPX_MIN_BLOCKS 4  // build the lean-staging experiment with -DRPX_LEAN_STAGE=1 -DRPX_MIN_BLOCKS=5
+#define RPX_MIN_BLOCKS 4
 #endif
 #ifndef RPX_BULK_PREFETCH
 #define RPX_BULK_PREFETCH 1

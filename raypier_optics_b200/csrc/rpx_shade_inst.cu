@@ -3,18 +3,6 @@
 // variants build in parallel.
 #include <mutex>
 
-// Plain rays stage their children "lean" (per-parent fields once, per-child fields per slot, see rpx_kernels.cuh):
-// 35 KB instead of 47 KB of staging per CTA leaves the SM a 3x larger L1 at the same 4 CTAs.  Measured on B200
-// (profiles/r02_notes.md section 9): +1.1 .. +3.1 % on every plain-ray workload, -13 % on gausslets, which keep the
-// full staging.
-#if !defined(RPX_LEAN_STAGE) && defined(RPX_I_GAUSS)
-#if RPX_I_GAUSS
-#define RPX_LEAN_STAGE 0
-#else
-#define RPX_LEAN_STAGE 1
-#endif
-#endif
-
 #include "rpx_launch.h"
 
 #if !defined(RPX_I_GAUSS) || !defined(RPX_I_FC) || !defined(RPX_I_MM)
