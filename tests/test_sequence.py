@@ -106,6 +106,40 @@ def test_drop_in_trace_functions(engine, core):
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("gauss", [False, True])
+def test_drop_in_retraces_the_same_collection(engine, core, gauss):
+    """A model re-traces ONE source collection over and over (raypier/tracer.py calls trace_rays on every trait
+    change): trace_rays mutates it in place -- after the first call it holds generation 0 as the device left it
+    (lengths / end_face_idx written back), in a pooled page-locked block that the next call lends straight to the
+    upload.  The second and third trace must reproduce the first byte for byte, results large enough for the
+    pool (> 4 MB per generation) included, and arrays handed out earlier must stay intact while the pool recycles."""
+    from raypier_optics_b200._hostpool import get_pool
+    ct = core.ctracer
+    cfg = configs.build(core, "config5", n=30000, gausslets=gauss)
+    cls = ct.GaussletCollection if gauss else ct.RayCollection
+    rc = cls.from_array(cfg['rays'])
+    rc.wavelengths = cfg['wavelengths']
+    kept = []
+    for rep in range(3):
+        traced, _ = T.trace_rays(rc, cfg['face_lists'], recursion_limit=cfg['recursion_limit'], max_length=cfg['max_length'])
+        assert traced[0] is rc
+        arrays = [t.copy_as_array() for t in traced]
+        if rep == 0:
+            first = arrays
+            kept = traced                      # holds the pooled blocks of the first trace
+            snapshot = [a.copy() for a in arrays]
+        else:
+            assert len(arrays) == len(first)
+            for g, (a, b) in enumerate(zip(arrays, first)):
+                assert a.tobytes() == b.tobytes(), "generation %d differs on re-trace %d" % (g, rep)
+    # the first trace's generations (still referenced) were not overwritten by the later ones
+    for t, snap in zip(kept[1:], snapshot[1:]):
+        assert t.copy_as_array().tobytes() == snap.tobytes()
+    st = get_pool(None).stats()
+    assert st["hits"] + st["misses"] + st["fallbacks"] > 0   # the generations did go through the result pool
+
+
+@pytest.mark.gpu
 @pytest.mark.parametrize("name,kw", [("config2", dict(n=20000)), ("config5", dict(n=3000, gausslets=True)),
                                      ("config4_prisms", dict(n=4000))])
 def test_drop_in_trace_rays_with_genuine_reference_objects(engine, name, kw):
