@@ -145,9 +145,14 @@ _pool = None
 _pool_lock = threading.Lock()
 
 
-def get_pool(lib):
+def get_pool(lib=None):
+    """The process-wide pool (page-locked memory is not tied to a device context).  ``lib``: the loaded librpx
+    (``_lib.load()``); None loads it on first use."""
     global _pool
     with _pool_lock:
         if _pool is None:
+            if lib is None:
+                from ._lib import load
+                lib = load()
             _pool = HostPool(lib)
         return _pool

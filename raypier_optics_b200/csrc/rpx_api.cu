@@ -837,7 +837,7 @@ static int trace_loop(rpx_ctx* ctx, rpx_rays* rays, double max_length, int recur
 
     // Mesh / UV patch scenes run UNFUSED: k_shade leaves its children untraced and k_intersect finds every
     // generation's nearest hits.  The BVH walk lives on L1 hits (upper tree levels, per-thread stacks); inside
-    // k_shade the 47 KB of child staging per CTA leave it ~60 KB of L1 per SM (ncu: 58 % L1 hit rate against 79 % in
+    // k_shade the child staging (47 KB per CTA when this was measured) left it ~60 KB of L1 per SM (ncu: 58 % L1 hit rate against 79 % in
     // k_intersect), and the walk cost 1.21 ms per 1e6 rays there against 0.75 ms in k_intersect -- far more than the
     // 60 bytes per ray the extra pass moves.  RPX_MESH_FUSED=1 keeps the fused trace-ahead (A/B measurements).
     static const bool mesh_fused = [] { const char* e = getenv("RPX_MESH_FUSED"); return e && e[0] == '1'; }();

@@ -33,7 +33,7 @@ static constexpr uint32_t kMask = RPX_MM_ALL;
 #endif
 
 cudaError_t RPX_CAT(RPX_I_GAUSS, RPX_I_FC, RPX_I_MM)(cudaStream_t st, const ShadeArgs& a) {
-    // dynamic shared memory = child staging (47 KB) + the scene copy: needs the > 48 KB opt-in.
+    // dynamic shared memory = child staging (35 KB lean, 47 KB full) + the scene copy: may need the > 48 KB opt-in.
     // Persistent grid: one wave of resident CTAs (SMs x occupancy), never more than the tiles.
     // per-device state (cudaFuncSetAttribute and the occupancy answer are per device; one process may
     // open several GPUs through rpx_init): indexed by the current device, guarded by a mutex
