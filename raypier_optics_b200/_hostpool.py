@@ -60,7 +60,9 @@ class _Block(object):
 class HostPool(object):
     def __init__(self, lib):
         self._L = lib
-        self._lock = threading.Lock()
+        # re-entrant: a garbage-collection pass that starts inside _take (any allocation can trigger one) may finalise a
+        # _Block of an unreachable cycle on the same thread, which calls _release; it only appends to _free
+        self._lock = threading.RLock()
         self._free = []  # (cap, ptr), idle blocks
         self._idle = 0   # bytes in _free
         self._out = 0    # bytes handed out
