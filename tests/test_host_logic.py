@@ -162,8 +162,15 @@ def test_mesh_bvh_covers_every_triangle_once():
     import numpy as np
     from raypier_optics_b200 import configs
     from raypier_optics_b200.core.obbtree import LEAF_CELLS, build_bvh
-    for pts, cells in (configs.icosphere(5.0, 2), configs.bowl_mesh(60.0, 17, 30.0), configs.icosphere(1.0, 0)):
-        order, nodes = build_bvh(pts, cells)
+    import itertools
+    meshes = (configs.icosphere(5.0, 2), configs.bowl_mesh(60.0, 17, 30.0), configs.icosphere(1.0, 0))
+    for (pts, cells), sah in itertools.product(meshes, (False, True)):   # median split / binned surface-area heuristic
+        order, nodes = build_bvh(pts, cells, sah=sah)
+        height = np.ones(len(nodes), dtype=int)
+        for k in range(len(nodes) - 1, -1, -1):
+            if nodes[k, 6] >= 0:
+                height[k] = 1 + max(height[int(nodes[k, 6])], height[int(nodes[k, 7])])
+        assert height[0] <= 46                                             # what the packed device nodes hold
         assert sorted(order.tolist()) == list(range(len(cells)))
         cover = np.zeros(len(cells), dtype=int)
 
