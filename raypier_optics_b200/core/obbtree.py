@@ -4,8 +4,8 @@
 triangles, obbtree.pyx:204-223) and ``OBBTreeFace(tree=..., material=...)`` is the Face traced through it
 (obbtree.pyx:880-946).  In the reference the oriented-bounding-box tree is an acceleration structure for
 ``intersect_with_line_c`` (:367-400): its node test only prunes, the result is the nearest triangle with
-``tolerance / |p2 - p1| <= alpha < 1``.  The device path carries its own BVH (axis-aligned boxes, median
-split, built in :func:`build_bvh` when the scene is flattened), so ``build_tree`` here has nothing to
+``tolerance / |p2 - p1| <= alpha < 1``.  The device path carries its own BVH (axis-aligned boxes, binned
+surface-area-heuristic splits, built in :func:`build_bvh` when the scene is flattened), so ``build_tree`` here has nothing to
 compute; ``max_level`` / ``number_of_cells_per_node`` are kept for interface compatibility.
 """
 import os
@@ -40,7 +40,7 @@ class OBBTree(object):
 
     def build_tree(self):
         """obbtree.pyx:259-269.  The device BVH is built at flattening time; only ``level`` (> 0 = built)
-        is kept, as the depth a median split of this mesh reaches."""
+        is kept, as the depth a balanced split of this mesh reaches."""
         n = max(len(self.cells), 1)
         self.level = max(1, int(np.ceil(np.log2(max(n / float(LEAF_CELLS), 1.0)))) + 1)
 
